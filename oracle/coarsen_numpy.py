@@ -1,0 +1,102 @@
+"""TEST INFRASTRUCTURE ONLY (oracle) -- CPU restatement of the reference's
+coarsening path, open2c/cooler v0.10.4 ``src/cooler/_reduce.py:501-642``
+(``CoolerCoarsener``), in plain numpy.  Only tests/, ``smoke()`` and
+``bench.py``'s CPU legs may import it; the product never does.
+
+Parity status: PINNED against (a) the reference's own golden files
+(tests/data/toy.symm.upper.{2,4}.bg2, toy.asymm.{2,4,8,16,32}.bg2 -- the text
+twins of the .cool goldens compared in tests/test_reduce.py:83-175) and
+(b) golden outputs of the unmodified reference run through oracle/refshim.py on
+GM12878 2 Mb (factors 2, 5, 10), odd.1 (factor 4, tests/test_reduce.py:127-137)
+and a variable-bin table; see tests/golden/make_golden.py.
+
+The reference re-derives bin ids from genomic coordinates (join with the bin
+table, then ``chrom_binoffset[chrom] + floor(start / new_binsize)`` for fixed
+bins, _reduce.py:611-614, or ``searchsorted(start_abspos, abs_start,
+'right') - 1`` for variable bins, _reduce.py:601-609).  This restatement does
+exactly that, coordinate-based, so it is an independent check of the
+closed-form id map the CUDA path uses.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def coarsen_bins(bins_chrom, bins_start, bins_end, chromsizes, factor):
+    """New bin table (_reduce.py:563-580): every ``factor``-th start per
+    chromosome; end = end of the last pooled bin, or the chromosome length."""
+    bins_chrom = np.asarray(bins_chrom)
+    n_chroms = len(chromsizes)
+    out_c, out_s, out_e = [], [], []
+    for c in range(n_chroms):
+        sel = np.flatnonzero(bins_chrom == c)
+        if len(sel) == 0:
+            continue
+        start = np.asarray(bins_start)[sel][::factor]
+        end = np.asarray(bins_end)[sel][factor - 1::factor]
+        if len(end) < len(start):
+            end = np.r_[end, chromsizes[c]]
+        out_c.append(np.full(len(start), c, dtype=np.int32))
+        out_s.append(start)
+        out_e.append(end)
+    return (np.concatenate(out_c), np.concatenate(out_s).astype(np.int64),
+            np.concatenate(out_e).astype(np.int64))
+
+
+def _binsize_of(bins_chrom, bins_start, bins_end):
+    """util.get_binsize (util.py:393-411): uniform width ignoring each
+    chromosome's last bin, else None."""
+    sizes = set()
+    bins_chrom = np.asarray(bins_chrom)
+    width = np.asarray(bins_end) - np.asarray(bins_start)
+    for c in np.unique(bins_chrom):
+        w = width[bins_chrom == c][:-1]
+        sizes.update(np.unique(w).tolist())
+        if len(sizes) > 1:
+            return None
+    return next(iter(sizes)) if len(sizes) == 1 else None
+
+
+def coarsen_pixels(px, bins_chrom, bins_start, bins_end, chromsizes, factor,
+                   count_dtype=None):
+    """Restatement of ``CoolerCoarsener._aggregate`` over the whole table
+    (chunking never changes content: edges respect coarse rows, _reduce.py:550-561).
+
+    Returns (bin1_id int64, bin2_id int64, count, new_bins tuple).
+    """
+    bins_chrom = np.asarray(bins_chrom)
+    bins_start = np.asarray(bins_start, dtype=np.int64)
+    chromsizes = np.asarray(chromsizes, dtype=np.int64)
+    new_c, new_s, new_e = coarsen_bins(bins_chrom, bins_start, bins_end, chromsizes, factor)
+    n_chroms = len(chromsizes)
+    nb_per = np.bincount(new_c, minlength=n_chroms)
+    chrom_binoffset = np.r_[0, np.cumsum(nb_per)]            # util.py:803
+    chrom_abspos = np.r_[0, np.cumsum(chromsizes)]           # util.py:804
+    new_binsize = _binsize_of(new_c, new_s, new_e)
+
+    b1 = np.asarray(px["bin1_id"], dtype=np.int64)
+    b2 = np.asarray(px["bin2_id"], dtype=np.int64)
+    c1, c2 = bins_chrom[b1], bins_chrom[b2]
+    s1, s2 = bins_start[b1], bins_start[b2]
+    if new_binsize is None:                                  # 601-609
+        start_abspos = chrom_abspos[new_c] + new_s
+        n1 = np.searchsorted(start_abspos, chrom_abspos[c1] + s1, side="right") - 1
+        n2 = np.searchsorted(start_abspos, chrom_abspos[c2] + s2, side="right") - 1
+    else:                                                    # 611-614
+        n1 = chrom_binoffset[c1] + np.floor(s1 / new_binsize).astype(int)
+        n2 = chrom_binoffset[c2] + np.floor(s2 / new_binsize).astype(int)
+
+    # groupby([bin1_id, bin2_id], sort=True).sum()  (616-620)
+    cnt = np.asarray(px["count"])
+    order = np.lexsort((n2, n1))
+    n1, n2, cnt = n1[order], n2[order], cnt[order]
+    if len(n1):
+        head = np.r_[True, (n1[1:] != n1[:-1]) | (n2[1:] != n2[:-1])]
+        starts = np.flatnonzero(head)
+        acc = np.add.reduceat(cnt.astype(np.int64 if cnt.dtype.kind in "iu" else np.float64), starts)
+        n1, n2 = n1[starts], n2[starts]
+    else:
+        acc = cnt.astype(np.int64)
+    if count_dtype is None:
+        count_dtype = cnt.dtype
+    return n1.astype(np.int64), n2.astype(np.int64), acc.astype(count_dtype), (new_c, new_s, new_e)

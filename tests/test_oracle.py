@@ -1,0 +1,126 @@
+"""The oracle (oracle/*.py, a CPU restatement of the reference) against the
+golden vectors frozen from the UNMODIFIED reference (tests/golden/make_golden.py).
+Mirrors the reference's tests/test_balance.py and tests/test_reduce.py cases."""
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import coarsen_numpy, ice_numpy
+from tests import _golden
+
+BAL, META = _golden.balance_golden()
+
+
+def _stats_equal(got, want):
+    for k, w in want.items():
+        g = got[k]
+        if isinstance(w, list):
+            g = [None if (isinstance(x, float) and np.isnan(x)) else x for x in np.asarray(g).tolist()]
+            assert g == w, k
+        elif isinstance(g, (float, np.floating)) and np.isnan(g):
+            assert w is None, k
+        else:
+            assert g == w or bool(g) == w, (k, g, w)
+
+
+@pytest.mark.parametrize("key", sorted(META))
+def test_ice_oracle_bit_identical_to_reference(key):
+    src, case = key.split("/")
+    t = _golden.table_of(src)
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    kw = dict(META[key]["kwargs"])
+    if case == "x0":
+        kw["x0"] = BAL["gm/x0_input"].copy()
+    px = {k: t[k] for k in ("bin1_id", "bin2_id", "count")}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bias, stats, passes, warned = ice_numpy.balance_arrays(
+            px, chrom_offset, bin1_offset, return_passes=True, **kw)
+    assert passes == META[key]["passes"]
+    assert warned == META[key]["warned"]
+    np.testing.assert_array_equal(bias, BAL[key])          # bit-identical incl. NaN mask
+    _stats_equal(stats, META[key]["stats"])
+
+
+@pytest.mark.parametrize("chunksize", [None, 5000, 977])
+def test_ice_oracle_chunking_within_1e12(chunksize):
+    t = _golden.gm12878()
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    px = {k: t[k] for k in ("bin1_id", "bin2_id", "count")}
+    bias, stats, passes, _ = ice_numpy.balance_arrays(px, chrom_offset, bin1_offset,
+                                                      chunksize=chunksize, return_passes=True)
+    assert passes == [14]
+    np.testing.assert_allclose(bias, BAL["gm/defaults"], rtol=1e-12, equal_nan=True)
+
+
+def test_reference_property_flat_marginals():
+    """tests/test_balance.py:13-44 -- balanced marginals are flat."""
+    t = _golden.gm12878()
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    px = {k: t[k] for k in ("bin1_id", "bin2_id", "count")}
+    tol = 1e-2
+    bias, stats = ice_numpy.balance_arrays(px, chrom_offset, bin1_offset, ignore_diags=1,
+                                           min_nnz=10, tol=tol)
+    n = len(bias)
+    m = np.zeros((n, n))
+    m[t["bin1_id"], t["bin2_id"]] = t["count"]
+    m = m + np.triu(m, 1).T
+    np.fill_diagonal(m, 0)
+    mask = np.isnan(bias)
+    w = np.where(mask, 0, bias)
+    marg = (m * w[:, None] * w[None, :]).sum(axis=0)[~mask]
+    assert np.var(marg) < tol
+    assert abs(marg.mean() - 1) < 1e-3
+
+
+CO = _golden.coarsen_golden()
+
+
+@pytest.mark.parametrize("factor", [2, 5, 10])
+def test_coarsen_oracle_gm(factor):
+    t = _golden.gm12878()
+    px = {k: t[k] for k in ("bin1_id", "bin2_id", "count")}
+    b1, b2, c, (nc, ns, ne) = coarsen_numpy.coarsen_pixels(
+        px, t["bins_chrom"], t["bins_start"], t["bins_end"], t["chromsizes"], factor)
+    np.testing.assert_array_equal(b1, CO[f"gm/x{factor}/bin1_id"])
+    np.testing.assert_array_equal(b2, CO[f"gm/x{factor}/bin2_id"])
+    np.testing.assert_array_equal(c, CO[f"gm/x{factor}/count"])
+    assert c.dtype == np.int32
+    np.testing.assert_array_equal(ns, CO[f"gm/x{factor}/bins_start"])
+    np.testing.assert_array_equal(ne, CO[f"gm/x{factor}/bins_end"])
+
+
+@pytest.mark.parametrize("fam,r0,r1", [("symm.upper", 2, 4), ("asymm", 2, 4), ("asymm", 4, 8),
+                                       ("asymm", 8, 16), ("asymm", 16, 32), ("asymm", 2, 32)])
+def test_coarsen_oracle_toy_chain(fam, r0, r1):
+    a = CO[f"toy.{fam}/{r0}"]
+    g = CO[f"toy.{fam}/{r1}"]
+    sizes = np.array([32, 32])
+    bc, bs, be = _golden.uniform_bins(sizes, r0)
+    px = dict(bin1_id=a[:, 0], bin2_id=a[:, 1], count=a[:, 2].astype(np.int32))
+    b1, b2, c, _ = coarsen_numpy.coarsen_pixels(px, bc, bs, be, sizes, r1 // r0)
+    np.testing.assert_array_equal(np.stack([b1, b2, c], 1), g)
+
+
+@pytest.mark.parametrize("factor", [4, 3, 7, 200])
+def test_coarsen_oracle_odd(factor):
+    a = CO["odd/1"]
+    sizes = CO["odd/chromsizes"]
+    bc, bs, be = _golden.uniform_bins(sizes, 1)
+    px = dict(bin1_id=a[:, 0], bin2_id=a[:, 1], count=a[:, 2].astype(np.int32))
+    b1, b2, c, (nc, ns, ne) = coarsen_numpy.coarsen_pixels(px, bc, bs, be, sizes, factor)
+    g = CO["odd/4"] if factor == 4 else CO[f"odd/x{factor}"]
+    np.testing.assert_array_equal(np.stack([b1, b2, c], 1), g)
+    # no duplicate pixels (tests/test_reduce.py:134-137)
+    assert len(np.unique(np.stack([b1, b2], 1), axis=0)) == len(b1)
+
+
+@pytest.mark.parametrize("factor", [2, 3])
+def test_coarsen_oracle_variable_bins(factor):
+    bins, a = CO["var/bins"], CO["var/px"]
+    px = dict(bin1_id=a[:, 0], bin2_id=a[:, 1], count=a[:, 2].astype(np.int32))
+    b1, b2, c, (nc, ns, ne) = coarsen_numpy.coarsen_pixels(
+        px, bins[:, 0], bins[:, 1], bins[:, 2], np.array([32, 32]), factor)
+    np.testing.assert_array_equal(np.stack([b1, b2, c], 1), CO[f"var/x{factor}"])
+    np.testing.assert_array_equal(np.stack([nc, ns, ne], 1), CO[f"var/x{factor}/bins"])
