@@ -1,0 +1,103 @@
+"""ctypes binding of the C-ABI library ``libcooler_b200.so`` (include/cooler_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcooler_b200.so")
+
+KEEP_ALL, KEEP_CIS, KEEP_TRANS = 0, 1, 2
+
+
+class Copy(C.Structure):
+    """cb200_copy"""
+    _fields_ = [("px", C.c_void_p), ("indptr", C.c_void_p), ("tile_row", C.c_void_p),
+                ("nnz", C.c_int64)]
+
+
+class Ice(C.Structure):
+    """cb200_ice"""
+    _fields_ = [
+        ("csr", Copy), ("csc", Copy),
+        ("n_bins", C.c_int32), ("n_segs", C.c_int32),
+        ("seg_offset", C.c_void_p),
+        ("n_blocks", C.c_int32),
+        ("blk_seg", C.c_void_p), ("blk_lo", C.c_void_p), ("blk_hi", C.c_void_p),
+        ("seg_blk_offset", C.c_void_p),
+        ("bias", C.c_void_p), ("cweights", C.c_void_p), ("w", C.c_void_p),
+        ("direct_row", C.c_void_p), ("pieces_row", C.c_void_p),
+        ("direct_col", C.c_void_p), ("pieces_col", C.c_void_p),
+        ("s", C.c_void_p), ("marg", C.c_void_p),
+        ("blk_sum", C.c_void_p), ("blk_cnt", C.c_void_p), ("blk_dev", C.c_void_p),
+        ("seg_mean", C.c_void_p), ("seg_nnz", C.c_void_p),
+        ("seg_scale", C.c_void_p), ("seg_var", C.c_void_p),
+        ("seg_iters", C.c_void_p), ("seg_done", C.c_void_p), ("seg_empty", C.c_void_p),
+        ("all_done", C.c_void_p), ("var_hist", C.c_void_p),
+        ("tol", C.c_double), ("max_iters", C.c_int32),
+    ]
+
+
+_P, _I32, _I64, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol declared in include/cooler_b200.h
+SIGNATURES = {
+    "cb200_abi_version": (C.c_int, []),
+    "cb200_last_error": (C.c_char_p, []),
+    "cb200_set_device": (C.c_int, [C.c_int]),
+    "cb200_warp_tile": (C.c_int, []),
+    "cb200_scan_workspace_bytes": (_SZ, [_I64]),
+    "cb200_exclusive_scan_i32": (C.c_int, [_P, _P, _I64, _P, _SZ, _P]),
+    "cb200_sort_workspace_bytes": (_SZ, [_I64]),
+    "cb200_sort_pairs": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, C.c_int, _P, _SZ, _P]),
+    "cb200_pack_pixels": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "cb200_tile_rows": (C.c_int, [_P, _I32, _I64, _P, _P]),
+    "cb200_indptr_from_sorted": (C.c_int, [_P, _I64, _I32, _P, _P]),
+    "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _P, _P]),
+    "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
+    "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),
+    "cb200_ice_combine": (C.c_int, [C.POINTER(Ice), _P]),
+    "cb200_ice_update": (C.c_int, [C.POINTER(Ice), _I32, _P]),
+    "cb200_coarsen_remap": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
+    "cb200_runs_count": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "cb200_runs_write": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P]),
+    "cb200_unpack_pixels": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library (once).  Raises NativeLibraryError if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            f"{LIB_PATH} is missing: build it with `python -m cooler_b200.build` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().cb200_last_error().decode("utf-8", "replace")
+        raise NativeLibraryError(f"{what} failed (rc={rc}): {msg}")
+
+
+def call(name, *args):
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,337 @@
+"""ICE matrix balancing on B200 -- drop-in for ``cooler.balance_cooler``.
+
+Mirrors open2c/cooler v0.10.4 ``src/cooler/_balance.py`` (names, arguments,
+return values, warnings).  The chunk map-reduce of the reference
+(``parallel.split(...).pipe(...).reduce(add)``) and the three
+``_balance_*`` loops are replaced by CUDA kernels in libcooler_b200.so; the
+O(n_bins) filter arithmetic (min_nnz, min_count, MAD-max, blacklist;
+_balance.py:375-413) stays on the host in numpy, statement for statement, so
+that the filter masks are bit-exact.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import warnings
+
+import numpy as np
+import torch
+
+from . import _lib
+from .table import (PixelTable, TableCopy, _ptr, _stream, _use_device, filter_copy,  # noqa: F401
+                    marginals_i64, n_tiles, transpose_from)
+
+__all__ = ["balance_cooler", "balance_table", "ConvergenceWarning", "IceProblem"]
+
+logger = logging.getLogger("cooler")   # same logger name as the reference (_logging.py)
+
+_F64, _I32 = torch.float64, torch.int32
+UPD_BINS = 1024                         # bins per block of the per-bin kernels (csrc/ice.cu)
+
+
+class ConvergenceWarning(UserWarning):
+    """Same role as cooler._balance.ConvergenceWarning (_balance.py:21)."""
+
+
+def mad(data, axis=None):
+    """util.mad (src/cooler/util.py:513-514)."""
+    return np.median(np.abs(data - np.median(data, axis)), axis)
+
+
+def _allreduce(t, group):
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+class IceProblem:
+    """Filtered CSR/CSC copies of one table for one (mode, ignore_diags) choice.
+
+    Stage A applies the reference's ``base_filters`` (_balance.py:360-364):
+    ``_zero_trans`` for cis_only, ``_zero_diags``; the prefilter marginals
+    (min_nnz pass and raw marginal, _balance.py:375-393) are taken on it.
+    For trans_only stage B additionally removes cis pixels (``_zero_cis`` is
+    only piped inside ``_balance_transonly``, _balance.py:227).
+    """
+
+    def __init__(self, table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2,
+                 group=None):
+        self.table = table
+        self.group = group
+        self.mode = "cis" if cis_only else ("trans" if trans_only else "gw")
+        ndiag = int(ignore_diags) if ignore_diags else 0
+        keep = _lib.KEEP_CIS if cis_only else _lib.KEEP_ALL
+        csr, tkey, tval = filter_copy(table.raw, table.row_lo, table.row_hi, ndiag, keep,
+                                      want_transpose=True)
+        csc = transpose_from(tkey, tval, table.n_bins)
+        del tkey, tval
+        # prefilter marginals (exact integers)
+        nnz_r, sum_r = marginals_i64(csr)
+        nnz_c, sum_c = marginals_i64(csc)
+        marg = torch.stack([nnz_r + nnz_c, sum_r + sum_c])
+        _allreduce(marg, group)
+        marg = marg.cpu().numpy()
+        self.marg_nnz = marg[0].astype(np.float64)
+        self.marg_sum = marg[1].astype(np.float64)
+        if trans_only:
+            csr, _, _ = filter_copy(csr, table.row_lo, table.row_hi, 0, _lib.KEEP_TRANS)
+            csc, _, _ = filter_copy(csc, table.row_lo, table.row_hi, 0, _lib.KEEP_TRANS)
+        self.csr, self.csc = csr, csc
+
+    @property
+    def nnz_eff(self):
+        """Stored pixels surviving the static filters (one copy)."""
+        return self.csr.nnz
+
+    def bytes_per_pass(self):
+        """Algorithmic bytes of one marginal pass: 16 B/effective pixel + 40 B/bin."""
+        return 16 * self.nnz_eff + 40 * self.table.n_bins
+
+
+class IceState:
+    """Device buffers + cb200_ice descriptor for the iteration loop."""
+
+    def __init__(self, prob: IceProblem, bias0, cweights, seg_offset, tol, max_iters):
+        dev = prob.table.device
+        n = prob.table.n_bins
+        seg_offset = np.asarray(seg_offset, dtype=np.int64)
+        S = len(seg_offset) - 1
+        # host block table: blocks of UPD_BINS bins, never straddling a segment
+        blk_seg, blk_lo, blk_hi, seg_blk = [], [], [], [0]
+        for s in range(S):
+            lo, hi = int(seg_offset[s]), int(seg_offset[s + 1])
+            for b in range(lo, hi, UPD_BINS):
+                blk_seg.append(s), blk_lo.append(b), blk_hi.append(min(b + UPD_BINS, hi))
+            seg_blk.append(len(blk_seg))
+        nb = len(blk_seg)
+
+        def i32(a):
+            return torch.tensor(np.asarray(a, dtype=np.int32), dtype=_I32, device=dev)
+
+        def f64(k, fill=0.0):
+            return torch.full((max(int(k), 1),), fill, dtype=_F64, device=dev)
+
+        self.n, self.S, self.max_iters = n, S, int(max_iters)
+        self.t = t = {}
+        t["seg_offset"], t["blk_seg"], t["blk_lo"], t["blk_hi"] = i32(seg_offset), i32(blk_seg), i32(blk_lo), i32(blk_hi)
+        t["seg_blk_offset"] = i32(seg_blk)
+        t["bias"] = torch.from_numpy(np.ascontiguousarray(bias0, dtype=np.float64)).to(dev)
+        if cweights is not None:
+            t["cweights"] = torch.from_numpy(np.ascontiguousarray(cweights, dtype=np.float64)).to(dev)
+            t["w"] = t["bias"] * t["cweights"]
+        else:
+            t["cweights"] = None
+            t["w"] = t["bias"]
+        t["direct_row"], t["direct_col"] = f64(n), f64(n)
+        t["pieces_row"], t["pieces_col"] = f64(2 * n_tiles(prob.csr.nnz)), f64(2 * n_tiles(prob.csc.nnz))
+        t["s"], t["marg"] = f64(n), f64(n)
+        t["blk_sum"], t["blk_cnt"], t["blk_dev"] = f64(nb), f64(nb), f64(nb)
+        t["seg_mean"], t["seg_nnz"] = f64(S), f64(S)
+        t["seg_scale"], t["seg_var"] = f64(S, 1.0), f64(S, float("nan"))
+        for k in ("seg_iters", "seg_done", "seg_empty"):
+            t[k] = torch.zeros(max(S, 1), dtype=_I32, device=dev)
+        t["all_done"] = torch.zeros(1, dtype=_I32, device=dev)
+        t["var_hist"] = f64(self.max_iters * S, float("nan"))
+        st = _lib.Ice()
+        st.csr, st.csc = prob.csr.c_struct(), prob.csc.c_struct()
+        st.n_bins, st.n_segs, st.n_blocks = n, S, nb
+        for k in ("seg_offset", "blk_seg", "blk_lo", "blk_hi", "seg_blk_offset", "bias", "cweights", "w",
+                  "direct_row", "pieces_row", "direct_col", "pieces_col", "s", "marg", "blk_sum", "blk_cnt",
+                  "blk_dev", "seg_mean", "seg_nnz", "seg_scale", "seg_var", "seg_iters", "seg_done",
+                  "seg_empty", "all_done", "var_hist"):
+            setattr(st, k, t[k].data_ptr() if t[k] is not None else None)
+        st.tol, st.max_iters = float(tol), self.max_iters
+        self.st = st
+        self.prob = prob
+        self.flag_host = torch.zeros(1, dtype=_I32).pin_memory() if torch.cuda.is_available() else None
+        self.launches = 0
+
+    def one_pass(self, it):
+        """sweep (K3) -> combine -> [allreduce] -> update (K4).  Asynchronous."""
+        st, stream = C.byref(self.st), _stream()
+        _lib.call("cb200_ice_sweep", st, stream)
+        _lib.call("cb200_ice_combine", st, stream)
+        _allreduce(self.t["s"], self.prob.group)
+        _lib.call("cb200_ice_update", st, int(it), stream)
+        self.launches += 6
+
+    def run(self, check_every=8):
+        """Iterate until every segment converged or max_iters.  Returns passes launched."""
+        it = 0
+        while it < self.max_iters:
+            k = min(check_every, self.max_iters - it)
+            for j in range(k):
+                self.one_pass(it + j)
+            it += k
+            self.flag_host.copy_(self.t["all_done"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            if int(self.flag_host[0]):
+                break
+        return it
+
+    def results(self):
+        t = self.t
+        out = {k: t[k][: self.S].cpu().numpy() for k in
+               ("seg_scale", "seg_var", "seg_iters", "seg_done", "seg_empty")}
+        out["bias"] = t["bias"][: self.n].cpu().numpy()
+        out["var_hist"] = t["var_hist"][: self.max_iters * self.S].cpu().numpy().reshape(self.max_iters, self.S)
+        return out
+
+
+def prefilter_bias(prob: IceProblem, chrom_offset, *, mad_max, min_nnz, min_count, blacklist, x0):
+    """Host-side bin filters, statement for statement (_balance.py:366-413)."""
+    n_bins = prob.table.n_bins
+    if x0 is not None:
+        bias = x0
+        bias[np.isnan(bias)] = 0
+    else:
+        bias = np.ones(n_bins, dtype=float)
+
+    if min_nnz > 0:
+        bias[prob.marg_nnz < min_nnz] = 0
+
+    marg = prob.marg_sum.copy()
+    if min_count:
+        bias[marg < min_count] = 0
+
+    if mad_max > 0:
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for lo, hi in zip(chrom_offset[:-1], chrom_offset[1:]):
+                c_marg = marg[lo:hi]
+                marg[lo:hi] /= np.median(c_marg[c_marg > 0])
+            logNzMarg = np.log(marg[marg > 0])
+            med_logNzMarg = np.median(logNzMarg)
+            dev_logNzMarg = mad(logNzMarg)
+            cutoff = np.exp(med_logNzMarg - mad_max * dev_logNzMarg)
+            bias[marg < cutoff] = 0
+
+    if blacklist is not None:
+        bias[blacklist] = 0
+    return bias
+
+
+def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2, mad_max=5,
+                  min_nnz=10, min_count=0, blacklist=None, rescale_marginals=True, x0=None,
+                  tol=1e-5, max_iters=200, group=None, problem=None, chromnames=None,
+                  return_info=False):
+    """Balance a device-resident table.  Same semantics as ``balance_cooler``.
+
+    ``problem`` lets callers reuse the filtered copies (bench: inputs resident
+    in HBM).  ``group``: torch.distributed process group when the table is a
+    row shard (marginals are all-reduced across ranks).
+    """
+    _use_device(table.device)
+    chrom_offset = table.chrom_offset
+    n_bins = table.n_bins
+    n_chroms = len(chrom_offset) - 1
+    prob = problem or IceProblem(table, cis_only=cis_only, trans_only=trans_only,
+                                 ignore_diags=ignore_diags, group=group)
+    bias = prefilter_bias(prob, chrom_offset, mad_max=mad_max, min_nnz=min_nnz, min_count=min_count,
+                          blacklist=blacklist, x0=x0)
+
+    cweights = None
+    if cis_only:
+        seg_offset = chrom_offset
+    else:
+        seg_offset = np.array([0, n_bins])
+        if trans_only:                                            # _balance.py:214-220
+            cweights = 1.0 / np.concatenate(
+                [[(1 - (hi - lo) / n_bins)] * (hi - lo)
+                 for lo, hi in zip(chrom_offset[:-1], chrom_offset[1:])]) if n_bins else np.zeros(0)
+
+    state = IceState(prob, bias, cweights, seg_offset, tol, max_iters)
+    passes = state.run()
+    res = state.results()
+    bias[:] = res["bias"]
+
+    hit_limit = False
+    if cis_only:
+        scales = np.ones(n_chroms)
+        variances = np.full_like(scales, np.nan)
+        for cid, lo, hi in zip(range(n_chroms), chrom_offset[:-1], chrom_offset[1:]):
+            if chromnames is not None:
+                logger.info(chromnames[cid])
+            for v in res["var_hist"][: res["seg_iters"][cid], cid]:
+                logger.info(f"variance is {v}")
+            if res["seg_empty"][cid]:                             # _balance.py:166-170
+                scale, var = np.nan, 0.0
+                bias[lo:hi] = np.nan
+            else:
+                scale, var = res["seg_scale"][cid], res["seg_var"][cid]
+                if not res["seg_done"][cid]:
+                    hit_limit = True
+                    name = chromnames[cid] if chromnames is not None else cid
+                    warnings.warn(f"Iteration limit reached without convergence on {name}.",
+                                  ConvergenceWarning, stacklevel=2)
+            b = bias[lo:hi]
+            b[b == 0] = np.nan
+            scales[cid] = scale
+            variances[cid] = var
+            if rescale_marginals:
+                bias[lo:hi] /= np.sqrt(scale)
+        scale, var = scales, variances
+    else:
+        for v in res["var_hist"][: res["seg_iters"][0], 0]:
+            logger.info(f"variance is {v}")
+        if res["seg_empty"][0]:                                   # _balance.py:98-102
+            scale, var = np.nan, 0.0
+            bias[:] = np.nan
+        else:
+            scale, var = res["seg_scale"][0], res["seg_var"][0]
+            if not res["seg_done"][0]:
+                hit_limit = True
+                warnings.warn("Iteration limit reached without convergence.",
+                              ConvergenceWarning, stacklevel=2)
+        bias[bias == 0] = np.nan
+        if rescale_marginals:
+            bias /= np.sqrt(scale)
+
+    stats = {
+        "tol": tol, "min_nnz": min_nnz, "min_count": min_count, "mad_max": mad_max,
+        "cis_only": cis_only, "ignore_diags": ignore_diags, "scale": scale,
+        "converged": var < tol, "var": var, "divisive_weights": False,
+    }
+    if return_info:
+        info = {"passes": res["seg_iters"].tolist(), "launched_passes": passes,
+                "nnz_eff": prob.nnz_eff, "bytes_per_pass": prob.bytes_per_pass(),
+                "hit_limit": hit_limit, "gpu_launches": state.launches}
+        return bias, stats, info
+    return bias, stats
+
+
+def balance_cooler(clr, *, cis_only=False, trans_only=False, ignore_diags=2, mad_max=5, min_nnz=10,
+                   min_count=0, blacklist=None, rescale_marginals=True, x0=None, tol=1e-5,
+                   max_iters=200, chunksize=10_000_000, map=map, use_lock=False, store=False,
+                   store_name="weight", device="cuda"):
+    """Iterative correction of a cooler on the GPU.
+
+    Same signature, return value ``(bias, stats)`` and side effects as
+    ``cooler.balance_cooler`` (_balance.py:263-477).  ``chunksize``, ``map`` and
+    ``use_lock`` are accepted for compatibility and ignored: the pixel table is
+    read once and stays resident in HBM.  ``clr`` is a ``cooler.Cooler`` or any
+    object with the same read protocol (e.g. ``cooler_b200.store.MemCooler``).
+    """
+    table = PixelTable.from_cooler(clr, device=device)
+    try:
+        chromnames = list(clr.chroms()["name"][:])
+    except Exception:  # pragma: no cover - duck-typed stores without a chroms selector
+        chromnames = None
+    bias, stats = balance_table(
+        table, cis_only=cis_only, trans_only=trans_only, ignore_diags=ignore_diags, mad_max=mad_max,
+        min_nnz=min_nnz, min_count=min_count, blacklist=blacklist,
+        rescale_marginals=rescale_marginals, x0=x0, tol=tol, max_iters=max_iters,
+        chromnames=chromnames)
+
+    if store:                                                     # _balance.py:469-475
+        with clr.open("r+") as grp:
+            if store_name in grp["bins"]:
+                del grp["bins"][store_name]
+            h5opts = {"compression": "gzip", "compression_opts": 6}
+            grp["bins"].create_dataset(store_name, data=bias, **h5opts)
+            grp["bins"][store_name].attrs.update(stats)
+    return bias, stats
+
+
+iterative_correction = balance_cooler  # alias (_balance.py:480)

@@ -1,0 +1,158 @@
+// Coarsening kernels (K5): fused bin remap feeding the stable radix sort, then
+// reduce-by-key.  Replaces CoolerCoarsener._aggregate's annotate-join + pandas
+// groupby(sort=True).sum() (open2c/cooler src/cooler/_reduce.py:582-620).
+//
+// Chain for one level (host side: cooler_b200/reduce.py):
+//   CSR(bin1,bin2) --remap--> key=bin2', val={bin1',v}  --stable sort by bin2'-->
+//   runs of equal (bin2',bin1') are adjacent --runs_write(swap)--> key=bin1', val={bin2',sum}
+//   --stable sort by bin1'--> CSR' sorted by (bin1',bin2'), duplicate-free.
+#include "walk.cuh"
+#include "../../include/cooler_b200.h"
+
+namespace cb200 {
+
+struct RemapOut {
+  const int32_t* __restrict__ bin_map;
+  int32_t* key_out;
+  int2* val_out;
+  __device__ __forceinline__ void operator()(int64_t pos, bool ok0, bool ok1, int r0, int r1, int4 q) {
+    if (ok0) {
+      key_out[pos] = __ldg(bin_map + q.x);
+      val_out[pos] = make_int2(__ldg(bin_map + r0), q.y);
+    }
+    if (ok1) {
+      key_out[pos + 1] = __ldg(bin_map + q.z);
+      val_out[pos + 1] = make_int2(__ldg(bin_map + r1), q.w);
+    }
+  }
+};
+
+__global__ void __launch_bounds__(BLOCK_THREADS)
+coarsen_remap_kernel(const int2* __restrict__ px, const int64_t* __restrict__ indptr,
+                     const int32_t* __restrict__ tile_row, int64_t nnz, int64_t n_tiles,
+                     const int32_t* __restrict__ bin_map, int32_t* __restrict__ key_out,
+                     int2* __restrict__ val_out) {
+  const int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (t >= n_tiles) return;
+  RemapOut f{bin_map, key_out, val_out};
+  walk_map_tile(px, indptr, nnz, t, tile_row[t], f);
+}
+
+// A run head is an element whose (key, other) differs from its predecessor's.
+__device__ __forceinline__ bool is_head(const int32_t* __restrict__ keys, const int2* __restrict__ vals,
+                                        int64_t p) {
+  if (p == 0) return true;
+  return keys[p] != keys[p - 1] || vals[p].x != vals[p - 1].x;
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS)
+runs_count_kernel(const int32_t* __restrict__ keys, const int2* __restrict__ vals, int64_t n,
+                  int64_t n_tiles, int32_t* __restrict__ tile_count) {
+  const int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (t >= n_tiles) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t p0 = t * (int64_t)WARP_TILE, p1 = min(p0 + (int64_t)WARP_TILE, n);
+  int c = 0;
+  for (int64_t p = p0 + lane; p < p1; p += 32) c += is_head(keys, vals, p) ? 1 : 0;
+  c = warp_sum(c);
+  if (lane == 0) tile_count[t] = c;
+}
+
+__global__ void __launch_bounds__(BLOCK_THREADS)
+runs_write_kernel(const int32_t* __restrict__ keys, const int2* __restrict__ vals, int64_t n,
+                  int64_t n_tiles, const int64_t* __restrict__ tile_off, int swap,
+                  int32_t* __restrict__ key_out, int2* __restrict__ val_out,
+                  int64_t* __restrict__ sum64_out, int32_t* __restrict__ overflow) {
+  const int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (t >= n_tiles) return;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int64_t p0 = t * (int64_t)WARP_TILE, p1 = min(p0 + (int64_t)WARP_TILE, n);
+  int64_t base = tile_off[t];
+  for (int64_t c = p0; c < p1; c += 32) {
+    const int64_t p = c + lane;
+    const bool head = (p < p1) && is_head(keys, vals, p);
+    const unsigned hb = __ballot_sync(0xffffffffu, head);
+    if (head) {
+      const int k = keys[p];
+      const int o = vals[p].x;
+      long long sum = vals[p].y;
+      for (int64_t e = p + 1; e < n && keys[e] == k && vals[e].x == o; ++e) sum += vals[e].y;   // run may cross tiles
+      const int64_t out = base + __popc(hb & lt);
+      const int lo32 = (int)sum;
+      if ((long long)lo32 != sum) *overflow = 1;
+      key_out[out] = swap ? o : k;
+      val_out[out] = make_int2(swap ? k : o, lo32);
+      if (sum64_out) sum64_out[out] = sum;
+    }
+    base += __popc(hb);
+  }
+}
+
+__global__ void unpack_pixels_kernel(const int32_t* __restrict__ bin1, const int2* __restrict__ val,
+                                     int64_t n, int64_t* __restrict__ b1, int64_t* __restrict__ b2,
+                                     int32_t* __restrict__ cnt) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int2 v = val[i];
+    b1[i] = bin1[i];
+    b2[i] = v.x;
+    cnt[i] = v.y;
+  }
+}
+
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_coarsen_remap(const cb200_copy* csr, int32_t n_rows, const int32_t* bin_map,
+                        int32_t* key_out, cb200_px* val_out, void* stream) {
+  (void)n_rows;
+  const int64_t n_tiles = ceil_div64(csr->nnz, WARP_TILE);
+  if (n_tiles <= 0) return 0;
+  coarsen_remap_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0,
+                         (cudaStream_t)stream>>>(reinterpret_cast<const int2*>(csr->px), csr->indptr,
+                                                 csr->tile_row, csr->nnz, n_tiles, bin_map, key_out,
+                                                 reinterpret_cast<int2*>(val_out));
+  CB_LAUNCH_CHECK("coarsen_remap");
+  return 0;
+}
+
+int cb200_runs_count(const int32_t* keys, const cb200_px* vals, int64_t n, int32_t* tile_count,
+                     void* stream) {
+  const int64_t n_tiles = ceil_div64(n, WARP_TILE);
+  if (n_tiles <= 0) return 0;
+  runs_count_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0,
+                      (cudaStream_t)stream>>>(keys, reinterpret_cast<const int2*>(vals), n, n_tiles,
+                                              tile_count);
+  CB_LAUNCH_CHECK("runs_count");
+  return 0;
+}
+
+int cb200_runs_write(const int32_t* keys, const cb200_px* vals, int64_t n, const int64_t* tile_off,
+                     int32_t swap, int32_t* key_out, cb200_px* val_out, int64_t* sum64_out,
+                     int32_t* overflow, void* stream) {
+  const int64_t n_tiles = ceil_div64(n, WARP_TILE);
+  if (n_tiles <= 0) return 0;
+  runs_write_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0,
+                      (cudaStream_t)stream>>>(keys, reinterpret_cast<const int2*>(vals), n, n_tiles,
+                                              tile_off, swap, key_out,
+                                              reinterpret_cast<int2*>(val_out), sum64_out, overflow);
+  CB_LAUNCH_CHECK("runs_write");
+  return 0;
+}
+
+int cb200_unpack_pixels(const int32_t* bin1, const cb200_px* val, int64_t n, int64_t* bin1_out,
+                        int64_t* bin2_out, int32_t* count_out, void* stream) {
+  if (n <= 0) return 0;
+  int64_t blocks = ceil_div64(n, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  unpack_pixels_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      bin1, reinterpret_cast<const int2*>(val), n, bin1_out, bin2_out, count_out);
+  CB_LAUNCH_CHECK("unpack_pixels");
+  return 0;
+}
+
+}  // extern "C"

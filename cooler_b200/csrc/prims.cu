@@ -1,0 +1,279 @@
+// Device-wide primitives: exclusive scan and stable LSD radix sort of
+// (int32 key, 8-byte value) pairs.  Hand-written for sm_100a; no CUB/Thrust.
+#include "common.cuh"
+#include "../../include/cooler_b200.h"
+
+namespace cb200 {
+
+// ---------------------------------------------------------------- scan ----
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_tile_sums(const TIn* __restrict__ in, int64_t n, int64_t* __restrict__ tile_sum) {
+  __shared__ long long wsum[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+  long long v = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + (int64_t)k * SCAN_THREADS + threadIdx.x;
+    if (i < n) v += (long long)in[i];
+  }
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t = 0;
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) t += wsum[w];
+    tile_sum[blockIdx.x] = t;
+  }
+}
+
+// Each thread owns SCAN_ITEMS consecutive elements (blocked layout).
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_apply(const TIn* __restrict__ in, int64_t n, const int64_t* __restrict__ tile_off,
+           int64_t* __restrict__ out) {
+  __shared__ long long wsum[SCAN_THREADS / 32];
+  const int64_t base = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+  long long x[SCAN_ITEMS];
+  long long tsum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + k;
+    x[k] = (i < n) ? (long long)in[i] : 0;
+    tsum += x[k];
+  }
+  // inclusive warp scan of the thread sums
+  long long incl = tsum;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    long long y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  long long woff = 0;
+  for (int w = 0; w < wid; ++w) woff += wsum[w];
+  long long run = (long long)tile_off[blockIdx.x] + woff + incl - tsum;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    int64_t i = base + k;
+    if (i < n) out[i] = run;
+    run += x[k];
+    if (i == n - 1) out[n] = run;
+  }
+}
+
+__global__ void scan_zero(int64_t* out) { out[0] = 0; }
+
+static size_t scan_ws_bytes(int64_t n) {
+  size_t total = 0;
+  while (n > 1) {
+    int64_t tiles = ceil_div64(n, SCAN_TILE);
+    total += (size_t)(tiles + 1) * sizeof(int64_t) * 2;  // sums + scanned sums
+    n = tiles;
+  }
+  return total + 64;
+}
+
+template <typename TIn>
+static int scan_rec(const TIn* in, int64_t* out, int64_t n, char* ws, cudaStream_t st) {
+  if (n <= 0) {
+    scan_zero<<<1, 1, 0, st>>>(out);
+    CB_LAUNCH_CHECK("scan_zero");
+    return 0;
+  }
+  int64_t tiles = ceil_div64(n, SCAN_TILE);
+  int64_t* sums = reinterpret_cast<int64_t*>(ws);
+  int64_t* offs = sums + (tiles + 1);
+  char* next_ws = reinterpret_cast<char*>(offs + (tiles + 1));
+  scan_tile_sums<TIn><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, sums);
+  CB_LAUNCH_CHECK("scan_tile_sums");
+  if (tiles == 1) {
+    scan_zero<<<1, 1, 0, st>>>(offs);
+    CB_LAUNCH_CHECK("scan_zero");
+  } else {
+    int rc = scan_rec<int64_t>(sums, offs, tiles, next_ws, st);
+    if (rc) return rc;
+  }
+  scan_apply<TIn><<<(unsigned)tiles, SCAN_THREADS, 0, st>>>(in, n, offs, out);
+  CB_LAUNCH_CHECK("scan_apply");
+  return 0;
+}
+
+int exclusive_scan_i32(const int32_t* in, int64_t* out, int64_t n, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+  if (ws_bytes < scan_ws_bytes(n)) {
+    set_error_msg("scan workspace too small");
+    return -1;
+  }
+  return scan_rec<int32_t>(in, out, n, reinterpret_cast<char*>(ws), st);
+}
+
+// ---------------------------------------------------------- radix sort ----
+constexpr int SORT_WARPS = 16;
+constexpr int SORT_THREADS = SORT_WARPS * 32;
+constexpr int SORT_STEPS = 8;                        // elements per thread
+constexpr int SORT_WARP_SPAN = SORT_STEPS * 32;      // consecutive elements owned by a warp
+constexpr int SORT_TILE = SORT_THREADS * SORT_STEPS; // 4096 elements per CTA
+constexpr int RADIX = 256;
+
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_hist(const int32_t* __restrict__ keys, int64_t n, int shift, int mask,
+           int32_t* __restrict__ hist, int nblocks) {
+  __shared__ int h[RADIX];
+  for (int d = threadIdx.x; d < RADIX; d += SORT_THREADS) h[d] = 0;
+  __syncthreads();
+  const int64_t base = (int64_t)blockIdx.x * SORT_TILE;
+#pragma unroll
+  for (int s = 0; s < SORT_STEPS; ++s) {
+    int64_t e = base + (int64_t)s * SORT_THREADS + threadIdx.x;
+    if (e < n) atomicAdd(&h[(keys[e] >> shift) & mask], 1);   // integer: order-independent
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d <= mask; d += SORT_THREADS)
+    hist[(int64_t)d * nblocks + blockIdx.x] = h[d];
+}
+
+// Stable scatter: a warp owns SORT_WARP_SPAN consecutive elements and ranks
+// them 32 at a time in element order with match.any; warps are then chained
+// per digit in warp order, so equal digits keep their input order.
+__global__ void __launch_bounds__(SORT_THREADS)
+radix_scatter(const int32_t* __restrict__ keys_in, const int2* __restrict__ vals_in,
+              int32_t* __restrict__ keys_out, int2* __restrict__ vals_out, int64_t n,
+              int shift, int mask, const int64_t* __restrict__ off, int nblocks) {
+  __shared__ unsigned wcount[SORT_WARPS][RADIX];
+  __shared__ long long dbase[RADIX];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&wcount[0][0])[i] = 0u;
+  __syncthreads();
+
+  const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + (int64_t)wid * SORT_WARP_SPAN;
+  int32_t key[SORT_STEPS];
+  int2 val[SORT_STEPS];
+  unsigned rank[SORT_STEPS];
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int s = 0; s < SORT_STEPS; ++s) {
+    int64_t e = wbase + s * 32 + lane;
+    bool ok = e < n;
+    key[s] = ok ? keys_in[e] : 0;
+    val[s] = ok ? vals_in[e] : make_int2(0, 0);
+  }
+#pragma unroll
+  for (int s = 0; s < SORT_STEPS; ++s) {
+    int64_t e = wbase + s * 32 + lane;
+    bool ok = e < n;
+    int d = ok ? ((key[s] >> shift) & mask) : (RADIX + lane);   // invalid lanes match nobody
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    unsigned old = 0;
+    if (ok) old = wcount[wid][d];
+    __syncwarp();
+    if (ok && (peers & lt) == 0) wcount[wid][d] = old + __popc(peers);
+    __syncwarp();
+    rank[s] = old + __popc(peers & lt);
+  }
+  __syncthreads();
+  if (threadIdx.x <= mask) {
+    const int d = threadIdx.x;
+    dbase[d] = off[(int64_t)d * nblocks + blockIdx.x];
+    unsigned run = 0;
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      unsigned c = wcount[w][d];
+      wcount[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int s = 0; s < SORT_STEPS; ++s) {
+    int64_t e = wbase + s * 32 + lane;
+    if (e < n) {
+      int d = (key[s] >> shift) & mask;
+      int64_t pos = dbase[d] + wcount[wid][d] + rank[s];
+      keys_out[pos] = key[s];
+      vals_out[pos] = val[s];
+    }
+  }
+}
+
+static size_t sort_ws_bytes(int64_t n) {
+  int64_t nblocks = ceil_div64(n > 0 ? n : 1, SORT_TILE);
+  int64_t m = nblocks * RADIX;
+  return (size_t)m * sizeof(int32_t) + (size_t)(m + 1) * sizeof(int64_t) + scan_ws_bytes(m) + 256;
+}
+
+int sort_pairs(const int32_t* keys_in, const int2* vals_in, int32_t* keys_out, int2* vals_out,
+               int32_t* keys_tmp, int2* vals_tmp, int64_t n, int key_bits, void* ws,
+               size_t ws_bytes, cudaStream_t st) {
+  if (ws_bytes < sort_ws_bytes(n)) {
+    set_error_msg("sort workspace too small");
+    return -1;
+  }
+  if (n <= 0) return 0;
+  if (key_bits < 1) key_bits = 1;
+  if (key_bits > 31) key_bits = 31;
+  const int passes = (key_bits + 7) / 8;
+  const int bits = (key_bits + passes - 1) / passes;
+  const int64_t nblocks = ceil_div64(n, SORT_TILE);
+  if (nblocks > 0x7fffffff) {
+    set_error_msg("sort: too many elements");
+    return -1;
+  }
+  char* p = reinterpret_cast<char*>(ws);
+  int32_t* hist = reinterpret_cast<int32_t*>(p);
+  size_t hist_bytes = ((size_t)nblocks * RADIX * sizeof(int32_t) + 127) / 128 * 128;
+  int64_t* off = reinterpret_cast<int64_t*>(p + hist_bytes);
+  size_t off_bytes = (((size_t)nblocks * RADIX + 1) * sizeof(int64_t) + 127) / 128 * 128;
+  char* scan_ws = p + hist_bytes + off_bytes;
+  size_t scan_bytes = ws_bytes - hist_bytes - off_bytes;
+
+  const int32_t* ksrc = keys_in;
+  const int2* vsrc = vals_in;
+  for (int k = 0; k < passes; ++k) {
+    const int shift = k * bits;
+    const int nb = (k == passes - 1) ? (key_bits - shift) : bits;
+    const int mask = (1 << nb) - 1;
+    const bool to_out = ((passes - k) % 2) == 1;
+    int32_t* kdst = to_out ? keys_out : keys_tmp;
+    int2* vdst = to_out ? vals_out : vals_tmp;
+    radix_hist<<<(unsigned)nblocks, SORT_THREADS, 0, st>>>(ksrc, n, shift, mask, hist, (int)nblocks);
+    CB_LAUNCH_CHECK("radix_hist");
+    int rc = exclusive_scan_i32(hist, off, (int64_t)(mask + 1) * nblocks, scan_ws, scan_bytes, st);
+    if (rc) return rc;
+    radix_scatter<<<(unsigned)nblocks, SORT_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, shift,
+                                                              mask, off, (int)nblocks);
+    CB_LAUNCH_CHECK("radix_scatter");
+    ksrc = kdst;
+    vsrc = vdst;
+  }
+  return 0;
+}
+
+}  // namespace cb200
+
+extern "C" {
+
+size_t cb200_scan_workspace_bytes(int64_t n) { return cb200::scan_ws_bytes(n); }
+
+int cb200_exclusive_scan_i32(const int32_t* in, int64_t* out, int64_t n, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  return cb200::exclusive_scan_i32(in, out, n, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t cb200_sort_workspace_bytes(int64_t n) { return cb200::sort_ws_bytes(n); }
+
+int cb200_sort_pairs(const int32_t* keys_in, const cb200_px* vals_in, int32_t* keys_out,
+                     cb200_px* vals_out, int32_t* keys_tmp, cb200_px* vals_tmp, int64_t n,
+                     int key_bits, void* workspace, size_t workspace_bytes, void* stream) {
+  return cb200::sort_pairs(keys_in, reinterpret_cast<const int2*>(vals_in), keys_out,
+                           reinterpret_cast<int2*>(vals_out), keys_tmp,
+                           reinterpret_cast<int2*>(vals_tmp), n, key_bits, workspace,
+                           workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

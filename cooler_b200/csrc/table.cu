@@ -1,0 +1,260 @@
+// Pixel-table build kernels: packing, warp-tile row index, indptr from sorted
+// ids, static filters by stable compaction, integer (prefilter) marginals.
+#include <cstdio>
+#include "walk.cuh"
+#include "../../include/cooler_b200.h"
+
+namespace cb200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), where);
+}
+void set_error_msg(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
+
+// ------------------------------------------------------------------ pack ----
+__global__ void pack_pixels_kernel(const int64_t* __restrict__ bin2, const int32_t* __restrict__ count,
+                                   int64_t nnz, int2* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride)
+    out[i] = make_int2((int)bin2[i], count[i]);
+  // zero the pad element so that 128-bit loads of the last pair are defined
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (nnz & 1)) out[nnz] = make_int2(0, 0);
+}
+
+// ------------------------------------------------------------- tile rows ----
+__global__ void tile_rows_kernel(const int64_t* __restrict__ indptr, int n_rows, int64_t nnz,
+                                 int64_t n_tiles, int32_t* __restrict__ tile_row) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_tiles) return;
+  const int64_t p = t * (int64_t)WARP_TILE;
+  // largest r in [0, n_rows) with indptr[r] <= p   (upper_bound - 1)
+  int lo = 0, hi = n_rows;  // invariant: indptr[lo] <= p, indptr[hi] > p  (indptr[n_rows] = nnz > p)
+  while (hi - lo > 1) {
+    int mid = lo + ((hi - lo) >> 1);
+    if (indptr[mid] <= p) lo = mid; else hi = mid;
+  }
+  tile_row[t] = lo;
+}
+
+// --------------------------------------------------- indptr from sorted ----
+__global__ void indptr_from_sorted_kernel(const int32_t* __restrict__ keys, int64_t n, int n_rows,
+                                          int64_t* __restrict__ indptr) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += stride) {
+    const int prev = (p == 0) ? -1 : keys[p - 1];
+    const int cur = (p == n) ? n_rows : keys[p];
+    for (int r = prev + 1; r <= cur; ++r) indptr[r] = p;
+  }
+}
+
+// ---------------------------------------------------------------- filter ----
+struct KeepRule {
+  const int32_t* row_lo;
+  const int32_t* row_hi;
+  int ndiag;
+  int keep;
+  __device__ __forceinline__ bool operator()(int r, int c) const {
+    if (ndiag > 0) {
+      int d = r - c;
+      if (d < 0) d = -d;
+      if (d < ndiag) return false;
+    }
+    if (keep == CB200_KEEP_ALL) return true;
+    const bool cis = (c >= row_lo[r]) && (c < row_hi[r]);
+    return (keep == CB200_KEEP_CIS) ? cis : !cis;
+  }
+};
+
+struct CountKept {
+  KeepRule rule;
+  int n;
+  __device__ __forceinline__ void operator()(int64_t, bool ok0, bool ok1, int r0, int r1, int4 q) {
+    n += (ok0 && rule(r0, q.x)) ? 1 : 0;
+    n += (ok1 && rule(r1, q.z)) ? 1 : 0;
+  }
+};
+
+__global__ void __launch_bounds__(BLOCK_THREADS)
+filter_count_kernel(const int2* __restrict__ px, const int64_t* __restrict__ indptr,
+                    const int32_t* __restrict__ tile_row, int64_t nnz, int64_t n_tiles,
+                    KeepRule rule, int32_t* __restrict__ tile_count) {
+  const int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (t >= n_tiles) return;
+  CountKept f{rule, 0};
+  walk_map_tile(px, indptr, nnz, t, tile_row[t], f);
+  int tot = warp_sum(f.n);
+  if ((threadIdx.x & 31) == 0) tile_count[t] = tot;
+}
+
+struct WriteKept {
+  KeepRule rule;
+  int64_t base;      // next output position (warp-uniform)
+  int2* px_out;
+  int32_t* row_out;
+  int32_t* tkey_out;
+  int2* tval_out;
+  __device__ __forceinline__ void emit(int64_t o, int r, int c, int v) {
+    px_out[o] = make_int2(c, v);
+    if (row_out) row_out[o] = r;
+    if (tkey_out) tkey_out[o] = c;
+    if (tval_out) tval_out[o] = make_int2(r, v);
+  }
+  __device__ __forceinline__ void operator()(int64_t, bool ok0, bool ok1, int r0, int r1, int4 q) {
+    const int lane = threadIdx.x & 31;
+    const bool k0 = ok0 && rule(r0, q.x);
+    const bool k1 = ok1 && rule(r1, q.z);
+    const unsigned b0 = __ballot_sync(0xffffffffu, k0);
+    const unsigned b1 = __ballot_sync(0xffffffffu, k1);
+    const unsigned lt = (1u << lane) - 1u;
+    int64_t o = base + __popc(b0 & lt) + __popc(b1 & lt);
+    if (k0) emit(o, r0, q.x, q.y);
+    if (k1) emit(o + (k0 ? 1 : 0), r1, q.z, q.w);
+    base += __popc(b0) + __popc(b1);
+  }
+};
+
+__global__ void __launch_bounds__(BLOCK_THREADS)
+filter_write_kernel(const int2* __restrict__ px, const int64_t* __restrict__ indptr,
+                    const int32_t* __restrict__ tile_row, int64_t nnz, int64_t n_tiles,
+                    KeepRule rule, const int64_t* __restrict__ tile_off, int2* __restrict__ px_out,
+                    int32_t* __restrict__ row_out, int32_t* __restrict__ tkey_out,
+                    int2* __restrict__ tval_out) {
+  const int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (t >= n_tiles) return;
+  WriteKept f{rule, tile_off[t], px_out, row_out, tkey_out, tval_out};
+  walk_map_tile(px, indptr, nnz, t, tile_row[t], f);
+  // pad element after the last kept pixel (total = tile_off[n_tiles])
+  if (t == n_tiles - 1 && (threadIdx.x & 31) == 0 && (f.base & 1)) px_out[f.base] = make_int2(0, 0);
+}
+
+// ---------------------------------------------------- integer marginals ----
+struct NnzSumOp {
+  typedef I64x2 T;
+  __device__ __forceinline__ I64x2 value(int, int count) const {
+    return I64x2{count != 0 ? 1 : 0, (long long)count};
+  }
+};
+
+__global__ void __launch_bounds__(BLOCK_THREADS)
+marginals_sweep_kernel(const int2* __restrict__ px, const int64_t* __restrict__ indptr,
+                       const int32_t* __restrict__ tile_row, int64_t nnz, int64_t n_tiles,
+                       I64x2* __restrict__ direct, I64x2* __restrict__ pieces) {
+  const int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (t >= n_tiles) return;
+  NnzSumOp op;
+  walk_reduce_tile<NnzSumOp, 4>(px, indptr, nnz, t, tile_row[t], op, direct, pieces);
+}
+
+// direct is laid over (nnz_out, sum_out) as scratch is not possible (interleaved
+// I64x2), so the sweep writes direct rows into pieces-side scratch `direct`.
+__global__ void marginals_finish_kernel(const int64_t* __restrict__ indptr, int64_t nnz, int n_rows,
+                                        const I64x2* __restrict__ direct,
+                                        const I64x2* __restrict__ pieces,
+                                        int64_t* __restrict__ nnz_out, int64_t* __restrict__ sum_out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  I64x2 v = row_total<I64x2>(r, indptr, nnz, direct, pieces);
+  nnz_out[r] = v.a;
+  sum_out[r] = v.b;
+}
+
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_abi_version(void) { return 1; }
+const char* cb200_last_error(void) { return g_err; }
+int cb200_set_device(int device) {
+  CB_CHECK(cudaSetDevice(device));
+  return 0;
+}
+int cb200_warp_tile(void) { return WARP_TILE; }
+
+int cb200_pack_pixels(const int64_t* bin2_id, const int32_t* count, int64_t nnz, cb200_px* px_out,
+                      void* stream) {
+  if (nnz <= 0) return 0;
+  int64_t blocks = ceil_div64(nnz, 256 * 8);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_pixels_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      bin2_id, count, nnz, reinterpret_cast<int2*>(px_out));
+  CB_LAUNCH_CHECK("pack_pixels");
+  return 0;
+}
+
+int cb200_tile_rows(const int64_t* indptr, int32_t n_rows, int64_t nnz, int32_t* tile_row,
+                    void* stream) {
+  const int64_t n_tiles = ceil_div64(nnz, WARP_TILE);
+  if (n_tiles <= 0) return 0;
+  tile_rows_kernel<<<(unsigned)ceil_div64(n_tiles, 256), 256, 0, (cudaStream_t)stream>>>(
+      indptr, n_rows, nnz, n_tiles, tile_row);
+  CB_LAUNCH_CHECK("tile_rows");
+  return 0;
+}
+
+int cb200_indptr_from_sorted(const int32_t* keys, int64_t n, int32_t n_rows, int64_t* indptr,
+                             void* stream) {
+  int64_t blocks = ceil_div64(n + 1, 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  indptr_from_sorted_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(keys, n, n_rows,
+                                                                               indptr);
+  CB_LAUNCH_CHECK("indptr_from_sorted");
+  return 0;
+}
+
+int cb200_filter_count(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
+                       int32_t n_rows, int64_t nnz, const int32_t* row_lo, const int32_t* row_hi,
+                       int32_t ndiag, int32_t keep, int32_t* tile_count, void* stream) {
+  (void)n_rows;
+  const int64_t n_tiles = ceil_div64(nnz, WARP_TILE);
+  if (n_tiles <= 0) return 0;
+  KeepRule rule{row_lo, row_hi, ndiag, keep};
+  filter_count_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0,
+                        (cudaStream_t)stream>>>(reinterpret_cast<const int2*>(px), indptr, tile_row,
+                                                nnz, n_tiles, rule, tile_count);
+  CB_LAUNCH_CHECK("filter_count");
+  return 0;
+}
+
+int cb200_filter_write(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
+                       int32_t n_rows, int64_t nnz, const int32_t* row_lo, const int32_t* row_hi,
+                       int32_t ndiag, int32_t keep, const int64_t* tile_off, cb200_px* px_out,
+                       int32_t* row_out, int32_t* tkey_out, cb200_px* tval_out, void* stream) {
+  (void)n_rows;
+  const int64_t n_tiles = ceil_div64(nnz, WARP_TILE);
+  if (n_tiles <= 0) return 0;
+  KeepRule rule{row_lo, row_hi, ndiag, keep};
+  filter_write_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0,
+                        (cudaStream_t)stream>>>(
+      reinterpret_cast<const int2*>(px), indptr, tile_row, nnz, n_tiles, rule, tile_off,
+      reinterpret_cast<int2*>(px_out), row_out, tkey_out, reinterpret_cast<int2*>(tval_out));
+  CB_LAUNCH_CHECK("filter_write");
+  return 0;
+}
+
+int cb200_marginals_i64(const cb200_copy* copy, int32_t n_rows, int64_t* nnz_out, int64_t* sum_out,
+                        int64_t* pieces, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t nnz = copy->nnz;
+  const int64_t n_tiles = ceil_div64(nnz, WARP_TILE);
+  // scratch layout: pieces[2*n_tiles] (I64x2) then direct[n_rows] (I64x2)
+  I64x2* pc = reinterpret_cast<I64x2*>(pieces);
+  I64x2* direct = pc + 2 * n_tiles;
+  if (n_tiles > 0) {
+    marginals_sweep_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0, st>>>(
+        reinterpret_cast<const int2*>(copy->px), copy->indptr, copy->tile_row, nnz, n_tiles, direct,
+        pc);
+    CB_LAUNCH_CHECK("marginals_sweep");
+  }
+  if (n_rows > 0) {
+    marginals_finish_kernel<<<(unsigned)ceil_div64(n_rows, 256), 256, 0, st>>>(
+        copy->indptr, nnz, n_rows, direct, pc, nnz_out, sum_out);
+    CB_LAUNCH_CHECK("marginals_finish");
+  }
+  return 0;
+}
+
+}  // extern "C"

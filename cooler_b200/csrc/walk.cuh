@@ -1,0 +1,147 @@
+// Row-walking building blocks shared by the ICE, filter and coarsen kernels.
+//
+// A copy of the pixel table is an array px[nnz] of int2 {other bin, count}
+// ordered by row, plus indptr[n_rows+1].  Work is split by PIXELS, not rows:
+// warp tile t owns pixels [t*WARP_TILE, (t+1)*WARP_TILE).  Rows are located by
+// walking indptr from tile_row[t] (the row holding the tile's first pixel).
+//
+//   walk_reduce_tile : deterministic warp-level segmented reduction (no atomics).
+//       Rows strictly inside the tile are written to direct[row]; the first and
+//       last row of the tile (which may continue in neighbouring tiles) are
+//       written as pieces[2t], pieces[2t+1]; row_total() reassembles a row.
+//   walk_map_tile    : calls a functor for every pixel with its row known.
+#pragma once
+#include "common.cuh"
+
+namespace cb200 {
+
+// ---- accumulator types ------------------------------------------------------
+struct I64x2 {
+  long long a, b;
+};
+__device__ __forceinline__ double acc_zero(double*) { return 0.0; }
+__device__ __forceinline__ I64x2 acc_zero(I64x2*) { return I64x2{0, 0}; }
+__device__ __forceinline__ double acc_add(double x, double y) { return x + y; }
+__device__ __forceinline__ I64x2 acc_add(I64x2 x, I64x2 y) { return I64x2{x.a + y.a, x.b + y.b}; }
+__device__ __forceinline__ double acc_wsum(double x) { return warp_sum(x); }
+__device__ __forceinline__ I64x2 acc_wsum(I64x2 x) { return I64x2{warp_sum(x.a), warp_sum(x.b)}; }
+
+// Op: struct with  typedef T;  __device__ T value(int other, int count) const;
+template <typename Op, int U>
+__device__ __forceinline__ void walk_reduce_tile(const int2* __restrict__ px,
+                                                 const int64_t* __restrict__ indptr, int64_t nnz,
+                                                 int64_t t, int row0, const Op& op,
+                                                 typename Op::T* __restrict__ direct,
+                                                 typename Op::T* __restrict__ pieces) {
+  typedef typename Op::T T;
+  const int lane = threadIdx.x & 31;
+  const int64_t p0 = t * (int64_t)WARP_TILE;
+  const int64_t p1 = min(p0 + (int64_t)WARP_TILE, nnz);
+  int row = row0;
+  int64_t row_end = indptr[row + 1];
+  T acc = acc_zero((T*)nullptr);
+  bool first = true;
+
+  for (int64_t c = p0; c < p1; c += (int64_t)CHUNK * U) {
+    int4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t pos = c + u * CHUNK + 2 * lane;
+      q[u] = (pos < p1) ? ld_stream_int4(reinterpret_cast<const int4*>(px + pos))
+                        : make_int4(0, 0, 0, 0);
+    }
+    T v0[U], v1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t pos = c + u * CHUNK + 2 * lane;
+      v0[u] = (pos < p1) ? op.value(q[u].x, q[u].y) : acc_zero((T*)nullptr);
+      v1[u] = (pos + 1 < p1) ? op.value(q[u].z, q[u].w) : acc_zero((T*)nullptr);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t cbeg = c + u * CHUNK;
+      if (cbeg >= p1) break;
+      const int64_t cend = min(cbeg + (int64_t)CHUNK, p1);
+      if (cend <= row_end) {                       // whole chunk inside the current row
+        acc = acc_add(acc, acc_add(v0[u], v1[u]));
+      } else {                                     // one or more rows end inside this chunk
+        const int64_t pos = cbeg + 2 * lane;
+        T a0 = v0[u], a1 = v1[u];
+        while (true) {
+          if (pos < row_end) { acc = acc_add(acc, a0); a0 = acc_zero((T*)nullptr); }
+          if (pos + 1 < row_end) { acc = acc_add(acc, a1); a1 = acc_zero((T*)nullptr); }
+          if (row_end >= cend) break;
+          T tot = acc_wsum(acc);
+          if (lane == 0) {
+            if (first) pieces[2 * t] = tot; else direct[row] = tot;
+          }
+          first = false;
+          acc = acc_zero((T*)nullptr);
+          const int64_t done_to = row_end;
+          do {                                     // next non-empty row
+            ++row;
+            row_end = indptr[row + 1];
+          } while (row_end == done_to);
+        }
+      }
+    }
+  }
+  T tot = acc_wsum(acc);
+  if (lane == 0) pieces[2 * t + (first ? 0 : 1)] = tot;
+}
+
+// Total of row r from the outputs of walk_reduce_tile.
+template <typename T>
+__device__ __forceinline__ T row_total(int r, const int64_t* __restrict__ indptr, int64_t nnz,
+                                       const T* __restrict__ direct,
+                                       const T* __restrict__ pieces) {
+  const int64_t a = indptr[r], b = indptr[r + 1];
+  if (a >= b) return acc_zero((T*)nullptr);
+  const int64_t ta = a / WARP_TILE, tb = (b - 1) / WARP_TILE;
+  if (ta == tb) {
+    if (a == ta * WARP_TILE) return pieces[2 * ta];
+    if (b == min((ta + 1) * (int64_t)WARP_TILE, nnz)) return pieces[2 * ta + 1];
+    return direct[r];
+  }
+  T v = (a == ta * WARP_TILE) ? pieces[2 * ta] : pieces[2 * ta + 1];
+  for (int64_t t = ta + 1; t <= tb; ++t) v = acc_add(v, pieces[2 * t]);
+  return v;
+}
+
+// F: __device__ void operator()(int64_t pos, bool ok0, bool ok1, int r0, int r1, int4 q)
+// called by all 32 lanes for every chunk (warp-collectives allowed inside).
+// Lane l sees pixels pos = chunk_begin + 2l (q.x, q.y) and pos + 1 (q.z, q.w).
+template <typename F>
+__device__ __forceinline__ void walk_map_tile(const int2* __restrict__ px,
+                                              const int64_t* __restrict__ indptr, int64_t nnz,
+                                              int64_t t, int row0, F& f) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p0 = t * (int64_t)WARP_TILE;
+  const int64_t p1 = min(p0 + (int64_t)WARP_TILE, nnz);
+  int row = row0;
+  int64_t row_end = indptr[row + 1];
+  for (int64_t cbeg = p0; cbeg < p1; cbeg += CHUNK) {
+    const int64_t cend = min(cbeg + (int64_t)CHUNK, p1);
+    const int64_t pos = cbeg + 2 * lane;
+    const bool ok0 = pos < p1, ok1 = pos + 1 < p1;
+    int4 q = ok0 ? ld_stream_int4(reinterpret_cast<const int4*>(px + pos)) : make_int4(0, 0, 0, 0);
+    int r0 = row, r1 = row;
+    if (cend > row_end) {                          // rows change inside the chunk
+      int r = row;
+      int64_t e = row_end;
+      if (ok0) {
+        while (pos >= e) { ++r; e = indptr[r + 1]; }
+        r0 = r;
+        if (ok1) while (pos + 1 >= e) { ++r; e = indptr[r + 1]; }
+        r1 = r;
+      }
+      // continue from the row of the chunk's last pixel
+      const int last_lane = (int)((cend - 1 - cbeg) >> 1);
+      row = __shfl_sync(0xffffffffu, r, last_lane);
+      row_end = indptr[row + 1];
+    }
+    f(pos, ok0, ok1, r0, r1, q);
+  }
+}
+
+}  // namespace cb200

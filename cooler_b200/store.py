@@ -1,0 +1,222 @@
+"""In-memory cooler store.
+
+``MemCooler`` exposes the part of ``cooler.Cooler`` (reference
+src/cooler/api.py:32-409) that the balancing / coarsening hot path touches, on
+top of plain numpy arrays laid out like the cooler schema (docs/schema_v3.rst):
+groups ``chroms``, ``bins``, ``pixels``, ``indexes`` plus the info attributes.
+It is the input/output object of the array-level API and of the tests (h5py /
+libhdf5 are not available in the build image); a real ``cooler.Cooler`` works
+with the same façade functions because only this protocol is used.
+"""
+from __future__ import annotations
+
+from contextlib import contextmanager
+
+import numpy as np
+
+
+class MemDataset:
+    """A numpy array with ``attrs`` (stand-in for h5py.Dataset)."""
+
+    def __init__(self, data):
+        self.data = np.asarray(data)
+        self.attrs = {}
+
+    def __getitem__(self, key):
+        return self.data[key]
+
+    def __len__(self):
+        return len(self.data)
+
+    @property
+    def dtype(self):
+        return self.data.dtype
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+    def __array__(self, dtype=None, copy=None):
+        return self.data if dtype is None else self.data.astype(dtype)
+
+
+class MemGroup(dict):
+    """dict of MemDataset / MemGroup with an ``attrs`` dict (stand-in for h5py.Group)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.attrs = {}
+
+    def __getitem__(self, path):
+        cur = self
+        for item in str(path).strip("/").split("/"):
+            if item:
+                cur = dict.__getitem__(cur, item)
+        return cur
+
+    def __contains__(self, path):
+        try:
+            self[path]
+            return True
+        except KeyError:
+            return False
+
+    def create_dataset(self, name, data=None, **_h5opts):
+        ds = MemDataset(np.array(data))
+        dict.__setitem__(self, name, ds)
+        return ds
+
+    def create_group(self, name):
+        g = MemGroup()
+        dict.__setitem__(self, name, g)
+        return g
+
+
+class _Selector:
+    """``clr.bins()[:]`` / ``clr.chroms()["name"][:]`` style access."""
+
+    def __init__(self, group, fields=None, decode=None):
+        self._g, self._fields, self._decode = group, fields, decode or {}
+
+    def _frame(self, sl):
+        import pandas as pd
+        cols = self._fields or list(self._g.keys())
+        data = {}
+        for c in cols:
+            v = self._g[c][sl]
+            if c in self._decode:
+                v = self._decode[c](v)
+            data[c] = v
+        return pd.DataFrame(data)
+
+    def __getitem__(self, key):
+        if isinstance(key, str):
+            return _Selector(self._g, [key], self._decode)._column()
+        if isinstance(key, list):
+            return _Selector(self._g, key, self._decode)
+        return self._frame(key)
+
+    def _column(self):
+        sel = self
+
+        class _Col:
+            def __getitem__(self, sl):
+                return sel._frame(sl)[sel._fields[0]]
+        return _Col()
+
+    @property
+    def dtypes(self):
+        import pandas as pd
+        return pd.Series({k: self._g[k].dtype for k in (self._fields or self._g.keys())})
+
+    def __len__(self):
+        k = next(iter(self._g.keys()))
+        return len(self._g[k])
+
+
+class MemCooler:
+    """Duck-typed ``cooler.Cooler`` over an in-memory ``MemGroup``."""
+
+    def __init__(self, root: MemGroup, filename="<memory>"):
+        self.root = root
+        self.filename = filename
+        self.uri = filename
+
+    # ---- construction ----------------------------------------------------
+    @classmethod
+    def from_arrays(cls, chromnames, chromsizes, bins_chrom, bins_start, bins_end,
+                    bin1_id, bin2_id, count, *, binsize, symmetric_upper=True, filename="<memory>",
+                    extra_pixel_columns=None):
+        bins_chrom = np.asarray(bins_chrom, dtype=np.int32)
+        n_bins = len(bins_chrom)
+        n_chroms = len(chromnames)
+        bin1_id = np.asarray(bin1_id, dtype=np.int64)
+        root = MemGroup()
+        g = root.create_group("chroms")
+        g.create_dataset("name", np.asarray(chromnames, dtype="S"))
+        g.create_dataset("length", np.asarray(chromsizes, dtype=np.int32))
+        g = root.create_group("bins")
+        g.create_dataset("chrom", bins_chrom)
+        g.create_dataset("start", np.asarray(bins_start, dtype=np.int32))
+        g.create_dataset("end", np.asarray(bins_end, dtype=np.int32))
+        g = root.create_group("pixels")
+        g.create_dataset("bin1_id", bin1_id)
+        g.create_dataset("bin2_id", np.asarray(bin2_id, dtype=np.int64))
+        g.create_dataset("count", np.asarray(count))
+        for k, v in (extra_pixel_columns or {}).items():
+            g.create_dataset(k, np.asarray(v))
+        g = root.create_group("indexes")
+        g.create_dataset("chrom_offset",
+                         np.searchsorted(bins_chrom, np.arange(n_chroms + 1)).astype(np.int64))
+        g.create_dataset("bin1_offset",
+                         np.searchsorted(bin1_id, np.arange(n_bins + 1)).astype(np.int64))
+        cnt = np.asarray(count)
+        root.attrs.update({
+            "format": "HDF5::Cooler", "format-version": 3,
+            "bin-type": "fixed" if binsize is not None else "variable",
+            "bin-size": int(binsize) if binsize is not None else None,
+            "storage-mode": "symmetric-upper" if symmetric_upper else "square",
+            "nchroms": n_chroms, "nbins": n_bins, "nnz": len(bin1_id),
+            "sum": cnt.sum().item() if len(cnt) else 0,
+        })
+        return cls(root, filename=filename)
+
+    @classmethod
+    def from_chromsizes(cls, chromnames, chromsizes, binsize, bin1_id, bin2_id, count, **kw):
+        """Uniform ``binsize`` bins over the chromosomes (util.binnify semantics)."""
+        c, s, e = [], [], []
+        for i, L in enumerate(chromsizes):
+            st = np.arange(0, int(L), int(binsize), dtype=np.int64)
+            c.append(np.full(len(st), i, np.int32))
+            s.append(st)
+            e.append(np.minimum(st + int(binsize), int(L)))
+        return cls.from_arrays(chromnames, chromsizes, np.concatenate(c), np.concatenate(s),
+                               np.concatenate(e), bin1_id, bin2_id, count, binsize=binsize, **kw)
+
+    # ---- the cooler.Cooler protocol used by the hot path -----------------
+    @property
+    def info(self):
+        return dict(self.root.attrs)
+
+    @property
+    def binsize(self):
+        return self.root.attrs.get("bin-size")
+
+    @property
+    def storage_mode(self):
+        return self.root.attrs.get("storage-mode", "symmetric-upper")
+
+    @property
+    def chromnames(self):
+        return [n.decode() if isinstance(n, bytes) else str(n) for n in self.root["chroms/name"][:]]
+
+    @property
+    def chromsizes(self):
+        import pandas as pd
+        return pd.Series(self.root["chroms/length"][:].astype(np.int64), index=self.chromnames,
+                         name="length")
+
+    def _load_dset(self, path):
+        return self.root[path][:]
+
+    @contextmanager
+    def open(self, mode="r", **kwargs):
+        yield self.root
+
+    def chroms(self, **kwargs):
+        return _Selector(self.root["chroms"],
+                         decode={"name": lambda v: np.array([x.decode() if isinstance(x, bytes) else x for x in v],
+                                                            dtype=object)})
+
+    def bins(self, **kwargs):
+        return _Selector(self.root["bins"])
+
+    def pixels(self, join=False, **kwargs):
+        if join:
+            raise NotImplementedError("MemCooler.pixels(join=True)")
+        return _Selector(self.root["pixels"])
+
+    @property
+    def shape(self):
+        n = self.root.attrs["nbins"]
+        return (n, n)

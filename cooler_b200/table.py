@@ -1,0 +1,245 @@
+"""Device-resident pixel table: the HBM layout of the hot path.
+
+A *copy* of the table is ``px[nnz]`` of 8-byte records ``{other bin, count}``
+ordered by row, plus ``indptr[n_rows+1]`` (int64) and ``tile_row[n_tiles]``
+(row of the first pixel of every warp tile).  The bin1-major copy ("CSR")
+stores ``other = bin2``; the bin2-major copy ("CSC"), built once by the
+on-device stable radix sort, stores ``other = bin1``.
+
+torch is used for device memory and streams only; every kernel is in
+``libcooler_b200.so`` (include/cooler_b200.h).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_I32 = torch.int32
+_I64 = torch.int64
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _use_device(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.NativeLibraryError("cooler_b200 runs on CUDA devices only (no CPU fallback)")
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    torch.cuda.set_device(idx)
+    _lib.call("cb200_set_device", idx)
+    return torch.device("cuda", idx)
+
+
+def warp_tile():
+    return _lib.load().cb200_warp_tile()
+
+
+def n_tiles(nnz):
+    wt = warp_tile()
+    return (int(nnz) + wt - 1) // wt
+
+
+def _new_px(nnz, device):
+    # +2 records: pad so that the 128-bit load of the last pair stays in bounds
+    return torch.empty((int(nnz) + 2, 2), dtype=_I32, device=device)
+
+
+class TableCopy:
+    """One row-ordered copy of the pixel table on the device."""
+
+    def __init__(self, px, indptr, nnz, n_rows, tile_row=None):
+        self.px, self.indptr, self.nnz, self.n_rows = px, indptr, int(nnz), int(n_rows)
+        if tile_row is None:
+            tile_row = torch.empty(max(n_tiles(nnz), 1), dtype=_I32, device=px.device)
+            _lib.call("cb200_tile_rows", _ptr(indptr), self.n_rows, self.nnz, _ptr(tile_row), _stream())
+        self.tile_row = tile_row
+
+    @property
+    def device(self):
+        return self.px.device
+
+    def c_struct(self):
+        return _lib.Copy(self.px.data_ptr(), self.indptr.data_ptr(), self.tile_row.data_ptr(), self.nnz)
+
+    def nbytes(self):
+        return self.nnz * 8 + self.indptr.numel() * 8 + self.tile_row.numel() * 4
+
+    # -- debugging / tests ---------------------------------------------------
+    def to_host(self):
+        """(row ids, other ids, counts) as numpy int64/int64/int32."""
+        ind = self.indptr.cpu().numpy()
+        px = self.px[: self.nnz].cpu().numpy()
+        rows = np.repeat(np.arange(self.n_rows, dtype=np.int64), np.diff(ind))
+        return rows, px[:, 0].astype(np.int64), px[:, 1].copy()
+
+
+def exclusive_scan_i32(x):
+    """int32[n] -> int64[n+1] exclusive prefix sums (device)."""
+    n = x.numel()
+    out = torch.empty(n + 1, dtype=_I64, device=x.device)
+    ws_bytes = _lib.load().cb200_scan_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    _lib.call("cb200_exclusive_scan_i32", _ptr(x), _ptr(out), n, _ptr(ws), ws_bytes, _stream())
+    return out
+
+
+def sort_pairs(keys, vals, key_bits):
+    """Stable sort of (int32 key, int32x2 value) by the low ``key_bits`` bits of key."""
+    n = keys.numel()
+    dev = keys.device
+    keys_out = torch.empty(n, dtype=_I32, device=dev)
+    vals_out = _new_px(n, dev)
+    if n == 0:
+        return keys_out, vals_out
+    passes = (max(key_bits, 1) + 7) // 8
+    keys_tmp = torch.empty(n if passes > 1 else 1, dtype=_I32, device=dev)
+    vals_tmp = torch.empty((n if passes > 1 else 1, 2), dtype=_I32, device=dev)
+    ws_bytes = _lib.load().cb200_sort_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.call("cb200_sort_pairs", _ptr(keys), _ptr(vals), _ptr(keys_out), _ptr(vals_out),
+              _ptr(keys_tmp), _ptr(vals_tmp), n, int(key_bits), _ptr(ws), ws_bytes, _stream())
+    return keys_out, vals_out
+
+
+def indptr_from_sorted(keys, n, n_rows):
+    out = torch.empty(n_rows + 1, dtype=_I64, device=keys.device)
+    _lib.call("cb200_indptr_from_sorted", _ptr(keys), int(n), int(n_rows), _ptr(out), _stream())
+    return out
+
+
+def key_bits_for(n_rows):
+    return max(1, int(n_rows - 1).bit_length()) if n_rows > 1 else 1
+
+
+def filter_copy(copy, row_lo, row_hi, ndiag, keep, *, want_rows=False, want_transpose=False):
+    """Stable compaction of ``copy`` by the static filter (see cb200_filter_count).
+
+    Returns (new_copy, tkey, tval); the new copy's indptr is rebuilt from the
+    kept pixels' row ids.  tkey/tval (if requested) feed the transposition sort.
+    """
+    dev = copy.device
+    nt = n_tiles(copy.nnz)
+    tile_count = torch.zeros(max(nt, 1), dtype=_I32, device=dev)
+    _lib.call("cb200_filter_count", _ptr(copy.px), _ptr(copy.indptr), _ptr(copy.tile_row),
+              copy.n_rows, copy.nnz, _ptr(row_lo), _ptr(row_hi), int(ndiag), int(keep),
+              _ptr(tile_count), _stream())
+    tile_off = exclusive_scan_i32(tile_count[:nt] if nt else tile_count[:0])
+    kept = int(tile_off[-1].item())                      # one sync per build step
+    px_out = _new_px(kept, dev)
+    rows = torch.empty(max(kept, 1), dtype=_I32, device=dev)
+    tkey = torch.empty(max(kept, 1), dtype=_I32, device=dev) if want_transpose else None
+    tval = _new_px(kept, dev) if want_transpose else None
+    _lib.call("cb200_filter_write", _ptr(copy.px), _ptr(copy.indptr), _ptr(copy.tile_row),
+              copy.n_rows, copy.nnz, _ptr(row_lo), _ptr(row_hi), int(ndiag), int(keep),
+              _ptr(tile_off), _ptr(px_out), _ptr(rows), _ptr(tkey), _ptr(tval), _stream())
+    indptr = indptr_from_sorted(rows, kept, copy.n_rows)
+    new = TableCopy(px_out, indptr, kept, copy.n_rows)
+    if want_rows:
+        new.rows = rows
+    return new, (tkey[:kept] if tkey is not None else None), tval
+
+
+def transpose_from(tkey, tval, n_rows):
+    """(key = other bin, val = {row, count}) in row-major order -> the other-major copy."""
+    n = tkey.numel()
+    keys_sorted, vals_sorted = sort_pairs(tkey, tval, key_bits_for(n_rows))
+    indptr = indptr_from_sorted(keys_sorted, n, n_rows)
+    return TableCopy(vals_sorted, indptr, n, n_rows)
+
+
+def marginals_i64(copy):
+    """(nnz_marg, sum_marg) int64 row marginals of one copy."""
+    dev = copy.device
+    n = copy.n_rows
+    nnz_out = torch.empty(n, dtype=_I64, device=dev)
+    sum_out = torch.empty(n, dtype=_I64, device=dev)
+    scratch = torch.empty((2 * n_tiles(copy.nnz) + n) * 2 + 2, dtype=_I64, device=dev)
+    cs = copy.c_struct()
+    _lib.call("cb200_marginals_i64", C.byref(cs), n, _ptr(nnz_out), _ptr(sum_out), _ptr(scratch), _stream())
+    return nnz_out, sum_out
+
+
+class PixelTable:
+    """The uploaded, unfiltered bin1-major copy plus the genome segmentation.
+
+    Built once per cooler ("h5py reads the pixel table once"); balancing with
+    different options and coarsening both start from it without touching the
+    host again.  ``row_range`` marks a shard: this table holds the stored pixels
+    of rows [row_range[0], row_range[1]) of an n_bins x n_bins matrix.
+    """
+
+    def __init__(self, raw, chrom_offset, row_range=None):
+        self.raw = raw
+        self.n_bins = raw.n_rows
+        self.chrom_offset = np.asarray(chrom_offset, dtype=np.int64)
+        self.row_range = row_range or (0, self.n_bins)
+        nb = np.diff(self.chrom_offset)
+        lo = np.repeat(self.chrom_offset[:-1], nb).astype(np.int32)
+        hi = np.repeat(self.chrom_offset[1:], nb).astype(np.int32)
+        self.row_lo = torch.from_numpy(lo).to(raw.device)
+        self.row_hi = torch.from_numpy(hi).to(raw.device)
+
+    @property
+    def device(self):
+        return self.raw.device
+
+    @property
+    def nnz(self):
+        return self.raw.nnz
+
+    @classmethod
+    def from_arrays(cls, bin1_offset, bin2_id, count, chrom_offset, device="cuda", row_range=None):
+        """Upload (host arrays or tensors; pinned memory is copied asynchronously).
+
+        ``bin1_offset`` is the cooler's ``indexes/bin1_offset`` (the CSR indptr;
+        docs/schema_v3.rst) -- bin1_id itself is never shipped to the device.
+        """
+        device = _use_device(device)
+        n_bins = len(bin1_offset) - 1
+        if n_bins >= 2**31 - 1:
+            raise ValueError("n_bins must fit int32")
+        nnz = len(bin2_id)
+
+        def dev(a, dtype):
+            t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+            if t.dtype != dtype:
+                t = t.to(dtype)
+            return t.to(device, non_blocking=True)
+
+        count_t = count if isinstance(count, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(count))
+        if count_t.dtype.is_floating_point:
+            raise NotImplementedError(
+                "cooler_b200 balances integer count columns only (float value columns are not "
+                "supported by the CUDA path yet)")
+        indptr = dev(bin1_offset, _I64)
+        bin2_d = dev(bin2_id, _I64)
+        count_d = dev(count_t, _I32)
+        px = _new_px(nnz, device)
+        _lib.call("cb200_pack_pixels", _ptr(bin2_d), _ptr(count_d), nnz, _ptr(px), _stream())
+        raw = TableCopy(px, indptr, nnz, n_bins)
+        return cls(raw, chrom_offset, row_range=row_range)
+
+    @classmethod
+    def from_cooler(cls, clr, device="cuda"):
+        """Read the pixel table of a ``cooler.Cooler``-like object once.
+
+        Protocol used (reference: src/cooler/parallel.py:289-304, _balance.py:141-142):
+        ``clr.open('r')`` -> group with ``pixels/bin2_id``, ``pixels/count``;
+        ``clr._load_dset('indexes/chrom_offset' | 'indexes/bin1_offset')``.
+        """
+        chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
+        bin1_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
+        with clr.open("r") as grp:
+            bin2 = grp["pixels"]["bin2_id"][:]
+            count = grp["pixels"]["count"][:]
+        return cls.from_arrays(bin1_offset, bin2, count, chrom_offset, device=device)

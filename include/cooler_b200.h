@@ -1,0 +1,180 @@
+/*
+ * cooler_b200 -- C ABI of the B200-native (sm_100a) ICE balancing + coarsening
+ * hot path of open2c/cooler.  Shared library: cooler_b200/libcooler_b200.so.
+ *
+ * The reference (open2c/cooler v0.10.4) is pure Python and has no FFI; the
+ * entry points below are what a binding for its hot path would call.  Each one
+ * cites the reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
+ *     calls are asynchronous on that stream and never synchronise;
+ *   - return value 0 = success, otherwise a cudaError_t (or -1 for argument
+ *     errors); cb200_last_error() returns a thread-local description;
+ *   - the caller owns every buffer (in Python: torch tensors); the library
+ *     allocates nothing;
+ *   - pixel copies are arrays of cb200_px {other, count} (8 bytes), 16-byte
+ *     aligned and padded to an even number of elements;
+ *   - a "warp tile" is cb200_warp_tile() consecutive pixels of one copy;
+ *     n_tiles = ceil(nnz / warp_tile).
+ */
+#ifndef COOLER_B200_H
+#define COOLER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { int32_t other; int32_t count; } cb200_px;
+
+/* ---- library ---------------------------------------------------------- */
+int         cb200_abi_version(void);
+const char* cb200_last_error(void);
+int         cb200_set_device(int device);
+int         cb200_warp_tile(void);
+
+/* ---- primitives ------------------------------------------------------- */
+/* out[0..n] = exclusive prefix sum of in[0..n-1] (out has n+1 entries). */
+size_t cb200_scan_workspace_bytes(int64_t n);
+int cb200_exclusive_scan_i32(const int32_t* in, int64_t* out, int64_t n,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Stable LSD radix sort of (key, 8-byte value) pairs on the low `key_bits`
+ * bits of the key.  Result lands in keys_out/vals_out; *_tmp are scratch of
+ * the same size.  Replaces nothing in the reference directly: it builds the
+ * transposed (bin2-major) copy that the reference re-derives every pass with
+ * np.bincount(bin2_id) (src/cooler/_balance.py:63-69), and is the sort of the
+ * groupby(sort=True) in src/cooler/_reduce.py:616-620. */
+size_t cb200_sort_workspace_bytes(int64_t n);
+int cb200_sort_pairs(const int32_t* keys_in, const cb200_px* vals_in,
+                     int32_t* keys_out, cb200_px* vals_out,
+                     int32_t* keys_tmp, cb200_px* vals_tmp,
+                     int64_t n, int key_bits,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- pixel table build (replaces parallel.chunkgetter re-reading the file
+ *      every pass, src/cooler/parallel.py:276-304, and the per-chunk filter
+ *      functions _zero_diags/_zero_trans/_zero_cis, src/cooler/_balance.py:34-54,
+ *      which here are applied ONCE by compaction) --------------------------- */
+/* (bin2_id int64, count int32) -> packed px {bin2, count}. */
+int cb200_pack_pixels(const int64_t* bin2_id, const int32_t* count, int64_t nnz,
+                      cb200_px* px_out, void* stream);
+/* tile_row[t] = row that contains pixel t*warp_tile (n_tiles entries). */
+int cb200_tile_rows(const int64_t* indptr, int32_t n_rows, int64_t nnz,
+                    int32_t* tile_row, void* stream);
+/* indptr[r] = first position p with keys[p] >= r, r = 0..n_rows (keys sorted). */
+int cb200_indptr_from_sorted(const int32_t* keys, int64_t n, int32_t n_rows,
+                             int64_t* indptr, void* stream);
+
+/* Static pixel filter.  A pixel (row r, other c) is KEPT iff
+ *   !(ndiag > 0 && |r - c| < ndiag)                       (_zero_diags)
+ *   && (keep == CB200_KEEP_ALL
+ *       || (keep == CB200_KEEP_CIS   &&  row_lo[r] <= c < row_hi[r])   (_zero_trans)
+ *       || (keep == CB200_KEEP_TRANS && !(row_lo[r] <= c < row_hi[r])))(_zero_cis)
+ * where [row_lo[r], row_hi[r]) is the bin range of r's chromosome. */
+enum { CB200_KEEP_ALL = 0, CB200_KEEP_CIS = 1, CB200_KEEP_TRANS = 2 };
+int cb200_filter_count(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
+                       int32_t n_rows, int64_t nnz,
+                       const int32_t* row_lo, const int32_t* row_hi, int32_t ndiag, int32_t keep,
+                       int32_t* tile_count, void* stream);
+/* Second pass: writes kept pixels, order preserved, at tile_off[t] + rank.
+ * Optional outputs (NULL to skip): row_out[q] = row of kept pixel q;
+ * tkey_out[q] = other, tval_out[q] = {row, count} (input of the transposition sort). */
+int cb200_filter_write(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
+                       int32_t n_rows, int64_t nnz,
+                       const int32_t* row_lo, const int32_t* row_hi, int32_t ndiag, int32_t keep,
+                       const int64_t* tile_off,
+                       cb200_px* px_out, int32_t* row_out, int32_t* tkey_out, cb200_px* tval_out,
+                       void* stream);
+
+/* ---- marginals -------------------------------------------------------- */
+/* One copy of the table as the row-walking kernels see it. */
+typedef struct {
+  const cb200_px* px;        /* [nnz] (+pad) */
+  const int64_t*  indptr;    /* [n_rows + 1] */
+  const int32_t*  tile_row;  /* [n_tiles] */
+  int64_t         nnz;
+} cb200_copy;
+
+/* Integer marginals of one copy (prefilter passes A and B of balance_cooler,
+ * src/cooler/_balance.py:375-393): for every row r
+ *   nnz_out[r] = #{p in row r : count != 0}     (_binarize then _marginalize)
+ *   sum_out[r] = sum of count over row r
+ * exact in int64.  The marginal of the reference is row(CSR) + row(CSC).
+ * scratch: [(2 * n_tiles + n_rows) * 2] int64.  Outputs are fully written. */
+int cb200_marginals_i64(const cb200_copy* copy, int32_t n_rows,
+                        int64_t* nnz_out, int64_t* sum_out, int64_t* scratch, void* stream);
+
+/* ---- ICE iteration (replaces the PASS C map-reduce + the O(n_bins) numpy
+ *      update of _balance_genomewide/_cisonly/_transonly,
+ *      src/cooler/_balance.py:72-260) ------------------------------------- */
+typedef struct {
+  cb200_copy csr, csc;       /* bin1-major and bin2-major copies (static filters applied) */
+  int32_t  n_bins;
+  int32_t  n_segs;           /* 1 (genome-wide / trans) or n_chroms (cis_only) */
+  const int32_t* seg_offset; /* [n_segs + 1] bin range of each independently balanced segment */
+  /* block table of the per-bin kernels: block b covers bins [blk_lo[b], blk_hi[b]) of segment blk_seg[b] */
+  int32_t  n_blocks;
+  const int32_t* blk_seg; const int32_t* blk_lo; const int32_t* blk_hi;
+  const int32_t* seg_blk_offset;  /* [n_segs + 1] blocks of each segment */
+  double*  bias;             /* [n_bins] in/out */
+  const double* cweights;    /* [n_bins] or NULL (trans_only: 1/(1 - nbins_chrom/n_bins), _balance.py:214-220) */
+  double*  w;                /* [n_bins] gathered vector = bias * cweights (may alias bias when cweights == NULL) */
+  /* sweep outputs (scratch) */
+  double*  direct_row; double* pieces_row;   /* [n_bins], [2 * n_tiles(csr)] */
+  double*  direct_col; double* pieces_col;   /* [n_bins], [2 * n_tiles(csc)] */
+  double*  s;                /* [n_bins] per-bin sum  sum_j w_j x_ij  (row + column part); allreduced across ranks */
+  double*  marg;             /* [n_bins] scratch */
+  double*  blk_sum; double* blk_cnt; double* blk_dev;  /* [n_blocks] scratch */
+  /* per-segment state */
+  double*  seg_mean; double* seg_nnz;        /* [n_segs] scratch */
+  double*  seg_scale; double* seg_var;       /* [n_segs] out: nzmarg.mean() and nzmarg.var() of the last pass */
+  int32_t* seg_iters;        /* [n_segs] out: number of "variance is" passes */
+  int32_t* seg_done;         /* [n_segs] out: 1 = converged or empty */
+  int32_t* seg_empty;        /* [n_segs] out: 1 = no nonzero marginal (reference sets bias to NaN) */
+  int32_t* all_done;         /* [1] out: every segment done -> later launches are no-ops */
+  double*  var_hist;         /* [max_iters * n_segs] variance per pass (NaN where not run) or NULL */
+  double   tol;
+  int32_t  max_iters;
+} cb200_ice;
+
+/* K3: both marginal sweeps (CSR rows, CSC columns), one launch.  No-op once *all_done. */
+int cb200_ice_sweep(const cb200_ice* st, void* stream);
+/* s[i] = rowpart(i) + colpart(i) -- the vector ranks all-reduce.  No-op once *all_done. */
+int cb200_ice_combine(const cb200_ice* st, void* stream);
+/* K4: marg = w*s, per-segment nonzero mean/variance, bias /= marg/mean,
+ * convergence flags, iteration counters.  `iter` = 0-based index of this pass. */
+int cb200_ice_update(const cb200_ice* st, int32_t iter, void* stream);
+
+/* ---- coarsen (replaces CoolerCoarsener._aggregate's join + pandas
+ *      groupby(sort=True).sum(), src/cooler/_reduce.py:582-620) ------------ */
+/* Fused bin remap of one CSR copy: for every pixel (r, c, v)
+ *   key_out = bin_map[c], val_out = {bin_map[r], v}   (sort input). */
+int cb200_coarsen_remap(const cb200_copy* csr, int32_t n_rows, const int32_t* bin_map,
+                        int32_t* key_out, cb200_px* val_out, void* stream);
+/* Reduce-by-key over a stream sorted so that equal (key, val.other) pairs are
+ * adjacent.  Pass 1 counts run heads per tile of cb200_warp_tile() elements. */
+int cb200_runs_count(const int32_t* keys, const cb200_px* vals, int64_t n,
+                     int32_t* tile_count, void* stream);
+/* Pass 2 writes one element per run at tile_off[t] + rank: key, {other, sum}
+ * (swap != 0: key_out = other, val_out = {key, sum} -- the input of the second
+ * sort).  Sums are accumulated in int64; *overflow is set to 1 if any sum does
+ * not fit int32 (val_out.count then holds the low 32 bits; sum64_out, if not
+ * NULL, the exact sums). */
+int cb200_runs_write(const int32_t* keys, const cb200_px* vals, int64_t n,
+                     const int64_t* tile_off, int32_t swap,
+                     int32_t* key_out, cb200_px* val_out, int64_t* sum64_out,
+                     int32_t* overflow, void* stream);
+/* (bin1', val={bin2', v}) sorted by (bin1', bin2') -> bin1_id/bin2_id int64 + count,
+ * the ContactBinner chunk layout (src/cooler/create/_ingest.py:507-528). */
+int cb200_unpack_pixels(const int32_t* bin1, const cb200_px* val, int64_t n,
+                        int64_t* bin1_out, int64_t* bin2_out, int32_t* count_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COOLER_B200_H */

@@ -1,0 +1,160 @@
+"""Parity of the CUDA ICE path (through the C ABI) with the golden vectors of
+the unmodified reference and with the oracle.  Bar (BASELINE.json north_star):
+filter masks and iteration counts bit-exact, bias within 1e-9 relative."""
+import logging
+import warnings
+
+import numpy as np
+import pytest
+
+from tests import _golden
+
+pytestmark = pytest.mark.gpu
+
+BAL, META = _golden.balance_golden()
+RTOL = 1e-9
+
+
+def _mem_cooler(t):
+    from cooler_b200 import MemCooler
+    return MemCooler.from_arrays(t["chromnames"], t["chromsizes"], t["bins_chrom"], t["bins_start"],
+                                 t["bins_end"], t["bin1_id"], t["bin2_id"], t["count"],
+                                 binsize=int(t["binsize"]))
+
+
+class _Count(logging.Handler):
+    def __init__(self):
+        super().__init__(level=logging.INFO)
+        self.lines = []
+
+    def emit(self, record):
+        self.lines.append(record.getMessage())
+
+
+def _check_stats(got, want, cis):
+    for k in ("tol", "min_nnz", "min_count", "mad_max", "cis_only", "ignore_diags", "divisive_weights"):
+        assert got[k] == want[k], k
+    for k in ("scale", "var"):
+        g = np.atleast_1d(np.asarray(got[k], dtype=float))
+        w = np.array([np.nan if x is None else x for x in np.atleast_1d(want[k])], dtype=float)
+        np.testing.assert_allclose(g, w, rtol=1e-9, atol=0, equal_nan=True, err_msg=k)
+    np.testing.assert_array_equal(np.atleast_1d(got["converged"]), np.atleast_1d(want["converged"]))
+
+
+@pytest.mark.parametrize("key", sorted(META))
+def test_balance_matches_reference_golden(key):
+    import cooler_b200
+    src, case = key.split("/")
+    clr = _mem_cooler(_golden.table_of(src))
+    kw = dict(META[key]["kwargs"])
+    if case == "x0":
+        kw["x0"] = BAL["gm/x0_input"].copy()
+    lg = logging.getLogger("cooler")
+    h = _Count()
+    lg.addHandler(h)
+    old = lg.level
+    lg.setLevel(logging.INFO)
+    try:
+        with warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            bias, stats = cooler_b200.balance_cooler(clr, **kw)
+    finally:
+        lg.removeHandler(h)
+        lg.setLevel(old)
+    warned = any(issubclass(x.category, cooler_b200.ConvergenceWarning) for x in w)
+    want = BAL[key]
+    # masks bit-exact
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    # iteration counts bit-exact ("variance is" log lines, as the reference logs them)
+    n_var = sum(1 for m in h.lines if m.startswith("variance is"))
+    assert n_var == sum(META[key]["passes"])
+    assert warned == META[key]["warned"]
+    # bias within 1e-9 relative
+    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
+    _check_stats(stats, META[key]["stats"], kw.get("cis_only", False))
+    if case == "x0":
+        assert bias is kw["x0"]          # the reference mutates and returns x0 (_balance.py:368-370)
+
+
+def _synthetic(seed, n_per_chrom, density):
+    rng = np.random.default_rng(seed)
+    n = int(sum(n_per_chrom))
+    chrom_offset = np.r_[0, np.cumsum(n_per_chrom)].astype(np.int64)
+    b = rng.lognormal(0, 0.3, n)
+    b[rng.random(n) < 0.02] *= 0.01
+    nnz_target = int(density * n * n / 2)
+    i = rng.integers(0, n, nnz_target)
+    d = np.minimum((rng.pareto(0.7, nnz_target) * 3).astype(np.int64), n - 1)
+    far = rng.random(nnz_target) < 0.3
+    j = np.where(far, rng.integers(0, n, nnz_target), np.minimum(i + d, n - 1))
+    i, j = np.minimum(i, j), np.maximum(i, j)
+    key = np.unique(i.astype(np.int64) * n + j)
+    b1, b2 = key // n, key % n
+    cnt = (1 + rng.poisson(30 * b[b1] * b[b2] / (1 + np.abs(b1 - b2)) ** 0.5)).astype(np.int32)
+    return b1, b2, cnt, chrom_offset
+
+
+@pytest.mark.parametrize("mode", ["gw", "cis", "trans"])
+@pytest.mark.parametrize("seed,n_per_chrom,density", [(11, [3000, 2500, 40, 1800, 1], 0.05),
+                                                      (12, [20000, 15000, 9000], 0.004)])
+def test_balance_matches_oracle_synthetic(mode, seed, n_per_chrom, density):
+    """Sizes the oracle finishes in seconds; rows from empty to tens of thousands of pixels."""
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    from oracle import ice_numpy
+    b1, b2, cnt, chrom_offset = _synthetic(seed, n_per_chrom, density)
+    n = int(chrom_offset[-1])
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    kw = dict(cis_only=(mode == "cis"), trans_only=(mode == "trans"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want, wstats, wpasses, wwarned = ice_numpy.balance_arrays(
+            dict(bin1_id=b1, bin2_id=b2, count=cnt), chrom_offset, bin1_offset,
+            return_passes=True, **kw)
+        tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
+        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, **kw)
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    assert info["passes"] == wpasses
+    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
+    np.testing.assert_allclose(np.atleast_1d(stats["var"]), np.atleast_1d(wstats["var"]), rtol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(np.atleast_1d(stats["scale"]), np.atleast_1d(wstats["scale"]), rtol=1e-9, equal_nan=True)
+
+
+def test_balance_is_deterministic():
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    b1, b2, cnt, chrom_offset = _synthetic(5, [5000, 3000], 0.02)
+    n = int(chrom_offset[-1])
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    outs = []
+    for _ in range(2):
+        tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
+        outs.append(cooler_b200.balance_table(tab)[0])
+    np.testing.assert_array_equal(outs[0], outs[1])       # bit-identical run to run
+
+
+def test_store_writes_weight_column():
+    import cooler_b200
+    clr = _mem_cooler(_golden.gm12878())
+    bias, stats = cooler_b200.balance_cooler(clr, store=True, store_name="weight")
+    with clr.open("r") as grp:
+        np.testing.assert_array_equal(grp["bins"]["weight"][:], bias)
+        assert grp["bins"]["weight"].attrs["converged"]
+
+
+def test_flat_marginals_property():
+    """The reference's own test (tests/test_balance.py:13-44) re-targeted at the CUDA path."""
+    import cooler_b200
+    t = _golden.gm12878()
+    clr = _mem_cooler(t)
+    tol = 1e-2
+    bias, stats = cooler_b200.balance_cooler(clr, ignore_diags=1, min_nnz=10, tol=tol)
+    n = len(bias)
+    m = np.zeros((n, n))
+    m[t["bin1_id"], t["bin2_id"]] = t["count"]
+    m = m + np.triu(m, 1).T
+    np.fill_diagonal(m, 0)
+    mask = np.isnan(bias)
+    w = np.where(mask, 0, bias)
+    marg = (m * w[:, None] * w[None, :]).sum(axis=0)[~mask]
+    assert np.var(marg) < tol

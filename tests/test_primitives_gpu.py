@@ -1,0 +1,86 @@
+"""GPU primitives (scan, stable radix sort, filters, transposition, integer
+marginals) against numpy, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _table(n_bins, nnz_target, seed, chrom_offset=None):
+    rng = np.random.default_rng(seed)
+    i = rng.integers(0, n_bins, nnz_target)
+    j = rng.integers(0, n_bins, nnz_target)
+    i, j = np.minimum(i, j), np.maximum(i, j)
+    key = np.unique(i.astype(np.int64) * n_bins + j)
+    b1, b2 = key // n_bins, key % n_bins
+    cnt = rng.integers(0, 50, len(b1)).astype(np.int32)     # includes stored zeros
+    ind = np.searchsorted(b1, np.arange(n_bins + 1)).astype(np.int64)
+    if chrom_offset is None:
+        chrom_offset = np.array([0, n_bins // 3, n_bins // 3 + 1, n_bins])
+    return b1, b2, cnt, ind, np.asarray(chrom_offset)
+
+
+@pytest.mark.parametrize("n", [0, 1, 5, 2048, 2049, 100_003, 5_000_000])
+def test_exclusive_scan(n):
+    from cooler_b200 import table as T
+    T._use_device("cuda")
+    rng = np.random.default_rng(n)
+    x = rng.integers(0, 1000, n).astype(np.int32)
+    out = T.exclusive_scan_i32(torch.from_numpy(x).cuda()).cpu().numpy()
+    want = np.r_[0, np.cumsum(x.astype(np.int64))]
+    np.testing.assert_array_equal(out, want)
+
+
+@pytest.mark.parametrize("n,bits", [(1, 1), (31, 3), (4096, 8), (4097, 9), (200_000, 15),
+                                    (1_000_003, 22), (300_000, 31)])
+def test_sort_pairs_stable(n, bits):
+    from cooler_b200 import table as T
+    T._use_device("cuda")
+    rng = np.random.default_rng(bits)
+    keys = rng.integers(0, 2 ** bits if bits < 31 else 2 ** 31 - 1, n).astype(np.int32)
+    vals = np.stack([np.arange(n, dtype=np.int32), rng.integers(0, 9, n).astype(np.int32)], 1)
+    ko, vo = T.sort_pairs(torch.from_numpy(keys).cuda(), torch.from_numpy(vals).cuda(), bits)
+    order = np.argsort(keys, kind="stable")
+    np.testing.assert_array_equal(ko.cpu().numpy(), keys[order])
+    np.testing.assert_array_equal(vo[:n].cpu().numpy(), vals[order])
+
+
+@pytest.mark.parametrize("n_bins,nnz,seed", [(50, 300, 0), (3000, 200_000, 1), (100_000, 150_000, 2),
+                                             (7, 0, 3), (2500, 1_000_000, 4)])
+@pytest.mark.parametrize("ndiag,keep", [(0, 0), (2, 0), (1, 1), (3, 2)])
+def test_filter_transpose_marginals(n_bins, nnz, seed, ndiag, keep):
+    from cooler_b200 import table as T
+    b1, b2, cnt, ind, chrom_offset = _table(n_bins, nnz, seed)
+    tab = T.PixelTable.from_arrays(ind, b2, cnt, chrom_offset)
+    r, c, v = tab.raw.to_host()
+    np.testing.assert_array_equal(r, b1), np.testing.assert_array_equal(c, b2), np.testing.assert_array_equal(v, cnt)
+
+    chrom = np.repeat(np.arange(len(chrom_offset) - 1), np.diff(chrom_offset))
+    cis = chrom[b1] == chrom[b2]
+    m = np.ones(len(b1), bool)
+    if ndiag:
+        m &= np.abs(b1 - b2) >= ndiag
+    if keep == 1:
+        m &= cis
+    elif keep == 2:
+        m &= ~cis
+    csr, tkey, tval = T.filter_copy(tab.raw, tab.row_lo, tab.row_hi, ndiag, keep, want_transpose=True)
+    r, c, v = csr.to_host()
+    np.testing.assert_array_equal(r, b1[m]), np.testing.assert_array_equal(c, b2[m])
+    np.testing.assert_array_equal(v, cnt[m])
+    np.testing.assert_array_equal(csr.indptr.cpu().numpy(), np.searchsorted(b1[m], np.arange(n_bins + 1)))
+
+    csc = T.transpose_from(tkey, tval, n_bins)
+    r, c, v = csc.to_host()          # rows of the CSC copy are bin2, 'other' is bin1
+    order = np.lexsort((b1[m], b2[m]))
+    np.testing.assert_array_equal(r, b2[m][order]), np.testing.assert_array_equal(c, b1[m][order])
+    np.testing.assert_array_equal(v, cnt[m][order])
+
+    for copy, rows in ((csr, b1[m]), (csc, b2[m][order])):
+        vals = cnt[m] if copy is csr else cnt[m][order]
+        nnz_m, sum_m = T.marginals_i64(copy)
+        np.testing.assert_array_equal(nnz_m.cpu().numpy(),
+                                      np.bincount(rows, weights=(vals != 0), minlength=n_bins).astype(np.int64))
+        np.testing.assert_array_equal(sum_m.cpu().numpy(),
+                                      np.bincount(rows, weights=vals, minlength=n_bins).astype(np.int64))
