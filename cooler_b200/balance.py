@@ -146,11 +146,31 @@ class IceState:
         self.prob = prob
         self.flag_host = torch.zeros(1, dtype=_I32).pin_memory() if torch.cuda.is_available() else None
         self.launches = 0
+        self.sweep_events = None          # list of (start, end) CUDA events per pass when profiling
+
+    def reset(self, bias0):
+        """Back to the initial state (same resident copies): lets a bench repeat the loop."""
+        t = self.t
+        t["bias"].copy_(torch.from_numpy(np.ascontiguousarray(bias0, dtype=np.float64)), non_blocking=True)
+        if t["cweights"] is not None:
+            torch.mul(t["bias"], t["cweights"], out=t["w"])
+        for k in ("seg_iters", "seg_done", "seg_empty", "all_done"):
+            t[k].zero_()
+        t["seg_scale"].fill_(1.0)
+        t["seg_var"].fill_(float("nan"))
+        t["var_hist"].fill_(float("nan"))
 
     def one_pass(self, it):
         """sweep (K3) -> combine -> [allreduce] -> update (K4).  Asynchronous."""
         st, stream = C.byref(self.st), _stream()
-        _lib.call("cb200_ice_sweep", st, stream)
+        if self.sweep_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.call("cb200_ice_sweep", st, stream)
+            e1.record()
+            self.sweep_events.append((e0, e1))
+        else:
+            _lib.call("cb200_ice_sweep", st, stream)
         _lib.call("cb200_ice_combine", st, stream)
         _allreduce(self.t["s"], self.prob.group)
         _lib.call("cb200_ice_update", st, int(it), stream)

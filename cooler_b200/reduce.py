@@ -1,0 +1,345 @@
+"""Coarsening / zoomify on B200 -- mirrors open2c/cooler v0.10.4
+``src/cooler/_reduce.py`` (``CoolerCoarsener``, ``coarsen_cooler``,
+``zoomify_cooler`` and the resolution planners).
+
+The reference re-bins every pixel chunk by joining it with the bin table and
+running a pandas ``groupby([bin1_id, bin2_id], sort=True).sum()``
+(_reduce.py:582-620).  Here one level is: fused bin-remap kernel -> stable
+radix sort by bin2' -> reduce-by-key -> stable radix sort by bin1'
+(csrc/coarsen.cu), all on the device-resident table; the result is again a
+``PixelTable`` so a zoomify chain (and per-level balancing) never leaves HBM.
+The bin id map is the closed form of the reference's coordinate arithmetic:
+``new_id = new_chrom_offset[c] + (old_id - old_chrom_offset[c]) // factor``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .store import MemCooler
+from .table import (PixelTable, TableCopy, _ptr, _stream, _use_device, exclusive_scan_i32,
+                    indptr_from_sorted, key_bits_for, n_tiles, sort_pairs)
+
+__all__ = ["CoolerCoarsener", "coarsen_cooler", "zoomify_cooler", "coarsen_table",
+           "get_multiplier_sequence", "preferred_sequence", "ZOOMS_4DN", "get_quadtree_depth"]
+
+# Resolutions of the 4DN multires standard (_reduce.py:30-44).
+ZOOMS_4DN = [1000, 2000, 5000, 10000, 25000, 50000, 100000, 250000, 500000,
+             1000000, 2500000, 5000000, 10000000]
+
+_I32, _I64 = torch.int32, torch.int64
+
+
+# --------------------------------------------------------------------------
+# host-side planning (pure integer logic)
+# --------------------------------------------------------------------------
+def coarsen_chrom_offset(chrom_offset, factor):
+    """New ``chrom_offset``: each chromosome keeps ceil(n_bins_chrom / factor) bins."""
+    nb = np.diff(np.asarray(chrom_offset, dtype=np.int64))
+    return np.r_[0, np.cumsum(-(-nb // factor))].astype(np.int64)
+
+
+def coarsen_bin_map(chrom_offset, factor):
+    """int32 map old bin id -> new bin id (closed form of _reduce.py:597-614)."""
+    chrom_offset = np.asarray(chrom_offset, dtype=np.int64)
+    new_off = coarsen_chrom_offset(chrom_offset, factor)
+    nb = np.diff(chrom_offset)
+    old = np.arange(chrom_offset[-1], dtype=np.int64)
+    start = np.repeat(chrom_offset[:-1], nb)
+    return (np.repeat(new_off[:-1], nb) + (old - start) // factor).astype(np.int32), new_off
+
+
+def coarsen_bins(bins_chrom, bins_start, bins_end, chromsizes, factor):
+    """New bin table (semantics of ``CoolerCoarsener.coarsen_bins``, _reduce.py:563-580):
+    per chromosome every ``factor``-th bin start; the end is the end of the last
+    pooled bin, or the chromosome length for a trailing partial group."""
+    bins_chrom = np.asarray(bins_chrom)
+    bins_start = np.asarray(bins_start, dtype=np.int64)
+    bins_end = np.asarray(bins_end, dtype=np.int64)
+    n_chroms = len(chromsizes)
+    off = np.searchsorted(bins_chrom, np.arange(n_chroms + 1))
+    cs, ss, es = [], [], []
+    for c in range(n_chroms):
+        lo, hi = off[c], off[c + 1]
+        if hi == lo:
+            continue
+        s = bins_start[lo:hi:factor]
+        e = bins_end[lo + factor - 1:hi:factor]
+        if len(e) < len(s):
+            e = np.append(e, int(chromsizes[c]))
+        cs.append(np.full(len(s), c, dtype=np.int32))
+        ss.append(s)
+        es.append(e)
+    if not cs:
+        z = np.zeros(0, dtype=np.int64)
+        return z.astype(np.int32), z, z
+    return np.concatenate(cs), np.concatenate(ss), np.concatenate(es)
+
+
+def _prune_edges(edges, maxlen):
+    """Thin a partition of 0..nnz to pieces of about ``maxlen``
+    (role of ``_greedy_prune_partition``, _reduce.py:310-320)."""
+    edges = np.asarray(edges, dtype=np.int64)
+    total = int(edges[-1])
+    cuts = list(range(0, total, max(int(maxlen), 1))) + [total]
+    idx = np.unique(np.searchsorted(edges, cuts))
+    return edges[idx]
+
+
+def get_quadtree_depth(chromsizes, base_binsize, bins_per_tile):
+    """Zoom levels needed to coarsen down to a single tile (_reduce.py:323-347)."""
+    tile_bp = bins_per_tile * base_binsize
+    n_tiles_ = math.ceil(sum(chromsizes) / tile_bp)
+    return math.ceil(np.log2(n_tiles_))
+
+
+def preferred_sequence(start, stop, style="nice"):
+    """1-2-5 ("nice") or doubling ("binary") progression from ``start`` up to
+    ``stop`` inclusive (_reduce.py:382-440)."""
+    if start > stop:
+        return []
+    if style not in ("nice", "binary"):
+        raise ValueError(f"Expected style value of 'binary' or 'nice'; got '{style}'.")
+    seq, cur = [], int(start)
+    if style == "binary":
+        while cur <= stop:
+            seq.append(cur)
+            cur *= 2
+        return seq
+    decade = int(start)
+    while True:
+        for m in (1, 2, 5):
+            v = decade * m
+            if v > stop:
+                return seq
+            seq.append(v)
+        decade *= 10
+
+
+def get_multiplier_sequence(resolutions, bases=None):
+    """For each target resolution pick the largest smaller resolution that divides it
+    (_reduce.py:443-498).  Returns (resn, pred, mult) arrays; pred == -1 marks a base."""
+    bases = {min(resolutions)} if bases is None else set(bases)
+    resn = np.array(sorted(bases.union(resolutions)))
+    pred = np.full(len(resn), -1, dtype=int)
+    mult = np.full(len(resn), -1, dtype=int)
+    for i in range(len(resn) - 1, -1, -1):
+        for p in range(i - 1, -1, -1):
+            if resn[i] % resn[p] == 0:
+                pred[i], mult[i] = p, resn[i] // resn[p]
+                break
+    for i, p in enumerate(pred):
+        if p == -1 and resn[i] not in bases:
+            raise ValueError(
+                f"Resolution {resn[i]} cannot be derived from the base resolutions: {bases}.")
+    return resn, pred, mult
+
+
+# --------------------------------------------------------------------------
+# device path
+# --------------------------------------------------------------------------
+def coarsen_table(table: PixelTable, factor: int):
+    """Coarsen a device-resident table by ``factor``.  Returns (new PixelTable, bin1' ids).
+
+    The new table's raw copy is sorted by (bin1', bin2') and duplicate-free, with
+    counts summed (int64 accumulation; OverflowError if a sum leaves int32).
+    """
+    factor = int(factor)
+    assert factor > 1
+    dev = _use_device(table.device)
+    csr = table.raw
+    bin_map, new_off = coarsen_bin_map(table.chrom_offset, factor)
+    n_new = int(new_off[-1])
+    bits = key_bits_for(n_new)
+    bin_map_d = torch.from_numpy(bin_map).to(dev)
+    n = csr.nnz
+    key = torch.empty(max(n, 1), dtype=_I32, device=dev)
+    val = torch.empty((n + 2, 2), dtype=_I32, device=dev)
+    cs = csr.c_struct()
+    _lib.call("cb200_coarsen_remap", C.byref(cs), csr.n_rows, _ptr(bin_map_d), _ptr(key), _ptr(val), _stream())
+    ks, vs = sort_pairs(key[:n], val, bits)
+    del key, val
+    nt = n_tiles(n)
+    tile_count = torch.zeros(max(nt, 1), dtype=_I32, device=dev)
+    _lib.call("cb200_runs_count", _ptr(ks), _ptr(vs), n, _ptr(tile_count), _stream())
+    tile_off = exclusive_scan_i32(tile_count[:nt])
+    n_out = int(tile_off[-1].item())
+    k2 = torch.empty(max(n_out, 1), dtype=_I32, device=dev)
+    v2 = torch.empty((n_out + 2, 2), dtype=_I32, device=dev)
+    overflow = torch.zeros(1, dtype=_I32, device=dev)
+    _lib.call("cb200_runs_write", _ptr(ks), _ptr(vs), n, _ptr(tile_off), 1, _ptr(k2), _ptr(v2),
+              C.c_void_p(0), _ptr(overflow), _stream())
+    del ks, vs
+    k3, v3 = sort_pairs(k2[:n_out], v2, bits)
+    del k2, v2
+    if int(overflow.item()):
+        raise OverflowError("coarsened count does not fit int32")
+    indptr = indptr_from_sorted(k3, n_out, n_new)
+    new_raw = TableCopy(v3, indptr, n_out, n_new)
+    return PixelTable(new_raw, new_off), k3
+
+
+def table_to_host(table: PixelTable, bin1_ids=None):
+    """(bin1_id int64, bin2_id int64, count int32) host arrays of a table's raw copy."""
+    raw = table.raw
+    n = raw.nnz
+    dev = raw.device
+    if bin1_ids is None:
+        ind = raw.indptr
+        bin1_ids = torch.repeat_interleave(torch.arange(raw.n_rows, device=dev, dtype=_I32),
+                                           (ind[1:] - ind[:-1]))
+    b1 = torch.empty(n, dtype=_I64, device=dev)
+    b2 = torch.empty(n, dtype=_I64, device=dev)
+    cnt = torch.empty(n, dtype=_I32, device=dev)
+    _lib.call("cb200_unpack_pixels", _ptr(bin1_ids), _ptr(raw.px), n, _ptr(b1), _ptr(b2), _ptr(cnt), _stream())
+    return b1.cpu().numpy(), b2.cpu().numpy(), cnt.cpu().numpy()
+
+
+def _check_columns(clr, columns, agg):
+    columns = ["count"] if columns is None else list(columns)
+    input_dtypes = clr.pixels().dtypes
+    for col in columns:
+        if col not in input_dtypes:
+            raise ValueError(
+                f"Pixel value column '{col}' not found in input '{clr.filename}'.")
+    if columns != ["count"] or (agg and any(v != "sum" for v in agg.values())):
+        raise NotImplementedError(
+            "the CUDA coarsener aggregates the integer 'count' column with 'sum' only")
+    return columns
+
+
+class CoolerCoarsener:
+    """GPU replacement of ``cooler._reduce.CoolerCoarsener`` (_reduce.py:501-642).
+
+    A ContactBinner-style iterable (create/_ingest.py:507-528): yields dict chunks
+    ``{bin1_id, bin2_id, count}`` lexsorted by (bin1_id, bin2_id), globally sorted
+    and duplicate-free across chunks, of about ``chunksize`` input pixels each and
+    never splitting a coarse row.  ``new_bins`` is the coarsened bin table.
+    """
+
+    def __init__(self, source, factor, chunksize, columns=None, agg=None, batchsize=1, map=map,
+                 device="cuda", table=None):
+        assert isinstance(factor, int) and factor > 1
+        self.clr = source
+        self.factor = factor
+        self.chunksize = int(chunksize)
+        self.columns = _check_columns(source, columns, agg)
+        self.old_binsize = source.binsize
+        self.new_binsize = None if self.old_binsize is None else self.old_binsize * factor
+        old_bins = source.bins()[:]
+        chromsizes = source.chromsizes
+        c, s, e = coarsen_bins(np.asarray(source._load_dset("bins/chrom")), old_bins["start"].values,
+                               old_bins["end"].values, chromsizes.values, factor)
+        self.new_bins_arrays = (c, s, e)
+        self._chromnames = list(chromsizes.index)
+        self._table = table if table is not None else PixelTable.from_cooler(source, device=device)
+        self.result_table = None
+
+    @property
+    def new_bins(self):
+        import pandas as pd
+        c, s, e = self.new_bins_arrays
+        chrom = pd.Categorical.from_codes(c, categories=self._chromnames, ordered=True)
+        return pd.DataFrame({"chrom": chrom, "start": s, "end": e})
+
+    def __iter__(self):
+        new_table, b1ids = coarsen_table(self._table, self.factor)
+        self.result_table = new_table
+        b1, b2, cnt = table_to_host(new_table, b1ids)
+        count_dtype = self.clr.pixels().dtypes["count"]
+        cnt = cnt.astype(count_dtype, copy=False)
+        ind = new_table.raw.indptr.cpu().numpy()
+        edges = _prune_edges(ind, self.chunksize)
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            if hi > lo:
+                yield {"bin1_id": b1[lo:hi], "bin2_id": b2[lo:hi], "count": cnt[lo:hi]}
+
+
+def _as_cooler(obj):
+    if hasattr(obj, "_load_dset"):
+        return obj
+    try:
+        import cooler  # the real package, when h5py is available
+    except ImportError as e:  # pragma: no cover
+        raise ImportError("opening cooler URIs needs the `cooler` package (h5py); "
+                          "pass a Cooler-like object instead") from e
+    return cooler.Cooler(obj)
+
+
+def coarsen_cooler(base_uri, output_uri, factor, chunksize, nproc=1, columns=None, dtypes=None,
+                   agg=None, device="cuda", **kwargs):
+    """Coarsen a cooler by an integer factor on the GPU.
+
+    Same arguments as ``cooler.coarsen_cooler`` (_reduce.py:645-749); ``nproc`` is
+    accepted and ignored (no process pool).  ``base_uri`` may be a URI/path (needs the
+    ``cooler`` package) or a Cooler-like object.  With ``output_uri=None`` the result
+    is returned as a ``MemCooler``; otherwise it is written with ``cooler.create``
+    exactly as the reference does (``append=True``, ``symmetric_upper`` propagated).
+    """
+    clr = _as_cooler(base_uri)
+    factor = int(factor)
+    columns = _check_columns(clr, columns, agg)
+    dtypes = dict(dtypes or {})
+    input_dtypes = clr.pixels().dtypes
+    for col in columns:
+        dtypes.setdefault(col, input_dtypes[col])
+    iterator = CoolerCoarsener(clr, factor, chunksize, columns=columns, agg=agg, batchsize=nproc,
+                               device=device, table=kwargs.pop("table", None))
+    symmetric_upper = clr.storage_mode == "symmetric-upper"
+    if output_uri is None:
+        chunks = list(iterator)
+        cat = {k: (np.concatenate([c[k] for c in chunks]) if chunks else np.zeros(0, dtype=np.int64))
+               for k in ("bin1_id", "bin2_id", "count")}
+        c, s, e = iterator.new_bins_arrays
+        out = MemCooler.from_arrays(iterator._chromnames, clr.chromsizes.values, c, s, e,
+                                    cat["bin1_id"], cat["bin2_id"],
+                                    cat["count"].astype(dtypes["count"], copy=False),
+                                    binsize=iterator.new_binsize, symmetric_upper=symmetric_upper)
+        out.device_table = iterator.result_table
+        return out
+    from cooler.create import create  # real writer (h5py)
+    kwargs.setdefault("append", True)
+    create(output_uri, iterator.new_bins, iterator, dtypes=dtypes, symmetric_upper=symmetric_upper,
+           **kwargs)
+    return None
+
+
+def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=None, dtypes=None,
+                   agg=None, device="cuda", **kwargs):
+    """Multi-resolution coarsening chain (``cooler.zoomify_cooler``, _reduce.py:752-877).
+
+    Each target resolution is derived from the largest already-available
+    resolution that divides it.  Levels are chained on the device: level k's output
+    table feeds level k+1 without a host round trip.  With ``outfile=None`` returns
+    ``{resolution: MemCooler}`` (the base included); otherwise writes an .mcool through
+    the ``cooler`` package like the reference.
+    """
+    if not isinstance(base_uris, (list, tuple)):
+        base_uris = [base_uris]
+    bases = {}
+    for b in base_uris:
+        clr = _as_cooler(b)
+        if clr.binsize is None:
+            raise ValueError("Cannot zoomify a cooler with variable-size bins")   # cli/zoomify.py
+        bases[int(clr.binsize)] = clr
+    resn, pred, mult = get_multiplier_sequence(list(resolutions), list(bases))
+    if outfile is not None:  # pragma: no cover - needs h5py
+        raise NotImplementedError("writing .mcool files needs the cooler package; pass outfile=None")
+    out = {}
+    tables = {}
+    for i, res in enumerate(resn):
+        res = int(res)
+        if pred[i] == -1:
+            out[res] = bases[res]
+            continue
+        prev = int(resn[pred[i]])
+        src = out[prev]
+        tab = tables.get(prev)
+        out[res] = coarsen_cooler(src, None, int(mult[i]), chunksize, nproc=nproc, columns=columns,
+                                  dtypes=dtypes, agg=agg, device=device, table=tab)
+        tables[res] = out[res].device_table
+    return out

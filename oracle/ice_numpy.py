@@ -209,3 +209,32 @@ def balance_arrays(px, chrom_offset, bin1_offset, *, cis_only=False, trans_only=
     if return_passes:
         return bias, stats, passes, warned
     return bias, stats
+
+
+# ---------------------------------------------------------------------------
+# Process-pool form of one marginal pass (the reference's `cooler balance -p N`
+# path: cli/balance.py:237-243 -> Pool.imap_unordered over pixel spans).  The
+# pixel arrays are inherited by fork()ed workers through this module global --
+# the stand-in for every worker re-opening the file (parallel.py:289-304) --
+# while the per-task bias vector and the per-span n_bins result vector travel
+# by pickle exactly as in the reference.
+# ---------------------------------------------------------------------------
+_SHARED = {}
+
+
+def share(px, chrom_ids, n_bins):
+    _SHARED.clear()
+    _SHARED.update(px=px, chrom_ids=chrom_ids, n_bins=n_bins)
+
+
+def shared_span_task(args):
+    lo, hi, kw = args
+    return _span_marginal(_SHARED["px"], _SHARED["chrom_ids"], _SHARED["n_bins"], lo, hi, **kw)
+
+
+def pool_marginal(map_, spans, **kw):
+    """reduce(add, zeros) over spans mapped with ``map_`` (e.g. Pool.imap_unordered)."""
+    acc = np.zeros(_SHARED["n_bins"])
+    for part in map_(shared_span_task, [(lo, hi, kw) for lo, hi in spans]):
+        acc = acc + part
+    return acc

@@ -1,0 +1,132 @@
+"""Parity of the CUDA coarsening path with the reference's golden files
+(toy.*.bg2 chains, tests/test_reduce.py:83-175), with reference outputs frozen in
+tests/golden (GM12878 x2/x5/x10, odd.1 x4 & co., variable bins) and with the oracle
+on larger random tables.  Bar: bit-exact pixels."""
+import numpy as np
+import pytest
+
+from tests import _golden
+
+pytestmark = pytest.mark.gpu
+
+CO = _golden.coarsen_golden()
+
+
+def _cat(chunks):
+    return np.stack([np.concatenate([c[k] for c in chunks]) for k in ("bin1_id", "bin2_id", "count")], 1) \
+        if chunks else np.zeros((0, 3), dtype=np.int64)
+
+
+def _mem(names, sizes, bc, bs, be, px, binsize, symm=True):
+    from cooler_b200 import MemCooler
+    return MemCooler.from_arrays(names, sizes, bc, bs, be, px[:, 0], px[:, 1], px[:, 2].astype(np.int32),
+                                 binsize=binsize, symmetric_upper=symm)
+
+
+@pytest.mark.parametrize("factor", [2, 5, 10])
+@pytest.mark.parametrize("chunksize", [10_000, 777])
+def test_coarsen_gm12878(factor, chunksize):
+    from cooler_b200.reduce import CoolerCoarsener
+    t = _golden.gm12878()
+    px = np.stack([t["bin1_id"], t["bin2_id"], t["count"]], 1)
+    clr = _mem(t["chromnames"], t["chromsizes"], t["bins_chrom"], t["bins_start"], t["bins_end"], px, 2_000_000)
+    it = CoolerCoarsener(clr, factor, chunksize)
+    chunks = list(it)
+    got = _cat(chunks)
+    np.testing.assert_array_equal(got[:, 0], CO[f"gm/x{factor}/bin1_id"])
+    np.testing.assert_array_equal(got[:, 1], CO[f"gm/x{factor}/bin2_id"])
+    np.testing.assert_array_equal(got[:, 2], CO[f"gm/x{factor}/count"])
+    assert chunks[0]["bin1_id"].dtype == np.int64 and chunks[0]["count"].dtype == np.int32
+    nb = it.new_bins
+    np.testing.assert_array_equal(nb["start"].values, CO[f"gm/x{factor}/bins_start"])
+    np.testing.assert_array_equal(nb["end"].values, CO[f"gm/x{factor}/bins_end"])
+    np.testing.assert_array_equal(nb["chrom"].cat.codes.values, CO[f"gm/x{factor}/bins_chrom"])
+    # chunks never split a coarse row and are globally sorted
+    for a, b in zip(chunks[:-1], chunks[1:]):
+        assert a["bin1_id"][-1] < b["bin1_id"][0]
+
+
+@pytest.mark.parametrize("fam,r0,r1", [("symm.upper", 2, 4), ("asymm", 2, 4), ("asymm", 4, 8),
+                                       ("asymm", 8, 16), ("asymm", 16, 32), ("asymm", 2, 32)])
+def test_coarsen_toy_golden_files(fam, r0, r1):
+    from cooler_b200.reduce import coarsen_cooler
+    sizes = np.array([32, 32])
+    bc, bs, be = _golden.uniform_bins(sizes, r0)
+    clr = _mem(["chr1", "chr2"], sizes, bc, bs, be, CO[f"toy.{fam}/{r0}"], r0, symm=(fam == "symm.upper"))
+    out = coarsen_cooler(clr, None, r1 // r0, chunksize=7)
+    with out.open() as g:
+        got = np.stack([g["pixels/bin1_id"][:], g["pixels/bin2_id"][:], g["pixels/count"][:]], 1)
+    np.testing.assert_array_equal(got, CO[f"toy.{fam}/{r1}"])
+    assert out.binsize == r1 and out.info["nbins"] == 2 * (32 // r1)
+    assert out.storage_mode == clr.storage_mode
+
+
+def test_zoomify_toy_chain():
+    """tests/test_reduce.py:140-175: toy.asymm.2 -> [4, 8, 16, 32], each vs its golden."""
+    from cooler_b200.reduce import zoomify_cooler
+    sizes = np.array([32, 32])
+    bc, bs, be = _golden.uniform_bins(sizes, 2)
+    clr = _mem(["chr1", "chr2"], sizes, bc, bs, be, CO["toy.asymm/2"], 2, symm=False)
+    out = zoomify_cooler(clr, None, [4, 8, 16, 32], chunksize=10)
+    for res in (4, 8, 16, 32):
+        with out[res].open() as g:
+            got = np.stack([g["pixels/bin1_id"][:], g["pixels/bin2_id"][:], g["pixels/count"][:]], 1)
+        np.testing.assert_array_equal(got, CO[f"toy.asymm/{res}"])
+    with pytest.raises(ValueError):
+        zoomify_cooler(clr, None, [4, 5, 32], chunksize=10)
+
+
+@pytest.mark.parametrize("factor", [4, 3, 7, 200])
+def test_coarsen_odd_partitions_correctly(factor):
+    from cooler_b200.reduce import CoolerCoarsener
+    sizes = CO["odd/chromsizes"]
+    bc, bs, be = _golden.uniform_bins(sizes, 1)
+    clr = _mem(["chr1", "chr2", "chr3"], sizes, bc, bs, be, CO["odd/1"], 1)
+    got = _cat(list(CoolerCoarsener(clr, factor, 2)))
+    want = CO["odd/4"] if factor == 4 else CO[f"odd/x{factor}"]
+    np.testing.assert_array_equal(got, want)
+    assert len(np.unique(got[:, :2], axis=0)) == len(got)
+
+
+@pytest.mark.parametrize("factor", [2, 3])
+def test_coarsen_variable_bins(factor):
+    from cooler_b200.reduce import CoolerCoarsener
+    bins = CO["var/bins"]
+    clr = _mem(["chr1", "chr2"], np.array([32, 32]), bins[:, 0], bins[:, 1], bins[:, 2], CO["var/px"], None)
+    it = CoolerCoarsener(clr, factor, 11)
+    got = _cat(list(it))
+    np.testing.assert_array_equal(got, CO[f"var/x{factor}"])
+    nb = it.new_bins
+    np.testing.assert_array_equal(
+        np.stack([nb["chrom"].cat.codes.values, nb["start"].values, nb["end"].values], 1), CO[f"var/x{factor}/bins"])
+
+
+def test_coarsen_missing_column_raises():
+    from cooler_b200.reduce import coarsen_cooler
+    sizes = np.array([32, 32])
+    bc, bs, be = _golden.uniform_bins(sizes, 2)
+    clr = _mem(["chr1", "chr2"], sizes, bc, bs, be, CO["toy.asymm/2"], 2, symm=False)
+    with pytest.raises(ValueError):
+        coarsen_cooler(clr, None, 2, 10, columns=["missing"])
+
+
+@pytest.mark.parametrize("factor", [2, 5])
+def test_coarsen_matches_oracle_large(factor):
+    """~2e6 pixels, long and empty rows, a 1-bin chromosome."""
+    from cooler_b200 import PixelTable
+    from cooler_b200.reduce import coarsen_table, table_to_host
+    from oracle import coarsen_numpy
+    from tests.test_balance_gpu import _synthetic
+    b1, b2, cnt, chrom_offset = _synthetic(21, [30000, 17001, 1, 9000], 0.0015)
+    n = int(chrom_offset[-1])
+    sizes = np.diff(chrom_offset) * 1000
+    bc, bs, be = _golden.uniform_bins(sizes, 1000)
+    want = coarsen_numpy.coarsen_pixels(dict(bin1_id=b1, bin2_id=b2, count=cnt), bc, bs, be, sizes, factor)
+    tab = PixelTable.from_arrays(np.searchsorted(b1, np.arange(n + 1)), b2, cnt, chrom_offset)
+    new, ids = coarsen_table(tab, factor)
+    g1, g2, gc = table_to_host(new, ids)
+    np.testing.assert_array_equal(g1, want[0]), np.testing.assert_array_equal(g2, want[1])
+    np.testing.assert_array_equal(gc, want[2])
+    assert int(gc.sum()) == int(cnt.sum())           # size-independent invariant: total count preserved
+    # the coarse table is itself a valid input: its indptr matches its ids
+    np.testing.assert_array_equal(new.raw.indptr.cpu().numpy(), np.searchsorted(g1, np.arange(new.n_bins + 1)))
