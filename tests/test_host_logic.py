@@ -1,0 +1,141 @@
+"""Host-side logic that needs no GPU: resolution planners, bin maps, coarsened bin
+tables, the in-memory store, prefilter arithmetic, the synthetic generator."""
+import numpy as np
+import pytest
+
+from tests import _golden
+
+
+def test_get_multiplier_sequence_matches_reference_semantics():
+    from cooler_b200.reduce import ZOOMS_4DN, get_multiplier_sequence
+    resn, pred, mult = get_multiplier_sequence(ZOOMS_4DN)
+    assert list(resn) == ZOOMS_4DN
+    assert list(mult[1:]) == [2, 5, 2, 5, 2, 2, 5, 2, 2, 5, 2, 2]       # SURVEY 3.3 probe
+    assert pred[0] == -1 and list(pred[1:]) == [0, 0, 2, 2, 4, 5, 5, 7, 8, 8, 10, 11]
+    resn, pred, mult = get_multiplier_sequence([4, 8, 16, 32], [2])
+    assert list(resn) == [2, 4, 8, 16, 32] and list(mult[1:]) == [2, 2, 2, 2]
+    with pytest.raises(ValueError):
+        get_multiplier_sequence([4, 5, 32], [2])
+    # two bases
+    resn, pred, mult = get_multiplier_sequence([1000, 5000, 10000, 3000], [1000, 3000])
+    assert list(resn) == [1000, 3000, 5000, 10000]
+    assert list(pred) == [-1, 0, 0, 2]            # a base that another base divides still gets a predecessor (_reduce.py:481-489)
+
+
+def test_preferred_sequence():
+    from cooler_b200.reduce import preferred_sequence
+    assert preferred_sequence(1, 100, "nice") == [1, 2, 5, 10, 20, 50, 100]
+    assert preferred_sequence(5, 100, "nice") == [5, 10, 25, 50, 100]
+    assert preferred_sequence(1000, 10_000_000, "nice") == [
+        1000, 2000, 5000, 10000, 20000, 50000, 100000, 200000, 500000, 1000000, 2000000, 5000000, 10000000]
+    assert preferred_sequence(3, 50, "binary") == [3, 6, 12, 24, 48]
+    assert preferred_sequence(10, 5) == []
+
+
+def test_get_quadtree_depth():
+    from cooler_b200.reduce import get_quadtree_depth
+    assert get_quadtree_depth([1000, 3000], 10, 256) == 1
+    assert get_quadtree_depth([248956422, 242193529], 1000, 256) == 11
+
+
+@pytest.mark.parametrize("factor", [2, 3, 5, 7, 200])
+def test_bin_map_equals_coordinate_rebinning(factor):
+    """Closed-form id map == the reference's coordinate arithmetic (oracle restates _reduce.py:597-614)."""
+    from cooler_b200.reduce import coarsen_bin_map, coarsen_bins
+    from oracle import coarsen_numpy
+    sizes = np.array([51, 107, 33, 1, 400])
+    bc, bs, be = _golden.uniform_bins(sizes, 1)
+    off = np.r_[0, np.cumsum(sizes)]
+    bmap, new_off = coarsen_bin_map(off, factor)
+    n = off[-1]
+    px = dict(bin1_id=np.arange(n), bin2_id=np.arange(n), count=np.ones(n, dtype=np.int32))
+    b1, b2, c, (nc, ns, ne) = coarsen_numpy.coarsen_pixels(px, bc, bs, be, sizes, factor)
+    # every old diagonal pixel i lands on (map[i], map[i]); counts = pooled bins
+    want = np.bincount(bmap, minlength=new_off[-1])
+    np.testing.assert_array_equal(b1, np.arange(new_off[-1]))
+    np.testing.assert_array_equal(c, want)
+    gc, gs, ge = coarsen_bins(bc, bs, be, sizes, factor)
+    np.testing.assert_array_equal(gc, nc), np.testing.assert_array_equal(gs, ns), np.testing.assert_array_equal(ge, ne)
+
+
+def test_coarsen_bins_gm12878_golden():
+    from cooler_b200.reduce import coarsen_bins
+    t = _golden.gm12878()
+    CO = _golden.coarsen_golden()
+    for f in (2, 5, 10):
+        c, s, e = coarsen_bins(t["bins_chrom"], t["bins_start"], t["bins_end"], t["chromsizes"], f)
+        np.testing.assert_array_equal(s, CO[f"gm/x{f}/bins_start"])
+        np.testing.assert_array_equal(e, CO[f"gm/x{f}/bins_end"])
+        np.testing.assert_array_equal(c, CO[f"gm/x{f}/bins_chrom"])
+    c, s, e = coarsen_bins(t["bins_chrom"], t["bins_start"], t["bins_end"], t["chromsizes"], 2)
+    assert (s[c == 0][-1], e[c == 0][-1]) == (248_000_000, 249_250_621)
+
+
+def test_prune_edges_never_splits_rows():
+    from cooler_b200.reduce import _prune_edges
+    ind = np.array([0, 0, 5, 5, 9, 30, 31, 31, 40])
+    e = _prune_edges(ind, 10)
+    assert e[0] == 0 and e[-1] == 40 and set(e) <= set(ind) and np.all(np.diff(e) > 0)
+
+
+def test_memcooler_protocol():
+    from cooler_b200 import MemCooler
+    t = _golden.gm12878()
+    clr = MemCooler.from_arrays(t["chromnames"], t["chromsizes"], t["bins_chrom"], t["bins_start"],
+                                t["bins_end"], t["bin1_id"], t["bin2_id"], t["count"], binsize=2_000_000)
+    assert clr.info["nnz"] == 38156 and clr.info["nbins"] == 1561 and clr.info["sum"] == 100000
+    assert clr.binsize == 2_000_000 and clr.storage_mode == "symmetric-upper"
+    off = clr._load_dset("indexes/chrom_offset")
+    assert list(off[:4]) == [0, 125, 247, 347] and off[-1] == 1561
+    assert list(clr.chroms()["name"][:])[:2] == ["chr1", "chr2"]
+    assert clr.chromsizes["chr1"] == 249250621
+    assert clr.bins()[:].shape == (1561, 3)
+    assert "count" in clr.pixels().dtypes
+    with clr.open("r+") as grp:
+        grp["bins"].create_dataset("weight", data=np.ones(1561), compression="gzip")
+        grp["bins"]["weight"].attrs.update({"converged": True})
+        assert "weight" in grp["bins"]
+        del grp["bins"]["weight"]
+        assert "weight" not in grp["bins"]
+
+
+def test_prefilter_bias_matches_oracle_masks():
+    """Host filter arithmetic on exact integer marginals == the reference's masks."""
+    from types import SimpleNamespace
+
+    from cooler_b200.balance import prefilter_bias
+    t = _golden.gm12878()
+    BAL, META = _golden.balance_golden()
+    chrom_offset, _ = _golden.offsets(t)
+    b1, b2, c = t["bin1_id"], t["bin2_id"], t["count"]
+    n = 1561
+    for key, nd in (("gm/defaults", 2), ("gm/diag0", 0), ("gm/test_balance_cfg", 1)):
+        keep = np.abs(b1 - b2) >= nd
+        nnzm = np.bincount(b1[keep], c[keep] != 0, n) + np.bincount(b2[keep], c[keep] != 0, n)
+        summ = np.bincount(b1[keep], c[keep], n) + np.bincount(b2[keep], c[keep], n)
+        prob = SimpleNamespace(table=SimpleNamespace(n_bins=n), marg_nnz=nnzm.astype(float), marg_sum=summ.astype(float))
+        bias = prefilter_bias(prob, chrom_offset, mad_max=5, min_nnz=10, min_count=0, blacklist=None, x0=None)
+        np.testing.assert_array_equal(bias == 0, np.isnan(BAL[key]))
+
+
+def test_synth_generator_shards_tile_the_matrix():
+    from cooler_b200 import synth
+    plan = synth.SynthPlan(1_000_000, 1_200_000, seed=3)
+    synth.ROWS_PER_BLOCK_TARGET, old = 150_000, synth.ROWS_PER_BLOCK_TARGET
+    try:
+        plan = synth.SynthPlan(1_000_000, 1_200_000, seed=3)
+        full = synth.generate(plan, device="cpu", pin=False)
+        assert len(plan.block_edges) > 4
+        parts = [synth.generate(plan, blocks=plan.shard_rows(r, 3), device="cpu", pin=False) for r in range(3)]
+    finally:
+        synth.ROWS_PER_BLOCK_TARGET = old
+    assert sum(p["nnz"] for p in parts) == full["nnz"]
+    np.testing.assert_array_equal(np.concatenate([p["bin2_id"].numpy() for p in parts]), full["bin2_id"].numpy())
+    np.testing.assert_array_equal(sum(np.diff(p["bin1_offset"].numpy()) for p in parts),
+                                  np.diff(full["bin1_offset"].numpy()))
+    assert parts[0]["row_range"][1] == parts[1]["row_range"][0]
+    off = full["bin1_offset"].numpy()
+    b1 = np.repeat(np.arange(full["n_bins"]), np.diff(off))
+    key = b1 * full["n_bins"] + full["bin2_id"].numpy()
+    assert np.all(np.diff(key) > 0) and np.all(full["bin2_id"].numpy() >= b1)
+    assert 0.7 < full["nnz"] / 1_200_000 < 1.3
