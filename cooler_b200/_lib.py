@@ -19,18 +19,26 @@ class Copy(C.Structure):
                 ("nnz", C.c_int64)]
 
 
+class Sub(C.Structure):
+    """cb200_sub"""
+    _fields_ = [("px", C.c_void_p), ("indptr", C.c_void_p), ("tile_row", C.c_void_p),
+                ("nnz", C.c_int64), ("direct", C.c_void_p), ("pieces", C.c_void_p),
+                ("first_warp", C.c_int64), ("first_tile", C.c_int64),
+                ("gather_base", C.c_int32), ("gather_len", C.c_int32)]
+
+
 class Ice(C.Structure):
     """cb200_ice"""
     _fields_ = [
-        ("csr", Copy), ("csc", Copy),
+        ("subs", C.c_void_p), ("n_subs", C.c_int32), ("span", C.c_int32),
+        ("total_warps", C.c_int64), ("total_tiles", C.c_int64), ("smem_bins", C.c_int32),
+        ("claim", C.c_void_p),
         ("n_bins", C.c_int32), ("n_segs", C.c_int32),
         ("seg_offset", C.c_void_p),
         ("n_blocks", C.c_int32),
         ("blk_seg", C.c_void_p), ("blk_lo", C.c_void_p), ("blk_hi", C.c_void_p),
         ("seg_blk_offset", C.c_void_p),
         ("bias", C.c_void_p), ("cweights", C.c_void_p), ("w", C.c_void_p),
-        ("direct_row", C.c_void_p), ("pieces_row", C.c_void_p),
-        ("direct_col", C.c_void_p), ("pieces_col", C.c_void_p),
         ("s", C.c_void_p), ("marg", C.c_void_p),
         ("blk_sum", C.c_void_p), ("blk_cnt", C.c_void_p), ("blk_dev", C.c_void_p),
         ("seg_mean", C.c_void_p), ("seg_nnz", C.c_void_p),
@@ -52,13 +60,16 @@ SIGNATURES = {
     "cb200_scan_workspace_bytes": (_SZ, [_I64]),
     "cb200_exclusive_scan_i32": (C.c_int, [_P, _P, _I64, _P, _SZ, _P]),
     "cb200_sort_workspace_bytes": (_SZ, [_I64]),
-    "cb200_sort_pairs": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, C.c_int, _P, _SZ, _P]),
+    "cb200_sort_pairs": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, C.c_int, C.c_int, _P, _SZ, _P]),
     "cb200_pack_pixels": (C.c_int, [_P, _P, _I64, _P, _P]),
     "cb200_tile_rows": (C.c_int, [_P, _I32, _I64, _P, _P]),
-    "cb200_indptr_from_sorted": (C.c_int, [_P, _I64, _I32, _P, _P]),
+    "cb200_indptr_from_sorted": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
+    "cb200_swap_key_other": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "cb200_strip_finish": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
     "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _P, _P]),
     "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
+    "cb200_set_tuning": (C.c_int, [_I32]),
     "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_combine": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_update": (C.c_int, [C.POINTER(Ice), _I32, _P]),

@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from .table import (PixelTable, TableCopy, _ptr, _stream, _use_device, filter_copy,  # noqa: F401
-                    marginals_i64, n_tiles, transpose_from)
+                    marginals_i64, n_tiles, strip_partition, swap_key_other, transpose_from)
 
 __all__ = ["balance_cooler", "balance_table", "ConvergenceWarning", "IceProblem"]
 
@@ -56,37 +56,90 @@ class IceProblem:
     """
 
     def __init__(self, table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2,
-                 group=None):
+                 group=None, strip_bins=None, use_smem=True):
         self.table = table
+        self.use_smem = use_smem
         self.group = group
         self.mode = "cis" if cis_only else ("trans" if trans_only else "gw")
+        n_bins = table.n_bins
         ndiag = int(ignore_diags) if ignore_diags else 0
         keep = _lib.KEEP_CIS if cis_only else _lib.KEEP_ALL
         csr, tkey, tval = filter_copy(table.raw, table.row_lo, table.row_hi, ndiag, keep,
                                       want_transpose=True)
-        csc = transpose_from(tkey, tval, table.n_bins)
-        del tkey, tval
+        csc, ckeys = transpose_from(tkey, tval, n_bins, return_keys=True)
         # prefilter marginals (exact integers)
         nnz_r, sum_r = marginals_i64(csr)
         nnz_c, sum_c = marginals_i64(csc)
         marg = torch.stack([nnz_r + nnz_c, sum_r + sum_c])
+        del nnz_r, sum_r, nnz_c, sum_c
         _allreduce(marg, group)
         marg = marg.cpu().numpy()
         self.marg_nnz = marg[0].astype(np.float64)
         self.marg_sum = marg[1].astype(np.float64)
+        cval = None
         if trans_only:
-            csr, _, _ = filter_copy(csr, table.row_lo, table.row_hi, 0, _lib.KEEP_TRANS)
-            csc, _, _ = filter_copy(csc, table.row_lo, table.row_hi, 0, _lib.KEEP_TRANS)
+            del tkey, tval, ckeys
+            csr, tkey, tval = filter_copy(csr, table.row_lo, table.row_hi, 0, _lib.KEEP_TRANS,
+                                          want_transpose=True)
+            csc, ckeys, cval = filter_copy(csc, table.row_lo, table.row_hi, 0, _lib.KEEP_TRANS,
+                                           want_transpose=True)
         self.csr, self.csc = csr, csc
+        # column strips of the gathered bias vector (cache blocking), see choose_strip_shift
+        self.strip_shift = choose_strip_shift(n_bins, csr.nnz, strip_bins)
+        if self.strip_shift is None:
+            self.subs = [csr, csc]
+        else:
+            sh = self.strip_shift
+            subs = strip_partition(tkey[: csr.nnz], tval, csr.nnz, n_bins, sh)
+            del tkey, tval
+            if cval is None:                      # csc came from the sort: (key = row, val = {other, count})
+                ckeys, cval = swap_key_other(ckeys, csc.px, csc.nnz)
+            subs += strip_partition(ckeys[: csc.nnz], cval, csc.nnz, n_bins, sh)
+            self.subs = subs
+            self.csr = self.csc = None            # the strips replace the whole copies
+            self._nnz_eff = csr.nnz
+        del ckeys, cval
+        if self.strip_shift is None:
+            self._nnz_eff = csr.nnz
 
     @property
     def nnz_eff(self):
         """Stored pixels surviving the static filters (one copy)."""
-        return self.csr.nnz
+        return self._nnz_eff
 
     def bytes_per_pass(self):
         """Algorithmic bytes of one marginal pass: 16 B/effective pixel + 40 B/bin."""
         return 16 * self.nnz_eff + 40 * self.table.n_bins
+
+
+L1_RESIDENT_BINS = 49_152      # bias vectors up to 384 KB are served well enough by L1 + L2
+DEFAULT_STRIP_BINS = 16_384    # 128 KB of float64 bias per strip: stays in the SM's L1
+MIN_PIXELS_PER_ROW_STRIP = 16  # below this the per-(row, strip) bookkeeping costs more than it saves
+
+
+def choose_strip_shift(n_bins, nnz_eff, strip_bins=None):
+    """log2 of the strip width in bins, or None for "no strips".
+
+    The sweep gathers bias[other] per pixel.  When the bias vector is much larger than
+    L1 every gather costs a 32-byte L2 sector per 8-byte pixel and L2 bandwidth, not
+    HBM, bounds the pass.  Splitting a copy into strips of the gathered index keeps the
+    gathered slice L1-resident, at the price of one partial sum per (row, strip).
+    """
+    if strip_bins == 0:
+        return None
+    if strip_bins is None:
+        if n_bins <= L1_RESIDENT_BINS:
+            return None
+        strip_bins = DEFAULT_STRIP_BINS
+        n_strips = -(-n_bins // strip_bins)
+        if nnz_eff < MIN_PIXELS_PER_ROW_STRIP * n_bins * n_strips:
+            return None
+    shift = int(strip_bins).bit_length() - 1
+    if (1 << shift) != int(strip_bins):
+        raise ValueError("strip_bins must be a power of two")
+    if ((max(n_bins, 1) - 1) >> shift) + 1 > 256:
+        return None
+    return shift
 
 
 class IceState:
@@ -123,8 +176,31 @@ class IceState:
         else:
             t["cweights"] = None
             t["w"] = t["bias"]
-        t["direct_row"], t["direct_col"] = f64(n), f64(n)
-        t["pieces_row"], t["pieces_col"] = f64(2 * n_tiles(prob.csr.nnz)), f64(2 * n_tiles(prob.csc.nnz))
+        # sub-copy descriptors (whole copies or column strips) for K3 / combine
+        subs = prob.subs
+        total_tiles = sum(n_tiles(c.nnz) for c in subs)
+        span = int(min(8, max(1, -(-total_tiles // (148 * 32 * 8)))))
+        arr = (_lib.Sub * max(len(subs), 1))()
+        t["direct"] = f64(max(len(subs), 1) * max(n, 1))
+        t["pieces"] = f64(2 * total_tiles + 2)
+        warp0, tile0 = 0, 0
+        for k, c in enumerate(subs):
+            arr[k].px, arr[k].indptr, arr[k].tile_row = c.px.data_ptr(), c.indptr.data_ptr(), c.tile_row.data_ptr()
+            arr[k].nnz = c.nnz
+            arr[k].direct = t["direct"].data_ptr() + 8 * k * n
+            arr[k].pieces = t["pieces"].data_ptr() + 8 * 2 * tile0
+            arr[k].first_warp = warp0
+            arr[k].first_tile = tile0
+            strip = getattr(c, "strip", None)
+            if strip is None or prob.strip_shift is None:
+                arr[k].gather_base, arr[k].gather_len = 0, n
+            else:
+                base = strip << prob.strip_shift
+                arr[k].gather_base, arr[k].gather_len = base, min(1 << prob.strip_shift, n - base)
+            warp0 += -(-n_tiles(c.nnz) // span)
+            tile0 += n_tiles(c.nnz)
+        t["subs"] = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+        t["claim"] = torch.zeros(len(subs) + 1, dtype=torch.int64, device=dev)
         t["s"], t["marg"] = f64(n), f64(n)
         t["blk_sum"], t["blk_cnt"], t["blk_dev"] = f64(nb), f64(nb), f64(nb)
         t["seg_mean"], t["seg_nnz"] = f64(S), f64(S)
@@ -134,10 +210,11 @@ class IceState:
         t["all_done"] = torch.zeros(1, dtype=_I32, device=dev)
         t["var_hist"] = f64(self.max_iters * S, float("nan"))
         st = _lib.Ice()
-        st.csr, st.csc = prob.csr.c_struct(), prob.csc.c_struct()
+        st.n_subs, st.span, st.total_warps, st.total_tiles = len(subs), span, warp0, total_tiles
+        st.smem_bins = (1 << prob.strip_shift) if (prob.strip_shift is not None and prob.use_smem) else 0
         st.n_bins, st.n_segs, st.n_blocks = n, S, nb
-        for k in ("seg_offset", "blk_seg", "blk_lo", "blk_hi", "seg_blk_offset", "bias", "cweights", "w",
-                  "direct_row", "pieces_row", "direct_col", "pieces_col", "s", "marg", "blk_sum", "blk_cnt",
+        for k in ("subs", "claim", "seg_offset", "blk_seg", "blk_lo", "blk_hi", "seg_blk_offset", "bias", "cweights", "w",
+                  "s", "marg", "blk_sum", "blk_cnt",
                   "blk_dev", "seg_mean", "seg_nnz", "seg_scale", "seg_var", "seg_iters", "seg_done",
                   "seg_empty", "all_done", "var_hist"):
             setattr(st, k, t[k].data_ptr() if t[k] is not None else None)
@@ -235,7 +312,7 @@ def prefilter_bias(prob: IceProblem, chrom_offset, *, mad_max, min_nnz, min_coun
 def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2, mad_max=5,
                   min_nnz=10, min_count=0, blacklist=None, rescale_marginals=True, x0=None,
                   tol=1e-5, max_iters=200, group=None, problem=None, chromnames=None,
-                  return_info=False):
+                  return_info=False, strip_bins=None):
     """Balance a device-resident table.  Same semantics as ``balance_cooler``.
 
     ``problem`` lets callers reuse the filtered copies (bench: inputs resident
@@ -247,7 +324,7 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
     n_bins = table.n_bins
     n_chroms = len(chrom_offset) - 1
     prob = problem or IceProblem(table, cis_only=cis_only, trans_only=trans_only,
-                                 ignore_diags=ignore_diags, group=group)
+                                 ignore_diags=ignore_diags, group=group, strip_bins=strip_bins)
     bias = prefilter_bias(prob, chrom_offset, mad_max=mad_max, min_nnz=min_nnz, min_count=min_count,
                           blacklist=blacklist, x0=x0)
 
@@ -316,7 +393,8 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
     if return_info:
         info = {"passes": res["seg_iters"].tolist(), "launched_passes": passes,
                 "nnz_eff": prob.nnz_eff, "bytes_per_pass": prob.bytes_per_pass(),
-                "hit_limit": hit_limit, "gpu_launches": state.launches}
+                "hit_limit": hit_limit, "gpu_launches": state.launches,
+                "n_subcopies": len(prob.subs), "strip_shift": prob.strip_shift}
         return bias, stats, info
     return bias, stats
 

@@ -20,38 +20,115 @@ struct IceOp {
   }
 };
 
-constexpr int ICE_UNROLL = 4;
+// Tuning knob (cb200_set_tuning): 128-bit stream loads kept in flight per lane.
+static int g_ice_unroll = 2;
 
+template <int U>
 __global__ void __launch_bounds__(BLOCK_THREADS)
-ice_sweep_kernel(const int2* __restrict__ px_a, const int64_t* __restrict__ indptr_a,
-                 const int32_t* __restrict__ tile_row_a, int64_t nnz_a, int64_t n_tiles_a,
-                 double* __restrict__ direct_a, double* __restrict__ pieces_a,
-                 const int2* __restrict__ px_b, const int64_t* __restrict__ indptr_b,
-                 const int32_t* __restrict__ tile_row_b, int64_t nnz_b, int64_t n_tiles_b,
-                 double* __restrict__ direct_b, double* __restrict__ pieces_b,
+ice_sweep_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span, int64_t total_warps,
                  const double* __restrict__ w, const int32_t* __restrict__ all_done) {
   if (*all_done) return;
-  int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  const int64_t wg = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
+  if (wg >= total_warps) return;
+  int lo = 0, hi = n_subs;                         // largest k with subs[k].first_warp <= wg
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (subs[mid].first_warp <= wg) lo = mid; else hi = mid;
+  }
+  const cb200_sub sub = subs[lo];
+  const int64_t n_tiles = (sub.nnz + WARP_TILE - 1) / WARP_TILE;
+  const int64_t t0 = (wg - sub.first_warp) * span;
+  if (t0 >= n_tiles) return;
   IceOp op{w};
-  if (t < n_tiles_a) {
-    walk_reduce_tile<IceOp, ICE_UNROLL>(px_a, indptr_a, nnz_a, t, tile_row_a[t], op, direct_a, pieces_a);
-  } else {
-    t -= n_tiles_a;
-    if (t < n_tiles_b)
-      walk_reduce_tile<IceOp, ICE_UNROLL>(px_b, indptr_b, nnz_b, t, tile_row_b[t], op, direct_b, pieces_b);
+  walk_reduce_span<IceOp, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row, sub.nnz,
+                             t0, min(t0 + span, n_tiles), op, sub.direct, sub.pieces);
+}
+
+// Shared-memory form of K3 for column strips: a persistent CTA per SM owns a
+// contiguous range of the global tile sequence (sub-copies concatenated); for every
+// strip it touches it stages that strip's slice of w (<= smem_bins doubles) in shared
+// memory once and its 32 warps gather from there.  Random 8-byte gathers cost a few
+// bank-conflict cycles in shared memory instead of one L1 tag lookup per lane.
+struct IceOpSmem {
+  typedef double T;
+  const double* ws;     // shared memory slice
+  int base;
+  __device__ __forceinline__ double value(int other, int count) const {
+    return ws[other - base] * (double)count;
+  }
+};
+
+constexpr int STRIP_THREADS = 1024;
+constexpr int STRIP_WARPS = STRIP_THREADS / 32;
+
+// Work distribution: one persistent CTA per SM.  Every sub-copy has a claim counter;
+// a CTA starts at the sub-copy where an even split of all tiles would put it, claims
+// chunks of STRIP_WARPS*span tiles until that sub-copy is exhausted, then moves on
+// (cyclically).  Claims only decide WHO computes a tile, never the arithmetic, so the
+// results stay bit-reproducible.  The last CTA to finish re-arms the counters.
+template <int U>
+__global__ void __launch_bounds__(STRIP_THREADS, 1)
+ice_sweep_strips_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span,
+                        int64_t total_tiles, const double* __restrict__ w,
+                        unsigned long long* __restrict__ claim,
+                        const int32_t* __restrict__ all_done) {
+  extern __shared__ double w_s[];
+  __shared__ unsigned long long s_claim;
+  if (*all_done) return;
+  const int warp = threadIdx.x >> 5;
+  const int64_t g0 = total_tiles * (int64_t)blockIdx.x / gridDim.x;
+  int lo = 0, hi = n_subs;                         // sub-copy that holds global tile g0
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (subs[mid].first_tile <= g0) lo = mid; else hi = mid;
+  }
+  const int64_t chunk = (int64_t)STRIP_WARPS * span;
+  int k = lo, loaded = -1;
+  for (int visited = 0; visited < n_subs; ++visited, k = (k + 1 == n_subs) ? 0 : k + 1) {
+    const cb200_sub sub = subs[k];
+    const int64_t n_tiles = (sub.nnz + WARP_TILE - 1) / WARP_TILE;
+    while (true) {
+      __syncthreads();                             // previous chunk done: s_claim and w_s are free
+      if (threadIdx.x == 0) s_claim = atomicAdd(&claim[k], (unsigned long long)chunk);
+      __syncthreads();
+      const int64_t c0 = (int64_t)s_claim;
+      if (c0 >= n_tiles) break;
+      if (loaded != k) {                           // stage this strip's slice of w
+        for (int i = threadIdx.x; i < sub.gather_len; i += STRIP_THREADS) w_s[i] = w[sub.gather_base + i];
+        loaded = k;
+        __syncthreads();
+      }
+      const int64_t c1 = min(c0 + chunk, n_tiles);
+      const int64_t t0 = c0 + (int64_t)warp * span;
+      if (t0 < c1) {
+        IceOpSmem op{w_s, sub.gather_base};
+        walk_reduce_span<IceOpSmem, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
+                                       sub.nnz, t0, min(t0 + span, c1), op, sub.direct, sub.pieces);
+      }
+    }
+  }
+  // re-arm the claim counters once every CTA is through
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(&claim[n_subs], 1ULL);
+    if (ticket == gridDim.x - 1) {
+      for (int i = 0; i <= n_subs; ++i) claim[i] = 0ULL;
+      __threadfence();
+    }
   }
 }
 
-__global__ void ice_combine_kernel(const int64_t* __restrict__ indptr_a, int64_t nnz_a,
-                                   const double* __restrict__ direct_a, const double* __restrict__ pieces_a,
-                                   const int64_t* __restrict__ indptr_b, int64_t nnz_b,
-                                   const double* __restrict__ direct_b, const double* __restrict__ pieces_b,
-                                   int n_bins, double* __restrict__ s, const int32_t* __restrict__ all_done) {
+// s[i] = sum over sub-copies (fixed order) of the row total of bin i.
+__global__ void ice_combine_kernel(const cb200_sub* __restrict__ subs, int n_subs, int n_bins,
+                                   double* __restrict__ s, const int32_t* __restrict__ all_done) {
   if (*all_done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_bins) return;
-  s[i] = row_total<double>(i, indptr_a, nnz_a, direct_a, pieces_a) +
-         row_total<double>(i, indptr_b, nnz_b, direct_b, pieces_b);
+  double v = 0.0;
+  for (int k = 0; k < n_subs; ++k)
+    v += row_total<double>(i, subs[k].indptr, subs[k].nnz, subs[k].direct, subs[k].pieces);
+  s[i] = v;
 }
 
 constexpr int UPD_THREADS = 256;
@@ -179,14 +256,51 @@ using namespace cb200;
 
 extern "C" {
 
+int cb200_set_tuning(int32_t ice_unroll) {
+  if (ice_unroll != 1 && ice_unroll != 2 && ice_unroll != 4 && ice_unroll != 8) return -1;
+  g_ice_unroll = ice_unroll;
+  return 0;
+}
+
 int cb200_ice_sweep(const cb200_ice* st, void* stream) {
-  const int64_t ta = ceil_div64(st->csr.nnz, WARP_TILE), tb = ceil_div64(st->csc.nnz, WARP_TILE);
-  const int64_t blocks = ceil_div64(ta + tb, WARPS_PER_BLOCK);
-  if (blocks <= 0) return 0;
-  ice_sweep_kernel<<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const int2*>(st->csr.px), st->csr.indptr, st->csr.tile_row, st->csr.nnz, ta,
-      st->direct_row, st->pieces_row, reinterpret_cast<const int2*>(st->csc.px), st->csc.indptr,
-      st->csc.tile_row, st->csc.nnz, tb, st->direct_col, st->pieces_col, st->w, st->all_done);
+  if (st->total_warps <= 0 || st->n_subs <= 0) return 0;
+  if (st->smem_bins > 0) {                          // column strips: persistent shared-memory kernel
+    const size_t smem = (size_t)st->smem_bins * sizeof(double);
+    static size_t attr_bytes = 0;
+    if (smem > attr_bytes) {
+      if (smem > 226 * 1024) {
+        set_error_msg("ice_sweep: strip slice does not fit shared memory");
+        return -1;
+      }
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_bytes = smem;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_ice_unroll == 1)
+      ice_sweep_strips_kernel<1><<<sms, STRIP_THREADS, smem, (cudaStream_t)stream>>>(
+          st->subs, st->n_subs, st->span, st->total_tiles, st->w,
+          reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
+    else
+      ice_sweep_strips_kernel<2><<<sms, STRIP_THREADS, smem, (cudaStream_t)stream>>>(
+          st->subs, st->n_subs, st->span, st->total_tiles, st->w,
+          reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
+    CB_LAUNCH_CHECK("ice_sweep_strips");
+    return 0;
+  }
+  const int64_t blocks = ceil_div64(st->total_warps, WARPS_PER_BLOCK);
+#define CB_SWEEP(U)                                                                    \
+  ice_sweep_kernel<U><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(   \
+      st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done)
+  switch (g_ice_unroll) {
+    case 1: CB_SWEEP(1); break;
+    case 4: CB_SWEEP(4); break;
+    case 8: CB_SWEEP(8); break;
+    default: CB_SWEEP(2); break;
+  }
+#undef CB_SWEEP
   CB_LAUNCH_CHECK("ice_sweep");
   return 0;
 }
@@ -194,8 +308,7 @@ int cb200_ice_sweep(const cb200_ice* st, void* stream) {
 int cb200_ice_combine(const cb200_ice* st, void* stream) {
   if (st->n_bins <= 0) return 0;
   ice_combine_kernel<<<(unsigned)ceil_div64(st->n_bins, 256), 256, 0, (cudaStream_t)stream>>>(
-      st->csr.indptr, st->csr.nnz, st->direct_row, st->pieces_row, st->csc.indptr, st->csc.nnz,
-      st->direct_col, st->pieces_col, st->n_bins, st->s, st->all_done);
+      st->subs, st->n_subs, st->n_bins, st->s, st->all_done);
   CB_LAUNCH_CHECK("ice_combine");
   return 0;
 }

@@ -208,15 +208,16 @@ static size_t sort_ws_bytes(int64_t n) {
 }
 
 int sort_pairs(const int32_t* keys_in, const int2* vals_in, int32_t* keys_out, int2* vals_out,
-               int32_t* keys_tmp, int2* vals_tmp, int64_t n, int key_bits, void* ws,
+               int32_t* keys_tmp, int2* vals_tmp, int64_t n, int key_shift, int key_bits, void* ws,
                size_t ws_bytes, cudaStream_t st) {
   if (ws_bytes < sort_ws_bytes(n)) {
     set_error_msg("sort workspace too small");
     return -1;
   }
   if (n <= 0) return 0;
+  if (key_shift < 0) key_shift = 0;
   if (key_bits < 1) key_bits = 1;
-  if (key_bits > 31) key_bits = 31;
+  if (key_shift + key_bits > 31) key_bits = 31 - key_shift;
   const int passes = (key_bits + 7) / 8;
   const int bits = (key_bits + passes - 1) / passes;
   const int64_t nblocks = ceil_div64(n, SORT_TILE);
@@ -235,8 +236,8 @@ int sort_pairs(const int32_t* keys_in, const int2* vals_in, int32_t* keys_out, i
   const int32_t* ksrc = keys_in;
   const int2* vsrc = vals_in;
   for (int k = 0; k < passes; ++k) {
-    const int shift = k * bits;
-    const int nb = (k == passes - 1) ? (key_bits - shift) : bits;
+    const int shift = key_shift + k * bits;
+    const int nb = (k == passes - 1) ? (key_bits - k * bits) : bits;
     const int mask = (1 << nb) - 1;
     const bool to_out = ((passes - k) % 2) == 1;
     int32_t* kdst = to_out ? keys_out : keys_tmp;
@@ -269,10 +270,11 @@ size_t cb200_sort_workspace_bytes(int64_t n) { return cb200::sort_ws_bytes(n); }
 
 int cb200_sort_pairs(const int32_t* keys_in, const cb200_px* vals_in, int32_t* keys_out,
                      cb200_px* vals_out, int32_t* keys_tmp, cb200_px* vals_tmp, int64_t n,
-                     int key_bits, void* workspace, size_t workspace_bytes, void* stream) {
+                     int key_shift, int key_bits, void* workspace, size_t workspace_bytes,
+                     void* stream) {
   return cb200::sort_pairs(keys_in, reinterpret_cast<const int2*>(vals_in), keys_out,
                            reinterpret_cast<int2*>(vals_out), keys_tmp,
-                           reinterpret_cast<int2*>(vals_tmp), n, key_bits, workspace,
+                           reinterpret_cast<int2*>(vals_tmp), n, key_shift, key_bits, workspace,
                            workspace_bytes, (cudaStream_t)stream);
 }
 

@@ -40,12 +40,44 @@ __global__ void tile_rows_kernel(const int64_t* __restrict__ indptr, int n_rows,
 
 // --------------------------------------------------- indptr from sorted ----
 __global__ void indptr_from_sorted_kernel(const int32_t* __restrict__ keys, int64_t n, int n_rows,
-                                          int64_t* __restrict__ indptr) {
+                                          int shift, int64_t* __restrict__ indptr) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += stride) {
-    const int prev = (p == 0) ? -1 : keys[p - 1];
-    const int cur = (p == n) ? n_rows : keys[p];
+    const int prev = (p == 0) ? -1 : (keys[p - 1] >> shift);
+    const int cur = (p == n) ? n_rows : (keys[p] >> shift);
     for (int r = prev + 1; r <= cur; ++r) indptr[r] = p;
+  }
+}
+
+// ---------------------------------------------------------- strip helpers ----
+// (key, {a, v}) -> (a, {key, v}): makes the gathered index the sort key.
+__global__ void swap_key_other_kernel(const int32_t* __restrict__ keys, const int2* __restrict__ vals,
+                                      int64_t n, int32_t* __restrict__ keys_out,
+                                      int2* __restrict__ vals_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int2 v = vals[i];
+    keys_out[i] = v.x;
+    vals_out[i] = make_int2(keys[i], v.y);
+  }
+}
+
+// Elements are grouped by strip = key >> shift (tight packing, strip s starts at
+// strip_start[s]).  Writes px {key, count} and the row id of every element at
+// p + pad_before[s], which makes every strip start at an even (16-byte aligned)
+// position (the pad record between strips is never used: walkers stop at nnz).
+__global__ void strip_finish_kernel(const int32_t* __restrict__ keys, const int2* __restrict__ vals,
+                                    int64_t n, int shift,
+                                    const int64_t* __restrict__ pad_before,
+                                    int2* __restrict__ px_out, int32_t* __restrict__ rows_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int k = keys[i];
+    const int s = k >> shift;
+    const int2 v = vals[i];
+    const int64_t o = i + pad_before[s];
+    px_out[o] = make_int2(k, v.y);
+    rows_out[o] = v.x;
   }
 }
 
@@ -144,7 +176,7 @@ marginals_sweep_kernel(const int2* __restrict__ px, const int64_t* __restrict__ 
   const int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (t >= n_tiles) return;
   NnzSumOp op;
-  walk_reduce_tile<NnzSumOp, 4>(px, indptr, nnz, t, tile_row[t], op, direct, pieces);
+  walk_reduce_tile<NnzSumOp, 4>(px, indptr, nnz, t, tile_row, op, direct, pieces);
 }
 
 // direct is laid over (nnz_out, sum_out) as scratch is not possible (interleaved
@@ -195,13 +227,37 @@ int cb200_tile_rows(const int64_t* indptr, int32_t n_rows, int64_t nnz, int32_t*
   return 0;
 }
 
-int cb200_indptr_from_sorted(const int32_t* keys, int64_t n, int32_t n_rows, int64_t* indptr,
-                             void* stream) {
+int cb200_indptr_from_sorted(const int32_t* keys, int64_t n, int32_t n_rows, int32_t shift,
+                             int64_t* indptr, void* stream) {
   int64_t blocks = ceil_div64(n + 1, 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
   indptr_from_sorted_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(keys, n, n_rows,
-                                                                               indptr);
+                                                                               shift, indptr);
   CB_LAUNCH_CHECK("indptr_from_sorted");
+  return 0;
+}
+
+int cb200_swap_key_other(const int32_t* keys, const cb200_px* vals, int64_t n, int32_t* keys_out,
+                         cb200_px* vals_out, void* stream) {
+  if (n <= 0) return 0;
+  int64_t blocks = ceil_div64(n, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  swap_key_other_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      keys, reinterpret_cast<const int2*>(vals), n, keys_out, reinterpret_cast<int2*>(vals_out));
+  CB_LAUNCH_CHECK("swap_key_other");
+  return 0;
+}
+
+int cb200_strip_finish(const int32_t* keys, const cb200_px* vals, int64_t n, int32_t shift,
+                       const int64_t* pad_before, cb200_px* px_out, int32_t* rows_out,
+                       void* stream) {
+  if (n <= 0) return 0;
+  int64_t blocks = ceil_div64(n, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  strip_finish_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      keys, reinterpret_cast<const int2*>(vals), n, shift, pad_before,
+      reinterpret_cast<int2*>(px_out), rows_out);
+  CB_LAUNCH_CHECK("strip_finish");
   return 0;
 }
 

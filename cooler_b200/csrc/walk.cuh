@@ -27,41 +27,63 @@ __device__ __forceinline__ double acc_wsum(double x) { return warp_sum(x); }
 __device__ __forceinline__ I64x2 acc_wsum(I64x2 x) { return I64x2{warp_sum(x.a), warp_sum(x.b)}; }
 
 // Op: struct with  typedef T;  __device__ T value(int other, int count) const;
+//
+// One warp streams through the consecutive tiles [t_begin, t_end) of a copy.
+// The pixel stream is software-pipelined in registers: the U 128-bit loads of
+// group g+1 are issued before group g is consumed, across tile boundaries, so
+// a warp always has 512*U bytes of the stream in flight next to its gathers.
+// A "group" is U chunks (U*64 pixels); WARP_TILE is a multiple of the group.
 template <typename Op, int U>
-__device__ __forceinline__ void walk_reduce_tile(const int2* __restrict__ px,
-                                                 const int64_t* __restrict__ indptr, int64_t nnz,
-                                                 int64_t t, int row0, const Op& op,
-                                                 typename Op::T* __restrict__ direct,
+__device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
+                                                 const int64_t* __restrict__ indptr,
+                                                 const int32_t* __restrict__ tile_row,
+                                                 int64_t nnz, int64_t t_begin, int64_t t_end,
+                                                 const Op& op, typename Op::T* __restrict__ direct,
                                                  typename Op::T* __restrict__ pieces) {
   typedef typename Op::T T;
+  static_assert(WARP_TILE % (CHUNK * U) == 0, "tile must be a whole number of groups");
   const int lane = threadIdx.x & 31;
-  const int64_t p0 = t * (int64_t)WARP_TILE;
-  const int64_t p1 = min(p0 + (int64_t)WARP_TILE, nnz);
-  int row = row0;
+  const int64_t pbeg = t_begin * (int64_t)WARP_TILE;
+  const int64_t pend = min(t_end * (int64_t)WARP_TILE, nnz);
+  const int4* __restrict__ src = reinterpret_cast<const int4*>(px);
+
+  int4 qn[U];                                      // next group (in flight)
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int64_t pos = pbeg + u * CHUNK + 2 * lane;
+    qn[u] = (pos < pend) ? ld_stream_int4(src + (pos >> 1)) : make_int4(0, 0, 0, 0);
+  }
+  int row = tile_row[t_begin];
   int64_t row_end = indptr[row + 1];
   T acc = acc_zero((T*)nullptr);
   bool first = true;
+  int64_t t = t_begin;
+  int64_t tile_end = min(pbeg + (int64_t)WARP_TILE, nnz);
 
-  for (int64_t c = p0; c < p1; c += (int64_t)CHUNK * U) {
+  for (int64_t c = pbeg; c < pend; c += (int64_t)CHUNK * U) {
     int4 q[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t pos = c + u * CHUNK + 2 * lane;
-      q[u] = (pos < p1) ? ld_stream_int4(reinterpret_cast<const int4*>(px + pos))
-                        : make_int4(0, 0, 0, 0);
+    for (int u = 0; u < U; ++u) q[u] = qn[u];
+    {                                              // issue the next group's loads
+      const int64_t cn = c + (int64_t)CHUNK * U;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t pos = cn + u * CHUNK + 2 * lane;
+        if (pos < pend) qn[u] = ld_stream_int4(src + (pos >> 1));
+      }
     }
     T v0[U], v1[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t pos = c + u * CHUNK + 2 * lane;
-      v0[u] = (pos < p1) ? op.value(q[u].x, q[u].y) : acc_zero((T*)nullptr);
-      v1[u] = (pos + 1 < p1) ? op.value(q[u].z, q[u].w) : acc_zero((T*)nullptr);
+      v0[u] = (pos < pend) ? op.value(q[u].x, q[u].y) : acc_zero((T*)nullptr);
+      v1[u] = (pos + 1 < pend) ? op.value(q[u].z, q[u].w) : acc_zero((T*)nullptr);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t cbeg = c + u * CHUNK;
-      if (cbeg >= p1) break;
-      const int64_t cend = min(cbeg + (int64_t)CHUNK, p1);
+      if (cbeg >= pend) break;
+      const int64_t cend = min(cbeg + (int64_t)CHUNK, pend);
       if (cend <= row_end) {                       // whole chunk inside the current row
         acc = acc_add(acc, acc_add(v0[u], v1[u]));
       } else {                                     // one or more rows end inside this chunk
@@ -85,9 +107,32 @@ __device__ __forceinline__ void walk_reduce_tile(const int2* __restrict__ px,
         }
       }
     }
+    if (c + (int64_t)CHUNK * U >= tile_end) {      // tile finished: emit its closing piece
+      T tot = acc_wsum(acc);
+      if (lane == 0) pieces[2 * t + (first ? 0 : 1)] = tot;
+      acc = acc_zero((T*)nullptr);
+      first = true;
+      ++t;
+      const int64_t tile_start = tile_end;         // first pixel of the next tile
+      tile_end = min(tile_end + (int64_t)WARP_TILE, nnz);
+      if (tile_start < pend && row_end <= tile_start) {
+        do {                                       // the row ended exactly at the tile boundary
+          ++row;
+          row_end = indptr[row + 1];
+        } while (row_end <= tile_start);
+      }
+    }
   }
-  T tot = acc_wsum(acc);
-  if (lane == 0) pieces[2 * t + (first ? 0 : 1)] = tot;
+}
+
+// Single-tile form (integer marginals and other one-time passes).
+template <typename Op, int U>
+__device__ __forceinline__ void walk_reduce_tile(const int2* __restrict__ px,
+                                                 const int64_t* __restrict__ indptr, int64_t nnz,
+                                                 int64_t t, const int32_t* __restrict__ tile_row,
+                                                 const Op& op, typename Op::T* __restrict__ direct,
+                                                 typename Op::T* __restrict__ pieces) {
+  walk_reduce_span<Op, U>(px, indptr, tile_row, nnz, t, t + 1, op, direct, pieces);
 }
 
 // Total of row r from the outputs of walk_reduce_tile.

@@ -93,8 +93,8 @@ def exclusive_scan_i32(x):
     return out
 
 
-def sort_pairs(keys, vals, key_bits):
-    """Stable sort of (int32 key, int32x2 value) by the low ``key_bits`` bits of key."""
+def sort_pairs(keys, vals, key_bits, key_shift=0):
+    """Stable sort of (int32 key, int32x2 value) by key bits [key_shift, key_shift + key_bits)."""
     n = keys.numel()
     dev = keys.device
     keys_out = torch.empty(n, dtype=_I32, device=dev)
@@ -107,13 +107,13 @@ def sort_pairs(keys, vals, key_bits):
     ws_bytes = _lib.load().cb200_sort_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     _lib.call("cb200_sort_pairs", _ptr(keys), _ptr(vals), _ptr(keys_out), _ptr(vals_out),
-              _ptr(keys_tmp), _ptr(vals_tmp), n, int(key_bits), _ptr(ws), ws_bytes, _stream())
+              _ptr(keys_tmp), _ptr(vals_tmp), n, int(key_shift), int(key_bits), _ptr(ws), ws_bytes, _stream())
     return keys_out, vals_out
 
 
-def indptr_from_sorted(keys, n, n_rows):
+def indptr_from_sorted(keys, n, n_rows, shift=0):
     out = torch.empty(n_rows + 1, dtype=_I64, device=keys.device)
-    _lib.call("cb200_indptr_from_sorted", _ptr(keys), int(n), int(n_rows), _ptr(out), _stream())
+    _lib.call("cb200_indptr_from_sorted", _ptr(keys), int(n), int(n_rows), int(shift), _ptr(out), _stream())
     return out
 
 
@@ -149,12 +149,57 @@ def filter_copy(copy, row_lo, row_hi, ndiag, keep, *, want_rows=False, want_tran
     return new, (tkey[:kept] if tkey is not None else None), tval
 
 
-def transpose_from(tkey, tval, n_rows):
+def transpose_from(tkey, tval, n_rows, return_keys=False):
     """(key = other bin, val = {row, count}) in row-major order -> the other-major copy."""
     n = tkey.numel()
     keys_sorted, vals_sorted = sort_pairs(tkey, tval, key_bits_for(n_rows))
     indptr = indptr_from_sorted(keys_sorted, n, n_rows)
-    return TableCopy(vals_sorted, indptr, n, n_rows)
+    copy = TableCopy(vals_sorted, indptr, n, n_rows)
+    return (copy, keys_sorted) if return_keys else copy
+
+
+def swap_key_other(keys, vals, n):
+    """(key, {a, v}) -> (a, {key, v})."""
+    dev = keys.device
+    keys_out = torch.empty(max(n, 1), dtype=_I32, device=dev)
+    vals_out = _new_px(n, dev)
+    _lib.call("cb200_swap_key_other", _ptr(keys), _ptr(vals), int(n), _ptr(keys_out), _ptr(vals_out), _stream())
+    return keys_out[:n], vals_out
+
+
+def strip_partition(key_other, val_rowcount, n, n_rows, shift):
+    """Split a row-ordered stream (key = gathered bin, val = {row, count}) into column
+    strips ``key >> shift``; every strip becomes a TableCopy of its own (views into one
+    buffer, strip starts 16-byte aligned).  Row order inside a strip is preserved
+    (stable radix pass), so a strip is a valid row-major copy."""
+    dev = key_other.device
+    n_strips = ((max(n_rows, 1) - 1) >> shift) + 1
+    if n == 0:
+        return []
+    ks, vs = sort_pairs(key_other, val_rowcount, key_bits_for(n_strips), key_shift=shift)
+    start = indptr_from_sorted(ks, n, n_strips, shift).cpu().numpy()
+    counts = np.diff(start)
+    pad_before = np.r_[0, np.cumsum(counts & 1)[:-1]].astype(np.int64)
+    aligned = start[:-1] + pad_before
+    total = int(n + n_strips + 2)
+    px_out = torch.empty((total, 2), dtype=_I32, device=dev)
+    rows_out = torch.empty(total, dtype=_I32, device=dev)
+    pad_d = torch.from_numpy(pad_before).to(dev)
+    _lib.call("cb200_strip_finish", _ptr(ks), _ptr(vs), int(n), int(shift), _ptr(pad_d), _ptr(px_out),
+              _ptr(rows_out), _stream())
+    del ks, vs
+    subs = []
+    for s_ in range(n_strips):
+        c = int(counts[s_])
+        if c == 0:
+            continue
+        a = int(aligned[s_])
+        rows_s = rows_out[a:a + c]
+        indptr = indptr_from_sorted(rows_s, c, n_rows)
+        sub = TableCopy(px_out[a:a + c + 2], indptr, c, n_rows)
+        sub.strip = s_
+        subs.append(sub)
+    return subs
 
 
 def marginals_i64(copy):

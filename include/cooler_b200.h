@@ -43,8 +43,8 @@ size_t cb200_scan_workspace_bytes(int64_t n);
 int cb200_exclusive_scan_i32(const int32_t* in, int64_t* out, int64_t n,
                              void* workspace, size_t workspace_bytes, void* stream);
 
-/* Stable LSD radix sort of (key, 8-byte value) pairs on the low `key_bits`
- * bits of the key.  Result lands in keys_out/vals_out; *_tmp are scratch of
+/* Stable LSD radix sort of (key, 8-byte value) pairs on key bits
+ * [key_shift, key_shift + key_bits).  Result lands in keys_out/vals_out; *_tmp are scratch of
  * the same size.  Replaces nothing in the reference directly: it builds the
  * transposed (bin2-major) copy that the reference re-derives every pass with
  * np.bincount(bin2_id) (src/cooler/_balance.py:63-69), and is the sort of the
@@ -53,7 +53,7 @@ size_t cb200_sort_workspace_bytes(int64_t n);
 int cb200_sort_pairs(const int32_t* keys_in, const cb200_px* vals_in,
                      int32_t* keys_out, cb200_px* vals_out,
                      int32_t* keys_tmp, cb200_px* vals_tmp,
-                     int64_t n, int key_bits,
+                     int64_t n, int key_shift, int key_bits,
                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- pixel table build (replaces parallel.chunkgetter re-reading the file
@@ -66,9 +66,20 @@ int cb200_pack_pixels(const int64_t* bin2_id, const int32_t* count, int64_t nnz,
 /* tile_row[t] = row that contains pixel t*warp_tile (n_tiles entries). */
 int cb200_tile_rows(const int64_t* indptr, int32_t n_rows, int64_t nnz,
                     int32_t* tile_row, void* stream);
-/* indptr[r] = first position p with keys[p] >= r, r = 0..n_rows (keys sorted). */
-int cb200_indptr_from_sorted(const int32_t* keys, int64_t n, int32_t n_rows,
+/* indptr[r] = first position p with (keys[p] >> shift) >= r, r = 0..n_rows (keys sorted). */
+int cb200_indptr_from_sorted(const int32_t* keys, int64_t n, int32_t n_rows, int32_t shift,
                              int64_t* indptr, void* stream);
+/* Column strips ("cache blocking" of the gathered bias vector): a copy can be
+ * split into strips by other >> shift, each strip again a row-ordered copy, so
+ * that the slice of the bias vector one strip gathers from stays L1-resident.
+ * swap: (key, {a, v}) -> (a, {key, v}).  finish: elements grouped by strip
+ * (key >> shift) -> px {key, count} and row ids, element i written at
+ * i + pad_before[strip] so that every strip starts 16-byte aligned. */
+int cb200_swap_key_other(const int32_t* keys, const cb200_px* vals, int64_t n,
+                         int32_t* keys_out, cb200_px* vals_out, void* stream);
+int cb200_strip_finish(const int32_t* keys, const cb200_px* vals, int64_t n, int32_t shift,
+                       const int64_t* pad_before, cb200_px* px_out, int32_t* rows_out,
+                       void* stream);
 
 /* Static pixel filter.  A pixel (row r, other c) is KEPT iff
  *   !(ndiag > 0 && |r - c| < ndiag)                       (_zero_diags)
@@ -112,8 +123,25 @@ int cb200_marginals_i64(const cb200_copy* copy, int32_t n_rows,
 /* ---- ICE iteration (replaces the PASS C map-reduce + the O(n_bins) numpy
  *      update of _balance_genomewide/_cisonly/_transonly,
  *      src/cooler/_balance.py:72-260) ------------------------------------- */
+/* A sub-copy swept by K3: a whole copy or one column strip of it. */
 typedef struct {
-  cb200_copy csr, csc;       /* bin1-major and bin2-major copies (static filters applied) */
+  const cb200_px* px; const int64_t* indptr; const int32_t* tile_row; int64_t nnz;
+  double*  direct;           /* [n_bins] rows closed strictly inside a warp tile */
+  double*  pieces;           /* [2 * n_tiles] first / last row of every warp tile */
+  int64_t  first_warp;       /* prefix sum over sub-copies of ceil(n_tiles / span) */
+  int64_t  first_tile;       /* prefix sum over sub-copies of n_tiles */
+  int32_t  gather_base;      /* `other` of this sub-copy lies in [gather_base, gather_base + gather_len) */
+  int32_t  gather_len;
+} cb200_sub;
+
+typedef struct {
+  const cb200_sub* subs;     /* DEVICE array: bin1-major sub-copies then bin2-major ones (static filters applied) */
+  int32_t  n_subs;
+  int32_t  span;             /* warp tiles per warp in K3 */
+  int64_t  total_warps;      /* sum over sub-copies of ceil(n_tiles / span) */
+  int64_t  total_tiles;      /* sum over sub-copies of n_tiles */
+  int32_t  smem_bins;        /* 0: gather through L1/L2; else max gather_len (column strips staged in shared memory) */
+  int64_t* claim;            /* [n_subs + 1] zero-initialised work-claim counters of the strip kernel (self re-arming) */
   int32_t  n_bins;
   int32_t  n_segs;           /* 1 (genome-wide / trans) or n_chroms (cis_only) */
   const int32_t* seg_offset; /* [n_segs + 1] bin range of each independently balanced segment */
@@ -124,9 +152,6 @@ typedef struct {
   double*  bias;             /* [n_bins] in/out */
   const double* cweights;    /* [n_bins] or NULL (trans_only: 1/(1 - nbins_chrom/n_bins), _balance.py:214-220) */
   double*  w;                /* [n_bins] gathered vector = bias * cweights (may alias bias when cweights == NULL) */
-  /* sweep outputs (scratch) */
-  double*  direct_row; double* pieces_row;   /* [n_bins], [2 * n_tiles(csr)] */
-  double*  direct_col; double* pieces_col;   /* [n_bins], [2 * n_tiles(csc)] */
   double*  s;                /* [n_bins] per-bin sum  sum_j w_j x_ij  (row + column part); allreduced across ranks */
   double*  marg;             /* [n_bins] scratch */
   double*  blk_sum; double* blk_cnt; double* blk_dev;  /* [n_blocks] scratch */
@@ -142,7 +167,11 @@ typedef struct {
   int32_t  max_iters;
 } cb200_ice;
 
-/* K3: both marginal sweeps (CSR rows, CSC columns), one launch.  No-op once *all_done. */
+/* Tuning of K3 (optional): ice_unroll in {1,2,4,8} = 128-bit stream loads kept in
+ * flight per lane (default 2). */
+int cb200_set_tuning(int32_t ice_unroll);
+/* K3: the marginal sweeps of every sub-copy (bin1-major rows, bin2-major columns), one
+ * launch.  No-op once *all_done. */
 int cb200_ice_sweep(const cb200_ice* st, void* stream);
 /* s[i] = rowpart(i) + colpart(i) -- the vector ranks all-reduce.  No-op once *all_done. */
 int cb200_ice_combine(const cb200_ice* st, void* stream);
