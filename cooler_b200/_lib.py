@@ -44,7 +44,7 @@ class Ice(C.Structure):
         ("seg_mean", C.c_void_p), ("seg_nnz", C.c_void_p),
         ("seg_scale", C.c_void_p), ("seg_var", C.c_void_p),
         ("seg_iters", C.c_void_p), ("seg_done", C.c_void_p), ("seg_empty", C.c_void_p),
-        ("all_done", C.c_void_p), ("var_hist", C.c_void_p),
+        ("all_done", C.c_void_p), ("tickets", C.c_void_p), ("var_hist", C.c_void_p),
         ("tol", C.c_double), ("max_iters", C.c_int32),
     ]
 
@@ -72,7 +72,7 @@ SIGNATURES = {
     "cb200_set_tuning": (C.c_int, [_I32]),
     "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_combine": (C.c_int, [C.POINTER(Ice), _P]),
-    "cb200_ice_update": (C.c_int, [C.POINTER(Ice), _I32, _P]),
+    "cb200_ice_update": (C.c_int, [C.POINTER(Ice), _I32, _I32, _P]),
     "cb200_coarsen_remap": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
     "cb200_runs_count": (C.c_int, [_P, _P, _I64, _P, _P]),
     "cb200_runs_write": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P]),

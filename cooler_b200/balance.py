@@ -208,6 +208,7 @@ class IceState:
         for k in ("seg_iters", "seg_done", "seg_empty"):
             t[k] = torch.zeros(max(S, 1), dtype=_I32, device=dev)
         t["all_done"] = torch.zeros(1, dtype=_I32, device=dev)
+        t["tickets"] = torch.zeros(2, dtype=_I32, device=dev)
         t["var_hist"] = f64(self.max_iters * S, float("nan"))
         st = _lib.Ice()
         st.n_subs, st.span, st.total_warps, st.total_tiles = len(subs), span, warp0, total_tiles
@@ -216,7 +217,7 @@ class IceState:
         for k in ("subs", "claim", "seg_offset", "blk_seg", "blk_lo", "blk_hi", "seg_blk_offset", "bias", "cweights", "w",
                   "s", "marg", "blk_sum", "blk_cnt",
                   "blk_dev", "seg_mean", "seg_nnz", "seg_scale", "seg_var", "seg_iters", "seg_done",
-                  "seg_empty", "all_done", "var_hist"):
+                  "seg_empty", "all_done", "tickets", "var_hist"):
             setattr(st, k, t[k].data_ptr() if t[k] is not None else None)
         st.tol, st.max_iters = float(tol), self.max_iters
         self.st = st
@@ -248,10 +249,14 @@ class IceState:
             self.sweep_events.append((e0, e1))
         else:
             _lib.call("cb200_ice_sweep", st, stream)
-        _lib.call("cb200_ice_combine", st, stream)
-        _allreduce(self.t["s"], self.prob.group)
-        _lib.call("cb200_ice_update", st, int(it), stream)
-        self.launches += 6
+        if self.prob.group is None:                   # single GPU: combine fused into K4a
+            _lib.call("cb200_ice_update", st, int(it), 1, stream)
+            self.launches += 3
+        else:
+            _lib.call("cb200_ice_combine", st, stream)
+            _allreduce(self.t["s"], self.prob.group)
+            _lib.call("cb200_ice_update", st, int(it), 0, stream)
+            self.launches += 4
 
     def run(self, check_every=8):
         """Iterate until every segment converged or max_iters.  Returns passes launched."""

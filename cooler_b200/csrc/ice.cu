@@ -146,105 +146,125 @@ __device__ __forceinline__ double block_sum(double v, double* sm) {
   return t;  // valid in thread 0
 }
 
-// K4a: marg = w * s; per-block sum and count of the nonzero marginals.
+// Deterministic "last block finishes" pattern: every block publishes its partials,
+// takes a ticket, and the block that draws the last ticket reduces all partials in a
+// fixed order.  The ticket only elects WHO reduces; the summation order is fixed.
+__device__ __forceinline__ bool last_block_ticket(int32_t* ticket) {
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int t = atomicAdd(ticket, 1);
+    s_last = (t == (int)gridDim.x - 1);
+    if (s_last) *ticket = 0;                       // re-arm for the next launch
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// K4a: [s = row totals over sub-copies] -> marg = w * s -> per-block sum / count of the
+// nonzero marginals -> (last block) per-segment mean.
+template <bool kCombine>
 __global__ void __launch_bounds__(UPD_THREADS)
 ice_marg_kernel(cb200_ice st) {
   __shared__ double sm[UPD_THREADS / 32];
   if (*st.all_done) return;
   const int b = blockIdx.x;
   const int seg = st.blk_seg[b];
-  if (st.seg_done[seg]) return;
-  const int lo = st.blk_lo[b], hi = st.blk_hi[b];
-  double sum = 0.0, cnt = 0.0;
-  for (int i = lo + threadIdx.x; i < hi; i += UPD_THREADS) {
-    const double m = st.w[i] * st.s[i];
-    st.marg[i] = m;
-    if (m != 0.0) { sum += m; cnt += 1.0; }
-  }
-  const double bs = block_sum(sum, sm);
-  const double bc = block_sum(cnt, sm);
-  if (threadIdx.x == 0) { st.blk_sum[b] = bs; st.blk_cnt[b] = bc; }
-}
-
-// one block; warp per segment
-__global__ void __launch_bounds__(1024)
-ice_mean_kernel(cb200_ice st) {
-  if (*st.all_done) return;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int seg = wid; seg < st.n_segs; seg += 32) {
-    if (st.seg_done[seg]) continue;
+  if (!st.seg_done[seg]) {
+    const int lo = st.blk_lo[b], hi = st.blk_hi[b];
     double sum = 0.0, cnt = 0.0;
-    for (int b = st.seg_blk_offset[seg] + lane; b < st.seg_blk_offset[seg + 1]; b += 32) {
-      sum += st.blk_sum[b];
-      cnt += st.blk_cnt[b];
+    for (int i = lo + threadIdx.x; i < hi; i += UPD_THREADS) {
+      double si;
+      if (kCombine) {
+        si = 0.0;
+        for (int k = 0; k < st.n_subs; ++k)
+          si += row_total<double>(i, st.subs[k].indptr, st.subs[k].nnz, st.subs[k].direct, st.subs[k].pieces);
+      } else {
+        si = st.s[i];
+      }
+      const double m = st.w[i] * si;
+      st.marg[i] = m;
+      if (m != 0.0) { sum += m; cnt += 1.0; }
+    }
+    const double bs = block_sum(sum, sm);
+    const double bc = block_sum(cnt, sm);
+    if (threadIdx.x == 0) { st.blk_sum[b] = bs; st.blk_cnt[b] = bc; }
+  }
+  if (!last_block_ticket(st.tickets)) return;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int seg2 = wid; seg2 < st.n_segs; seg2 += UPD_THREADS / 32) {
+    if (st.seg_done[seg2]) continue;
+    double sum = 0.0, cnt = 0.0;
+    for (int k = st.seg_blk_offset[seg2] + lane; k < st.seg_blk_offset[seg2 + 1]; k += 32) {
+      sum += __ldcg(st.blk_sum + k);
+      cnt += __ldcg(st.blk_cnt + k);
     }
     sum = warp_sum(sum);
     cnt = warp_sum(cnt);
     if (lane == 0) {
-      st.seg_nnz[seg] = cnt;
-      st.seg_mean[seg] = (cnt > 0.0) ? sum / cnt : nan("");
+      st.seg_nnz[seg2] = cnt;
+      st.seg_mean[seg2] = (cnt > 0.0) ? sum / cnt : nan("");
     }
   }
 }
 
-// K4b: bias /= marg/mean (0 -> 1), refresh w, per-block squared deviations.
+// K4b: bias /= marg/mean (0 -> 1), refresh w, per-block squared deviations ->
+// (last block) per-segment variance, iteration counters, convergence flags.
 __global__ void __launch_bounds__(UPD_THREADS)
-ice_update_kernel(cb200_ice st) {
+ice_update_kernel(cb200_ice st, int iter) {
   __shared__ double sm[UPD_THREADS / 32];
   if (*st.all_done) return;
   const int b = blockIdx.x;
   const int seg = st.blk_seg[b];
-  if (st.seg_done[seg]) return;
   const double nz = st.seg_nnz[seg];
-  if (nz == 0.0) return;                       // empty segment: handled in ice_var_kernel
-  const double mean = st.seg_mean[seg];
-  const int lo = st.blk_lo[b], hi = st.blk_hi[b];
-  double dev = 0.0;
-  for (int i = lo + threadIdx.x; i < hi; i += UPD_THREADS) {
-    const double m = st.marg[i];
-    if (m != 0.0) { const double d = m - mean; dev += d * d; }
-    double q = m / mean;
-    if (q == 0.0) q = 1.0;
-    const double nb = st.bias[i] / q;
-    st.bias[i] = nb;
-    if (st.cweights) st.w[i] = nb * st.cweights[i];
-    else if (st.w != st.bias) st.w[i] = nb;
+  if (!st.seg_done[seg] && nz != 0.0) {          // empty segments are finalised below
+    const double mean = st.seg_mean[seg];
+    const int lo = st.blk_lo[b], hi = st.blk_hi[b];
+    double dev = 0.0;
+    for (int i = lo + threadIdx.x; i < hi; i += UPD_THREADS) {
+      const double m = st.marg[i];
+      if (m != 0.0) { const double d = m - mean; dev += d * d; }
+      double q = m / mean;
+      if (q == 0.0) q = 1.0;
+      const double nb = st.bias[i] / q;
+      st.bias[i] = nb;
+      if (st.cweights) st.w[i] = nb * st.cweights[i];
+      else if (st.w != st.bias) st.w[i] = nb;
+    }
+    const double bd = block_sum(dev, sm);
+    if (threadIdx.x == 0) st.blk_dev[b] = bd;
   }
-  const double bd = block_sum(dev, sm);
-  if (threadIdx.x == 0) st.blk_dev[b] = bd;
-}
-
-__global__ void __launch_bounds__(1024)
-ice_var_kernel(cb200_ice st, int iter) {
-  if (*st.all_done) return;
+  if (!last_block_ticket(st.tickets + 1)) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   int my_all = 1;
-  for (int seg = wid; seg < st.n_segs; seg += 32) {
-    if (!st.seg_done[seg]) {
-      const double nz = st.seg_nnz[seg];
+  for (int seg2 = wid; seg2 < st.n_segs; seg2 += UPD_THREADS / 32) {
+    if (!st.seg_done[seg2]) {
+      const double nz2 = st.seg_nnz[seg2];
       double dev = 0.0;
-      if (nz > 0.0)
-        for (int b = st.seg_blk_offset[seg] + lane; b < st.seg_blk_offset[seg + 1]; b += 32)
-          dev += st.blk_dev[b];
+      if (nz2 > 0.0)
+        for (int k = st.seg_blk_offset[seg2] + lane; k < st.seg_blk_offset[seg2 + 1]; k += 32)
+          dev += __ldcg(st.blk_dev + k);
       dev = warp_sum(dev);
       if (lane == 0) {
-        if (nz == 0.0) {                       // _balance.py:98-102 / 166-170
-          st.seg_scale[seg] = nan("");
-          st.seg_var[seg] = 0.0;
-          st.seg_empty[seg] = 1;
-          st.seg_done[seg] = 1;
+        if (nz2 == 0.0) {                          // _balance.py:98-102 / 166-170
+          st.seg_scale[seg2] = nan("");
+          st.seg_var[seg2] = 0.0;
+          st.seg_empty[seg2] = 1;
+          st.seg_done[seg2] = 1;
         } else {
-          const double var = dev / nz;
-          st.seg_scale[seg] = st.seg_mean[seg];
-          st.seg_var[seg] = var;
-          st.seg_iters[seg] += 1;
-          if (st.var_hist) st.var_hist[(int64_t)iter * st.n_segs + seg] = var;
-          if (var < st.tol) st.seg_done[seg] = 1;
+          const double var = dev / nz2;
+          st.seg_scale[seg2] = st.seg_mean[seg2];
+          st.seg_var[seg2] = var;
+          st.seg_iters[seg2] += 1;
+          if (st.var_hist) st.var_hist[(int64_t)iter * st.n_segs + seg2] = var;
+          if (var < st.tol) st.seg_done[seg2] = 1;
         }
       }
       __syncwarp();
     }
-    if (!((volatile int32_t*)st.seg_done)[seg]) my_all = 0;   // lane 0's write, ordered by __syncwarp
+    if (!((volatile int32_t*)st.seg_done)[seg2]) my_all = 0;   // lane 0's write, ordered by __syncwarp
   }
   const int all = __syncthreads_and(my_all);
   if (threadIdx.x == 0 && all) *st.all_done = 1;
@@ -313,20 +333,16 @@ int cb200_ice_combine(const cb200_ice* st, void* stream) {
   return 0;
 }
 
-int cb200_ice_update(const cb200_ice* st, int32_t iter, void* stream) {
+int cb200_ice_update(const cb200_ice* st, int32_t iter, int32_t fused_combine, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
-  if (st->n_blocks > 0) {
-    ice_marg_kernel<<<st->n_blocks, UPD_THREADS, 0, s>>>(*st);
-    CB_LAUNCH_CHECK("ice_marg");
-  }
-  ice_mean_kernel<<<1, 1024, 0, s>>>(*st);
-  CB_LAUNCH_CHECK("ice_mean");
-  if (st->n_blocks > 0) {
-    ice_update_kernel<<<st->n_blocks, UPD_THREADS, 0, s>>>(*st);
-    CB_LAUNCH_CHECK("ice_update");
-  }
-  ice_var_kernel<<<1, 1024, 0, s>>>(*st, iter);
-  CB_LAUNCH_CHECK("ice_var");
+  if (st->n_blocks <= 0) return 0;
+  if (fused_combine)
+    ice_marg_kernel<true><<<st->n_blocks, UPD_THREADS, 0, s>>>(*st);
+  else
+    ice_marg_kernel<false><<<st->n_blocks, UPD_THREADS, 0, s>>>(*st);
+  CB_LAUNCH_CHECK("ice_marg");
+  ice_update_kernel<<<st->n_blocks, UPD_THREADS, 0, s>>>(*st, iter);
+  CB_LAUNCH_CHECK("ice_update");
   return 0;
 }
 

@@ -141,18 +141,30 @@ radix_hist(const int32_t* __restrict__ keys, int64_t n, int shift, int mask,
 
 // Stable scatter: a warp owns SORT_WARP_SPAN consecutive elements and ranks
 // them 32 at a time in element order with match.any; warps are then chained
-// per digit in warp order, so equal digits keep their input order.
+// per digit in warp order, so equal digits keep their input order.  Elements
+// are first placed at their block-local sorted position in shared memory and
+// then written out in that order, so every digit run leaves the block as one
+// contiguous, coalesced segment.
+struct ScatterSmem {
+  unsigned wcount[SORT_WARPS][RADIX];
+  unsigned lbase[RADIX];          // block-local exclusive offset of every digit
+  long long gbase[RADIX];         // global base of the digit minus lbase
+  int32_t skey[SORT_TILE];
+  int2 sval[SORT_TILE];
+};
+
 __global__ void __launch_bounds__(SORT_THREADS)
 radix_scatter(const int32_t* __restrict__ keys_in, const int2* __restrict__ vals_in,
               int32_t* __restrict__ keys_out, int2* __restrict__ vals_out, int64_t n,
               int shift, int mask, const int64_t* __restrict__ off, int nblocks) {
-  __shared__ unsigned wcount[SORT_WARPS][RADIX];
-  __shared__ long long dbase[RADIX];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ScatterSmem& sm = *reinterpret_cast<ScatterSmem*>(smem_raw);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&wcount[0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&sm.wcount[0][0])[i] = 0u;
   __syncthreads();
 
-  const int64_t wbase = (int64_t)blockIdx.x * SORT_TILE + (int64_t)wid * SORT_WARP_SPAN;
+  const int64_t tbase = (int64_t)blockIdx.x * SORT_TILE;
+  const int64_t wbase = tbase + (int64_t)wid * SORT_WARP_SPAN;
   int32_t key[SORT_STEPS];
   int2 val[SORT_STEPS];
   unsigned rank[SORT_STEPS];
@@ -171,21 +183,45 @@ radix_scatter(const int32_t* __restrict__ keys_in, const int2* __restrict__ vals
     int d = ok ? ((key[s] >> shift) & mask) : (RADIX + lane);   // invalid lanes match nobody
     unsigned peers = __match_any_sync(0xffffffffu, d);
     unsigned old = 0;
-    if (ok) old = wcount[wid][d];
+    if (ok) old = sm.wcount[wid][d];
     __syncwarp();
-    if (ok && (peers & lt) == 0) wcount[wid][d] = old + __popc(peers);
+    if (ok && (peers & lt) == 0) sm.wcount[wid][d] = old + __popc(peers);
     __syncwarp();
     rank[s] = old + __popc(peers & lt);
   }
   __syncthreads();
-  if (threadIdx.x <= mask) {
+  // per digit: chain the warps; then an exclusive scan over the digit totals (warp 0)
+  if (threadIdx.x < RADIX) {
     const int d = threadIdx.x;
-    dbase[d] = off[(int64_t)d * nblocks + blockIdx.x];
     unsigned run = 0;
-    for (int w = 0; w < SORT_WARPS; ++w) {
-      unsigned c = wcount[w][d];
-      wcount[w][d] = run;
-      run += c;
+    if (d <= mask) {
+      for (int w = 0; w < SORT_WARPS; ++w) {
+        unsigned c = sm.wcount[w][d];
+        sm.wcount[w][d] = run;
+        run += c;
+      }
+    }
+    sm.lbase[d] = run;                              // digit total, scanned below
+  }
+  __syncthreads();
+  if (wid == 0) {
+    unsigned v[RADIX / 32];
+    unsigned tsum = 0;
+#pragma unroll
+    for (int k = 0; k < RADIX / 32; ++k) { v[k] = sm.lbase[lane * (RADIX / 32) + k]; tsum += v[k]; }
+    unsigned incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    unsigned run = incl - tsum;
+#pragma unroll
+    for (int k = 0; k < RADIX / 32; ++k) {
+      const int d = lane * (RADIX / 32) + k;
+      sm.lbase[d] = run;
+      if (d <= mask) sm.gbase[d] = off[(int64_t)d * nblocks + blockIdx.x] - (long long)run;
+      run += v[k];
     }
   }
   __syncthreads();
@@ -193,11 +229,19 @@ radix_scatter(const int32_t* __restrict__ keys_in, const int2* __restrict__ vals
   for (int s = 0; s < SORT_STEPS; ++s) {
     int64_t e = wbase + s * 32 + lane;
     if (e < n) {
-      int d = (key[s] >> shift) & mask;
-      int64_t pos = dbase[d] + wcount[wid][d] + rank[s];
-      keys_out[pos] = key[s];
-      vals_out[pos] = val[s];
+      const int d = (key[s] >> shift) & mask;
+      const unsigned lp = sm.lbase[d] + sm.wcount[wid][d] + rank[s];
+      sm.skey[lp] = key[s];
+      sm.sval[lp] = val[s];
     }
+  }
+  __syncthreads();
+  const int n_tile = (int)min((int64_t)SORT_TILE, n - tbase);
+  for (int i = threadIdx.x; i < n_tile; i += SORT_THREADS) {
+    const int32_t k = sm.skey[i];
+    const int64_t pos = sm.gbase[(k >> shift) & mask] + i;
+    keys_out[pos] = k;
+    vals_out[pos] = sm.sval[i];
   }
 }
 
@@ -233,6 +277,12 @@ int sort_pairs(const int32_t* keys_in, const int2* vals_in, int32_t* keys_out, i
   char* scan_ws = p + hist_bytes + off_bytes;
   size_t scan_bytes = ws_bytes - hist_bytes - off_bytes;
 
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB_CHECK(cudaFuncSetAttribute(radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(ScatterSmem)));
+    attr_set = true;
+  }
   const int32_t* ksrc = keys_in;
   const int2* vsrc = vals_in;
   for (int k = 0; k < passes; ++k) {
@@ -246,8 +296,8 @@ int sort_pairs(const int32_t* keys_in, const int2* vals_in, int32_t* keys_out, i
     CB_LAUNCH_CHECK("radix_hist");
     int rc = exclusive_scan_i32(hist, off, (int64_t)(mask + 1) * nblocks, scan_ws, scan_bytes, st);
     if (rc) return rc;
-    radix_scatter<<<(unsigned)nblocks, SORT_THREADS, 0, st>>>(ksrc, vsrc, kdst, vdst, n, shift,
-                                                              mask, off, (int)nblocks);
+    radix_scatter<<<(unsigned)nblocks, SORT_THREADS, sizeof(ScatterSmem), st>>>(
+        ksrc, vsrc, kdst, vdst, n, shift, mask, off, (int)nblocks);
     CB_LAUNCH_CHECK("radix_scatter");
     ksrc = kdst;
     vsrc = vdst;

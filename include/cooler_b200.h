@@ -162,6 +162,7 @@ typedef struct {
   int32_t* seg_done;         /* [n_segs] out: 1 = converged or empty */
   int32_t* seg_empty;        /* [n_segs] out: 1 = no nonzero marginal (reference sets bias to NaN) */
   int32_t* all_done;         /* [1] out: every segment done -> later launches are no-ops */
+  int32_t* tickets;          /* [2] zero-initialised; elect the block that finishes a reduction (self re-arming) */
   double*  var_hist;         /* [max_iters * n_segs] variance per pass (NaN where not run) or NULL */
   double   tol;
   int32_t  max_iters;
@@ -175,9 +176,12 @@ int cb200_set_tuning(int32_t ice_unroll);
 int cb200_ice_sweep(const cb200_ice* st, void* stream);
 /* s[i] = rowpart(i) + colpart(i) -- the vector ranks all-reduce.  No-op once *all_done. */
 int cb200_ice_combine(const cb200_ice* st, void* stream);
-/* K4: marg = w*s, per-segment nonzero mean/variance, bias /= marg/mean,
- * convergence flags, iteration counters.  `iter` = 0-based index of this pass. */
-int cb200_ice_update(const cb200_ice* st, int32_t iter, void* stream);
+/* K4 (two launches): marg = w*s, per-segment nonzero mean/variance, bias /= marg/mean,
+ * convergence flags, iteration counters.  `iter` = 0-based index of this pass.
+ * fused_combine != 0: s is computed from the sweep outputs inside the first kernel
+ * (single GPU; cb200_ice_combine is then not needed); 0: st->s is read as given
+ * (multi-GPU: after the all-reduce). */
+int cb200_ice_update(const cb200_ice* st, int32_t iter, int32_t fused_combine, void* stream);
 
 /* ---- coarsen (replaces CoolerCoarsener._aggregate's join + pandas
  *      groupby(sort=True).sum(), src/cooler/_reduce.py:582-620) ------------ */
