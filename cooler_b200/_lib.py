@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcooler_b200.so")
 
-KEEP_ALL, KEEP_CIS, KEEP_TRANS = 0, 1, 2
+KEEP_ALL, KEEP_CIS, KEEP_TRANS, KEEP_BAND_NEAR, KEEP_BAND_FAR = 0, 1, 2, 3, 4
 
 
 class Copy(C.Structure):
@@ -24,7 +24,8 @@ class Sub(C.Structure):
     _fields_ = [("px", C.c_void_p), ("indptr", C.c_void_p), ("tile_row", C.c_void_p),
                 ("nnz", C.c_int64), ("direct", C.c_void_p), ("pieces", C.c_void_p),
                 ("first_warp", C.c_int64), ("first_tile", C.c_int64),
-                ("gather_base", C.c_int32), ("gather_len", C.c_int32)]
+                ("gather_base", C.c_int32), ("gather_len", C.c_int32),
+                ("row_base", C.c_int32), ("row_count", C.c_int32)]
 
 
 class Ice(C.Structure):
@@ -63,11 +64,11 @@ SIGNATURES = {
     "cb200_sort_pairs": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, C.c_int, C.c_int, _P, _SZ, _P]),
     "cb200_pack_pixels": (C.c_int, [_P, _P, _I64, _P, _P]),
     "cb200_tile_rows": (C.c_int, [_P, _I32, _I64, _P, _P]),
-    "cb200_indptr_from_sorted": (C.c_int, [_P, _I64, _I32, _I32, _P, _P]),
+    "cb200_indptr_from_sorted": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P]),
     "cb200_swap_key_other": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "cb200_strip_finish": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
-    "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _P, _P]),
-    "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _P, _P]),
+    "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
     "cb200_set_tuning": (C.c_int, [_I32]),
     "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import logging
+import os
 import warnings
 
 import numpy as np
@@ -56,7 +57,7 @@ class IceProblem:
     """
 
     def __init__(self, table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2,
-                 group=None, strip_bins=None, use_smem=True):
+                 group=None, strip_bins=None, use_smem=True, band=None):
         self.table = table
         self.use_smem = use_smem
         self.group = group
@@ -78,29 +79,41 @@ class IceProblem:
         self.marg_sum = marg[1].astype(np.float64)
         cval = None
         if trans_only:
-            del tkey, tval, ckeys
+            tkey = tval = ckeys = None
             csr, tkey, tval = filter_copy(csr, table.row_lo, table.row_hi, 0, _lib.KEEP_TRANS,
                                           want_transpose=True)
             csc, ckeys, cval = filter_copy(csc, table.row_lo, table.row_hi, 0, _lib.KEEP_TRANS,
                                            want_transpose=True)
-        self.csr, self.csc = csr, csc
-        # column strips of the gathered bias vector (cache blocking), see choose_strip_shift
-        self.strip_shift = choose_strip_shift(n_bins, csr.nnz, strip_bins)
-        if self.strip_shift is None:
-            self.subs = [csr, csc]
-        else:
-            sh = self.strip_shift
+        self._nnz_eff = csr.nnz
+        # layout of the sweep: whole copies, column strips, or diagonal band strips + far rest
+        self.strip_shift, self.band = choose_layout(n_bins, csr.nnz, strip_bins, band)
+        sh = self.strip_shift
+        if sh is None:
+            self.subs = [csr.tight(), csc.tight()]
+            self.csr, self.csc = csr, csc
+        elif not self.band:
             subs = strip_partition(tkey[: csr.nnz], tval, csr.nnz, n_bins, sh)
-            del tkey, tval
+            tkey = tval = None
             if cval is None:                      # csc came from the sort: (key = row, val = {other, count})
                 ckeys, cval = swap_key_other(ckeys, csc.px, csc.nnz)
             subs += strip_partition(ckeys[: csc.nnz], cval, csc.nnz, n_bins, sh)
             self.subs = subs
             self.csr = self.csc = None            # the strips replace the whole copies
-            self._nnz_eff = csr.nnz
-        del ckeys, cval
-        if self.strip_shift is None:
-            self._nnz_eff = csr.nnz
+        else:
+            tkey = tval = ckeys = cval = None
+            subs = []
+            for copy in (csr, csc):
+                near, nkey, nval = filter_copy(copy, table.row_lo, table.row_hi, 0, _lib.KEEP_BAND_NEAR,
+                                               want_transpose=True, band_shift=sh)
+                subs += strip_partition(nkey[: near.nnz], nval, near.nnz, n_bins, sh)
+                del near, nkey, nval
+                far, _, _ = filter_copy(copy, table.row_lo, table.row_hi, 0, _lib.KEEP_BAND_FAR,
+                                        band_shift=sh)
+                if far.nnz:
+                    subs.append(far.tight())
+            self.subs = subs
+            self.csr = self.csc = None
+        tkey = tval = ckeys = cval = None
 
     @property
     def nnz_eff(self):
@@ -117,29 +130,37 @@ DEFAULT_STRIP_BINS = 16_384    # 128 KB of float64 bias per strip: stays in the 
 MIN_PIXELS_PER_ROW_STRIP = 16  # below this the per-(row, strip) bookkeeping costs more than it saves
 
 
-def choose_strip_shift(n_bins, nnz_eff, strip_bins=None):
-    """log2 of the strip width in bins, or None for "no strips".
+def choose_layout(n_bins, nnz_eff, strip_bins=None, band=None):
+    """(log2 strip width in bins | None, band: bool) -- how the sweep gathers the bias.
 
     The sweep gathers bias[other] per pixel.  When the bias vector is much larger than
     L1 every gather costs a 32-byte L2 sector per 8-byte pixel and L2 bandwidth, not
-    HBM, bounds the pass.  Splitting a copy into strips of the gathered index keeps the
-    gathered slice L1-resident, at the price of one partial sum per (row, strip).
+    HBM, bounds the pass.  Splitting a copy into strips of the gathered index lets a
+    persistent CTA stage the gathered slice in shared memory, at the price of one
+    partial sum per (row, strip).  That pays while (row, strip) segments stay long
+    ("strips": every strip).  For very sparse far fields (1 kb matrices) only the band
+    of strips around the diagonal is cut into strips and the far remainder stays one
+    row-ordered copy gathered through L2 ("band").
     """
     if strip_bins == 0:
-        return None
-    if strip_bins is None:
+        return None, False
+    auto = strip_bins is None
+    if auto:
         if n_bins <= L1_RESIDENT_BINS:
-            return None
+            return None, False
         strip_bins = DEFAULT_STRIP_BINS
-        n_strips = -(-n_bins // strip_bins)
-        if nnz_eff < MIN_PIXELS_PER_ROW_STRIP * n_bins * n_strips:
-            return None
     shift = int(strip_bins).bit_length() - 1
     if (1 << shift) != int(strip_bins):
         raise ValueError("strip_bins must be a power of two")
-    if ((max(n_bins, 1) - 1) >> shift) + 1 > 256:
-        return None
-    return shift
+    n_strips = ((max(n_bins, 1) - 1) >> shift) + 1
+    sparse = nnz_eff < MIN_PIXELS_PER_ROW_STRIP * n_bins * n_strips or n_strips > 1024
+    if band is None:
+        if auto and sparse:
+            # measured (tools/tune_sweep.py, 1 kb shard): band strips gain ~7 % per pass over
+            # whole copies but cost two more filter passes at build time -> not the default
+            return None, False
+        band = sparse
+    return shift, bool(band)
 
 
 class IceState:
@@ -180,14 +201,20 @@ class IceState:
         subs = prob.subs
         total_tiles = sum(n_tiles(c.nnz) for c in subs)
         span = int(min(8, max(1, -(-total_tiles // (148 * 32 * 8)))))
+        if prob.strip_shift is not None and prob.use_smem:
+            span = min(span, 4)                       # persistent strip kernel: finer claims, see csrc/ice.cu
+        if os.environ.get("CB200_SPAN"):              # tuning override
+            span = int(os.environ["CB200_SPAN"])
         arr = (_lib.Sub * max(len(subs), 1))()
-        t["direct"] = f64(max(len(subs), 1) * max(n, 1))
+        t["direct"] = f64(sum(c.n_rows for c in subs) + 1)
         t["pieces"] = f64(2 * total_tiles + 2)
-        warp0, tile0 = 0, 0
+        warp0, tile0, row0 = 0, 0, 0
         for k, c in enumerate(subs):
             arr[k].px, arr[k].indptr, arr[k].tile_row = c.px.data_ptr(), c.indptr.data_ptr(), c.tile_row.data_ptr()
             arr[k].nnz = c.nnz
-            arr[k].direct = t["direct"].data_ptr() + 8 * k * n
+            arr[k].row_base, arr[k].row_count = c.row_base, c.n_rows
+            arr[k].direct = t["direct"].data_ptr() + 8 * row0
+            row0 += c.n_rows
             arr[k].pieces = t["pieces"].data_ptr() + 8 * 2 * tile0
             arr[k].first_warp = warp0
             arr[k].first_tile = tile0
@@ -317,7 +344,7 @@ def prefilter_bias(prob: IceProblem, chrom_offset, *, mad_max, min_nnz, min_coun
 def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2, mad_max=5,
                   min_nnz=10, min_count=0, blacklist=None, rescale_marginals=True, x0=None,
                   tol=1e-5, max_iters=200, group=None, problem=None, chromnames=None,
-                  return_info=False, strip_bins=None):
+                  return_info=False, strip_bins=None, band=None):
     """Balance a device-resident table.  Same semantics as ``balance_cooler``.
 
     ``problem`` lets callers reuse the filtered copies (bench: inputs resident
@@ -329,7 +356,7 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
     n_bins = table.n_bins
     n_chroms = len(chrom_offset) - 1
     prob = problem or IceProblem(table, cis_only=cis_only, trans_only=trans_only,
-                                 ignore_diags=ignore_diags, group=group, strip_bins=strip_bins)
+                                 ignore_diags=ignore_diags, group=group, strip_bins=strip_bins, band=band)
     bias = prefilter_bias(prob, chrom_offset, mad_max=mad_max, min_nnz=min_nnz, min_count=min_count,
                           blacklist=blacklist, x0=x0)
 
@@ -399,7 +426,7 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
         info = {"passes": res["seg_iters"].tolist(), "launched_passes": passes,
                 "nnz_eff": prob.nnz_eff, "bytes_per_pass": prob.bytes_per_pass(),
                 "hit_limit": hit_limit, "gpu_launches": state.launches,
-                "n_subcopies": len(prob.subs), "strip_shift": prob.strip_shift}
+                "n_subcopies": len(prob.subs), "strip_shift": prob.strip_shift, "band": prob.band}
         return bias, stats, info
     return bias, stats
 

@@ -61,49 +61,65 @@ struct IceOpSmem {
 constexpr int STRIP_THREADS = 1024;
 constexpr int STRIP_WARPS = STRIP_THREADS / 32;
 
-// Work distribution: one persistent CTA per SM.  Every sub-copy has a claim counter;
-// a CTA starts at the sub-copy where an even split of all tiles would put it, claims
-// chunks of STRIP_WARPS*span tiles until that sub-copy is exhausted, then moves on
-// (cyclically).  Claims only decide WHO computes a tile, never the arithmetic, so the
-// results stay bit-reproducible.  The last CTA to finish re-arms the counters.
+// Work distribution: one persistent CTA per SM.  Every sub-copy has a claim counter.
+// A CTA starts at the sub-copy where an even split of all tiles would put it and
+// visits the sub-copies cyclically; on a sub-copy that still has work it stages the
+// strip's slice of w once, then each of its WARPS claims `span` tiles at a time until
+// the sub-copy is exhausted (no CTA barrier per claim).  Claims only decide WHO
+// computes a tile, never the arithmetic, so results stay bit-reproducible.  The last
+// CTA to finish re-arms the counters.
 template <int U>
 __global__ void __launch_bounds__(STRIP_THREADS, 1)
 ice_sweep_strips_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span,
-                        int64_t total_tiles, const double* __restrict__ w,
+                        int64_t total_tiles, int smem_bins, const double* __restrict__ w,
                         unsigned long long* __restrict__ claim,
                         const int32_t* __restrict__ all_done) {
   extern __shared__ double w_s[];
-  __shared__ unsigned long long s_claim;
+  __shared__ int s_has_work;
   if (*all_done) return;
-  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int64_t g0 = total_tiles * (int64_t)blockIdx.x / gridDim.x;
   int lo = 0, hi = n_subs;                         // sub-copy that holds global tile g0
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
     if (subs[mid].first_tile <= g0) lo = mid; else hi = mid;
   }
-  const int64_t chunk = (int64_t)STRIP_WARPS * span;
-  int k = lo, loaded = -1;
+  int k = lo;
   for (int visited = 0; visited < n_subs; ++visited, k = (k + 1 == n_subs) ? 0 : k + 1) {
     const cb200_sub sub = subs[k];
     const int64_t n_tiles = (sub.nnz + WARP_TILE - 1) / WARP_TILE;
-    while (true) {
-      __syncthreads();                             // previous chunk done: s_claim and w_s are free
-      if (threadIdx.x == 0) s_claim = atomicAdd(&claim[k], (unsigned long long)chunk);
+    __syncthreads();                               // everyone is done with the previous strip's w_s
+    if (threadIdx.x == 0)
+      s_has_work = (int64_t)(*reinterpret_cast<volatile unsigned long long*>(claim + k)) < n_tiles;
+    __syncthreads();
+    if (!s_has_work) continue;                     // CTA-uniform
+    const bool in_smem = sub.gather_len <= smem_bins;
+    if (in_smem) {                                 // stage this strip's slice of w
+      for (int i = threadIdx.x; i < sub.gather_len; i += STRIP_THREADS) w_s[i] = w[sub.gather_base + i];
       __syncthreads();
-      const int64_t c0 = (int64_t)s_claim;
-      if (c0 >= n_tiles) break;
-      if (loaded != k) {                           // stage this strip's slice of w
-        for (int i = threadIdx.x; i < sub.gather_len; i += STRIP_THREADS) w_s[i] = w[sub.gather_base + i];
-        loaded = k;
-        __syncthreads();
+    }
+    while (true) {
+      // guided self-scheduling: claims shrink towards the end of a sub-copy so that the
+      // warps of a CTA reach the end-of-strip barrier at nearly the same time
+      unsigned long long c = 0;
+      int take = span;
+      if (lane == 0) {
+        const int64_t rem = n_tiles - (int64_t)(*reinterpret_cast<volatile unsigned long long*>(claim + k));
+        take = (int)max((int64_t)1, min((int64_t)span, rem / 512));
+        c = atomicAdd(&claim[k], (unsigned long long)take);
       }
-      const int64_t c1 = min(c0 + chunk, n_tiles);
-      const int64_t t0 = c0 + (int64_t)warp * span;
-      if (t0 < c1) {
+      const int64_t t0 = (int64_t)__shfl_sync(0xffffffffu, c, 0);
+      take = __shfl_sync(0xffffffffu, take, 0);
+      if (t0 >= n_tiles) break;
+      const int64_t t1 = min(t0 + take, n_tiles);
+      if (in_smem) {
         IceOpSmem op{w_s, sub.gather_base};
         walk_reduce_span<IceOpSmem, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
-                                       sub.nnz, t0, min(t0 + span, c1), op, sub.direct, sub.pieces);
+                                       sub.nnz, t0, t1, op, sub.direct, sub.pieces);
+      } else {                                     // far-field remainder: gather through L1/L2
+        IceOp op{w};
+        walk_reduce_span<IceOp, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
+                                   sub.nnz, t0, t1, op, sub.direct, sub.pieces);
       }
     }
   }
@@ -126,8 +142,11 @@ __global__ void ice_combine_kernel(const cb200_sub* __restrict__ subs, int n_sub
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_bins) return;
   double v = 0.0;
-  for (int k = 0; k < n_subs; ++k)
-    v += row_total<double>(i, subs[k].indptr, subs[k].nnz, subs[k].direct, subs[k].pieces);
+  for (int k = 0; k < n_subs; ++k) {
+    const unsigned r = (unsigned)(i - subs[k].row_base);
+    if (r < (unsigned)subs[k].row_count)
+      v += row_total<double>((int)r, subs[k].indptr, subs[k].nnz, subs[k].direct, subs[k].pieces);
+  }
   s[i] = v;
 }
 
@@ -179,8 +198,12 @@ ice_marg_kernel(cb200_ice st) {
       double si;
       if (kCombine) {
         si = 0.0;
-        for (int k = 0; k < st.n_subs; ++k)
-          si += row_total<double>(i, st.subs[k].indptr, st.subs[k].nnz, st.subs[k].direct, st.subs[k].pieces);
+        for (int k = 0; k < st.n_subs; ++k) {
+          const unsigned r = (unsigned)(i - st.subs[k].row_base);
+          if (r < (unsigned)st.subs[k].row_count)
+            si += row_total<double>((int)r, st.subs[k].indptr, st.subs[k].nnz, st.subs[k].direct,
+                                    st.subs[k].pieces);
+        }
       } else {
         si = st.s[i];
       }
@@ -301,11 +324,11 @@ int cb200_ice_sweep(const cb200_ice* st, void* stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_ice_unroll == 1)
       ice_sweep_strips_kernel<1><<<sms, STRIP_THREADS, smem, (cudaStream_t)stream>>>(
-          st->subs, st->n_subs, st->span, st->total_tiles, st->w,
+          st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,
           reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
     else
       ice_sweep_strips_kernel<2><<<sms, STRIP_THREADS, smem, (cudaStream_t)stream>>>(
-          st->subs, st->n_subs, st->span, st->total_tiles, st->w,
+          st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,
           reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
     CB_LAUNCH_CHECK("ice_sweep_strips");
     return 0;

@@ -40,11 +40,11 @@ __global__ void tile_rows_kernel(const int64_t* __restrict__ indptr, int n_rows,
 
 // --------------------------------------------------- indptr from sorted ----
 __global__ void indptr_from_sorted_kernel(const int32_t* __restrict__ keys, int64_t n, int n_rows,
-                                          int shift, int64_t* __restrict__ indptr) {
+                                          int key_base, int shift, int64_t* __restrict__ indptr) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p <= n; p += stride) {
-    const int prev = (p == 0) ? -1 : (keys[p - 1] >> shift);
-    const int cur = (p == n) ? n_rows : (keys[p] >> shift);
+    const int prev = (p == 0) ? -1 : ((keys[p - 1] - key_base) >> shift);
+    const int cur = (p == n) ? n_rows : ((keys[p] - key_base) >> shift);
     for (int r = prev + 1; r <= cur; ++r) indptr[r] = p;
   }
 }
@@ -87,6 +87,7 @@ struct KeepRule {
   const int32_t* row_hi;
   int ndiag;
   int keep;
+  int band_shift;
   __device__ __forceinline__ bool operator()(int r, int c) const {
     if (ndiag > 0) {
       int d = r - c;
@@ -94,6 +95,11 @@ struct KeepRule {
       if (d < ndiag) return false;
     }
     if (keep == CB200_KEEP_ALL) return true;
+    if (keep == CB200_KEEP_BAND_NEAR || keep == CB200_KEEP_BAND_FAR) {
+      int ds = (c >> band_shift) - (r >> band_shift);
+      if (ds < 0) ds = -ds;
+      return (keep == CB200_KEEP_BAND_NEAR) ? (ds <= 1) : (ds > 1);
+    }
     const bool cis = (c >= row_lo[r]) && (c < row_hi[r]);
     return (keep == CB200_KEEP_CIS) ? cis : !cis;
   }
@@ -227,12 +233,12 @@ int cb200_tile_rows(const int64_t* indptr, int32_t n_rows, int64_t nnz, int32_t*
   return 0;
 }
 
-int cb200_indptr_from_sorted(const int32_t* keys, int64_t n, int32_t n_rows, int32_t shift,
-                             int64_t* indptr, void* stream) {
+int cb200_indptr_from_sorted(const int32_t* keys, int64_t n, int32_t n_rows, int32_t key_base,
+                             int32_t shift, int64_t* indptr, void* stream) {
   int64_t blocks = ceil_div64(n + 1, 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  indptr_from_sorted_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(keys, n, n_rows,
-                                                                               shift, indptr);
+  indptr_from_sorted_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      keys, n, n_rows, key_base, shift, indptr);
   CB_LAUNCH_CHECK("indptr_from_sorted");
   return 0;
 }
@@ -263,11 +269,12 @@ int cb200_strip_finish(const int32_t* keys, const cb200_px* vals, int64_t n, int
 
 int cb200_filter_count(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
                        int32_t n_rows, int64_t nnz, const int32_t* row_lo, const int32_t* row_hi,
-                       int32_t ndiag, int32_t keep, int32_t* tile_count, void* stream) {
+                       int32_t ndiag, int32_t keep, int32_t band_shift, int32_t* tile_count,
+                       void* stream) {
   (void)n_rows;
   const int64_t n_tiles = ceil_div64(nnz, WARP_TILE);
   if (n_tiles <= 0) return 0;
-  KeepRule rule{row_lo, row_hi, ndiag, keep};
+  KeepRule rule{row_lo, row_hi, ndiag, keep, band_shift};
   filter_count_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0,
                         (cudaStream_t)stream>>>(reinterpret_cast<const int2*>(px), indptr, tile_row,
                                                 nnz, n_tiles, rule, tile_count);
@@ -277,12 +284,13 @@ int cb200_filter_count(const cb200_px* px, const int64_t* indptr, const int32_t*
 
 int cb200_filter_write(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
                        int32_t n_rows, int64_t nnz, const int32_t* row_lo, const int32_t* row_hi,
-                       int32_t ndiag, int32_t keep, const int64_t* tile_off, cb200_px* px_out,
-                       int32_t* row_out, int32_t* tkey_out, cb200_px* tval_out, void* stream) {
+                       int32_t ndiag, int32_t keep, int32_t band_shift, const int64_t* tile_off,
+                       cb200_px* px_out, int32_t* row_out, int32_t* tkey_out, cb200_px* tval_out,
+                       void* stream) {
   (void)n_rows;
   const int64_t n_tiles = ceil_div64(nnz, WARP_TILE);
   if (n_tiles <= 0) return 0;
-  KeepRule rule{row_lo, row_hi, ndiag, keep};
+  KeepRule rule{row_lo, row_hi, ndiag, keep, band_shift};
   filter_write_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0,
                         (cudaStream_t)stream>>>(
       reinterpret_cast<const int2*>(px), indptr, tile_row, nnz, n_tiles, rule, tile_off,

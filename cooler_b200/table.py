@@ -57,8 +57,10 @@ def _new_px(nnz, device):
 class TableCopy:
     """One row-ordered copy of the pixel table on the device."""
 
-    def __init__(self, px, indptr, nnz, n_rows, tile_row=None):
+    def __init__(self, px, indptr, nnz, n_rows, tile_row=None, row_base=0):
+        # rows [row_base, row_base + n_rows) of the matrix; indptr / tile_row are local to that range
         self.px, self.indptr, self.nnz, self.n_rows = px, indptr, int(nnz), int(n_rows)
+        self.row_base = int(row_base)
         if tile_row is None:
             tile_row = torch.empty(max(n_tiles(nnz), 1), dtype=_I32, device=px.device)
             _lib.call("cb200_tile_rows", _ptr(indptr), self.n_rows, self.nnz, _ptr(tile_row), _stream())
@@ -75,11 +77,28 @@ class TableCopy:
         return self.nnz * 8 + self.indptr.numel() * 8 + self.tile_row.numel() * 4
 
     # -- debugging / tests ---------------------------------------------------
+    def tight(self):
+        """Same pixels, row range shrunk to [first non-empty row, last non-empty row]."""
+        if self.nnz == 0:
+            return self
+        edge = torch.tensor([0, self.nnz], dtype=_I64, device=self.indptr.device)
+        pos = torch.searchsorted(self.indptr, edge, right=False).cpu().numpy()
+        first_r = torch.searchsorted(self.indptr, edge[:1], right=True).item() - 1
+        last_r = int(pos[1]) - 1                      # last row r with indptr[r] < nnz
+        if first_r == 0 and last_r == self.n_rows - 1:
+            return self
+        sub = TableCopy(self.px, self.indptr[first_r:last_r + 2], self.nnz, last_r - first_r + 1,
+                        row_base=self.row_base + first_r)
+        for a in ("strip",):
+            if hasattr(self, a):
+                setattr(sub, a, getattr(self, a))
+        return sub
+
     def to_host(self):
         """(row ids, other ids, counts) as numpy int64/int64/int32."""
         ind = self.indptr.cpu().numpy()
         px = self.px[: self.nnz].cpu().numpy()
-        rows = np.repeat(np.arange(self.n_rows, dtype=np.int64), np.diff(ind))
+        rows = self.row_base + np.repeat(np.arange(self.n_rows, dtype=np.int64), np.diff(ind))
         return rows, px[:, 0].astype(np.int64), px[:, 1].copy()
 
 
@@ -111,9 +130,10 @@ def sort_pairs(keys, vals, key_bits, key_shift=0):
     return keys_out, vals_out
 
 
-def indptr_from_sorted(keys, n, n_rows, shift=0):
+def indptr_from_sorted(keys, n, n_rows, shift=0, key_base=0):
     out = torch.empty(n_rows + 1, dtype=_I64, device=keys.device)
-    _lib.call("cb200_indptr_from_sorted", _ptr(keys), int(n), int(n_rows), int(shift), _ptr(out), _stream())
+    _lib.call("cb200_indptr_from_sorted", _ptr(keys), int(n), int(n_rows), int(key_base), int(shift),
+              _ptr(out), _stream())
     return out
 
 
@@ -121,7 +141,8 @@ def key_bits_for(n_rows):
     return max(1, int(n_rows - 1).bit_length()) if n_rows > 1 else 1
 
 
-def filter_copy(copy, row_lo, row_hi, ndiag, keep, *, want_rows=False, want_transpose=False):
+def filter_copy(copy, row_lo, row_hi, ndiag, keep, *, want_rows=False, want_transpose=False,
+                band_shift=0):
     """Stable compaction of ``copy`` by the static filter (see cb200_filter_count).
 
     Returns (new_copy, tkey, tval); the new copy's indptr is rebuilt from the
@@ -131,7 +152,7 @@ def filter_copy(copy, row_lo, row_hi, ndiag, keep, *, want_rows=False, want_tran
     nt = n_tiles(copy.nnz)
     tile_count = torch.zeros(max(nt, 1), dtype=_I32, device=dev)
     _lib.call("cb200_filter_count", _ptr(copy.px), _ptr(copy.indptr), _ptr(copy.tile_row),
-              copy.n_rows, copy.nnz, _ptr(row_lo), _ptr(row_hi), int(ndiag), int(keep),
+              copy.n_rows, copy.nnz, _ptr(row_lo), _ptr(row_hi), int(ndiag), int(keep), int(band_shift),
               _ptr(tile_count), _stream())
     tile_off = exclusive_scan_i32(tile_count[:nt] if nt else tile_count[:0])
     kept = int(tile_off[-1].item())                      # one sync per build step
@@ -140,7 +161,7 @@ def filter_copy(copy, row_lo, row_hi, ndiag, keep, *, want_rows=False, want_tran
     tkey = torch.empty(max(kept, 1), dtype=_I32, device=dev) if want_transpose else None
     tval = _new_px(kept, dev) if want_transpose else None
     _lib.call("cb200_filter_write", _ptr(copy.px), _ptr(copy.indptr), _ptr(copy.tile_row),
-              copy.n_rows, copy.nnz, _ptr(row_lo), _ptr(row_hi), int(ndiag), int(keep),
+              copy.n_rows, copy.nnz, _ptr(row_lo), _ptr(row_hi), int(ndiag), int(keep), int(band_shift),
               _ptr(tile_off), _ptr(px_out), _ptr(rows), _ptr(tkey), _ptr(tval), _stream())
     indptr = indptr_from_sorted(rows, kept, copy.n_rows)
     new = TableCopy(px_out, indptr, kept, copy.n_rows)
@@ -188,16 +209,18 @@ def strip_partition(key_other, val_rowcount, n, n_rows, shift):
     _lib.call("cb200_strip_finish", _ptr(ks), _ptr(vs), int(n), int(shift), _ptr(pad_d), _ptr(px_out),
               _ptr(rows_out), _stream())
     del ks, vs
+    live = np.flatnonzero(counts > 0)
+    # row range of every strip = [first row id, last row id] of its (row-sorted) elements
+    idx = np.concatenate([aligned[live], aligned[live] + counts[live] - 1])
+    ends = rows_out[torch.from_numpy(idx).to(dev)].cpu().numpy()
+    first_rows, last_rows = ends[: len(live)], ends[len(live):]
     subs = []
-    for s_ in range(n_strips):
-        c = int(counts[s_])
-        if c == 0:
-            continue
-        a = int(aligned[s_])
-        rows_s = rows_out[a:a + c]
-        indptr = indptr_from_sorted(rows_s, c, n_rows)
-        sub = TableCopy(px_out[a:a + c + 2], indptr, c, n_rows)
-        sub.strip = s_
+    for j, s_ in enumerate(live):
+        c, a = int(counts[s_]), int(aligned[s_])
+        r0, r1 = int(first_rows[j]), int(last_rows[j])
+        indptr = indptr_from_sorted(rows_out[a:a + c], c, r1 - r0 + 1, key_base=r0)
+        sub = TableCopy(px_out[a:a + c + 2], indptr, c, r1 - r0 + 1, row_base=r0)
+        sub.strip = int(s_)
         subs.append(sub)
     return subs
 

@@ -66,9 +66,10 @@ int cb200_pack_pixels(const int64_t* bin2_id, const int32_t* count, int64_t nnz,
 /* tile_row[t] = row that contains pixel t*warp_tile (n_tiles entries). */
 int cb200_tile_rows(const int64_t* indptr, int32_t n_rows, int64_t nnz,
                     int32_t* tile_row, void* stream);
-/* indptr[r] = first position p with (keys[p] >> shift) >= r, r = 0..n_rows (keys sorted). */
-int cb200_indptr_from_sorted(const int32_t* keys, int64_t n, int32_t n_rows, int32_t shift,
-                             int64_t* indptr, void* stream);
+/* indptr[r] = first position p with ((keys[p] - key_base) >> shift) >= r, r = 0..n_rows
+ * (keys sorted, all >= key_base). */
+int cb200_indptr_from_sorted(const int32_t* keys, int64_t n, int32_t n_rows, int32_t key_base,
+                             int32_t shift, int64_t* indptr, void* stream);
 /* Column strips ("cache blocking" of the gathered bias vector): a copy can be
  * split into strips by other >> shift, each strip again a row-ordered copy, so
  * that the slice of the bias vector one strip gathers from stays L1-resident.
@@ -87,18 +88,21 @@ int cb200_strip_finish(const int32_t* keys, const cb200_px* vals, int64_t n, int
  *       || (keep == CB200_KEEP_CIS   &&  row_lo[r] <= c < row_hi[r])   (_zero_trans)
  *       || (keep == CB200_KEEP_TRANS && !(row_lo[r] <= c < row_hi[r])))(_zero_cis)
  * where [row_lo[r], row_hi[r]) is the bin range of r's chromosome. */
-enum { CB200_KEEP_ALL = 0, CB200_KEEP_CIS = 1, CB200_KEEP_TRANS = 2 };
+enum { CB200_KEEP_ALL = 0, CB200_KEEP_CIS = 1, CB200_KEEP_TRANS = 2,
+       /* layout-only rules (no reference counterpart): split a copy into the band
+        * |(c >> band_shift) - (r >> band_shift)| <= 1 around the diagonal and the rest */
+       CB200_KEEP_BAND_NEAR = 3, CB200_KEEP_BAND_FAR = 4 };
 int cb200_filter_count(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
                        int32_t n_rows, int64_t nnz,
                        const int32_t* row_lo, const int32_t* row_hi, int32_t ndiag, int32_t keep,
-                       int32_t* tile_count, void* stream);
+                       int32_t band_shift, int32_t* tile_count, void* stream);
 /* Second pass: writes kept pixels, order preserved, at tile_off[t] + rank.
  * Optional outputs (NULL to skip): row_out[q] = row of kept pixel q;
  * tkey_out[q] = other, tval_out[q] = {row, count} (input of the transposition sort). */
 int cb200_filter_write(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
                        int32_t n_rows, int64_t nnz,
                        const int32_t* row_lo, const int32_t* row_hi, int32_t ndiag, int32_t keep,
-                       const int64_t* tile_off,
+                       int32_t band_shift, const int64_t* tile_off,
                        cb200_px* px_out, int32_t* row_out, int32_t* tkey_out, cb200_px* tval_out,
                        void* stream);
 
@@ -123,15 +127,19 @@ int cb200_marginals_i64(const cb200_copy* copy, int32_t n_rows,
 /* ---- ICE iteration (replaces the PASS C map-reduce + the O(n_bins) numpy
  *      update of _balance_genomewide/_cisonly/_transonly,
  *      src/cooler/_balance.py:72-260) ------------------------------------- */
-/* A sub-copy swept by K3: a whole copy or one column strip of it. */
+/* A sub-copy swept by K3: a whole copy or one column strip of it.  It covers the
+ * rows [row_base, row_base + row_count); indptr, tile_row and direct are local to
+ * that range. */
 typedef struct {
   const cb200_px* px; const int64_t* indptr; const int32_t* tile_row; int64_t nnz;
-  double*  direct;           /* [n_bins] rows closed strictly inside a warp tile */
+  double*  direct;           /* [row_count] rows closed strictly inside a warp tile */
   double*  pieces;           /* [2 * n_tiles] first / last row of every warp tile */
   int64_t  first_warp;       /* prefix sum over sub-copies of ceil(n_tiles / span) */
   int64_t  first_tile;       /* prefix sum over sub-copies of n_tiles */
   int32_t  gather_base;      /* `other` of this sub-copy lies in [gather_base, gather_base + gather_len) */
   int32_t  gather_len;
+  int32_t  row_base;
+  int32_t  row_count;
 } cb200_sub;
 
 typedef struct {

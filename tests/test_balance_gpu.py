@@ -174,8 +174,8 @@ def test_column_strips_match_reference_golden(key, strip_bins):
     tab = PixelTable.from_arrays(bin1_offset, t["bin2_id"], t["count"], chrom_offset)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, **kw)
-    assert info["n_subcopies"] > 2 and info["strip_shift"] is not None
+        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, band=False, **kw)
+    assert info["n_subcopies"] > 2 and info["strip_shift"] is not None and not info["band"]
     want = BAL[key]
     np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
     assert sum(info["passes"]) == sum(META[key]["passes"])
@@ -191,12 +191,48 @@ def test_column_strips_large_synthetic_matches_unstripped():
     tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
     from cooler_b200.balance import IceProblem
     a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0)
-    b, sb, ib = cooler_b200.balance_table(tab, return_info=True, strip_bins=16384)
+    b, sb, ib = cooler_b200.balance_table(tab, return_info=True, strip_bins=16384, band=False)
     assert ia["n_subcopies"] == 2 and ib["n_subcopies"] == 12
     assert ia["passes"] == ib["passes"]
     np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
     np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
     # the L1-gather kernel on the same strips is bit-identical to the shared-memory kernel
-    prob = IceProblem(tab, strip_bins=16384, use_smem=False)
+    prob = IceProblem(tab, strip_bins=16384, use_smem=False, band=False)
     c, sc, ic = cooler_b200.balance_table(tab, return_info=True, problem=prob)
     np.testing.assert_array_equal(b, c)
+
+
+@pytest.mark.parametrize("key,strip_bins", [("gm/defaults", 64), ("gm/cis_only", 128), ("gm/trans_only", 32),
+                                            ("rnd3/gw", 16), ("rnd2/cis", 16), ("rnd3/trans", 32)])
+def test_band_layout_matches_reference_golden(key, strip_bins):
+    """Diagonal-band strips + far remainder (the layout for very sparse, very large matrices)."""
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    src, case = key.split("/")
+    t = _golden.table_of(src)
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    kw = dict(META[key]["kwargs"])
+    tab = PixelTable.from_arrays(bin1_offset, t["bin2_id"], t["count"], chrom_offset)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, band=True, **kw)
+    assert info["band"] and info["n_subcopies"] > 2
+    want = BAL[key]
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    assert sum(info["passes"]) == sum(META[key]["passes"])
+    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
+
+
+def test_band_layout_large_synthetic_matches_unstripped():
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    b1, b2, cnt, chrom_offset = _synthetic(33, [50000, 30000, 20001], 0.002)
+    n = int(chrom_offset[-1])
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
+    a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0)
+    b, sb, ib = cooler_b200.balance_table(tab, return_info=True, strip_bins=16384, band=True)
+    assert ib["band"] and ib["n_subcopies"] > 4
+    assert ia["passes"] == ib["passes"]
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)

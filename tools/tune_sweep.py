@@ -19,7 +19,7 @@ binsize = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000
 target = int(float(sys.argv[2])) if len(sys.argv) > 2 else 200_000_000
 world = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 rank = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-variants = [(2, 16384, 0), (2, 16384, 1), (2, 8192, 1), (2, 4096, 1), (2, 8192, 0)]   # (unroll, strip_bins, use_smem)
+variants = [(2, 0, 0), (2, 16384, 1), (2, 16384, 2), (2, 8192, 2), (2, 32768, 2)]   # (unroll, strip_bins, use_smem)
 if os.environ.get('TUNE_VARIANTS'):
     variants = [tuple(int(x) for x in v.split(':')) for v in os.environ['TUNE_VARIANTS'].split(',')]
 plan = synth.SynthPlan(binsize, target, seed=0)
@@ -35,7 +35,7 @@ for unroll, strip_bins, use_smem in variants:
     if (strip_bins, use_smem) != last_strip:
         prob = state = None
         torch.cuda.empty_cache()
-        prob = IceProblem(tab, strip_bins=strip_bins, use_smem=bool(use_smem))
+        prob = IceProblem(tab, strip_bins=strip_bins, use_smem=bool(use_smem), band=(use_smem == 2) if strip_bins else None)
         bias0 = prefilter_bias(prob, tab.chrom_offset, mad_max=5, min_nnz=10, min_count=0, blacklist=None, x0=None)
         state = IceState(prob, bias0, None, np.array([0, tab.n_bins]), 1e-5, 200)
         last_strip = (strip_bins, use_smem)
