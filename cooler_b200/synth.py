@@ -67,7 +67,17 @@ class SynthPlan:
         n_blocks = max(1, int(math.ceil(cw[-1] / ROWS_PER_BLOCK_TARGET)))
         cuts = np.searchsorted(cw, np.linspace(0, cw[-1], n_blocks + 1)[1:-1])
         self.block_edges = np.unique(np.r_[0, cuts, n]).astype(np.int64)
-        self.row_weight_cum = cw
+        # expected DISTINCT pixels per row (candidates collide near the diagonal), used to
+        # balance shards by pixels rather than by candidates
+        rho = self.m_far / cells
+        uniq_far = (n - rows) * (1.0 - math.exp(-rho))
+        nb = np.diff(self.chrom_offset)
+        room = np.repeat(self.chrom_offset[1:], nb) - rows            # bins left in the chromosome
+        lnr = np.log1p(room)
+        c = self.cis_per_row
+        dstar = np.clip(c / lnr - 1.0, 0.0, room)                      # distances with >= 1 expected candidate
+        uniq_cis = dstar + c * (lnr - np.log1p(dstar)) / lnr
+        self.row_weight_cum = np.r_[0.0, np.cumsum(uniq_far + np.minimum(uniq_cis, room))]
 
     def shard_rows(self, rank, world):
         """Contiguous block-aligned row range of ``rank`` with ~1/world of the candidates."""

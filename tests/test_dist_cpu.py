@@ -24,6 +24,7 @@ def _free_port():
 
 def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
+    torch.set_num_threads(1)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from cooler_b200 import synth
@@ -56,7 +57,7 @@ def test_sharded_marginal_allreduce_equals_global(tmp_path):
     world = 2
     out = str(tmp_path / "marg.npy")
     port = _free_port()
-    mp.start_processes(_worker, args=(world, port, out), nprocs=world, join=True, start_method="fork")
+    mp.start_processes(_worker, args=(world, port, out), nprocs=world, join=True, start_method="spawn")
     got = np.load(out)
     sys.path.insert(0, ROOT)
     from cooler_b200 import synth
