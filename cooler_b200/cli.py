@@ -1,0 +1,297 @@
+"""``cooler balance | coarsen | zoomify`` command-line entry points on the B200 path.
+
+Same flags, defaults, messages and exit codes as the reference's click commands
+(open2c/cooler src/cooler/cli/balance.py, coarsen.py, zoomify.py); ``--nproc`` and
+``--chunksize`` are accepted and ignored (no process pool: the GPU path must not
+fork after CUDA initialisation).  COOL_PATH is resolved by
+``cooler_b200.store.open_cooler``: a registered in-memory store, else the real
+``cooler`` package (h5py).
+
+    python -m cooler_b200.cli balance sample.cool --cis-only
+"""
+from __future__ import annotations
+
+import logging
+import shlex
+import sys
+import warnings
+from math import ceil
+
+import click
+import numpy as np
+
+from . import store
+from .balance import balance_cooler
+from .reduce import coarsen_cooler, preferred_sequence, zoomify_cooler
+
+HIGLASS_TILE_DIM = 256      # _reduce.py:28
+logger = logging.getLogger("cooler")
+
+
+@click.group()
+def cli():
+    """B200-native subset of the cooler CLI: balance, coarsen, zoomify."""
+    if not logger.handlers:
+        h = logging.StreamHandler(sys.stderr)
+        h.setFormatter(logging.Formatter("%(levelname)s:%(name)s:%(message)s"))
+        logger.addHandler(h)
+        logger.setLevel(logging.INFO)
+
+
+def parse_field_param(arg):
+    """'<name>[:dtype=<dtype>][,agg=<agg>]' (cli/_util.py:53-97, includes_colnum=False)."""
+    parts = arg.split(":")
+    if len(parts) > 2:
+        raise click.BadParameter(arg)
+    name, dtype, agg = parts[0], None, None
+    if len(parts) == 2:
+        for item in parts[1].split(","):
+            try:
+                prop, value = item.split("=")
+            except ValueError as e:
+                raise click.BadParameter(arg) from e
+            if prop == "dtype":
+                dtype = np.dtype(value)
+            elif prop == "agg":
+                agg = value
+            else:
+                raise click.BadParameter(f"Invalid property: '{prop}'.", param_hint=arg)
+    return name, dtype, agg
+
+
+def _fields(field):
+    if len(field):
+        specs = [parse_field_param(a) for a in field]
+        columns = [s[0] for s in specs]
+        dtypes = {s[0]: s[1] for s in specs if s[1] is not None}
+        agg = {s[0]: s[2] for s in specs if s[2] is not None}
+        return columns, dtypes, agg
+    return ["count"], None, None
+
+
+def _blacklist_bins(clr, path):
+    """BED regions -> concatenated bin ids (cli/balance.py:211-232; util.bedslice)."""
+    import csv
+
+    import pandas as pd
+    with open(path) as f:
+        has_header = csv.Sniffer().has_header(f.read(1024))
+    bad = pd.read_csv(path, sep="\t", header=0 if has_header else None, usecols=[0, 1, 2],
+                      names=["chrom", "start", "end"], dtype={"chrom": str})
+    bins = clr.bins()[:]
+    names = clr.chromnames
+    chrom = np.asarray(bins["chrom"])
+    if chrom.dtype.kind in "iu":
+        chrom = np.asarray(names, dtype=object)[chrom]
+    else:
+        chrom = chrom.astype(str)
+    start, end = bins["start"].values, bins["end"].values
+    out = []
+    for _, reg in bad.iterrows():
+        sel = np.flatnonzero((chrom == reg.chrom) & (end > reg.start) & (start < reg.end))
+        out.append(sel)
+    return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+
+
+@cli.command()
+@click.argument("cool_uri", type=str, metavar="COOL_PATH")
+@click.option("--cis-only", is_flag=True, default=False,
+              help="Calculate weights against intra-chromosomal data only instead of genome-wide.")
+@click.option("--trans-only", is_flag=True, default=False,
+              help="Calculate weights against inter-chromosomal data only instead of genome-wide.")
+@click.option("--ignore-diags", type=int, default=2, show_default=True,
+              help="Number of diagonals of the contact matrix to ignore, including the main diagonal.")
+@click.option("--ignore-dist", type=int,
+              help="Distance from the diagonal in bp to ignore (max with --ignore-diags is used).")
+@click.option("--mad-max", type=int, default=5, show_default=True, help="MAD-max bin filter.")
+@click.option("--min-nnz", type=int, default=10, show_default=True,
+              help="Ignore bins whose marginal number of nonzeros is less than this number.")
+@click.option("--min-count", type=int, default=0, show_default=True,
+              help="Ignore bins whose marginal count is less than this number.")
+@click.option("--blacklist", type=click.Path(exists=True),
+              help="3-column BED file of genomic regions to mask out.")
+@click.option("--nproc", "-p", type=int, default=8, show_default=True,
+              help="Accepted for compatibility; ignored (no process pool on the GPU path).")
+@click.option("--chunksize", "-c", type=int, default=int(10e6), show_default=True,
+              help="Accepted for compatibility; ignored (the table is resident in HBM).")
+@click.option("--tol", type=float, default=1e-5, show_default=True,
+              help="Threshold value of variance of the marginals for the algorithm to converge.")
+@click.option("--max-iters", type=int, default=200, show_default=True, help="Iteration limit.")
+@click.option("--name", type=str, default="weight", show_default=True, help="Name of column to write to.")
+@click.option("--force", "-f", is_flag=True, default=False,
+              help="Overwrite the target dataset, 'weight', if it already exists.")
+@click.option("--check", is_flag=True, default=False,
+              help="Check whether a data column 'weight' already exists.")
+@click.option("--stdout", is_flag=True, default=False,
+              help="Print weight column to stdout instead of saving to file.")
+@click.option("--convergence-policy", default="store_final", show_default=True,
+              type=click.Choice(["store_final", "store_nan", "discard", "error"]),
+              help="What to do with weights when balancing doesn't converge in max_iters.")
+def balance(cool_uri, nproc, chunksize, mad_max, min_nnz, min_count, blacklist, ignore_diags, tol,
+            cis_only, trans_only, max_iters, name, force, check, stdout, convergence_policy,
+            ignore_dist):
+    """Matrix balancing on the GPU.  COOL_PATH : Path to a COOL file."""
+    cool_path, group_path = store.parse_cooler_uri(cool_uri)
+    clr = store.open_cooler(cool_uri)
+
+    if check:                                                     # cli/balance.py:180-188
+        with clr.open("r") as grp:
+            if name not in grp["bins"]:
+                click.echo(f"{cool_path}: No '{name}' column found.")
+                sys.exit(1)
+            else:
+                click.echo(f"{cool_path}::{group_path} is balanced.")
+                sys.exit(0)
+
+    if cis_only and trans_only:                                   # 190-193
+        raise click.UsageError("Provide at most one of --cis-only and --trans-only flags")
+
+    with clr.open("r+") as grp:                                   # 195-206
+        if name in grp["bins"] and not stdout:
+            if not force:
+                print(f"'{name}' column already exists. Use --force option to overwrite.", file=sys.stderr)
+                sys.exit(1)
+            else:
+                del grp["bins"][name]
+
+    logger.info(f'Balancing "{cool_uri}"')
+    bad_bins = _blacklist_bins(clr, blacklist) if blacklist is not None else None
+    if ignore_dist is not None:                                   # 234-235
+        ignore_diags = max(ignore_diags, int(np.ceil(ignore_dist / clr.binsize)))
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                           # the CLI reports through the logger
+        bias, stats = balance_cooler(
+            clr, chunksize=chunksize, cis_only=cis_only, trans_only=trans_only, tol=tol,
+            min_nnz=min_nnz, min_count=min_count, blacklist=bad_bins, mad_max=mad_max,
+            max_iters=max_iters, ignore_diags=ignore_diags, rescale_marginals=True, use_lock=False)
+
+    if not np.all(stats["converged"]):                            # 265-277
+        logger.error("Iteration limit reached without convergence")
+        if convergence_policy == "store_final":
+            logger.error("Storing final result. Check log to assess convergence.")
+        elif convergence_policy == "store_nan":
+            logger.error("Saving weights as NaN.")
+            bias[:] = np.nan
+        elif convergence_policy == "discard":
+            logger.error("Discarding result and aborting.")
+            sys.exit(0)
+        elif convergence_policy == "error":
+            logger.error("Discarding result and aborting.")
+            sys.exit(1)
+
+    if stdout:                                                    # 279-282
+        import pandas as pd
+        pd.Series(bias).to_string(sys.stdout, header=False, index=False, na_rep="", float_format="%g")
+    else:                                                         # 283-289
+        with clr.open("r+") as grp:
+            h5opts = {"compression": "gzip", "compression_opts": 6}
+            grp["bins"].create_dataset(name, data=bias, **h5opts)
+            grp["bins"][name].attrs.update(stats)
+
+
+@cli.command()
+@click.argument("cool_uri", metavar="COOL_PATH")
+@click.option("--factor", "-k", type=int, default=2, show_default=True, help="Gridding factor.")
+@click.option("--nproc", "-n", "-p", default=1, type=int, help="Accepted for compatibility; ignored.")
+@click.option("--chunksize", "-c", type=int, default=int(10e6), show_default=True,
+              help="Number of pixels per output chunk.")
+@click.option("--field", type=str, multiple=True,
+              help="Value columns to merge as '<name>[:dtype=<dtype>][,agg=<agg>]'.")
+@click.option("--out", "-o", required=True, help="Output file or URI")
+@click.option("--append", "-a", is_flag=True, default=False,
+              help="Append the output cooler to an existing file instead of overwriting the file.")
+def coarsen(cool_uri, factor, nproc, chunksize, field, out, append):
+    """Coarsen a cooler to a lower resolution (k-by-k pooling per chromosomal block)."""
+    columns, dtypes, agg = _fields(field)
+    clr = store.open_cooler(cool_uri)
+    if store.is_memory_uri(cool_uri):
+        result = coarsen_cooler(clr, None, factor, chunksize=chunksize, nproc=nproc, columns=columns,
+                                dtypes=dtypes, agg=agg)
+        store.register(out, result)
+    else:  # pragma: no cover - needs h5py
+        coarsen_cooler(clr, out, factor, chunksize=chunksize, nproc=nproc, columns=columns,
+                       dtypes=dtypes, agg=agg, mode="a" if append else "w")
+
+
+def invoke_balance(args, resolutions, outfile):
+    """Balance every zoom level that lacks a 'weight' column (cli/zoomify.py:20-46)."""
+    args = [] if args is None else shlex.split(args)
+    for res in resolutions:
+        uri = outfile + "::resolutions/" + str(res)
+        with store.open_cooler(uri).open("r") as grp:
+            if "weight" in grp["bins"]:
+                continue
+        logger.info(f"Balancing zoom level with bin size {res}")
+        try:
+            balance.main(args=[uri, *args], prog_name="cooler")
+        except SystemExit as e:
+            if (e.code or 0) != 0:
+                raise e
+
+
+@cli.command()
+@click.argument("cool_uri", metavar="COOL_PATH")
+@click.option("--nproc", "-n", "-p", default=1, type=int, help="Accepted for compatibility; ignored.")
+@click.option("--chunksize", "-c", type=int, default=int(10e6), show_default=True)
+@click.option("--resolutions", "-r",
+              help="Comma-separated target resolutions; suffix B (binary) or N (nice) for a "
+                   "progression; 4DN = 1000,2000,5000N [default: B]")
+@click.option("--balance", "do_balance", is_flag=True, default=False, help="Apply balancing to each zoom level.")
+@click.option("--balance-args", type=str, help="Additional arguments to pass to cooler balance.")
+@click.option("--base-uri", "-i", multiple=True, help="Additional base coolers to aggregate from.")
+@click.option("--out", "-o", help="Output file or URI")
+@click.option("--field", type=str, multiple=True, help="Value columns to merge.")
+@click.option("--legacy", is_flag=True, default=False, help="Legacy integer-labeled zoom levels (not supported).")
+def zoomify(cool_uri, nproc, chunksize, resolutions, do_balance, balance_args, field, legacy, base_uri, out):
+    """Generate a multi-resolution cooler by coarsening on the GPU."""
+    if legacy:
+        raise click.UsageError("--legacy layout is not supported by the B200 path")
+    infile, _ = store.parse_cooler_uri(cool_uri)
+    outfile = infile.replace(".cool", ".mcool") if out is None else store.parse_cooler_uri(out)[0]
+    logger.info(f'Recursively aggregating "{cool_uri}"')
+    logger.info(f'Writing to "{outfile}"')
+    clr = store.open_cooler(cool_uri)
+    genome_length = clr.chromsizes.values.sum()
+    if clr.binsize:                                               # cli/zoomify.py:176-186
+        maxres = ceil(genome_length / HIGLASS_TILE_DIM)
+        curres = clr.binsize
+    else:
+        b = clr.bins()[["start", "end"]][:]
+        maxres = ceil(genome_length / (b["end"] - b["start"]).mean() / HIGLASS_TILE_DIM)
+        curres = 1
+    if resolutions is None:
+        resolutions = "b"
+    resolutions, rstring = [], resolutions
+    for res in [s.strip().lower() for s in rstring.split(",")]:   # 192-217
+        if ("n" in res or "b" in res) and maxres < curres:
+            warnings.warn("Map is already < 256 x 256. Provide resolutions explicitly if you want "
+                          "to coarsen more.", stacklevel=1)
+        if res == "n":
+            r = preferred_sequence(curres, maxres, "nice")
+        elif res == "b":
+            r = preferred_sequence(curres, maxres, "binary")
+        elif res == "4dn":
+            r = [1000, 2000, *preferred_sequence(5000, maxres, "nice")]
+        elif res.endswith("n"):
+            r = preferred_sequence(int(res.split("n")[0]), maxres, "nice")
+        elif res.endswith("b"):   # the reference repeats endswith("n") here and cannot reach this branch
+            r = preferred_sequence(int(res.split("b")[0]), maxres, "binary")
+        else:
+            r = [int(res)]
+        resolutions.extend(r)
+    columns, dtypes, agg = _fields(field)
+    bases = [clr] + [store.open_cooler(u) for u in base_uri]
+    if store.is_memory_uri(cool_uri):
+        levels = zoomify_cooler(bases, None, resolutions, chunksize, nproc=nproc, columns=columns,
+                                dtypes=dtypes, agg=agg)
+        store.register(outfile, {int(r): c for r, c in levels.items()})
+    else:  # pragma: no cover - needs h5py
+        zoomify_cooler([cool_uri, *list(base_uri)], outfile, resolutions, chunksize, nproc=nproc,
+                       columns=columns, dtypes=dtypes, agg=agg)
+    if do_balance:
+        invoke_balance(balance_args, resolutions, outfile)
+
+
+if __name__ == "__main__":
+    cli(prog_name="cooler")

@@ -15,6 +15,57 @@ from contextlib import contextmanager
 import numpy as np
 
 
+# ---------------------------------------------------------------------------
+# URI resolution: "mem://name" (or any registered name) -> in-memory store, anything
+# else -> the real cooler package (h5py).  A registered value may be a MemCooler or a
+# dict {resolution: MemCooler} standing for an .mcool ("name::resolutions/<res>").
+# ---------------------------------------------------------------------------
+REGISTRY: dict = {}
+
+
+def parse_cooler_uri(s):
+    """'path.cool::/group' -> (path, '/group')   (util.parse_cooler_uri, util.py:36-52)."""
+    parts = s.split("::")
+    if len(parts) == 1:
+        return parts[0], "/"
+    if len(parts) == 2:
+        g = parts[1]
+        return parts[0], g if g.startswith("/") else "/" + g
+    raise ValueError("Invalid Cooler URI string")
+
+
+def register(name, obj):
+    REGISTRY[parse_cooler_uri(name)[0]] = obj
+    return obj
+
+
+def is_memory_uri(uri):
+    return parse_cooler_uri(uri)[0] in REGISTRY
+
+
+def open_cooler(uri):
+    """Resolve a cooler URI to a Cooler-like object."""
+    if hasattr(uri, "_load_dset"):
+        return uri
+    path, group = parse_cooler_uri(uri)
+    if path in REGISTRY:
+        obj = REGISTRY[path]
+        if isinstance(obj, dict):
+            parts = [p for p in group.split("/") if p]
+            if len(parts) == 2 and parts[0] == "resolutions" and int(parts[1]) in obj:
+                return obj[int(parts[1])]
+            raise KeyError(f"No cooler found at: {path}::{group}")      # api.py:101-109
+        if group != "/":
+            raise KeyError(f"No cooler found at: {path}::{group}")
+        return obj
+    try:
+        import cooler
+    except ImportError as e:
+        raise ImportError(f"cannot open '{uri}': it is not a registered in-memory store and the "
+                          "`cooler` package (h5py) is not installed") from e
+    return cooler.Cooler(uri)
+
+
 class MemDataset:
     """A numpy array with ``attrs`` (stand-in for h5py.Dataset)."""
 
