@@ -21,7 +21,7 @@ struct IceOp {
 };
 
 // Tuning knob (cb200_set_tuning): 128-bit stream loads kept in flight per lane.
-static int g_ice_unroll = 2;
+static int g_ice_unroll = 0;   // 0 = automatic: 4 for the L1/L2-gather kernel, 2 for the shared-memory strip kernel
 
 template <int U>
 __global__ void __launch_bounds__(BLOCK_THREADS)
@@ -300,7 +300,7 @@ using namespace cb200;
 extern "C" {
 
 int cb200_set_tuning(int32_t ice_unroll) {
-  if (ice_unroll != 1 && ice_unroll != 2 && ice_unroll != 4 && ice_unroll != 8) return -1;
+  if (ice_unroll != 0 && ice_unroll != 1 && ice_unroll != 2 && ice_unroll != 4 && ice_unroll != 8) return -1;
   g_ice_unroll = ice_unroll;
   return 0;
 }
@@ -317,6 +317,7 @@ int cb200_ice_sweep(const cb200_ice* st, void* stream) {
       }
       CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_bytes = smem;
     }
     int dev = 0, sms = 148;
@@ -324,6 +325,10 @@ int cb200_ice_sweep(const cb200_ice* st, void* stream) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (g_ice_unroll == 1)
       ice_sweep_strips_kernel<1><<<sms, STRIP_THREADS, smem, (cudaStream_t)stream>>>(
+          st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,
+          reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
+    else if (g_ice_unroll == 4)
+      ice_sweep_strips_kernel<4><<<sms, STRIP_THREADS, smem, (cudaStream_t)stream>>>(
           st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,
           reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
     else
@@ -339,9 +344,9 @@ int cb200_ice_sweep(const cb200_ice* st, void* stream) {
       st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done)
   switch (g_ice_unroll) {
     case 1: CB_SWEEP(1); break;
-    case 4: CB_SWEEP(4); break;
+    case 2: CB_SWEEP(2); break;
     case 8: CB_SWEEP(8); break;
-    default: CB_SWEEP(2); break;
+    default: CB_SWEEP(4); break;
   }
 #undef CB_SWEEP
   CB_LAUNCH_CHECK("ice_sweep");

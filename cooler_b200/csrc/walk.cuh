@@ -41,85 +41,97 @@ __device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
                                                  const Op& op, typename Op::T* __restrict__ direct,
                                                  typename Op::T* __restrict__ pieces) {
   typedef typename Op::T T;
-  static_assert(WARP_TILE % (CHUNK * U) == 0, "tile must be a whole number of groups");
+  constexpr int G = CHUNK * U;                     // pixels per group
+  static_assert(WARP_TILE % G == 0, "tile must be a whole number of groups");
   const int lane = threadIdx.x & 31;
   const int64_t pbeg = t_begin * (int64_t)WARP_TILE;
-  const int64_t pend = min(t_end * (int64_t)WARP_TILE, nnz);
-  const int4* __restrict__ src = reinterpret_cast<const int4*>(px);
+  // all positions below are 32-bit offsets relative to pbeg (a span is a few tiles)
+  const int n = (int)(min(t_end * (int64_t)WARP_TILE, nnz) - pbeg);
+  const int4* __restrict__ src = reinterpret_cast<const int4*>(px + pbeg) + lane;
+  const T zero = acc_zero((T*)nullptr);
 
   int4 qn[U];                                      // next group (in flight)
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int64_t pos = pbeg + u * CHUNK + 2 * lane;
-    qn[u] = (pos < pend) ? ld_stream_int4(src + (pos >> 1)) : make_int4(0, 0, 0, 0);
-  }
+  for (int u = 0; u < U; ++u)
+    qn[u] = (u * CHUNK + 2 * lane < n) ? ld_stream_int4(src + u * (CHUNK / 2)) : make_int4(0, 0, 0, 0);
+
   int row = tile_row[t_begin];
-  int64_t row_end = indptr[row + 1];
-  T acc = acc_zero((T*)nullptr);
+  auto rel_end = [&](int r) -> int {               // end of row r relative to pbeg, clamped
+    const int64_t e = indptr[r + 1] - pbeg;
+    return e > (int64_t)0x7fffffff ? 0x7fffffff : (int)e;
+  };
+  int re = rel_end(row);
+  T acc = zero;
   bool first = true;
   int64_t t = t_begin;
-  int64_t tile_end = min(pbeg + (int64_t)WARP_TILE, nnz);
 
-  for (int64_t c = pbeg; c < pend; c += (int64_t)CHUNK * U) {
+  for (int c = 0; c < n; c += G) {
     int4 q[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) q[u] = qn[u];
-    {                                              // issue the next group's loads
-      const int64_t cn = c + (int64_t)CHUNK * U;
+    const int cn = c + G;
+    if (cn + G <= n) {                             // next group is full: unpredicated loads
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t pos = cn + u * CHUNK + 2 * lane;
-        if (pos < pend) qn[u] = ld_stream_int4(src + (pos >> 1));
-      }
+      for (int u = 0; u < U; ++u) qn[u] = ld_stream_int4(src + (cn >> 1) + u * (CHUNK / 2));
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (cn + u * CHUNK + 2 * lane < n) qn[u] = ld_stream_int4(src + (cn >> 1) + u * (CHUNK / 2));
     }
     T v0[U], v1[U];
+    if (cn <= n) {                                 // this group is full
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t pos = c + u * CHUNK + 2 * lane;
-      v0[u] = (pos < pend) ? op.value(q[u].x, q[u].y) : acc_zero((T*)nullptr);
-      v1[u] = (pos + 1 < pend) ? op.value(q[u].z, q[u].w) : acc_zero((T*)nullptr);
+      for (int u = 0; u < U; ++u) {
+        v0[u] = op.value(q[u].x, q[u].y);
+        v1[u] = op.value(q[u].z, q[u].w);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int pos = c + u * CHUNK + 2 * lane;
+        v0[u] = (pos < n) ? op.value(q[u].x, q[u].y) : zero;
+        v1[u] = (pos + 1 < n) ? op.value(q[u].z, q[u].w) : zero;
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int64_t cbeg = c + u * CHUNK;
-      if (cbeg >= pend) break;
-      const int64_t cend = min(cbeg + (int64_t)CHUNK, pend);
-      if (cend <= row_end) {                       // whole chunk inside the current row
+      const int cbeg = c + u * CHUNK;
+      if (cbeg >= n) break;
+      const int cend = min(cbeg + CHUNK, n);
+      if (cend <= re) {                            // whole chunk inside the current row
         acc = acc_add(acc, acc_add(v0[u], v1[u]));
       } else {                                     // one or more rows end inside this chunk
-        const int64_t pos = cbeg + 2 * lane;
+        const int pos = cbeg + 2 * lane;
         T a0 = v0[u], a1 = v1[u];
         while (true) {
-          if (pos < row_end) { acc = acc_add(acc, a0); a0 = acc_zero((T*)nullptr); }
-          if (pos + 1 < row_end) { acc = acc_add(acc, a1); a1 = acc_zero((T*)nullptr); }
-          if (row_end >= cend) break;
+          if (pos < re) { acc = acc_add(acc, a0); a0 = zero; }
+          if (pos + 1 < re) { acc = acc_add(acc, a1); a1 = zero; }
+          if (re >= cend) break;
           T tot = acc_wsum(acc);
           if (lane == 0) {
             if (first) pieces[2 * t] = tot; else direct[row] = tot;
           }
           first = false;
-          acc = acc_zero((T*)nullptr);
-          const int64_t done_to = row_end;
+          acc = zero;
+          const int done_to = re;
           do {                                     // next non-empty row
             ++row;
-            row_end = indptr[row + 1];
-          } while (row_end == done_to);
+            re = rel_end(row);
+          } while (re == done_to);
         }
       }
     }
-    if (c + (int64_t)CHUNK * U >= tile_end) {      // tile finished: emit its closing piece
+    if ((cn & (WARP_TILE - 1)) == 0 || cn >= n) {  // tile finished: emit its closing piece
       T tot = acc_wsum(acc);
       if (lane == 0) pieces[2 * t + (first ? 0 : 1)] = tot;
-      acc = acc_zero((T*)nullptr);
+      acc = zero;
       first = true;
       ++t;
-      const int64_t tile_start = tile_end;         // first pixel of the next tile
-      tile_end = min(tile_end + (int64_t)WARP_TILE, nnz);
-      if (tile_start < pend && row_end <= tile_start) {
+      if (cn < n && re <= cn) {
         do {                                       // the row ended exactly at the tile boundary
           ++row;
-          row_end = indptr[row + 1];
-        } while (row_end <= tile_start);
+          re = rel_end(row);
+        } while (re <= cn);
       }
     }
   }

@@ -58,9 +58,25 @@ class SynthPlan:
         thin = 0.78                       # mean of min(1, b_i*b_j) for b ~ LogNormal(0, 0.3)
         far_target = min((1 - f_cis) * self.nnz_target / thin, 0.95 * cells)
         self.m_far = int(-cells * math.log(max(1 - far_target / cells, 1e-3)))
-        self.cis_per_row = f_cis * self.nnz_target / n / thin * (oversample or (1.35 if fill < 0.2 else 1.6))
-        # per-row candidate weights -> block boundaries of ~equal candidate count
         rows = np.arange(n, dtype=np.float64)
+        nb_ = np.diff(self.chrom_offset)
+        room_ = np.repeat(self.chrom_offset[1:], nb_) - rows           # bins left in the chromosome
+        lnr_ = np.log1p(room_)
+
+        def expected_cis(c):
+            # candidates are log-uniform in distance: cells with >= 1 expected candidate saturate
+            dstar = np.clip(c / lnr_ - 1.0, 0.0, room_)
+            return np.minimum(dstar + c * (lnr_ - np.log1p(dstar)) / lnr_, room_)
+
+        want = f_cis * self.nnz_target / thin                          # distinct cis cells before thinning
+        c = want / n
+        for _ in range(30):                                            # fixed point on the candidate count
+            got = float(expected_cis(c).sum())
+            if got <= 0 or abs(got - want) < 1e-3 * want:
+                break
+            c *= min(4.0, want / got)
+        self.cis_per_row = c * (oversample or 1.0)
+        # per-row candidate weights -> block boundaries of ~equal candidate count
         far_w = (n - rows) / cells * self.m_far
         w = far_w + self.cis_per_row
         cw = np.r_[0.0, np.cumsum(w)]
@@ -71,13 +87,7 @@ class SynthPlan:
         # balance shards by pixels rather than by candidates
         rho = self.m_far / cells
         uniq_far = (n - rows) * (1.0 - math.exp(-rho))
-        nb = np.diff(self.chrom_offset)
-        room = np.repeat(self.chrom_offset[1:], nb) - rows            # bins left in the chromosome
-        lnr = np.log1p(room)
-        c = self.cis_per_row
-        dstar = np.clip(c / lnr - 1.0, 0.0, room)                      # distances with >= 1 expected candidate
-        uniq_cis = dstar + c * (lnr - np.log1p(dstar)) / lnr
-        self.row_weight_cum = np.r_[0.0, np.cumsum(uniq_far + np.minimum(uniq_cis, room))]
+        self.row_weight_cum = np.r_[0.0, np.cumsum(uniq_far + expected_cis(self.cis_per_row))]
 
     def shard_rows(self, rank, world):
         """Contiguous block-aligned row range of ``rank`` with ~1/world of the candidates."""

@@ -176,8 +176,8 @@ typedef struct {
   int32_t  max_iters;
 } cb200_ice;
 
-/* Tuning of K3 (optional): ice_unroll in {1,2,4,8} = 128-bit stream loads kept in
- * flight per lane (default 2). */
+/* Tuning of K3 (optional): ice_unroll in {0,1,2,4,8} = 128-bit stream loads kept in
+ * flight per lane; 0 (default) = 4 for the L1/L2-gather kernel, 2 for the strip kernel. */
 int cb200_set_tuning(int32_t ice_unroll);
 /* K3: the marginal sweeps of every sub-copy (bin1-major rows, bin2-major columns), one
  * launch.  No-op once *all_done. */
