@@ -175,7 +175,7 @@ def main():
         if rank != 0:
             return
         blocks = plan.shard_rows(0, n_gpus)
-        data = synth.generate(plan, blocks=blocks, pin=False)
+        data = synth.generate(plan, rows=blocks, pin=False)
         res = cpu_ice_passes(data, max(args.steps, 1), warmup=min(args.warmup, 1))
         val = res["value"]
         line = {"impl": "reference", "metric": "ICE pixels/s", "value": val, "unit": "pixels/s",
@@ -200,7 +200,7 @@ def main():
     from cooler_b200.balance import IceProblem, IceState, prefilter_bias
 
     blocks = plan.shard_rows(rank, world)
-    data = synth.generate(plan, blocks=blocks, device=f"cuda:{local_rank}")
+    data = synth.generate(plan, rows=blocks, device=f"cuda:{local_rank}")
     torch.cuda.empty_cache()
     nnz_local = data["nnz"]
     nnz_total = torch.tensor([nnz_local], dtype=torch.int64, device="cuda")
@@ -267,6 +267,14 @@ def main():
     sweep_ms = [e0.elapsed_time(e1) for k, (e0, e1) in enumerate(state.sweep_events)
                 if (k % per_step) < passes_per_step]
     sweep_ms_avg = float(np.mean(sweep_ms)) if sweep_ms else float("nan")
+    comm_ms = [c0.elapsed_time(c1) for k, (c0, c1) in enumerate(state.comm_events)
+               if (k % per_step) < passes_per_step]
+    comm_ms_avg = float(np.mean(comm_ms)) if comm_ms else 0.0
+    # slowest / fastest rank of the dominant kernel (shard balance) and the all-reduce share
+    rk = torch.tensor([sweep_ms_avg, -sweep_ms_avg, comm_ms_avg], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(rk, op=dist.ReduceOp.MAX)
+    sweep_ms_max, sweep_ms_min, comm_ms_max = float(rk[0]), -float(rk[1]), float(rk[2])
     gpu_launches = state.launches
     state.sweep_events = None
     value = nnz_total * passes_per_step * args.steps / (t_ms * 1e-3)
@@ -274,8 +282,18 @@ def main():
     peak, peak_src = load_peaks()
     bytes_pass_local = prob.bytes_per_pass()
     achieved = bytes_pass_local / (sweep_ms_avg * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "ice_sweep_kernel", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on
+    # this workload (profiles/r01_traffic.json), reported only when the pixel count matches
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tp) and world == 1:
+        with open(tp) as f:
+            for ent in json.load(f):
+                if ent["binsize"] == binsize and ent["mode"] == args.mode and ent["nnz_effective"] == prob.nnz_eff:
+                    traffic = ent["dram_bytes_per_launch"]
+    kernel_name = "ice_sweep_strips_kernel" if prob.strip_shift is not None else "ice_sweep_kernel"
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_pass_local, "kernel_ms_avg": sweep_ms_avg,
                 "formula": "16 B x effective pixels + 40 B x n_bins (per rank), SURVEY.md 8d",
                 "frac_of_nominal_8TBs": achieved / 8000.0}
@@ -322,7 +340,11 @@ def main():
                 "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e,
                 "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
                 "time_to_converge_s": {"resident_loop": t_ms * 1e-3 / max(args.steps, 1),
-                                       "e2e_from_pinned_host": float(t_e.item())}}
+                                       "e2e_from_pinned_host": float(t_e.item())},
+                "per_pass_ms": {"total": t_ms / max(args.steps, 1) / max(passes_per_step, 1),
+                                "sweep_rank0": sweep_ms_avg, "sweep_slowest_rank": sweep_ms_max,
+                                "sweep_fastest_rank": sweep_ms_min,
+                                "allreduce_incl_wait_slowest_rank": comm_ms_max}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -252,6 +252,7 @@ class IceState:
         self.flag_host = torch.zeros(1, dtype=_I32).pin_memory() if torch.cuda.is_available() else None
         self.launches = 0
         self.sweep_events = None          # list of (start, end) CUDA events per pass when profiling
+        self.comm_events = []             # same for the all-reduce (multi-GPU)
 
     def reset(self, bias0):
         """Back to the initial state (same resident copies): lets a bench repeat the loop."""
@@ -281,7 +282,14 @@ class IceState:
             self.launches += 3
         else:
             _lib.call("cb200_ice_combine", st, stream)
-            _allreduce(self.t["s"], self.prob.group)
+            if self.sweep_events is not None:
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                _allreduce(self.t["s"], self.prob.group)
+                c1.record()
+                self.comm_events.append((c0, c1))
+            else:
+                _allreduce(self.t["s"], self.prob.group)
             _lib.call("cb200_ice_update", st, int(it), 0, stream)
             self.launches += 4
 

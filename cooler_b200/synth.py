@@ -90,13 +90,13 @@ class SynthPlan:
         self.row_weight_cum = np.r_[0.0, np.cumsum(uniq_far + expected_cis(self.cis_per_row))]
 
     def shard_rows(self, rank, world):
-        """Contiguous block-aligned row range of ``rank`` with ~1/world of the candidates."""
-        nb = len(self.block_edges) - 1
-        cw = self.row_weight_cum[self.block_edges]
-        lo_b = int(np.searchsorted(cw, cw[-1] * rank / world, side="left")) if rank else 0
-        hi_b = int(np.searchsorted(cw, cw[-1] * (rank + 1) / world, side="left")) if rank + 1 < world else nb
-        lo_b, hi_b = min(lo_b, nb), min(max(hi_b, lo_b), nb)
-        return lo_b, hi_b
+        """Contiguous row range [lo, hi) of ``rank`` holding ~1/world of the expected pixels."""
+        cw = self.row_weight_cum
+        n = self.n_bins
+        lo = int(np.searchsorted(cw, cw[-1] * rank / world, side="left")) if rank else 0
+        hi = int(np.searchsorted(cw, cw[-1] * (rank + 1) / world, side="left")) if rank + 1 < world else n
+        lo, hi = min(lo, n), min(max(hi, lo), n)
+        return lo, hi
 
 
 def _gen_block(plan: SynthPlan, blk, bias_t, row_lo_t, row_hi_t, device):
@@ -141,8 +141,11 @@ def _gen_block(plan: SynthPlan, blk, bias_t, row_lo_t, row_hi_t, device):
     return b1, b2, cnt
 
 
-def generate(plan: SynthPlan, blocks=None, device=None, pin=True):
-    """Generate row blocks ``blocks=(lo_b, hi_b)`` (default: all).
+def generate(plan: SynthPlan, rows=None, device=None, pin=True):
+    """Generate the pixels of the row range ``rows=(lo, hi)`` (default: all rows).
+
+    Row blocks are the unit of random generation; a shard that starts or ends inside a
+    block generates that block and keeps its own rows, so shards tile the matrix exactly.
 
     Returns a dict of HOST tensors in the reference's on-disk dtypes
     (docs/schema_v3.rst): bin2_id int64, count int32, bin1_offset int64 [n_bins+1]
@@ -153,7 +156,13 @@ def generate(plan: SynthPlan, blocks=None, device=None, pin=True):
         device = "cuda" if torch.cuda.is_available() else "cpu"
     device = torch.device(device)
     n = plan.n_bins
-    lo_b, hi_b = blocks if blocks is not None else (0, len(plan.block_edges) - 1)
+    r_lo, r_hi = rows if rows is not None else (0, n)
+    edges = plan.block_edges
+    lo_b = int(np.searchsorted(edges, r_lo, side="right")) - 1
+    hi_b = int(np.searchsorted(edges, r_hi, side="left"))
+    lo_b, hi_b = max(lo_b, 0), min(max(hi_b, lo_b), len(edges) - 1)
+    if r_hi <= r_lo:
+        hi_b = lo_b
     bias_t = torch.from_numpy(hidden_bias(n, plan.seed)).to(device)
     nb = np.diff(plan.chrom_offset)
     row_lo_t = torch.from_numpy(np.repeat(plan.chrom_offset[:-1], nb)).to(device)
@@ -162,6 +171,9 @@ def generate(plan: SynthPlan, blocks=None, device=None, pin=True):
     row_counts = torch.zeros(n, dtype=torch.int64, device=device)
     for blk in range(lo_b, hi_b):
         b1, b2, cnt = _gen_block(plan, blk, bias_t, row_lo_t, row_hi_t, device)
+        if int(edges[blk]) < r_lo or int(edges[blk + 1]) > r_hi:      # block shared with a neighbour shard
+            keep = (b1 >= r_lo) & (b1 < r_hi)
+            b1, b2, cnt = b1[keep], b2[keep], cnt[keep]
         if b1.numel():
             row_counts += torch.bincount(b1, minlength=n)
         parts.append((b2.cpu(), cnt.cpu()))
@@ -181,5 +193,5 @@ def generate(plan: SynthPlan, blocks=None, device=None, pin=True):
     if use_pin:
         off = off.pin_memory()
     return {"bin2_id": bin2, "count": count, "bin1_offset": off, "nnz": nnz,
-            "row_range": (int(plan.block_edges[lo_b]), int(plan.block_edges[hi_b])),
+            "row_range": (int(r_lo), int(r_hi)),
             "chrom_offset": plan.chrom_offset, "n_bins": n}

@@ -32,7 +32,7 @@ def _worker(rank, world, port, out):
     from oracle import ice_numpy
     synth.ROWS_PER_BLOCK_TARGET = 200_000
     plan = synth.SynthPlan(1_000_000, 900_000, seed=5)
-    shard = synth.generate(plan, blocks=plan.shard_rows(rank, world), device="cpu", pin=False)
+    shard = synth.generate(plan, rows=plan.shard_rows(rank, world), device="cpu", pin=False)
     n = shard["n_bins"]
     off = shard["bin1_offset"].numpy()
     b1 = np.repeat(np.arange(n, dtype=np.int64), np.diff(off))

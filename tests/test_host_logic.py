@@ -126,7 +126,7 @@ def test_synth_generator_shards_tile_the_matrix():
         plan = synth.SynthPlan(1_000_000, 1_200_000, seed=3)
         full = synth.generate(plan, device="cpu", pin=False)
         assert len(plan.block_edges) > 4
-        parts = [synth.generate(plan, blocks=plan.shard_rows(r, 3), device="cpu", pin=False) for r in range(3)]
+        parts = [synth.generate(plan, rows=plan.shard_rows(r, 3), device="cpu", pin=False) for r in range(3)]
     finally:
         synth.ROWS_PER_BLOCK_TARGET = old
     assert sum(p["nnz"] for p in parts) == full["nnz"]

@@ -30,7 +30,7 @@ def main():
         plan = synth.SynthPlan(binsize, target, seed=1)
         for mode in ("gw", "cis", "trans"):
             kw = dict(cis_only=mode == "cis", trans_only=mode == "trans")
-            shard = synth.generate(plan, blocks=plan.shard_rows(rank, world), device=f"cuda:{local}")
+            shard = synth.generate(plan, rows=plan.shard_rows(rank, world), device=f"cuda:{local}")
             tab = cooler_b200.PixelTable.from_arrays(shard["bin1_offset"], shard["bin2_id"], shard["count"],
                                                      shard["chrom_offset"], device=f"cuda:{local}",
                                                      row_range=shard["row_range"])

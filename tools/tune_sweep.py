@@ -23,7 +23,7 @@ variants = [(2, 0, 0), (2, 16384, 1), (2, 16384, 2), (2, 8192, 2), (2, 32768, 2)
 if os.environ.get('TUNE_VARIANTS'):
     variants = [tuple(int(x) for x in v.split(':')) for v in os.environ['TUNE_VARIANTS'].split(',')]
 plan = synth.SynthPlan(binsize, target, seed=0)
-data = synth.generate(plan, blocks=plan.shard_rows(rank, world))
+data = synth.generate(plan, rows=plan.shard_rows(rank, world))
 print("n_bins", plan.n_bins, "nnz(shard)", data["nnz"], "rows", data["row_range"], flush=True)
 tab = cooler_b200.PixelTable.from_arrays(data["bin1_offset"], data["bin2_id"], data["count"], data["chrom_offset"])
 del data
