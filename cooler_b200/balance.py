@@ -46,6 +46,30 @@ def _allreduce(t, group):
     return t
 
 
+class _PeerVectors:
+    """Double-buffered per-bin vector in NVLink peer-mapped (symmetric) memory."""
+
+    def __init__(self, local, handle, ptrs, stride, world):
+        self.local, self.handle, self.ptrs, self.stride, self.world = local, handle, ptrs, stride, world
+
+    @classmethod
+    def create(cls, n, group, dev):
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            if dist.get_backend(group) != "nccl":
+                return None
+            stride = -(-max(n, 1) // 64) * 64
+            local = symm_mem.empty(2 * stride, dtype=_F64, device=dev)
+            local.zero_()
+            handle = symm_mem.rendezvous(local, group)
+            ptrs = torch.tensor(list(handle.buffer_ptrs), dtype=torch.int64, device=dev)
+            return cls(local, handle, ptrs, stride, handle.world_size)
+        except Exception as e:  # pragma: no cover - depends on the platform
+            logger.warning(f"peer-memory reduction unavailable ({e!r}); using NCCL all-reduce")
+            return None
+
+
 class IceProblem:
     """Filtered CSR/CSC copies of one table for one (mode, ignore_diags) choice.
 
@@ -57,9 +81,12 @@ class IceProblem:
     """
 
     def __init__(self, table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2,
-                 group=None, strip_bins=None, use_smem=True, band=None):
+                 group=None, strip_bins=None, use_smem=True, band=None, peer_reduce=None):
         self.table = table
         self.use_smem = use_smem
+        if peer_reduce is None:
+            peer_reduce = os.environ.get("CB200_PEER_REDUCE", "1") != "0"
+        self.peer_reduce = peer_reduce
         self.group = group
         self.mode = "cis" if cis_only else ("trans" if trans_only else "gw")
         n_bins = table.n_bins
@@ -229,6 +256,13 @@ class IceState:
         t["subs"] = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         t["claim"] = torch.zeros(len(subs) + 1, dtype=torch.int64, device=dev)
         t["s"], t["marg"] = f64(n), f64(n)
+        # multi-GPU: local s vectors live in peer-mapped symmetric memory (double-buffered) and
+        # K4a sums them over NVLink; falls back to an NCCL all-reduce if that is unavailable
+        self.peer = None
+        if prob.group is not None and prob.peer_reduce:
+            self.peer = _PeerVectors.create(n, prob.group, dev)
+            if self.peer is not None:
+                t["s"] = self.peer.local[: max(n, 1)]
         t["blk_sum"], t["blk_cnt"], t["blk_dev"] = f64(nb), f64(nb), f64(nb)
         t["seg_mean"], t["seg_nnz"] = f64(S), f64(S)
         t["seg_scale"], t["seg_var"] = f64(S, 1.0), f64(S, float("nan"))
@@ -253,6 +287,7 @@ class IceState:
         self.launches = 0
         self.sweep_events = None          # list of (start, end) CUDA events per pass when profiling
         self.comm_events = []             # same for the all-reduce (multi-GPU)
+        self._peer_tick = 0
 
     def reset(self, bias0):
         """Back to the initial state (same resident copies): lets a bench repeat the loop."""
@@ -280,6 +315,22 @@ class IceState:
         if self.prob.group is None:                   # single GPU: combine fused into K4a
             _lib.call("cb200_ice_update", st, int(it), 1, stream)
             self.launches += 3
+        elif self.peer is not None:                   # multi-GPU, all-reduce fused into K4a over NVLink
+            half = self._peer_tick & 1            # keeps alternating across runs (no reuse hazard)
+            self._peer_tick += 1
+            self.st.s = self.peer.local.data_ptr() + 8 * half * self.peer.stride
+            _lib.call("cb200_ice_combine", C.byref(self.st), stream)
+            timed = self.sweep_events is not None
+            if timed:
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+            self.peer.handle.barrier(channel=half)
+            if timed:
+                c1.record()
+                self.comm_events.append((c0, c1))
+            _lib.call("cb200_ice_update_peer", C.byref(self.st), int(it), _ptr(self.peer.ptrs),
+                      self.peer.world, half * self.peer.stride, stream)
+            self.launches += 4
         else:
             _lib.call("cb200_ice_combine", st, stream)
             if self.sweep_events is not None:

@@ -184,9 +184,13 @@ __device__ __forceinline__ bool last_block_ticket(int32_t* ticket) {
 
 // K4a: [s = row totals over sub-copies] -> marg = w * s -> per-block sum / count of the
 // nonzero marginals -> (last block) per-segment mean.
-template <bool kCombine>
+// kMode 0: s is given (after an NCCL all-reduce); 1: s = row totals of the local
+// sub-copies (single GPU); 2: s = sum over ranks, in rank order, of every rank's local s
+// read through peer (NVLink) pointers -- the all-reduce fused into K4a, identical bits
+// on every rank.
+template <int kMode>
 __global__ void __launch_bounds__(UPD_THREADS)
-ice_marg_kernel(cb200_ice st) {
+ice_marg_kernel(cb200_ice st, const double* const* __restrict__ peer_s, int world, int64_t peer_off) {
   __shared__ double sm[UPD_THREADS / 32];
   if (*st.all_done) return;
   const int b = blockIdx.x;
@@ -196,7 +200,10 @@ ice_marg_kernel(cb200_ice st) {
     double sum = 0.0, cnt = 0.0;
     for (int i = lo + threadIdx.x; i < hi; i += UPD_THREADS) {
       double si;
-      if (kCombine) {
+      if (kMode == 2) {
+        si = 0.0;
+        for (int r = 0; r < world; ++r) si += __ldcv(peer_s[r] + peer_off + i);
+      } else if (kMode == 1) {
         si = 0.0;
         for (int k = 0; k < st.n_subs; ++k) {
           const unsigned r = (unsigned)(i - st.subs[k].row_base);
@@ -361,13 +368,24 @@ int cb200_ice_combine(const cb200_ice* st, void* stream) {
   return 0;
 }
 
+int cb200_ice_update_peer(const cb200_ice* st, int32_t iter, const double* const* peer_s,
+                          int32_t world, int64_t peer_offset, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (st->n_blocks <= 0) return 0;
+  ice_marg_kernel<2><<<st->n_blocks, UPD_THREADS, 0, s>>>(*st, peer_s, world, peer_offset);
+  CB_LAUNCH_CHECK("ice_marg_peer");
+  ice_update_kernel<<<st->n_blocks, UPD_THREADS, 0, s>>>(*st, iter);
+  CB_LAUNCH_CHECK("ice_update");
+  return 0;
+}
+
 int cb200_ice_update(const cb200_ice* st, int32_t iter, int32_t fused_combine, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (st->n_blocks <= 0) return 0;
   if (fused_combine)
-    ice_marg_kernel<true><<<st->n_blocks, UPD_THREADS, 0, s>>>(*st);
+    ice_marg_kernel<1><<<st->n_blocks, UPD_THREADS, 0, s>>>(*st, nullptr, 0, 0);
   else
-    ice_marg_kernel<false><<<st->n_blocks, UPD_THREADS, 0, s>>>(*st);
+    ice_marg_kernel<0><<<st->n_blocks, UPD_THREADS, 0, s>>>(*st, nullptr, 0, 0);
   CB_LAUNCH_CHECK("ice_marg");
   ice_update_kernel<<<st->n_blocks, UPD_THREADS, 0, s>>>(*st, iter);
   CB_LAUNCH_CHECK("ice_update");

@@ -190,6 +190,13 @@ int cb200_ice_combine(const cb200_ice* st, void* stream);
  * (single GPU; cb200_ice_combine is then not needed); 0: st->s is read as given
  * (multi-GPU: after the all-reduce). */
 int cb200_ice_update(const cb200_ice* st, int32_t iter, int32_t fused_combine, void* stream);
+/* Multi-GPU K4 with the all-reduce fused in: peer_s is a DEVICE array of `world`
+ * pointers, peer_s[r] + peer_offset = rank r's local s vector (written by
+ * cb200_ice_combine into peer-mapped symmetric memory; the caller places a
+ * cross-rank barrier between the two calls).  Every rank sums the `world` vectors in
+ * rank order over NVLink, so all ranks get identical bits without an NCCL call. */
+int cb200_ice_update_peer(const cb200_ice* st, int32_t iter, const double* const* peer_s,
+                          int32_t world, int64_t peer_offset, void* stream);
 
 /* ---- coarsen (replaces CoolerCoarsener._aggregate's join + pandas
  *      groupby(sort=True).sum(), src/cooler/_reduce.py:582-620) ------------ */
