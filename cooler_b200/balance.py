@@ -52,8 +52,25 @@ class _PeerVectors:
     def __init__(self, local, handle, ptrs, stride, world):
         self.local, self.handle, self.ptrs, self.stride, self.world = local, handle, ptrs, stride, world
 
+    _cache: dict = {}
+
     @classmethod
     def create(cls, n, group, dev):
+        """Allocate + rendezvous once per (group, size, device); later calls reuse the buffers
+        (the rendezvous is a collective that costs ~0.1 s)."""
+        import torch.distributed as dist
+        key = (id(group), int(n), str(dev))
+        if key in cls._cache:
+            pv = cls._cache[key]
+            if pv is not None:
+                pv.local.zero_()
+            return pv
+        pv = cls._create(n, group, dev)
+        cls._cache[key] = pv
+        return pv
+
+    @classmethod
+    def _create(cls, n, group, dev):
         import torch.distributed as dist
         try:
             import torch.distributed._symmetric_memory as symm_mem
