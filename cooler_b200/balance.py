@@ -51,6 +51,8 @@ class _PeerVectors:
 
     def __init__(self, local, handle, ptrs, stride, world):
         self.local, self.handle, self.ptrs, self.stride, self.world = local, handle, ptrs, stride, world
+        self.tick = 0     # which half is written next; never reset, so a half is only reused after
+                          # a later barrier proved every peer is done reading it
 
     _cache: dict = {}
 
@@ -61,10 +63,7 @@ class _PeerVectors:
         import torch.distributed as dist
         key = (id(group), int(n), str(dev))
         if key in cls._cache:
-            pv = cls._cache[key]
-            if pv is not None:
-                pv.local.zero_()
-            return pv
+            return cls._cache[key]
         pv = cls._create(n, group, dev)
         cls._cache[key] = pv
         return pv
@@ -333,8 +332,8 @@ class IceState:
             _lib.call("cb200_ice_update", st, int(it), 1, stream)
             self.launches += 3
         elif self.peer is not None:                   # multi-GPU, all-reduce fused into K4a over NVLink
-            half = self._peer_tick & 1            # keeps alternating across runs (no reuse hazard)
-            self._peer_tick += 1
+            half = self.peer.tick & 1             # keeps alternating across runs and calls
+            self.peer.tick += 1
             self.st.s = self.peer.local.data_ptr() + 8 * half * self.peer.stride
             _lib.call("cb200_ice_combine", C.byref(self.st), stream)
             timed = self.sweep_events is not None
