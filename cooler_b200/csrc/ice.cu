@@ -12,11 +12,17 @@
 
 namespace cb200 {
 
+// Exact int32 -> double without the (quarter-rate, XU pipe) I2F.F64 instruction:
+// the bit pattern {0x43300000, count ^ 0x80000000} is 2^52 + 2^31 + count.
+__device__ __forceinline__ double i32_to_f64(int v) {
+  return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
+}
+
 struct IceOp {
   typedef double T;
   const double* __restrict__ w;
   __device__ __forceinline__ double value(int other, int count) const {
-    return __ldg(w + other) * (double)count;
+    return __ldg(w + other) * i32_to_f64(count);
   }
 };
 
@@ -54,7 +60,7 @@ struct IceOpSmem {
   const double* ws;     // shared memory slice
   int base;
   __device__ __forceinline__ double value(int other, int count) const {
-    return ws[other - base] * (double)count;
+    return ws[other - base] * i32_to_f64(count);
   }
 };
 
