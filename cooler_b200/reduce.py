@@ -22,9 +22,10 @@ import torch
 from . import _lib
 from .store import MemCooler
 from .table import (PixelTable, TableCopy, _ptr, _stream, _use_device, exclusive_scan_i32,
-                    indptr_from_sorted, key_bits_for, n_tiles, sort_pairs)
+                    indptr_from_sorted, key_bits_for, n_tiles, sort_pairs, swap_key_other)
 
 __all__ = ["CoolerCoarsener", "coarsen_cooler", "zoomify_cooler", "coarsen_table",
+           "CoolerMerger", "merge_coolers", "merge_tables",
            "get_multiplier_sequence", "preferred_sequence", "ZOOMS_4DN", "get_quadtree_depth"]
 
 # Resolutions of the 4DN multires standard (_reduce.py:30-44).
@@ -163,16 +164,7 @@ def coarsen_table(table: PixelTable, factor: int):
     _lib.call("cb200_coarsen_remap", C.byref(cs), csr.n_rows, _ptr(bin_map_d), _ptr(key), _ptr(val), _stream())
     ks, vs = sort_pairs(key[:n], val, bits)
     del key, val
-    nt = n_tiles(n)
-    tile_count = torch.zeros(max(nt, 1), dtype=_I32, device=dev)
-    _lib.call("cb200_runs_count", _ptr(ks), _ptr(vs), n, _ptr(tile_count), _stream())
-    tile_off = exclusive_scan_i32(tile_count[:nt])
-    n_out = int(tile_off[-1].item())
-    k2 = torch.empty(max(n_out, 1), dtype=_I32, device=dev)
-    v2 = torch.empty((n_out + 2, 2), dtype=_I32, device=dev)
-    overflow = torch.zeros(1, dtype=_I32, device=dev)
-    _lib.call("cb200_runs_write", _ptr(ks), _ptr(vs), n, _ptr(tile_off), 1, _ptr(k2), _ptr(v2),
-              C.c_void_p(0), _ptr(overflow), _stream())
+    k2, v2, n_out, overflow = _reduce_runs(ks, vs, n, 1, dev)
     del ks, vs
     k3, v3 = sort_pairs(k2[:n_out], v2, bits)
     del k2, v2
@@ -181,6 +173,58 @@ def coarsen_table(table: PixelTable, factor: int):
     indptr = indptr_from_sorted(k3, n_out, n_new)
     new_raw = TableCopy(v3, indptr, n_out, n_new)
     return PixelTable(new_raw, new_off), k3
+
+
+def _reduce_runs(keys, vals, n, swap, dev):
+    """Reduce-by-key over adjacent equal (key, val.other) pairs; returns (key', val', n_out)."""
+    nt = n_tiles(n)
+    tile_count = torch.zeros(max(nt, 1), dtype=_I32, device=dev)
+    _lib.call("cb200_runs_count", _ptr(keys), _ptr(vals), n, _ptr(tile_count), _stream())
+    tile_off = exclusive_scan_i32(tile_count[:nt])
+    n_out = int(tile_off[-1].item())
+    k2 = torch.empty(max(n_out, 1), dtype=_I32, device=dev)
+    v2 = torch.empty((n_out + 2, 2), dtype=_I32, device=dev)
+    overflow = torch.zeros(1, dtype=_I32, device=dev)
+    _lib.call("cb200_runs_write", _ptr(keys), _ptr(vals), n, _ptr(tile_off), int(swap), _ptr(k2), _ptr(v2),
+              C.c_void_p(0), _ptr(overflow), _stream())
+    return k2, v2, n_out, overflow
+
+
+def merge_tables(tables):
+    """Sum several device-resident tables over identical bins (the k-way merge of
+    ``CoolerMerger``, _reduce.py:132-208): concatenate, stable radix sort by bin2 then by
+    bin1, reduce-by-key.  Returns (PixelTable, bin1 ids)."""
+    n_bins = tables[0].n_bins
+    dev = _use_device(tables[0].device)
+    ident = torch.arange(n_bins, dtype=_I32, device=dev)
+    keys, vals = [], []
+    for t in tables:
+        if t.n_bins != n_bins:
+            raise ValueError("tables must share one bin segmentation")
+        csr = t.raw
+        key = torch.empty(max(csr.nnz, 1), dtype=_I32, device=dev)
+        val = torch.empty((csr.nnz + 2, 2), dtype=_I32, device=dev)
+        cs = csr.c_struct()
+        _lib.call("cb200_coarsen_remap", C.byref(cs), csr.n_rows, _ptr(ident), _ptr(key), _ptr(val), _stream())
+        keys.append(key[: csr.nnz])
+        vals.append(val[: csr.nnz])
+    n = int(sum(k.numel() for k in keys))
+    key = torch.cat(keys)
+    val = torch.cat(vals + [torch.zeros((2, 2), dtype=_I32, device=dev)])
+    del keys, vals
+    bits = key_bits_for(n_bins)
+    ks, vs = sort_pairs(key, val, bits)                       # by bin2
+    del key, val
+    k2, v2 = swap_key_other(ks, vs, n)                         # key = bin1, val = {bin2, count}
+    del ks, vs
+    k3, v3 = sort_pairs(k2, v2, bits)                          # stable by bin1 -> (bin1, bin2) order
+    del k2, v2
+    k4, v4, n_out, overflow = _reduce_runs(k3, v3, n, 0, dev)
+    del k3, v3
+    if int(overflow.item()):
+        raise OverflowError("merged count does not fit int32")
+    indptr = indptr_from_sorted(k4, n_out, n_bins)
+    return PixelTable(TableCopy(v4, indptr, n_out, n_bins), tables[0].chrom_offset), k4[:n_out]
 
 
 def table_to_host(table: PixelTable, bin1_ids=None):
@@ -343,3 +387,93 @@ def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=
                                   dtypes=dtypes, agg=agg, device=device, table=tab)
         tables[res] = out[res].device_table
     return out
+
+
+class CoolerMerger:
+    """GPU replacement of ``cooler._reduce.CoolerMerger`` (_reduce.py:132-208): a
+    ContactBinner-style iterable over the merged, lexsorted, duplicate-free pixels of
+    several coolers with identical axes, in chunks of about ``mergebuf`` pixels."""
+
+    def __init__(self, coolers, mergebuf, columns=None, agg=None, device="cuda"):
+        self.coolers = list(coolers)
+        self.mergebuf = int(mergebuf)
+        self.columns = ["count"] if columns is None else list(columns)
+        if self.columns != ["count"] or (agg and any(v != "sum" for v in agg.values())):
+            raise NotImplementedError(
+                "the CUDA merger aggregates the integer 'count' column with 'sum' only")
+        binsize = self.coolers[0].binsize                          # compatibility checks: 150-166
+        if binsize is not None:
+            if len({c.binsize for c in self.coolers}) > 1:
+                raise ValueError("Coolers must have the same resolution")
+            chromsizes = self.coolers[0].chromsizes
+            for c in self.coolers[1:]:
+                cs = c.chromsizes
+                if len(cs) != len(chromsizes) or not np.all(cs.values == chromsizes.values) \
+                        or list(cs.index) != list(chromsizes.index):
+                    raise ValueError("Coolers must have the same chromosomes")
+        else:
+            bins = self.coolers[0].bins()[["chrom", "start", "end"]][:]
+            for c in self.coolers[1:]:
+                if c.binsize is not None:
+                    raise ValueError("Coolers must have same bin structure")
+                b2 = c.bins()[["chrom", "start", "end"]][:]
+                if len(b2) != len(bins) or not np.all(b2.values == bins.values):
+                    raise ValueError("Coolers must have same bin structure")
+        self.device = device
+        self.result_table = None
+
+    def __iter__(self):
+        tables = [PixelTable.from_cooler(c, device=self.device) for c in self.coolers]
+        merged, ids = merge_tables(tables)
+        self.result_table = merged
+        b1, b2, cnt = table_to_host(merged, ids)
+        ind = merged.raw.indptr.cpu().numpy()
+        edges = _prune_edges(ind, self.mergebuf)
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            if hi > lo:
+                yield {"bin1_id": b1[lo:hi], "bin2_id": b2[lo:hi], "count": cnt[lo:hi]}
+
+
+def merge_coolers(output_uri, input_uris, mergebuf, columns=None, dtypes=None, agg=None,
+                  device="cuda", **kwargs):
+    """Merge coolers with identical axes on the GPU (``cooler.merge_coolers``,
+    _reduce.py:211-307).  ``input_uris``: URIs/paths (needs the ``cooler`` package) or
+    Cooler-like objects.  ``output_uri=None`` returns a ``MemCooler``."""
+    clrs = [_as_cooler(u) for u in input_uris]
+    is_symm = [c.storage_mode == "symmetric-upper" for c in clrs]
+    if all(is_symm):
+        symmetric_upper = True
+    elif not any(is_symm):
+        symmetric_upper = False
+    else:
+        raise ValueError("Cannot merge symmetric and non-symmetric coolers.")
+    columns = ["count"] if columns is None else list(columns)
+    dtype_map = {col: [] for col in columns}
+    for c in clrs:
+        pd_ = c.pixels().dtypes
+        for col in columns:
+            if col not in pd_:
+                raise ValueError(f"Pixel value column '{col}' not found in input '{c.filename}'.")
+            dtype_map[col].append(pd_[col])
+    dtypes = dict(dtypes or {})
+    for col in columns:
+        dtypes.setdefault(col, np.result_type(*dtype_map[col]))
+    iterator = CoolerMerger(clrs, mergebuf=mergebuf, columns=columns, agg=agg, device=device)
+    if output_uri is None:
+        chunks = list(iterator)
+        cat = {k: (np.concatenate([c[k] for c in chunks]) if chunks else np.zeros(0, dtype=np.int64))
+               for k in ("bin1_id", "bin2_id", "count")}
+        c0 = clrs[0]
+        bins = c0.bins()[:]
+        out = MemCooler.from_arrays(list(c0.chromsizes.index), c0.chromsizes.values,
+                                    np.asarray(c0._load_dset("bins/chrom")), bins["start"].values,
+                                    bins["end"].values, cat["bin1_id"], cat["bin2_id"],
+                                    cat["count"].astype(dtypes["count"], copy=False),
+                                    binsize=c0.binsize, symmetric_upper=symmetric_upper)
+        out.device_table = iterator.result_table
+        return out
+    from cooler.create import create  # real writer (h5py)
+    bins = clrs[0].bins()[["chrom", "start", "end"]][:]
+    create(output_uri, bins, iterator, columns=columns, dtypes=dtypes,
+           assembly=clrs[0].info.get("genome-assembly", None), symmetric_upper=symmetric_upper, **kwargs)
+    return None

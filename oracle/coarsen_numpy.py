@@ -100,3 +100,23 @@ def coarsen_pixels(px, bins_chrom, bins_start, bins_end, chromsizes, factor,
     if count_dtype is None:
         count_dtype = cnt.dtype
     return n1.astype(np.int64), n2.astype(np.int64), acc.astype(count_dtype), (new_c, new_s, new_e)
+
+
+def merge_pixels(tables, count_dtype=None):
+    """Restatement of ``CoolerMerger.__iter__`` over whole tables (_reduce.py:170-208):
+    concatenate the pixel tables, ``groupby([bin1_id, bin2_id], sort=True).sum()``.
+    Epoch boundaries (merge_breakpoints) only chunk the output; content is independent.
+    tables: list of dicts with bin1_id, bin2_id, count."""
+    b1 = np.concatenate([np.asarray(t["bin1_id"], dtype=np.int64) for t in tables])
+    b2 = np.concatenate([np.asarray(t["bin2_id"], dtype=np.int64) for t in tables])
+    cnt = np.concatenate([np.asarray(t["count"]) for t in tables])
+    if count_dtype is None:
+        count_dtype = np.result_type(*[np.asarray(t["count"]).dtype for t in tables])   # merge_coolers: 286-291
+    order = np.lexsort((b2, b1))
+    b1, b2, cnt = b1[order], b2[order], cnt[order]
+    if len(b1) == 0:
+        return b1, b2, cnt.astype(count_dtype)
+    head = np.r_[True, (b1[1:] != b1[:-1]) | (b2[1:] != b2[:-1])]
+    starts = np.flatnonzero(head)
+    acc = np.add.reduceat(cnt.astype(np.int64 if cnt.dtype.kind in "iu" else np.float64), starts)
+    return b1[starts], b2[starts], acc.astype(count_dtype)

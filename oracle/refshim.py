@@ -233,3 +233,12 @@ def ref_coarsen(name, factor, chunksize=10_000_000):
     new_bins = {"chrom": np.asarray(nb["chrom"].cat.codes if hasattr(nb["chrom"], "cat") else nb["chrom"]),
                 "start": nb["start"].values, "end": nb["end"].values}
     return out, new_bins
+
+
+def ref_merge(names, mergebuf=20_000_000):
+    """Concatenated chunk stream of the reference's CoolerMerger (_reduce.py:132-208)."""
+    cooler = import_reference()
+    clrs = [cooler.Cooler(n) for n in names]
+    it = cooler._reduce.CoolerMerger(clrs, mergebuf=mergebuf)
+    chunks = list(it)
+    return {k: np.concatenate([c[k] for c in chunks]) for k in ("bin1_id", "bin2_id", "count")}

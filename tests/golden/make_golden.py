@@ -234,6 +234,24 @@ def main():
         co[f"var/x{f}"] = np.stack([out["bin1_id"], out["bin2_id"], out["count"]], axis=1)
         co[f"var/x{f}/bins"] = np.stack([np.asarray(nb["chrom"]), np.asarray(nb["start"]), np.asarray(nb["end"])], axis=1)
         print("var coarsen", f, len(out["bin1_id"]))
+    # ---------------- merge (CoolerMerger, _reduce.py:132-208) ----------------
+    rng = np.random.default_rng(11)
+    parts = []
+    for k in range(3):
+        sel = rng.random(len(gm["bin1_id"])) < (0.5, 0.3, 0.8)[k]
+        cnt = (gm["count"][sel] * (k + 1)).astype(np.int32)
+        nm = f"gm.part{k}.cool"
+        refshim.register(nm, gm["chromnames"].tolist(), gm["chromsizes"], gm["bins_chrom"], gm["bins_start"],
+                         gm["bins_end"], gm["bin1_id"][sel], gm["bin2_id"][sel], cnt, 2_000_000)
+        co[f"merge/part{k}"] = np.stack([gm["bin1_id"][sel], gm["bin2_id"][sel], cnt], axis=1)
+        parts.append(nm)
+    for mergebuf in (20_000_000, 5000):
+        out = refshim.ref_merge(parts, mergebuf=mergebuf)
+        m = np.stack([out["bin1_id"], out["bin2_id"], out["count"]], axis=1)
+        if "merge/out" in co:
+            assert np.array_equal(co["merge/out"], m)          # epochs only chunk the output
+        co["merge/out"] = m
+    print("merge 3-way", len(co["merge/out"]), int(co["merge/out"][:, 2].sum()))
     np.savez_compressed(os.path.join(HERE, "coarsen_golden.npz"), **co)
 
 

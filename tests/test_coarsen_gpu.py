@@ -130,3 +130,68 @@ def test_coarsen_matches_oracle_large(factor):
     assert int(gc.sum()) == int(cnt.sum())           # size-independent invariant: total count preserved
     # the coarse table is itself a valid input: its indptr matches its ids
     np.testing.assert_array_equal(new.raw.indptr.cpu().numpy(), np.searchsorted(g1, np.arange(new.n_bins + 1)))
+
+
+def _gm_part(k):
+    t = _golden.gm12878()
+    return _mem(t["chromnames"], t["chromsizes"], t["bins_chrom"], t["bins_start"], t["bins_end"],
+                CO[f"merge/part{k}"], 2_000_000)
+
+
+@pytest.mark.parametrize("mergebuf", [20_000_000, 5000])
+def test_merge_matches_reference_golden(mergebuf):
+    """3-way merge vs the unmodified reference's CoolerMerger (tests/golden/make_golden.py)."""
+    from cooler_b200.reduce import CoolerMerger
+    chunks = list(CoolerMerger([_gm_part(k) for k in range(3)], mergebuf))
+    got = _cat(chunks)
+    np.testing.assert_array_equal(got, CO["merge/out"])
+    if mergebuf == 5000:
+        assert len(chunks) > 3
+
+
+def test_merge_coolers_semantics():
+    """tests/test_reduce.py:34-75 re-targeted: doubled counts, dtype promotion, ValueErrors."""
+    from cooler_b200.reduce import merge_coolers
+    sizes = np.array([32, 32])
+    bc, bs, be = _golden.uniform_bins(sizes, 2)
+    toy2 = _mem(["chr1", "chr2"], sizes, bc, bs, be, CO["toy.symm.upper/2"], 2)
+    out = merge_coolers(None, [toy2, toy2], mergebuf=3)
+    with out.open() as g:
+        got = np.stack([g["pixels/bin1_id"][:], g["pixels/bin2_id"][:], g["pixels/count"][:]], 1)
+    want = CO["toy.symm.upper/2"].copy()
+    want[:, 2] *= 2
+    np.testing.assert_array_equal(got, want)
+    bc4, bs4, be4 = _golden.uniform_bins(sizes, 4)
+    toy4 = _mem(["chr1", "chr2"], sizes, bc4, bs4, be4, CO["toy.symm.upper/4"], 4)
+    with pytest.raises(ValueError):
+        merge_coolers(None, [toy2, toy4], mergebuf=3)                 # different resolution
+    asym = _mem(["chr1", "chr2"], sizes, bc, bs, be, CO["toy.asymm/2"], 2, symm=False)
+    with pytest.raises(ValueError):
+        merge_coolers(None, [toy2, asym], mergebuf=3)                 # incompatible symmetry
+    bins = CO["var/bins"]
+    var = _mem(["chr1", "chr2"], sizes, bins[:, 0], bins[:, 1], bins[:, 2], CO["var/px"], None)
+    with pytest.raises(ValueError):
+        merge_coolers(None, [var, toy2], mergebuf=3)                  # incompatible bins
+    with pytest.raises(ValueError):
+        merge_coolers(None, [toy2, var], mergebuf=3)
+    with pytest.raises(ValueError):
+        merge_coolers(None, [toy2, toy2], mergebuf=3, columns=["missing"])
+
+
+def test_merge_matches_oracle_large():
+    from cooler_b200 import PixelTable
+    from cooler_b200.reduce import merge_tables, table_to_host
+    from oracle import coarsen_numpy
+    from tests.test_balance_gpu import _synthetic
+    tabs, pxs = [], []
+    for seed in (41, 42, 43, 44):
+        b1, b2, cnt, chrom_offset = _synthetic(seed, [30000, 17001, 1, 9000], 0.0008)
+        n = int(chrom_offset[-1])
+        pxs.append(dict(bin1_id=b1, bin2_id=b2, count=cnt))
+        tabs.append(PixelTable.from_arrays(np.searchsorted(b1, np.arange(n + 1)), b2, cnt, chrom_offset))
+    want = coarsen_numpy.merge_pixels(pxs)
+    merged, ids = merge_tables(tabs)
+    g1, g2, gc = table_to_host(merged, ids)
+    np.testing.assert_array_equal(g1, want[0]), np.testing.assert_array_equal(g2, want[1])
+    np.testing.assert_array_equal(gc, want[2])
+    assert int(gc.sum()) == sum(int(p["count"].sum()) for p in pxs)

@@ -124,3 +124,11 @@ def test_coarsen_oracle_variable_bins(factor):
         px, bins[:, 0], bins[:, 1], bins[:, 2], np.array([32, 32]), factor)
     np.testing.assert_array_equal(np.stack([b1, b2, c], 1), CO[f"var/x{factor}"])
     np.testing.assert_array_equal(np.stack([nc, ns, ne], 1), CO[f"var/x{factor}/bins"])
+
+
+def test_merge_oracle_matches_reference_golden():
+    parts = [dict(bin1_id=CO[f"merge/part{k}"][:, 0], bin2_id=CO[f"merge/part{k}"][:, 1],
+                  count=CO[f"merge/part{k}"][:, 2].astype(np.int32)) for k in range(3)]
+    b1, b2, c = coarsen_numpy.merge_pixels(parts)
+    np.testing.assert_array_equal(np.stack([b1, b2, c], 1), CO["merge/out"])
+    assert c.dtype == np.int32
