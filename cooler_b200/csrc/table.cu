@@ -14,7 +14,8 @@ void set_error(cudaError_t e, const char* where) {
 void set_error_msg(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg); }
 
 // ------------------------------------------------------------------ pack ----
-__global__ void pack_pixels_kernel(const int64_t* __restrict__ bin2, const int32_t* __restrict__ count,
+template <typename TBin>
+__global__ void pack_pixels_kernel(const TBin* __restrict__ bin2, const int32_t* __restrict__ count,
                                    int64_t nnz, int2* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride)
@@ -217,9 +218,20 @@ int cb200_pack_pixels(const int64_t* bin2_id, const int32_t* count, int64_t nnz,
   if (nnz <= 0) return 0;
   int64_t blocks = ceil_div64(nnz, 256 * 8);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  pack_pixels_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+  pack_pixels_kernel<int64_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       bin2_id, count, nnz, reinterpret_cast<int2*>(px_out));
   CB_LAUNCH_CHECK("pack_pixels");
+  return 0;
+}
+
+int cb200_pack_pixels_i32(const int32_t* bin2_id, const int32_t* count, int64_t nnz,
+                          cb200_px* px_out, void* stream) {
+  if (nnz <= 0) return 0;
+  int64_t blocks = ceil_div64(nnz, 256 * 8);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  pack_pixels_kernel<int32_t><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      bin2_id, count, nnz, reinterpret_cast<int2*>(px_out));
+  CB_LAUNCH_CHECK("pack_pixels_i32");
   return 0;
 }
 

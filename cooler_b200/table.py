@@ -290,10 +290,13 @@ class PixelTable:
                 "cooler_b200 balances integer count columns only (float value columns are not "
                 "supported by the CUDA path yet)")
         indptr = dev(bin1_offset, _I64)
-        bin2_d = dev(bin2_id, _I64)
+        bin2_t = bin2_id if isinstance(bin2_id, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bin2_id))
+        narrow = bin2_t.dtype == _I32                 # reader already narrowed the ids: 8 B/pixel over PCIe
+        bin2_d = dev(bin2_t, _I32 if narrow else _I64)
         count_d = dev(count_t, _I32)
         px = _new_px(nnz, device)
-        _lib.call("cb200_pack_pixels", _ptr(bin2_d), _ptr(count_d), nnz, _ptr(px), _stream())
+        _lib.call("cb200_pack_pixels_i32" if narrow else "cb200_pack_pixels", _ptr(bin2_d), _ptr(count_d),
+                  nnz, _ptr(px), _stream())
         raw = TableCopy(px, indptr, nnz, n_bins)
         return cls(raw, chrom_offset, row_range=row_range)
 
@@ -307,7 +310,12 @@ class PixelTable:
         """
         chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
         bin1_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
+        n_bins = len(bin1_offset) - 1
         with clr.open("r") as grp:
-            bin2 = grp["pixels"]["bin2_id"][:]
+            d2 = grp["pixels"]["bin2_id"]
+            if hasattr(d2, "astype") and hasattr(d2, "id") and n_bins < 2**31 - 1:
+                bin2 = d2.astype(np.int32)[:]          # h5py converts while reading: no int64 staging
+            else:
+                bin2 = d2[:]
             count = grp["pixels"]["count"][:]
         return cls.from_arrays(bin1_offset, bin2, count, chrom_offset, device=device)

@@ -63,6 +63,10 @@ int cb200_sort_pairs(const int32_t* keys_in, const cb200_px* vals_in,
 /* (bin2_id int64, count int32) -> packed px {bin2, count}. */
 int cb200_pack_pixels(const int64_t* bin2_id, const int32_t* count, int64_t nnz,
                       cb200_px* px_out, void* stream);
+/* Same for a bin2_id column already narrowed to int32 by the reader (h5py:
+ * dset.astype("int32")[:]), which cuts the host->device copy from 12 to 8 B/pixel. */
+int cb200_pack_pixels_i32(const int32_t* bin2_id, const int32_t* count, int64_t nnz,
+                          cb200_px* px_out, void* stream);
 /* tile_row[t] = row that contains pixel t*warp_tile (n_tiles entries). */
 int cb200_tile_rows(const int64_t* indptr, int32_t n_rows, int64_t nnz,
                     int32_t* tile_row, void* stream);

@@ -84,3 +84,11 @@ def test_filter_transpose_marginals(n_bins, nnz, seed, ndiag, keep):
                                       np.bincount(rows, weights=(vals != 0), minlength=n_bins).astype(np.int64))
         np.testing.assert_array_equal(sum_m.cpu().numpy(),
                                       np.bincount(rows, weights=vals, minlength=n_bins).astype(np.int64))
+
+
+def test_from_arrays_int32_bin2_equals_int64():
+    from cooler_b200 import table as T
+    b1, b2, cnt, ind, chrom_offset = _table(3000, 200_000, 7)
+    a = T.PixelTable.from_arrays(ind, b2, cnt, chrom_offset)
+    b = T.PixelTable.from_arrays(ind, b2.astype(np.int32), cnt, chrom_offset)
+    assert torch.equal(a.raw.px[: a.nnz], b.raw.px[: b.nnz])
