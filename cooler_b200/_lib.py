@@ -71,7 +71,7 @@ SIGNATURES = {
     "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _P, _P]),
     "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
-    "cb200_set_tuning": (C.c_int, [_I32]),
+    "cb200_set_tuning": (C.c_int, [_I32, _I32]),
     "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_combine": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_update": (C.c_int, [C.POINTER(Ice), _I32, _I32, _P]),

@@ -18,18 +18,41 @@ __device__ __forceinline__ double i32_to_f64(int v) {
   return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;   // 2^52 + 2^31
 }
 
-struct IceOp {
+// Gather of w[other] through L1/L2.  For bias vectors far larger than L1 only the band
+// around the current row is worth caching in L1: gathers farther than kNearBins from the
+// row bypass L1 allocation so that they do not evict the band (the stream loads bypass
+// L1 as well).  The result is the same either way.
+constexpr int kNearBins = 12288;      // 96 KB of fp64 on either side of the diagonal
+
+__device__ __forceinline__ double ld_gather_far(const double* p) {
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+
+template <bool kSelective>
+struct IceOpT {
   typedef double T;
   const double* __restrict__ w;
+  int row_base;      // bin id of local row 0 of the sub-copy
+  int center;
+  __device__ __forceinline__ void at_row(int row) { if (kSelective) center = row + row_base; }
   __device__ __forceinline__ double value(int other, int count) const {
-    return __ldg(w + other) * i32_to_f64(count);
+    double wv;
+    if (kSelective && (unsigned)(other - center + kNearBins) > (unsigned)(2 * kNearBins))
+      wv = ld_gather_far(w + other);
+    else
+      wv = __ldg(w + other);
+    return wv * i32_to_f64(count);
   }
 };
+typedef IceOpT<false> IceOp;
 
 // Tuning knob (cb200_set_tuning): 128-bit stream loads kept in flight per lane.
+static int g_selective = -1;   // -1 = automatic
 static int g_ice_unroll = 0;   // 0 = automatic: 4 for the L1/L2-gather kernel, 2 for the shared-memory strip kernel
 
-template <int U>
+template <int U, bool kSelective>
 __global__ void __launch_bounds__(BLOCK_THREADS)
 ice_sweep_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span, int64_t total_warps,
                  const double* __restrict__ w, const int32_t* __restrict__ all_done) {
@@ -45,9 +68,9 @@ ice_sweep_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span, int64
   const int64_t n_tiles = (sub.nnz + WARP_TILE - 1) / WARP_TILE;
   const int64_t t0 = (wg - sub.first_warp) * span;
   if (t0 >= n_tiles) return;
-  IceOp op{w};
-  walk_reduce_span<IceOp, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row, sub.nnz,
-                             t0, min(t0 + span, n_tiles), op, sub.direct, sub.pieces);
+  IceOpT<kSelective> op{w, sub.row_base, 0};
+  walk_reduce_span<IceOpT<kSelective>, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
+                                          sub.nnz, t0, min(t0 + span, n_tiles), op, sub.direct, sub.pieces);
 }
 
 // Shared-memory form of K3 for column strips: a persistent CTA per SM owns a
@@ -59,6 +82,7 @@ struct IceOpSmem {
   typedef double T;
   const double* ws;     // shared memory slice
   int base;
+  __device__ __forceinline__ void at_row(int) {}
   __device__ __forceinline__ double value(int other, int count) const {
     return ws[other - base] * i32_to_f64(count);
   }
@@ -312,9 +336,10 @@ using namespace cb200;
 
 extern "C" {
 
-int cb200_set_tuning(int32_t ice_unroll) {
+int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1) {
   if (ice_unroll != 0 && ice_unroll != 1 && ice_unroll != 2 && ice_unroll != 4 && ice_unroll != 8) return -1;
   g_ice_unroll = ice_unroll;
+  g_selective = selective_l1 < 0 ? -1 : (selective_l1 ? 1 : 0);
   return 0;
 }
 
@@ -352,9 +377,17 @@ int cb200_ice_sweep(const cb200_ice* st, void* stream) {
     return 0;
   }
   const int64_t blocks = ceil_div64(st->total_warps, WARPS_PER_BLOCK);
-#define CB_SWEEP(U)                                                                    \
-  ice_sweep_kernel<U><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(   \
-      st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done)
+  // selective L1 allocation only pays when w is much larger than L1 (tools/tune_sweep.py)
+  const int selective = g_selective < 0 ? (st->n_bins > 4 * kNearBins ? 1 : 0) : g_selective;
+#define CB_SWEEP(U)                                                                                 \
+  do {                                                                                              \
+    if (selective)                                                                                  \
+      ice_sweep_kernel<U, true><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(      \
+          st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);                    \
+    else                                                                                            \
+      ice_sweep_kernel<U, false><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(     \
+          st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);                    \
+  } while (0)
   switch (g_ice_unroll) {
     case 1: CB_SWEEP(1); break;
     case 2: CB_SWEEP(2); break;

@@ -171,6 +171,7 @@ filter_write_kernel(const int2* __restrict__ px, const int64_t* __restrict__ ind
 // ---------------------------------------------------- integer marginals ----
 struct NnzSumOp {
   typedef I64x2 T;
+  __device__ __forceinline__ void at_row(int) {}
   __device__ __forceinline__ I64x2 value(int, int count) const {
     return I64x2{count != 0 ? 1 : 0, (long long)count};
   }

@@ -38,7 +38,7 @@ __device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
                                                  const int64_t* __restrict__ indptr,
                                                  const int32_t* __restrict__ tile_row,
                                                  int64_t nnz, int64_t t_begin, int64_t t_end,
-                                                 const Op& op, typename Op::T* __restrict__ direct,
+                                                 Op& op, typename Op::T* __restrict__ direct,
                                                  typename Op::T* __restrict__ pieces) {
   typedef typename Op::T T;
   constexpr int G = CHUNK * U;                     // pixels per group
@@ -64,6 +64,7 @@ __device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
   T acc = zero;
   bool first = true;
   int64_t t = t_begin;
+  op.at_row(row);
 
   for (int c = 0; c < n; c += G) {
     int4 q[U];
@@ -118,6 +119,7 @@ __device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
             ++row;
             re = rel_end(row);
           } while (re == done_to);
+          op.at_row(row);
         }
       }
     }
@@ -132,6 +134,7 @@ __device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
           ++row;
           re = rel_end(row);
         } while (re <= cn);
+        op.at_row(row);
       }
     }
   }
@@ -142,7 +145,7 @@ template <typename Op, int U>
 __device__ __forceinline__ void walk_reduce_tile(const int2* __restrict__ px,
                                                  const int64_t* __restrict__ indptr, int64_t nnz,
                                                  int64_t t, const int32_t* __restrict__ tile_row,
-                                                 const Op& op, typename Op::T* __restrict__ direct,
+                                                 Op& op, typename Op::T* __restrict__ direct,
                                                  typename Op::T* __restrict__ pieces) {
   walk_reduce_span<Op, U>(px, indptr, tile_row, nnz, t, t + 1, op, direct, pieces);
 }

@@ -39,7 +39,7 @@ for unroll, strip_bins, use_smem in variants:
         bias0 = prefilter_bias(prob, tab.chrom_offset, mad_max=5, min_nnz=10, min_count=0, blacklist=None, x0=None)
         state = IceState(prob, bias0, None, np.array([0, tab.n_bins]), 1e-5, 200)
         last_strip = (strip_bins, use_smem)
-    assert lib.cb200_set_tuning(unroll) == 0
+    assert lib.cb200_set_tuning(unroll % 10, -1 if unroll < 10 else (unroll // 10) - 1) == 0   # 1x: selective off, 2x: on
     state.reset(bias0)
     st = C.byref(state.st)
     for _ in range(3):
