@@ -236,3 +236,44 @@ def test_band_layout_large_synthetic_matches_unstripped():
     assert ia["passes"] == ib["passes"]
     np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
     np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("case", ["empty", "diag_only", "one_bin", "one_pixel", "all_masked"])
+@pytest.mark.parametrize("mode", ["gw", "cis", "trans"])
+def test_degenerate_tables_match_oracle(case, mode):
+    """Edge cases of the reference: no pixels, everything filtered, a single bin."""
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    from oracle import ice_numpy
+    if case == "empty":
+        chrom_offset = np.array([0, 5, 9]); b1 = b2 = np.zeros(0, np.int64); cnt = np.zeros(0, np.int32)
+    elif case == "diag_only":
+        chrom_offset = np.array([0, 5, 9]); b1 = np.arange(9); b2 = b1.copy(); cnt = np.full(9, 7, np.int32)
+    elif case == "one_bin":
+        chrom_offset = np.array([0, 1]); b1 = np.array([0]); b2 = np.array([0]); cnt = np.array([3], np.int32)
+    elif case == "one_pixel":
+        chrom_offset = np.array([0, 4, 8]); b1 = np.array([1]); b2 = np.array([6]); cnt = np.array([5], np.int32)
+    else:
+        chrom_offset = np.array([0, 6, 12])
+        i, j = np.triu_indices(12, 2)
+        b1, b2, cnt = i, j, np.ones(len(i), np.int32)
+    n = int(chrom_offset[-1])
+    b1, b2 = b1.astype(np.int64), b2.astype(np.int64)
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    kw = dict(cis_only=(mode == "cis"), trans_only=(mode == "trans"))
+    if case == "all_masked":
+        kw["min_nnz"] = 1000
+    elif case in ("one_pixel",):
+        kw.update(min_nnz=0, mad_max=0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want, wstats, wpasses, _ = ice_numpy.balance_arrays(dict(bin1_id=b1, bin2_id=b2, count=cnt), chrom_offset,
+                                                           bin1_offset, return_passes=True, max_iters=50, **kw)
+        tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
+        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, max_iters=50, **kw)
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    np.testing.assert_allclose(bias, want, rtol=RTOL, equal_nan=True)
+    assert info["passes"] == wpasses
+    np.testing.assert_allclose(np.atleast_1d(stats["var"]), np.atleast_1d(wstats["var"]), rtol=1e-9, equal_nan=True)
+    np.testing.assert_allclose(np.atleast_1d(stats["scale"]), np.atleast_1d(wstats["scale"]), rtol=1e-9, equal_nan=True)
+    np.testing.assert_array_equal(np.atleast_1d(stats["converged"]), np.atleast_1d(wstats["converged"]))
