@@ -140,6 +140,19 @@ def get_multiplier_sequence(resolutions, bases=None):
     return resn, pred, mult
 
 
+def align_rows_to_factor(chrom_offset, factor, row):
+    """Largest row <= ``row`` that starts a coarse bin (a multiple of ``factor`` counted from
+    its chromosome's first bin).  Shards cut at such rows coarsen independently: no coarse
+    row is split between ranks (the reference's chunk edges obey the same rule,
+    _reduce.py:550-561)."""
+    chrom_offset = np.asarray(chrom_offset, dtype=np.int64)
+    row = int(row)
+    if row >= chrom_offset[-1]:
+        return int(chrom_offset[-1])
+    c = int(np.searchsorted(chrom_offset, row, side="right")) - 1
+    return int(chrom_offset[c] + (row - chrom_offset[c]) // factor * factor)
+
+
 # --------------------------------------------------------------------------
 # device path
 # --------------------------------------------------------------------------

@@ -139,3 +139,14 @@ def test_synth_generator_shards_tile_the_matrix():
     key = b1 * full["n_bins"] + full["bin2_id"].numpy()
     assert np.all(np.diff(key) > 0) and np.all(full["bin2_id"].numpy() >= b1)
     assert 0.7 < full["nnz"] / 1_200_000 < 1.3
+
+
+def test_align_rows_to_factor():
+    from cooler_b200.reduce import align_rows_to_factor, coarsen_bin_map
+    off = np.array([0, 51, 158, 191])
+    for f in (2, 4, 7):
+        bmap, _ = coarsen_bin_map(off, f)
+        for row in range(0, 192):
+            a = align_rows_to_factor(off, f, row)
+            assert a <= row and (a == 191 or a == 0 or bmap[a] != bmap[a - 1])   # a starts a coarse bin
+            assert row == 191 or bmap[a] == bmap[row]                             # and it is row's coarse bin

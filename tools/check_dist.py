@@ -48,6 +48,39 @@ def main():
                       f"passes={max(info['passes'])} mask_equal={same_mask} max_rel_err={err:.2e} "
                       f"{'OK' if good else 'FAIL'}", flush=True)
             dist.barrier()
+    # coarsening shards with no exchange: rows cut at coarse-bin boundaries, every rank coarsens its
+    # shard, rank-ordered concatenation == single-GPU result (bit-exact)
+    from cooler_b200.reduce import align_rows_to_factor, coarsen_table, table_to_host
+    plan = synth.SynthPlan(250_000, 6_000_000, seed=2)
+    for factor in (2, 5):
+        lo, hi = plan.shard_rows(rank, world)
+        lo = align_rows_to_factor(plan.chrom_offset, factor, lo)
+        hi = align_rows_to_factor(plan.chrom_offset, factor, hi) if rank + 1 < world else plan.n_bins
+        shard = synth.generate(plan, rows=(lo, hi), device=f"cuda:{local}")
+        tab = cooler_b200.PixelTable.from_arrays(shard["bin1_offset"], shard["bin2_id"], shard["count"],
+                                                 shard["chrom_offset"], device=f"cuda:{local}", row_range=(lo, hi))
+        new, ids = coarsen_table(tab, factor)
+        g = [torch.from_numpy(x).cuda() for x in table_to_host(new, ids)]
+        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([g[0].numel()], dtype=torch.int64, device="cuda"))
+        sizes = [int(x.item()) for x in sizes]
+        parts = []
+        for col in g:
+            bufs = [torch.zeros(max(sizes), dtype=col.dtype, device="cuda") for _ in range(world)]
+            pad = torch.zeros(max(sizes), dtype=col.dtype, device="cuda")
+            pad[: col.numel()] = col
+            dist.all_gather(bufs, pad)
+            parts.append(torch.cat([b[:k] for b, k in zip(bufs, sizes)]).cpu().numpy())
+        if rank == 0:
+            full = synth.generate(plan, device=f"cuda:{local}")
+            tab1 = cooler_b200.PixelTable.from_arrays(full["bin1_offset"], full["bin2_id"], full["count"],
+                                                      full["chrom_offset"], device=f"cuda:{local}")
+            w = table_to_host(*coarsen_table(tab1, factor))
+            good = all(np.array_equal(a, b) for a, b in zip(parts, w))
+            ok &= bool(good)
+            print(f"[check_dist] world={world} sharded coarsen x{factor}: nnz_out={len(w[0])} "
+                  f"{'OK (bit-exact)' if good else 'FAIL'}", flush=True)
+        dist.barrier()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()
