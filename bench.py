@@ -315,15 +315,13 @@ def main():
     for k in range(1 + e2e_steps):       # first run = warm-up
         barrier()
         t0 = time.perf_counter()
-        tab = cooler_b200.PixelTable.from_arrays(data["bin1_offset"], data["bin2_id"], data["count"],
-                                                 data["chrom_offset"], device=f"cuda:{local_rank}",
-                                                 row_range=data["row_range"])
-        bias, stats, info = cooler_b200.balance_table(tab, group=group, return_info=True, **kw,
-                                                      **{k_: v for k_, v in ICE_KW.items()})
+        bias, stats, info = cooler_b200.balance_arrays(
+            data["bin1_offset"], data["bin2_id"], data["count"], data["chrom_offset"],
+            device=f"cuda:{local_rank}", row_range=data["row_range"], group=group, return_info=True,
+            **kw, **{k_: v for k_, v in ICE_KW.items()})
         barrier()
         if k > 0:
             t_e2e.append(time.perf_counter() - t0)
-        del tab
     t_e = torch.tensor([float(np.mean(t_e2e))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
@@ -332,7 +330,8 @@ def main():
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "seconds_per_call": float(t_e.item()), "passes": e2e_passes,
            "host_bin2_dtype": args.host_bin2,
-           "api": "cooler_b200.PixelTable.from_arrays(pinned host) + balance_table -> numpy bias"}
+           "n_subcopies": info["n_subcopies"],
+           "api": "cooler_b200.balance_arrays(pinned host arrays) -> numpy bias (build pipelined with the H2D copy)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

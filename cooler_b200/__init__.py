@@ -8,7 +8,8 @@ All compute runs in hand-written CUDA kernels (cooler_b200/csrc, C ABI in
 include/cooler_b200.h).  There is no CPU fallback: importing the compute
 entry points without the built library or without a CUDA device raises.
 """
-from .balance import ConvergenceWarning, balance_cooler, balance_table, iterative_correction  # noqa: F401
+from .balance import (ConvergenceWarning, balance_arrays, balance_cooler, balance_table,  # noqa: F401
+                      iterative_correction)
 from .store import MemCooler  # noqa: F401
 from .table import PixelTable  # noqa: F401
 

@@ -68,8 +68,8 @@ SIGNATURES = {
     "cb200_indptr_from_sorted": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P]),
     "cb200_swap_key_other": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "cb200_strip_finish": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
-    "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _P, _P]),
-    "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
+    "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
     "cb200_set_tuning": (C.c_int, [_I32, _I32]),
     "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),

@@ -19,10 +19,11 @@ import numpy as np
 import torch
 
 from . import _lib
-from .table import (PixelTable, TableCopy, _ptr, _stream, _use_device, filter_copy,  # noqa: F401
-                    marginals_i64, n_tiles, strip_partition, swap_key_other, transpose_from)
+from .table import (PixelTable, TableCopy, _new_px, _ptr, _stream, _use_device, filter_copy,  # noqa: F401
+                    marginals_i64, n_tiles, read_cooler_arrays, strip_partition, swap_key_other,
+                    transpose_from)
 
-__all__ = ["balance_cooler", "balance_table", "ConvergenceWarning", "IceProblem"]
+__all__ = ["balance_cooler", "balance_table", "balance_arrays", "ConvergenceWarning", "IceProblem"]
 
 logger = logging.getLogger("cooler")   # same logger name as the reference (_logging.py)
 
@@ -44,6 +45,26 @@ def _allreduce(t, group):
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+_COPY_STREAMS: dict = {}
+
+
+def _copy_stream(dev):
+    key = str(dev)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[key]
+
+
+class _TableInfo:
+    """What balance_table needs to know about a table that was consumed while streaming."""
+
+    def __init__(self, n_bins, chrom_offset, device, row_range):
+        self.n_bins, self.chrom_offset, self.device, self.row_range = n_bins, chrom_offset, device, row_range
+        nb = np.diff(chrom_offset)
+        self.row_lo = torch.from_numpy(np.repeat(chrom_offset[:-1], nb).astype(np.int32)).to(device)
+        self.row_hi = torch.from_numpy(np.repeat(chrom_offset[1:], nb).astype(np.int32)).to(device)
 
 
 class _PeerVectors:
@@ -157,6 +178,109 @@ class IceProblem:
             self.subs = subs
             self.csr = self.csc = None
         tkey = tval = ckeys = cval = None
+
+    # ------------------------------------------------------------------ streamed build
+    @classmethod
+    def from_host(cls, bin1_offset, bin2_id, count, chrom_offset, *, cis_only=False, trans_only=False,
+                  ignore_diags=2, group=None, device="cuda", n_chunks=8, peer_reduce=None,
+                  row_range=None):
+        """Build the problem straight from host arrays, **pipelined with the host->device copy**.
+
+        The table is cut into row chunks; chunk c+1 crosses PCIe (copy stream) while chunk c is
+        packed, filtered, radix-sorted into its own bin2-major copy and marginalised on the main
+        stream.  Every chunk contributes a bin1-major and a bin2-major sub-copy (the column sums
+        of the chunks add up exactly like column strips or multi-GPU shards), so nothing has to
+        wait for the whole table.  Returns None when the layout needs column strips (large
+        n_bins): the caller then uses the two-step path (PixelTable + IceProblem).
+        """
+        dev = _use_device(device)
+        off_t = bin1_offset if isinstance(bin1_offset, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(bin1_offset, dtype=np.int64))
+        off_np = off_t.numpy()
+        n_bins = len(off_np) - 1
+        b2_t = bin2_id if isinstance(bin2_id, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bin2_id))
+        c_t = count if isinstance(count, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(count))
+        if c_t.dtype.is_floating_point:
+            raise NotImplementedError("cooler_b200 balances integer count columns only")
+        if c_t.dtype != _I32:
+            c_t = c_t.to(_I32)
+        if b2_t.dtype not in (_I32, torch.int64):
+            b2_t = b2_t.to(torch.int64)
+        nnz = int(b2_t.numel())
+        if n_bins >= 2**31 - 1:
+            raise ValueError("n_bins must fit int32")
+        if choose_layout(n_bins, nnz, None)[0] is not None or nnz == 0:
+            return None
+        chrom_offset = np.asarray(chrom_offset, dtype=np.int64)
+        info = _TableInfo(n_bins, chrom_offset, dev, row_range or (0, n_bins))
+        # row-aligned chunks of about nnz / n_chunks pixels
+        targets = (np.arange(1, n_chunks) * (nnz / n_chunks)).astype(np.int64)
+        rows = np.unique(np.r_[0, np.searchsorted(off_np, targets, side="left"), n_bins])
+        rows = rows[np.r_[True, np.diff(off_np[rows]) > 0]] if len(rows) > 2 else rows
+        rows[-1] = n_bins
+        main = torch.cuda.current_stream()
+        copy_stream = _copy_stream(dev)
+        indptr_d = off_t.to(dev, non_blocking=True)
+        bin2_d = torch.empty(nnz, dtype=b2_t.dtype, device=dev)
+        count_d = torch.empty(nnz, dtype=_I32, device=dev)
+        copy_stream.wait_stream(main)
+        events = []
+        with torch.cuda.stream(copy_stream):
+            for r0, r1 in zip(rows[:-1], rows[1:]):
+                p0, p1 = int(off_np[r0]), int(off_np[r1])
+                bin2_d[p0:p1].copy_(b2_t[p0:p1], non_blocking=True)
+                count_d[p0:p1].copy_(c_t[p0:p1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append(ev)
+        bin2_d.record_stream(copy_stream)
+        count_d.record_stream(copy_stream)
+
+        self = cls.__new__(cls)
+        self.table, self.group, self.use_smem = info, group, True
+        self.mode = "cis" if cis_only else ("trans" if trans_only else "gw")
+        if peer_reduce is None:
+            peer_reduce = os.environ.get("CB200_PEER_REDUCE", "1") != "0"
+        self.peer_reduce = peer_reduce
+        self.strip_shift, self.band, self.csr, self.csc = None, False, None, None
+        ndiag = int(ignore_diags) if ignore_diags else 0
+        keep = _lib.KEEP_CIS if cis_only else _lib.KEEP_ALL
+        marg = torch.zeros((2, n_bins), dtype=torch.int64, device=dev)
+        subs, nnz_eff = [], 0
+        pack = "cb200_pack_pixels_i32" if b2_t.dtype == _I32 else "cb200_pack_pixels"
+        for ev, r0, r1 in zip(events, rows[:-1], rows[1:]):
+            r0, r1 = int(r0), int(r1)
+            p0, p1 = int(off_np[r0]), int(off_np[r1])
+            if p1 == p0:
+                continue
+            main.wait_event(ev)
+            px = _new_px(p1 - p0, dev)
+            _lib.call(pack, _ptr(bin2_d[p0:p1]), _ptr(count_d[p0:p1]), p1 - p0, _ptr(px), _stream())
+            raw = TableCopy(px, indptr_d[r0:r1 + 1] - p0, p1 - p0, r1 - r0, row_base=r0)
+            csr, tkey, tval = filter_copy(raw, info.row_lo, info.row_hi, ndiag, keep, want_transpose=True)
+            del raw, px
+            csc = transpose_from(tkey, tval, n_bins)
+            del tkey, tval
+            a_nnz, a_sum = marginals_i64(csr)
+            marg[0, r0:r1] += a_nnz
+            marg[1, r0:r1] += a_sum
+            b_nnz, b_sum = marginals_i64(csc)
+            marg[0] += b_nnz
+            marg[1] += b_sum
+            if trans_only:
+                csr, _, _ = filter_copy(csr, info.row_lo, info.row_hi, 0, _lib.KEEP_TRANS)
+                csc, _, _ = filter_copy(csc, info.row_lo, info.row_hi, 0, _lib.KEEP_TRANS)
+            nnz_eff += csr.nnz
+            if csr.nnz:
+                subs += [csr.tight(), csc.tight()]
+        del bin2_d, count_d
+        _allreduce(marg, group)
+        marg = marg.cpu().numpy()
+        self.marg_nnz = marg[0].astype(np.float64)
+        self.marg_sum = marg[1].astype(np.float64)
+        self.subs = subs
+        self._nnz_eff = nnz_eff
+        return self
 
     @property
     def nnz_eff(self):
@@ -506,6 +630,29 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
     return bias, stats
 
 
+def balance_arrays(bin1_offset, bin2_id, count, chrom_offset, *, cis_only=False, trans_only=False,
+                   ignore_diags=2, device="cuda", group=None, row_range=None, return_info=False,
+                   chromnames=None, strip_bins=None, band=None, **kwargs):
+    """Balance a pixel table given as HOST arrays (numpy or torch, ideally pinned):
+    ``bin1_offset`` int64[n_bins+1] (the cooler's indexes/bin1_offset), ``bin2_id`` int64 or int32,
+    ``count`` int32.  The build is pipelined with the host->device copy (IceProblem.from_host);
+    tables that need column strips go through PixelTable + IceProblem.  Other keyword
+    arguments and the return value are those of ``balance_table``."""
+    prob = None
+    if strip_bins is None and band is None:
+        prob = IceProblem.from_host(bin1_offset, bin2_id, count, chrom_offset, cis_only=cis_only,
+                                    trans_only=trans_only, ignore_diags=ignore_diags, group=group,
+                                    device=device, row_range=row_range)
+    if prob is not None:
+        table = prob.table
+    else:
+        table = PixelTable.from_arrays(bin1_offset, bin2_id, count, chrom_offset, device=device,
+                                       row_range=row_range)
+    return balance_table(table, cis_only=cis_only, trans_only=trans_only, ignore_diags=ignore_diags,
+                         group=group, problem=prob, return_info=return_info, chromnames=chromnames,
+                         strip_bins=strip_bins, band=band, **kwargs)
+
+
 def balance_cooler(clr, *, cis_only=False, trans_only=False, ignore_diags=2, mad_max=5, min_nnz=10,
                    min_count=0, blacklist=None, rescale_marginals=True, x0=None, tol=1e-5,
                    max_iters=200, chunksize=10_000_000, map=map, use_lock=False, store=False,
@@ -518,13 +665,14 @@ def balance_cooler(clr, *, cis_only=False, trans_only=False, ignore_diags=2, mad
     read once and stays resident in HBM.  ``clr`` is a ``cooler.Cooler`` or any
     object with the same read protocol (e.g. ``cooler_b200.store.MemCooler``).
     """
-    table = PixelTable.from_cooler(clr, device=device)
+    bin1_offset, bin2, count, chrom_offset = read_cooler_arrays(clr)
     try:
         chromnames = list(clr.chroms()["name"][:])
     except Exception:  # pragma: no cover - duck-typed stores without a chroms selector
         chromnames = None
-    bias, stats = balance_table(
-        table, cis_only=cis_only, trans_only=trans_only, ignore_diags=ignore_diags, mad_max=mad_max,
+    bias, stats = balance_arrays(
+        bin1_offset, bin2, count, chrom_offset, device=device,
+        cis_only=cis_only, trans_only=trans_only, ignore_diags=ignore_diags, mad_max=mad_max,
         min_nnz=min_nnz, min_count=min_count, blacklist=blacklist,
         rescale_marginals=rescale_marginals, x0=x0, tol=tol, max_iters=max_iters,
         chromnames=chromnames)

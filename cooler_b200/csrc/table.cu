@@ -89,7 +89,9 @@ struct KeepRule {
   int ndiag;
   int keep;
   int band_shift;
-  __device__ __forceinline__ bool operator()(int r, int c) const {
+  int row_base;      // bin id of local row 0 (row chunks / shards)
+  __device__ __forceinline__ bool operator()(int r_local, int c) const {
+    const int r = r_local + row_base;
     if (ndiag > 0) {
       int d = r - c;
       if (d < 0) d = -d;
@@ -134,7 +136,8 @@ struct WriteKept {
   int32_t* row_out;
   int32_t* tkey_out;
   int2* tval_out;
-  __device__ __forceinline__ void emit(int64_t o, int r, int c, int v) {
+  __device__ __forceinline__ void emit(int64_t o, int r_local, int c, int v) {
+    const int r = r_local + rule.row_base;         // absolute bin id
     px_out[o] = make_int2(c, v);
     if (row_out) row_out[o] = r;
     if (tkey_out) tkey_out[o] = c;
@@ -282,12 +285,12 @@ int cb200_strip_finish(const int32_t* keys, const cb200_px* vals, int64_t n, int
 
 int cb200_filter_count(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
                        int32_t n_rows, int64_t nnz, const int32_t* row_lo, const int32_t* row_hi,
-                       int32_t ndiag, int32_t keep, int32_t band_shift, int32_t* tile_count,
-                       void* stream) {
+                       int32_t ndiag, int32_t keep, int32_t band_shift, int32_t row_base,
+                       int32_t* tile_count, void* stream) {
   (void)n_rows;
   const int64_t n_tiles = ceil_div64(nnz, WARP_TILE);
   if (n_tiles <= 0) return 0;
-  KeepRule rule{row_lo, row_hi, ndiag, keep, band_shift};
+  KeepRule rule{row_lo, row_hi, ndiag, keep, band_shift, row_base};
   filter_count_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0,
                         (cudaStream_t)stream>>>(reinterpret_cast<const int2*>(px), indptr, tile_row,
                                                 nnz, n_tiles, rule, tile_count);
@@ -297,13 +300,13 @@ int cb200_filter_count(const cb200_px* px, const int64_t* indptr, const int32_t*
 
 int cb200_filter_write(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
                        int32_t n_rows, int64_t nnz, const int32_t* row_lo, const int32_t* row_hi,
-                       int32_t ndiag, int32_t keep, int32_t band_shift, const int64_t* tile_off,
-                       cb200_px* px_out, int32_t* row_out, int32_t* tkey_out, cb200_px* tval_out,
-                       void* stream) {
+                       int32_t ndiag, int32_t keep, int32_t band_shift, int32_t row_base,
+                       const int64_t* tile_off, cb200_px* px_out, int32_t* row_out, int32_t* tkey_out,
+                       cb200_px* tval_out, void* stream) {
   (void)n_rows;
   const int64_t n_tiles = ceil_div64(nnz, WARP_TILE);
   if (n_tiles <= 0) return 0;
-  KeepRule rule{row_lo, row_hi, ndiag, keep, band_shift};
+  KeepRule rule{row_lo, row_hi, ndiag, keep, band_shift, row_base};
   filter_write_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0,
                         (cudaStream_t)stream>>>(
       reinterpret_cast<const int2*>(px), indptr, tile_row, nnz, n_tiles, rule, tile_off,

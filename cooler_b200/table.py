@@ -153,7 +153,7 @@ def filter_copy(copy, row_lo, row_hi, ndiag, keep, *, want_rows=False, want_tran
     tile_count = torch.zeros(max(nt, 1), dtype=_I32, device=dev)
     _lib.call("cb200_filter_count", _ptr(copy.px), _ptr(copy.indptr), _ptr(copy.tile_row),
               copy.n_rows, copy.nnz, _ptr(row_lo), _ptr(row_hi), int(ndiag), int(keep), int(band_shift),
-              _ptr(tile_count), _stream())
+              copy.row_base, _ptr(tile_count), _stream())
     tile_off = exclusive_scan_i32(tile_count[:nt] if nt else tile_count[:0])
     kept = int(tile_off[-1].item())                      # one sync per build step
     px_out = _new_px(kept, dev)
@@ -162,9 +162,9 @@ def filter_copy(copy, row_lo, row_hi, ndiag, keep, *, want_rows=False, want_tran
     tval = _new_px(kept, dev) if want_transpose else None
     _lib.call("cb200_filter_write", _ptr(copy.px), _ptr(copy.indptr), _ptr(copy.tile_row),
               copy.n_rows, copy.nnz, _ptr(row_lo), _ptr(row_hi), int(ndiag), int(keep), int(band_shift),
-              _ptr(tile_off), _ptr(px_out), _ptr(rows), _ptr(tkey), _ptr(tval), _stream())
-    indptr = indptr_from_sorted(rows, kept, copy.n_rows)
-    new = TableCopy(px_out, indptr, kept, copy.n_rows)
+              copy.row_base, _ptr(tile_off), _ptr(px_out), _ptr(rows), _ptr(tkey), _ptr(tval), _stream())
+    indptr = indptr_from_sorted(rows, kept, copy.n_rows, key_base=copy.row_base)
+    new = TableCopy(px_out, indptr, kept, copy.n_rows, row_base=copy.row_base)
     if want_rows:
         new.rows = rows
     return new, (tkey[:kept] if tkey is not None else None), tval
@@ -302,20 +302,26 @@ class PixelTable:
 
     @classmethod
     def from_cooler(cls, clr, device="cuda"):
-        """Read the pixel table of a ``cooler.Cooler``-like object once.
-
-        Protocol used (reference: src/cooler/parallel.py:289-304, _balance.py:141-142):
-        ``clr.open('r')`` -> group with ``pixels/bin2_id``, ``pixels/count``;
-        ``clr._load_dset('indexes/chrom_offset' | 'indexes/bin1_offset')``.
-        """
-        chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
-        bin1_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
-        n_bins = len(bin1_offset) - 1
-        with clr.open("r") as grp:
-            d2 = grp["pixels"]["bin2_id"]
-            if hasattr(d2, "astype") and hasattr(d2, "id") and n_bins < 2**31 - 1:
-                bin2 = d2.astype(np.int32)[:]          # h5py converts while reading: no int64 staging
-            else:
-                bin2 = d2[:]
-            count = grp["pixels"]["count"][:]
+        """Read the pixel table of a ``cooler.Cooler``-like object once (see read_cooler_arrays)."""
+        bin1_offset, bin2, count, chrom_offset = read_cooler_arrays(clr)
         return cls.from_arrays(bin1_offset, bin2, count, chrom_offset, device=device)
+
+
+def read_cooler_arrays(clr):
+    """(bin1_offset, bin2_id, count, chrom_offset) host arrays of a Cooler-like object.
+
+    Protocol used (reference: src/cooler/parallel.py:289-304, _balance.py:141-142):
+    ``clr.open('r')`` -> group with ``pixels/bin2_id``, ``pixels/count``;
+    ``clr._load_dset('indexes/chrom_offset' | 'indexes/bin1_offset')``.  bin1_id is never read.
+    """
+    chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
+    bin1_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
+    n_bins = len(bin1_offset) - 1
+    with clr.open("r") as grp:
+        d2 = grp["pixels"]["bin2_id"]
+        if hasattr(d2, "astype") and hasattr(d2, "id") and n_bins < 2**31 - 1:
+            bin2 = d2.astype(np.int32)[:]              # h5py converts while reading: no int64 staging
+        else:
+            bin2 = d2[:]
+        count = grp["pixels"]["count"][:]
+    return bin1_offset, bin2, count, chrom_offset

@@ -91,7 +91,9 @@ int cb200_strip_finish(const int32_t* keys, const cb200_px* vals, int64_t n, int
  *   && (keep == CB200_KEEP_ALL
  *       || (keep == CB200_KEEP_CIS   &&  row_lo[r] <= c < row_hi[r])   (_zero_trans)
  *       || (keep == CB200_KEEP_TRANS && !(row_lo[r] <= c < row_hi[r])))(_zero_cis)
- * where [row_lo[r], row_hi[r]) is the bin range of r's chromosome. */
+ * where [row_lo[r], row_hi[r]) is the bin range of r's chromosome.  The copy may be a row
+ * chunk: its local row 0 is bin `row_base`; r above, row_lo/row_hi indices and the emitted
+ * row ids are absolute bin ids (local row + row_base). */
 enum { CB200_KEEP_ALL = 0, CB200_KEEP_CIS = 1, CB200_KEEP_TRANS = 2,
        /* layout-only rules (no reference counterpart): split a copy into the band
         * |(c >> band_shift) - (r >> band_shift)| <= 1 around the diagonal and the rest */
@@ -99,14 +101,14 @@ enum { CB200_KEEP_ALL = 0, CB200_KEEP_CIS = 1, CB200_KEEP_TRANS = 2,
 int cb200_filter_count(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
                        int32_t n_rows, int64_t nnz,
                        const int32_t* row_lo, const int32_t* row_hi, int32_t ndiag, int32_t keep,
-                       int32_t band_shift, int32_t* tile_count, void* stream);
+                       int32_t band_shift, int32_t row_base, int32_t* tile_count, void* stream);
 /* Second pass: writes kept pixels, order preserved, at tile_off[t] + rank.
  * Optional outputs (NULL to skip): row_out[q] = row of kept pixel q;
  * tkey_out[q] = other, tval_out[q] = {row, count} (input of the transposition sort). */
 int cb200_filter_write(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
                        int32_t n_rows, int64_t nnz,
                        const int32_t* row_lo, const int32_t* row_hi, int32_t ndiag, int32_t keep,
-                       int32_t band_shift, const int64_t* tile_off,
+                       int32_t band_shift, int32_t row_base, const int64_t* tile_off,
                        cb200_px* px_out, int32_t* row_out, int32_t* tkey_out, cb200_px* tval_out,
                        void* stream);
 

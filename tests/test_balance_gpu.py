@@ -277,3 +277,44 @@ def test_degenerate_tables_match_oracle(case, mode):
     np.testing.assert_allclose(np.atleast_1d(stats["var"]), np.atleast_1d(wstats["var"]), rtol=1e-9, equal_nan=True)
     np.testing.assert_allclose(np.atleast_1d(stats["scale"]), np.atleast_1d(wstats["scale"]), rtol=1e-9, equal_nan=True)
     np.testing.assert_array_equal(np.atleast_1d(stats["converged"]), np.atleast_1d(wstats["converged"]))
+
+
+@pytest.mark.parametrize("key", ["gm/defaults", "gm/cis_only", "gm/trans_only", "gm/diag0", "rnd3/gw",
+                                 "rnd3/cis", "rnd3/trans", "rnd1/cis"])
+def test_streamed_build_matches_reference_golden(key):
+    """balance_arrays: row-chunked build pipelined with the H2D copy (chunk CSR/CSC sub-copies)."""
+    import cooler_b200
+    src, case = key.split("/")
+    t = _golden.table_of(src)
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    kw = dict(META[key]["kwargs"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bias, stats, info = cooler_b200.balance_arrays(bin1_offset, t["bin2_id"], t["count"], chrom_offset,
+                                                       return_info=True, **kw)
+    assert info["n_subcopies"] > 2                        # several row chunks were used
+    want = BAL[key]
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    assert sum(info["passes"]) == sum(META[key]["passes"])
+    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
+    _check_stats(stats, META[key]["stats"], kw.get("cis_only", False))
+
+
+@pytest.mark.parametrize("mode", ["gw", "cis", "trans"])
+def test_streamed_build_large_synthetic_matches_table_path(mode):
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    import torch
+    b1, b2, cnt, chrom_offset = _synthetic(51, [9000, 7000, 3, 5000], 0.02)
+    n = int(chrom_offset[-1])
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    kw = dict(cis_only=(mode == "cis"), trans_only=(mode == "trans"))
+    tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
+    a, sa, ia = cooler_b200.balance_table(tab, return_info=True, **kw)
+    pinned = [torch.from_numpy(x).pin_memory() for x in (bin1_offset, b2, cnt)]
+    for b2_dtype in (torch.int64, torch.int32):
+        b, sb, ib = cooler_b200.balance_arrays(pinned[0], pinned[1].to(b2_dtype).pin_memory(), pinned[2],
+                                               chrom_offset, return_info=True, **kw)
+        assert ib["n_subcopies"] >= 8 and ia["passes"] == ib["passes"] and ib["nnz_eff"] == ia["nnz_eff"]
+        np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+        np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
