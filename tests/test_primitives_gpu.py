@@ -92,3 +92,65 @@ def test_from_arrays_int32_bin2_equals_int64():
     a = T.PixelTable.from_arrays(ind, b2, cnt, chrom_offset)
     b = T.PixelTable.from_arrays(ind, b2.astype(np.int32), cnt, chrom_offset)
     assert torch.equal(a.raw.px[: a.nnz], b.raw.px[: b.nnz])
+
+
+def _rows_to_table(row_lens, n_cols, seed):
+    """Upper-triangle-free synthetic table with prescribed row lengths (columns random, sorted)."""
+    rng = np.random.default_rng(seed)
+    n = len(row_lens)
+    ind = np.r_[0, np.cumsum(row_lens)].astype(np.int64)
+    b1 = np.repeat(np.arange(n, dtype=np.int64), row_lens)
+    b2 = np.empty(ind[-1], dtype=np.int64)
+    for r in np.flatnonzero(row_lens):
+        k = row_lens[r]
+        b2[ind[r]:ind[r + 1]] = np.sort(rng.choice(n_cols, size=k, replace=False)) if k <= n_cols // 2 \
+            else np.sort(rng.permutation(n_cols)[:k])
+    cnt = rng.integers(1, 100, ind[-1]).astype(np.int32)
+    return b1, b2, cnt, ind
+
+
+@pytest.mark.parametrize("name", ["tile_aligned", "ones", "around_chunk", "one_giant", "alternating_empty",
+                                  "span_aligned", "mixed"])
+def test_row_walk_adversarial_shapes(name):
+    """Row lengths chosen to hit every boundary case of the warp-tile walk (rows ending exactly on
+    chunk / tile / span boundaries, single-pixel rows, one row over many tiles, empty rows)."""
+    import ctypes as C
+
+    from cooler_b200 import _lib
+    from cooler_b200 import table as T
+    from cooler_b200.balance import IceProblem, IceState
+    n_cols = 6000
+    shapes = {
+        "tile_aligned": [2048] * 7 + [0, 0] + [4096, 2048, 1, 2047],
+        "ones": [1] * 5000,
+        "around_chunk": [63, 64, 65, 1, 127, 128, 129, 0, 191, 192, 193] * 20,
+        "one_giant": [0] * 10 + [5999] + [0] * 10 + [3] + [0] * 5,
+        "alternating_empty": [0, 700] * 300,
+        "span_aligned": [2048 * 6, 2048 * 6, 5, 2048 * 12 - 5 - 100, 100],
+        "mixed": list(np.random.default_rng(5).integers(0, 3000, 400) * (np.random.default_rng(6).random(400) < 0.6)),
+    }
+    row_lens = np.asarray(shapes[name], dtype=np.int64)
+    if name == "span_aligned":
+        n_cols = 30000
+    row_lens = np.minimum(row_lens, n_cols)
+    n = max(len(row_lens), n_cols)
+    row_lens = np.r_[row_lens, np.zeros(n - len(row_lens), dtype=np.int64)]
+    b1, b2, cnt, ind = _rows_to_table(row_lens, n_cols, 3)
+    chrom_offset = np.array([0, n // 2, n])
+    tab = T.PixelTable.from_arrays(ind, b2, cnt, chrom_offset)
+    # exact integer marginals of the raw copy
+    nnz_m, sum_m = T.marginals_i64(tab.raw)
+    np.testing.assert_array_equal(sum_m.cpu().numpy(), np.bincount(b1, weights=cnt, minlength=n).astype(np.int64))
+    np.testing.assert_array_equal(nnz_m.cpu().numpy(), np.bincount(b1, minlength=n))
+    # one fp64 sweep over both copies with a random bias, whole copies and strips (smem kernel)
+    rng = np.random.default_rng(9)
+    w = rng.lognormal(0, 0.5, n)
+    want = np.bincount(b1, weights=w[b2] * cnt, minlength=n) + np.bincount(b2, weights=w[b1] * cnt, minlength=n)
+    for strip_bins in (0, 2048):
+        prob = IceProblem(tab, ignore_diags=0, strip_bins=strip_bins, band=False if strip_bins else None)
+        state = IceState(prob, w, None, np.array([0, n]), 1e-5, 5)
+        st = C.byref(state.st)
+        _lib.call("cb200_ice_sweep", st, T._stream())
+        _lib.call("cb200_ice_combine", st, T._stream())
+        got = state.t["s"][:n].cpu().numpy()
+        np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-9)
