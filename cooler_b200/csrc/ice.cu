@@ -50,7 +50,7 @@ typedef IceOpT<false> IceOp;
 
 // Tuning knob (cb200_set_tuning): 128-bit stream loads kept in flight per lane.
 static int g_selective = -1;   // -1 = automatic
-static int g_ice_unroll = 0;   // 0 = automatic: 4 for the L1/L2-gather kernel, 2 for the shared-memory strip kernel
+static int g_ice_unroll = 0;   // 0 = automatic: 4 chunks in flight per lane (strip kernel: 768-thread CTAs)
 
 template <int U, bool kSelective>
 __global__ void __launch_bounds__(BLOCK_THREADS)
@@ -88,8 +88,6 @@ struct IceOpSmem {
   }
 };
 
-constexpr int STRIP_THREADS = 1024;
-constexpr int STRIP_WARPS = STRIP_THREADS / 32;
 
 // Work distribution: one persistent CTA per SM.  Every sub-copy has a claim counter.
 // A CTA starts at the sub-copy where an even split of all tiles would put it and
@@ -98,7 +96,7 @@ constexpr int STRIP_WARPS = STRIP_THREADS / 32;
 // the sub-copy is exhausted (no CTA barrier per claim).  Claims only decide WHO
 // computes a tile, never the arithmetic, so results stay bit-reproducible.  The last
 // CTA to finish re-arms the counters.
-template <int U>
+template <int U, int STRIP_THREADS>
 __global__ void __launch_bounds__(STRIP_THREADS, 1)
 ice_sweep_strips_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span,
                         int64_t total_tiles, int smem_bins, const double* __restrict__ w,
@@ -353,26 +351,27 @@ int cb200_ice_sweep(const cb200_ice* st, void* stream) {
         set_error_msg("ice_sweep: strip slice does not fit shared memory");
         return -1;
       }
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_bytes = smem;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_ice_unroll == 1)
-      ice_sweep_strips_kernel<1><<<sms, STRIP_THREADS, smem, (cudaStream_t)stream>>>(
-          st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,
-          reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
-    else if (g_ice_unroll == 4)
-      ice_sweep_strips_kernel<4><<<sms, STRIP_THREADS, smem, (cudaStream_t)stream>>>(
-          st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,
-          reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
-    else
-      ice_sweep_strips_kernel<2><<<sms, STRIP_THREADS, smem, (cudaStream_t)stream>>>(
-          st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,
-          reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
+#define CB_STRIPS(U, T)                                                                      \
+  ice_sweep_strips_kernel<U, T><<<sms, T, smem, (cudaStream_t)stream>>>(                     \
+      st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,                 \
+      reinterpret_cast<unsigned long long*>(st->claim), st->all_done)
+    // default: 24 warps x 4 chunks in flight (80 registers, no spills) beats 32 warps x 2
+    switch (g_ice_unroll) {
+      case 1: CB_STRIPS(1, 1024); break;
+      case 2: CB_STRIPS(2, 1024); break;
+      case 8: CB_STRIPS(4, 512); break;
+      default: CB_STRIPS(4, 768); break;
+    }
+#undef CB_STRIPS
     CB_LAUNCH_CHECK("ice_sweep_strips");
     return 0;
   }

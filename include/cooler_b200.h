@@ -183,7 +183,7 @@ typedef struct {
 } cb200_ice;
 
 /* Tuning of K3 (optional): ice_unroll in {0,1,2,4,8} = 128-bit stream loads kept in
- * flight per lane; 0 (default) = 4 for the L1/L2-gather kernel, 2 for the strip kernel.
+ * flight per lane; 0 (default) = 4 (the strip kernel then runs 768-thread CTAs).
  * selective_l1: -1 automatic, 0/1 = whether gathers far from the diagonal bypass L1
  * allocation in the L1/L2-gather kernel. */
 int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1);
