@@ -91,7 +91,7 @@ class ClockSampler:
         os.unlink(self.f.name)
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": float(max(mx)) if mx else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "window": "warm-up + timed steps, 20 ms period"}
 
 
 def host_arrays_for_cpu(data):
@@ -239,14 +239,17 @@ def main():
         dist.all_reduce(nnz_eff)
     nnz_eff = int(nnz_eff.item())
 
-    for _ in range(args.warmup):
+    # the timed region lasts tens of milliseconds, less than nvidia-smi needs to start: the sampler
+    # runs from before the warm-up steps (same kernels, same load) to the end of the timed steps
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    for _ in range(max(args.warmup, 3)):
         state.reset(bias0)
         state.run()
     passes_per_step = int(state.results()["seg_iters"].max())
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
     state.sweep_events = []
     state.launches = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
