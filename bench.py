@@ -154,7 +154,7 @@ def main():
                     help="dtype of the pinned host bin2_id column of the e2e leg: int64 = the on-disk "
                          "dtype (default); int32 = narrowed by the HDF5 read as PixelTable.from_cooler does")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 0)
+    args.warmup = max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -245,7 +245,7 @@ def main():
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(args.warmup):
         state.reset(bias0)
         state.run()
     passes_per_step = int(state.results()["seg_iters"].max())
