@@ -179,7 +179,7 @@ def main():
             return
         blocks = plan.shard_rows(0, n_gpus)
         data = synth.generate(plan, rows=blocks, pin=False)
-        res = cpu_ice_passes(data, max(args.steps, 1), warmup=min(args.warmup, 1))
+        res = cpu_ice_passes(data, max(args.steps, 1), warmup=args.warmup)
         val = res["value"]
         line = {"impl": "reference", "metric": "ICE pixels/s", "value": val, "unit": "pixels/s",
                 "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
