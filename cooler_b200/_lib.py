@@ -47,7 +47,26 @@ class Ice(C.Structure):
         ("seg_iters", C.c_void_p), ("seg_done", C.c_void_p), ("seg_empty", C.c_void_p),
         ("all_done", C.c_void_p), ("tickets", C.c_void_p), ("var_hist", C.c_void_p),
         ("tol", C.c_double), ("max_iters", C.c_int32),
+        ("n_far_copies", C.c_int32),
+        ("far_copies", C.c_void_p), ("far_units", C.c_void_p), ("far_tiles", C.c_void_p),
+        ("far_parts", C.c_void_p), ("far_claim", C.c_void_p),
+        ("n_far_units", C.c_int32), ("far_col_shift", C.c_int32), ("far_warps", C.c_int32),
     ]
+
+
+class FarCopy(C.Structure):
+    """cb200_far_copy"""
+    _fields_ = [("px", C.c_void_p), ("ptr", C.c_void_p), ("nnz", C.c_int64),
+                ("rb0", C.c_int32), ("n_rb", C.c_int32), ("j0", C.c_int32), ("n_j", C.c_int32),
+                ("rb_unit", C.c_void_p)]
+
+
+class FarUnit(C.Structure):
+    """cb200_far_unit"""
+    _fields_ = [("copy", C.c_int32), ("rb", C.c_int32), ("t0", C.c_int32), ("t1", C.c_int32)]
+
+
+FAR_ROW_SHIFT = 14
 
 
 _P, _I32, _I64, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
@@ -68,10 +87,14 @@ SIGNATURES = {
     "cb200_indptr_from_sorted": (C.c_int, [_P, _I64, _I32, _I32, _I32, _P, _P]),
     "cb200_swap_key_other": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "cb200_strip_finish": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
+    "cb200_far_finish": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "cb200_far_slot_chunks": (C.c_int, [_P, _I64, _P, _P]),
+    "cb200_far_interleave": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P]),
     "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
     "cb200_set_tuning": (C.c_int, [_I32, _I32]),
+    "cb200_set_far_tuning": (C.c_int, [_I32]),
     "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_combine": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_update": (C.c_int, [C.POINTER(Ice), _I32, _I32, _P]),

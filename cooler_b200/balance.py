@@ -19,9 +19,9 @@ import numpy as np
 import torch
 
 from . import _lib
-from .table import (PixelTable, TableCopy, _new_px, _ptr, _stream, _use_device, filter_copy,  # noqa: F401
-                    marginals_i64, n_tiles, read_cooler_arrays, strip_partition, swap_key_other,
-                    transpose_from)
+from .table import (FAR_ROWS, PixelTable, TableCopy, _new_px, _ptr, _stream, _use_device,  # noqa: F401
+                    far_blocks, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays,
+                    strip_partition, swap_key_other, transpose_from)
 
 __all__ = ["balance_cooler", "balance_table", "balance_arrays", "ConvergenceWarning", "IceProblem"]
 
@@ -118,9 +118,13 @@ class IceProblem:
     """
 
     def __init__(self, table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2,
-                 group=None, strip_bins=None, use_smem=True, band=None, peer_reduce=None):
+                 group=None, strip_bins=None, use_smem=True, band=None, peer_reduce=None,
+                 far_col_shift=None, far_warps=None):
         self.table = table
         self.use_smem = use_smem
+        self.far_copies = []
+        self.far_col_shift = int(far_col_shift or os.environ.get("CB200_FAR_COL_SHIFT", 12))
+        self.far_warps = int(far_warps or os.environ.get("CB200_FAR_WARPS", 16))
         if peer_reduce is None:
             peer_reduce = os.environ.get("CB200_PEER_REDUCE", "1") != "0"
         self.peer_reduce = peer_reduce
@@ -152,7 +156,17 @@ class IceProblem:
         # layout of the sweep: whole copies, column strips, or diagonal band strips + far rest
         self.strip_shift, self.band = choose_layout(n_bins, csr.nnz, strip_bins, band)
         sh = self.strip_shift
-        if sh is None:
+        if band == "allblocks":                   # every pixel through the 2-D blocked kernel (csrc/far.cuh)
+            self.band, self.strip_shift = "allblocks", None
+            if cval is None:
+                ckeys, cval = swap_key_other(ckeys, csc.px, csc.nnz)
+            n1, n2 = csr.nnz, csc.nnz
+            self.csr = self.csc = csr = csc = None
+            self.far_copies = [far_blocks(tkey[:n1], tval, n1, n_bins, self.far_col_shift, self.far_warps)]
+            tkey = tval = None
+            self.far_copies.append(far_blocks(ckeys[:n2], cval, n2, n_bins, self.far_col_shift, self.far_warps))
+            self.subs = []
+        elif sh is None:
             self.subs = [csr.tight(), csc.tight()]
             self.csr, self.csc = csr, csc
         elif not self.band:
@@ -171,10 +185,17 @@ class IceProblem:
                                                want_transpose=True, band_shift=sh)
                 subs += strip_partition(nkey[: near.nnz], nval, near.nnz, n_bins, sh)
                 del near, nkey, nval
-                far, _, _ = filter_copy(copy, table.row_lo, table.row_hi, 0, _lib.KEEP_BAND_FAR,
-                                        band_shift=sh)
-                if far.nnz:
+                blocks = self.band == "blocks"
+                far, fkey, fval = filter_copy(copy, table.row_lo, table.row_hi, 0, _lib.KEEP_BAND_FAR,
+                                              want_transpose=blocks, band_shift=sh)
+                if far.nnz and blocks:            # far field in (row block, column tile) order: csrc/far.cuh
+                    nfar = far.nnz
+                    del far
+                    self.far_copies.append(far_blocks(fkey, fval, nfar, n_bins, self.far_col_shift,
+                                                      self.far_warps))
+                elif far.nnz:                     # far field as one row-ordered copy gathered through L2
                     subs.append(far.tight())
+                del fkey, fval
             self.subs = subs
             self.csr = self.csc = None
         tkey = tval = ckeys = cval = None
@@ -243,6 +264,7 @@ class IceProblem:
             peer_reduce = os.environ.get("CB200_PEER_REDUCE", "1") != "0"
         self.peer_reduce = peer_reduce
         self.strip_shift, self.band, self.csr, self.csc = None, False, None, None
+        self.far_copies, self.far_col_shift, self.far_warps = [], 12, 16
         ndiag = int(ignore_diags) if ignore_diags else 0
         keep = _lib.KEEP_CIS if cis_only else _lib.KEEP_ALL
         marg = torch.zeros((2, n_bins), dtype=torch.int64, device=dev)
@@ -327,7 +349,7 @@ def choose_layout(n_bins, nnz_eff, strip_bins=None, band=None):
             # whole copies but cost two more filter passes at build time -> not the default
             return None, False
         band = sparse
-    return shift, bool(band)
+    return shift, (band if band in ("blocks", "allblocks") else bool(band))
 
 
 class IceState:
@@ -396,6 +418,27 @@ class IceState:
         t["subs"] = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
         t["claim"] = torch.zeros(len(subs) + 1, dtype=torch.int64, device=dev)
         t["s"], t["marg"] = f64(n), f64(n)
+        # far-field blocks: units of about equal size, a few per SM (csrc/far.cuh)
+        far = [f for f in getattr(prob, "far_copies", []) if f is not None]
+        n_far_units = 0
+        if far:
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            per_sm = int(os.environ.get("CB200_FAR_UNITS_PER_SM", 4))
+            target = max(sum(f.nnz for f in far) // (sms * per_sm), 4096)
+            units, tiles, rb_units = plan_far_units([(f.rb0, f.j0, f.tile_counts) for f in far], target)
+            n_far_units = len(units)
+            t["far_units"] = torch.from_numpy(np.ascontiguousarray(units)).to(dev)
+            t["far_tiles"] = torch.from_numpy(np.ascontiguousarray(tiles)).to(dev)
+            t["far_rb_unit"] = [torch.from_numpy(r).to(dev) for r in rb_units]
+            farr = (_lib.FarCopy * len(far))()
+            for k, f in enumerate(far):
+                farr[k].px, farr[k].ptr, farr[k].nnz = f.px.data_ptr(), f.ptr.data_ptr(), f.nnz
+                farr[k].rb0, farr[k].n_rb, farr[k].j0, farr[k].n_j = f.rb0, f.n_rb, f.j0, f.n_j
+                farr[k].rb_unit = t["far_rb_unit"][k].data_ptr()
+            t["far_copies"] = torch.frombuffer(bytearray(bytes(farr)), dtype=torch.uint8).to(dev)
+            t["far_parts"] = torch.empty(max(n_far_units, 1) * FAR_ROWS, dtype=_F64, device=dev)
+            t["far_claim"] = torch.zeros(2, dtype=torch.int64, device=dev)
+        self.n_far_units = n_far_units
         # multi-GPU: local s vectors live in peer-mapped symmetric memory (double-buffered) and
         # K4a sums them over NVLink; falls back to an NCCL all-reduce if that is unavailable
         self.peer = None
@@ -421,6 +464,11 @@ class IceState:
                   "seg_empty", "all_done", "tickets", "var_hist"):
             setattr(st, k, t[k].data_ptr() if t[k] is not None else None)
         st.tol, st.max_iters = float(tol), self.max_iters
+        st.n_far_units, st.n_far_copies = n_far_units, len(far)
+        if far:
+            for k in ("far_copies", "far_units", "far_tiles", "far_parts", "far_claim"):
+                setattr(st, k, t[k].data_ptr())
+            st.far_col_shift, st.far_warps = far[0].col_shift, far[0].warps
         self.st = st
         self.prob = prob
         self.flag_host = torch.zeros(1, dtype=_I32).pin_memory() if torch.cuda.is_available() else None
@@ -454,7 +502,7 @@ class IceState:
             _lib.call("cb200_ice_sweep", st, stream)
         if self.prob.group is None:                   # single GPU: combine fused into K4a
             _lib.call("cb200_ice_update", st, int(it), 1, stream)
-            self.launches += 3
+            self.launches += 3 + (1 if self.n_far_units else 0)
         elif self.peer is not None:                   # multi-GPU, all-reduce fused into K4a over NVLink
             half = self.peer.tick & 1             # keeps alternating across runs and calls
             self.peer.tick += 1
@@ -470,7 +518,7 @@ class IceState:
                 self.comm_events.append((c0, c1))
             _lib.call("cb200_ice_update_peer", C.byref(self.st), int(it), _ptr(self.peer.ptrs),
                       self.peer.world, half * self.peer.stride, stream)
-            self.launches += 4
+            self.launches += 4 + (1 if self.n_far_units else 0)
         else:
             _lib.call("cb200_ice_combine", st, stream)
             if self.sweep_events is not None:
@@ -482,7 +530,7 @@ class IceState:
             else:
                 _allreduce(self.t["s"], self.prob.group)
             _lib.call("cb200_ice_update", st, int(it), 0, stream)
-            self.launches += 4
+            self.launches += 4 + (1 if self.n_far_units else 0)
 
     def run(self, check_every=8):
         """Iterate until every segment converged or max_iters.  Returns passes launched."""
@@ -543,7 +591,7 @@ def prefilter_bias(prob: IceProblem, chrom_offset, *, mad_max, min_nnz, min_coun
 def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2, mad_max=5,
                   min_nnz=10, min_count=0, blacklist=None, rescale_marginals=True, x0=None,
                   tol=1e-5, max_iters=200, group=None, problem=None, chromnames=None,
-                  return_info=False, strip_bins=None, band=None):
+                  return_info=False, strip_bins=None, band=None, far_col_shift=None, far_warps=None):
     """Balance a device-resident table.  Same semantics as ``balance_cooler``.
 
     ``problem`` lets callers reuse the filtered copies (bench: inputs resident
@@ -555,7 +603,8 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
     n_bins = table.n_bins
     n_chroms = len(chrom_offset) - 1
     prob = problem or IceProblem(table, cis_only=cis_only, trans_only=trans_only,
-                                 ignore_diags=ignore_diags, group=group, strip_bins=strip_bins, band=band)
+                                 ignore_diags=ignore_diags, group=group, strip_bins=strip_bins, band=band,
+                                 far_col_shift=far_col_shift, far_warps=far_warps)
     bias = prefilter_bias(prob, chrom_offset, mad_max=mad_max, min_nnz=min_nnz, min_count=min_count,
                           blacklist=blacklist, x0=x0)
 
@@ -625,7 +674,9 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
         info = {"passes": res["seg_iters"].tolist(), "launched_passes": passes,
                 "nnz_eff": prob.nnz_eff, "bytes_per_pass": prob.bytes_per_pass(),
                 "hit_limit": hit_limit, "gpu_launches": state.launches,
-                "n_subcopies": len(prob.subs), "strip_shift": prob.strip_shift, "band": prob.band}
+                "n_subcopies": len(prob.subs), "strip_shift": prob.strip_shift, "band": prob.band,
+                "far_units": state.n_far_units,
+                "far_pixels": sum(f.nnz for f in getattr(prob, "far_copies", []) if f is not None)}
         return bias, stats, info
     return bias, stats
 

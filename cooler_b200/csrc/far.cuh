@@ -1,0 +1,234 @@
+// K3 for far-field blocks (see cb200_far_copy in include/cooler_b200.h).
+//
+// Very large, very sparse matrices (1 kb human Hi-C: 3.1e6 bins, ~1e3 pixels per row spread
+// over the whole genome) defeat both forms of the row-walking sweep: gathers of w[other]
+// through L1/L2 cost one 32-byte L2 sector per 8-byte pixel (L2-bound at ~0.5 of the HBM
+// rate), and column strips need one partial sum per (row, strip) although such a segment
+// holds 1-2 pixels.  Here the far pixels are blocked in BOTH dimensions: a persistent CTA owns
+// 16384 rows whose sums stay in shared memory while it walks along the column tiles of that
+// row block, staging the C-wide slice of w of the next tile with cp.async while the current
+// one is consumed.  Records carry block-local (row, column) ids, so there is no row pointer
+// per (row, tile).
+//
+// Warp k owns rows [k, k+1) * 16384 / WARPS of the block; the records of one (tile, warp
+// slice) = "slot" are sorted by row and cut into 32 equal contiguous pieces, one per lane,
+// stored lane-interleaved so that every warp load is one coalesced 512-byte chunk.  A lane
+// walks through its piece sequentially: it sums a run of equal rows in a register and adds
+// the run total to the row's accumulator when the row changes.  Only the LAST run of a lane
+// can continue in the next lane; it is left open and merged once per slot by a warp-level
+// segmented scan over the 32 lanes.  A run that ends inside a lane's piece ends nowhere
+// else, so every accumulator is updated by exactly one lane per phase (pieces, then the
+// merge, separated by __syncwarp): no atomics, fixed summation order,
+// bit-reproducible.  Padding records (row id 16384 = a dummy accumulator) fill the last chunk
+// of a slot.
+#pragma once
+#include "walk.cuh"
+#include "../../include/cooler_b200.h"
+
+namespace cb200 {
+
+constexpr int FAR_ROWS = 1 << CB200_FAR_ROW_SHIFT;
+constexpr unsigned FAR_NOKEY = FAR_ROWS;           // row id of padding records: a dummy accumulator slot
+constexpr int FAR_PAD_X = (int)(FAR_NOKEY << 16);  // first word of a padding record
+constexpr int FAR_ACC = FAR_ROWS + 8;              // accumulators incl. the dummy slot (keeps 64-byte alignment)
+
+__device__ __forceinline__ double far_i32_to_f64(int v) {      // exact, see i32_to_f64 in ice.cu
+  return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;
+}
+
+__device__ __forceinline__ void cp_async_f64(unsigned smem_dst, const double* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// shared-memory accesses by 32-bit shared-space address (keeps address arithmetic to one shift/add)
+__device__ __forceinline__ double lds_f64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+
+// Bank swizzle of the block-local row id stored in the records (applied by cb200_far_finish):
+// a lane's piece covers about RW/32 consecutive rows of the warp's slice of RW rows, lane l
+// roughly rows [l, l+1) * RW/32.  Row lr of the slice is kept at accumulator
+// (lr % (RW/32)) * 32 + lr / (RW/32), so lanes that are in step hit 32 different words and
+// the run-end updates are (nearly) free of shared-memory bank conflicts.
+__host__ __device__ inline int far_swizzle(int lrow, int warps) {
+  const int rw = FAR_ROWS / warps, g = rw / 32;
+  const int lr = lrow & (rw - 1);
+  return (lrow - lr) + ((lr & (g - 1)) << 5) + lr / g;
+}
+
+// One record of a lane's piece: (k, v) = (block-local row, w[col] * count).  `key`/`val` hold
+// the run being summed.  When the row changes the finished run is added to its accumulator;
+// the initial state and padding records use row id FAR_ROWS, whose accumulator is a dummy
+// slot behind the real ones, so the update needs no special cases.
+__device__ __forceinline__ void far_add(unsigned& key, double& val, const unsigned k, const double v,
+                                        const unsigned acc_s) {
+  const bool changed = (k != key);
+  if (changed) {
+    const unsigned a = acc_s + (key << 3);
+    sts_f64(a, lds_f64(a) + val);
+  }
+  val = changed ? v : val + v;
+  key = k;
+}
+
+template <int U>
+__device__ __forceinline__ void far_first_group(const int4* __restrict__ px4, const int64_t c0,
+                                                const int64_t c1, int4 (&qn)[U], const int lane) {
+  const int4* __restrict__ src = px4 + c0 * 32 + lane;
+  const int nch = (int)(c1 - c0);
+#pragma unroll
+  for (int u = 0; u < U; ++u)
+    qn[u] = (u < nch) ? ld_stream_int4(src + u * 32) : make_int4(FAR_PAD_X, 0, FAR_PAD_X, 0);
+}
+
+// Chunks [c0, c1) of one slot; qn holds the first group (already in flight).
+template <int U>
+__device__ __forceinline__ void far_slot(const int4* __restrict__ px4, const int64_t c0, const int64_t c1,
+                                         int4 (&qn)[U], const unsigned ws_s, const unsigned acc_s,
+                                         const int lane) {
+  constexpr unsigned F = 0xffffffffu;
+  const int nch = (int)(c1 - c0);
+  if (nch <= 0) return;                            // warp-uniform
+  const int4* __restrict__ src = px4 + c0 * 32 + lane;
+  unsigned key = FAR_NOKEY;
+  double val = 0.0;
+  for (int c = 0; c < nch; c += U) {
+    int4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = qn[u];
+    const int cn = c + U;
+    if (cn < nch) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        qn[u] = (cn + u < nch) ? ld_stream_int4(src + (cn + u) * 32) : make_int4(FAR_PAD_X, 0, FAR_PAD_X, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      // Never walk into a chunk past the end: its padding would make EVERY lane close its
+      // last run at the same instruction, and adjacent lanes may share that run.
+      if (c + u >= nch) break;                     // warp-uniform
+      const double g0 = lds_f64(ws_s + (((unsigned)q[u].x & 0xFFFFu) << 3));
+      const double g1 = lds_f64(ws_s + (((unsigned)q[u].z & 0xFFFFu) << 3));
+      far_add(key, val, (unsigned)q[u].x >> 16, g0 * far_i32_to_f64(q[u].y), acc_s);
+      far_add(key, val, (unsigned)q[u].z >> 16, g1 * far_i32_to_f64(q[u].w), acc_s);
+    }
+  }
+  // The LAST run of every lane is still open and may continue in the next lanes (whose first
+  // run was added above, or is their last run too): merge equal adjacent keys with a
+  // segmented scan over the lanes and let the last lane of each run add the total.
+  __syncwarp();
+  const unsigned pk = __shfl_up_sync(F, key, 1);
+  const unsigned nk = __shfl_down_sync(F, key, 1);
+  const bool head = (lane == 0) || (pk != key);
+  const unsigned heads = __ballot_sync(F, head);
+  const int h = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+  const int span = (key != FAR_NOKEY) ? lane - h : 0;
+  const int ms = __reduce_max_sync(F, span);
+  double x = val;
+  for (int d = 1; d <= ms; d <<= 1) {
+    const double y = __shfl_up_sync(F, x, d);
+    if (lane - d >= h) x += y;
+  }
+  if (key != FAR_NOKEY && (lane == 31 || nk != key)) {
+    const unsigned a = acc_s + (key << 3);
+    sts_f64(a, lds_f64(a) + x);
+  }
+  __syncwarp();
+}
+
+template <int WARPS, int U>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+ice_sweep_far_kernel(const cb200_ice st) {
+  extern __shared__ double far_sm[];               // acc[FAR_ACC] | w tile [2][C]
+  __shared__ int s_unit;
+  if (*st.all_done) return;
+  constexpr int RW = FAR_ROWS / WARPS;             // rows per warp slice
+  constexpr int THREADS = WARPS * 32;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int cs = st.far_col_shift, C = 1 << cs;
+  double* __restrict__ acc = far_sm;
+  const unsigned acc_s = (unsigned)__cvta_generic_to_shared(far_sm);
+  const unsigned wb_s = acc_s + FAR_ACC * 8;
+  unsigned long long* claim = reinterpret_cast<unsigned long long*>(st.far_claim);
+
+  auto stage = [&](unsigned dst_s, int j) {        // cp.async the slice of w of column tile j
+    const int64_t base = (int64_t)j << cs;
+    for (int i = threadIdx.x; i < C; i += THREADS)
+      if (base + i < st.n_bins) cp_async_f64(dst_s + i * 8, st.w + base + i);
+    cp_async_commit();
+  };
+
+  while (true) {
+    __syncthreads();                               // the previous unit is finished by every warp
+    if (threadIdx.x == 0) s_unit = (int)atomicAdd(claim, 1ULL);
+    __syncthreads();
+    const int u = s_unit;
+    if (u >= st.n_far_units) break;                // CTA-uniform
+    const cb200_far_unit un = st.far_units[u];
+    const cb200_far_copy fc = st.far_copies[un.copy];
+    for (int i = lane; i < RW; i += 32) acc[wid * RW + i] = 0.0;
+    // slot (j, wid) of this row block: chunks tp[j * WARPS] .. tp[j * WARPS + 1]
+    const int64_t* __restrict__ tp = fc.ptr + ((int64_t)(un.rb - fc.rb0) * fc.n_j - fc.j0) * WARPS + wid;
+    const int4* __restrict__ px4 = reinterpret_cast<const int4*>(fc.px);
+    const int j_first = st.far_tiles[un.t0];
+    int jn = (un.t0 + 1 < un.t1) ? st.far_tiles[un.t0 + 1] : -1;
+    stage(wb_s, j_first);
+    int64_t a = tp[(int64_t)j_first * WARPS], b = tp[(int64_t)j_first * WARPS + 1];
+    int4 qn[U];
+    far_first_group<U>(px4, a, b, qn, lane);
+    cp_async_wait_all();
+    __syncthreads();                               // tile 0 staged; accumulators zeroed
+    int buf = 0;
+    for (int t = un.t0; t < un.t1; ++t) {
+      const int jnn = (t + 2 < un.t1) ? st.far_tiles[t + 2] : -1;     // in flight during this tile
+      int64_t a2 = 0, b2 = 0;
+      if (jn >= 0) {
+        stage(wb_s + (unsigned)((buf ^ 1) * C * 8), jn);
+        a2 = tp[(int64_t)jn * WARPS];
+        b2 = tp[(int64_t)jn * WARPS + 1];
+      }
+      far_slot<U>(px4, a, b, qn, wb_s + (unsigned)(buf * C * 8), acc_s, lane);
+      if (jn >= 0) far_first_group<U>(px4, a2, b2, qn, lane);
+      cp_async_wait_all();
+      __syncthreads();                             // next tile staged, this one released
+      buf ^= 1;
+      a = a2;
+      b = b2;
+      jn = jnn;
+    }
+    double* __restrict__ part = st.far_parts + (int64_t)u * FAR_ROWS + wid * RW;
+    for (int i = lane; i < RW; i += 32)            // undo the bank swizzle of the row ids (see far_swizzle)
+      part[i] = acc[wid * RW + ((i & (RW / 32 - 1)) << 5) + i / (RW / 32)];
+  }
+  // re-arm the claim counter once every CTA is through
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long ticket = atomicAdd(&claim[1], 1ULL);
+    if (ticket == gridDim.x - 1) {
+      claim[0] = 0ULL;
+      claim[1] = 0ULL;
+      __threadfence();
+    }
+  }
+}
+
+// Far-field part of s[i]: the units of i's row block, in unit order.
+__device__ __forceinline__ double far_row_total(const cb200_ice& st, int i) {
+  double v = 0.0;
+  const int rb = i >> CB200_FAR_ROW_SHIFT, lr = i & (FAR_ROWS - 1);
+  for (int c = 0; c < st.n_far_copies; ++c) {
+    const cb200_far_copy& fc = st.far_copies[c];
+    const unsigned k = (unsigned)(rb - fc.rb0);
+    if (k < (unsigned)fc.n_rb)
+      for (int u = fc.rb_unit[k]; u < fc.rb_unit[k + 1]; ++u) v += st.far_parts[(int64_t)u * FAR_ROWS + lr];
+  }
+  return v;
+}
+
+}  // namespace cb200

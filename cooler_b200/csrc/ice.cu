@@ -8,6 +8,7 @@
 // deterministic segmented reductions (rows of the bin1-major copy + rows of the
 // bin2-major copy), float64, no atomics.
 #include "walk.cuh"
+#include "far.cuh"
 #include "../../include/cooler_b200.h"
 
 namespace cb200 {
@@ -50,6 +51,7 @@ typedef IceOpT<false> IceOp;
 
 // Tuning knob (cb200_set_tuning): 128-bit stream loads kept in flight per lane.
 static int g_selective = -1;   // -1 = automatic
+static int g_far_unroll = 0;   // far-field kernel: 0 = automatic
 static int g_ice_unroll = 0;   // 0 = automatic: 4 chunks in flight per lane (strip kernel: 768-thread CTAs)
 
 template <int U, bool kSelective>
@@ -163,19 +165,19 @@ ice_sweep_strips_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span
   }
 }
 
-// s[i] = sum over sub-copies (fixed order) of the row total of bin i.
-__global__ void ice_combine_kernel(const cb200_sub* __restrict__ subs, int n_subs, int n_bins,
-                                   double* __restrict__ s, const int32_t* __restrict__ all_done) {
-  if (*all_done) return;
+// s[i] = sum over sub-copies (fixed order) of the row total of bin i, plus the far-field units.
+__global__ void ice_combine_kernel(const cb200_ice st) {
+  if (*st.all_done) return;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_bins) return;
+  if (i >= st.n_bins) return;
   double v = 0.0;
-  for (int k = 0; k < n_subs; ++k) {
-    const unsigned r = (unsigned)(i - subs[k].row_base);
-    if (r < (unsigned)subs[k].row_count)
-      v += row_total<double>((int)r, subs[k].indptr, subs[k].nnz, subs[k].direct, subs[k].pieces);
+  for (int k = 0; k < st.n_subs; ++k) {
+    const unsigned r = (unsigned)(i - st.subs[k].row_base);
+    if (r < (unsigned)st.subs[k].row_count)
+      v += row_total<double>((int)r, st.subs[k].indptr, st.subs[k].nnz, st.subs[k].direct, st.subs[k].pieces);
   }
-  s[i] = v;
+  if (st.n_far_units > 0) v += far_row_total(st, i);
+  st.s[i] = v;
 }
 
 constexpr int UPD_THREADS = 256;
@@ -239,6 +241,7 @@ ice_marg_kernel(cb200_ice st, const double* const* __restrict__ peer_s, int worl
             si += row_total<double>((int)r, st.subs[k].indptr, st.subs[k].nnz, st.subs[k].direct,
                                     st.subs[k].pieces);
         }
+        if (st.n_far_units > 0) si += far_row_total(st, i);
       } else {
         si = st.s[i];
       }
@@ -341,7 +344,58 @@ int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1) {
   return 0;
 }
 
+int cb200_set_far_tuning(int32_t far_unroll) {
+  if (far_unroll != 0 && far_unroll != 1 && far_unroll != 2 && far_unroll != 4 && far_unroll != 8) return -1;
+  g_far_unroll = far_unroll;
+  return 0;
+}
+
+// K3 over the far-field blocks (far.cuh): one persistent CTA per SM claims units.
+static int ice_sweep_far(const cb200_ice* st, void* stream) {
+  if (st->n_far_units <= 0) return 0;
+  if (st->far_col_shift < 1 || st->far_col_shift > 12 || (st->far_warps != 16 && st->far_warps != 32)) {
+    set_error_msg("ice_sweep: far_col_shift must be in 1..12 and far_warps 16 or 32");
+    return -1;
+  }
+  const size_t smem = ((size_t)FAR_ACC + 2 * ((size_t)1 << st->far_col_shift)) * sizeof(double);
+  static bool attr_done = false;
+  if (!attr_done) {
+    const int mx = (int)(((size_t)FAR_ACC + 2 * 4096) * sizeof(double));
+    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = st->n_far_units < sms ? st->n_far_units : sms;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (st->far_warps == 16) {
+    if (g_far_unroll == 2) ice_sweep_far_kernel<16, 2><<<grid, 512, smem, s>>>(*st);
+    else if (g_far_unroll == 8) ice_sweep_far_kernel<16, 8><<<grid, 512, smem, s>>>(*st);
+    else ice_sweep_far_kernel<16, 4><<<grid, 512, smem, s>>>(*st);
+  } else {
+    if (g_far_unroll == 1) ice_sweep_far_kernel<32, 1><<<grid, 1024, smem, s>>>(*st);
+    else if (g_far_unroll == 4) ice_sweep_far_kernel<32, 4><<<grid, 1024, smem, s>>>(*st);
+    else ice_sweep_far_kernel<32, 2><<<grid, 1024, smem, s>>>(*st);
+  }
+  CB_LAUNCH_CHECK("ice_sweep_far");
+  return 0;
+}
+
+static int ice_sweep_near(const cb200_ice* st, void* stream);
+
 int cb200_ice_sweep(const cb200_ice* st, void* stream) {
+  const int rc = ice_sweep_near(st, stream);
+  if (rc != 0) return rc;
+  return ice_sweep_far(st, stream);
+}
+
+static int ice_sweep_near(const cb200_ice* st, void* stream) {
   if (st->total_warps <= 0 || st->n_subs <= 0) return 0;
   if (st->smem_bins > 0) {                          // column strips: persistent shared-memory kernel
     const size_t smem = (size_t)st->smem_bins * sizeof(double);
@@ -400,8 +454,7 @@ int cb200_ice_sweep(const cb200_ice* st, void* stream) {
 
 int cb200_ice_combine(const cb200_ice* st, void* stream) {
   if (st->n_bins <= 0) return 0;
-  ice_combine_kernel<<<(unsigned)ceil_div64(st->n_bins, 256), 256, 0, (cudaStream_t)stream>>>(
-      st->subs, st->n_subs, st->n_bins, st->s, st->all_done);
+  ice_combine_kernel<<<(unsigned)ceil_div64(st->n_bins, 256), 256, 0, (cudaStream_t)stream>>>(*st);
   CB_LAUNCH_CHECK("ice_combine");
   return 0;
 }

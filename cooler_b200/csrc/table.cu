@@ -2,6 +2,7 @@
 // ids, static filters by stable compaction, integer (prefilter) marginals.
 #include <cstdio>
 #include "walk.cuh"
+#include "far.cuh"
 #include "../../include/cooler_b200.h"
 
 namespace cb200 {
@@ -79,6 +80,61 @@ __global__ void strip_finish_kernel(const int32_t* __restrict__ keys, const int2
     const int64_t o = i + pad_before[s];
     px_out[o] = make_int2(k, v.y);
     rows_out[o] = v.x;
+  }
+}
+
+// Far-field blocks: see cb200_far_copy in the header.  The input is sorted by
+// (row >> 14, other >> col_shift, row, other); every element becomes an 8-byte record with
+// block-local coordinates plus its slot id (row block, column tile, warp row slice).
+__global__ void far_finish_kernel(const int32_t* __restrict__ rows, const int2* __restrict__ vals,
+                                  int64_t n, int col_shift, int rb0, int j0, int n_j, int warps,
+                                  int2* __restrict__ px_out, int32_t* __restrict__ slot_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int cmask = (1 << col_shift) - 1;
+  constexpr int RS = CB200_FAR_ROW_SHIFT;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int r = rows[i];
+    const int2 v = vals[i];
+    const int lrow = r & ((1 << RS) - 1);
+    px_out[i] = make_int2((far_swizzle(lrow, warps) << 16) | (v.x & cmask), v.y);
+    slot_out[i] = (((r >> RS) - rb0) * n_j + ((v.x >> col_shift) - j0)) * warps + ((lrow * warps) >> RS);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {       // defined pad records (never used: guarded by range checks)
+    px_out[n] = make_int2(0, 0);
+    px_out[n + 1] = make_int2(0, 0);
+  }
+}
+
+// Slot s holds records [ptr_rec[s], ptr_rec[s+1]) of the sorted stream; it becomes
+// nch[s] = ceil(len / CHUNK) lane-interleaved chunks.
+__global__ void far_slot_chunks_kernel(const int64_t* __restrict__ ptr_rec, int64_t n_slots,
+                                       int32_t* __restrict__ nch) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; s < n_slots; s += stride)
+    nch[s] = (int32_t)((ptr_rec[s + 1] - ptr_rec[s] + CHUNK - 1) / CHUNK);
+}
+
+__global__ void far_fill_kernel(int2* __restrict__ px_out, int64_t n_total) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += stride)
+    px_out[i] = make_int2((int)((1u << CB200_FAR_ROW_SHIFT) << 16), 0);   // padding record: row id 16384 (dummy), count 0
+}
+
+// Record i of slot s (j-th of the slot) goes to lane j / L, position j % L of that lane's
+// piece, L = 2 * nch(s) records per lane; lane pieces are interleaved in units of one int4
+// (2 records): chunk c of the slot holds records 2c, 2c+1 of every lane.
+__global__ void far_interleave_kernel(const int2* __restrict__ rec, const int32_t* __restrict__ slot,
+                                      const int64_t* __restrict__ ptr_rec,
+                                      const int64_t* __restrict__ cptr, int64_t n,
+                                      int2* __restrict__ px_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int s = slot[i];
+    const int j = (int)(i - ptr_rec[s]);
+    const int64_t c0 = cptr[s];
+    const int L = 2 * (int)(cptr[s + 1] - c0);
+    const int lane = j / L, idx = j - lane * L;
+    px_out[(c0 + (idx >> 1)) * CHUNK + 2 * lane + (idx & 1)] = rec[i];
   }
 }
 
@@ -209,7 +265,7 @@ using namespace cb200;
 
 extern "C" {
 
-int cb200_abi_version(void) { return 1; }
+int cb200_abi_version(void) { return 2; }
 const char* cb200_last_error(void) { return g_err; }
 int cb200_set_device(int device) {
   CB_CHECK(cudaSetDevice(device));
@@ -280,6 +336,48 @@ int cb200_strip_finish(const int32_t* keys, const cb200_px* vals, int64_t n, int
       keys, reinterpret_cast<const int2*>(vals), n, shift, pad_before,
       reinterpret_cast<int2*>(px_out), rows_out);
   CB_LAUNCH_CHECK("strip_finish");
+  return 0;
+}
+
+int cb200_far_finish(const int32_t* rows, const cb200_px* vals, int64_t n, int32_t col_shift,
+                     int32_t rb0, int32_t j0, int32_t n_j, int32_t warps, cb200_px* px_out,
+                     int32_t* slot_out, void* stream) {
+  if (col_shift < 1 || col_shift > 16 || (warps != 16 && warps != 32) || n_j <= 0) {
+    set_error_msg("far_finish: bad arguments");
+    return -1;
+  }
+  int64_t blocks = ceil_div64(n > 0 ? n : 1, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  far_finish_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      rows, reinterpret_cast<const int2*>(vals), n, col_shift, rb0, j0, n_j, warps,
+      reinterpret_cast<int2*>(px_out), slot_out);
+  CB_LAUNCH_CHECK("far_finish");
+  return 0;
+}
+
+int cb200_far_slot_chunks(const int64_t* ptr_rec, int64_t n_slots, int32_t* nch_out, void* stream) {
+  if (n_slots <= 0) return 0;
+  int64_t blocks = ceil_div64(n_slots, 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  far_slot_chunks_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(ptr_rec, n_slots, nch_out);
+  CB_LAUNCH_CHECK("far_slot_chunks");
+  return 0;
+}
+
+int cb200_far_interleave(const cb200_px* rec, const int32_t* slot, const int64_t* ptr_rec,
+                         const int64_t* chunk_ptr, int64_t n, int64_t total_chunks, cb200_px* px_out,
+                         void* stream) {
+  const int64_t n_total = total_chunks * CHUNK + 2;
+  int64_t blocks = ceil_div64(n_total, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  far_fill_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<int2*>(px_out), n_total);
+  CB_LAUNCH_CHECK("far_fill");
+  if (n <= 0) return 0;
+  blocks = ceil_div64(n, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  far_interleave_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const int2*>(rec), slot, ptr_rec, chunk_ptr, n, reinterpret_cast<int2*>(px_out));
+  CB_LAUNCH_CHECK("far_interleave");
   return 0;
 }
 

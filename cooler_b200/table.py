@@ -225,6 +225,101 @@ def strip_partition(key_other, val_rowcount, n, n_rows, shift):
     return subs
 
 
+FAR_ROW_SHIFT = _lib.FAR_ROW_SHIFT      # rows per far-field block = 1 << 14 (csrc/far.cuh)
+FAR_ROWS = 1 << FAR_ROW_SHIFT
+
+
+class FarCopy:
+    """Far-field pixels of one copy in block order (cb200_far_copy in the header)."""
+
+    def __init__(self, px, ptr, nnz, rb0, n_rb, j0, n_j, col_shift, warps, tile_counts):
+        self.px, self.ptr, self.nnz = px, ptr, int(nnz)
+        self.rb0, self.n_rb, self.j0, self.n_j = int(rb0), int(n_rb), int(j0), int(n_j)
+        self.col_shift, self.warps = int(col_shift), int(warps)
+        self.tile_counts = tile_counts            # host int64 [n_rb, n_j]: records per (row block, column tile)
+
+    def nbytes(self):
+        return self.px.numel() * 4 + self.ptr.numel() * 8
+
+
+def far_blocks(key_other, val_rowcount, n, n_bins, col_shift, warps):
+    """Row-ordered stream (key = gathered bin, val = {row, count}) -> FarCopy.
+
+    Two stable radix sorts bring the records into (row >> 14, other >> col_shift, row,
+    other) order: first on the column-tile bits of the gathered bin, then -- after swapping
+    key and other -- on the row-block bits of the row."""
+    dev = key_other.device
+    n = int(n)
+    if n == 0:
+        return None
+    n_j_all = ((max(n_bins, 1) - 1) >> col_shift) + 1
+    n_rb_all = ((max(n_bins, 1) - 1) >> FAR_ROW_SHIFT) + 1
+    ks, vs = sort_pairs(key_other[:n], val_rowcount, key_bits_for(n_j_all), key_shift=col_shift)
+    kr, vr = swap_key_other(ks, vs, n)            # key = row, val = {other, count}
+    del ks, vs
+    if n_rb_all > 1:
+        kr, vr = sort_pairs(kr, vr, key_bits_for(n_rb_all), key_shift=FAR_ROW_SHIFT)
+    ends = kr[torch.tensor([0, n - 1], device=dev)].cpu().numpy()
+    rb0, rb1 = int(ends[0]) >> FAR_ROW_SHIFT, int(ends[1]) >> FAR_ROW_SHIFT
+    n_rb, j0, n_j = rb1 - rb0 + 1, 0, n_j_all
+    n_slots = n_rb * n_j * warps
+    if n_slots >= 2**31 - 1:
+        raise ValueError("far-field slot table does not fit int32")
+    rec = _new_px(n, dev)
+    slot = torch.empty(n, dtype=_I32, device=dev)
+    _lib.call("cb200_far_finish", _ptr(kr), _ptr(vr), n, int(col_shift), rb0, j0, n_j, int(warps),
+              _ptr(rec), _ptr(slot), _stream())
+    del kr, vr
+    ptr_rec = indptr_from_sorted(slot, n, n_slots)            # first record of every slot
+    # lane-interleaved chunks: every slot is padded to whole 64-record chunks
+    nch = torch.empty(n_slots, dtype=_I32, device=dev)
+    _lib.call("cb200_far_slot_chunks", _ptr(ptr_rec), n_slots, _ptr(nch), _stream())
+    cptr = exclusive_scan_i32(nch)                            # first chunk of every slot
+    del nch
+    total_chunks = int(cptr[-1].item())
+    px = torch.empty((total_chunks * 64 + 2, 2), dtype=_I32, device=dev)
+    _lib.call("cb200_far_interleave", _ptr(rec), _ptr(slot), _ptr(ptr_rec), _ptr(cptr), n, total_chunks,
+              _ptr(px), _stream())
+    del rec, slot
+    tile_start = ptr_rec[::warps].cpu().numpy()               # [n_rb * n_j + 1]
+    counts = np.diff(tile_start).reshape(n_rb, n_j)
+    fc = FarCopy(px, cptr, n, rb0, n_rb, j0, n_j, col_shift, warps, counts)
+    fc.n_chunks = total_chunks
+    return fc
+
+
+def plan_far_units(copies_counts, target):
+    """Split the non-empty (row block, column tile) pairs of every far copy into units.
+
+    ``copies_counts``: list of (rb0, j0, counts[n_rb, n_j]).  A unit is a run of consecutive
+    non-empty tiles of ONE row block holding about ``target`` records (a persistent CTA of the
+    far kernel processes one unit at a time).  Returns (units int32 [n_units, 4] = copy, rb,
+    t0, t1; tiles int32 [n_tiles] = column tile ids; rb_unit: list of int32 [n_rb + 1] per copy).
+    Units are ordered by (copy, row block, t0) -- the order in which the per-bin kernels add
+    their partial sums."""
+    target = max(int(target), 1)
+    units, tiles, rb_units = [], [], []
+    for c, (rb0, j0, counts) in enumerate(copies_counts):
+        rb_unit = np.zeros(counts.shape[0] + 1, dtype=np.int32)
+        for k in range(counts.shape[0]):
+            rb_unit[k] = len(units)               # global index of the first unit of this row block
+            row = counts[k]
+            js = np.flatnonzero(row)
+            if len(js) == 0:
+                continue
+            cum = np.cumsum(row[js])
+            parts = max(1, int(round(cum[-1] / target)))     # equal parts of about `target` records
+            edges = np.searchsorted(cum, cum[-1] * np.arange(1, parts) / parts, side="left") + 1
+            edges = np.unique(np.r_[0, edges, len(js)])
+            base = len(tiles)
+            tiles.extend((js + j0).tolist())
+            for e0, e1 in zip(edges[:-1], edges[1:]):
+                units.append((c, rb0 + k, base + int(e0), base + int(e1)))
+        rb_unit[counts.shape[0]] = len(units)
+        rb_units.append(rb_unit)
+    return (np.asarray(units, dtype=np.int32).reshape(-1, 4), np.asarray(tiles, dtype=np.int32), rb_units)
+
+
 def marginals_i64(copy):
     """(nnz_marg, sum_marg) int64 row marginals of one copy."""
     dev = copy.device

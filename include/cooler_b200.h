@@ -85,6 +85,26 @@ int cb200_swap_key_other(const int32_t* keys, const cb200_px* vals, int64_t n,
 int cb200_strip_finish(const int32_t* keys, const cb200_px* vals, int64_t n, int32_t shift,
                        const int64_t* pad_before, cb200_px* px_out, int32_t* rows_out,
                        void* stream);
+/* Far-field blocks: elements (key = row, val = {other, count}) sorted by (row >> 14,
+ * other >> col_shift, row, other) -> records {swz(row & 16383) << 16 | (other & (C-1)), count}
+ * (swz: bank swizzle of the row id inside its warp slice, see far_swizzle in csrc/far.cuh)
+ * and the slot id g = (((row >> 14) - rb0) * n_j + (other >> col_shift) - j0) * warps
+ * + ((row & 16383) * warps >> 14) of every element (non-decreasing; cb200_indptr_from_sorted
+ * on g gives cb200_far_copy.ptr). */
+int cb200_far_finish(const int32_t* rows, const cb200_px* vals, int64_t n, int32_t col_shift,
+                     int32_t rb0, int32_t j0, int32_t n_j, int32_t warps,
+                     cb200_px* px_out, int32_t* slot_out, void* stream);
+/* nch_out[s] = ceil((ptr_rec[s+1] - ptr_rec[s]) / 64): 64-record chunks of every slot. */
+int cb200_far_slot_chunks(const int64_t* ptr_rec, int64_t n_slots, int32_t* nch_out, void* stream);
+/* Lane-interleaved layout of the far-field records: slot s (records [ptr_rec[s], ptr_rec[s+1])
+ * of `rec`, sorted by row) occupies chunks [chunk_ptr[s], chunk_ptr[s+1]) of px_out; its
+ * records are cut into 32 contiguous pieces of L = 2 * n_chunks(s) records (lane l gets records
+ * [l L, (l+1) L)), and chunk c holds records 2c, 2c+1 of every lane at positions 2 lane,
+ * 2 lane + 1 -- one coalesced 128-bit load per lane.  Unused positions hold padding records
+ * {16384 << 16, 0}.  px_out has total_chunks * 64 + 2 records. */
+int cb200_far_interleave(const cb200_px* rec, const int32_t* slot, const int64_t* ptr_rec,
+                         const int64_t* chunk_ptr, int64_t n, int64_t total_chunks, cb200_px* px_out,
+                         void* stream);
 
 /* Static pixel filter.  A pixel (row r, other c) is KEPT iff
  *   !(ndiag > 0 && |r - c| < ndiag)                       (_zero_diags)
@@ -148,6 +168,34 @@ typedef struct {
   int32_t  row_count;
 } cb200_sub;
 
+/* Far-field blocks (large, very sparse matrices: the gathered bias vector is far larger
+ * than L1 and (row, column strip) segments hold only a few pixels).  The far pixels of a
+ * copy are re-ordered by (row block = row >> 14, column tile = other >> col_shift, row,
+ * other) and stored as records {(row & 16383) << 16 | (other & (C - 1)), count},
+ * C = 1 << col_shift.  A persistent CTA owns a unit = (row block, run of non-empty column
+ * tiles): it keeps the 16384 row sums in shared memory and stages the C-wide slice of the
+ * bias vector of one tile after the other (double-buffered cp.async).  Warp k owns the rows
+ * [k, k+1) * 16384 / far_warps of the block; the records of one (row block, tile, warp slice)
+ * = slot are stored as lane-interleaved 64-record chunks (cb200_far_interleave): every lane
+ * sums the runs of equal rows of its own contiguous piece and adds them to the accumulators;
+ * lane-boundary runs are merged once per slot by a warp-level segmented scan -- no atomics,
+ * fixed summation order.  Unit u writes its row sums to far_parts[u * 16384 ...]; the
+ * per-bin kernels add the units of a row block in order. */
+enum { CB200_FAR_ROW_SHIFT = 14 };
+typedef struct {
+  const cb200_px* px;        /* [n_chunks * 64] (+2 pad) lane-interleaved records, see above */
+  const int64_t*  ptr;       /* [n_rb * n_j * far_warps + 1] first CHUNK of every slot (row block, column tile, warp row slice) */
+  int64_t  nnz;              /* records without padding */
+  int32_t  rb0, n_rb;        /* row blocks [rb0, rb0 + n_rb) */
+  int32_t  j0, n_j;          /* column tiles [j0, j0 + n_j) */
+  const int32_t* rb_unit;    /* [n_rb + 1] units (indices into far_units) of each row block */
+} cb200_far_copy;
+typedef struct {
+  int32_t copy;              /* index into far_copies */
+  int32_t rb;                /* absolute row block */
+  int32_t t0, t1;            /* this unit handles the non-empty column tiles far_tiles[t0 .. t1) */
+} cb200_far_unit;
+
 typedef struct {
   const cb200_sub* subs;     /* DEVICE array: bin1-major sub-copies then bin2-major ones (static filters applied) */
   int32_t  n_subs;
@@ -180,6 +228,16 @@ typedef struct {
   double*  var_hist;         /* [max_iters * n_segs] variance per pass (NaN where not run) or NULL */
   double   tol;
   int32_t  max_iters;
+  /* far-field blocks (n_far_units == 0: none) */
+  int32_t  n_far_copies;
+  const cb200_far_copy* far_copies;   /* DEVICE array */
+  const cb200_far_unit* far_units;    /* DEVICE array, ordered by (copy, row block, t0) */
+  const int32_t* far_tiles;           /* column tile of every non-empty (row block, tile), grouped by unit */
+  double*  far_parts;                 /* [n_far_units * 16384] */
+  int64_t* far_claim;                 /* [2] zero-initialised (self re-arming) */
+  int32_t  n_far_units;
+  int32_t  far_col_shift;             /* log2 C, 4..12 */
+  int32_t  far_warps;                 /* 16 or 32: warps per CTA = row slices per block */
 } cb200_ice;
 
 /* Tuning of K3 (optional): ice_unroll in {0,1,2,4,8} = 128-bit stream loads kept in
@@ -187,8 +245,12 @@ typedef struct {
  * selective_l1: -1 automatic, 0/1 = whether gathers far from the diagonal bypass L1
  * allocation in the L1/L2-gather kernel. */
 int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1);
+/* Far-field kernel: 128-bit stream loads in flight per lane (0 = default: 4 with 16 warps,
+ * 2 with 32 warps). */
+int cb200_set_far_tuning(int32_t far_unroll);
 /* K3: the marginal sweeps of every sub-copy (bin1-major rows, bin2-major columns), one
- * launch.  No-op once *all_done. */
+ * launch, followed by one launch over the far-field blocks if there are any.  No-op once
+ * *all_done. */
 int cb200_ice_sweep(const cb200_ice* st, void* stream);
 /* s[i] = rowpart(i) + colpart(i) -- the vector ranks all-reduce.  No-op once *all_done. */
 int cb200_ice_combine(const cb200_ice* st, void* stream);

@@ -238,6 +238,116 @@ def test_band_layout_large_synthetic_matches_unstripped():
     np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
 
 
+@pytest.mark.parametrize("key,strip_bins,col_shift,warps", [
+    ("gm/defaults", 64, 4, 16), ("gm/cis_only", 128, 6, 32), ("gm/trans_only", 32, 3, 16),
+    ("rnd3/gw", 16, 2, 32), ("rnd2/cis", 16, 5, 16), ("rnd3/trans", 32, 12, 16), ("gm/diag0", 16, 1, 16)])
+def test_far_blocks_layout_matches_reference_golden(key, strip_bins, col_shift, warps):
+    """Band strips + far-field blocks (csrc/far.cuh: 2-D blocked far pixels, segmented-scan kernel)."""
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    src, case = key.split("/")
+    t = _golden.table_of(src)
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    kw = dict(META[key]["kwargs"])
+    tab = PixelTable.from_arrays(bin1_offset, t["bin2_id"], t["count"], chrom_offset)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, band="blocks",
+                                                      far_col_shift=col_shift, far_warps=warps, **kw)
+    assert info["band"] == "blocks"
+    if case != "cis_only":
+        assert info["far_units"] > 0 and info["far_pixels"] > 0
+    want = BAL[key]
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    assert sum(info["passes"]) == sum(META[key]["passes"])
+    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
+
+
+@pytest.mark.parametrize("strip_bins,col_shift,warps,unroll", [(1024, 8, 16, 0), (4096, 12, 32, 0), (256, 10, 16, 2),
+                                                             (16384, 12, 16, 0), (512, 5, 32, 1)])
+def test_far_blocks_large_synthetic_matches_unstripped(strip_bins, col_shift, warps, unroll):
+    """Several 16384-row blocks, hundreds of column tiles, rows from empty to dense; every
+    far-kernel variant agrees with the whole-copy sweep to rounding and is bit-reproducible."""
+    import cooler_b200
+    from cooler_b200 import PixelTable, _lib
+    b1, b2, cnt, chrom_offset = _synthetic(35, [50000, 30000, 20001], 0.002)
+    n = int(chrom_offset[-1])
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
+    a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0)
+    assert _lib.load().cb200_set_far_tuning(unroll) == 0
+    try:
+        b, sb, ib = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, band="blocks",
+                                              far_col_shift=col_shift, far_warps=warps)
+        c, sc, ic = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, band="blocks",
+                                              far_col_shift=col_shift, far_warps=warps)
+    finally:
+        _lib.load().cb200_set_far_tuning(0)
+    assert ib["band"] == "blocks" and ib["far_units"] > 4 and ib["far_pixels"] > 100000
+    assert ia["passes"] == ib["passes"]
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
+    np.testing.assert_array_equal(b, c)
+
+
+@pytest.mark.parametrize("key,col_shift,warps", [("gm/defaults", 4, 16), ("gm/cis_only", 7, 32), ("gm/trans_only", 5, 16),
+                                                 ("rnd3/gw", 2, 32), ("gm/diag0", 12, 16), ("gm/mad0_nnz0", 6, 32)])
+def test_all_blocks_layout_matches_reference_golden(key, col_shift, warps):
+    """Every pixel (dense diagonal runs included) through the 2-D blocked kernel."""
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    src, case = key.split("/")
+    t = _golden.table_of(src)
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    kw = dict(META[key]["kwargs"])
+    tab = PixelTable.from_arrays(bin1_offset, t["bin2_id"], t["count"], chrom_offset)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, band="allblocks",
+                                                      far_col_shift=col_shift, far_warps=warps, **kw)
+    assert info["band"] == "allblocks" and info["n_subcopies"] == 0 and info["far_units"] > 0
+    want = BAL[key]
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    assert sum(info["passes"]) == sum(META[key]["passes"])
+    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
+
+
+def test_all_blocks_large_synthetic_matches_unstripped():
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    b1, b2, cnt, chrom_offset = _synthetic(37, [50000, 30000, 20001], 0.002)
+    n = int(chrom_offset[-1])
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
+    a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0)
+    for warps in (16, 32):
+        b, sb, ib = cooler_b200.balance_table(tab, return_info=True, band="allblocks", far_warps=warps)
+        assert ib["far_pixels"] == 2 * ia["nnz_eff"] and ia["passes"] == ib["passes"]
+        np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+        np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("mode", ["cis", "trans"])
+def test_far_blocks_modes_match_oracle(mode):
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    from oracle import ice_numpy
+    b1, b2, cnt, chrom_offset = _synthetic(36, [20000, 15000, 9000], 0.004)
+    n = int(chrom_offset[-1])
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    kw = dict(cis_only=(mode == "cis"), trans_only=(mode == "trans"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want, wstats, wpasses, wwarned = ice_numpy.balance_arrays(
+            dict(bin1_id=b1, bin2_id=b2, count=cnt), chrom_offset, bin1_offset, return_passes=True, **kw)
+        tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
+        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, strip_bins=512, band="blocks",
+                                                      far_col_shift=9, **kw)
+    assert info["far_units"] > 0 and info["passes"] == wpasses
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
+
+
 @pytest.mark.parametrize("case", ["empty", "diag_only", "one_bin", "one_pixel", "all_masked"])
 @pytest.mark.parametrize("mode", ["gw", "cis", "trans"])
 def test_degenerate_tables_match_oracle(case, mode):
