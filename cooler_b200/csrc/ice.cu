@@ -54,8 +54,8 @@ static int g_selective = -1;   // -1 = automatic
 static int g_far_unroll = 0;   // far-field kernel: 0 = automatic
 static int g_ice_unroll = 0;   // 0 = automatic: 4 chunks in flight per lane (strip kernel: 768-thread CTAs)
 
-template <int U, bool kSelective>
-__global__ void __launch_bounds__(BLOCK_THREADS)
+template <int U, bool kSelective, int MINB>
+__global__ void __launch_bounds__(BLOCK_THREADS, MINB)
 ice_sweep_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span, int64_t total_warps,
                  const double* __restrict__ w, const int32_t* __restrict__ all_done) {
   if (*all_done) return;
@@ -72,7 +72,7 @@ ice_sweep_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span, int64
   if (t0 >= n_tiles) return;
   IceOpT<kSelective> op{w, sub.row_base, 0};
   walk_reduce_span<IceOpT<kSelective>, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
-                                          sub.nnz, t0, min(t0 + span, n_tiles), op, sub.direct, sub.pieces);
+                                          sub.row_count, sub.nnz, t0, min(t0 + span, n_tiles), op, sub.direct, sub.pieces);
 }
 
 // Shared-memory form of K3 for column strips: a persistent CTA per SM owns a
@@ -145,11 +145,11 @@ ice_sweep_strips_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span
       if (in_smem) {
         IceOpSmem op{w_s, sub.gather_base};
         walk_reduce_span<IceOpSmem, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
-                                       sub.nnz, t0, t1, op, sub.direct, sub.pieces);
+                                       sub.row_count, sub.nnz, t0, t1, op, sub.direct, sub.pieces);
       } else {                                     // far-field remainder: gather through L1/L2
         IceOp op{w};
         walk_reduce_span<IceOp, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
-                                   sub.nnz, t0, t1, op, sub.direct, sub.pieces);
+                                   sub.row_count, sub.nnz, t0, t1, op, sub.direct, sub.pieces);
       }
     }
   }
@@ -338,7 +338,7 @@ using namespace cb200;
 extern "C" {
 
 int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1) {
-  if (ice_unroll != 0 && ice_unroll != 1 && ice_unroll != 2 && ice_unroll != 4 && ice_unroll != 8) return -1;
+  if (ice_unroll != 0 && ice_unroll != 1 && ice_unroll != 2 && ice_unroll != 4 && ice_unroll != 5 && ice_unroll != 8) return -1;
   g_ice_unroll = ice_unroll;
   g_selective = selective_l1 < 0 ? -1 : (selective_l1 ? 1 : 0);
   return 0;
@@ -432,20 +432,21 @@ static int ice_sweep_near(const cb200_ice* st, void* stream) {
   const int64_t blocks = ceil_div64(st->total_warps, WARPS_PER_BLOCK);
   // selective L1 allocation only pays when w is much larger than L1 (tools/tune_sweep.py)
   const int selective = g_selective < 0 ? (st->n_bins > 4 * kNearBins ? 1 : 0) : g_selective;
-#define CB_SWEEP(U)                                                                                 \
+#define CB_SWEEP(U, MINB)                                                                           \
   do {                                                                                              \
     if (selective)                                                                                  \
-      ice_sweep_kernel<U, true><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(      \
+      ice_sweep_kernel<U, true, MINB><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(\
           st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);                    \
     else                                                                                            \
-      ice_sweep_kernel<U, false><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(     \
+      ice_sweep_kernel<U, false, MINB><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(\
           st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);                    \
   } while (0)
   switch (g_ice_unroll) {
-    case 1: CB_SWEEP(1); break;
-    case 2: CB_SWEEP(2); break;
-    case 8: CB_SWEEP(8); break;
-    default: CB_SWEEP(4); break;
+    case 1: CB_SWEEP(1, 4); break;
+    case 2: CB_SWEEP(2, 4); break;
+    case 8: CB_SWEEP(8, 2); break;
+    case 5: CB_SWEEP(4, 4); break;     // 64 registers (4 blocks per SM) at the price of a few spills
+    default: CB_SWEEP(4, 3); break;
   }
 #undef CB_SWEEP
   CB_LAUNCH_CHECK("ice_sweep");

@@ -238,12 +238,12 @@ struct NnzSumOp {
 
 __global__ void __launch_bounds__(BLOCK_THREADS)
 marginals_sweep_kernel(const int2* __restrict__ px, const int64_t* __restrict__ indptr,
-                       const int32_t* __restrict__ tile_row, int64_t nnz, int64_t n_tiles,
+                       const int32_t* __restrict__ tile_row, int n_rows, int64_t nnz, int64_t n_tiles,
                        I64x2* __restrict__ direct, I64x2* __restrict__ pieces) {
   const int64_t t = (int64_t)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
   if (t >= n_tiles) return;
   NnzSumOp op;
-  walk_reduce_tile<NnzSumOp, 4>(px, indptr, nnz, t, tile_row, op, direct, pieces);
+  walk_reduce_tile<NnzSumOp, 4>(px, indptr, n_rows, nnz, t, tile_row, op, direct, pieces);
 }
 
 // direct is laid over (nnz_out, sum_out) as scratch is not possible (interleaved
@@ -423,8 +423,8 @@ int cb200_marginals_i64(const cb200_copy* copy, int32_t n_rows, int64_t* nnz_out
   I64x2* direct = pc + 2 * n_tiles;
   if (n_tiles > 0) {
     marginals_sweep_kernel<<<(unsigned)ceil_div64(n_tiles, WARPS_PER_BLOCK), BLOCK_THREADS, 0, st>>>(
-        reinterpret_cast<const int2*>(copy->px), copy->indptr, copy->tile_row, nnz, n_tiles, direct,
-        pc);
+        reinterpret_cast<const int2*>(copy->px), copy->indptr, copy->tile_row, n_rows, nnz, n_tiles,
+        direct, pc);
     CB_LAUNCH_CHECK("marginals_sweep");
   }
   if (n_rows > 0) {

@@ -36,7 +36,7 @@ __device__ __forceinline__ I64x2 acc_wsum(I64x2 x) { return I64x2{warp_sum(x.a),
 template <typename Op, int U>
 __device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
                                                  const int64_t* __restrict__ indptr,
-                                                 const int32_t* __restrict__ tile_row,
+                                                 const int32_t* __restrict__ tile_row, int n_rows,
                                                  int64_t nnz, int64_t t_begin, int64_t t_end,
                                                  Op& op, typename Op::T* __restrict__ direct,
                                                  typename Op::T* __restrict__ pieces) {
@@ -56,11 +56,37 @@ __device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
     qn[u] = (u * CHUNK + 2 * lane < n) ? ld_stream_int4(src + u * (CHUNK / 2)) : make_int4(0, 0, 0, 0);
 
   int row = tile_row[t_begin];
-  auto rel_end = [&](int r) -> int {               // end of row r relative to pbeg, clamped
+  // Row ends are read through a register window: lane l holds the end of row wbase + l
+  // (relative to pbeg, clamped), the next 32 are prefetched.  Moving to the next row is a
+  // ballot + shuffle instead of a dependent global load per row, which matters when rows
+  // are short (a few chunks) or mostly empty.
+  constexpr unsigned FULL = 0xffffffffu;
+  auto load_end = [&](int r) -> int {
+    if (r >= n_rows) return 0x7fffffff;
     const int64_t e = indptr[r + 1] - pbeg;
     return e > (int64_t)0x7fffffff ? 0x7fffffff : (int)e;
   };
-  int re = rel_end(row);
+  int wbase = row;
+  int wcur = load_end(wbase + lane);
+  int wnext = load_end(wbase + 32 + lane);
+  int re = __shfl_sync(FULL, wcur, 0);
+  auto advance = [&](int done_to) {                // first later row whose end is > done_to
+    while (true) {
+      const int k = row - wbase + 1;               // first candidate lane of the window
+      unsigned m = __ballot_sync(FULL, wcur > done_to);
+      m = (k < 32) ? (m & (FULL << k)) : 0u;
+      if (m) {
+        const int kk = __ffs(m) - 1;
+        row = wbase + kk;
+        re = __shfl_sync(FULL, wcur, kk);
+        return;
+      }
+      wbase += 32;
+      wcur = wnext;
+      wnext = load_end(wbase + 32 + lane);
+      row = wbase - 1;
+    }
+  };
   T acc = zero;
   bool first = true;
   int64_t t = t_begin;
@@ -114,11 +140,7 @@ __device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
           }
           first = false;
           acc = zero;
-          const int done_to = re;
-          do {                                     // next non-empty row
-            ++row;
-            re = rel_end(row);
-          } while (re == done_to);
+          advance(re);                             // next non-empty row
           op.at_row(row);
         }
       }
@@ -129,11 +151,8 @@ __device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
       acc = zero;
       first = true;
       ++t;
-      if (cn < n && re <= cn) {
-        do {                                       // the row ended exactly at the tile boundary
-          ++row;
-          re = rel_end(row);
-        } while (re <= cn);
+      if (cn < n && re <= cn) {                    // the row ended exactly at the tile boundary
+        advance(cn);
         op.at_row(row);
       }
     }
@@ -143,11 +162,12 @@ __device__ __forceinline__ void walk_reduce_span(const int2* __restrict__ px,
 // Single-tile form (integer marginals and other one-time passes).
 template <typename Op, int U>
 __device__ __forceinline__ void walk_reduce_tile(const int2* __restrict__ px,
-                                                 const int64_t* __restrict__ indptr, int64_t nnz,
-                                                 int64_t t, const int32_t* __restrict__ tile_row,
+                                                 const int64_t* __restrict__ indptr, int n_rows,
+                                                 int64_t nnz, int64_t t,
+                                                 const int32_t* __restrict__ tile_row,
                                                  Op& op, typename Op::T* __restrict__ direct,
                                                  typename Op::T* __restrict__ pieces) {
-  walk_reduce_span<Op, U>(px, indptr, tile_row, nnz, t, t + 1, op, direct, pieces);
+  walk_reduce_span<Op, U>(px, indptr, tile_row, n_rows, nnz, t, t + 1, op, direct, pieces);
 }
 
 // Total of row r from the outputs of walk_reduce_tile.
