@@ -10,7 +10,8 @@ entry points without the built library or without a CUDA device raises.
 """
 from .balance import (ConvergenceWarning, balance_arrays, balance_cooler, balance_table,  # noqa: F401
                       iterative_correction)
-from .store import MemCooler  # noqa: F401
+from .api import matrix  # noqa: F401
+from .store import H5Cooler, MemCooler, open_cooler  # noqa: F401
 from .table import PixelTable  # noqa: F401
 
 __version__ = "0.1.0"

@@ -5,7 +5,9 @@ Same flags, defaults, messages and exit codes as the reference's click commands
 ``--chunksize`` are accepted and ignored (no process pool: the GPU path must not
 fork after CUDA initialisation).  COOL_PATH is resolved by
 ``cooler_b200.store.open_cooler``: a registered in-memory store, else the real
-``cooler`` package (h5py).
+``cooler`` package (h5py) if installed, else the built-in read-only HDF5 reader
+(``cooler_b200.h5lite``: ``balance --stdout`` / ``--check`` work on real ``.cool`` files;
+storing a column or writing a new file needs h5py).
 
     python -m cooler_b200.cli balance sample.cool --cis-only
 """
@@ -146,7 +148,9 @@ def balance(cool_uri, nproc, chunksize, mad_max, min_nnz, min_count, blacklist, 
     if cis_only and trans_only:                                   # 190-193
         raise click.UsageError("Provide at most one of --cis-only and --trans-only flags")
 
-    with clr.open("r+") as grp:                                   # 195-206
+    # 195-206 (the reference opens "r+" here even with --stdout; read-only stores -- a .cool read
+    # by the built-in HDF5 reader -- can still print their weights)
+    with clr.open("r" if stdout else "r+") as grp:
         if name in grp["bins"] and not stdout:
             if not force:
                 print(f"'{name}' column already exists. Use --force option to overwrite.", file=sys.stderr)

@@ -60,9 +60,9 @@ def open_cooler(uri):
         return obj
     try:
         import cooler
-    except ImportError as e:
-        raise ImportError(f"cannot open '{uri}': it is not a registered in-memory store and the "
-                          "`cooler` package (h5py) is not installed") from e
+    except ImportError:
+        # no h5py / libhdf5 here: read the file with the built-in HDF5 subset reader (read-only)
+        return H5Cooler(path, group)
     return cooler.Cooler(uri)
 
 
@@ -271,3 +271,90 @@ class MemCooler:
     def shape(self):
         n = self.root.attrs["nbins"]
         return (n, n)
+
+
+class H5Cooler(MemCooler):
+    """A ``.cool`` file (or one resolution of an ``.mcool``) read with ``cooler_b200.h5lite``.
+
+    Same read protocol as ``cooler.Cooler`` for the hot path (api.py:32-409): columns are
+    decoded (gzip + shuffle) on access, so ``balance_cooler`` / ``CoolerCoarsener`` read the
+    pixel table exactly once.  The built-in reader cannot write: ``open('r+')`` (e.g.
+    ``balance_cooler(..., store=True)``) raises -- install h5py + cooler for in-place storage.
+    """
+
+    def __init__(self, path, group="/"):
+        from . import h5lite
+        self._file = h5lite.File(path)
+        try:
+            root = self._file[group] if group not in ("", "/") else self._file
+        except KeyError:
+            raise KeyError(f"No cooler found at: {path}::{group}") from None     # api.py:101-109
+        if not isinstance(root, h5lite.Group) or any(k not in root for k in ("chroms", "bins", "pixels", "indexes")):
+            raise KeyError(f"No cooler found at: {path}::{group}")
+        super().__init__(root, filename=path)
+        self.uri = path if group in ("", "/") else f"{path}::{group}"
+        self.group = group
+
+    @property
+    def info(self):
+        d = dict(self.root.attrs)
+        for k in ("storage-mode",):                  # some old files keep it as a scalar dataset
+            if k not in d and k in self.root:
+                d[k] = self.root[k][()]
+        if "nbins" not in d:
+            d["nbins"] = len(self.root["bins/chrom"])
+        if "nnz" not in d:
+            d["nnz"] = len(self.root["pixels/bin1_id"])
+        return d
+
+    @property
+    def binsize(self):
+        v = self.root.attrs.get("bin-size")
+        return None if v in (None, "null", "None") else int(v)
+
+    @property
+    def storage_mode(self):
+        return self.info.get("storage-mode", "symmetric-upper")
+
+    @property
+    def shape(self):
+        n = self.info["nbins"]
+        return (n, n)
+
+    @staticmethod
+    def _ordered(group, first):
+        keys = group.keys()
+        return [k for k in first if k in keys] + [k for k in keys if k not in first]
+
+    def bins(self, **kwargs):
+        return _Selector(self.root["bins"], self._ordered(self.root["bins"], ["chrom", "start", "end"]))
+
+    def pixels(self, join=False, **kwargs):
+        if join:
+            raise NotImplementedError("H5Cooler.pixels(join=True)")
+        return _Selector(self.root["pixels"], self._ordered(self.root["pixels"], ["bin1_id", "bin2_id", "count"]))
+
+    @contextmanager
+    def open(self, mode="r", **kwargs):
+        if mode != "r":
+            raise OSError(f"{self.filename}: the built-in HDF5 reader (cooler_b200.h5lite) is read-only; "
+                          "writing columns into a .cool file needs h5py + cooler")
+        yield self.root
+
+
+def list_coolers(path):
+    """Group paths of every cooler in a file (fileops.list_coolers, fileops.py:113-150)."""
+    from . import h5lite
+    f = h5lite.File(path)
+    out = []
+
+    def visit(g, name):
+        if all(k in g for k in ("chroms", "bins", "pixels", "indexes")):
+            out.append(name or "/")
+            return
+        for k in g.keys():
+            o = g[k]
+            if isinstance(o, h5lite.Group):
+                visit(o, f"{name}/{k}")
+    visit(f, "")
+    return out

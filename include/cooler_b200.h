@@ -292,6 +292,32 @@ int cb200_runs_write(const int32_t* keys, const cb200_px* vals, int64_t n,
 int cb200_unpack_pixels(const int32_t* bin1, const cb200_px* val, int64_t n,
                         int64_t* bin1_out, int64_t* bin2_out, int32_t* count_out, void* stream);
 
+/* ---- balanced matrix fetch (replaces cooler.api.matrix: the CSR range query of
+ *      core/_rangequery.py:153-368 -- CSRReader, DirectRangeQuery2D, FillLowerRangeQuery2D --
+ *      and the weight application of src/cooler/api.py:742-798) ----------------------------- */
+/* Window [i0,i1) x [j0,j1) of the matrix stored in `csr` (the UNFILTERED bin1-major copy,
+ * n_rows bins).  fill_lower != 0 (symmetric-upper storage): cells below the diagonal are
+ * filled from their mirror images.  Query rows: (i1-i0) direct rows, then (j1-j0) mirrored
+ * rows when fill_lower.
+ * count: row_count[q] = pixels produced by query row q (scan it for cb200_fetch_coo).
+ * dense: dense_out[(i1-i0)*(j1-j0)] int32, fully written (zeros where nothing is stored).
+ * coo:   window-relative (row, col, value) triples of query row q at row_off[q] ... */
+int cb200_fetch_count(const cb200_copy* csr, int32_t n_rows, int32_t i0, int32_t i1, int32_t j0,
+                      int32_t j1, int32_t fill_lower, int32_t* row_count, void* stream);
+int cb200_fetch_dense(const cb200_copy* csr, int32_t n_rows, int32_t i0, int32_t i1, int32_t j0,
+                      int32_t j1, int32_t fill_lower, int32_t* dense_out, void* stream);
+int cb200_fetch_coo(const cb200_copy* csr, int32_t n_rows, int32_t i0, int32_t i1, int32_t j0,
+                    int32_t j1, int32_t fill_lower, const int64_t* row_off, int32_t* row_out,
+                    int32_t* col_out, int32_t* val_out, void* stream);
+/* out = dense * outer(w1, w2)  (w1 = weights[i0:i1], w2 = weights[j0:j1]; divisive != 0:
+ * reciprocal weights), evaluated as x * (w1_i * w2_j) like `arr * np.outer(bias1, bias2)`. */
+int cb200_fetch_balance_dense(const int32_t* dense, int64_t h, int64_t w, const double* w1,
+                              const double* w2, int32_t divisive, double* out, void* stream);
+/* out[k] = w1[row[k]] * w2[col[k]] * val[k]  (`bias1[mat.row] * bias2[mat.col] * mat.data`). */
+int cb200_fetch_balance_coo(const int32_t* row, const int32_t* col, const int32_t* val, int64_t n,
+                            const double* w1, const double* w2, int32_t divisive, double* out,
+                            void* stream);
+
 #ifdef __cplusplus
 }
 #endif

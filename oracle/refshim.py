@@ -79,8 +79,9 @@ def _install_stubs() -> None:
     cz = types.ModuleType("cytoolz")
 
     def compose(*fs):
-        def f(x):
-            for g in reversed(fs):
+        def f(*args, **kwargs):
+            x = fs[-1](*args, **kwargs)
+            for g in reversed(fs[:-1]):
                 x = g(x)
             return x
 

@@ -1,0 +1,108 @@
+"""GPU: balanced matrix fetch (csrc/fetch.cu through the C ABI) against golden vectors from the
+unmodified reference and against the oracle on larger random tables.  Bar: counts bit-exact,
+balanced values bit-exact as well (same two roundings as `arr * np.outer(b1, b2)`)."""
+import numpy as np
+import pytest
+
+from tests import _golden, _matrix_cases as MC
+
+pytestmark = pytest.mark.gpu
+
+
+def _clr(t, symmetric_upper=True, weights=None):
+    from cooler_b200 import MemCooler
+    clr = MemCooler.from_arrays([str(x) for x in t["chromnames"]], t["chromsizes"], t["bins_chrom"],
+                                t["bins_start"], t["bins_end"], t["bin1_id"], t["bin2_id"], t["count"],
+                                binsize=int(t["binsize"]) if "binsize" in t else 2_000_000,
+                                symmetric_upper=symmetric_upper)
+    if weights is not None:
+        with clr.open("r+") as g:
+            g["bins"].create_dataset("weight", data=weights)
+    return clr
+
+
+@pytest.mark.parametrize("case", MC.DENSE)
+def test_dense_fetch_matches_reference_golden(case):
+    import cooler_b200
+    t, w, (i0, i1, j0, j1), kw = MC.inputs(case)
+    clr = _clr(t, kw["symmetric_upper"], w)
+    sel = cooler_b200.matrix(clr, balance=w is not None, divisive_weights=kw.get("divisive_weights", False))
+    got = sel[i0:i1, j0:j1]
+    want = MC.GOLD[case]
+    assert got.shape == want.shape and got.dtype == want.dtype
+    np.testing.assert_array_equal(got, want)
+
+
+def test_region_fetch_and_missing_weights():
+    import cooler_b200
+    t, w, _, _ = MC.inputs("chr1_bal")
+    clr = _clr(t, True, w)
+    sel = cooler_b200.matrix(clr, balance=True)
+    np.testing.assert_array_equal(sel.fetch("chr1"), MC.GOLD["chr1_bal"])
+    np.testing.assert_array_equal(sel.fetch("chr5", "chr2:10,000,000-50,000,000"), MC.GOLD["rect_lower_bal"])
+    raw = cooler_b200.matrix(clr, balance=False, table=sel.table)
+    np.testing.assert_array_equal(raw.fetch("chr2:10,000,000-50,000,000", "chr5"), MC.GOLD["rect_raw"])
+    assert sel.shape == (1561, 1561)
+    with pytest.raises(ValueError, match="No column 'bins/nope'"):
+        cooler_b200.matrix(clr, balance="nope")
+    # weights handed over directly (e.g. the bias balance_cooler just returned)
+    bias, _ = cooler_b200.balance_cooler(clr)
+    direct = cooler_b200.matrix(clr, weights=bias, table=sel.table).fetch("chr1")
+    np.testing.assert_allclose(direct, MC.GOLD["chr1_bal"], rtol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("case", MC.SPARSE)
+def test_sparse_fetch_matches_reference_golden(case):
+    import cooler_b200
+    t, w, (i0, i1, j0, j1), kw = MC.inputs(case)
+    m = cooler_b200.matrix(_clr(t, True, w), balance=w is not None, sparse=True)[i0:i1, j0:j1]
+    o = np.lexsort((m.col, m.row))
+    np.testing.assert_array_equal(m.row[o], MC.GOLD[case + "/row"])
+    np.testing.assert_array_equal(m.col[o], MC.GOLD[case + "/col"])
+    np.testing.assert_array_equal(m.data[o], MC.GOLD[case + "/data"])
+    assert m.shape == tuple(MC.GOLD[case + "/shape"])
+
+
+@pytest.mark.parametrize("case", MC.PIXELS)
+def test_pixel_fetch_matches_reference_golden(case):
+    import cooler_b200
+    t, w, (i0, i1, j0, j1), kw = MC.inputs(case)
+    df = cooler_b200.matrix(_clr(t, True, w), balance=w is not None, as_pixels=True)[i0:i1, j0:j1]
+    for c in ("bin1_id", "bin2_id", "count") + (("balanced",) if w is not None else ()):
+        np.testing.assert_array_equal(df[c].to_numpy(), MC.GOLD[f"{case}/{c}"])
+
+
+def test_dense_fetch_matches_oracle_on_random_table():
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    from oracle import matrix_numpy
+    rng = np.random.default_rng(5)
+    n = 20000
+    nnz = 600000
+    i = rng.integers(0, n, nnz)
+    j = np.minimum(i + (rng.pareto(0.8, nnz) * 4).astype(np.int64), n - 1)
+    far = rng.random(nnz) < 0.2
+    j = np.where(far, rng.integers(0, n, nnz), j)
+    i, j = np.minimum(i, j), np.maximum(i, j)
+    key = np.unique(i * n + j)
+    b1, b2 = key // n, key % n
+    cnt = rng.integers(0, 1000, len(key)).astype(np.int32)            # explicit zeros included
+    w = rng.lognormal(0, 0.3, n)
+    w[rng.random(n) < 0.05] = np.nan
+    off = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    tab = PixelTable.from_arrays(off, b2, cnt, np.array([0, 9000, n]))
+    for sym in (True, False):
+        sel = cooler_b200.api.MatrixSelector(None, tab, w, fill_lower=sym)
+        raw = cooler_b200.api.MatrixSelector(None, tab, None, fill_lower=sym)
+        for (i0, i1, j0, j1) in [(0, 3000, 0, 3000), (5000, 5600, 4800, 9000), (9000, 20000, 100, 900),
+                                 (19990, 20000, 0, 20000), (7, 8, 7, 8), (100, 100, 0, 50)]:
+            want = matrix_numpy.fetch_dense(b1, b2, cnt, i0, i1, j0, j1, symmetric_upper=sym, weights=w)
+            np.testing.assert_array_equal(sel[i0:i1, j0:j1], want)
+            want = matrix_numpy.fetch_dense(b1, b2, cnt, i0, i1, j0, j1, symmetric_upper=sym)
+            np.testing.assert_array_equal(raw[i0:i1, j0:j1], want)
+        sp = cooler_b200.api.MatrixSelector(None, tab, w, sparse=True, fill_lower=sym)[4000:9500, 3000:9100]
+        r, c, d = matrix_numpy.fetch_sparse(b1, b2, cnt, 4000, 9500, 3000, 9100, symmetric_upper=sym, weights=w)
+        o = np.lexsort((sp.col, sp.row))
+        np.testing.assert_array_equal(sp.row[o], r)
+        np.testing.assert_array_equal(sp.col[o], c)
+        np.testing.assert_array_equal(sp.data[o], d)
