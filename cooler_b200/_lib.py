@@ -99,6 +99,7 @@ SIGNATURES = {
     "cb200_ice_combine": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_update": (C.c_int, [C.POINTER(Ice), _I32, _I32, _P]),
     "cb200_ice_update_peer": (C.c_int, [C.POINTER(Ice), _I32, _P, _I32, _I64, _P]),
+    "cb200_bin_pairs": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P]),
     "cb200_fetch_count": (C.c_int, [C.POINTER(Copy), _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "cb200_fetch_dense": (C.c_int, [C.POINTER(Copy), _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "cb200_fetch_coo": (C.c_int, [C.POINTER(Copy), _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),

@@ -156,3 +156,73 @@ int cb200_unpack_pixels(const int32_t* bin1, const cb200_px* val, int64_t n, int
 }
 
 }  // extern "C"
+
+// ---- ingest binning: pairs -> (bin1, bin2) records -----------------------------
+// Reference: open2c/cooler src/cooler/create/_ingest.py:68-214 (_sanitize_records: drop records on
+// unknown chromosomes, 1-based -> 0-based, bounds checks, reflect / drop / raise lower-triangle
+// records, bin id = chrom_binoffset[chrom] + pos // binsize); the groupby(bin1, bin2).size() of
+// aggregate_records (:452-504) is then the same sort + reduce-by-key as coarsening.
+namespace cb200 {
+
+__global__ void bin_pairs_kernel(const int32_t* __restrict__ chrom1, const int64_t* __restrict__ pos1,
+                                 const int32_t* __restrict__ chrom2, const int64_t* __restrict__ pos2,
+                                 int64_t n, const int32_t* __restrict__ chrom_binoffset,
+                                 const int64_t* __restrict__ chromsizes, int64_t binsize, int one_based,
+                                 int tril_action, int n_bins, int32_t* __restrict__ key_out,
+                                 int2* __restrict__ val_out, int32_t* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int f_neg = 0, f_exc = 0, f_tril = 0, dropped = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int c1 = chrom1[i], c2 = chrom2[i];
+    int key = n_bins, other = n_bins, cnt = 0;            // dropped records sort behind every bin
+    if (c1 >= 0 && c2 >= 0) {
+      int64_t a1 = pos1[i] - one_based, a2 = pos2[i] - one_based;
+      if (a1 < 0 || a2 < 0) f_neg = 1;
+      else if (a1 > chromsizes[c1] || a2 > chromsizes[c2]) f_exc = 1;
+      else {
+        bool keep = true;
+        if (tril_action != CB200_TRIL_NONE && (c1 > c2 || (c1 == c2 && a1 > a2))) {
+          if (tril_action == CB200_TRIL_REFLECT) {
+            const int tc = c1; c1 = c2; c2 = tc;
+            const int64_t ta = a1; a1 = a2; a2 = ta;
+          } else if (tril_action == CB200_TRIL_DROP) keep = false;
+          else { f_tril = 1; keep = false; }
+        }
+        if (keep) {
+          other = chrom_binoffset[c1] + (int)(a1 / binsize);   // bin1
+          key = chrom_binoffset[c2] + (int)(a2 / binsize);     // bin2: first sort key
+          cnt = 1;
+        }
+      }
+    }
+    if (cnt == 0) ++dropped;
+    key_out[i] = key;
+    val_out[i] = make_int2(other, cnt);
+  }
+  if (f_neg) atomicOr(&flags[0], 1);
+  if (f_exc) atomicOr(&flags[1], 1);
+  if (f_tril) atomicOr(&flags[2], 1);
+  dropped = warp_sum(dropped);
+  if ((threadIdx.x & 31) == 0 && dropped) atomicAdd(&flags[3], dropped);
+}
+
+}  // namespace cb200
+
+extern "C" int cb200_bin_pairs(const int32_t* chrom1, const int64_t* pos1, const int32_t* chrom2,
+                               const int64_t* pos2, int64_t n, const int32_t* chrom_binoffset,
+                               const int64_t* chromsizes, int64_t binsize, int32_t one_based,
+                               int32_t tril_action, int32_t n_bins, int32_t* key_out,
+                               cb200_px* val_out, int32_t* flags, void* stream) {
+  if (binsize <= 0 || tril_action < 0 || tril_action > 3) {
+    cb200::set_error_msg("bin_pairs: bad arguments");
+    return -1;
+  }
+  if (n <= 0) return 0;
+  int64_t blocks = cb200::ceil_div64(n, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  cb200::bin_pairs_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      chrom1, pos1, chrom2, pos2, n, chrom_binoffset, chromsizes, binsize, one_based, tril_action, n_bins,
+      key_out, reinterpret_cast<int2*>(val_out), flags);
+  CB_LAUNCH_CHECK("bin_pairs");
+  return 0;
+}

@@ -292,6 +292,21 @@ int cb200_runs_write(const int32_t* keys, const cb200_px* vals, int64_t n,
 int cb200_unpack_pixels(const int32_t* bin1, const cb200_px* val, int64_t n,
                         int64_t* bin1_out, int64_t* bin2_out, int32_t* count_out, void* stream);
 
+/* ---- ingest binning (replaces create/_ingest.py:68-214 _sanitize_records for integer chromosome
+ *      ids and fixed-size bins; the groupby(bin1, bin2).size() of aggregate_records, :452-504, is
+ *      cb200_sort_pairs x2 + cb200_runs_count / cb200_runs_write as for coarsening) ------------- */
+enum { CB200_TRIL_NONE = 0, CB200_TRIL_REFLECT = 1, CB200_TRIL_DROP = 2, CB200_TRIL_RAISE = 3 };
+/* Record i -> key_out[i] = bin2, val_out[i] = {bin1, 1}; records with a chromosome id < 0, dropped
+ * lower-triangle records and records failing a check get key = n_bins, val = {n_bins, 0} (they sort
+ * behind every bin).  flags[0]: some anchor < 0; flags[1]: some anchor > chromosome length;
+ * flags[2]: lower-triangle record seen with CB200_TRIL_RAISE; flags[3]: number of dropped records
+ * (flags must be zero-initialised).  pos is 1-based when one_based != 0. */
+int cb200_bin_pairs(const int32_t* chrom1, const int64_t* pos1, const int32_t* chrom2,
+                    const int64_t* pos2, int64_t n, const int32_t* chrom_binoffset,
+                    const int64_t* chromsizes, int64_t binsize, int32_t one_based,
+                    int32_t tril_action, int32_t n_bins, int32_t* key_out, cb200_px* val_out,
+                    int32_t* flags, void* stream);
+
 /* ---- balanced matrix fetch (replaces cooler.api.matrix: the CSR range query of
  *      core/_rangequery.py:153-368 -- CSRReader, DirectRangeQuery2D, FillLowerRangeQuery2D --
  *      and the weight application of src/cooler/api.py:742-798) ----------------------------- */
