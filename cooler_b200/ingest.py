@@ -50,7 +50,7 @@ def bin_pairs(chrom1_ids, pos1, chrom2_ids, pos2, chromsizes, binsize, *, is_one
 
     def dev_arr(a, dtype, what):
         t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
-        if validate and (t.dtype.is_floating_point or t.dtype == torch.bool):
+        if t.numel() and validate and (t.dtype.is_floating_point or t.dtype == torch.bool):
             if what == "chrom":
                 raise BadInputError("`chrom` column is non-integer. If string, convert to an enumeration first")
             raise BadInputError("Found a non-integer anchor column")
