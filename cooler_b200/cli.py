@@ -5,9 +5,9 @@ Same flags, defaults, messages and exit codes as the reference's click commands
 ``--chunksize`` are accepted and ignored (no process pool: the GPU path must not
 fork after CUDA initialisation).  COOL_PATH is resolved by
 ``cooler_b200.store.open_cooler``: a registered in-memory store, else the real
-``cooler`` package (h5py) if installed, else the built-in read-only HDF5 reader
-(``cooler_b200.h5lite``: ``balance --stdout`` / ``--check`` work on real ``.cool`` files;
-storing a column or writing a new file needs h5py).
+``cooler`` package (h5py) if installed, else the built-in HDF5 subset reader / writer
+(``cooler_b200.h5lite`` / ``h5write``): ``balance`` stores ``bins/<name>`` + stats in the
+file, ``coarsen -o out.cool`` and ``zoomify -o out.mcool [--balance]`` write real files.
 
     python -m cooler_b200.cli balance sample.cool --cis-only
 """
@@ -213,7 +213,7 @@ def coarsen(cool_uri, factor, nproc, chunksize, field, out, append):
         result = coarsen_cooler(clr, None, factor, chunksize=chunksize, nproc=nproc, columns=columns,
                                 dtypes=dtypes, agg=agg)
         store.register(out, result)
-    else:  # pragma: no cover - needs h5py
+    else:
         coarsen_cooler(clr, out, factor, chunksize=chunksize, nproc=nproc, columns=columns,
                        dtypes=dtypes, agg=agg, mode="a" if append else "w")
 
@@ -290,7 +290,7 @@ def zoomify(cool_uri, nproc, chunksize, resolutions, do_balance, balance_args, f
         levels = zoomify_cooler(bases, None, resolutions, chunksize, nproc=nproc, columns=columns,
                                 dtypes=dtypes, agg=agg)
         store.register(outfile, {int(r): c for r, c in levels.items()})
-    else:  # pragma: no cover - needs h5py
+    else:
         zoomify_cooler([cool_uri, *list(base_uri)], outfile, resolutions, chunksize, nproc=nproc,
                        columns=columns, dtypes=dtypes, agg=agg)
     if do_balance:

@@ -149,6 +149,8 @@ class _Obj:
     def __init__(self, rd: _Reader, addr):
         self.rd, self.addr = rd, addr
         self.msgs = []
+        self.moffs = []                                 # file offset of every message body
+        self.version = 2 if rd.bytes(addr, 4) == b"OHDR" else 1
         if rd.bytes(addr, 4) == b"OHDR":
             self._parse_v2(addr)
         else:
@@ -167,6 +169,7 @@ class _Obj:
             while p + 8 <= end and len(self.msgs) < nmsg:
                 mtype, msize, mflags = rd.u(p, 2), rd.u(p + 2, 2), rd.u(p + 4, 1)
                 body = rd.bytes(p + 8, msize)
+                self.moffs.append(p + 8)
                 p += 8 + msize
                 if mtype == 0x10:
                     blocks.append((int.from_bytes(body[:rd.O], "little") + rd.base,
@@ -195,6 +198,7 @@ class _Obj:
                 if p + msize > end:
                     break
                 body = rd.bytes(p, msize)
+                self.moffs.append(p)
                 p += msize
                 if mtype == 0x10:
                     caddr = int.from_bytes(body[:rd.O], "little") + rd.base
@@ -252,6 +256,9 @@ def _decode_values(rd, typ: _Type, shape, raw):
         vals = _read_vlen_strings(rd, raw, n)
         return vals[0] if shape == () else np.array(vals, dtype=object).reshape(shape)
     arr = np.frombuffer(raw, dtype=typ.np_dtype, count=n)
+    if typ.kind == "enum" and set(typ.enum or ()) == {"FALSE", "TRUE"}:      # h5py's encoding of numpy bool
+        arr = arr != typ.enum["FALSE"]
+        return bool(arr[0]) if shape == () else arr.reshape(shape).copy()
     if typ.kind == "string":
         if shape == ():
             return arr[0].decode("utf-8", "replace")
@@ -693,12 +700,16 @@ class File(Group):
             rd.O, rd.L = rd.u(sb + 13, 1), rd.u(sb + 14, 1)
             p = sb + 24 + (4 if ver == 1 else 0)
             rd.base = rd.u(p, rd.O)
+            self._sb = {"off": sb, "ver": ver, "leaf_k": rd.u(sb + 16, 2), "internal_k": rd.u(sb + 18, 2),
+                        "chunk_k": rd.u(sb + 24, 2) if ver == 1 else 32, "eof_off": p + 2 * rd.O,
+                        "eof": rd.u(p + 2 * rd.O, rd.O), "root_entry_off": p + 4 * rd.O}
             p += 4 * rd.O                               # base, free-space, eof, driver info
             root_addr = rd.off_(p + rd.O)               # symbol table entry: name offset, header address
         elif ver in (2, 3):
             rd.O, rd.L = rd.u(sb + 9, 1), rd.u(sb + 10, 1)
             p = sb + 12
             rd.base = rd.u(p, rd.O)
+            self._sb = {"off": sb, "ver": ver}
             root_addr = rd.off_(p + 3 * rd.O)
         else:
             raise H5FormatError(f"unsupported HDF5 superblock version {ver}")

@@ -317,27 +317,24 @@ class CoolerCoarsener:
 
 
 def _as_cooler(obj):
-    if hasattr(obj, "_load_dset"):
-        return obj
+    """A Cooler-like object for a URI / path: the real ``cooler.Cooler`` when the package (h5py)
+    is importable, else the built-in HDF5 reader (``store.H5Cooler``); registered in-memory
+    stores and Cooler-like objects pass through."""
+    from .store import open_cooler
+    return open_cooler(obj)
+
+
+def _create(output_uri, bins, iterator, **kwargs):
+    """``cooler.create.create`` when available (h5py), else the built-in writer (create.py)."""
     try:
-        import cooler  # the real package, when h5py is available
-    except ImportError as e:  # pragma: no cover
-        raise ImportError("opening cooler URIs needs the `cooler` package (h5py); "
-                          "pass a Cooler-like object instead") from e
-    return cooler.Cooler(obj)
+        from cooler.create import create
+    except ImportError:
+        from .create import create_cooler as create
+    return create(output_uri, bins, iterator, **kwargs)
 
 
-def coarsen_cooler(base_uri, output_uri, factor, chunksize, nproc=1, columns=None, dtypes=None,
-                   agg=None, device="cuda", **kwargs):
-    """Coarsen a cooler by an integer factor on the GPU.
-
-    Same arguments as ``cooler.coarsen_cooler`` (_reduce.py:645-749); ``nproc`` is
-    accepted and ignored (no process pool).  ``base_uri`` may be a URI/path (needs the
-    ``cooler`` package) or a Cooler-like object.  With ``output_uri=None`` the result
-    is returned as a ``MemCooler``; otherwise it is written with ``cooler.create``
-    exactly as the reference does (``append=True``, ``symmetric_upper`` propagated).
-    """
-    clr = _as_cooler(base_uri)
+def _coarsen(clr, output_uri, factor, chunksize, nproc, columns, dtypes, agg, device, table, kwargs):
+    """Shared body of coarsen_cooler / zoomify_cooler: returns (MemCooler or None, device table)."""
     factor = int(factor)
     columns = _check_columns(clr, columns, agg)
     dtypes = dict(dtypes or {})
@@ -345,7 +342,7 @@ def coarsen_cooler(base_uri, output_uri, factor, chunksize, nproc=1, columns=Non
     for col in columns:
         dtypes.setdefault(col, input_dtypes[col])
     iterator = CoolerCoarsener(clr, factor, chunksize, columns=columns, agg=agg, batchsize=nproc,
-                               device=device, table=kwargs.pop("table", None))
+                               device=device, table=table)
     symmetric_upper = clr.storage_mode == "symmetric-upper"
     if output_uri is None:
         chunks = list(iterator)
@@ -357,12 +354,30 @@ def coarsen_cooler(base_uri, output_uri, factor, chunksize, nproc=1, columns=Non
                                     cat["count"].astype(dtypes["count"], copy=False),
                                     binsize=iterator.new_binsize, symmetric_upper=symmetric_upper)
         out.device_table = iterator.result_table
-        return out
-    from cooler.create import create  # real writer (h5py)
+        return out, iterator.result_table
+    kwargs = dict(kwargs)
     kwargs.setdefault("append", True)
-    create(output_uri, iterator.new_bins, iterator, dtypes=dtypes, symmetric_upper=symmetric_upper,
-           **kwargs)
-    return None
+    _create(output_uri, iterator.new_bins, iterator, dtypes=dtypes, symmetric_upper=symmetric_upper,
+            **kwargs)
+    return None, iterator.result_table
+
+
+def coarsen_cooler(base_uri, output_uri, factor, chunksize, nproc=1, columns=None, dtypes=None,
+                   agg=None, device="cuda", **kwargs):
+    """Coarsen a cooler by an integer factor on the GPU.
+
+    Same arguments as ``cooler.coarsen_cooler`` (_reduce.py:645-749); ``nproc`` is
+    accepted and ignored (no process pool).  ``base_uri`` may be a URI / path (read by the
+    ``cooler`` package when it is importable, else by the built-in HDF5 reader) or a
+    Cooler-like object.  With ``output_uri=None`` the result is returned as a ``MemCooler``;
+    otherwise it is written like the reference does it -- ``create(..., append=True,
+    symmetric_upper=<propagated>)`` -- through ``cooler.create`` (h5py) when available, else
+    through the built-in writer (``cooler_b200.create`` / ``h5write``).
+    """
+    clr = _as_cooler(base_uri)
+    table = kwargs.pop("table", None)
+    out, _ = _coarsen(clr, output_uri, factor, chunksize, nproc, columns, dtypes, agg, device, table, kwargs)
+    return out
 
 
 def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=None, dtypes=None,
@@ -371,9 +386,11 @@ def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=
 
     Each target resolution is derived from the largest already-available
     resolution that divides it.  Levels are chained on the device: level k's output
-    table feeds level k+1 without a host round trip.  With ``outfile=None`` returns
-    ``{resolution: MemCooler}`` (the base included); otherwise writes an .mcool through
-    the ``cooler`` package like the reference.
+    table feeds level k+1 without a host round trip (the reference re-reads each
+    predecessor from the file).  With ``outfile=None`` returns ``{resolution: MemCooler}``
+    (the base included); otherwise writes the MCOOL v2 layout ``resolutions/<r>`` into
+    ``outfile`` (base levels copied first, _reduce.py:838-854; root attributes ``format`` /
+    ``format-version`` last, 873-877) and returns None.
     """
     if not isinstance(base_uris, (list, tuple)):
         base_uris = [base_uris]
@@ -384,8 +401,14 @@ def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=
             raise ValueError("Cannot zoomify a cooler with variable-size bins")   # cli/zoomify.py
         bases[int(clr.binsize)] = clr
     resn, pred, mult = get_multiplier_sequence(list(resolutions), list(bases))
-    if outfile is not None:  # pragma: no cover - needs h5py
-        raise NotImplementedError("writing .mcool files needs the cooler package; pass outfile=None")
+    if outfile is not None:
+        from . import create as _cr
+        from . import h5write
+        cols = tuple(columns) if columns is not None else ("count",)
+        first = True
+        for res, clr in bases.items():
+            _cr.copy_cooler(clr, f"{outfile}::resolutions/{res}", columns=cols, mode="w" if first else "r+")
+            first = False
     out = {}
     tables = {}
     for i, res in enumerate(resn):
@@ -394,12 +417,18 @@ def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=
             out[res] = bases[res]
             continue
         prev = int(resn[pred[i]])
-        src = out[prev]
-        tab = tables.get(prev)
-        out[res] = coarsen_cooler(src, None, int(mult[i]), chunksize, nproc=nproc, columns=columns,
-                                  dtypes=dtypes, agg=agg, device=device, table=tab)
-        tables[res] = out[res].device_table
-    return out
+        dest = None if outfile is None else f"{outfile}::resolutions/{res}"
+        kw = dict(kwargs)
+        if outfile is not None:
+            kw["mode"] = "r+"
+        lvl, tables[res] = _coarsen(out[prev], dest, int(mult[i]), chunksize, nproc, columns, dtypes, agg,
+                                    device, tables.get(prev), kw)
+        out[res] = lvl if outfile is None else _as_cooler(dest)
+    if outfile is None:
+        return out
+    with h5write.File(outfile, "r+") as fw:
+        fw.attrs.update({"format": "HDF5::MCOOL", "format-version": _cr.FORMAT_VERSION_MCOOL})
+    return None
 
 
 class CoolerMerger:

@@ -278,8 +278,8 @@ class H5Cooler(MemCooler):
 
     Same read protocol as ``cooler.Cooler`` for the hot path (api.py:32-409): columns are
     decoded (gzip + shuffle) on access, so ``balance_cooler`` / ``CoolerCoarsener`` read the
-    pixel table exactly once.  The built-in reader cannot write: ``open('r+')`` (e.g.
-    ``balance_cooler(..., store=True)``) raises -- install h5py + cooler for in-place storage.
+    pixel table exactly once.  ``open('r+')`` (``balance_cooler(..., store=True)``, the
+    ``cooler balance`` CLI) appends through ``cooler_b200.h5write``.
     """
 
     def __init__(self, path, group="/"):
@@ -334,12 +334,26 @@ class H5Cooler(MemCooler):
             raise NotImplementedError("H5Cooler.pixels(join=True)")
         return _Selector(self.root["pixels"], self._ordered(self.root["pixels"], ["bin1_id", "bin2_id", "count"]))
 
+    def _reload(self):
+        from . import h5lite
+        self._file = h5lite.File(self.filename)
+        self.root = self._file[self.group] if self.group not in ("", "/") else self._file
+
     @contextmanager
     def open(self, mode="r", **kwargs):
-        if mode != "r":
-            raise OSError(f"{self.filename}: the built-in HDF5 reader (cooler_b200.h5lite) is read-only; "
-                          "writing columns into a .cool file needs h5py + cooler")
-        yield self.root
+        """``'r'``: the h5lite group.  ``'r+'`` / ``'a'``: the same group of a writable
+        ``h5write.File`` (append-only writer: create_dataset / del / attrs.update); the reader
+        is refreshed when the block ends, like ``Cooler.open`` re-opening the file (api.py:139-150)."""
+        if mode == "r":
+            yield self.root
+            return
+        from . import h5write
+        f = h5write.File(self.filename, "r+")
+        try:
+            yield f[self.group] if self.group not in ("", "/") else f
+        finally:
+            f.close()
+            self._reload()
 
 
 def list_coolers(path):

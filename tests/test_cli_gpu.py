@@ -156,11 +156,111 @@ def test_balance_cli_stdout_on_cool_file():
     want = BAL["gm/defaults"]
     np.testing.assert_array_equal(np.isnan(vals), np.isnan(want))
     np.testing.assert_allclose(vals, want, rtol=1e-5, equal_nan=True)      # printed with %g (6 significant digits)
-    try:
-        import h5py  # noqa: F401
-    except ImportError:
-        res = r.invoke(cli, ["balance", GM_COOL])                        # storing needs h5py
-        assert res.exit_code != 0 and isinstance(res.exception, OSError)
+
+
+def _copy_cool(name, tmp_path):
+    import shutil
+    dst = str(tmp_path / name)
+    shutil.copy(os.path.join(COOL, name), dst)
+    os.chmod(dst, 0o644)
+    return dst
+
+
+def test_balance_cli_stores_weight_in_cool_file(tmp_path):
+    """BASELINE config 1 end to end: `cooler balance file.cool` writes bins/weight + stats into the file
+    (cli/balance.py:283-289), then --check / the exists-guard / --force behave like the reference."""
+    from cooler_b200 import store
+    from cooler_b200.cli import cli
+    from ._h5check import check
+    BAL, META = _golden.balance_golden()
+    path = _copy_cool("hg19.GM12878-MboI.matrix.2000kb.cool", tmp_path)
+    r = CliRunner()
+    res = r.invoke(cli, ["balance", path])
+    assert res.exit_code == 0, (res.output, res.exception)
+    check(path)
+    clr = store.open_cooler(path)
+    with clr.open("r") as g:
+        w = g["bins/weight"][:]
+        at = dict(g["bins/weight"].attrs)
+        px = g["pixels/count"][:]
+    np.testing.assert_array_equal(np.isnan(w), np.isnan(BAL["gm/defaults"]))
+    np.testing.assert_allclose(w, BAL["gm/defaults"], rtol=1e-9, atol=0, equal_nan=True)
+    assert at["converged"] is True and at["ignore_diags"] == 2 and at["mad_max"] == 5 and at["min_nnz"] == 10
+    assert at["cis_only"] is False and at["divisive_weights"] is False
+    assert abs(at["scale"] / 56.94014353567062 - 1) < 1e-9 and abs(at["var"] / 3.7801217049722795e-06 - 1) < 1e-6
+    assert len(px) == 38156 and px.sum() == 100000
+    res = r.invoke(cli, ["balance", path, "--check"])
+    assert res.exit_code == 0 and "is balanced" in res.output
+    res = r.invoke(cli, ["balance", path])
+    assert res.exit_code == 1
+    res = r.invoke(cli, ["balance", path, "--force", "--cis-only", "--name", "weight"])
+    assert res.exit_code == 0, (res.output, res.exception)
+    check(path)
+    with store.open_cooler(path).open("r") as g:
+        np.testing.assert_allclose(g["bins/weight"][:], BAL["gm/cis_only"], rtol=1e-9, atol=0, equal_nan=True)
+        at = dict(g["bins/weight"].attrs)
+    assert at["cis_only"] is True and len(at["scale"]) == 25 and len(at["converged"]) == 25
+    # balance_cooler(store=True) through the API, second column
+    import cooler_b200
+    bias, stats = cooler_b200.balance_cooler(store.open_cooler(path), trans_only=True, store=True, store_name="wt")
+    with store.open_cooler(path).open("r") as g:
+        np.testing.assert_array_equal(g["bins/wt"][:], bias)
+        assert sorted(g["bins"].keys()) == ["chrom", "end", "start", "weight", "wt"]
+
+
+def test_coarsen_and_zoomify_cli_write_files(tmp_path):
+    """`cooler coarsen -o out.cool` and `cooler zoomify -o out.mcool --balance` on real files."""
+    from cooler_b200 import store
+    from cooler_b200.cli import cli
+    from ._h5check import check
+    CO = _golden.coarsen_golden()
+    src = _copy_cool("toy.asymm.2.cool", tmp_path)
+    out = str(tmp_path / "toy.4.cool")
+    r = CliRunner()
+    res = r.invoke(cli, ["coarsen", src, "-k", "2", "-o", out])
+    assert res.exit_code == 0, (res.output, res.exception)
+    check(out)
+    c = store.open_cooler(out)
+
+    def table(clr):
+        return np.stack([np.asarray(clr._load_dset("pixels/" + k)).astype(np.int64)
+                         for k in ("bin1_id", "bin2_id", "count")], 1)
+
+    np.testing.assert_array_equal(table(c), CO["toy.asymm/4"])
+    assert c.binsize == 4 and c.storage_mode == "square" and c.info["nnz"] == len(CO["toy.asymm/4"])
+    assert c.info["sum"] == CO["toy.asymm/4"][:, 2].sum()
+    ind = np.asarray(c._load_dset("indexes/bin1_offset"))
+    np.testing.assert_array_equal(ind, np.searchsorted(CO["toy.asymm/4"][:, 0], np.arange(len(ind))))
+    assert c._load_dset("pixels/count").dtype == np.int32 and c._load_dset("pixels/bin1_id").dtype == np.int64
+    # zoomify the same file into an .mcool, balancing every level that can converge
+    mc = str(tmp_path / "toy.mcool")
+    res = r.invoke(cli, ["zoomify", src, "-r", "4,8,16,32", "-o", mc, "--balance",
+                         "--balance-args", "--mad-max 0 --min-nnz 0 --ignore-diags 0 --max-iters 500"])
+    assert res.exit_code == 0, (res.output, res.exception)
+    check(mc)
+    assert sorted(store.list_coolers(mc)) == sorted(f"/resolutions/{x}" for x in (2, 4, 8, 16, 32))
+    from cooler_b200 import h5lite
+    assert dict(h5lite.File(mc).attrs) == {"format": "HDF5::MCOOL", "format-version": 2}
+    np.testing.assert_array_equal(table(store.open_cooler(mc + "::resolutions/2")), table(store.open_cooler(src)))
+    for res_ in (4, 8, 16, 32):
+        lvl = store.open_cooler(f"{mc}::resolutions/{res_}")
+        np.testing.assert_array_equal(table(lvl), CO[f"toy.asymm/{res_}"])
+        assert lvl.binsize == (res_ if res_ < 32 else None)     # one bin per chromosome: util.get_binsize -> None
+        with lvl.open("r") as g:
+            assert "weight" in g["bins"]
+    # the symmetric-upper .mcool of the reference: re-derive its levels and compare with the file's own
+    m = os.path.join(COOL, "toy.symm.upper.2.mcool")
+    mc2 = str(tmp_path / "toy.symm.mcool")
+    res = r.invoke(cli, ["zoomify", m + "::resolutions/2", "-r", "4,8,16,32", "-o", mc2])
+    assert res.exit_code == 0, (res.output, res.exception)
+    check(mc2)
+    for res_ in (2, 4, 8, 16, 32):
+        a = store.open_cooler(f"{m}::resolutions/{res_}")
+        b = store.open_cooler(f"{mc2}::resolutions/{res_}")
+        np.testing.assert_array_equal(table(a), table(b))
+        for k in ("bins/chrom", "bins/start", "bins/end", "indexes/bin1_offset", "indexes/chrom_offset"):
+            np.testing.assert_array_equal(np.asarray(a._load_dset(k)), np.asarray(b._load_dset(k)))
+        assert b.storage_mode == "symmetric-upper"
 
 
 def test_coarsen_real_cool_files_match_reference_goldens():

@@ -55,9 +55,10 @@ def test_h5cooler_protocol_and_mcool_uri():
     t = _golden.table_of("gm")
     assert b2.dtype == np.int32 and np.array_equal(b2, t["bin2_id"]) and np.array_equal(cnt, t["count"])
     assert len(off) == 1562 and off[-1] == 38156 and co[-1] == 1561
-    with pytest.raises(OSError):
-        with clr.open("r+"):
-            pass
+    before = open(GM, "rb").read()
+    with clr.open("r+") as g:                           # writable through h5write; untouched -> unchanged
+        assert "weight" not in g["bins"]
+    assert open(GM, "rb").read() == before
     m = os.path.join(COOL, "toy.symm.upper.2.mcool")
     assert store.list_coolers(m) == [f"/resolutions/{r}" for r in (16, 2, 32, 4, 8)]
     c4 = store.H5Cooler(m, "/resolutions/4")
