@@ -24,7 +24,7 @@ import numpy as np
 
 from . import store
 from .balance import balance_cooler
-from .reduce import coarsen_cooler, preferred_sequence, zoomify_cooler
+from .reduce import coarsen_cooler, legacy_zoomify, preferred_sequence, zoomify_cooler
 
 HIGLASS_TILE_DIM = 256      # _reduce.py:28
 logger = logging.getLogger("cooler")
@@ -246,15 +246,33 @@ def invoke_balance(args, resolutions, outfile):
 @click.option("--base-uri", "-i", multiple=True, help="Additional base coolers to aggregate from.")
 @click.option("--out", "-o", help="Output file or URI")
 @click.option("--field", type=str, multiple=True, help="Value columns to merge.")
-@click.option("--legacy", is_flag=True, default=False, help="Legacy integer-labeled zoom levels (not supported).")
+@click.option("--legacy", is_flag=True, default=False,
+              help="Use the legacy layout of integer-labeled zoom levels.")
 def zoomify(cool_uri, nproc, chunksize, resolutions, do_balance, balance_args, field, legacy, base_uri, out):
     """Generate a multi-resolution cooler by coarsening on the GPU."""
-    if legacy:
-        raise click.UsageError("--legacy layout is not supported by the B200 path")
     infile, _ = store.parse_cooler_uri(cool_uri)
     outfile = infile.replace(".cool", ".mcool") if out is None else store.parse_cooler_uri(out)[0]
     logger.info(f'Recursively aggregating "{cool_uri}"')
     logger.info(f'Writing to "{outfile}"')
+    if legacy:                                                    # cli/zoomify.py:139-173
+        if store.is_memory_uri(cool_uri):
+            raise click.UsageError("--legacy writes an .mcool file; it needs a file input")
+        n_zooms, zoom_levels = legacy_zoomify(cool_uri, outfile, nproc, chunksize)
+        if do_balance:
+            args = [] if balance_args is None else shlex.split(balance_args)
+            for level, res in reversed(list(zoom_levels.items())):
+                uri = outfile + "::" + str(level)
+                if level == str(n_zooms):
+                    with store.open_cooler(uri).open("r") as grp:
+                        if "weight" in grp["bins"]:
+                            continue
+                logger.info(f"Balancing zoom level {level}, bin size {res}")
+                try:
+                    balance.main(args=[uri, *args], prog_name="cooler")
+                except SystemExit as e:
+                    if (e.code or 0) != 0:
+                        raise e
+        return
     clr = store.open_cooler(cool_uri)
     genome_length = clr.chromsizes.values.sum()
     if clr.binsize:                                               # cli/zoomify.py:176-186

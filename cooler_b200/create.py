@@ -215,7 +215,8 @@ def create_cooler(cool_uri, bins, pixels, columns=None, dtypes=None, metadata=No
 def copy_cooler(src, dst_uri, columns=("count",), mode="w"):
     """Copy one cooler (chroms, bins, pixels, indexes, attributes) into ``dst_uri``.
 
-    The base-resolution copy of ``zoomify_cooler`` (_reduce.py:838-854).  ``src`` is a
+    The base-resolution copy of ``zoomify_cooler`` (_reduce.py:838-854) and, with
+    ``columns=None`` (every pixel column), of ``legacy_zoomify`` (909-914).  ``src`` is a
     Cooler-like object; columns are decoded and re-encoded (the built-in writer has no raw
     chunk copy).
     """
@@ -227,7 +228,7 @@ def copy_cooler(src, dst_uri, columns=("count",), mode="w"):
             for grp_name in ("chroms", "bins", "pixels", "indexes"):
                 out = h5.create_group(grp_name)
                 names = list(g[grp_name].keys())
-                if grp_name == "pixels":
+                if grp_name == "pixels" and columns is not None:
                     names = [c for c in names if c in ("bin1_id", "bin2_id", *columns)]
                 for k in names:
                     d = g[grp_name][k]

@@ -24,9 +24,12 @@ from .store import MemCooler
 from .table import (PixelTable, TableCopy, _ptr, _stream, _use_device, exclusive_scan_i32,
                     indptr_from_sorted, key_bits_for, n_tiles, sort_pairs, swap_key_other)
 
+HIGLASS_TILE_DIM = 256      # _reduce.py:28
+
 __all__ = ["CoolerCoarsener", "coarsen_cooler", "zoomify_cooler", "coarsen_table",
            "CoolerMerger", "merge_coolers", "merge_tables",
-           "get_multiplier_sequence", "preferred_sequence", "ZOOMS_4DN", "get_quadtree_depth"]
+           "get_multiplier_sequence", "preferred_sequence", "ZOOMS_4DN", "get_quadtree_depth",
+           "legacy_zoomify"]
 
 # Resolutions of the 4DN multires standard (_reduce.py:30-44).
 ZOOMS_4DN = [1000, 2000, 5000, 10000, 25000, 50000, 100000, 250000, 500000,
@@ -429,6 +432,39 @@ def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=
     with h5write.File(outfile, "r+") as fw:
         fw.attrs.update({"format": "HDF5::MCOOL", "format-version": _cr.FORMAT_VERSION_MCOOL})
     return None
+
+
+def legacy_zoomify(input_uri, outfile, nproc, chunksize, lock=None, device="cuda"):
+    """Quad-tree tiling in the legacy MCOOL layout ``::0, ::1, ...`` (_reduce.py:880-944).
+
+    The base matrix is copied to level ``n_zooms`` and coarsened by 2 down to level 0; the
+    levels are chained on the device.  Returns ``(n_zooms, {level: binsize})`` and writes the
+    root attributes ``max-zoom``, ``max-zooms`` and one ``<level> -> binsize`` entry per level.
+    """
+    from collections import OrderedDict
+
+    from . import create as _cr
+    from . import h5write
+    clr = _as_cooler(input_uri)
+    n_zooms = get_quadtree_depth(clr.chromsizes, clr.binsize, HIGLASS_TILE_DIM)
+    factor = 2
+    zoom_levels = OrderedDict()
+    level = str(n_zooms)
+    binsize = clr.binsize
+    _cr.copy_cooler(clr, f"{outfile}::{level}", columns=None, mode="w")
+    zoom_levels[level] = binsize
+    src, table = _as_cooler(f"{outfile}::{level}"), None
+    for i in range(n_zooms - 1, -1, -1):
+        binsize *= factor
+        dest = f"{outfile}::{i}"
+        _, table = _coarsen(src, dest, factor, chunksize, nproc, None, None, None, device, table, {"mode": "r+"})
+        src = _as_cooler(dest)
+        zoom_levels[str(i)] = binsize
+    with h5write.File(outfile, "r+") as fw:
+        fw.attrs.update({"max-zoom": n_zooms})
+        fw.attrs["max-zooms"] = n_zooms
+        fw.attrs.update({k: int(v) for k, v in zoom_levels.items()})
+    return n_zooms, zoom_levels
 
 
 class CoolerMerger:

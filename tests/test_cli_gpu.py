@@ -282,3 +282,27 @@ def test_coarsen_real_cool_files_match_reference_goldens():
     want4 = store.open_cooler(m + "::resolutions/4")
     with want4.open() as g:
         np.testing.assert_array_equal(got[:, 2], g["pixels/count"][:])
+
+
+def test_zoomify_cli_legacy_layout(tmp_path):
+    """`cooler zoomify --legacy`: integer-labeled levels ::3 (base) .. ::0 (_reduce.py:880-944)."""
+    from cooler_b200 import h5lite, store
+    from cooler_b200.cli import cli
+    from ._h5check import check
+    CO = _golden.coarsen_golden()
+    src = _copy_cool("hg19.GM12878-MboI.matrix.2000kb.cool", tmp_path)
+    out = str(tmp_path / "legacy.mcool")
+    r = CliRunner()
+    res = r.invoke(cli, ["zoomify", src, "--legacy", "-o", out])
+    assert res.exit_code == 0, (res.output, res.exception)
+    check(out)
+    at = dict(h5lite.File(out).attrs)
+    assert at == {"max-zoom": 3, "max-zooms": 3, "3": 2000000, "2": 4000000, "1": 8000000, "0": 16000000}
+    assert sorted(store.list_coolers(out)) == ["/0", "/1", "/2", "/3"]
+    lvl2 = store.open_cooler(out + "::2")
+    for k in ("bin1_id", "bin2_id", "count"):
+        np.testing.assert_array_equal(np.asarray(lvl2._load_dset("pixels/" + k)), CO[f"gm/x2/{k}"])
+    np.testing.assert_array_equal(np.asarray(lvl2._load_dset("bins/start")), CO["gm/x2/bins_start"])
+    np.testing.assert_array_equal(np.asarray(lvl2._load_dset("bins/end")), CO["gm/x2/bins_end"])
+    sums = [int(np.asarray(store.open_cooler(f"{out}::{i}")._load_dset("pixels/count")).sum()) for i in range(4)]
+    assert sums == [100000] * 4

@@ -366,3 +366,38 @@ def test_zoomify_file_plumbing_with_oracle_coarsener(tmp_path, monkeypatch):
         for k in ("bins/chrom", "bins/start", "bins/end", "indexes/bin1_offset", "indexes/chrom_offset"):
             np.testing.assert_array_equal(np.asarray(a._load_dset(k)), np.asarray(b._load_dset(k)))
         assert b.storage_mode == "symmetric-upper" and b.binsize == a.binsize
+
+
+def test_legacy_zoomify_plumbing_with_oracle_coarsener(tmp_path, monkeypatch):
+    """legacy_zoomify (_reduce.py:880-944): levels ::n .. ::0, root attributes; oracle as the coarsener."""
+    from cooler_b200 import reduce, store
+    from oracle import coarsen_numpy
+
+    class OracleCoarsener(reduce.CoolerCoarsener):
+        def __init__(self, source, factor, chunksize, columns=None, agg=None, batchsize=1, map=map,
+                     device="cuda", table=None):
+            super().__init__(source, factor, chunksize, columns=columns, agg=agg, table=object())
+
+        def __iter__(self):
+            clr = self.clr
+            px = {k: np.asarray(clr._load_dset("pixels/" + k)) for k in ("bin1_id", "bin2_id", "count")}
+            b1, b2, cnt, _ = coarsen_numpy.coarsen_pixels(
+                px, np.asarray(clr._load_dset("bins/chrom")), np.asarray(clr._load_dset("bins/start")),
+                np.asarray(clr._load_dset("bins/end")), clr.chromsizes.values, self.factor)
+            yield {"bin1_id": b1, "bin2_id": b2, "count": cnt}
+
+    monkeypatch.setattr(reduce, "CoolerCoarsener", OracleCoarsener)
+    monkeypatch.setattr(reduce, "HIGLASS_TILE_DIM", 4)            # toy genome: 64 bp, 2 bp bins -> 3 zoom levels
+    src = os.path.join(COOL, "toy.symm.upper.2.mcool") + "::resolutions/2"
+    out = str(tmp_path / "legacy.mcool")
+    n_zooms, levels = reduce.legacy_zoomify(src, out, 1, 1000)
+    assert n_zooms == 3 and dict(levels) == {"3": 2, "2": 4, "1": 8, "0": 16}
+    check(out)
+    at = dict(h5lite.File(out).attrs)
+    assert at == {"max-zoom": 3, "max-zooms": 3, "3": 2, "2": 4, "1": 8, "0": 16}
+    assert sorted(store.list_coolers(out)) == ["/0", "/1", "/2", "/3"]
+    m = os.path.join(COOL, "toy.symm.upper.2.mcool")
+    for lvl, res in levels.items():
+        a, b = store.open_cooler(f"{m}::resolutions/{res}"), store.open_cooler(f"{out}::{lvl}")
+        for k in ("pixels/bin1_id", "pixels/bin2_id", "pixels/count", "bins/start", "bins/end"):
+            np.testing.assert_array_equal(np.asarray(a._load_dset(k)), np.asarray(b._load_dset(k)))
