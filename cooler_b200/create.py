@@ -18,7 +18,7 @@ from datetime import datetime
 
 import numpy as np
 
-from . import h5write
+from . import h5lite, h5write
 from .store import parse_cooler_uri
 
 __all__ = ["create_cooler", "copy_cooler", "BadInputError", "MAGIC", "MAGIC_MCOOL"]
@@ -46,14 +46,22 @@ def _validate_chunk(chunk, n_bins, boundscheck, triucheck, dupcheck, ensure_sort
                                 "Check whether your bin table is correct.")
     if triucheck and np.any(b1 > b2):
         raise BadInputError("Found bin1_id greater than bin2_id")
+    d1 = np.diff(b1)
+    in_order = bool(np.all((d1 > 0) | ((d1 == 0) & (b2[1:] >= b2[:-1])))) if len(b1) > 1 else True
     if dupcheck and len(b1) > 1:
-        order = np.lexsort((b2, b1))
-        s1, s2 = b1[order], b2[order]
-        dup = (s1[1:] == s1[:-1]) & (s2[1:] == s2[:-1])
-        if dup.any():
+        if in_order:                                   # lexsorted chunk (the usual case): duplicates are adjacent
+            dup = (d1 == 0) & (b2[1:] == b2[:-1])
+            k = np.flatnonzero(dup)[:5] + 1
+        else:
+            order = np.lexsort((b2, b1))
+            s1, s2 = b1[order], b2[order]
+            dup = (s1[1:] == s1[:-1]) & (s2[1:] == s2[:-1])
             k = order[1:][dup][:5]
+        if dup.any():
             rows = "\n".join(f"{i}\t{b1[i]}\t{b2[i]}" for i in k)
             raise BadInputError("Found duplicate pixels:\n" + rows)
+    if ensure_sorted and in_order:
+        return chunk
     if ensure_sorted:
         order = np.lexsort((b2, b1))
         chunk = {k: np.asarray(v)[order] for k, v in chunk.items()}
@@ -217,8 +225,8 @@ def copy_cooler(src, dst_uri, columns=("count",), mode="w"):
 
     The base-resolution copy of ``zoomify_cooler`` (_reduce.py:838-854) and, with
     ``columns=None`` (every pixel column), of ``legacy_zoomify`` (909-914).  ``src`` is a
-    Cooler-like object; columns are decoded and re-encoded (the built-in writer has no raw
-    chunk copy).
+    Cooler-like object: columns of a file read by h5lite are copied chunk by chunk without
+    re-encoding (like ``h5py.Group.copy``); other sources are read and encoded.
     """
     file_path, group_path = parse_cooler_uri(dst_uri)
     opts = {"compression": "gzip", "compression_opts": 6, "shuffle": True}
@@ -232,6 +240,9 @@ def copy_cooler(src, dst_uri, columns=("count",), mode="w"):
                     names = [c for c in names if c in ("bin1_id", "bin2_id", *columns)]
                 for k in names:
                     d = g[grp_name][k]
+                    if isinstance(d, h5lite.Dataset):                    # file source: raw chunk copy (h5py's src.copy)
+                        out.copy_dataset(d, k)
+                        continue
                     enum = getattr(d, "enum", None)
                     attrs = dict(getattr(d, "attrs", {}) or {})
                     out.create_dataset(k, data=np.asarray(d[:]), enum=enum, attrs=attrs or None, **opts)

@@ -593,6 +593,10 @@ class Group:
             raise TypeError(f"'{path}' is not a group")
         return g
 
+    def copy_dataset(self, src, name):
+        """Raw copy of an ``h5lite.Dataset`` (chunks are not re-encoded); see ``_copy_dataset_raw``."""
+        return _copy_dataset_raw(self, name, src)
+
     def _target(self, name):
         parts = [p for p in str(name).split("/") if p]
         grp = self if len(parts) == 1 else self.require_group("/".join(parts[:-1]))
@@ -632,6 +636,50 @@ class Group:
         ds.append(arr)
         ds.close(attrs)
         return Dataset(self._f, grp._state, leaf)
+
+
+def _copy_dataset_raw(dst_group, name, src):
+    """Copy the h5lite dataset ``src`` into ``dst_group`` without re-encoding its chunks.
+
+    The header messages (dataspace, datatype, fill value, filter pipeline) are taken verbatim and the
+    stored chunk bytes are copied as they are, like ``h5py.Group.copy``; attributes are re-encoded
+    from their values (vlen strings live in the source file's global heap).  Falls back to a
+    decode / encode copy for layouts other than version-3 chunked / contiguous.
+    """
+    f = dst_group._f
+    grp, leaf = dst_group._target(name)
+    rd, lay = src._rd, src._layout
+    attrs = {k: v for k, v in dict(src.attrs).items() if v is not None}
+    keep = [m for m in src._obj.msgs if m[0] in (0x01, 0x03, 0x05, 0x0B)]
+    if src._obj.version != 1 or lay[0] != 3 or lay[1] not in (1, 2) or len(src.shape) != 1 or \
+            any(len(b) % 8 for _, _, b in keep):
+        return grp.create_dataset(leaf, data=src[:], enum=src.enum, attrs=attrs or None)
+    if lay[1] == 2:
+        cdims, chunks = src._chunk_index()
+        es = struct.unpack_from("<I", lay, 3 + rd.O + 4)[0]
+        entries = []
+        for offs, addr, nbytes, mask in sorted(chunks, key=lambda c: c[0]):
+            entries.append((offs[0], f._out.append(rd.bytes(addr, nbytes)), nbytes, mask))
+        if entries:
+            keys = [struct.pack("<IIQQ", nb, mk, off, 0) for off, _, nb, mk in entries]
+            keys.append(struct.pack("<IIQQ", 0, 0, entries[-1][0], es))
+            btree = _build_btree(f._out, 1, f._chunk_k, keys, [a for _, a, _, _ in entries])
+        else:
+            btree = _UNDEF
+        layout = _pad8(struct.pack("<BBBQII", 3, 2, 2, btree, cdims[0], es))
+    else:
+        addr = int.from_bytes(lay[2:2 + rd.O], "little")
+        size = int.from_bytes(lay[2 + rd.O:2 + rd.O + rd.L], "little")
+        new = _UNDEF if addr == _UNDEF or size == 0 else f._out.append(rd.bytes(addr + rd.base, size))
+        layout = _pad8(struct.pack("<BBQQ", 3, 1, new, size))
+    msgs = [(t, fl, b) for t, fl, b in keep] + [(0x08, 0, layout)]
+    if attrs:
+        msgs += _enc_attrs(f._out, attrs)
+    addr, _ = _write_ohdr(f._out, msgs)
+    f._session[addr] = msgs
+    grp._state.links[leaf] = addr
+    f._touch(grp._state)
+    return Dataset(f, grp._state, leaf)
 
 
 class File(Group):

@@ -401,3 +401,22 @@ def test_legacy_zoomify_plumbing_with_oracle_coarsener(tmp_path, monkeypatch):
         a, b = store.open_cooler(f"{m}::resolutions/{res}"), store.open_cooler(f"{out}::{lvl}")
         for k in ("pixels/bin1_id", "pixels/bin2_id", "pixels/count", "bins/start", "bins/end"):
             np.testing.assert_array_equal(np.asarray(a._load_dset(k)), np.asarray(b._load_dset(k)))
+
+
+def test_copy_cooler_is_a_raw_chunk_copy(tmp_path):
+    """copy_cooler from a file: header messages and stored chunk bytes are carried over unchanged."""
+    m = os.path.join(COOL, "toy.symm.upper.2.mcool")
+    src = H5Cooler(m, "/resolutions/2")
+    out = str(tmp_path / "raw.cool")
+    create.copy_cooler(src, out, mode="w")
+    check(out)
+    a, b = h5lite.File(m)["resolutions/2"], h5lite.File(out)
+    for k in ("bins/chrom", "pixels/bin1_id", "pixels/count", "chroms/name", "indexes/bin1_offset"):
+        ma = {t: body for t, _f, body in a[k]._obj.msgs}
+        mb = {t: body for t, _f, body in b[k]._obj.msgs}
+        for t in (0x01, 0x03, 0x05, 0x0B):
+            assert ma[t] == mb[t], (k, hex(t))
+        ca, cb = a[k]._chunk_index()[1], b[k]._chunk_index()[1]
+        assert [c[0] for c in ca] == [c[0] for c in cb] and [c[2:] for c in ca] == [c[2:] for c in cb]
+        assert all(a._rd.bytes(x[1], x[2]) == b._rd.bytes(y[1], y[2]) for x, y in zip(ca, cb))
+    assert b["bins/chrom"].enum == a["bins/chrom"].enum
