@@ -8,7 +8,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcooler_b200.so")
+# CB200_LIB selects another build of the same ABI (e.g. a far-field row-block size variant made by
+# `python -m cooler_b200.build --far-row-shift 13`); default: the in-tree library.
+LIB_PATH = os.environ.get("CB200_LIB") or os.path.join(_HERE, "libcooler_b200.so")
 
 KEEP_ALL, KEEP_CIS, KEEP_TRANS, KEEP_BAND_NEAR, KEEP_BAND_FAR = 0, 1, 2, 3, 4
 
@@ -66,7 +68,9 @@ class FarUnit(C.Structure):
     _fields_ = [("copy", C.c_int32), ("rb", C.c_int32), ("t0", C.c_int32), ("t1", C.c_int32)]
 
 
-FAR_ROW_SHIFT = 14
+def far_row_shift():
+    """log2 rows per far-field block of the loaded library (CB200_FAR_ROW_SHIFT, build-time)."""
+    return int(load().cb200_far_row_shift())
 
 
 _P, _I32, _I64, _SZ = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t
@@ -95,6 +99,7 @@ SIGNATURES = {
     "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
     "cb200_set_tuning": (C.c_int, [_I32, _I32]),
     "cb200_set_far_tuning": (C.c_int, [_I32]),
+    "cb200_far_row_shift": (C.c_int, []),
     "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_combine": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_update": (C.c_int, [C.POINTER(Ice), _I32, _I32, _P]),

@@ -19,8 +19,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .table import (FAR_ROWS, PixelTable, TableCopy, _new_px, _ptr, _stream, _use_device,  # noqa: F401
-                    far_blocks, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays,
+from .table import (PixelTable, TableCopy, _new_px, _ptr, _stream, _use_device,  # noqa: F401
+                    far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays,
                     strip_partition, swap_key_other, transpose_from)
 
 __all__ = ["balance_cooler", "balance_table", "balance_arrays", "ConvergenceWarning", "IceProblem"]
@@ -123,7 +123,7 @@ class IceProblem:
         self.table = table
         self.use_smem = use_smem
         self.far_copies = []
-        self.far_col_shift = int(far_col_shift or os.environ.get("CB200_FAR_COL_SHIFT", 12))
+        self.far_col_shift = int(far_col_shift or os.environ.get("CB200_FAR_COL_SHIFT", 13))
         self.far_warps = int(far_warps or os.environ.get("CB200_FAR_WARPS", 16))
         if peer_reduce is None:
             peer_reduce = os.environ.get("CB200_PEER_REDUCE", "1") != "0"
@@ -264,7 +264,7 @@ class IceProblem:
             peer_reduce = os.environ.get("CB200_PEER_REDUCE", "1") != "0"
         self.peer_reduce = peer_reduce
         self.strip_shift, self.band, self.csr, self.csc = None, False, None, None
-        self.far_copies, self.far_col_shift, self.far_warps = [], 12, 16
+        self.far_copies, self.far_col_shift, self.far_warps = [], 13, 16
         ndiag = int(ignore_diags) if ignore_diags else 0
         keep = _lib.KEEP_CIS if cis_only else _lib.KEEP_ALL
         marg = torch.zeros((2, n_bins), dtype=torch.int64, device=dev)
@@ -436,7 +436,7 @@ class IceState:
                 farr[k].rb0, farr[k].n_rb, farr[k].j0, farr[k].n_j = f.rb0, f.n_rb, f.j0, f.n_j
                 farr[k].rb_unit = t["far_rb_unit"][k].data_ptr()
             t["far_copies"] = torch.frombuffer(bytearray(bytes(farr)), dtype=torch.uint8).to(dev)
-            t["far_parts"] = torch.empty(max(n_far_units, 1) * FAR_ROWS, dtype=_F64, device=dev)
+            t["far_parts"] = torch.empty(max(n_far_units, 1) * far_rows(), dtype=_F64, device=dev)
             t["far_claim"] = torch.zeros(2, dtype=torch.int64, device=dev)
         self.n_far_units = n_far_units
         # multi-GPU: local s vectors live in peer-mapped symmetric memory (double-buffered) and

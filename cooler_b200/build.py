@@ -28,11 +28,17 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not _stale():
+def build(force=False, verbose=False, far_row_shift=None):
+    """Build the library.  ``far_row_shift`` (12..14) builds a variant with another far-field
+    row-block size next to it (``libcooler_b200_rs<k>.so``; select it with ``CB200_LIB``)."""
+    out, extra = OUT, []
+    if far_row_shift is not None:
+        out = os.path.join(_HERE, f"libcooler_b200_rs{int(far_row_shift)}.so")
+        extra = [f"-DCB200_FAR_ROW_SHIFT_VALUE={int(far_row_shift)}"]
+    elif not force and not _stale():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", OUT] + [os.path.join(SRC_DIR, s) for s in SOURCES]
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", out] + [os.path.join(SRC_DIR, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -41,8 +47,9 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    rs = int(sys.argv[sys.argv.index("--far-row-shift") + 1]) if "--far-row-shift" in sys.argv else None
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, far_row_shift=rs))

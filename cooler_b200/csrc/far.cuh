@@ -5,12 +5,12 @@
 // through L1/L2 cost one 32-byte L2 sector per 8-byte pixel (L2-bound at ~0.5 of the HBM
 // rate), and column strips need one partial sum per (row, strip) although such a segment
 // holds 1-2 pixels.  Here the far pixels are blocked in BOTH dimensions: a persistent CTA owns
-// 16384 rows whose sums stay in shared memory while it walks along the column tiles of that
+// R = 1 << CB200_FAR_ROW_SHIFT rows (4096) whose sums stay in shared memory while it walks along the column tiles of that
 // row block, staging the C-wide slice of w of the next tile with cp.async while the current
 // one is consumed.  Records carry block-local (row, column) ids, so there is no row pointer
 // per (row, tile).
 //
-// Warp k owns rows [k, k+1) * 16384 / WARPS of the block; the records of one (tile, warp
+// Warp k owns rows [k, k+1) * R / WARPS of the block; the records of one (tile, warp
 // slice) = "slot" are sorted by row and cut into 32 equal contiguous pieces, one per lane,
 // stored lane-interleaved so that every warp load is one coalesced 512-byte chunk.  A lane
 // walks through its piece sequentially: it sums a run of equal rows in a register and adds
@@ -19,7 +19,7 @@
 // segmented scan over the 32 lanes.  A run that ends inside a lane's piece ends nowhere
 // else, so every accumulator is updated by exactly one lane per phase (pieces, then the
 // merge, separated by __syncwarp): no atomics, fixed summation order,
-// bit-reproducible.  Padding records (row id 16384 = a dummy accumulator) fill the last chunk
+// bit-reproducible.  Padding records (row id R = a dummy accumulator) fill the last chunk
 // of a slot.
 #pragma once
 #include "walk.cuh"

@@ -344,6 +344,8 @@ int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1) {
   return 0;
 }
 
+int cb200_far_row_shift(void) { return CB200_FAR_ROW_SHIFT; }
+
 int cb200_set_far_tuning(int32_t far_unroll) {
   if (far_unroll != 0 && far_unroll != 1 && far_unroll != 2 && far_unroll != 4 && far_unroll != 8) return -1;
   g_far_unroll = far_unroll;
@@ -353,14 +355,20 @@ int cb200_set_far_tuning(int32_t far_unroll) {
 // K3 over the far-field blocks (far.cuh): one persistent CTA per SM claims units.
 static int ice_sweep_far(const cb200_ice* st, void* stream) {
   if (st->n_far_units <= 0) return 0;
-  if (st->far_col_shift < 1 || st->far_col_shift > 12 || (st->far_warps != 16 && st->far_warps != 32)) {
-    set_error_msg("ice_sweep: far_col_shift must be in 1..12 and far_warps 16 or 32");
+  if (st->far_col_shift < 1 || st->far_col_shift > 13 || (st->far_warps != 16 && st->far_warps != 32)) {
+    set_error_msg("ice_sweep: far_col_shift must be in 1..13 and far_warps 16 or 32");
     return -1;
   }
   const size_t smem = ((size_t)FAR_ACC + 2 * ((size_t)1 << st->far_col_shift)) * sizeof(double);
+  constexpr size_t kSmemLimit = 227 * 1024;        // opt-in maximum of dynamic shared memory per CTA on sm_100
+  if (smem > kSmemLimit) {
+    set_error_msg("ice_sweep: far-field row sums + two column tiles exceed 227 KB of shared memory");
+    return -1;
+  }
   static bool attr_done = false;
   if (!attr_done) {
-    const int mx = (int)(((size_t)FAR_ACC + 2 * 4096) * sizeof(double));
+    const size_t want = ((size_t)FAR_ACC + 2 * 8192) * sizeof(double);
+    const int mx = (int)(want < kSmemLimit ? want : kSmemLimit);
     CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));

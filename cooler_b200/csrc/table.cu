@@ -84,7 +84,7 @@ __global__ void strip_finish_kernel(const int32_t* __restrict__ keys, const int2
 }
 
 // Far-field blocks: see cb200_far_copy in the header.  The input is sorted by
-// (row >> 14, other >> col_shift, row, other); every element becomes an 8-byte record with
+// (row >> RS, other >> col_shift, row, other); every element becomes an 8-byte record with
 // block-local coordinates plus its slot id (row block, column tile, warp row slice).
 __global__ void far_finish_kernel(const int32_t* __restrict__ rows, const int2* __restrict__ vals,
                                   int64_t n, int col_shift, int rb0, int j0, int n_j, int warps,
@@ -117,7 +117,7 @@ __global__ void far_slot_chunks_kernel(const int64_t* __restrict__ ptr_rec, int6
 __global__ void far_fill_kernel(int2* __restrict__ px_out, int64_t n_total) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += stride)
-    px_out[i] = make_int2((int)((1u << CB200_FAR_ROW_SHIFT) << 16), 0);   // padding record: row id 16384 (dummy), count 0
+    px_out[i] = make_int2((int)((1u << CB200_FAR_ROW_SHIFT) << 16), 0);   // padding record: row id R (dummy), count 0
 }
 
 // Record i of slot s (j-th of the slot) goes to lane j / L, position j % L of that lane's

@@ -225,8 +225,9 @@ def strip_partition(key_other, val_rowcount, n, n_rows, shift):
     return subs
 
 
-FAR_ROW_SHIFT = _lib.FAR_ROW_SHIFT      # rows per far-field block = 1 << 14 (csrc/far.cuh)
-FAR_ROWS = 1 << FAR_ROW_SHIFT
+def far_rows():
+    """Rows per far-field block of the loaded library (1 << CB200_FAR_ROW_SHIFT, csrc/far.cuh)."""
+    return 1 << _lib.far_row_shift()
 
 
 class FarCopy:
@@ -245,13 +246,14 @@ class FarCopy:
 def far_blocks(key_other, val_rowcount, n, n_bins, col_shift, warps):
     """Row-ordered stream (key = gathered bin, val = {row, count}) -> FarCopy.
 
-    Two stable radix sorts bring the records into (row >> 14, other >> col_shift, row,
+    Two stable radix sorts bring the records into (row >> RS, other >> col_shift, row,
     other) order: first on the column-tile bits of the gathered bin, then -- after swapping
     key and other -- on the row-block bits of the row."""
     dev = key_other.device
     n = int(n)
     if n == 0:
         return None
+    FAR_ROW_SHIFT = _lib.far_row_shift()
     n_j_all = ((max(n_bins, 1) - 1) >> col_shift) + 1
     n_rb_all = ((max(n_bins, 1) - 1) >> FAR_ROW_SHIFT) + 1
     ks, vs = sort_pairs(key_other[:n], val_rowcount, key_bits_for(n_j_all), key_shift=col_shift)

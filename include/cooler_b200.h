@@ -85,11 +85,11 @@ int cb200_swap_key_other(const int32_t* keys, const cb200_px* vals, int64_t n,
 int cb200_strip_finish(const int32_t* keys, const cb200_px* vals, int64_t n, int32_t shift,
                        const int64_t* pad_before, cb200_px* px_out, int32_t* rows_out,
                        void* stream);
-/* Far-field blocks: elements (key = row, val = {other, count}) sorted by (row >> 14,
- * other >> col_shift, row, other) -> records {swz(row & 16383) << 16 | (other & (C-1)), count}
+/* Far-field blocks: elements (key = row, val = {other, count}) sorted by (row >> RS,
+ * other >> col_shift, row, other) -> records {swz(row & (R - 1)) << 16 | (other & (C-1)), count}
  * (swz: bank swizzle of the row id inside its warp slice, see far_swizzle in csrc/far.cuh)
- * and the slot id g = (((row >> 14) - rb0) * n_j + (other >> col_shift) - j0) * warps
- * + ((row & 16383) * warps >> 14) of every element (non-decreasing; cb200_indptr_from_sorted
+ * and the slot id g = (((row >> RS) - rb0) * n_j + (other >> col_shift) - j0) * warps
+ * + ((row & (R - 1)) * warps >> RS) of every element (non-decreasing; cb200_indptr_from_sorted
  * on g gives cb200_far_copy.ptr). */
 int cb200_far_finish(const int32_t* rows, const cb200_px* vals, int64_t n, int32_t col_shift,
                      int32_t rb0, int32_t j0, int32_t n_j, int32_t warps,
@@ -101,7 +101,7 @@ int cb200_far_slot_chunks(const int64_t* ptr_rec, int64_t n_slots, int32_t* nch_
  * records are cut into 32 contiguous pieces of L = 2 * n_chunks(s) records (lane l gets records
  * [l L, (l+1) L)), and chunk c holds records 2c, 2c+1 of every lane at positions 2 lane,
  * 2 lane + 1 -- one coalesced 128-bit load per lane.  Unused positions hold padding records
- * {16384 << 16, 0}.  px_out has total_chunks * 64 + 2 records. */
+ * {R << 16, 0}.  px_out has total_chunks * 64 + 2 records. */
 int cb200_far_interleave(const cb200_px* rec, const int32_t* slot, const int64_t* ptr_rec,
                          const int64_t* chunk_ptr, int64_t n, int64_t total_chunks, cb200_px* px_out,
                          void* stream);
@@ -170,18 +170,23 @@ typedef struct {
 
 /* Far-field blocks (large, very sparse matrices: the gathered bias vector is far larger
  * than L1 and (row, column strip) segments hold only a few pixels).  The far pixels of a
- * copy are re-ordered by (row block = row >> 14, column tile = other >> col_shift, row,
- * other) and stored as records {(row & 16383) << 16 | (other & (C - 1)), count},
+ * copy are re-ordered by (row block = row >> RS, column tile = other >> col_shift, row,
+ * other), RS = CB200_FAR_ROW_SHIFT, R = 1 << RS rows per block, and stored as records {(row & (R - 1)) << 16 | (other & (C - 1)), count},
  * C = 1 << col_shift.  A persistent CTA owns a unit = (row block, run of non-empty column
- * tiles): it keeps the 16384 row sums in shared memory and stages the C-wide slice of the
+ * tiles): it keeps the R row sums in shared memory and stages the C-wide slice of the
  * bias vector of one tile after the other (double-buffered cp.async).  Warp k owns the rows
- * [k, k+1) * 16384 / far_warps of the block; the records of one (row block, tile, warp slice)
+ * [k, k+1) * R / far_warps of the block; the records of one (row block, tile, warp slice)
  * = slot are stored as lane-interleaved 64-record chunks (cb200_far_interleave): every lane
  * sums the runs of equal rows of its own contiguous piece and adds them to the accumulators;
  * lane-boundary runs are merged once per slot by a warp-level segmented scan -- no atomics,
- * fixed summation order.  Unit u writes its row sums to far_parts[u * 16384 ...]; the
+ * fixed summation order.  Unit u writes its row sums to far_parts[u * R ...]; the
  * per-bin kernels add the units of a row block in order. */
-enum { CB200_FAR_ROW_SHIFT = 14 };
+#ifndef CB200_FAR_ROW_SHIFT_VALUE
+#define CB200_FAR_ROW_SHIFT_VALUE 12       /* build-time: log2 rows per far-field block (11..14); 12 measured best */
+#endif
+enum { CB200_FAR_ROW_SHIFT = CB200_FAR_ROW_SHIFT_VALUE };
+/* The value this library was built with (hosts size far_parts and sort keys from it). */
+int cb200_far_row_shift(void);
 typedef struct {
   const cb200_px* px;        /* [n_chunks * 64] (+2 pad) lane-interleaved records, see above */
   const int64_t*  ptr;       /* [n_rb * n_j * far_warps + 1] first CHUNK of every slot (row block, column tile, warp row slice) */
@@ -233,10 +238,10 @@ typedef struct {
   const cb200_far_copy* far_copies;   /* DEVICE array */
   const cb200_far_unit* far_units;    /* DEVICE array, ordered by (copy, row block, t0) */
   const int32_t* far_tiles;           /* column tile of every non-empty (row block, tile), grouped by unit */
-  double*  far_parts;                 /* [n_far_units * 16384] */
+  double*  far_parts;                 /* [n_far_units * R], R = 1 << CB200_FAR_ROW_SHIFT */
   int64_t* far_claim;                 /* [2] zero-initialised (self re-arming) */
   int32_t  n_far_units;
-  int32_t  far_col_shift;             /* log2 C, 4..12 */
+  int32_t  far_col_shift;             /* log2 C, 1..13; (rows + 2 C) * 8 B must fit the 227 KB of shared memory */
   int32_t  far_warps;                 /* 16 or 32: warps per CTA = row slices per block */
 } cb200_ice;
 
