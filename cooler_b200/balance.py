@@ -156,7 +156,7 @@ class IceProblem:
         # layout of the sweep: whole copies, column strips, or diagonal band strips + far rest
         self.strip_shift, self.band = choose_layout(n_bins, csr.nnz, strip_bins, band)
         sh = self.strip_shift
-        if band == "allblocks":                   # every pixel through the 2-D blocked kernel (csrc/far.cuh)
+        if band == "allblocks" or self.band == "allblocks":   # every pixel through the 2-D blocked kernel (csrc/far.cuh)
             self.band, self.strip_shift = "allblocks", None
             if cval is None:
                 ckeys, cval = swap_key_other(ckeys, csc.px, csc.nnz)
@@ -211,8 +211,8 @@ class IceProblem:
         packed, filtered, radix-sorted into its own bin2-major copy and marginalised on the main
         stream.  Every chunk contributes a bin1-major and a bin2-major sub-copy (the column sums
         of the chunks add up exactly like column strips or multi-GPU shards), so nothing has to
-        wait for the whole table.  Returns None when the layout needs column strips (large
-        n_bins): the caller then uses the two-step path (PixelTable + IceProblem).
+        wait for the whole table.  Returns None when the layout needs column strips or far-field
+        blocks (large n_bins): the caller then uses the two-step path (PixelTable + IceProblem).
         """
         dev = _use_device(device)
         off_t = bin1_offset if isinstance(bin1_offset, torch.Tensor) else torch.from_numpy(
@@ -230,7 +230,8 @@ class IceProblem:
         nnz = int(b2_t.numel())
         if n_bins >= 2**31 - 1:
             raise ValueError("n_bins must fit int32")
-        if choose_layout(n_bins, nnz, None)[0] is not None or nnz == 0:
+        lay = choose_layout(n_bins, nnz, None)
+        if lay[0] is not None or lay[1] or nnz == 0:
             return None
         chrom_offset = np.asarray(chrom_offset, dtype=np.int64)
         info = _TableInfo(n_bins, chrom_offset, dev, row_range or (0, n_bins))
@@ -317,10 +318,12 @@ class IceProblem:
 L1_RESIDENT_BINS = 49_152      # bias vectors up to 384 KB are served well enough by L1 + L2
 DEFAULT_STRIP_BINS = 16_384    # 128 KB of float64 bias per strip: stays in the SM's L1
 MIN_PIXELS_PER_ROW_STRIP = 16  # below this the per-(row, strip) bookkeeping costs more than it saves
+BLOCKS_MIN_BINS = 1 << 20      # sparse tables with at least this many bins use the 2-D blocked layout (csrc/far.cuh)
 
 
 def choose_layout(n_bins, nnz_eff, strip_bins=None, band=None):
-    """(log2 strip width in bins | None, band: bool) -- how the sweep gathers the bias.
+    """(log2 strip width in bins | None, band: False | True | "blocks" | "allblocks") -- how the
+    sweep gathers the bias.
 
     The sweep gathers bias[other] per pixel.  When the bias vector is much larger than
     L1 every gather costs a 32-byte L2 sector per 8-byte pixel and L2 bandwidth, not
@@ -329,7 +332,8 @@ def choose_layout(n_bins, nnz_eff, strip_bins=None, band=None):
     partial sum per (row, strip).  That pays while (row, strip) segments stay long
     ("strips": every strip).  For very sparse far fields (1 kb matrices) only the band
     of strips around the diagonal is cut into strips and the far remainder stays one
-    row-ordered copy gathered through L2 ("band").
+    row-ordered copy gathered through L2 ("band"), or -- the automatic choice from 2**20 bins
+    on -- every pixel goes through the 2-D blocked kernel ("allblocks", csrc/far.cuh).
     """
     if strip_bins == 0:
         return None, False
@@ -345,9 +349,11 @@ def choose_layout(n_bins, nnz_eff, strip_bins=None, band=None):
     sparse = nnz_eff < MIN_PIXELS_PER_ROW_STRIP * n_bins * n_strips or n_strips > 1024
     if band is None:
         if auto and sparse:
-            # measured (tools/tune_sweep.py, 1 kb shard): band strips gain ~7 % per pass over
-            # whole copies but cost two more filter passes at build time -> not the default
-            return None, False
+            # measured on the three kinds of 1 kb shards (tools/tune_sweep.py, profiles/r01d_tune_1kb_*):
+            # every pixel through the 2-D blocked kernel (4096 rows x 8192 columns) 1.56 / 1.42 / 1.42 ms
+            # against 2.29 / 1.98 / 1.36 ms for whole copies gathered through L2; band strips gain
+            # ~7 % over whole copies but cost two more filter passes -> never the default
+            return None, ("allblocks" if n_bins >= BLOCKS_MIN_BINS else False)
         band = sparse
     return shift, (band if band in ("blocks", "allblocks") else bool(band))
 

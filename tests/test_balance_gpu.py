@@ -428,3 +428,37 @@ def test_streamed_build_large_synthetic_matches_table_path(mode):
         assert ib["n_subcopies"] >= 8 and ia["passes"] == ib["passes"] and ib["nnz_eff"] == ia["nnz_eff"]
         np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
         np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
+
+
+def test_auto_layout_uses_blocks_for_huge_sparse_tables():
+    """From 2**20 bins on, sparse tables are swept by the 2-D blocked kernel automatically
+    (balance.choose_layout); results equal the whole-copy sweep, and balance_arrays (the call
+    balance_cooler makes) takes the same layout through the two-step build."""
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    from cooler_b200.balance import BLOCKS_MIN_BINS, choose_layout
+    rng = np.random.default_rng(5)
+    sizes = [600_000, 400_000, BLOCKS_MIN_BINS - 1_000_000 + 4097]
+    chrom_offset = np.r_[0, np.cumsum(sizes)].astype(np.int64)
+    n = int(chrom_offset[-1])
+    assert n >= BLOCKS_MIN_BINS
+    m = 24 * n
+    i = rng.integers(0, n, m)
+    d = np.where(rng.random(m) < 0.5, rng.integers(0, 200, m), rng.integers(0, n, m))
+    j = np.minimum(i + d, n - 1)
+    key = np.unique(i.astype(np.int64) * n + j)
+    b1, b2 = key // n, key % n
+    hidden = rng.lognormal(0, 0.3, n)
+    cnt = (1 + rng.poisson(2 * hidden[b1] * hidden[b2])).astype(np.int32)
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    assert choose_layout(n, len(b1)) == (None, "allblocks")
+    tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
+    a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0)
+    b, sb, ib = cooler_b200.balance_table(tab, return_info=True)
+    assert ia["band"] is False and ib["band"] == "allblocks" and ib["far_units"] > 0 and ib["n_subcopies"] == 0
+    assert ia["passes"] == ib["passes"] and sa["converged"] and sb["converged"]
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
+    c, sc = cooler_b200.balance_arrays(bin1_offset, b2, cnt, chrom_offset)
+    np.testing.assert_array_equal(b, c)
+    assert abs(sc["scale"] / sb["scale"] - 1) < 1e-12

@@ -150,3 +150,19 @@ def test_align_rows_to_factor():
             a = align_rows_to_factor(off, f, row)
             assert a <= row and (a == 191 or a == 0 or bmap[a] != bmap[a - 1])   # a starts a coarse bin
             assert row == 191 or bmap[a] == bmap[row]                             # and it is row's coarse bin
+
+
+def test_choose_layout_policy():
+    """Sweep layout by table shape (balance.choose_layout): whole copies while the bias vector fits
+    L1/L2 well, column strips for large dense tables, 2-D blocks for huge sparse ones."""
+    from cooler_b200.balance import BLOCKS_MIN_BINS, choose_layout
+    assert choose_layout(30_895, 200_000_000) == (None, False)                 # 100 kb: whole copies
+    assert choose_layout(308_839, 1_000_000_000) == (14, False)                # 10 kb: strips of 16384 bins
+    assert choose_layout(247_077, 200_000_000) == (14, False)                  # 12.5 kb shard
+    assert choose_layout(3_088_298, 380_000_000) == (None, "allblocks")        # 1 kb shard: blocked kernel
+    assert choose_layout(BLOCKS_MIN_BINS - 1, 50_000_000) == (None, False)     # sparse but not huge: whole copies
+    assert choose_layout(3_088_298, 380_000_000, strip_bins=0) == (None, False)
+    assert choose_layout(3_088_298, 380_000_000, strip_bins=16384, band="blocks") == (14, "blocks")
+    assert choose_layout(3_088_298, 380_000_000, strip_bins=16384) == (14, True)
+    with pytest.raises(ValueError):
+        choose_layout(100_000, 10, strip_bins=1000)
