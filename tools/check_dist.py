@@ -48,6 +48,18 @@ def main():
                       f"passes={max(info['passes'])} mask_equal={same_mask} max_rel_err={err:.2e} "
                       f"{'OK' if good else 'FAIL'}", flush=True)
             dist.barrier()
+            if mode == "gw":
+                # the layout huge sparse tables get automatically (2-D blocked kernel), forced here on the shards
+                b2, _, i2 = cooler_b200.balance_table(tab, group=dist.group.WORLD, return_info=True,
+                                                      band="allblocks", far_col_shift=9, **kw)
+                if rank == 0:
+                    err = np.nanmax(np.abs(b2 / want - 1)) if np.isfinite(want).any() else 0.0
+                    good = (np.array_equal(np.isnan(b2), np.isnan(want)) and i2["passes"] == winfo["passes"]
+                            and err < 1e-9 and i2["band"] == "allblocks")
+                    ok &= bool(good)
+                    print(f"[check_dist] world={world} binsize={binsize} all-blocks layout on shards: "
+                          f"max_rel_err={err:.2e} {'OK' if good else 'FAIL'}", flush=True)
+                dist.barrier()
     # coarsening shards with no exchange: rows cut at coarse-bin boundaries, every rank coarsens its
     # shard, rank-ordered concatenation == single-GPU result (bit-exact)
     from cooler_b200.reduce import align_rows_to_factor, coarsen_table, table_to_host
