@@ -24,7 +24,7 @@ import numpy as np
 
 from . import store
 from .balance import balance_cooler
-from .reduce import coarsen_cooler, legacy_zoomify, preferred_sequence, zoomify_cooler
+from .reduce import coarsen_cooler, legacy_zoomify, merge_coolers, preferred_sequence, zoomify_cooler
 
 HIGLASS_TILE_DIM = 256      # _reduce.py:28
 logger = logging.getLogger("cooler")
@@ -216,6 +216,27 @@ def coarsen(cool_uri, factor, nproc, chunksize, field, out, append):
     else:
         coarsen_cooler(clr, out, factor, chunksize=chunksize, nproc=nproc, columns=columns,
                        dtypes=dtypes, agg=agg, mode="a" if append else "w")
+
+
+@cli.command()
+@click.argument("out_path", type=click.Path(exists=False))
+@click.argument("in_paths", nargs=-1, type=click.Path(exists=False))
+@click.option("--chunksize", "-c", type=int, default=int(20e6), show_default=True,
+              help="Size of the merge buffer in number of pixel table rows.")
+@click.option("--field", type=str, multiple=True,
+              help="Value columns to merge as '<name>[,dtype=<dtype>][,agg=<agg>]'.")
+@click.option("--append", "-a", is_flag=True, default=False,
+              help="Append the output cooler to an existing file instead of overwriting the file.")
+def merge(out_path, in_paths, chunksize, field, append):
+    """Merge multiple coolers with identical axes (cli/merge.py:8-80) on the GPU."""
+    columns, dtypes, agg = _fields(field)
+    clrs = [store.open_cooler(p) for p in in_paths]
+    if in_paths and all(store.is_memory_uri(p) for p in in_paths):      # in-memory stores in, in-memory store out
+        store.register(out_path, merge_coolers(None, clrs, mergebuf=chunksize, columns=columns,
+                                               dtypes=dtypes, agg=agg))
+    else:
+        merge_coolers(out_path, clrs, mergebuf=chunksize, columns=columns, dtypes=dtypes, agg=agg,
+                      mode="a" if append else "w")
 
 
 def invoke_balance(args, resolutions, outfile):

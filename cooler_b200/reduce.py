@@ -327,6 +327,17 @@ def _as_cooler(obj):
     return open_cooler(obj)
 
 
+def _bins_frame(clr):
+    """``clr.bins()[["chrom", "start", "end"]][:]`` with ``chrom`` as names (a categorical), whatever
+    the store returns (the built-in stores keep the enum codes of ``bins/chrom``)."""
+    import pandas as pd
+    bins = clr.bins()[["chrom", "start", "end"]][:]
+    if bins["chrom"].dtype.kind in "iu":
+        names = list(clr.chromsizes.index)
+        bins = bins.assign(chrom=pd.Categorical.from_codes(bins["chrom"].to_numpy(), categories=names, ordered=True))
+    return bins
+
+
 def _create(output_uri, bins, iterator, **kwargs):
     """``cooler.create.create`` when available (h5py), else the built-in writer (create.py)."""
     try:
@@ -515,8 +526,9 @@ class CoolerMerger:
 def merge_coolers(output_uri, input_uris, mergebuf, columns=None, dtypes=None, agg=None,
                   device="cuda", **kwargs):
     """Merge coolers with identical axes on the GPU (``cooler.merge_coolers``,
-    _reduce.py:211-307).  ``input_uris``: URIs/paths (needs the ``cooler`` package) or
-    Cooler-like objects.  ``output_uri=None`` returns a ``MemCooler``."""
+    _reduce.py:211-307).  ``input_uris``: URIs / paths or Cooler-like objects.
+    ``output_uri=None`` returns a ``MemCooler``; otherwise the result is written like the
+    reference does it (``create(output_uri, bins, iterator, columns=..., dtypes=..., assembly=...)``)."""
     clrs = [_as_cooler(u) for u in input_uris]
     is_symm = [c.storage_mode == "symmetric-upper" for c in clrs]
     if all(is_symm):
@@ -550,8 +562,6 @@ def merge_coolers(output_uri, input_uris, mergebuf, columns=None, dtypes=None, a
                                     binsize=c0.binsize, symmetric_upper=symmetric_upper)
         out.device_table = iterator.result_table
         return out
-    from cooler.create import create  # real writer (h5py)
-    bins = clrs[0].bins()[["chrom", "start", "end"]][:]
-    create(output_uri, bins, iterator, columns=columns, dtypes=dtypes,
-           assembly=clrs[0].info.get("genome-assembly", None), symmetric_upper=symmetric_upper, **kwargs)
+    _create(output_uri, _bins_frame(clrs[0]), iterator, columns=columns, dtypes=dtypes,
+            assembly=clrs[0].info.get("genome-assembly", None), symmetric_upper=symmetric_upper, **kwargs)
     return None

@@ -363,10 +363,12 @@ def list_coolers(path):
     out = []
 
     def visit(g, name):
-        if all(k in g for k in ("chroms", "bins", "pixels", "indexes")):
+        is_clr = all(k in g for k in ("chroms", "bins", "pixels", "indexes"))
+        if is_clr:
             out.append(name or "/")
-            return
         for k in g.keys():
+            if is_clr and k in ("chroms", "bins", "pixels", "indexes"):
+                continue
             o = g[k]
             if isinstance(o, h5lite.Group):
                 visit(o, f"{name}/{k}")

@@ -306,3 +306,25 @@ def test_zoomify_cli_legacy_layout(tmp_path):
     np.testing.assert_array_equal(np.asarray(lvl2._load_dset("bins/end")), CO["gm/x2/bins_end"])
     sums = [int(np.asarray(store.open_cooler(f"{out}::{i}")._load_dset("pixels/count")).sum()) for i in range(4)]
     assert sums == [100000] * 4
+
+
+def test_merge_cli_writes_file(tmp_path):
+    """`cooler merge out.cool a b c` on real files (cli/merge.py:8-80)."""
+    from cooler_b200 import h5lite, store
+    from cooler_b200.cli import cli
+    from ._h5check import check
+    a = os.path.join(COOL, "toy.symm.upper.2.mcool") + "::resolutions/4"
+    out = str(tmp_path / "merged.cool")
+    r = CliRunner()
+    res = r.invoke(cli, ["merge", out, a, a, a, "-c", "5"])
+    assert res.exit_code == 0, (res.output, res.exception)
+    check(out)
+    src, dst = store.open_cooler(a), store.open_cooler(out)
+    for k in ("pixels/bin1_id", "pixels/bin2_id", "bins/chrom", "bins/start", "bins/end", "chroms/length",
+              "indexes/bin1_offset", "indexes/chrom_offset"):
+        np.testing.assert_array_equal(np.asarray(src._load_dset(k)), np.asarray(dst._load_dset(k)))
+    np.testing.assert_array_equal(3 * np.asarray(src._load_dset("pixels/count")),
+                                  np.asarray(dst._load_dset("pixels/count")))
+    assert dst.chromnames == src.chromnames and dst.binsize == 4 and dst.storage_mode == "symmetric-upper"
+    assert dst.info["sum"] == 3 * src.info["sum"] and dst.info["nnz"] == src.info["nnz"]
+    assert h5lite.File(out)["bins/chrom"].enum == {n: i for i, n in enumerate(src.chromnames)}

@@ -420,3 +420,44 @@ def test_copy_cooler_is_a_raw_chunk_copy(tmp_path):
         assert [c[0] for c in ca] == [c[0] for c in cb] and [c[2:] for c in ca] == [c[2:] for c in cb]
         assert all(a._rd.bytes(x[1], x[2]) == b._rd.bytes(y[1], y[2]) for x, y in zip(ca, cb))
     assert b["bins/chrom"].enum == a["bins/chrom"].enum
+
+
+def test_merge_file_plumbing_with_oracle_merger(tmp_path, monkeypatch):
+    """merge_coolers(out.cool, [a.cool, b.cool]) / `cooler merge`: bins with chromosome NAMES, attributes,
+    append mode -- the numpy oracle stands in for the device merger (GPU run: tests/test_cli_gpu.py)."""
+    from click.testing import CliRunner
+
+    from cooler_b200 import reduce, store
+    from cooler_b200.cli import cli
+    from oracle import coarsen_numpy
+
+    def oracle_iter(self):
+        pxs = [{k: np.asarray(c._load_dset("pixels/" + k)) for k in ("bin1_id", "bin2_id", "count")}
+               for c in self.coolers]
+        b1, b2, cnt = coarsen_numpy.merge_pixels(pxs)
+        for lo in range(0, len(b1), self.mergebuf):
+            hi = lo + self.mergebuf
+            yield {"bin1_id": b1[lo:hi], "bin2_id": b2[lo:hi], "count": cnt[lo:hi]}
+
+    monkeypatch.setattr(reduce.CoolerMerger, "__iter__", oracle_iter)
+    a = os.path.join(COOL, "toy.symm.upper.2.mcool") + "::resolutions/4"
+    out = str(tmp_path / "merged.cool")
+    assert reduce.merge_coolers(out, [a, a, a], mergebuf=5) is None
+    check(out)
+    src, dst = store.open_cooler(a), store.open_cooler(out)
+    for k in ("pixels/bin1_id", "pixels/bin2_id", "bins/chrom", "bins/start", "bins/end", "chroms/length",
+              "indexes/bin1_offset", "indexes/chrom_offset"):
+        np.testing.assert_array_equal(np.asarray(src._load_dset(k)), np.asarray(dst._load_dset(k)))
+    np.testing.assert_array_equal(3 * np.asarray(src._load_dset("pixels/count")), np.asarray(dst._load_dset("pixels/count")))
+    assert dst.chromnames == src.chromnames and dst.binsize == 4 and dst.storage_mode == "symmetric-upper"
+    assert dst.info["sum"] == 3 * src.info["sum"] and dst.info["nnz"] == src.info["nnz"]
+    assert h5lite.File(out)["bins/chrom"].enum == {n: i for i, n in enumerate(src.chromnames)}
+    # CLI, appending a second cooler to the same file
+    res = CliRunner().invoke(cli, ["merge", out + "::twice", a, a, "-c", "7", "--append"])
+    assert res.exit_code == 0, (res.output, res.exception)
+    check(out)
+    assert sorted(store.list_coolers(out)) == ["/", "/twice"]
+    tw = store.open_cooler(out + "::twice")
+    np.testing.assert_array_equal(2 * np.asarray(src._load_dset("pixels/count")), np.asarray(tw._load_dset("pixels/count")))
+    with pytest.raises(ValueError, match="same resolution"):
+        reduce.merge_coolers(out, [a, os.path.join(COOL, "toy.symm.upper.2.mcool") + "::resolutions/8"], mergebuf=5)
