@@ -32,7 +32,7 @@ logger = logging.getLogger("cooler")
 
 @click.group()
 def cli():
-    """B200-native subset of the cooler CLI: balance, coarsen, zoomify."""
+    """B200-native subset of the cooler CLI: balance, coarsen, zoomify, merge, cload pairs."""
     if not logger.handlers:
         h = logging.StreamHandler(sys.stderr)
         h.setFormatter(logging.Formatter("%(levelname)s:%(name)s:%(message)s"))
@@ -237,6 +237,134 @@ def merge(out_path, in_paths, chunksize, field, append):
     else:
         merge_coolers(out_path, clrs, mergebuf=chunksize, columns=columns, dtypes=dtypes, agg=agg,
                       mode="a" if append else "w")
+
+
+def parse_bins(arg):
+    """BINS argument: '<chromsizes file>:<binsize>' or a bins BED file (cli/_util.py:100-143).
+    Returns (chromsizes Series in file order, bins DataFrame)."""
+    import os.path as op
+
+    import pandas as pd
+    if ":" in op.splitdrive(arg)[1]:
+        chromsizes_file, binsize = arg.rsplit(":", maxsplit=1)
+        if not op.exists(chromsizes_file):
+            raise ValueError(f'File "{chromsizes_file}" not found')
+        try:
+            binsize = int(binsize)
+        except ValueError as e:
+            raise ValueError(f'Expected integer binsize argument (bp), got "{binsize}"') from e
+        tab = pd.read_csv(chromsizes_file, sep="\t", usecols=[0, 1], names=["name", "length"], dtype={"name": str})
+        chromsizes = pd.Series(tab["length"].values, index=tab["name"].values)        # read_chromsizes(all_names=True)
+        parts = []
+        for name, clen in chromsizes.items():                                             # util.binnify
+            nb = int(np.ceil(clen / binsize))
+            edges = np.arange(0, nb + 1) * binsize
+            edges[-1] = clen
+            parts.append(pd.DataFrame({"chrom": [name] * nb, "start": edges[:-1], "end": edges[1:]}))
+        bins = pd.concat(parts, axis=0, ignore_index=True)
+        bins["chrom"] = pd.Categorical(bins["chrom"], categories=list(chromsizes.index), ordered=True)
+    elif op.exists(arg):
+        bins = pd.read_csv(arg, sep="\t", names=["chrom", "start", "end"], usecols=[0, 1, 2], dtype={"chrom": str})
+        last = bins.drop_duplicates(["chrom"], keep="last")
+        chromsizes = pd.Series(last["end"].values, index=last["chrom"].values)
+    else:
+        raise ValueError("Expected BINS to be either <Path to bins file> or "
+                         "<Path to chromsizes file>:<binsize in bp>.")
+    return chromsizes, bins
+
+
+@cli.group()
+def cload():
+    """Create a cooler from genomic pairs and bins (GPU binning; `pairs` only)."""
+
+
+@cload.command()
+@click.argument("bins", metavar="BINS")
+@click.argument("pairs_path", metavar="PAIRS_PATH")
+@click.argument("cool_path", metavar="COOL_PATH")
+@click.option("--metadata", type=str, help="Path to JSON file containing user metadata.")
+@click.option("--assembly", type=str, help="Name of genome assembly (e.g. hg19, mm10)")
+@click.option("--chrom1", "-c1", type=int, required=True, help="chrom1 field number (one-based)")
+@click.option("--pos1", "-p1", type=int, required=True, help="pos1 field number (one-based)")
+@click.option("--chrom2", "-c2", type=int, required=True, help="chrom2 field number (one-based)")
+@click.option("--pos2", "-p2", type=int, required=True, help="pos2 field number (one-based)")
+@click.option("--zero-based", "-0", is_flag=True, default=False, show_default=True,
+              help="Positions are zero-based")
+@click.option("--comment-char", type=str, default="#", show_default=True, help="Comment character that skips lines")
+@click.option("--no-symmetric-upper", "-N", is_flag=True, default=False,
+              help="Create a complete square matrix without implicit symmetry.")
+@click.option("--input-copy-status", type=click.Choice(["unique", "duplex"]), default="unique", show_default=True,
+              help="Copy status of input data when using symmetric-upper storage.")
+@click.option("--field", type=str, multiple=True, help="Extra value columns (not supported by the GPU path).")
+@click.option("--chunksize", "-c", type=int, default=15_000_000, help="Lines of the input parsed at a time.")
+@click.option("--mergebuf", type=int, help="Accepted for compatibility; ignored (one device-wide sort).")
+@click.option("--max-merge", type=int, default=200, help="Accepted for compatibility; ignored.")
+@click.option("--temp-dir", type=str, help="Accepted for compatibility; ignored (no temporary coolers).")
+@click.option("--no-delete-temp", is_flag=True, default=False, help="Accepted for compatibility; ignored.")
+@click.option("--storage-options", help="HDF5 filter options 'k1=v1,k2=v2,...'.")
+@click.option("--append", "-a", is_flag=True, default=False,
+              help="Append the output cooler to an existing file instead of overwriting the file.")
+def pairs(bins, pairs_path, cool_path, metadata, assembly, chrom1, pos1, chrom2, pos2, zero_based, comment_char,
+          no_symmetric_upper, input_copy_status, field, chunksize, mergebuf, max_merge, temp_dir, no_delete_temp,
+          storage_options, append):
+    """Bin any text file or stream of pairs (cli/cload.py:484-666).  PAIRS_PATH '-' reads stdin.
+
+    The reference bins chunk by chunk into temporary coolers and merges them; here the parsed
+    columns are binned and counted by ONE device-wide sort / reduce-by-key (cooler_b200.ingest)."""
+    import json
+
+    import pandas as pd
+
+    from . import ingest
+    from .create import create_cooler
+    if len(field):
+        raise click.UsageError("--field value columns are not supported by the B200 ingest path")
+    chromsizes, bins = parse_bins(bins)
+    from .create import _binsize, _bins_arrays
+    names, ids, start, end, _ = _bins_arrays(bins)
+    binsize = _binsize(ids, start, end)
+    uniform = binsize is not None and np.array_equal(
+        np.asarray(start), np.concatenate([np.arange(k) * binsize for k in np.bincount(ids)]))
+    if not uniform:
+        raise click.UsageError("the B200 ingest path needs fixed-size bins (<chromsizes>:<binsize>)")
+    symmetric_upper = not no_symmetric_upper
+    tril_action = None
+    if symmetric_upper:                                          # 517-523
+        tril_action = "reflect" if input_copy_status == "unique" else "drop"
+    if metadata is not None:
+        with open(metadata) as f:
+            metadata = json.load(f)
+    cols = {}
+    for name, num in (("chrom1", chrom1), ("pos1", pos1), ("chrom2", chrom2), ("pos2", pos2)):
+        if num == 0:
+            raise click.BadParameter("Field numbers start at 1", param_hint=name)
+        cols[name] = num - 1
+    h5opts = None
+    if storage_options is not None:
+        h5opts = {}
+        for kv in storage_options.split(","):
+            k, v = kv.split("=", 1)
+            h5opts[k.strip()] = int(v) if v.strip().lstrip("-").isdigit() else v.strip()
+    order = sorted(cols, key=cols.get)                            # read_csv returns usecols in file order
+    reader = pd.read_csv(sys.stdin if pairs_path == "-" else pairs_path, sep="\t", comment=comment_char or None,
+                         header=None, usecols=sorted(cols.values()), names=order,
+                         dtype={"chrom1": str, "pos1": np.int64, "chrom2": str, "pos2": np.int64},
+                         iterator=True, chunksize=chunksize, compression="infer")
+    idx = pd.Index(names)
+    parts = {k: [] for k in cols}
+    for chunk in reader:                                          # names -> ids; unknown contigs get -1 and are dropped
+        parts["chrom1"].append(idx.get_indexer(chunk["chrom1"]).astype(np.int32))
+        parts["chrom2"].append(idx.get_indexer(chunk["chrom2"]).astype(np.int32))
+        parts["pos1"].append(chunk["pos1"].to_numpy(np.int64))
+        parts["pos2"].append(chunk["pos2"].to_numpy(np.int64))
+    cat = {k: (np.concatenate(v) if v else np.zeros(0, np.int32 if k.startswith("chrom") else np.int64))
+           for k, v in parts.items()}
+    lengths = np.asarray(end)[np.r_[ids[1:] != ids[:-1], True]]
+    px = ingest.bin_pairs(cat["chrom1"], cat["pos1"], cat["chrom2"], cat["pos2"], lengths, binsize,
+                          is_one_based=not zero_based, tril_action=tril_action, validate=True)
+    create_cooler(cool_path, bins, px, columns=["count"], metadata=metadata, assembly=assembly,
+                  boundscheck=False, triucheck=False, dupcheck=False, ensure_sorted=False,
+                  symmetric_upper=symmetric_upper, h5opts=h5opts, mode="a" if append else "w")
 
 
 def invoke_balance(args, resolutions, outfile):

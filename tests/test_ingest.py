@@ -97,3 +97,79 @@ def test_gpu_bin_pairs_matches_oracle_large_random():
         for c in ("bin1_id", "bin2_id", "count"):
             np.testing.assert_array_equal(got[c], want[c])
         assert got["count"].sum() == want["count"].sum()
+
+
+def _write_pairs(tmp_path, tag, n_max=200_000):
+    """A .pairs text file + chromsizes file from a golden case (chromosome i is named 'c<i>';
+    records on chromosomes the case marks as unknown (-1) are written as 'other')."""
+    c1, p1, c2, p2, sizes, binsize = _args(tag)
+    names = np.array([f"c{i}" for i in range(len(sizes))] + ["other"], dtype=object)
+    path = str(tmp_path / f"{tag}.pairs")
+    with open(path, "w") as f:
+        f.write("## pairs format v1.0\n#columns: readID chr1 pos1 chr2 pos2 strand1 strand2\n")
+        for k in range(len(c1)):
+            f.write(f"r{k}\t{names[c1[k]]}\t{p1[k]}\t{names[c2[k]]}\t{p2[k]}\t+\t-\n")
+        f.write("rX\tchrUn_zzz\t1\tc0\t1\t+\t-\n")            # contig missing from the bin table: dropped
+    cs = str(tmp_path / f"{tag}.chrom.sizes")
+    with open(cs, "w") as f:
+        for n, L in zip(names, sizes):
+            f.write(f"{n}\t{int(L)}\n")
+    return path, cs, binsize
+
+
+def _check_cload_output(out, tag):
+    from cooler_b200 import store
+    from ._h5check import check
+    check(out)
+    clr = store.open_cooler(out)
+    for c in ("bin1_id", "bin2_id", "count"):
+        np.testing.assert_array_equal(np.asarray(clr._load_dset("pixels/" + c)), G[f"{tag}/out_{c}"], err_msg=c)
+    sizes, binsize = G[f"{tag}/chromsizes"], int(G[f"{tag}/binsize"])
+    assert clr.chromnames == [f"c{i}" for i in range(len(sizes))] and list(clr.chromsizes.values) == list(sizes)
+    assert clr.info["nbins"] == int(np.sum(-(-sizes // binsize))) and clr.info["sum"] == int(G[f"{tag}/out_count"].sum())
+    assert clr.info["nnz"] == len(G[f"{tag}/out_count"]) and clr.storage_mode == "symmetric-upper"
+    ind = np.asarray(clr._load_dset("indexes/bin1_offset"))
+    np.testing.assert_array_equal(ind, np.searchsorted(G[f"{tag}/out_bin1_id"], np.arange(len(ind))))
+
+
+@pytest.mark.parametrize("tag", ["gm_subset_500kb", "toy4_zero_based", "gm_shuffled_1mb_drop"])
+def test_cload_pairs_cli_plumbing_with_oracle(tag, tmp_path, monkeypatch):
+    """`cooler cload pairs BINS PAIRS OUT` (cli/cload.py:484-666): text parsing, contig names -> ids,
+    flags, file output; the numpy oracle stands in for the device binning (GPU: next test)."""
+    from click.testing import CliRunner
+
+    from cooler_b200 import ingest
+    from cooler_b200.cli import cli
+    from oracle import ingest_numpy
+    monkeypatch.setattr(ingest, "bin_pairs", lambda *a, device="cuda", **kw: ingest_numpy.bin_pairs(*a, **kw))
+    path, cs, binsize = _write_pairs(tmp_path, tag)
+    out = str(tmp_path / "out.cool")
+    args = ["cload", "pairs", f"{cs}:{binsize}", path, out, "-c1", "2", "-p1", "3", "-c2", "4", "-p2", "5",
+            "--chunksize", "1000", "--assembly", "toy"]
+    if not bool(G[f"{tag}/one_based"]):
+        args.append("--zero-based")
+    if CASES[tag] == "drop":
+        args += ["--input-copy-status", "duplex"]
+    res = CliRunner().invoke(cli, args)
+    assert res.exit_code == 0, (res.output, res.exception)
+    _check_cload_output(out, tag)
+    from cooler_b200 import store
+    assert store.open_cooler(out).info["genome-assembly"] == "toy"
+    res = CliRunner().invoke(cli, args[:-2] + ["-c1", "0"])
+    assert res.exit_code != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["gm_subset_500kb", "toy4_zero_based"])
+def test_cload_pairs_cli_gpu(tag, tmp_path):
+    from click.testing import CliRunner
+
+    from cooler_b200.cli import cli
+    path, cs, binsize = _write_pairs(tmp_path, tag)
+    out = str(tmp_path / "out.cool")
+    args = ["cload", "pairs", f"{cs}:{binsize}", path, out, "-c1", "2", "-p1", "3", "-c2", "4", "-p2", "5"]
+    if not bool(G[f"{tag}/one_based"]):
+        args.append("--zero-based")
+    res = CliRunner().invoke(cli, args)
+    assert res.exit_code == 0, (res.output, res.exception)
+    _check_cload_output(out, tag)
