@@ -32,7 +32,7 @@ logger = logging.getLogger("cooler")
 
 @click.group()
 def cli():
-    """B200-native subset of the cooler CLI: balance, coarsen, zoomify, merge, cload pairs."""
+    """B200-native subset of the cooler CLI: balance, coarsen, zoomify, merge, cload pairs, dump."""
     if not logger.handlers:
         h = logging.StreamHandler(sys.stderr)
         h.setFormatter(logging.Formatter("%(levelname)s:%(name)s:%(message)s"))
@@ -365,6 +365,38 @@ def pairs(bins, pairs_path, cool_path, metadata, assembly, chrom1, pos1, chrom2,
     create_cooler(cool_path, bins, px, columns=["count"], metadata=metadata, assembly=assembly,
                   boundscheck=False, triucheck=False, dupcheck=False, ensure_sorted=False,
                   symmetric_upper=symmetric_upper, h5opts=h5opts, mode="a" if append else "w")
+
+
+@cli.command()
+@click.argument("cool_uri", metavar="COOL_PATH")
+@click.option("--table", "-t", type=click.Choice(["chroms", "bins", "pixels"]), default="pixels", show_default=True,
+              help="Which table to dump.")
+@click.option("--columns", "-c", type=str, help="Restrict output to a comma-separated subset of columns.")
+@click.option("--header", "-H", is_flag=True, default=False, help="Print the header of column names as the first row.")
+@click.option("--na-rep", default="", help="Missing data representation. Default is empty ''.")
+@click.option("--float-format", default="g", show_default=True, help="Format string for floating point numbers.")
+@click.option("--range", "-r", "range_", type=str, help="Genomic region along the row dimension (UCSC notation).")
+@click.option("--range2", "-r2", type=str, help="Genomic region along the column dimension.")
+@click.option("--fill-lower", "-f", is_flag=True, default=False,
+              help="For symmetric-upper coolers, generate the lower triangle pixels inside the query box.")
+@click.option("--balanced/--no-balance", "-b", is_flag=True, default=False,
+              help="Apply balancing weights to data (extra column `balanced`).")
+@click.option("--join", is_flag=True, default=False, help="Print chromosome bin coordinates instead of bin IDs.")
+@click.option("--annotate", type=str, help="Join additional bin-table columns (comma-separated) against the pixels.")
+@click.option("--one-based-ids", is_flag=True, default=False, help="Print bin IDs as one-based.")
+@click.option("--one-based-starts", is_flag=True, default=False, help="Print start coordinates as one-based.")
+@click.option("--chunksize", "-k", type=int, default=1_000_000, show_default=True,
+              help="Number of pixel records per query task.")
+@click.option("--out", "-o", help="Output text file (.gz is compressed). Default: stdout.")
+def dump(cool_uri, table, columns, header, na_rep, float_format, range_, range2, fill_lower, balanced, join,
+         annotate, one_based_ids, one_based_starts, chunksize, out):
+    """Dump a cooler's data to a text stream (cli/dump.py:57-304); pixel queries and balancing on the GPU."""
+    from .dump import dump as _dump
+    split = lambda v: tuple(x for x in v.split(",") if x) if v is not None else None   # noqa: E731
+    _dump(store.open_cooler(cool_uri), out, table=table, columns=split(columns), header=header, na_rep=na_rep,
+          float_format=float_format, range=range_, range2=range2, fill_lower=fill_lower, balanced=balanced,
+          join=join, annotate=split(annotate), one_based_ids=one_based_ids, one_based_starts=one_based_starts,
+          chunksize=chunksize)
 
 
 def invoke_balance(args, resolutions, outfile):
