@@ -297,7 +297,12 @@ def main():
             for ent in json.load(f):
                 if ent["binsize"] == binsize and ent["mode"] == args.mode and ent["nnz_effective"] == prob.nnz_eff:
                     traffic = ent["dram_bytes_per_launch"]
-    kernel_name = "ice_sweep_strips_kernel" if prob.strip_shift is not None else "ice_sweep_kernel"
+    if getattr(prob, "far_copies", None) and not prob.subs:
+        kernel_name = "ice_sweep_far_kernel"          # every pixel through the 2-D blocked kernel (csrc/far.cuh)
+    elif getattr(prob, "far_copies", None):
+        kernel_name = "ice_sweep_strips_kernel + ice_sweep_far_kernel"
+    else:
+        kernel_name = "ice_sweep_strips_kernel" if prob.strip_shift is not None else "ice_sweep_kernel"
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_pass_local, "kernel_ms_avg": sweep_ms_avg,
