@@ -297,6 +297,9 @@ def main():
             for ent in json.load(f):
                 if ent["binsize"] == binsize and ent["mode"] == args.mode and ent["nnz_effective"] == prob.nnz_eff:
                     traffic = ent["dram_bytes_per_launch"]
+    layout = ("all blocks" if getattr(prob, "far_copies", None) and not prob.subs else
+              "band strips + far blocks" if getattr(prob, "far_copies", None) else
+              f"column strips of {1 << prob.strip_shift} bins" if prob.strip_shift is not None else "whole copies")
     if getattr(prob, "far_copies", None) and not prob.subs:
         kernel_name = "ice_sweep_far_kernel"          # every pixel through the 2-D blocked kernel (csrc/far.cuh)
     elif getattr(prob, "far_copies", None):
@@ -346,7 +349,7 @@ def main():
         cpu = cpu_ice_passes(data, args.cpu_passes)
 
     if rank == 0:
-        cfg.update({"nnz_stored": nnz_total, "nnz_effective": nnz_eff, "passes_per_step": passes_per_step,
+        cfg.update({"sweep_layout": layout, "nnz_stored": nnz_total, "nnz_effective": nnz_eff, "passes_per_step": passes_per_step,
                     "converged": converged, "masked_bins": int(np.isnan(bias).sum())})
         line = {"metric": "ICE pixels/s", "value": value, "unit": "pixels/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / max(args.steps, 1),
