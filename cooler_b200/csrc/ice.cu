@@ -383,9 +383,10 @@ static int ice_sweep_far(const cb200_ice* st, void* stream) {
   const int grid = st->n_far_units < sms ? st->n_far_units : sms;
   cudaStream_t s = (cudaStream_t)stream;
   if (st->far_warps == 16) {
+    // default: 8 loads in flight per lane (measured 1.70 vs 2.15 ms with 4 on the 1 kb rank-0 shard)
     if (g_far_unroll == 2) ice_sweep_far_kernel<16, 2><<<grid, 512, smem, s>>>(*st);
-    else if (g_far_unroll == 8) ice_sweep_far_kernel<16, 8><<<grid, 512, smem, s>>>(*st);
-    else ice_sweep_far_kernel<16, 4><<<grid, 512, smem, s>>>(*st);
+    else if (g_far_unroll == 4) ice_sweep_far_kernel<16, 4><<<grid, 512, smem, s>>>(*st);
+    else ice_sweep_far_kernel<16, 8><<<grid, 512, smem, s>>>(*st);
   } else {
     if (g_far_unroll == 1) ice_sweep_far_kernel<32, 1><<<grid, 1024, smem, s>>>(*st);
     else if (g_far_unroll == 4) ice_sweep_far_kernel<32, 4><<<grid, 1024, smem, s>>>(*st);

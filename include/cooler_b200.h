@@ -250,7 +250,7 @@ typedef struct {
  * selective_l1: -1 automatic, 0/1 = whether gathers far from the diagonal bypass L1
  * allocation in the L1/L2-gather kernel. */
 int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1);
-/* Far-field kernel: 128-bit stream loads in flight per lane (0 = default: 4 with 16 warps,
+/* Far-field kernel: 128-bit stream loads in flight per lane (0 = default: 8 with 16 warps,
  * 2 with 32 warps). */
 int cb200_set_far_tuning(int32_t far_unroll);
 /* K3: the marginal sweeps of every sub-copy (bin1-major rows, bin2-major columns), one

@@ -264,7 +264,8 @@ def test_far_blocks_layout_matches_reference_golden(key, strip_bins, col_shift, 
 
 
 @pytest.mark.parametrize("strip_bins,col_shift,warps,unroll", [(1024, 8, 16, 0), (4096, 12, 32, 0), (256, 10, 16, 2),
-                                                             (16384, 12, 16, 0), (512, 5, 32, 1)])
+                                                             (16384, 12, 16, 0), (512, 5, 32, 1), (1024, 8, 16, 4),
+                                                             (1024, 9, 16, 8), (8192, 13, 32, 4), (16384, 13, 16, 0)])
 def test_far_blocks_large_synthetic_matches_unstripped(strip_bins, col_shift, warps, unroll):
     """Several 16384-row blocks, hundreds of column tiles, rows from empty to dense; every
     far-kernel variant agrees with the whole-copy sweep to rounding and is bit-reproducible."""
