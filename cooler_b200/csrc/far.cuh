@@ -41,6 +41,30 @@ __device__ __forceinline__ void cp_async_f64(unsigned smem_dst, const double* gs
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// mbarrier + 1-D bulk copy (TMA) staging of a column tile of w: one elected thread issues a single
+// cp.async.bulk for the whole contiguous slice instead of C / THREADS 8-byte cp.async per thread,
+// which takes the staging off the LSU instruction stream that bounds this kernel (opt-in: kTma).
+__device__ __forceinline__ void mbar_init(unsigned bar_s, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar_s, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar_s, unsigned phase) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar_s), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst_s, const void* src, unsigned bytes, unsigned bar_s) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar_s) : "memory");
+}
 // shared-memory accesses by 32-bit shared-space address (keeps address arithmetic to one shift/add)
 __device__ __forceinline__ double lds_f64(unsigned a) {
   double v;
@@ -142,11 +166,12 @@ __device__ __forceinline__ void far_slot(const int4* __restrict__ px4, const int
   __syncwarp();
 }
 
-template <int WARPS, int U>
+template <int WARPS, int U, bool kTma = false>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 ice_sweep_far_kernel(const cb200_ice st) {
   extern __shared__ double far_sm[];               // acc[FAR_ACC] | w tile [2][C]
   __shared__ int s_unit;
+  __shared__ unsigned long long s_bar[2];          // kTma: "tile staged" barrier of each w buffer
   if (*st.all_done) return;
   constexpr int RW = FAR_ROWS / WARPS;             // rows per warp slice
   constexpr int THREADS = WARPS * 32;
@@ -157,11 +182,41 @@ ice_sweep_far_kernel(const cb200_ice st) {
   const unsigned wb_s = acc_s + FAR_ACC * 8;
   unsigned long long* claim = reinterpret_cast<unsigned long long*>(st.far_claim);
 
-  auto stage = [&](unsigned dst_s, int j) {        // cp.async the slice of w of column tile j
+  const unsigned bar_s = (unsigned)__cvta_generic_to_shared(s_bar);
+  unsigned ph0 = 0, ph1 = 0;                       // phase parity of the two barriers (uniform over the CTA)
+  if (kTma) {
+    if (threadIdx.x == 0) {
+      mbar_init(bar_s, 1);
+      mbar_init(bar_s + 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+  // stage the slice of w of column tile j into buffer b (at dst_s)
+  auto stage = [&](unsigned dst_s, int j, int b) {
     const int64_t base = (int64_t)j << cs;
-    for (int i = threadIdx.x; i < C; i += THREADS)
-      if (base + i < st.n_bins) cp_async_f64(dst_s + i * 8, st.w + base + i);
-    cp_async_commit();
+    if (kTma) {
+      if (threadIdx.x == 0) {
+        const int64_t left = (int64_t)st.n_bins - base;
+        const int nv = (int)(left < C ? left : C);             // valid bins of this tile (>= 1)
+        const unsigned bytes = (unsigned)(nv & ~1) * 8u;       // bulk copies move multiples of 16 bytes
+        mbar_expect_tx(bar_s + 8 * b, bytes);                  // 0 bytes: the arrive alone completes the phase
+        if (bytes) bulk_g2s(dst_s, st.w + base, bytes, bar_s + 8 * b);
+        if (nv & 1) sts_f64(dst_s + (unsigned)(nv - 1) * 8u, st.w[base + nv - 1]);   // odd tail of the last tile
+      }
+    } else {
+      for (int i = threadIdx.x; i < C; i += THREADS)
+        if (base + i < st.n_bins) cp_async_f64(dst_s + i * 8, st.w + base + i);
+      cp_async_commit();
+    }
+  };
+  auto staged = [&](int b) {                       // wait until buffer b holds its tile (followed by __syncthreads)
+    if (kTma) {
+      if (b == 0) { mbar_wait(bar_s, ph0); ph0 ^= 1u; }
+      else { mbar_wait(bar_s + 8, ph1); ph1 ^= 1u; }
+    } else {
+      cp_async_wait_all();
+    }
   };
 
   while (true) {
@@ -178,24 +233,26 @@ ice_sweep_far_kernel(const cb200_ice st) {
     const int4* __restrict__ px4 = reinterpret_cast<const int4*>(fc.px);
     const int j_first = st.far_tiles[un.t0];
     int jn = (un.t0 + 1 < un.t1) ? st.far_tiles[un.t0 + 1] : -1;
-    stage(wb_s, j_first);
+    stage(wb_s, j_first, 0);
     int64_t a = tp[(int64_t)j_first * WARPS], b = tp[(int64_t)j_first * WARPS + 1];
     int4 qn[U];
     far_first_group<U>(px4, a, b, qn, lane);
-    cp_async_wait_all();
+    staged(0);
     __syncthreads();                               // tile 0 staged; accumulators zeroed
     int buf = 0;
     for (int t = un.t0; t < un.t1; ++t) {
       const int jnn = (t + 2 < un.t1) ? st.far_tiles[t + 2] : -1;     // in flight during this tile
       int64_t a2 = 0, b2 = 0;
       if (jn >= 0) {
-        stage(wb_s + (unsigned)((buf ^ 1) * C * 8), jn);
+        stage(wb_s + (unsigned)((buf ^ 1) * C * 8), jn, buf ^ 1);
         a2 = tp[(int64_t)jn * WARPS];
         b2 = tp[(int64_t)jn * WARPS + 1];
       }
       far_slot<U>(px4, a, b, qn, wb_s + (unsigned)(buf * C * 8), acc_s, lane);
-      if (jn >= 0) far_first_group<U>(px4, a2, b2, qn, lane);
-      cp_async_wait_all();
+      if (jn >= 0) {
+        far_first_group<U>(px4, a2, b2, qn, lane);
+        staged(buf ^ 1);                           // (a barrier is only waited on when a copy was issued to it)
+      }
       __syncthreads();                             // next tile staged, this one released
       buf ^= 1;
       a = a2;

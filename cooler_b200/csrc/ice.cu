@@ -8,6 +8,7 @@
 // deterministic segmented reductions (rows of the bin1-major copy + rows of the
 // bin2-major copy), float64, no atomics.
 #include "walk.cuh"
+#include <cstdlib>
 #include "far.cuh"
 #include "../../include/cooler_b200.h"
 
@@ -382,7 +383,21 @@ static int ice_sweep_far(const cb200_ice* st, void* stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = st->n_far_units < sms ? st->n_far_units : sms;
   cudaStream_t s = (cudaStream_t)stream;
-  if (st->far_warps == 16) {
+  // CB200_FAR_TMA=1 (experimental, not the default): stage the column tiles of w with one bulk copy
+  // (cp.async.bulk + mbarrier) per tile instead of per-thread 8-byte cp.async
+  static const bool use_tma = [] { const char* e = getenv("CB200_FAR_TMA"); return e && e[0] == '1'; }();
+  if (use_tma) {
+    static bool tma_attr_done = false;
+    if (!tma_attr_done) {
+      const size_t want = ((size_t)FAR_ACC + 2 * 8192) * sizeof(double);
+      const int mx = (int)(want < kSmemLimit ? want : kSmemLimit);
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      tma_attr_done = true;
+    }
+    if (st->far_warps == 16) ice_sweep_far_kernel<16, 8, true><<<grid, 512, smem, s>>>(*st);
+    else ice_sweep_far_kernel<32, 4, true><<<grid, 1024, smem, s>>>(*st);
+  } else if (st->far_warps == 16) {
     // default: 8 loads in flight per lane (measured 1.70 vs 2.15 ms with 4 on the 1 kb rank-0 shard)
     if (g_far_unroll == 2) ice_sweep_far_kernel<16, 2><<<grid, 512, smem, s>>>(*st);
     else if (g_far_unroll == 4) ice_sweep_far_kernel<16, 4><<<grid, 512, smem, s>>>(*st);
