@@ -463,3 +463,17 @@ def test_auto_layout_uses_blocks_for_huge_sparse_tables():
     c, sc = cooler_b200.balance_arrays(bin1_offset, b2, cnt, chrom_offset)
     np.testing.assert_array_equal(b, c)
     assert abs(sc["scale"] / sb["scale"] - 1) < 1e-12
+
+
+def test_far_kernel_tma_staging_variant_matches_whole_copies():
+    """CB200_FAR_TMA=1 (one cp.async.bulk + mbarrier per column tile instead of per-thread cp.async):
+    selected once per process, hence the subprocess.  Same bias as the whole-copy sweep."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CB200_FAR_TMA="1")
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "check_far_tma.py")], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert res.stdout.count(" OK") == 3 and "FAIL" not in res.stdout and "tma 1" in res.stdout, res.stdout
