@@ -244,6 +244,8 @@ def copy_cooler(src, dst_uri, columns=("count",), mode="w"):
                         out.copy_dataset(d, k)
                         continue
                     enum = getattr(d, "enum", None)
+                    if enum is None and grp_name == "bins" and k == "chrom" and np.asarray(d[:]).dtype.kind in "iu":
+                        enum = {n: i for i, n in enumerate(src.chromnames)}      # write_bins: chrom ids as an enum
                     attrs = dict(getattr(d, "attrs", {}) or {})
                     out.create_dataset(k, data=np.asarray(d[:]), enum=enum, attrs=attrs or None, **opts)
             attrs = dict(getattr(g, "attrs", {}) or {})

@@ -461,3 +461,18 @@ def test_merge_file_plumbing_with_oracle_merger(tmp_path, monkeypatch):
     np.testing.assert_array_equal(2 * np.asarray(src._load_dset("pixels/count")), np.asarray(tw._load_dset("pixels/count")))
     with pytest.raises(ValueError, match="same resolution"):
         reduce.merge_coolers(out, [a, os.path.join(COOL, "toy.symm.upper.2.mcool") + "::resolutions/8"], mergebuf=5)
+
+
+def test_copy_cooler_from_memory_store(tmp_path):
+    """copy_cooler from an in-memory store: columns are encoded, bins/chrom becomes an enum."""
+    from cooler_b200 import MemCooler
+    a = np.array([[0, 0, 3], [0, 2, 1], [1, 1, 5], [2, 3, 2]])
+    clr = MemCooler.from_chromsizes(["x", "y"], [25, 12], 10, a[:, 0], a[:, 1], a[:, 2].astype(np.int32))
+    out = str(tmp_path / "m.cool")
+    create.copy_cooler(clr, out)
+    check(out)
+    dst = H5Cooler(out)
+    assert dst.chromnames == ["x", "y"] and dst.binsize == 10 and dst.info["nnz"] == 4
+    assert h5lite.File(out)["bins/chrom"].enum == {"x": 0, "y": 1}
+    for k in ("pixels/bin1_id", "pixels/bin2_id", "pixels/count", "bins/start", "bins/end", "indexes/bin1_offset"):
+        np.testing.assert_array_equal(np.asarray(clr._load_dset(k)), np.asarray(dst._load_dset(k)))
