@@ -156,6 +156,13 @@ class IceProblem:
         # layout of the sweep: whole copies, column strips, or diagonal band strips + far rest
         self.strip_shift, self.band = choose_layout(n_bins, csr.nnz, strip_bins, band)
         sh = self.strip_shift
+        if band is None and self.band == "allblocks":
+            # automatic choice: the block build keeps ~5 transient 12-byte copies of the pixel stream
+            # alive (sort in / out / scratch of both orientations); fall back to whole copies when
+            # that does not fit next to the table (a whole 1 kb matrix on ONE GPU)
+            free = torch.cuda.mem_get_info(table.device)[0]
+            if 60 * csr.nnz > free:
+                self.band = False
         if band == "allblocks" or self.band == "allblocks":   # every pixel through the 2-D blocked kernel (csrc/far.cuh)
             self.band, self.strip_shift = "allblocks", None
             if cval is None:
