@@ -272,6 +272,15 @@ class MemCooler:
         n = self.root.attrs["nbins"]
         return (n, n)
 
+    def matrix(self, **kwargs):
+        """``Cooler.matrix(...)`` (api.py:326-409) on the GPU: a selector with ``.fetch(region[, region2])``
+        and ``[i0:i1, j0:j1]`` (see ``cooler_b200.api.matrix``).  The uploaded pixel table is kept for
+        the next call."""
+        from .api import matrix
+        sel = matrix(self, table=getattr(self, "_b200_table", None), **kwargs)
+        self._b200_table = sel.table
+        return sel
+
 
 class H5Cooler(MemCooler):
     """A ``.cool`` file (or one resolution of an ``.mcool``) read with ``cooler_b200.h5lite``.

@@ -106,3 +106,18 @@ def test_dense_fetch_matches_oracle_on_random_table():
         np.testing.assert_array_equal(sp.row[o], r)
         np.testing.assert_array_equal(sp.col[o], c)
         np.testing.assert_array_equal(sp.data[o], d)
+
+
+def test_cooler_objects_have_a_matrix_method():
+    """clr.matrix(balance=...).fetch(...) on the store objects, table uploaded once."""
+    import os
+
+    from cooler_b200 import store
+    clr = store.open_cooler(os.path.join(_golden.GOLD, "cool", "hg19.GM12878-MboI.matrix.2000kb.cool"))
+    a = clr.matrix(balance=False).fetch("chr21")
+    tab = clr._b200_table
+    b = clr.matrix(balance=False, sparse=True).fetch("chr21")
+    assert clr._b200_table is tab and a.shape == (25, 25) and np.array_equal(a, b.toarray())
+    assert np.array_equal(a, a.T) and a.sum() > 0
+    with pytest.raises(ValueError, match="No column 'bins/weight'"):
+        clr.matrix(balance=True)
