@@ -125,3 +125,58 @@ def test_dump_tasks_cover_the_window_exactly_once(case, fill):
     if not fill:                                       # direct queries come out in table order
         assert have == list(zip(got["bin1_id"].astype(int).tolist(), got["bin2_id"].astype(int).tolist(),
                                 got["count"].astype(int).tolist()))
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+@given(ops=st.lists(st.tuples(st.sampled_from(["add", "del", "attr", "group", "reopen"]), st.integers(0, 6),
+                              st.integers(0, 2**31 - 1)), min_size=1, max_size=14),
+       which=st.sampled_from(["toy.asymm.2.cool", "toy.symm.upper.2.mcool"]))
+def test_random_edit_sessions_on_reference_files(tmp_path, ops, which):
+    """Random sequences of in-place edits (new columns, deletions, attribute updates, new groups,
+    several sessions) on copies of files written by libhdf5: the file stays structurally valid, the
+    original columns never change, and the edits read back."""
+    import shutil
+    src = os.path.join(os.path.dirname(__file__), "golden", "cool", which)
+    p = str(tmp_path / ("e_" + which))
+    shutil.copy(src, p)
+    os.chmod(p, 0o644)
+    base = "/resolutions/4" if which.endswith(".mcool") else "/"
+    ref = h5lite.File(src)[base]
+    keep = {k: ref[k][:] for k in ("pixels/bin1_id", "pixels/bin2_id", "pixels/count", "bins/start", "indexes/bin1_offset")}
+    model, attrs = {}, {}
+    f = h5write.File(p, "r+")
+    try:
+        for op, k, seed in ops:
+            g = f[base]["bins"]
+            name = f"c{k}"
+            rng = np.random.default_rng(seed)
+            if op == "add" and name not in model:
+                model[name] = rng.standard_normal(int(rng.integers(0, 300)))
+                g.create_dataset(name, data=model[name])
+            elif op == "del" and name in model:
+                del g[name]
+                del model[name]
+            elif op == "attr" and model:
+                tgt = sorted(model)[k % len(model)]
+                val = [int(seed % 97), float(seed % 13) / 7, f"s{seed % 11}", bool(seed & 1)][k % 4]
+                g[tgt].attrs[f"a{k % 3}"] = val
+                attrs.setdefault(tgt, {})[f"a{k % 3}"] = val
+            elif op == "group":
+                f[base].require_group(f"extra/g{k}")
+            elif op == "reopen":
+                f.close()
+                check(p)
+                f = h5write.File(p, "r+")
+            for gone in [t for t in attrs if t not in model]:
+                del attrs[gone]
+    finally:
+        f.close()
+    check(p)
+    r = h5lite.File(p)[base]
+    for k, v in keep.items():
+        assert np.array_equal(r[k][:], v), k
+    assert set(r["bins"].keys()) == {"chrom", "start", "end"} | set(model)
+    for name, v in model.items():
+        assert np.array_equal(r["bins"][name][:], v)
+        assert dict(r["bins"][name].attrs) == attrs.get(name, {})
+    os.remove(p)
