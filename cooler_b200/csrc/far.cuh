@@ -166,8 +166,10 @@ __device__ __forceinline__ void far_slot(const int4* __restrict__ px4, const int
   __syncwarp();
 }
 
+// WARPS = 8: 256-thread CTAs, two per SM (each with its own row block and w tiles), so a barrier
+// synchronises 8 warps instead of 16 (experimental).
 template <int WARPS, int U, bool kTma = false>
-__global__ void __launch_bounds__(WARPS * 32, 1)
+__global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1))
 ice_sweep_far_kernel(const cb200_ice st) {
   extern __shared__ double far_sm[];               // acc[FAR_ACC] | w tile [2][C]
   __shared__ int s_unit;

@@ -356,8 +356,9 @@ int cb200_set_far_tuning(int32_t far_unroll) {
 // K3 over the far-field blocks (far.cuh): one persistent CTA per SM claims units.
 static int ice_sweep_far(const cb200_ice* st, void* stream) {
   if (st->n_far_units <= 0) return 0;
-  if (st->far_col_shift < 1 || st->far_col_shift > 13 || (st->far_warps != 16 && st->far_warps != 32)) {
-    set_error_msg("ice_sweep: far_col_shift must be in 1..13 and far_warps 16 or 32");
+  if (st->far_col_shift < 1 || st->far_col_shift > 13 ||
+      (st->far_warps != 8 && st->far_warps != 16 && st->far_warps != 32)) {
+    set_error_msg("ice_sweep: far_col_shift must be in 1..13 and far_warps 8, 16 or 32");
     return -1;
   }
   const size_t smem = ((size_t)FAR_ACC + 2 * ((size_t)1 << st->far_col_shift)) * sizeof(double);
@@ -376,12 +377,14 @@ static int ice_sweep_far(const cb200_ice* st, void* stream) {
     CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
     attr_done = true;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = st->n_far_units < sms ? st->n_far_units : sms;
+  const int ctas = (st->far_warps == 8 ? 2 : 1) * sms;          // 8-warp CTAs: two per SM
+  const int grid = st->n_far_units < ctas ? st->n_far_units : ctas;
   cudaStream_t s = (cudaStream_t)stream;
   // CB200_FAR_TMA=1 (experimental, not the default): stage the column tiles of w with one bulk copy
   // (cp.async.bulk + mbarrier) per tile instead of per-thread 8-byte cp.async
@@ -393,10 +396,14 @@ static int ice_sweep_far(const cb200_ice* st, void* stream) {
       const int mx = (int)(want < kSmemLimit ? want : kSmemLimit);
       CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
       CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<8, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
       tma_attr_done = true;
     }
-    if (st->far_warps == 16) ice_sweep_far_kernel<16, 8, true><<<grid, 512, smem, s>>>(*st);
+    if (st->far_warps == 8) ice_sweep_far_kernel<8, 8, true><<<grid, 256, smem, s>>>(*st);
+    else if (st->far_warps == 16) ice_sweep_far_kernel<16, 8, true><<<grid, 512, smem, s>>>(*st);
     else ice_sweep_far_kernel<32, 4, true><<<grid, 1024, smem, s>>>(*st);
+  } else if (st->far_warps == 8) {
+    ice_sweep_far_kernel<8, 8><<<grid, 256, smem, s>>>(*st);
   } else if (st->far_warps == 16) {
     // default: 8 loads in flight per lane (measured 1.70 vs 2.15 ms with 4 on the 1 kb rank-0 shard)
     if (g_far_unroll == 2) ice_sweep_far_kernel<16, 2><<<grid, 512, smem, s>>>(*st);

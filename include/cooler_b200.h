@@ -242,7 +242,7 @@ typedef struct {
   int64_t* far_claim;                 /* [2] zero-initialised (self re-arming) */
   int32_t  n_far_units;
   int32_t  far_col_shift;             /* log2 C, 1..13; (rows + 2 C) * 8 B must fit the 227 KB of shared memory */
-  int32_t  far_warps;                 /* 16 or 32: warps per CTA = row slices per block */
+  int32_t  far_warps;                 /* 16 or 32 (8: experimental, two CTAs per SM): warps per CTA = row slices per block */
 } cb200_ice;
 
 /* Tuning of K3 (optional): ice_unroll in {0,1,2,4,8} = 128-bit stream loads kept in
