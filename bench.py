@@ -3,17 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-Workload (weak scaling, ~2e8 stored pixels per GPU, synthetic hg38 power-law Hi-C,
-cooler_b200/synth.py):  N=1 hg38 100 kb genome-wide ICE (BASELINE configs[1]);
-N=2 50 kb / 4e8 px; N=4 25 kb / 8e8 px; N=8 12.5 kb / 1.6e9 px, sharded by
-contiguous bin1 row ranges with one NCCL all-reduce of the n_bins marginal vector
-per pass.
+Workloads are BASELINE.json's configs (synthetic hg38 power-law Hi-C, cooler_b200/synth.py, seed 0):
 
-A "step" is one complete ICE iteration loop (reference defaults: mad_max=5,
-min_nnz=10, ignore_diags=2, tol=1e-5) to convergence over the HBM-resident table;
-value = stored pixels x marginal passes / time.  `e2e` is the same
-metric through the host-buffer API: pinned host arrays -> H2D -> build (filter, radix
-sort, prefilter marginals) -> loop -> bias back on the host, all inside the timed region.
+  N = 1, 2, 4   configs[2]: hg38 10 kb genome-wide ICE, 308 839 bins, ~1e9 stored pixels, the whole
+                table on one GPU or sharded by contiguous bin1 row ranges (STRONG scaling);
+  N = 8         configs[3]: hg38 1 kb genome-wide ICE, 3 088 298 bins, ~3e9 stored pixels, sharded
+                over the 8 GPUs, per-pass all-reduce of the n_bins float64 vector over NVLink.
+
+A "step" is one complete ICE iteration loop (reference defaults: mad_max=5, min_nnz=10,
+ignore_diags=2, tol=1e-5) to convergence over the HBM-resident table; value = stored pixels x
+marginal passes / time.  `e2e` is the same metric through the host-buffer API:
+pinned host arrays -> H2D -> build (filter, radix sorts, prefilter marginals) -> loop -> bias back
+on the host, all inside the timed region.  `parity` compares this very run with the CPU oracle
+(oracle/ice_numpy.py) outside the timed region.  `--impl reference` (and the `cpu_baseline` leg at
+N = 1) time the UNMODIFIED reference `cooler.balance_cooler` (installed copy in oracle/_ref,
+multiprocess.Pool(P).imap_unordered over an in-memory store) on the host cores.
 """
 from __future__ import annotations
 
@@ -30,14 +34,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-PX_PER_GPU = 200_000_000
-BASE_BINSIZE = 100_000
 ICE_KW = dict(ignore_diags=2, mad_max=5, min_nnz=10, min_count=0, tol=1e-5, max_iters=200)
+CONFIGS = {   # n_gpus -> (BASELINE config, binsize, stored-pixel target of the WHOLE table)
+    1: ("configs[2] C3", 10_000, 1_000_000_000), 2: ("configs[2] C3", 10_000, 1_000_000_000),
+    4: ("configs[2] C3", 10_000, 1_000_000_000), 8: ("configs[3] C4", 1_000, 3_000_000_000),
+}
+REF_PIXEL_PASS_BUDGET = 4.0e10   # reference arm: pixels x passes it may process (a few minutes of host time)
 
 
-def workload(n_gpus, px_per_gpu, binsize):
-    binsize = binsize or BASE_BINSIZE // n_gpus
-    return binsize, px_per_gpu * n_gpus
+def workload(n_gpus, binsize, nnz):
+    name, b, t = CONFIGS.get(n_gpus, CONFIGS[1])
+    if binsize or nnz:
+        name = "custom"
+    return name, int(binsize or b), int(nnz or t)
 
 
 def load_peaks():
@@ -94,48 +103,192 @@ class ClockSampler:
                 "reasons": sorted(reasons), "window": "warm-up + timed steps, 20 ms period"}
 
 
-def host_arrays_for_cpu(data):
-    """numpy views in the reference's dtypes (bin1_id materialised from the offsets)."""
+# ------------------------------------------------------------------------------- CPU side
+def host_px(data):
+    """numpy arrays in the reference's on-disk dtypes (bin1_id materialised from the offsets)."""
     off = data["bin1_offset"].numpy()
+    b1 = np.repeat(np.arange(data["n_bins"], dtype=np.int64), np.diff(off))
+    return {"bin1_id": b1, "bin2_id": data["bin2_id"].numpy().astype(np.int64, copy=False),
+            "count": data["count"].numpy()}
+
+
+def reference_passes(plan, data, n_passes, warmup, nproc=None):
+    """Time ``n_passes`` marginal passes of the UNMODIFIED reference (cooler._balance.balance_cooler,
+    installed copy oracle/_ref or /root/reference) over ``data`` registered as an in-memory store
+    (oracle/refshim.py), with ``multiprocess.Pool(P).imap_unordered`` as the CLI does
+    (cli/balance.py:237-243).  tol = 0 keeps it iterating; every pass logs "variance is ..."
+    (_balance.py:109) and the log timestamps delimit the passes.  Falls back to the numpy port
+    (oracle/ice_numpy.py, kind "port") when the reference package is not available."""
+    import logging
+    import warnings
+
+    from oracle import refshim
+    P = nproc or os.cpu_count() or 1
+    px = host_px(data)
+    nnz = len(px["bin2_id"])
     n = data["n_bins"]
-    b1 = np.repeat(np.arange(n, dtype=np.int64), np.diff(off))
-    return {"bin1_id": b1, "bin2_id": data["bin2_id"].numpy(), "count": data["count"].numpy()}
+    co = np.asarray(data["chrom_offset"])
+    chunk = int(max(1_000_000, nnz // (4 * P)))
+    note = (f"{n_passes} timed marginal passes (after {warmup} warm-up passes and the 2 prefilter passes) over "
+            f"{nnz} stored pixels, chunksize {chunk}, Pool({P}).imap_unordered; in-memory store (no HDF5 "
+            "decode) => upper bound on the file-backed reference; tol=0 so that it keeps iterating")
+    if not refshim.available():
+        return port_passes(data, px, n_passes, warmup, P, chunk, note)
+    import multiprocess as mp
+    from cooler_b200 import synth
+    nb = np.diff(co)
+    chrom = np.repeat(np.arange(len(nb), dtype=np.int32), nb)
+    start = np.concatenate([np.arange(k, dtype=np.int64) * plan.binsize for k in nb])
+    end = np.minimum(start + plan.binsize, np.repeat(plan.chromsizes, nb))
+    name = f"bench_{plan.binsize}_{nnz}.cool"
+    refshim.register(name, synth.HG38_NAMES, plan.chromsizes, chrom, start, end, px["bin1_id"], px["bin2_id"],
+                     px["count"], plan.binsize)
+    cooler = refshim.import_reference()
+    stamps = []
+
+    class Stamp(logging.Handler):
+        def emit(self, record):
+            if record.getMessage().startswith("variance is"):
+                stamps.append(time.perf_counter())
+
+    lg = logging.getLogger("cooler")
+    h, old, old_handlers, old_prop = Stamp(level=logging.INFO), lg.level, lg.handlers[:], lg.propagate
+    lg.handlers[:] = [h]                           # only the time stamps: nothing but the JSON line on stdout
+    lg.propagate = False
+    lg.setLevel(logging.INFO)
+    pool = mp.Pool(P)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            kw = {k: v for k, v in ICE_KW.items() if k not in ("tol", "max_iters")}
+            cooler._balance.balance_cooler(cooler.Cooler(name), tol=0.0, max_iters=warmup + n_passes,
+                                           chunksize=chunk, map=pool.imap_unordered, **kw)
+    finally:
+        pool.terminate()
+        lg.handlers[:] = old_handlers
+        lg.propagate = old_prop
+        lg.setLevel(old)
+        refshim._REGISTRY.pop(name, None)
+    assert len(stamps) == warmup + n_passes, (len(stamps), warmup, n_passes)
+    t = stamps[-1] - stamps[warmup - 1]
+    return {"value": nnz * n_passes / t, "unit": "pixels/s", "cores": P, "kind": "reference",
+            "sample": note + "; code: unmodified cooler._balance.balance_cooler v0.10.4 via oracle/refshim.py",
+            "seconds": t, "nnz": nnz}
 
 
-def cpu_ice_passes(data, n_passes, warmup=0, nproc=None):
-    """Time ``n_passes`` ICE marginal passes (PASS C of _balance.py:88-95: filters,
-    outer product with the bias, bincount marginals, fold) of the oracle over the
-    host arrays with a fork()ed process pool, the reference's `-p N` path."""
+def port_passes(data, px, n_passes, warmup, P, chunk, note):
     import multiprocessing as mp
 
     from oracle import ice_numpy
-    px = host_arrays_for_cpu(data)
-    nnz = len(px["bin2_id"])
-    n = data["n_bins"]
-    P = nproc or os.cpu_count() or 1
-    chrom_ids = np.repeat(np.arange(len(data["chrom_offset"]) - 1, dtype=np.int32), np.diff(data["chrom_offset"]))
+    nnz, n = len(px["bin2_id"]), data["n_bins"]
+    co = np.asarray(data["chrom_offset"])
+    chrom_ids = np.repeat(np.arange(len(co) - 1, dtype=np.int32), np.diff(co))
     ice_numpy.share(px, chrom_ids, n)
-    chunk = int(max(1_000_000, nnz // (4 * P)))
     spans = [(lo, min(lo + chunk, nnz)) for lo in range(0, nnz, chunk)]
     bias = np.ones(n)
     kw = dict(binarize=False, zero_trans=False, n_diags=ICE_KW["ignore_diags"], zero_cis=False)
-    ctx = mp.get_context("fork")
     times = []
-    with ctx.Pool(P) as pool:
-        for k in range(warmup + n_passes):
+    with mp.get_context("fork").Pool(P) as pool:
+        for _ in range(warmup + n_passes):
             t0 = time.perf_counter()
-            marg = ice_numpy.pool_marginal(pool.imap_unordered, spans, vec=bias, **kw)
-            nz = marg[marg != 0]
-            m = marg / nz.mean()
-            m[m == 0] = 1
-            bias = bias / m
+            ice_numpy.ice_step(bias, ice_numpy.pool_marginal(pool.imap_unordered, spans, vec=bias, **kw))
             times.append(time.perf_counter() - t0)
     t = float(np.sum(times[warmup:]))
     return {"value": nnz * n_passes / t, "unit": "pixels/s", "cores": P, "kind": "port",
-            "sample": f"{n_passes} ICE marginal passes over {nnz} stored pixels "
-                      f"({len(spans)} spans of {chunk}), Pool({P}).imap_unordered, oracle/ice_numpy.py; "
-                      "in-memory arrays (no HDF5 decode) => upper bound on the file-backed reference",
+            "sample": note + "; code: oracle/ice_numpy.py (reference package not installed in oracle/_ref)",
             "seconds": t, "nnz": nnz}
+
+
+def bounded_rows(plan, nnz_total, passes_total, mem_bytes_per_px=60):
+    """Rows [0, r) of the table the CPU arm runs on: the whole table when the pixel-pass budget and
+    the host memory allow, else the leading rows holding about the affordable number of pixels."""
+    import psutil
+    afford = REF_PIXEL_PASS_BUDGET / max(passes_total, 1)
+    afford = min(afford, 0.5 * psutil.virtual_memory().available / mem_bytes_per_px)
+    if afford >= nnz_total:
+        return (0, plan.n_bins), "the whole table"
+    cw = plan.row_weight_cum
+    r = int(np.searchsorted(cw, cw[-1] * afford / nnz_total))
+    r = max(1, min(r, plan.n_bins))
+    return (0, r), f"rows [0, {r}) of {plan.n_bins} (~{afford:.3g} of {nnz_total:.3g} pixels: pixel-pass / host-memory budget)"
+
+
+def oracle_parity(data, prob, state_factory, bias0_gpu, group, world, rank, full, device):
+    """Parity of THIS run against the CPU oracle (oracle/ice_numpy.py), outside the timed region.
+
+    Every rank evaluates the oracle's span pipeline (_init, filters, outer product, _marginalize) on
+    its own host shard; partial marginals are summed across ranks (integers exactly).  Checked:
+    the two prefilter marginals (exact), the filter mask (exact), then ``n`` passes of the oracle's
+    update loop against the same number of passes of the kernels (bias and variance to 1e-9) --
+    all passes to convergence (mask, pass count, scale, var, bias) when ``full``."""
+    import torch
+    from oracle import ice_numpy
+    px = host_px(data)
+    n = data["n_bins"]
+    co = np.asarray(data["chrom_offset"])
+    chrom_ids = np.repeat(np.arange(len(co) - 1, dtype=np.int32), np.diff(co))
+    nnz = len(px["bin2_id"])
+    pool = None
+    if world == 1 and nnz > 20_000_000:
+        import multiprocessing as mp
+        ice_numpy.share(px, chrom_ids, n)
+        pool = mp.get_context("fork").Pool(os.cpu_count() or 1)
+    chunk = int(max(1_000_000, nnz // (4 * (os.cpu_count() or 1)))) if pool else 10_000_000
+    spans = [(lo, min(lo + chunk, nnz)) for lo in range(0, nnz, chunk)]
+
+    def marginal(**kw):
+        if pool is not None:
+            part = ice_numpy.pool_marginal(pool.imap_unordered, spans, **kw)
+        else:
+            part = ice_numpy._marginal(px, chrom_ids, n, spans, map, **kw)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.from_numpy(part).to(device)
+            dist.all_reduce(t, group=group)
+            part = t.cpu().numpy()
+        return part
+
+    t0 = time.perf_counter()
+    base = dict(zero_trans=False, n_diags=ICE_KW["ignore_diags"], zero_cis=False)
+    try:
+        m_nnz = marginal(binarize=True, vec=None, **base)
+        m_sum = marginal(binarize=False, vec=None, **base)
+        out = {"oracle": "oracle/ice_numpy.py", "prefilter_marginals_exact":
+               bool(np.array_equal(m_nnz, prob.marg_nnz) and np.array_equal(m_sum, prob.marg_sum))}
+        bias = ice_numpy.initial_bias(n, m_nnz, m_sum.copy(), co, mad_max=ICE_KW["mad_max"],
+                                      min_nnz=ICE_KW["min_nnz"], min_count=ICE_KW["min_count"])
+        out["mask_exact"] = bool(np.array_equal(bias == 0, np.asarray(bias0_gpu) == 0))
+        out["masked_bins"] = int((bias == 0).sum())
+        n_passes = ICE_KW["max_iters"] if full else 3
+        variances, mean = [], np.nan
+        for _ in range(n_passes):
+            var, mean = ice_numpy.ice_step(bias, marginal(binarize=False, vec=bias, **base))
+            variances.append(float(var))
+            if var < ICE_KW["tol"]:
+                break
+        state = state_factory(len(variances))
+        state.run()
+        res = state.results()
+        g_bias, g_var = res["bias"], res["var_hist"][: len(variances), 0]
+        keep = bias != 0
+        out["passes_compared"] = len(variances)
+        out["max_rel_bias_diff"] = float(np.max(np.abs(g_bias[keep] / bias[keep] - 1))) if keep.any() else 0.0
+        out["max_rel_var_diff"] = float(np.max(np.abs(g_var / np.asarray(variances) - 1)))
+        out["zero_bias_bins_equal"] = bool(np.array_equal(g_bias == 0, bias == 0))
+        if full:
+            out["converged_pass_count_equal"] = bool(int(res["seg_iters"][0]) == len(variances)
+                                                     and bool(res["seg_done"][0]) == (variances[-1] < ICE_KW["tol"]))
+            out["rel_scale_diff"] = float(abs(res["seg_scale"][0] / mean - 1))
+        out["scope"] = ("all passes to convergence" if full else "first 3 passes") + \
+                       (" on the whole table" if world == 1 else f"; every rank on its own shard, partials summed over {world} ranks")
+        out["ok"] = bool(out["prefilter_marginals_exact"] and out["mask_exact"] and out["zero_bias_bins_equal"]
+                         and out["max_rel_bias_diff"] <= 1e-9 and out["max_rel_var_diff"] <= 1e-9
+                         and out.get("converged_pass_count_equal", True))
+    finally:
+        if pool is not None:
+            pool.terminate()
+    out["seconds"] = time.perf_counter() - t0
+    return out
 
 
 def main():
@@ -144,15 +297,19 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--px-per-gpu", type=int, default=PX_PER_GPU)
-    ap.add_argument("--binsize", type=int, default=0)
+    ap.add_argument("--binsize", type=int, default=0, help="override the config's bin size")
+    ap.add_argument("--nnz", type=float, default=0, help="override the config's stored-pixel target (whole table)")
     ap.add_argument("--mode", default="gw", choices=["gw", "cis", "trans"])
     ap.add_argument("--cpu-passes", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--parity", default="auto", choices=["auto", "full", "3"],
+                    help="oracle passes compared: all to convergence, or the first 3 (auto: full on one GPU)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--host-bin2", default="int64", choices=["int64", "int32"],
-                    help="dtype of the pinned host bin2_id column of the e2e leg: int64 = the on-disk "
-                         "dtype (default); int32 = narrowed by the HDF5 read as PixelTable.from_cooler does")
+    ap.add_argument("--host-bin2", default="int32", choices=["int64", "int32"],
+                    help="dtype of the pinned host bin2_id column of the e2e leg: int32 = narrowed while "
+                         "reading the file, as read_cooler_arrays does (default); int64 = the on-disk dtype")
+    ap.add_argument("--layout", default=None, help="force a sweep layout (IceProblem band=...), e.g. rows, allblocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
 
@@ -160,31 +317,37 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = max(args.gpus, world)
-    binsize, nnz_target = workload(n_gpus, args.px_per_gpu, args.binsize)
+    cfg_name, binsize, nnz_target = workload(n_gpus, args.binsize, args.nnz)
 
     import torch
 
     from cooler_b200 import synth
 
     plan = synth.SynthPlan(binsize, nnz_target, seed=0)
-    cfg = {"workload": f"synthetic hg38 {binsize} bp genome-wide ICE ({plan.n_bins} bins, ~{nnz_target:.3g} px target), "
-                       f"mode={args.mode}, defaults mad_max=5 min_nnz=10 ignore_diags=2 tol=1e-5",
-           "binsize": binsize, "n_bins": plan.n_bins, "mode": args.mode,
-           "sharding": f"{world} contiguous bin1 row ranges" if world > 1 else "single GPU",
+    # identical in both arms (the driver compares it): only what follows from the command line
+    cfg = {"workload": f"BASELINE {cfg_name}: synthetic hg38 {binsize} bp genome-wide ICE, {plan.n_bins} bins, "
+                       f"~{nnz_target:.3g} stored pixels (whole table), mode={args.mode}, defaults mad_max=5 "
+                       "min_nnz=10 ignore_diags=2 tol=1e-5",
+           "binsize": binsize, "n_bins": plan.n_bins, "nnz_target": nnz_target, "mode": args.mode,
+           "sharding": f"{n_gpus} contiguous bin1 row ranges" if n_gpus > 1 else "single GPU",
            "l2": "inputs larger than L2 (no flush needed)"}
+    scaling = "weak" if cfg_name.endswith("C4") else "strong"
 
     # ------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return
-        blocks = plan.shard_rows(0, n_gpus)
-        data = synth.generate(plan, rows=blocks, pin=False)
-        res = cpu_ice_passes(data, max(args.steps, 1), warmup=args.warmup)
+        K = max(args.steps, 1)
+        rows, what = bounded_rows(plan, nnz_target, args.warmup + K + 2)
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"
+        data = synth.generate(plan, rows=rows, device=dev, pin=False)
+        res = reference_passes(plan, data, K, args.warmup)
+        res["sample"] = f"{what}; " + res["sample"]
         val = res["value"]
         line = {"impl": "reference", "metric": "ICE pixels/s", "value": val, "unit": "pixels/s",
                 "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * res["seconds"] / max(args.steps, 1), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "ms_per_step": 1e3 * res["seconds"] / K, "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg, "cpu_baseline": res,
                 "e2e": {"value": val, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -202,8 +365,9 @@ def main():
     import cooler_b200
     from cooler_b200.balance import IceProblem, IceState, prefilter_bias
 
+    dev = f"cuda:{local_rank}"
     blocks = plan.shard_rows(rank, world)
-    data = synth.generate(plan, rows=blocks, device=f"cuda:{local_rank}")
+    data = synth.generate(plan, rows=blocks, device=dev)
     torch.cuda.empty_cache()
     nnz_local = data["nnz"]
     nnz_total = torch.tensor([nnz_local], dtype=torch.int64, device="cuda")
@@ -219,9 +383,8 @@ def main():
 
     # --- resident leg: table and filtered copies already in HBM ---------------
     table = cooler_b200.PixelTable.from_arrays(data["bin1_offset"], data["bin2_id"], data["count"],
-                                               data["chrom_offset"], device=f"cuda:{local_rank}",
-                                               row_range=data["row_range"])
-    prob = IceProblem(table, ignore_diags=ICE_KW["ignore_diags"], group=group, **kw)
+                                               data["chrom_offset"], device=dev, row_range=data["row_range"])
+    prob = IceProblem(table, ignore_diags=ICE_KW["ignore_diags"], group=group, band=args.layout, **kw)
     bias0 = prefilter_bias(prob, table.chrom_offset, mad_max=ICE_KW["mad_max"], min_nnz=ICE_KW["min_nnz"],
                            min_count=ICE_KW["min_count"], blacklist=None, x0=None)
     n = table.n_bins
@@ -251,6 +414,7 @@ def main():
     passes_per_step = int(state.results()["seg_iters"].max())
     barrier()
     state.sweep_events = []
+    state.comm_events = []
     state.launches = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launched = 0
@@ -276,11 +440,6 @@ def main():
     comm_ms = [c0.elapsed_time(c1) for k, (c0, c1) in enumerate(state.comm_events)
                if (k % per_step) < passes_per_step]
     comm_ms_avg = float(np.mean(comm_ms)) if comm_ms else 0.0
-    # slowest / fastest rank of the dominant kernel (shard balance) and the all-reduce share
-    rk = torch.tensor([sweep_ms_avg, -sweep_ms_avg, comm_ms_avg], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(rk, op=dist.ReduceOp.MAX)
-    sweep_ms_max, sweep_ms_min, comm_ms_max = float(rk[0]), -float(rk[1]), float(rk[2])
     gpu_launches = state.launches
     state.sweep_events = None
     value = nnz_total * passes_per_step * args.steps / (t_ms * 1e-3)
@@ -288,29 +447,61 @@ def main():
     peak, peak_src = load_peaks()
     bytes_pass_local = prob.bytes_per_pass()
     achieved = bytes_pass_local / (sweep_ms_avg * 1e-3) / 1e9
+    # the roofline line is the SLOWEST rank's: the loop runs at its pace
+    per_rank = torch.zeros(world, 3, dtype=torch.float64, device="cuda")
+    per_rank[rank] = torch.tensor([sweep_ms_avg, achieved / peak, comm_ms_avg], dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(per_rank)
+    per_rank = per_rank.cpu().numpy()
+    slow = int(np.argmin(per_rank[:, 1]))
     # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel on
-    # this workload (profiles/r01_traffic.json), reported only when the pixel count matches
+    # this workload (profiles/*traffic.json), reported only when the pixel count matches
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tp) and world == 1:
-        with open(tp) as f:
-            for ent in json.load(f):
-                if ent["binsize"] == binsize and ent["mode"] == args.mode and ent["nnz_effective"] == prob.nnz_eff:
-                    traffic = ent["dram_bytes_per_launch"]
-    layout = ("all blocks" if getattr(prob, "far_copies", None) and not prob.subs else
-              "band strips + far blocks" if getattr(prob, "far_copies", None) else
-              f"column strips of {1 << prob.strip_shift} bins" if prob.strip_shift is not None else "whole copies")
-    if getattr(prob, "far_copies", None) and not prob.subs:
-        kernel_name = "ice_sweep_far_kernel"          # every pixel through the 2-D blocked kernel (csrc/far.cuh)
-    elif getattr(prob, "far_copies", None):
-        kernel_name = "ice_sweep_strips_kernel + ice_sweep_far_kernel"
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        tp = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(tp) and world == 1 and traffic is None:
+            with open(tp) as f:
+                for ent in json.load(f):
+                    if ent["binsize"] == binsize and ent["mode"] == args.mode and ent["nnz_effective"] == prob.nnz_eff:
+                        traffic = ent["dram_bytes_per_launch"]
+    far = bool(getattr(prob, "far_copies", None))
+    if far and not prob.subs:
+        layout = "2-D blocks, lane rows" if prob.band == "rows" else "2-D blocks, lane pieces"
+        kernel_name = "ice_sweep_rows_kernel" if prob.band == "rows" else "ice_sweep_far_kernel"
+    elif far:
+        layout, kernel_name = "band strips + far blocks", "ice_sweep_strips_kernel + ice_sweep_far_kernel"
+    elif prob.strip_shift is not None:
+        layout, kernel_name = f"column strips of {1 << prob.strip_shift} bins", "ice_sweep_strips_kernel"
     else:
-        kernel_name = "ice_sweep_strips_kernel" if prob.strip_shift is not None else "ice_sweep_kernel"
-    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": bytes_pass_local, "kernel_ms_avg": sweep_ms_avg,
-                "formula": "16 B x effective pixels + 40 B x n_bins (per rank), SURVEY.md 8d",
-                "frac_of_nominal_8TBs": achieved / 8000.0}
+        layout, kernel_name = "whole copies", "ice_sweep_kernel"
+    bytes_all = torch.tensor([float(bytes_pass_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        gathered = [torch.zeros_like(bytes_all) for _ in range(world)]
+        dist.all_gather(gathered, bytes_all)
+        bytes_slow = float(gathered[slow].item())
+    else:
+        bytes_slow = float(bytes_pass_local)
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": float(per_rank[slow, 1] * peak), "peak": peak,
+                "unit": "GB/s", "frac": float(per_rank[slow, 1]), "traffic": traffic, "peak_source": peak_src,
+                "rank": slow, "algorithmic_bytes_per_launch": int(bytes_slow),
+                "kernel_ms_avg": float(per_rank[slow, 0]),
+                "formula": "16 B x effective pixels + 40 B x n_bins (per rank), SURVEY.md 8d; the slowest rank's launch",
+                "frac_per_rank": [round(float(x), 4) for x in per_rank[:, 1]],
+                "frac_of_nominal_8TBs": float(per_rank[slow, 1] * peak / 8000.0)}
+
+    # --- parity gate (outside the timed region): this run against the CPU oracle ---------------
+    parity = None
+    if not args.no_parity and args.mode == "gw":
+        full = args.parity == "full" or (args.parity == "auto" and world == 1)
+
+        def state_factory(k):
+            return IceState(prob, bias0.copy(), None, seg_offset, ICE_KW["tol"], k)
+
+        parity = oracle_parity(data, prob, state_factory, bias0, group, world, rank, full, dev)
+        ok = torch.tensor([1 if parity["ok"] else 0], device="cuda")
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        parity["ok"] = bool(ok.item())
 
     # --- e2e leg: host buffers in, bias on the host out ---------------------------
     del state, prob, table
@@ -328,7 +519,7 @@ def main():
         t0 = time.perf_counter()
         bias, stats, info = cooler_b200.balance_arrays(
             data["bin1_offset"], data["bin2_id"], data["count"], data["chrom_offset"],
-            device=f"cuda:{local_rank}", row_range=data["row_range"], group=group, return_info=True,
+            device=dev, row_range=data["row_range"], group=group, return_info=True, band=args.layout,
             **kw, **{k_: v for k_, v in ICE_KW.items()})
         barrier()
         if k > 0:
@@ -342,26 +533,31 @@ def main():
            "seconds_per_call": float(t_e.item()), "passes": e2e_passes,
            "host_bin2_dtype": args.host_bin2,
            "n_subcopies": info["n_subcopies"],
-           "api": "cooler_b200.balance_arrays(pinned host arrays) -> numpy bias (build pipelined with the H2D copy)"}
+           "api": "cooler_b200.balance_arrays(pinned host arrays) -> numpy bias (per rank: its row shard)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_ice_passes(data, args.cpu_passes)
+        rows, what = bounded_rows(plan, nnz_total, args.cpu_passes + 3 + 2)
+        sample = data if rows == (0, plan.n_bins) else synth.generate(plan, rows=rows, device=dev, pin=False)
+        cpu = reference_passes(plan, sample, args.cpu_passes, 3)
+        cpu["sample"] = f"{what}; " + cpu["sample"]
 
     if rank == 0:
-        cfg.update({"sweep_layout": layout, "nnz_stored": nnz_total, "nnz_effective": nnz_eff, "passes_per_step": passes_per_step,
-                    "converged": converged, "masked_bins": int(np.isnan(bias).sum())})
+        detail = {"sweep_layout": layout, "nnz_stored": nnz_total, "nnz_effective": nnz_eff,
+                  "passes_per_step": passes_per_step, "converged": converged,
+                  "masked_bins": int(np.isnan(bias).sum())}
         line = {"metric": "ICE pixels/s", "value": value, "unit": "pixels/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_ms / max(args.steps, 1),
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic", "config": cfg, "clocks": clocks, "e2e": e2e,
-                "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu,
+                "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": cfg, "detail": detail, "clocks": clocks, "e2e": e2e,
+                "gpu_launches": gpu_launches, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
                 "time_to_converge_s": {"resident_loop": t_ms * 1e-3 / max(args.steps, 1),
                                        "e2e_from_pinned_host": float(t_e.item())},
                 "per_pass_ms": {"total": t_ms / max(args.steps, 1) / max(passes_per_step, 1),
-                                "sweep_rank0": sweep_ms_avg, "sweep_slowest_rank": sweep_ms_max,
-                                "sweep_fastest_rank": sweep_ms_min,
-                                "allreduce_incl_wait_slowest_rank": comm_ms_max}}
+                                "sweep_slowest_rank": float(per_rank[:, 0].max()),
+                                "sweep_fastest_rank": float(per_rank[:, 0].min()),
+                                "sweep_per_rank": [round(float(x), 4) for x in per_rank[:, 0]],
+                                "allreduce_incl_wait_slowest_rank": float(per_rank[:, 2].max())}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

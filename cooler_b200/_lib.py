@@ -53,6 +53,7 @@ class Ice(C.Structure):
         ("far_copies", C.c_void_p), ("far_units", C.c_void_p), ("far_tiles", C.c_void_p),
         ("far_parts", C.c_void_p), ("far_claim", C.c_void_p),
         ("n_far_units", C.c_int32), ("far_col_shift", C.c_int32), ("far_warps", C.c_int32),
+        ("far_layout", C.c_int32), ("far_stages", C.c_int32),
     ]
 
 
@@ -94,6 +95,12 @@ SIGNATURES = {
     "cb200_far_finish": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "cb200_far_slot_chunks": (C.c_int, [_P, _I64, _P, _P]),
     "cb200_far_interleave": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P]),
+    "cb200_rows_warps": (C.c_int, []),
+    "cb200_rows_flags": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
+    "cb200_rows_run_starts": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "cb200_rows_run_keys": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "cb200_rows_slot_steps": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
+    "cb200_rows_place": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P]),
     "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),

@@ -21,6 +21,7 @@ import torch
 from . import _lib
 from .table import (PixelTable, TableCopy, _new_px, _ptr, _stream, _use_device,  # noqa: F401
                     far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays,
+                    rows_blocks, shard_rows_by_pixels,
                     strip_partition, swap_key_other, transpose_from)
 
 __all__ = ["balance_cooler", "balance_table", "balance_arrays", "ConvergenceWarning", "IceProblem"]
@@ -163,15 +164,23 @@ class IceProblem:
             free = torch.cuda.mem_get_info(table.device)[0]
             if 60 * csr.nnz > free:
                 self.band = False
-        if band == "allblocks" or self.band == "allblocks":   # every pixel through the 2-D blocked kernel (csrc/far.cuh)
-            self.band, self.strip_shift = "allblocks", None
+        if band in ("allblocks", "rows") or self.band in ("allblocks", "rows"):
+            # every pixel through a 2-D blocked kernel: "rows" = lane rows (csrc/rows.cuh), "allblocks" =
+            # lane-interleaved pieces (csrc/far.cuh)
+            self.band, self.strip_shift = (band if band in ("allblocks", "rows") else self.band), None
             if cval is None:
                 ckeys, cval = swap_key_other(ckeys, csc.px, csc.nnz)
             n1, n2 = csr.nnz, csc.nnz
             self.csr = self.csc = csr = csc = None
-            self.far_copies = [far_blocks(tkey[:n1], tval, n1, n_bins, self.far_col_shift, self.far_warps)]
+            if self.band == "rows":
+                build = lambda k, v, m: rows_blocks(k, v, m, n_bins, self.far_col_shift)   # noqa: E731
+            else:
+                build = lambda k, v, m: far_blocks(k, v, m, n_bins, self.far_col_shift, self.far_warps)   # noqa: E731
+            self.far_copies = [build(tkey[:n1], tval, n1)]
             tkey = tval = None
-            self.far_copies.append(far_blocks(ckeys[:n2], cval, n2, n_bins, self.far_col_shift, self.far_warps))
+            self.far_copies.append(build(ckeys[:n2], cval, n2))
+            if self.band == "rows" and any(f is None for f, m in zip(self.far_copies, (n1, n2)) if m):
+                raise ValueError("duplicate pixels: the lane-rows layout cannot be built for this table")
             self.subs = []
         elif sh is None:
             self.subs = [csr.tight(), csc.tight()]
@@ -437,7 +446,7 @@ class IceState:
         if far:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
             per_sm = int(os.environ.get("CB200_FAR_UNITS_PER_SM", 4))
-            target = max(sum(f.nnz for f in far) // (sms * per_sm), 4096)
+            target = max(sum(int(f.tile_counts.sum()) for f in far) // (sms * per_sm), 4096)
             units, tiles, rb_units = plan_far_units([(f.rb0, f.j0, f.tile_counts) for f in far], target)
             n_far_units = len(units)
             t["far_units"] = torch.from_numpy(np.ascontiguousarray(units)).to(dev)
@@ -482,6 +491,10 @@ class IceState:
             for k in ("far_copies", "far_units", "far_tiles", "far_parts", "far_claim"):
                 setattr(st, k, t[k].data_ptr())
             st.far_col_shift, st.far_warps = far[0].col_shift, far[0].warps
+            st.far_layout = int(getattr(far[0], "layout", 0))
+            # lane rows: ring of w tiles next to the R + 16 row accumulators, as many stages as fit 227 KB
+            tile_b, acc_b = 8 << far[0].col_shift, 8 * (far_rows() + 16)
+            st.far_stages = int(min(8, max(2, (227 * 1024 - 512 - acc_b) // tile_b)))
         self.st = st
         self.prob = prob
         self.flag_host = torch.zeros(1, dtype=_I32).pin_memory() if torch.cuda.is_available() else None
@@ -720,7 +733,7 @@ def balance_arrays(bin1_offset, bin2_id, count, chrom_offset, *, cis_only=False,
 def balance_cooler(clr, *, cis_only=False, trans_only=False, ignore_diags=2, mad_max=5, min_nnz=10,
                    min_count=0, blacklist=None, rescale_marginals=True, x0=None, tol=1e-5,
                    max_iters=200, chunksize=10_000_000, map=map, use_lock=False, store=False,
-                   store_name="weight", device="cuda"):
+                   store_name="weight", device="cuda", group=None):
     """Iterative correction of a cooler on the GPU.
 
     Same signature, return value ``(bias, stats)`` and side effects as
@@ -728,26 +741,45 @@ def balance_cooler(clr, *, cis_only=False, trans_only=False, ignore_diags=2, mad
     ``use_lock`` are accepted for compatibility and ignored: the pixel table is
     read once and stays resident in HBM.  ``clr`` is a ``cooler.Cooler`` or any
     object with the same read protocol (e.g. ``cooler_b200.store.MemCooler``).
+
+    ``group``: a ``torch.distributed`` process group (NCCL, one rank per GPU).  Where the
+    reference hands pixel spans to a process pool (``map=Pool.imap_unordered``,
+    cli/balance.py:237-259), every rank here reads the stored pixels of ITS contiguous bin1 row
+    range ``pixels[bin1_offset[r_g]:bin1_offset[r_g+1]]`` (about nnz / world pixels,
+    table.shard_rows_by_pixels), keeps that shard resident on its GPU, and the per-pass partial
+    marginal vectors are summed over NVLink.  Every rank returns the same ``(bias, stats)``;
+    rank 0 alone stores.  Call it on all ranks, e.g.
+    ``torchrun --nproc-per-node 8 -m cooler_b200.cli balance FILE.cool``.
     """
-    bin1_offset, bin2, count, chrom_offset = read_cooler_arrays(clr)
+    rows = None
+    rank = 0
+    if group is not None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        full_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
+        rows = shard_rows_by_pixels(full_offset, rank, world)
+    bin1_offset, bin2, count, chrom_offset = read_cooler_arrays(clr, rows=rows)
     try:
         chromnames = list(clr.chroms()["name"][:])
     except Exception:  # pragma: no cover - duck-typed stores without a chroms selector
         chromnames = None
     bias, stats = balance_arrays(
-        bin1_offset, bin2, count, chrom_offset, device=device,
+        bin1_offset, bin2, count, chrom_offset, device=device, row_range=rows, group=group,
         cis_only=cis_only, trans_only=trans_only, ignore_diags=ignore_diags, mad_max=mad_max,
         min_nnz=min_nnz, min_count=min_count, blacklist=blacklist,
         rescale_marginals=rescale_marginals, x0=x0, tol=tol, max_iters=max_iters,
-        chromnames=chromnames)
+        chromnames=chromnames if rank == 0 else None)
 
-    if store:                                                     # _balance.py:469-475
+    if store and rank == 0:                                       # _balance.py:469-475
         with clr.open("r+") as grp:
             if store_name in grp["bins"]:
                 del grp["bins"][store_name]
             h5opts = {"compression": "gzip", "compression_opts": 6}
             grp["bins"].create_dataset(store_name, data=bias, **h5opts)
             grp["bins"][store_name].attrs.update(stats)
+    if store and group is not None:
+        import torch.distributed as dist
+        dist.barrier(group)                                       # the column exists when any rank returns
     return bias, stats
 
 

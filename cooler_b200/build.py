@@ -10,8 +10,8 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC_DIR = os.path.join(_HERE, "csrc")
-SOURCES = ["prims.cu", "table.cu", "ice.cu", "coarsen.cu", "fetch.cu"]
-HEADERS = ["common.cuh", "walk.cuh", "far.cuh", os.path.join("..", "..", "include", "cooler_b200.h")]
+SOURCES = ["prims.cu", "table.cu", "ice.cu", "rows.cu", "coarsen.cu", "fetch.cu"]
+HEADERS = ["common.cuh", "walk.cuh", "far.cuh", "rows.cuh", os.path.join("..", "..", "include", "cooler_b200.h")]
 OUT = os.path.join(_HERE, "libcooler_b200.so")
 
 NVCC_FLAGS = [

@@ -95,6 +95,51 @@ def _blacklist_bins(clr, path):
     return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
 
 
+def _dist_group():
+    """(process group, rank) when launched by torchrun with several ranks (one per GPU, NCCL),
+    else (None, 0).  Binds this process to GPU LOCAL_RANK."""
+    import os
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return None, 0
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lg = logging.getLogger("cooler")
+    if dist.get_rank() != 0:
+        lg.setLevel(logging.ERROR)                     # one log stream: rank 0's
+    return dist.group.WORLD, dist.get_rank()
+
+
+def _on_rank0(group, rank, fn):
+    """Run ``fn`` on rank 0 and hand its result (or its exception) to every rank."""
+    if group is None:
+        return fn()
+    import torch.distributed as dist
+    box = [None]
+    if rank == 0:
+        try:
+            box[0] = ("ok", fn())
+        except BaseException as e:  # noqa: BLE001 - re-raised on every rank
+            box[0] = ("err", e)
+    dist.broadcast_object_list(box, src=0, group=group)
+    kind, val = box[0]
+    if kind == "err":
+        if rank == 0:
+            raise val
+        sys.exit(2)
+    return val
+
+
+def _finish_dist(group):
+    if group is not None:
+        import torch.distributed as dist
+        dist.barrier(group)
+        dist.destroy_process_group()
+
+
 @cli.command()
 @click.argument("cool_uri", type=str, metavar="COOL_PATH")
 @click.option("--cis-only", is_flag=True, default=False,
@@ -132,33 +177,44 @@ def _blacklist_bins(clr, path):
 def balance(cool_uri, nproc, chunksize, mad_max, min_nnz, min_count, blacklist, ignore_diags, tol,
             cis_only, trans_only, max_iters, name, force, check, stdout, convergence_policy,
             ignore_dist):
-    """Matrix balancing on the GPU.  COOL_PATH : Path to a COOL file."""
+    """Matrix balancing on the GPU.  COOL_PATH : Path to a COOL file.
+
+    Multi-GPU: launch one process per GPU with torchrun, e.g.
+    ``torchrun --nproc-per-node 8 -m cooler_b200.cli balance FILE.cool``; every rank reads and keeps
+    its own row range of the pixel table (where the reference forks ``--nproc`` workers,
+    cli/balance.py:237-243), rank 0 checks, reports and writes."""
+    group, rank = _dist_group()
     cool_path, group_path = store.parse_cooler_uri(cool_uri)
+
+    def pre():
+        """Checks and column clean-up (rank 0).  Returns an exit code or None to go on."""
+        clr = store.open_cooler(cool_uri)
+        if check:                                                 # cli/balance.py:180-188
+            with clr.open("r") as grp:
+                if name not in grp["bins"]:
+                    click.echo(f"{cool_path}: No '{name}' column found.")
+                    return 1
+                click.echo(f"{cool_path}::{group_path} is balanced.")
+                return 0
+        if cis_only and trans_only:                               # 190-193
+            raise click.UsageError("Provide at most one of --cis-only and --trans-only flags")
+        # 195-206 (the reference opens "r+" here even with --stdout; read-only stores -- a .cool read
+        # by the built-in HDF5 reader -- can still print their weights)
+        with clr.open("r" if stdout else "r+") as grp:
+            if name in grp["bins"] and not stdout:
+                if not force:
+                    print(f"'{name}' column already exists. Use --force option to overwrite.", file=sys.stderr)
+                    return 1
+                del grp["bins"][name]
+        return None
+
+    code = _on_rank0(group, rank, pre)
+    if code is not None:
+        sys.exit(code)
     clr = store.open_cooler(cool_uri)
 
-    if check:                                                     # cli/balance.py:180-188
-        with clr.open("r") as grp:
-            if name not in grp["bins"]:
-                click.echo(f"{cool_path}: No '{name}' column found.")
-                sys.exit(1)
-            else:
-                click.echo(f"{cool_path}::{group_path} is balanced.")
-                sys.exit(0)
-
-    if cis_only and trans_only:                                   # 190-193
-        raise click.UsageError("Provide at most one of --cis-only and --trans-only flags")
-
-    # 195-206 (the reference opens "r+" here even with --stdout; read-only stores -- a .cool read
-    # by the built-in HDF5 reader -- can still print their weights)
-    with clr.open("r" if stdout else "r+") as grp:
-        if name in grp["bins"] and not stdout:
-            if not force:
-                print(f"'{name}' column already exists. Use --force option to overwrite.", file=sys.stderr)
-                sys.exit(1)
-            else:
-                del grp["bins"][name]
-
-    logger.info(f'Balancing "{cool_uri}"')
+    if rank == 0:
+        logger.info(f'Balancing "{cool_uri}"')
     bad_bins = _blacklist_bins(clr, blacklist) if blacklist is not None else None
     if ignore_dist is not None:                                   # 234-235
         ignore_diags = max(ignore_diags, int(np.ceil(ignore_dist / clr.binsize)))
@@ -168,8 +224,12 @@ def balance(cool_uri, nproc, chunksize, mad_max, min_nnz, min_count, blacklist, 
         bias, stats = balance_cooler(
             clr, chunksize=chunksize, cis_only=cis_only, trans_only=trans_only, tol=tol,
             min_nnz=min_nnz, min_count=min_count, blacklist=bad_bins, mad_max=mad_max,
-            max_iters=max_iters, ignore_diags=ignore_diags, rescale_marginals=True, use_lock=False)
+            max_iters=max_iters, ignore_diags=ignore_diags, rescale_marginals=True, use_lock=False,
+            group=group)
 
+    if rank != 0:                                                 # every rank holds the same result
+        _finish_dist(group)
+        return
     if not np.all(stats["converged"]):                            # 265-277
         logger.error("Iteration limit reached without convergence")
         if convergence_policy == "store_final":
@@ -179,9 +239,11 @@ def balance(cool_uri, nproc, chunksize, mad_max, min_nnz, min_count, blacklist, 
             bias[:] = np.nan
         elif convergence_policy == "discard":
             logger.error("Discarding result and aborting.")
+            _finish_dist(group)
             sys.exit(0)
         elif convergence_policy == "error":
             logger.error("Discarding result and aborting.")
+            _finish_dist(group)
             sys.exit(1)
 
     if stdout:                                                    # 279-282
@@ -192,6 +254,7 @@ def balance(cool_uri, nproc, chunksize, mad_max, min_nnz, min_count, blacklist, 
             h5opts = {"compression": "gzip", "compression_opts": 6}
             grp["bins"].create_dataset(name, data=bias, **h5opts)
             grp["bins"][name].attrs.update(stats)
+    _finish_dist(group)
 
 
 @cli.command()

@@ -351,7 +351,7 @@ class Dataset:
 
     def __getitem__(self, key):
         out = None
-        if isinstance(key, slice) and len(self.shape) == 1 and self._layout[1] == 2 and self._as is None:
+        if isinstance(key, slice) and len(self.shape) == 1 and self._layout[1] == 2:
             lo, hi, step = key.indices(self.shape[0])
             if step == 1:
                 out = self._read_chunked_1d(lo, max(hi, lo))

@@ -290,6 +290,73 @@ def far_blocks(key_other, val_rowcount, n, n_bins, col_shift, warps):
     return fc
 
 
+def rows_blocks(key_other, val_rowcount, n, n_bins, col_shift):
+    """Row-ordered stream (key = gathered bin, val = {row, count}) -> FarCopy in the "lane rows"
+    arrangement (csrc/rows.cuh, csrc/rows.cu; build steps in include/cooler_b200.h).
+
+    Returns None when a row holds more records in one column tile than the tile has columns
+    (duplicate pixels), which the arrangement cannot represent."""
+    dev = key_other.device
+    n = int(n)
+    if n == 0:
+        return None
+    warps = _lib.load().cb200_rows_warps()
+    FAR_ROW_SHIFT = _lib.far_row_shift()
+    n_j = ((max(n_bins, 1) - 1) >> col_shift) + 1
+    n_rb_all = ((max(n_bins, 1) - 1) >> FAR_ROW_SHIFT) + 1
+    ks, vs = sort_pairs(key_other[:n], val_rowcount, key_bits_for(n_j), key_shift=col_shift)
+    kr, vr = swap_key_other(ks, vs, n)            # key = row, val = {other, count}
+    del ks, vs
+    if n_rb_all > 1:
+        kr, vr = sort_pairs(kr, vr, key_bits_for(n_rb_all), key_shift=FAR_ROW_SHIFT)
+    ends = kr[torch.tensor([0, n - 1], device=dev)].cpu().numpy()
+    rb0, rb1 = int(ends[0]) >> FAR_ROW_SHIFT, int(ends[1]) >> FAR_ROW_SHIFT
+    n_rb = rb1 - rb0 + 1
+    n_slots = n_rb * n_j * warps
+    if n_slots >= 2**31 - 1:
+        raise ValueError("slot table of the blocked layout does not fit int32")
+    # runs = (row, column tile) groups of the sorted stream
+    flags = torch.empty(n, dtype=_I32, device=dev)
+    _lib.call("cb200_rows_flags", _ptr(kr), _ptr(vr), n, int(col_shift), _ptr(flags), _stream())
+    run_id = exclusive_scan_i32(flags)
+    n_runs = int(run_id[-1].item())
+    run_start = torch.empty(n_runs + 1, dtype=_I64, device=dev)
+    _lib.call("cb200_rows_run_starts", _ptr(flags), _ptr(run_id), n, _ptr(run_start), _stream())
+    del flags
+    rkey = torch.empty(n_runs, dtype=_I32, device=dev)
+    rval = _new_px(n_runs, dev)
+    err = torch.zeros(1, dtype=_I32, device=dev)
+    _lib.call("cb200_rows_run_keys", _ptr(kr), _ptr(vr), _ptr(run_start), n_runs, int(col_shift), rb0, 0, n_j,
+              _ptr(rkey), _ptr(rval), _ptr(err), _stream())
+    # order the runs by (slot, length descending): stable sort by C - length, then by slot
+    k1, v1 = sort_pairs(rkey, rval, int(col_shift))
+    del rkey, rval
+    k2, v2 = swap_key_other(k1, v1, n_runs)       # key = slot, val = {C - length, run}
+    del k1, v1
+    k2, v2 = sort_pairs(k2, v2, key_bits_for(n_slots))
+    slot_run_ptr = indptr_from_sorted(k2, n_runs, n_slots)
+    steps = torch.zeros(n_slots, dtype=_I32, device=dev)
+    _lib.call("cb200_rows_slot_steps", _ptr(slot_run_ptr), _ptr(v2), n_slots, int(col_shift), n_j, _ptr(steps),
+              _stream())
+    slot_base = exclusive_scan_i32(steps)         # first step of every slot, storage order (rb, warp, tile)
+    total_steps = int(slot_base[-1].item())
+    if int(err.item()):
+        return None
+    px = torch.empty((total_steps * 32 + 2, 2), dtype=_I32, device=dev)
+    dst = torch.empty(n_runs, dtype=_I64, device=dev)
+    slen = torch.empty(n_runs, dtype=_I32, device=dev)
+    _lib.call("cb200_rows_place", _ptr(k2), _ptr(v2), _ptr(slot_run_ptr), _ptr(slot_base), _ptr(kr), _ptr(vr),
+              _ptr(run_id), _ptr(run_start), n_runs, n, int(col_shift), n_j, _ptr(dst), _ptr(slen), _ptr(px),
+              _stream())
+    # records (incl. padding) per (row block, column tile): what a unit costs
+    counts = (steps.view(n_rb, warps, n_j).sum(1, dtype=_I64) * 32).cpu().numpy()
+    fc = FarCopy(px, slot_base, n, rb0, n_rb, 0, n_j, col_shift, warps, counts)
+    fc.n_chunks = total_steps // 2
+    fc.layout = 1
+    fc.padded = total_steps * 32
+    return fc
+
+
 def plan_far_units(copies_counts, target):
     """Split the non-empty (row block, column tile) pairs of every far copy into units.
 
@@ -404,21 +471,43 @@ class PixelTable:
         return cls.from_arrays(bin1_offset, bin2, count, chrom_offset, device=device)
 
 
-def read_cooler_arrays(clr):
+def shard_rows_by_pixels(bin1_offset, rank, world):
+    """Contiguous bin1 row range [lo, hi) of ``rank``: boundaries at
+    ``searchsorted(bin1_offset, g * nnz / world)`` -- about nnz / world stored pixels
+    per rank, rows never split.  The reference's counterpart is the chunk partition of
+    ``_balance.py:351-357`` handed to ``Pool.imap_unordered`` (cli/balance.py:237-243)."""
+    off = np.asarray(bin1_offset)
+    n_bins, nnz = len(off) - 1, int(off[-1])
+    cuts = np.searchsorted(off, nnz * np.arange(world + 1, dtype=np.float64) / world, side="left")
+    cuts = np.minimum(cuts, n_bins)
+    cuts[0], cuts[-1] = 0, n_bins
+    cuts = np.maximum.accumulate(cuts)
+    return int(cuts[rank]), int(cuts[rank + 1])
+
+
+def read_cooler_arrays(clr, rows=None):
     """(bin1_offset, bin2_id, count, chrom_offset) host arrays of a Cooler-like object.
 
     Protocol used (reference: src/cooler/parallel.py:289-304, _balance.py:141-142):
     ``clr.open('r')`` -> group with ``pixels/bin2_id``, ``pixels/count``;
     ``clr._load_dset('indexes/chrom_offset' | 'indexes/bin1_offset')``.  bin1_id is never read.
-    """
+
+    ``rows=(lo, hi)`` reads only the stored pixels of bin1 rows [lo, hi) -- the slice
+    ``pixels[bin1_offset[lo]:bin1_offset[hi]]`` a multi-GPU rank owns -- and returns LOCAL offsets
+    (``bin1_offset`` clipped to the slice and shifted; rows outside it are empty)."""
     chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
     bin1_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
     n_bins = len(bin1_offset) - 1
+    sl = slice(None)
+    if rows is not None:
+        p0, p1 = int(bin1_offset[rows[0]]), int(bin1_offset[rows[1]])
+        sl = slice(p0, p1)
+        bin1_offset = np.clip(bin1_offset, p0, p1) - p0
     with clr.open("r") as grp:
         d2 = grp["pixels"]["bin2_id"]
         if hasattr(d2, "astype") and hasattr(d2, "id") and n_bins < 2**31 - 1:
-            bin2 = d2.astype(np.int32)[:]              # h5py converts while reading: no int64 staging
+            bin2 = d2.astype(np.int32)[sl]             # h5py converts while reading: no int64 staging
         else:
-            bin2 = d2[:]
-        count = grp["pixels"]["count"][:]
+            bin2 = d2[sl]
+        count = grp["pixels"]["count"][sl]
     return bin1_offset, bin2, count, chrom_offset

@@ -106,6 +106,42 @@ int cb200_far_interleave(const cb200_px* rec, const int32_t* slot, const int64_t
                          const int64_t* chunk_ptr, int64_t n, int64_t total_chunks, cb200_px* px_out,
                          void* stream);
 
+/* "Lane rows" arrangement of the same blocks (far_layout = 1, csrc/rows.cuh): a RUN is the set of
+ * records of one row inside one column tile.  The runs of a slot (row block, warp row slice, column
+ * tile) are ordered by decreasing length and cut into slices of 32: lane l of the warp owns run
+ * 32 g + l of slice g and step k of the slice holds record k of its 32 runs (one coalesced 256-byte
+ * load), so a lane sums its row in a register and updates the row's accumulator once per slice.
+ * Records are {flag << 31 | (row & (R-1)) << 16 | (other & (C-1)), count}; flag marks the last step
+ * of a slice; shorter runs are padded with count-0 records, missing lanes use the dummy row id
+ * R + warp.  Slots are stored in (row block, warp, tile) order: cb200_far_copy.ptr[((rb - rb0) *
+ * cb200_rows_warps() + warp) * n_j + tile - j0] = first STEP (32 records) of the slot.
+ * Build steps (all on the stream sorted by (row >> RS, other >> col_shift, row, other)):
+ *   flags -> exclusive scan = run_id -> run_starts -> run_keys (key = C - length, val = {stream-order
+ *   slot, run}) -> cb200_sort_pairs by key, cb200_swap_key_other, cb200_sort_pairs by slot ->
+ *   cb200_indptr_from_sorted = slot_run_ptr -> slot_steps (storage order) -> exclusive scan =
+ *   slot_base -> place. */
+int cb200_rows_warps(void);
+int cb200_rows_flags(const int32_t* rows, const cb200_px* vals, int64_t n, int32_t col_shift,
+                     int32_t* flags_out, void* stream);
+/* run_start_out[r] = first record of run r, r = 0..n_runs (run_id = exclusive scan of flags, n + 1 entries). */
+int cb200_rows_run_starts(const int32_t* flags, const int64_t* run_id, int64_t n, int64_t* run_start_out,
+                          void* stream);
+/* *err_out (zero-initialised) is set when a run is longer than C (duplicate pixels: not representable). */
+int cb200_rows_run_keys(const int32_t* rows, const cb200_px* vals, const int64_t* run_start, int64_t n_runs,
+                        int32_t col_shift, int32_t rb0, int32_t j0, int32_t n_j, int32_t* key_out,
+                        cb200_px* val_out, int32_t* err_out, void* stream);
+/* steps_out[storage slot] = steps of the slot; keys2 / vals2 = runs sorted by (slot, length descending):
+ * keys2 = stream-order slot, vals2 = {C - length, run}. */
+int cb200_rows_slot_steps(const int64_t* slot_run_ptr, const cb200_px* vals2, int64_t n_slots, int32_t col_shift,
+                          int32_t n_j, int32_t* steps_out, void* stream);
+/* Writes every record, padding record and dummy lane of px_out[total_steps * 32]; dst_scratch
+ * int64[n_runs], len_scratch int32[n_runs]. */
+int cb200_rows_place(const int32_t* keys2, const cb200_px* vals2, const int64_t* slot_run_ptr,
+                     const int64_t* slot_base, const int32_t* rows, const cb200_px* vals,
+                     const int64_t* run_id, const int64_t* run_start, int64_t n_runs, int64_t n,
+                     int32_t col_shift, int32_t n_j, int64_t* dst_scratch, int32_t* len_scratch,
+                     cb200_px* px_out, void* stream);
+
 /* Static pixel filter.  A pixel (row r, other c) is KEPT iff
  *   !(ndiag > 0 && |r - c| < ndiag)                       (_zero_diags)
  *   && (keep == CB200_KEEP_ALL
@@ -243,6 +279,8 @@ typedef struct {
   int32_t  n_far_units;
   int32_t  far_col_shift;             /* log2 C, 1..13; (rows + 2 C) * 8 B must fit the 227 KB of shared memory */
   int32_t  far_warps;                 /* 16 or 32 (8: experimental, two CTAs per SM): warps per CTA = row slices per block */
+  int32_t  far_layout;                /* 0: lane-interleaved pieces (cb200_far_interleave); 1: lane rows (cb200_rows_place) */
+  int32_t  far_stages;                /* lane rows: shared-memory ring stages of C doubles (2..8); (R + 16 + stages * C) * 8 B must fit */
 } cb200_ice;
 
 /* Tuning of K3 (optional): ice_unroll in {0,1,2,4,8} = 128-bit stream loads kept in

@@ -106,6 +106,57 @@ def _iterate(bias_view, get_marg, tol, max_iters, on_var):
     return scale, var, passes, hit_limit
 
 
+def initial_bias(n_bins, marg_nnz, marg, chrom_offset, *, mad_max=5, min_nnz=10, min_count=0,
+                 blacklist=None, x0=None):
+    """Bias vector after the bin filters (_balance.py:366-413) given the two prefilter
+    marginals: ``marg_nnz`` (binarised counts; only read when min_nnz > 0) and ``marg`` (raw
+    counts; modified in place by the MAD-max normalisation exactly as in the reference)."""
+    import warnings
+
+    if x0 is not None:                                       # 368-372
+        bias = x0
+        bias[np.isnan(bias)] = 0
+    else:
+        bias = np.ones(n_bins, dtype=float)
+
+    if min_nnz > 0:                                          # 375-384
+        bias[marg_nnz < min_nnz] = 0
+
+    if min_count:                                            # 396-397
+        bias[marg < min_count] = 0
+
+    if mad_max > 0:                                          # 400-409
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for lo, hi in zip(chrom_offset[:-1], chrom_offset[1:]):
+                c_marg = marg[lo:hi]
+                marg[lo:hi] /= np.median(c_marg[c_marg > 0])
+            logNzMarg = np.log(marg[marg > 0])
+            med = np.median(logNzMarg)
+            dev = np.median(np.abs(logNzMarg - np.median(logNzMarg)))   # util.mad (util.py:513-514)
+            cutoff = np.exp(med - mad_max * dev)
+            bias[marg < cutoff] = 0
+
+    if blacklist is not None:                                # 412-413
+        bias[blacklist] = 0
+    return bias
+
+
+def ice_step(bias, marg):
+    """One update of the genome-wide loop (_balance.py:97-108) given the marginal ``marg`` of the
+    current bias: returns (var, mean) and divides ``bias`` in place; (0.0, nan) and bias = NaN when
+    every marginal is zero."""
+    nzmarg = marg[marg != 0]
+    if not len(nzmarg):
+        bias[:] = np.nan
+        return 0.0, np.nan
+    mean = nzmarg.mean()
+    marg = marg / mean
+    marg[marg == 0] = 1
+    bias /= marg
+    return nzmarg.var(), mean
+
+
 def balance_arrays(px, chrom_offset, bin1_offset, *, cis_only=False, trans_only=False,
                    ignore_diags=2, mad_max=5, min_nnz=10, min_count=0, blacklist=None,
                    rescale_marginals=True, x0=None, tol=1e-5, max_iters=200,
@@ -125,37 +176,15 @@ def balance_arrays(px, chrom_offset, bin1_offset, *, cis_only=False, trans_only=
     spans = _spans(nnz, chunksize)
     n_diags = ignore_diags if ignore_diags else 0
 
-    if x0 is not None:                                       # 368-372
-        bias = x0
-        bias[np.isnan(bias)] = 0
-    else:
-        bias = np.ones(n_bins, dtype=float)
-
     base = dict(zero_trans=cis_only, n_diags=n_diags)
+    marg_nnz = None
     if min_nnz > 0:                                          # 375-384
         marg_nnz = _marginal(px, chrom_ids, n_bins, spans, map, binarize=True,
                              zero_cis=False, vec=None, **base)
-        bias[marg_nnz < min_nnz] = 0
-
     marg = _marginal(px, chrom_ids, n_bins, spans, map, binarize=False,   # 386-393
                      zero_cis=False, vec=None, **base)
-    if min_count:                                            # 396-397
-        bias[marg < min_count] = 0
-
-    if mad_max > 0:                                          # 400-409
-        with np.errstate(all="ignore"), warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            for lo, hi in zip(chrom_offset[:-1], chrom_offset[1:]):
-                c_marg = marg[lo:hi]
-                marg[lo:hi] /= np.median(c_marg[c_marg > 0])
-            logNzMarg = np.log(marg[marg > 0])
-            med = np.median(logNzMarg)
-            dev = np.median(np.abs(logNzMarg - np.median(logNzMarg)))   # util.mad (util.py:513-514)
-            cutoff = np.exp(med - mad_max * dev)
-            bias[marg < cutoff] = 0
-
-    if blacklist is not None:                                # 412-413
-        bias[blacklist] = 0
+    bias = initial_bias(n_bins, marg_nnz, marg, chrom_offset, mad_max=mad_max, min_nnz=min_nnz,
+                        min_count=min_count, blacklist=blacklist, x0=x0)
 
     passes = []
     warned = False

@@ -5,10 +5,14 @@ h5py / libhdf5 by injecting stub modules for its missing dependencies and an
 in-memory dict-of-arrays that stands in for an open HDF5 group (the same trick
 the reference's own tests use: /root/reference/tests/conftest.py:8-106).
 
-/root/reference only exists in the build container, so this module is used
-(a) by ``tests/golden/make_golden.py`` to freeze golden vectors and
-(b) by CPU tests that are skipped when the reference is absent.
-Nothing under ``-m gpu``, ``smoke()`` or ``bench.py`` imports it.
+/root/reference only exists in the build container.  ``oracle/make_ref.py`` installs an
+unmodified copy of the package into the git-ignored ``oracle/_ref/`` (it travels to the GPU box
+with the built libraries), which is preferred when present.  This module is used
+(a) by ``tests/golden/make_golden.py`` to freeze golden vectors,
+(b) by CPU tests that are skipped when the reference is absent, and
+(c) by ``bench.py``'s ``--impl reference`` / ``cpu_baseline`` legs to time the reference's own
+    ``balance_cooler`` on the box's host cores (``kind: "reference"``).
+The product package never imports it.
 """
 from __future__ import annotations
 
@@ -20,7 +24,8 @@ import types
 
 import numpy as np
 
-REFERENCE_SRC = "/root/reference/src"
+_INSTALLED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+REFERENCE_SRC = _INSTALLED if os.path.isdir(os.path.join(_INSTALLED, "cooler")) else "/root/reference/src"
 _REGISTRY: dict = {}
 
 

@@ -328,6 +328,53 @@ def test_all_blocks_large_synthetic_matches_unstripped():
         np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
 
 
+@pytest.mark.parametrize("key,col_shift", [("gm/defaults", 4), ("gm/cis_only", 7), ("gm/trans_only", 5),
+                                           ("rnd3/gw", 2), ("gm/diag0", 12), ("gm/mad0_nnz0", 6),
+                                           ("rnd3/cis", 3), ("rnd1/cis", 13)])
+def test_lane_rows_layout_matches_reference_golden(key, col_shift):
+    """Every pixel through the lane-rows kernel (csrc/rows.cuh): sliced rows, mbarrier ring of w tiles."""
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    src, case = key.split("/")
+    t = _golden.table_of(src)
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    kw = dict(META[key]["kwargs"])
+    tab = PixelTable.from_arrays(bin1_offset, t["bin2_id"], t["count"], chrom_offset)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, band="rows",
+                                                      far_col_shift=col_shift, **kw)
+    assert info["band"] == "rows" and info["n_subcopies"] == 0 and info["far_units"] > 0
+    want = BAL[key]
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    assert sum(info["passes"]) == sum(META[key]["passes"])
+    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
+    _check_stats(stats, META[key]["stats"], kw.get("cis_only", False))
+
+
+@pytest.mark.parametrize("col_shift,unroll", [(13, 0), (9, 4), (11, 16)])
+def test_lane_rows_large_synthetic_matches_unstripped(col_shift, unroll):
+    """Several row blocks, dense diagonal slices of hundreds of steps next to 1-record slices;
+    repeat runs are bit-identical."""
+    import cooler_b200
+    from cooler_b200 import PixelTable, _lib
+    b1, b2, cnt, chrom_offset = _synthetic(37, [50000, 30000, 20001], 0.002)
+    n = int(chrom_offset[-1])
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
+    a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0)
+    _lib.load().cb200_set_far_tuning(unroll)
+    try:
+        b, sb, ib = cooler_b200.balance_table(tab, return_info=True, band="rows", far_col_shift=col_shift)
+        c, sc, ic = cooler_b200.balance_table(tab, return_info=True, band="rows", far_col_shift=col_shift)
+    finally:
+        _lib.load().cb200_set_far_tuning(0)
+    assert ib["far_pixels"] == 2 * ia["nnz_eff"] and ia["passes"] == ib["passes"]
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
+    np.testing.assert_array_equal(b, c)
+
+
 @pytest.mark.parametrize("mode", ["cis", "trans"])
 def test_far_blocks_modes_match_oracle(mode):
     import cooler_b200

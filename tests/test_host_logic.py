@@ -166,3 +166,49 @@ def test_choose_layout_policy():
     assert choose_layout(3_088_298, 380_000_000, strip_bins=16384) == (14, True)
     with pytest.raises(ValueError):
         choose_layout(100_000, 10, strip_bins=1000)
+
+
+def test_shard_rows_by_pixels_tiles_the_table():
+    """Multi-GPU split of balance_cooler(group=...): contiguous row ranges cut where the pixel
+    count crosses g * nnz / world, tiling [0, n_bins) exactly."""
+    from cooler_b200.table import shard_rows_by_pixels
+    rng = np.random.default_rng(3)
+    for n, world in [(1, 2), (50, 3), (1000, 8), (7, 8)]:
+        counts = rng.integers(0, 40, n) * (rng.random(n) < 0.7)
+        off = np.r_[0, np.cumsum(counts)].astype(np.int64)
+        cuts = [shard_rows_by_pixels(off, g, world) for g in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(cuts[:-1], cuts[1:]))
+        assert all(lo <= hi for lo, hi in cuts)
+        if n >= 1000:
+            px = np.array([off[hi] - off[lo] for lo, hi in cuts])
+            assert px.max() - px.min() <= 2 * counts.max()
+    # all pixels in one row: one rank owns everything, the others are empty
+    off = np.array([0, 0, 90, 90, 90])
+    cuts = [shard_rows_by_pixels(off, g, 4) for g in range(4)]
+    assert sum(off[hi] - off[lo] for lo, hi in cuts) == 90 and cuts[-1][1] == 4
+
+
+def test_read_cooler_arrays_row_slices_tile_the_pixel_table():
+    from cooler_b200.store import MemCooler
+    from cooler_b200.table import read_cooler_arrays, shard_rows_by_pixels
+    t = _golden.table_of("gm")
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    sizes = np.diff(chrom_offset) * 10
+    n = int(chrom_offset[-1])
+    b1 = np.repeat(np.arange(n, dtype=np.int64), np.diff(bin1_offset))
+    clr = MemCooler.from_chromsizes([f"c{i}" for i in range(len(sizes))], sizes, 10, b1, t["bin2_id"], t["count"])
+    off, b2, cnt, co = read_cooler_arrays(clr)
+    np.testing.assert_array_equal(off, bin1_offset)
+    parts2, partsc, total = [], [], 0
+    for g in range(3):
+        rows = shard_rows_by_pixels(off, g, 3)
+        o, p2, pc, _ = read_cooler_arrays(clr, rows=rows)
+        assert o[0] == 0 and o[-1] == len(p2) and len(o) == n + 1
+        assert (np.diff(o)[: rows[0]] == 0).all() and (np.diff(o)[rows[1]:] == 0).all()
+        np.testing.assert_array_equal(np.diff(o)[rows[0]:rows[1]], np.diff(off)[rows[0]:rows[1]])
+        parts2.append(np.asarray(p2)), partsc.append(np.asarray(pc))
+        total += len(p2)
+    assert total == len(b2)
+    np.testing.assert_array_equal(np.concatenate(parts2), np.asarray(b2))
+    np.testing.assert_array_equal(np.concatenate(partsc), np.asarray(cnt))
