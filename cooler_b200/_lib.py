@@ -53,7 +53,6 @@ class Ice(C.Structure):
         ("far_copies", C.c_void_p), ("far_units", C.c_void_p), ("far_tiles", C.c_void_p),
         ("far_parts", C.c_void_p), ("far_claim", C.c_void_p),
         ("n_far_units", C.c_int32), ("far_col_shift", C.c_int32), ("far_warps", C.c_int32),
-        ("far_layout", C.c_int32), ("far_stages", C.c_int32),
     ]
 
 
@@ -95,17 +94,10 @@ SIGNATURES = {
     "cb200_far_finish": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "cb200_far_slot_chunks": (C.c_int, [_P, _I64, _P, _P]),
     "cb200_far_interleave": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P]),
-    "cb200_rows_warps": (C.c_int, []),
-    "cb200_rows_flags": (C.c_int, [_P, _P, _I64, _I32, _P, _P]),
-    "cb200_rows_run_starts": (C.c_int, [_P, _P, _I64, _P, _P]),
-    "cb200_rows_run_keys": (C.c_int, [_P, _P, _P, _I64, _I32, _I32, _I32, _I32, _P, _P, _P, _P]),
-    "cb200_rows_slot_steps": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P]),
-    "cb200_rows_place": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32, _I32, _P, _P, _P, _P]),
     "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
     "cb200_set_tuning": (C.c_int, [_I32, _I32]),
-    "cb200_set_far_tuning": (C.c_int, [_I32]),
     "cb200_far_row_shift": (C.c_int, []),
     "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_combine": (C.c_int, [C.POINTER(Ice), _P]),
@@ -118,6 +110,7 @@ SIGNATURES = {
     "cb200_fetch_balance_dense": (C.c_int, [_P, _I64, _I64, _P, _P, _I32, _P, _P]),
     "cb200_fetch_balance_coo": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I32, _P, _P]),
     "cb200_coarsen_remap": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
+    "cb200_coarsen_merge_round": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "cb200_runs_count": (C.c_int, [_P, _P, _I64, _P, _P]),
     "cb200_runs_write": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P]),
     "cb200_unpack_pixels": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P]),

@@ -21,7 +21,7 @@ import torch
 from . import _lib
 from .table import (PixelTable, TableCopy, _new_px, _ptr, _stream, _use_device,  # noqa: F401
                     far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays,
-                    rows_blocks, shard_rows_by_pixels,
+                    shard_rows_by_pixels,
                     strip_partition, swap_key_other, transpose_from)
 
 __all__ = ["balance_cooler", "balance_table", "balance_arrays", "ConvergenceWarning", "IceProblem"]
@@ -120,15 +120,13 @@ class IceProblem:
 
     def __init__(self, table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2,
                  group=None, strip_bins=None, use_smem=True, band=None, peer_reduce=None,
-                 far_col_shift=None, far_warps=None):
+                 far_col_shift=None):
         self.table = table
         self.use_smem = use_smem
         self.far_copies = []
-        self.far_col_shift = int(far_col_shift or os.environ.get("CB200_FAR_COL_SHIFT", 13))
-        self.far_warps = int(far_warps or os.environ.get("CB200_FAR_WARPS", 16))
-        if peer_reduce is None:
-            peer_reduce = os.environ.get("CB200_PEER_REDUCE", "1") != "0"
-        self.peer_reduce = peer_reduce
+        self.far_col_shift = int(far_col_shift or FAR_COL_SHIFT)
+        self.far_warps = 16
+        self.peer_reduce = True if peer_reduce is None else bool(peer_reduce)
         self.group = group
         self.mode = "cis" if cis_only else ("trans" if trans_only else "gw")
         n_bins = table.n_bins
@@ -164,23 +162,15 @@ class IceProblem:
             free = torch.cuda.mem_get_info(table.device)[0]
             if 60 * csr.nnz > free:
                 self.band = False
-        if band in ("allblocks", "rows") or self.band in ("allblocks", "rows"):
-            # every pixel through a 2-D blocked kernel: "rows" = lane rows (csrc/rows.cuh), "allblocks" =
-            # lane-interleaved pieces (csrc/far.cuh)
-            self.band, self.strip_shift = (band if band in ("allblocks", "rows") else self.band), None
+        if band == "allblocks" or self.band == "allblocks":   # every pixel through the 2-D blocked kernel (csrc/far.cuh)
+            self.band, self.strip_shift = "allblocks", None
             if cval is None:
                 ckeys, cval = swap_key_other(ckeys, csc.px, csc.nnz)
             n1, n2 = csr.nnz, csc.nnz
             self.csr = self.csc = csr = csc = None
-            if self.band == "rows":
-                build = lambda k, v, m: rows_blocks(k, v, m, n_bins, self.far_col_shift)   # noqa: E731
-            else:
-                build = lambda k, v, m: far_blocks(k, v, m, n_bins, self.far_col_shift, self.far_warps)   # noqa: E731
-            self.far_copies = [build(tkey[:n1], tval, n1)]
+            self.far_copies = [far_blocks(tkey[:n1], tval, n1, n_bins, self.far_col_shift)]
             tkey = tval = None
-            self.far_copies.append(build(ckeys[:n2], cval, n2))
-            if self.band == "rows" and any(f is None for f, m in zip(self.far_copies, (n1, n2)) if m):
-                raise ValueError("duplicate pixels: the lane-rows layout cannot be built for this table")
+            self.far_copies.append(far_blocks(ckeys[:n2], cval, n2, n_bins, self.far_col_shift))
             self.subs = []
         elif sh is None:
             self.subs = [csr.tight(), csc.tight()]
@@ -207,8 +197,7 @@ class IceProblem:
                 if far.nnz and blocks:            # far field in (row block, column tile) order: csrc/far.cuh
                     nfar = far.nnz
                     del far
-                    self.far_copies.append(far_blocks(fkey, fval, nfar, n_bins, self.far_col_shift,
-                                                      self.far_warps))
+                    self.far_copies.append(far_blocks(fkey, fval, nfar, n_bins, self.far_col_shift))
                 elif far.nnz:                     # far field as one row-ordered copy gathered through L2
                     subs.append(far.tight())
                 del fkey, fval
@@ -277,9 +266,7 @@ class IceProblem:
         self = cls.__new__(cls)
         self.table, self.group, self.use_smem = info, group, True
         self.mode = "cis" if cis_only else ("trans" if trans_only else "gw")
-        if peer_reduce is None:
-            peer_reduce = os.environ.get("CB200_PEER_REDUCE", "1") != "0"
-        self.peer_reduce = peer_reduce
+        self.peer_reduce = True if peer_reduce is None else bool(peer_reduce)
         self.strip_shift, self.band, self.csr, self.csc = None, False, None, None
         self.far_copies, self.far_col_shift, self.far_warps = [], 13, 16
         ndiag = int(ignore_diags) if ignore_diags else 0
@@ -335,6 +322,8 @@ L1_RESIDENT_BINS = 49_152      # bias vectors up to 384 KB are served well enoug
 DEFAULT_STRIP_BINS = 16_384    # 128 KB of float64 bias per strip: stays in the SM's L1
 MIN_PIXELS_PER_ROW_STRIP = 16  # below this the per-(row, strip) bookkeeping costs more than it saves
 BLOCKS_MIN_BINS = 1 << 20      # sparse tables with at least this many bins use the 2-D blocked layout (csrc/far.cuh)
+FAR_COL_SHIFT = 13             # 8192-column tiles of w (64 KB each, two in shared memory next to the 4096 row sums)
+FAR_UNITS_PER_SM = 4           # work units of the blocked kernel per SM (2..16 measured equal)
 
 
 def choose_layout(n_bins, nnz_eff, strip_bins=None, band=None):
@@ -414,8 +403,6 @@ class IceState:
         span = int(min(8, max(1, -(-total_tiles // (148 * 32 * 8)))))
         if prob.strip_shift is not None and prob.use_smem:
             span = min(span, 4)                       # persistent strip kernel: finer claims, see csrc/ice.cu
-        if os.environ.get("CB200_SPAN"):              # tuning override
-            span = int(os.environ["CB200_SPAN"])
         arr = (_lib.Sub * max(len(subs), 1))()
         t["direct"] = f64(sum(c.n_rows for c in subs) + 1)
         t["pieces"] = f64(2 * total_tiles + 2)
@@ -445,8 +432,7 @@ class IceState:
         n_far_units = 0
         if far:
             sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            per_sm = int(os.environ.get("CB200_FAR_UNITS_PER_SM", 4))
-            target = max(sum(int(f.tile_counts.sum()) for f in far) // (sms * per_sm), 4096)
+            target = max(sum(f.nnz for f in far) // (sms * FAR_UNITS_PER_SM), 4096)
             units, tiles, rb_units = plan_far_units([(f.rb0, f.j0, f.tile_counts) for f in far], target)
             n_far_units = len(units)
             t["far_units"] = torch.from_numpy(np.ascontiguousarray(units)).to(dev)
@@ -491,10 +477,6 @@ class IceState:
             for k in ("far_copies", "far_units", "far_tiles", "far_parts", "far_claim"):
                 setattr(st, k, t[k].data_ptr())
             st.far_col_shift, st.far_warps = far[0].col_shift, far[0].warps
-            st.far_layout = int(getattr(far[0], "layout", 0))
-            # lane rows: ring of w tiles next to the R + 16 row accumulators, as many stages as fit 227 KB
-            tile_b, acc_b = 8 << far[0].col_shift, 8 * (far_rows() + 16)
-            st.far_stages = int(min(8, max(2, (227 * 1024 - 512 - acc_b) // tile_b)))
         self.st = st
         self.prob = prob
         self.flag_host = torch.zeros(1, dtype=_I32).pin_memory() if torch.cuda.is_available() else None
@@ -617,7 +599,7 @@ def prefilter_bias(prob: IceProblem, chrom_offset, *, mad_max, min_nnz, min_coun
 def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2, mad_max=5,
                   min_nnz=10, min_count=0, blacklist=None, rescale_marginals=True, x0=None,
                   tol=1e-5, max_iters=200, group=None, problem=None, chromnames=None,
-                  return_info=False, strip_bins=None, band=None, far_col_shift=None, far_warps=None):
+                  return_info=False, strip_bins=None, band=None, far_col_shift=None):
     """Balance a device-resident table.  Same semantics as ``balance_cooler``.
 
     ``problem`` lets callers reuse the filtered copies (bench: inputs resident
@@ -630,7 +612,7 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
     n_chroms = len(chrom_offset) - 1
     prob = problem or IceProblem(table, cis_only=cis_only, trans_only=trans_only,
                                  ignore_diags=ignore_diags, group=group, strip_bins=strip_bins, band=band,
-                                 far_col_shift=far_col_shift, far_warps=far_warps)
+                                 far_col_shift=far_col_shift)
     bias = prefilter_bias(prob, chrom_offset, mad_max=mad_max, min_nnz=min_nnz, min_count=min_count,
                           blacklist=blacklist, x0=x0)
 

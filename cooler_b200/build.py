@@ -10,8 +10,8 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC_DIR = os.path.join(_HERE, "csrc")
-SOURCES = ["prims.cu", "table.cu", "ice.cu", "rows.cu", "coarsen.cu", "fetch.cu"]
-HEADERS = ["common.cuh", "walk.cuh", "far.cuh", "rows.cuh", os.path.join("..", "..", "include", "cooler_b200.h")]
+SOURCES = ["prims.cu", "table.cu", "ice.cu", "coarsen.cu", "fetch.cu"]
+HEADERS = ["common.cuh", "walk.cuh", "far.cuh", os.path.join("..", "..", "include", "cooler_b200.h")]
 OUT = os.path.join(_HERE, "libcooler_b200.so")
 
 NVCC_FLAGS = [
@@ -20,12 +20,25 @@ NVCC_FLAGS = [
 ]
 
 
-def _stale():
-    if not os.path.exists(OUT):
+def source_hash(extra=()):
+    """sha256 over the sources, headers and compiler flags the library is built from."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in SOURCES + HEADERS:
+        with open(os.path.join(SRC_DIR, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
+    h.update(" ".join(NVCC_FLAGS + list(extra)).encode())
+    return h.hexdigest()
+
+
+def _stale(out=OUT, extra=()):
+    """The library is rebuilt unless the hash recorded next to it matches the current sources
+    (modification times are not trusted: a stale-but-newer .so must never be used silently)."""
+    tag = out + ".srchash"
+    if not (os.path.exists(out) and os.path.exists(tag)):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(SRC_DIR, s) for s in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(tag) as f:
+        return f.read().strip() != source_hash(extra)
 
 
 def build(force=False, verbose=False, far_row_shift=None):
@@ -35,8 +48,8 @@ def build(force=False, verbose=False, far_row_shift=None):
     if far_row_shift is not None:
         out = os.path.join(_HERE, f"libcooler_b200_rs{int(far_row_shift)}.so")
         extra = [f"-DCB200_FAR_ROW_SHIFT_VALUE={int(far_row_shift)}"]
-    elif not force and not _stale():
-        return OUT
+    if not force and not _stale(out, extra):
+        return out
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", out] + [os.path.join(SRC_DIR, s) for s in SOURCES]
     if verbose:
@@ -47,6 +60,8 @@ def build(force=False, verbose=False, far_row_shift=None):
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    with open(out + ".srchash", "w") as f:
+        f.write(source_hash(extra) + "\n")
     return out
 
 

@@ -89,6 +89,94 @@ runs_write_kernel(const int32_t* __restrict__ keys, const int2* __restrict__ val
   }
 }
 
+// ---- K5 as a merge (no global sort) ---------------------------------------------------------
+// The input copy is sorted by (bin1, bin2) and the bin map is monotone, so the f fine rows pooled
+// into one coarse row are f lists ALREADY sorted by the coarse column: the coarse row is their
+// f-way merge, done here as ceil(log2 f) rounds of pairwise merges.  In round r a "list" is the
+// concatenation of 2^r consecutive fine rows of one coarse row (merged by the previous rounds);
+// lists 2q and 2q+1 are merged into the same range of the output buffer, so no descriptor other
+// than the fine indptr and the first fine row of every coarse row is needed.
+//
+// One warp per (coarse row, pair), claimed dynamically.  The warp walks through the merged output
+// in chunks of 256 elements: it stages the next 256 elements of either list in shared memory
+// (coalesced loads; in round 0 the column ids are remapped on the fly), every lane finds the
+// start of its 8 outputs with a merge-path binary search in shared memory, merges them
+// sequentially (ties: the earlier list first, i.e. stable) and writes 64 contiguous bytes.
+constexpr int MG_VT = 8;                           // outputs per lane and chunk
+constexpr int MG_CHUNK = 32 * MG_VT;               // outputs per warp and chunk
+constexpr int MG_WARPS = 8;
+
+__global__ void __launch_bounds__(MG_WARPS * 32)
+coarsen_merge_round_kernel(const int2* __restrict__ in, int2* __restrict__ out,
+                           const int64_t* __restrict__ indptr, const int32_t* __restrict__ group_first,
+                           int n_groups, int round, int pairs_per_group,
+                           const int32_t* __restrict__ bin_map,      // round 0: column remap; else nullptr
+                           int32_t* __restrict__ key_out,            // last round: coarse row of every element; else nullptr
+                           unsigned long long* __restrict__ claim) {
+  __shared__ int2 sm[MG_WARPS][2][MG_CHUNK];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int2* sA = sm[wid][0];
+  int2* sB = sm[wid][1];
+  constexpr unsigned FULL = 0xffffffffu;
+  const int64_t n_items = (int64_t)n_groups * pairs_per_group;
+  const int span = 1 << round;                     // fine rows per list
+  while (true) {
+    unsigned long long w = 0;
+    if (lane == 0) w = atomicAdd(claim, 1ULL);
+    w = __shfl_sync(FULL, w, 0);
+    if ((int64_t)w >= n_items) break;
+    const int g = (int)(w / pairs_per_group), q = (int)(w % pairs_per_group);
+    const int g0 = group_first[g], g1 = group_first[g + 1];
+    const int a0 = g0 + 2 * q * span;
+    if (a0 >= g1) continue;                        // this coarse row has fewer lists
+    const int a1 = min(a0 + span, g1), a2 = min(a1 + span, g1);
+    const int64_t pa = indptr[a0], pb = indptr[a1], pe = indptr[a2];
+    const int na = (int)(pb - pa), nb = (int)(pe - pb);
+    const int2* __restrict__ A = in + pa;
+    const int2* __restrict__ B = in + pb;
+    int2* __restrict__ Y = out + pa;
+    int i0 = 0, j0 = 0;
+    while (i0 + j0 < na + nb) {
+      const int la = min(MG_CHUNK, na - i0), lb = min(MG_CHUNK, nb - j0);
+      const int nout = min(MG_CHUNK, la + lb);
+      for (int k = lane; k < la; k += 32) {
+        int2 v = A[i0 + k];
+        if (bin_map) v.x = __ldg(bin_map + v.x);
+        sA[k] = v;
+      }
+      for (int k = lane; k < lb; k += 32) {
+        int2 v = B[j0 + k];
+        if (bin_map) v.x = __ldg(bin_map + v.x);
+        sB[k] = v;
+      }
+      __syncwarp();
+      // merge path: the split (ia, ib), ia + ib = d, with A[ia-1] <= B[ib] and B[ib-1] < A[ia]
+      const int d = min(lane * MG_VT, nout);
+      int lo = max(0, d - lb), hi = min(d, la);
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (sA[mid].x <= sB[d - 1 - mid].x) lo = mid + 1; else hi = mid;
+      }
+      int ia = lo, ib = d - lo;
+      const int64_t o = (int64_t)(i0 + j0) + d;
+#pragma unroll
+      for (int v = 0; v < MG_VT; ++v) {
+        if (d + v < nout) {
+          const bool take_a = (ib >= lb) || (ia < la && sA[ia].x <= sB[ib].x);
+          const int2 e = take_a ? sA[ia] : sB[ib];
+          ia += take_a ? 1 : 0;
+          ib += take_a ? 0 : 1;
+          Y[o + v] = e;
+          if (key_out) key_out[pa + o + v] = g;
+        }
+      }
+      i0 += __shfl_sync(FULL, ia, 31);             // lane 31 ends at the split of diagonal nout
+      j0 += __shfl_sync(FULL, ib, 31);
+      __syncwarp();
+    }
+  }
+}
+
 __global__ void unpack_pixels_kernel(const int32_t* __restrict__ bin1, const int2* __restrict__ val,
                                      int64_t n, int64_t* __restrict__ b1, int64_t* __restrict__ b2,
                                      int32_t* __restrict__ cnt) {
@@ -117,6 +205,30 @@ int cb200_coarsen_remap(const cb200_copy* csr, int32_t n_rows, const int32_t* bi
                                                  csr->tile_row, csr->nnz, n_tiles, bin_map, key_out,
                                                  reinterpret_cast<int2*>(val_out));
   CB_LAUNCH_CHECK("coarsen_remap");
+  return 0;
+}
+
+int cb200_coarsen_merge_round(const cb200_px* in, cb200_px* out, const int64_t* indptr,
+                              const int32_t* group_first, int32_t n_groups, int32_t round,
+                              int32_t pairs_per_group, const int32_t* bin_map, int32_t* key_out,
+                              int64_t* claim, void* stream) {
+  if (n_groups <= 0 || pairs_per_group <= 0) return 0;
+  if (round < 0 || round > 30) {
+    set_error_msg("coarsen_merge_round: bad round");
+    return -1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  CB_CHECK(cudaMemsetAsync(claim, 0, sizeof(int64_t), s));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t items = (int64_t)n_groups * pairs_per_group;
+  int64_t blocks = ceil_div64(items, MG_WARPS);
+  if (blocks > (int64_t)sms * 6) blocks = (int64_t)sms * 6;      // 48 warps per SM claim the pairs dynamically
+  coarsen_merge_round_kernel<<<(unsigned)blocks, MG_WARPS * 32, 0, s>>>(
+      reinterpret_cast<const int2*>(in), reinterpret_cast<int2*>(out), indptr, group_first, n_groups, round,
+      pairs_per_group, bin_map, key_out, reinterpret_cast<unsigned long long*>(claim));
+  CB_LAUNCH_CHECK("coarsen_merge_round");
   return 0;
 }
 

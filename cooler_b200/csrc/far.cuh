@@ -36,14 +36,9 @@ __device__ __forceinline__ double far_i32_to_f64(int v) {      // exact, see i32
   return __hiloint2double(0x43300000, v ^ 0x80000000) - 4503601774854144.0;
 }
 
-__device__ __forceinline__ void cp_async_f64(unsigned smem_dst, const double* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // mbarrier + 1-D bulk copy (TMA) staging of a column tile of w: one elected thread issues a single
-// cp.async.bulk for the whole contiguous slice instead of C / THREADS 8-byte cp.async per thread,
-// which takes the staging off the LSU instruction stream that bounds this kernel (opt-in: kTma).
+// cp.async.bulk for the whole contiguous slice, which keeps the staging off the LSU instruction
+// stream that bounds this kernel.
 __device__ __forceinline__ void mbar_init(unsigned bar_s, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(count) : "memory");
 }
@@ -166,17 +161,21 @@ __device__ __forceinline__ void far_slot(const int4* __restrict__ px4, const int
   __syncwarp();
 }
 
-// WARPS = 8: 256-thread CTAs, two per SM (each with its own row block and w tiles), so a barrier
-// synchronises 8 warps instead of 16 (experimental).
-template <int WARPS, int U, bool kTma = false>
-__global__ void __launch_bounds__(WARPS * 32, (WARPS <= 8 ? 2 : 1))
+constexpr int FAR_BUFS = 2;                       // shared-memory buffers of C doubles: the tile in use + the next one
+
+// One persistent CTA per SM.  The slice of w of the NEXT column tile is staged with ONE bulk copy
+// (TMA, cp.async.bulk + mbarrier) issued by an elected thread while the current tile is consumed.
+// Measured on the 1 kb rank-0 shard (3.87e8 px): per-thread 8-byte cp.async 1.56 ms, one bulk copy
+// per tile 1.40 ms, two tiles in flight (three buffers) 1.63 ms -- the second copy competes with
+// the record stream for the SM's L2 port -- so the distance stays at one tile.
+template <int WARPS, int U>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 ice_sweep_far_kernel(const cb200_ice st) {
-  extern __shared__ double far_sm[];               // acc[FAR_ACC] | w tile [2][C]
+  extern __shared__ double far_sm[];               // acc[FAR_ACC] | w tile [FAR_BUFS][C]
   __shared__ int s_unit;
-  __shared__ unsigned long long s_bar[2];          // kTma: "tile staged" barrier of each w buffer
+  __shared__ unsigned long long s_bar[FAR_BUFS];   // "tile staged" barrier of each w buffer
   if (*st.all_done) return;
   constexpr int RW = FAR_ROWS / WARPS;             // rows per warp slice
-  constexpr int THREADS = WARPS * 32;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int cs = st.far_col_shift, C = 1 << cs;
   double* __restrict__ acc = far_sm;
@@ -185,40 +184,28 @@ ice_sweep_far_kernel(const cb200_ice st) {
   unsigned long long* claim = reinterpret_cast<unsigned long long*>(st.far_claim);
 
   const unsigned bar_s = (unsigned)__cvta_generic_to_shared(s_bar);
-  unsigned ph0 = 0, ph1 = 0;                       // phase parity of the two barriers (uniform over the CTA)
-  if (kTma) {
-    if (threadIdx.x == 0) {
-      mbar_init(bar_s, 1);
-      mbar_init(bar_s + 8, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
+  unsigned phases = 0;                             // bit b = parity of the phase barrier b is in (uniform over the CTA)
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < FAR_BUFS; ++b) mbar_init(bar_s + 8 * b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  // stage the slice of w of column tile j into buffer b (at dst_s)
-  auto stage = [&](unsigned dst_s, int j, int b) {
-    const int64_t base = (int64_t)j << cs;
-    if (kTma) {
-      if (threadIdx.x == 0) {
-        const int64_t left = (int64_t)st.n_bins - base;
-        const int nv = (int)(left < C ? left : C);             // valid bins of this tile (>= 1)
-        const unsigned bytes = (unsigned)(nv & ~1) * 8u;       // bulk copies move multiples of 16 bytes
-        mbar_expect_tx(bar_s + 8 * b, bytes);                  // 0 bytes: the arrive alone completes the phase
-        if (bytes) bulk_g2s(dst_s, st.w + base, bytes, bar_s + 8 * b);
-        if (nv & 1) sts_f64(dst_s + (unsigned)(nv - 1) * 8u, st.w[base + nv - 1]);   // odd tail of the last tile
-      }
-    } else {
-      for (int i = threadIdx.x; i < C; i += THREADS)
-        if (base + i < st.n_bins) cp_async_f64(dst_s + i * 8, st.w + base + i);
-      cp_async_commit();
+  __syncthreads();
+  // stage the slice of w of column tile j into buffer b
+  auto stage = [&](int j, int b) {
+    if (threadIdx.x == 0) {
+      const unsigned dst_s = wb_s + (unsigned)b * (unsigned)C * 8u;
+      const int64_t base = (int64_t)j << cs;
+      const int64_t left = (int64_t)st.n_bins - base;
+      const int nv = (int)(left < C ? left : C);               // valid bins of this tile (>= 1)
+      const unsigned bytes = (unsigned)(nv & ~1) * 8u;         // bulk copies move multiples of 16 bytes
+      if (nv & 1) sts_f64(dst_s + (unsigned)(nv - 1) * 8u, st.w[base + nv - 1]);   // odd tail, before the arrive
+      mbar_expect_tx(bar_s + 8 * b, bytes);                    // 0 bytes: the arrive alone completes the phase
+      if (bytes) bulk_g2s(dst_s, st.w + base, bytes, bar_s + 8 * b);
     }
   };
   auto staged = [&](int b) {                       // wait until buffer b holds its tile (followed by __syncthreads)
-    if (kTma) {
-      if (b == 0) { mbar_wait(bar_s, ph0); ph0 ^= 1u; }
-      else { mbar_wait(bar_s + 8, ph1); ph1 ^= 1u; }
-    } else {
-      cp_async_wait_all();
-    }
+    mbar_wait(bar_s + 8 * b, (phases >> b) & 1u);
+    phases ^= 1u << b;
   };
 
   while (true) {
@@ -235,7 +222,7 @@ ice_sweep_far_kernel(const cb200_ice st) {
     const int4* __restrict__ px4 = reinterpret_cast<const int4*>(fc.px);
     const int j_first = st.far_tiles[un.t0];
     int jn = (un.t0 + 1 < un.t1) ? st.far_tiles[un.t0 + 1] : -1;
-    stage(wb_s, j_first, 0);
+    stage(j_first, 0);
     int64_t a = tp[(int64_t)j_first * WARPS], b = tp[(int64_t)j_first * WARPS + 1];
     int4 qn[U];
     far_first_group<U>(px4, a, b, qn, lane);
@@ -246,11 +233,11 @@ ice_sweep_far_kernel(const cb200_ice st) {
       const int jnn = (t + 2 < un.t1) ? st.far_tiles[t + 2] : -1;     // in flight during this tile
       int64_t a2 = 0, b2 = 0;
       if (jn >= 0) {
-        stage(wb_s + (unsigned)((buf ^ 1) * C * 8), jn, buf ^ 1);
+        stage(jn, buf ^ 1);                        // every warp left that buffer at the barrier that ended tile t - 1
         a2 = tp[(int64_t)jn * WARPS];
         b2 = tp[(int64_t)jn * WARPS + 1];
       }
-      far_slot<U>(px4, a, b, qn, wb_s + (unsigned)(buf * C * 8), acc_s, lane);
+      far_slot<U>(px4, a, b, qn, wb_s + (unsigned)buf * (unsigned)C * 8u, acc_s, lane);
       if (jn >= 0) {
         far_first_group<U>(px4, a2, b2, qn, lane);
         staged(buf ^ 1);                           // (a barrier is only waited on when a copy was issued to it)

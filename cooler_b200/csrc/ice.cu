@@ -10,7 +10,6 @@
 #include "walk.cuh"
 #include <cstdlib>
 #include "far.cuh"
-#include "rows.cuh"
 #include "../../include/cooler_b200.h"
 
 namespace cb200 {
@@ -53,7 +52,6 @@ typedef IceOpT<false> IceOp;
 
 // Tuning knob (cb200_set_tuning): 128-bit stream loads kept in flight per lane.
 static int g_selective = -1;   // -1 = automatic
-static int g_far_unroll = 0;   // far-field kernel: 0 = automatic
 static int g_ice_unroll = 0;   // 0 = automatic: 4 chunks in flight per lane (strip kernel: 768-thread CTAs)
 
 template <int U, bool kSelective, int MINB>
@@ -348,107 +346,30 @@ int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1) {
 
 int cb200_far_row_shift(void) { return CB200_FAR_ROW_SHIFT; }
 
-int cb200_set_far_tuning(int32_t far_unroll) {
-  if (far_unroll != 0 && far_unroll != 1 && far_unroll != 2 && far_unroll != 4 && far_unroll != 8 && far_unroll != 16) return -1;
-  g_far_unroll = far_unroll;
-  return 0;
-}
-
-// K3 over the blocks in the lane-rows arrangement (rows.cuh): one persistent CTA per SM, a producer
-// warp feeds the ring of w tiles, 16 consumer warps walk their row slices.
-static int ice_sweep_rows(const cb200_ice* st, void* stream) {
-  constexpr size_t kSmemLimit = 227 * 1024;
-  const int stages = st->far_stages;
-  const size_t smem = ((size_t)ROWS_ACC + (size_t)stages * ((size_t)1 << st->far_col_shift)) * sizeof(double);
-  if (st->far_col_shift < 1 || st->far_col_shift > 16 || stages < 2 || stages > ROWS_MAX_STAGES ||
-      smem + 256 > kSmemLimit) {
-    set_error_msg("ice_sweep: lane-rows layout needs 2..8 ring stages of 2^far_col_shift doubles within 227 KB");
+// K3 over the far-field blocks (far.cuh): one persistent CTA per SM claims units.
+static int ice_sweep_far(const cb200_ice* st, void* stream) {
+  if (st->n_far_units <= 0) return 0;
+  if (st->far_col_shift < 1 || st->far_col_shift > 13 || st->far_warps != 16) {
+    set_error_msg("ice_sweep: far_col_shift must be in 1..13 and far_warps 16");
+    return -1;
+  }
+  const size_t smem = ((size_t)FAR_ACC + FAR_BUFS * ((size_t)1 << st->far_col_shift)) * sizeof(double);
+  constexpr size_t kSmemLimit = 227 * 1024;        // opt-in maximum of dynamic shared memory per CTA on sm_100
+  if (smem + 64 > kSmemLimit) {
+    set_error_msg("ice_sweep: far-field row sums + two column tiles exceed 227 KB of shared memory");
     return -1;
   }
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_rows_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_rows_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
   }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = st->n_far_units < sms ? st->n_far_units : sms;
-  cudaStream_t s = (cudaStream_t)stream;
-  static const int chunk = [] { const char* e = getenv("CB200_ROWS_TMA_CHUNK"); const int v = e ? atoi(e) : 0;
-                                return (v >= 16 && v % 16 == 0) ? v : (1 << 20); }();
-  static const int pf = [] { const char* e = getenv("CB200_ROWS_PF"); return e ? atoi(e) : 32; }();
-  if (g_far_unroll == 4) ice_sweep_rows_kernel<4><<<grid, ROWS_THREADS, smem, s>>>(*st, stages, chunk, pf);
-  else if (g_far_unroll == 16) ice_sweep_rows_kernel<16><<<grid, ROWS_THREADS, smem, s>>>(*st, stages, chunk, pf);
-  else ice_sweep_rows_kernel<8><<<grid, ROWS_THREADS, smem, s>>>(*st, stages, chunk, pf);
-  CB_LAUNCH_CHECK("ice_sweep_rows");
-  return 0;
-}
-
-// K3 over the far-field blocks (far.cuh): one persistent CTA per SM claims units.
-static int ice_sweep_far(const cb200_ice* st, void* stream) {
-  if (st->n_far_units <= 0) return 0;
-  if (st->far_layout == 1) return ice_sweep_rows(st, stream);
-  if (st->far_col_shift < 1 || st->far_col_shift > 13 ||
-      (st->far_warps != 8 && st->far_warps != 16 && st->far_warps != 32)) {
-    set_error_msg("ice_sweep: far_col_shift must be in 1..13 and far_warps 8, 16 or 32");
-    return -1;
-  }
-  const size_t smem = ((size_t)FAR_ACC + 2 * ((size_t)1 << st->far_col_shift)) * sizeof(double);
-  constexpr size_t kSmemLimit = 227 * 1024;        // opt-in maximum of dynamic shared memory per CTA on sm_100
-  if (smem > kSmemLimit) {
-    set_error_msg("ice_sweep: far-field row sums + two column tiles exceed 227 KB of shared memory");
-    return -1;
-  }
-  static bool attr_done = false;
-  if (!attr_done) {
-    const size_t want = ((size_t)FAR_ACC + 2 * 8192) * sizeof(double);
-    const int mx = (int)(want < kSmemLimit ? want : kSmemLimit);
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-    attr_done = true;
-  }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int ctas = (st->far_warps == 8 ? 2 : 1) * sms;          // 8-warp CTAs: two per SM
-  const int grid = st->n_far_units < ctas ? st->n_far_units : ctas;
-  cudaStream_t s = (cudaStream_t)stream;
-  // CB200_FAR_TMA=1 (experimental, not the default): stage the column tiles of w with one bulk copy
-  // (cp.async.bulk + mbarrier) per tile instead of per-thread 8-byte cp.async
-  static const bool use_tma = [] { const char* e = getenv("CB200_FAR_TMA"); return e && e[0] == '1'; }();
-  if (use_tma) {
-    static bool tma_attr_done = false;
-    if (!tma_attr_done) {
-      const size_t want = ((size_t)FAR_ACC + 2 * 8192) * sizeof(double);
-      const int mx = (int)(want < kSmemLimit ? want : kSmemLimit);
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<32, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<8, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx));
-      tma_attr_done = true;
-    }
-    if (st->far_warps == 8) ice_sweep_far_kernel<8, 8, true><<<grid, 256, smem, s>>>(*st);
-    else if (st->far_warps == 16) ice_sweep_far_kernel<16, 8, true><<<grid, 512, smem, s>>>(*st);
-    else ice_sweep_far_kernel<32, 4, true><<<grid, 1024, smem, s>>>(*st);
-  } else if (st->far_warps == 8) {
-    ice_sweep_far_kernel<8, 8><<<grid, 256, smem, s>>>(*st);
-  } else if (st->far_warps == 16) {
-    // default: 8 loads in flight per lane (measured 1.70 vs 2.15 ms with 4 on the 1 kb rank-0 shard)
-    if (g_far_unroll == 2) ice_sweep_far_kernel<16, 2><<<grid, 512, smem, s>>>(*st);
-    else if (g_far_unroll == 4) ice_sweep_far_kernel<16, 4><<<grid, 512, smem, s>>>(*st);
-    else ice_sweep_far_kernel<16, 8><<<grid, 512, smem, s>>>(*st);
-  } else {
-    if (g_far_unroll == 1) ice_sweep_far_kernel<32, 1><<<grid, 1024, smem, s>>>(*st);
-    else if (g_far_unroll == 4) ice_sweep_far_kernel<32, 4><<<grid, 1024, smem, s>>>(*st);
-    else ice_sweep_far_kernel<32, 2><<<grid, 1024, smem, s>>>(*st);
-  }
+  // 16 warps x 8 128-bit loads in flight per lane (measured 1.70 vs 2.15 ms with 4 on the 1 kb rank-0 shard)
+  ice_sweep_far_kernel<16, 8><<<grid, 512, smem, (cudaStream_t)stream>>>(*st);
   CB_LAUNCH_CHECK("ice_sweep_far");
   return 0;
 }

@@ -342,7 +342,7 @@ int cb200_strip_finish(const int32_t* keys, const cb200_px* vals, int64_t n, int
 int cb200_far_finish(const int32_t* rows, const cb200_px* vals, int64_t n, int32_t col_shift,
                      int32_t rb0, int32_t j0, int32_t n_j, int32_t warps, cb200_px* px_out,
                      int32_t* slot_out, void* stream) {
-  if (col_shift < 1 || col_shift > 16 || (warps != 16 && warps != 32) || n_j <= 0) {
+  if (col_shift < 1 || col_shift > 16 || warps != 16 || n_j <= 0) {
     set_error_msg("far_finish: bad arguments");
     return -1;
   }

@@ -164,31 +164,44 @@ def coarsen_table(table: PixelTable, factor: int):
 
     The new table's raw copy is sorted by (bin1', bin2') and duplicate-free, with
     counts summed (int64 accumulation; OverflowError if a sum leaves int32).
-    """
+
+    No global sort: the fine rows of a coarse row are already sorted by the (monotone) coarse
+    column, so the coarse row is their multi-way merge -- ceil(log2(rows per coarse row)) rounds of
+    pairwise merge-path merges (``cb200_coarsen_merge_round``), then one reduce-by-key over
+    adjacent equal (bin1', bin2')."""
     factor = int(factor)
     assert factor > 1
     dev = _use_device(table.device)
     csr = table.raw
     bin_map, new_off = coarsen_bin_map(table.chrom_offset, factor)
     n_new = int(new_off[-1])
-    bits = key_bits_for(n_new)
-    bin_map_d = torch.from_numpy(bin_map).to(dev)
     n = csr.nnz
-    key = torch.empty(max(n, 1), dtype=_I32, device=dev)
-    val = torch.empty((n + 2, 2), dtype=_I32, device=dev)
-    cs = csr.c_struct()
-    _lib.call("cb200_coarsen_remap", C.byref(cs), csr.n_rows, _ptr(bin_map_d), _ptr(key), _ptr(val), _stream())
-    ks, vs = sort_pairs(key[:n], val, bits)
-    del key, val
-    k2, v2, n_out, overflow = _reduce_runs(ks, vs, n, 1, dev)
-    del ks, vs
-    k3, v3 = sort_pairs(k2[:n_out], v2, bits)
-    del k2, v2
+    if csr.row_base != 0 or csr.n_rows != table.n_bins:
+        raise ValueError("coarsen_table needs the whole-row-range raw copy of the table")
+    # first fine row of every coarse row (the map is monotone and onto)
+    group_first = np.searchsorted(bin_map, np.arange(n_new + 1), side="left").astype(np.int32)
+    max_group = int(np.diff(group_first).max()) if n_new else 1
+    rounds = max(1, int(max_group - 1).bit_length())
+    bin_map_d = torch.from_numpy(bin_map).to(dev)
+    group_first_d = torch.from_numpy(group_first).to(dev)
+    claim = torch.zeros(1, dtype=_I64, device=dev)
+    keys = torch.empty(max(n, 1), dtype=_I32, device=dev)
+    bufs = [torch.empty((n + 2, 2), dtype=_I32, device=dev) for _ in range(min(rounds, 2))]
+    src = csr.px
+    for r in range(rounds):
+        dst = bufs[r % 2]
+        lists = -(-max_group // (1 << r))
+        _lib.call("cb200_coarsen_merge_round", _ptr(src), _ptr(dst), _ptr(csr.indptr), _ptr(group_first_d),
+                  n_new, r, -(-lists // 2), _ptr(bin_map_d) if r == 0 else C.c_void_p(0),
+                  _ptr(keys) if r == rounds - 1 else C.c_void_p(0), _ptr(claim), _stream())
+        src = dst
+    k2, v2, n_out, overflow = _reduce_runs(keys, src, n, 0, dev)
+    del keys, bufs, src
     if int(overflow.item()):
         raise OverflowError("coarsened count does not fit int32")
-    indptr = indptr_from_sorted(k3, n_out, n_new)
-    new_raw = TableCopy(v3, indptr, n_out, n_new)
-    return PixelTable(new_raw, new_off), k3
+    indptr = indptr_from_sorted(k2, n_out, n_new)
+    new_raw = TableCopy(v2, indptr, n_out, n_new)
+    return PixelTable(new_raw, new_off), k2[:n_out]
 
 
 def _reduce_runs(keys, vals, n, swap, dev):

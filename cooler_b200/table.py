@@ -243,7 +243,7 @@ class FarCopy:
         return self.px.numel() * 4 + self.ptr.numel() * 8
 
 
-def far_blocks(key_other, val_rowcount, n, n_bins, col_shift, warps):
+def far_blocks(key_other, val_rowcount, n, n_bins, col_shift, warps=16):
     """Row-ordered stream (key = gathered bin, val = {row, count}) -> FarCopy.
 
     Two stable radix sorts bring the records into (row >> RS, other >> col_shift, row,
@@ -287,73 +287,6 @@ def far_blocks(key_other, val_rowcount, n, n_bins, col_shift, warps):
     counts = np.diff(tile_start).reshape(n_rb, n_j)
     fc = FarCopy(px, cptr, n, rb0, n_rb, j0, n_j, col_shift, warps, counts)
     fc.n_chunks = total_chunks
-    return fc
-
-
-def rows_blocks(key_other, val_rowcount, n, n_bins, col_shift):
-    """Row-ordered stream (key = gathered bin, val = {row, count}) -> FarCopy in the "lane rows"
-    arrangement (csrc/rows.cuh, csrc/rows.cu; build steps in include/cooler_b200.h).
-
-    Returns None when a row holds more records in one column tile than the tile has columns
-    (duplicate pixels), which the arrangement cannot represent."""
-    dev = key_other.device
-    n = int(n)
-    if n == 0:
-        return None
-    warps = _lib.load().cb200_rows_warps()
-    FAR_ROW_SHIFT = _lib.far_row_shift()
-    n_j = ((max(n_bins, 1) - 1) >> col_shift) + 1
-    n_rb_all = ((max(n_bins, 1) - 1) >> FAR_ROW_SHIFT) + 1
-    ks, vs = sort_pairs(key_other[:n], val_rowcount, key_bits_for(n_j), key_shift=col_shift)
-    kr, vr = swap_key_other(ks, vs, n)            # key = row, val = {other, count}
-    del ks, vs
-    if n_rb_all > 1:
-        kr, vr = sort_pairs(kr, vr, key_bits_for(n_rb_all), key_shift=FAR_ROW_SHIFT)
-    ends = kr[torch.tensor([0, n - 1], device=dev)].cpu().numpy()
-    rb0, rb1 = int(ends[0]) >> FAR_ROW_SHIFT, int(ends[1]) >> FAR_ROW_SHIFT
-    n_rb = rb1 - rb0 + 1
-    n_slots = n_rb * n_j * warps
-    if n_slots >= 2**31 - 1:
-        raise ValueError("slot table of the blocked layout does not fit int32")
-    # runs = (row, column tile) groups of the sorted stream
-    flags = torch.empty(n, dtype=_I32, device=dev)
-    _lib.call("cb200_rows_flags", _ptr(kr), _ptr(vr), n, int(col_shift), _ptr(flags), _stream())
-    run_id = exclusive_scan_i32(flags)
-    n_runs = int(run_id[-1].item())
-    run_start = torch.empty(n_runs + 1, dtype=_I64, device=dev)
-    _lib.call("cb200_rows_run_starts", _ptr(flags), _ptr(run_id), n, _ptr(run_start), _stream())
-    del flags
-    rkey = torch.empty(n_runs, dtype=_I32, device=dev)
-    rval = _new_px(n_runs, dev)
-    err = torch.zeros(1, dtype=_I32, device=dev)
-    _lib.call("cb200_rows_run_keys", _ptr(kr), _ptr(vr), _ptr(run_start), n_runs, int(col_shift), rb0, 0, n_j,
-              _ptr(rkey), _ptr(rval), _ptr(err), _stream())
-    # order the runs by (slot, length descending): stable sort by C - length, then by slot
-    k1, v1 = sort_pairs(rkey, rval, int(col_shift))
-    del rkey, rval
-    k2, v2 = swap_key_other(k1, v1, n_runs)       # key = slot, val = {C - length, run}
-    del k1, v1
-    k2, v2 = sort_pairs(k2, v2, key_bits_for(n_slots))
-    slot_run_ptr = indptr_from_sorted(k2, n_runs, n_slots)
-    steps = torch.zeros(n_slots, dtype=_I32, device=dev)
-    _lib.call("cb200_rows_slot_steps", _ptr(slot_run_ptr), _ptr(v2), n_slots, int(col_shift), n_j, _ptr(steps),
-              _stream())
-    slot_base = exclusive_scan_i32(steps)         # first step of every slot, storage order (rb, warp, tile)
-    total_steps = int(slot_base[-1].item())
-    if int(err.item()):
-        return None
-    px = torch.empty((total_steps * 32 + 2, 2), dtype=_I32, device=dev)
-    dst = torch.empty(n_runs, dtype=_I64, device=dev)
-    slen = torch.empty(n_runs, dtype=_I32, device=dev)
-    _lib.call("cb200_rows_place", _ptr(k2), _ptr(v2), _ptr(slot_run_ptr), _ptr(slot_base), _ptr(kr), _ptr(vr),
-              _ptr(run_id), _ptr(run_start), n_runs, n, int(col_shift), n_j, _ptr(dst), _ptr(slen), _ptr(px),
-              _stream())
-    # records (incl. padding) per (row block, column tile): what a unit costs
-    counts = (steps.view(n_rb, warps, n_j).sum(1, dtype=_I64) * 32).cpu().numpy()
-    fc = FarCopy(px, slot_base, n, rb0, n_rb, 0, n_j, col_shift, warps, counts)
-    fc.n_chunks = total_steps // 2
-    fc.layout = 1
-    fc.padded = total_steps * 32
     return fc
 
 

@@ -106,42 +106,6 @@ int cb200_far_interleave(const cb200_px* rec, const int32_t* slot, const int64_t
                          const int64_t* chunk_ptr, int64_t n, int64_t total_chunks, cb200_px* px_out,
                          void* stream);
 
-/* "Lane rows" arrangement of the same blocks (far_layout = 1, csrc/rows.cuh): a RUN is the set of
- * records of one row inside one column tile.  The runs of a slot (row block, warp row slice, column
- * tile) are ordered by decreasing length and cut into slices of 32: lane l of the warp owns run
- * 32 g + l of slice g and step k of the slice holds record k of its 32 runs (one coalesced 256-byte
- * load), so a lane sums its row in a register and updates the row's accumulator once per slice.
- * Records are {flag << 31 | (row & (R-1)) << 16 | (other & (C-1)), count}; flag marks the last step
- * of a slice; shorter runs are padded with count-0 records, missing lanes use the dummy row id
- * R + warp.  Slots are stored in (row block, warp, tile) order: cb200_far_copy.ptr[((rb - rb0) *
- * cb200_rows_warps() + warp) * n_j + tile - j0] = first STEP (32 records) of the slot.
- * Build steps (all on the stream sorted by (row >> RS, other >> col_shift, row, other)):
- *   flags -> exclusive scan = run_id -> run_starts -> run_keys (key = C - length, val = {stream-order
- *   slot, run}) -> cb200_sort_pairs by key, cb200_swap_key_other, cb200_sort_pairs by slot ->
- *   cb200_indptr_from_sorted = slot_run_ptr -> slot_steps (storage order) -> exclusive scan =
- *   slot_base -> place. */
-int cb200_rows_warps(void);
-int cb200_rows_flags(const int32_t* rows, const cb200_px* vals, int64_t n, int32_t col_shift,
-                     int32_t* flags_out, void* stream);
-/* run_start_out[r] = first record of run r, r = 0..n_runs (run_id = exclusive scan of flags, n + 1 entries). */
-int cb200_rows_run_starts(const int32_t* flags, const int64_t* run_id, int64_t n, int64_t* run_start_out,
-                          void* stream);
-/* *err_out (zero-initialised) is set when a run is longer than C (duplicate pixels: not representable). */
-int cb200_rows_run_keys(const int32_t* rows, const cb200_px* vals, const int64_t* run_start, int64_t n_runs,
-                        int32_t col_shift, int32_t rb0, int32_t j0, int32_t n_j, int32_t* key_out,
-                        cb200_px* val_out, int32_t* err_out, void* stream);
-/* steps_out[storage slot] = steps of the slot; keys2 / vals2 = runs sorted by (slot, length descending):
- * keys2 = stream-order slot, vals2 = {C - length, run}. */
-int cb200_rows_slot_steps(const int64_t* slot_run_ptr, const cb200_px* vals2, int64_t n_slots, int32_t col_shift,
-                          int32_t n_j, int32_t* steps_out, void* stream);
-/* Writes every record, padding record and dummy lane of px_out[total_steps * 32]; dst_scratch
- * int64[n_runs], len_scratch int32[n_runs]. */
-int cb200_rows_place(const int32_t* keys2, const cb200_px* vals2, const int64_t* slot_run_ptr,
-                     const int64_t* slot_base, const int32_t* rows, const cb200_px* vals,
-                     const int64_t* run_id, const int64_t* run_start, int64_t n_runs, int64_t n,
-                     int32_t col_shift, int32_t n_j, int64_t* dst_scratch, int32_t* len_scratch,
-                     cb200_px* px_out, void* stream);
-
 /* Static pixel filter.  A pixel (row r, other c) is KEPT iff
  *   !(ndiag > 0 && |r - c| < ndiag)                       (_zero_diags)
  *   && (keep == CB200_KEEP_ALL
@@ -210,7 +174,7 @@ typedef struct {
  * other), RS = CB200_FAR_ROW_SHIFT, R = 1 << RS rows per block, and stored as records {(row & (R - 1)) << 16 | (other & (C - 1)), count},
  * C = 1 << col_shift.  A persistent CTA owns a unit = (row block, run of non-empty column
  * tiles): it keeps the R row sums in shared memory and stages the C-wide slice of the
- * bias vector of one tile after the other (double-buffered cp.async).  Warp k owns the rows
+ * bias vector of one tile after the other (one TMA bulk copy per tile, issued one tile ahead).  Warp k owns the rows
  * [k, k+1) * R / far_warps of the block; the records of one (row block, tile, warp slice)
  * = slot are stored as lane-interleaved 64-record chunks (cb200_far_interleave): every lane
  * sums the runs of equal rows of its own contiguous piece and adds them to the accumulators;
@@ -278,9 +242,7 @@ typedef struct {
   int64_t* far_claim;                 /* [2] zero-initialised (self re-arming) */
   int32_t  n_far_units;
   int32_t  far_col_shift;             /* log2 C, 1..13; (rows + 2 C) * 8 B must fit the 227 KB of shared memory */
-  int32_t  far_warps;                 /* 16 or 32 (8: experimental, two CTAs per SM): warps per CTA = row slices per block */
-  int32_t  far_layout;                /* 0: lane-interleaved pieces (cb200_far_interleave); 1: lane rows (cb200_rows_place) */
-  int32_t  far_stages;                /* lane rows: shared-memory ring stages of C doubles (2..8); (R + 16 + stages * C) * 8 B must fit */
+  int32_t  far_warps;                 /* 16: warps per CTA = row slices per block */
 } cb200_ice;
 
 /* Tuning of K3 (optional): ice_unroll in {0,1,2,4,8} = 128-bit stream loads kept in
@@ -288,9 +250,6 @@ typedef struct {
  * selective_l1: -1 automatic, 0/1 = whether gathers far from the diagonal bypass L1
  * allocation in the L1/L2-gather kernel. */
 int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1);
-/* Far-field kernel: 128-bit stream loads in flight per lane (0 = default: 8 with 16 warps,
- * 2 with 32 warps). */
-int cb200_set_far_tuning(int32_t far_unroll);
 /* K3: the marginal sweeps of every sub-copy (bin1-major rows, bin2-major columns), one
  * launch, followed by one launch over the far-field blocks if there are any.  No-op once
  * *all_done. */
@@ -317,6 +276,18 @@ int cb200_ice_update_peer(const cb200_ice* st, int32_t iter, const double* const
  *   key_out = bin_map[c], val_out = {bin_map[r], v}   (sort input). */
 int cb200_coarsen_remap(const cb200_copy* csr, int32_t n_rows, const int32_t* bin_map,
                         int32_t* key_out, cb200_px* val_out, void* stream);
+/* One round of the merge form of K5.  `in` = pixels {column, count} of a bin1-major copy (round 0:
+ * fine column ids, remapped through bin_map on the fly; later rounds: coarse column ids); the
+ * fine rows group_first[g] .. group_first[g+1] pool into coarse row g.  In round r a list is the
+ * run of 2^r consecutive fine rows of one coarse row; lists 2q and 2q+1 (q < pairs_per_group) are
+ * merged by coarse column (stable) into the same element range of `out`.  After
+ * ceil(log2(max rows per coarse row)) rounds every coarse row is sorted by coarse column with
+ * equal columns adjacent (cb200_runs_count / cb200_runs_write then sum them).  key_out (last
+ * round, else NULL): coarse row of every element.  claim: one int64 of scratch. */
+int cb200_coarsen_merge_round(const cb200_px* in, cb200_px* out, const int64_t* indptr,
+                              const int32_t* group_first, int32_t n_groups, int32_t round,
+                              int32_t pairs_per_group, const int32_t* bin_map, int32_t* key_out,
+                              int64_t* claim, void* stream);
 /* Reduce-by-key over a stream sorted so that equal (key, val.other) pairs are
  * adjacent.  Pass 1 counts run heads per tile of cb200_warp_tile() elements. */
 int cb200_runs_count(const int32_t* keys, const cb200_px* vals, int64_t n,

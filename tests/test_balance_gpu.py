@@ -238,10 +238,10 @@ def test_band_layout_large_synthetic_matches_unstripped():
     np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
 
 
-@pytest.mark.parametrize("key,strip_bins,col_shift,warps", [
-    ("gm/defaults", 64, 4, 16), ("gm/cis_only", 128, 6, 32), ("gm/trans_only", 32, 3, 16),
-    ("rnd3/gw", 16, 2, 32), ("rnd2/cis", 16, 5, 16), ("rnd3/trans", 32, 12, 16), ("gm/diag0", 16, 1, 16)])
-def test_far_blocks_layout_matches_reference_golden(key, strip_bins, col_shift, warps):
+@pytest.mark.parametrize("key,strip_bins,col_shift", [
+    ("gm/defaults", 64, 4), ("gm/cis_only", 128, 6), ("gm/trans_only", 32, 3),
+    ("rnd3/gw", 16, 2), ("rnd2/cis", 16, 5), ("rnd3/trans", 32, 12), ("gm/diag0", 16, 1)])
+def test_far_blocks_layout_matches_reference_golden(key, strip_bins, col_shift):
     """Band strips + far-field blocks (csrc/far.cuh: 2-D blocked far pixels, segmented-scan kernel)."""
     import cooler_b200
     from cooler_b200 import PixelTable
@@ -253,7 +253,7 @@ def test_far_blocks_layout_matches_reference_golden(key, strip_bins, col_shift, 
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         bias, stats, info = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, band="blocks",
-                                                      far_col_shift=col_shift, far_warps=warps, **kw)
+                                                      far_col_shift=col_shift, **kw)
     assert info["band"] == "blocks"
     if case != "cis_only":
         assert info["far_units"] > 0 and info["far_pixels"] > 0
@@ -263,27 +263,22 @@ def test_far_blocks_layout_matches_reference_golden(key, strip_bins, col_shift, 
     np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
 
 
-@pytest.mark.parametrize("strip_bins,col_shift,warps,unroll", [(1024, 8, 16, 0), (4096, 12, 32, 0), (256, 10, 16, 2),
-                                                             (16384, 12, 16, 0), (512, 5, 32, 1), (1024, 8, 16, 4),
-                                                             (1024, 9, 16, 8), (8192, 13, 32, 4), (16384, 13, 16, 0)])
-def test_far_blocks_large_synthetic_matches_unstripped(strip_bins, col_shift, warps, unroll):
+@pytest.mark.parametrize("strip_bins,col_shift", [(1024, 8), (4096, 12), (256, 10), (16384, 12), (512, 5),
+                                                  (1024, 9), (8192, 13), (16384, 13)])
+def test_far_blocks_large_synthetic_matches_unstripped(strip_bins, col_shift):
     """Several 16384-row blocks, hundreds of column tiles, rows from empty to dense; every
     far-kernel variant agrees with the whole-copy sweep to rounding and is bit-reproducible."""
     import cooler_b200
-    from cooler_b200 import PixelTable, _lib
+    from cooler_b200 import PixelTable
     b1, b2, cnt, chrom_offset = _synthetic(35, [50000, 30000, 20001], 0.002)
     n = int(chrom_offset[-1])
     bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
     tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
     a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0)
-    assert _lib.load().cb200_set_far_tuning(unroll) == 0
-    try:
-        b, sb, ib = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, band="blocks",
-                                              far_col_shift=col_shift, far_warps=warps)
-        c, sc, ic = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, band="blocks",
-                                              far_col_shift=col_shift, far_warps=warps)
-    finally:
-        _lib.load().cb200_set_far_tuning(0)
+    b, sb, ib = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, band="blocks",
+                                          far_col_shift=col_shift)
+    c, sc, ic = cooler_b200.balance_table(tab, return_info=True, strip_bins=strip_bins, band="blocks",
+                                          far_col_shift=col_shift)
     assert ib["band"] == "blocks" and ib["far_units"] > 4 and ib["far_pixels"] > 100000
     assert ia["passes"] == ib["passes"]
     np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
@@ -291,9 +286,9 @@ def test_far_blocks_large_synthetic_matches_unstripped(strip_bins, col_shift, wa
     np.testing.assert_array_equal(b, c)
 
 
-@pytest.mark.parametrize("key,col_shift,warps", [("gm/defaults", 4, 16), ("gm/cis_only", 7, 32), ("gm/trans_only", 5, 16),
-                                                 ("rnd3/gw", 2, 32), ("gm/diag0", 12, 16), ("gm/mad0_nnz0", 6, 32)])
-def test_all_blocks_layout_matches_reference_golden(key, col_shift, warps):
+@pytest.mark.parametrize("key,col_shift", [("gm/defaults", 4), ("gm/cis_only", 7), ("gm/trans_only", 5),
+                                           ("rnd3/gw", 2), ("gm/diag0", 12), ("gm/mad0_nnz0", 6), ("rnd1/cis", 13)])
+def test_all_blocks_layout_matches_reference_golden(key, col_shift):
     """Every pixel (dense diagonal runs included) through the 2-D blocked kernel."""
     import cooler_b200
     from cooler_b200 import PixelTable
@@ -305,7 +300,7 @@ def test_all_blocks_layout_matches_reference_golden(key, col_shift, warps):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         bias, stats, info = cooler_b200.balance_table(tab, return_info=True, band="allblocks",
-                                                      far_col_shift=col_shift, far_warps=warps, **kw)
+                                                      far_col_shift=col_shift, **kw)
     assert info["band"] == "allblocks" and info["n_subcopies"] == 0 and info["far_units"] > 0
     want = BAL[key]
     np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
@@ -321,58 +316,11 @@ def test_all_blocks_large_synthetic_matches_unstripped():
     bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
     tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
     a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0)
-    for warps in (16, 32):
-        b, sb, ib = cooler_b200.balance_table(tab, return_info=True, band="allblocks", far_warps=warps)
+    for col_shift in (13, 10):       # the default 8192-column tiles (three 64 KB buffers) and narrow ones
+        b, sb, ib = cooler_b200.balance_table(tab, return_info=True, band="allblocks", far_col_shift=col_shift)
         assert ib["far_pixels"] == 2 * ia["nnz_eff"] and ia["passes"] == ib["passes"]
         np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
         np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
-
-
-@pytest.mark.parametrize("key,col_shift", [("gm/defaults", 4), ("gm/cis_only", 7), ("gm/trans_only", 5),
-                                           ("rnd3/gw", 2), ("gm/diag0", 12), ("gm/mad0_nnz0", 6),
-                                           ("rnd3/cis", 3), ("rnd1/cis", 13)])
-def test_lane_rows_layout_matches_reference_golden(key, col_shift):
-    """Every pixel through the lane-rows kernel (csrc/rows.cuh): sliced rows, mbarrier ring of w tiles."""
-    import cooler_b200
-    from cooler_b200 import PixelTable
-    src, case = key.split("/")
-    t = _golden.table_of(src)
-    chrom_offset, bin1_offset = _golden.offsets(t)
-    kw = dict(META[key]["kwargs"])
-    tab = PixelTable.from_arrays(bin1_offset, t["bin2_id"], t["count"], chrom_offset)
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, band="rows",
-                                                      far_col_shift=col_shift, **kw)
-    assert info["band"] == "rows" and info["n_subcopies"] == 0 and info["far_units"] > 0
-    want = BAL[key]
-    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
-    assert sum(info["passes"]) == sum(META[key]["passes"])
-    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
-    _check_stats(stats, META[key]["stats"], kw.get("cis_only", False))
-
-
-@pytest.mark.parametrize("col_shift,unroll", [(13, 0), (9, 4), (11, 16)])
-def test_lane_rows_large_synthetic_matches_unstripped(col_shift, unroll):
-    """Several row blocks, dense diagonal slices of hundreds of steps next to 1-record slices;
-    repeat runs are bit-identical."""
-    import cooler_b200
-    from cooler_b200 import PixelTable, _lib
-    b1, b2, cnt, chrom_offset = _synthetic(37, [50000, 30000, 20001], 0.002)
-    n = int(chrom_offset[-1])
-    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
-    tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
-    a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0)
-    _lib.load().cb200_set_far_tuning(unroll)
-    try:
-        b, sb, ib = cooler_b200.balance_table(tab, return_info=True, band="rows", far_col_shift=col_shift)
-        c, sc, ic = cooler_b200.balance_table(tab, return_info=True, band="rows", far_col_shift=col_shift)
-    finally:
-        _lib.load().cb200_set_far_tuning(0)
-    assert ib["far_pixels"] == 2 * ia["nnz_eff"] and ia["passes"] == ib["passes"]
-    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
-    np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
-    np.testing.assert_array_equal(b, c)
 
 
 @pytest.mark.parametrize("mode", ["cis", "trans"])
@@ -510,17 +458,3 @@ def test_auto_layout_uses_blocks_for_huge_sparse_tables():
     c, sc = cooler_b200.balance_arrays(bin1_offset, b2, cnt, chrom_offset)
     np.testing.assert_array_equal(b, c)
     assert abs(sc["scale"] / sb["scale"] - 1) < 1e-12
-
-
-def test_far_kernel_tma_staging_variant_matches_whole_copies():
-    """CB200_FAR_TMA=1 (one cp.async.bulk + mbarrier per column tile instead of per-thread cp.async):
-    selected once per process, hence the subprocess.  Same bias as the whole-copy sweep."""
-    import os
-    import subprocess
-    import sys
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, CB200_FAR_TMA="1")
-    res = subprocess.run([sys.executable, os.path.join(root, "tools", "check_far_tma.py")], env=env,
-                         capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0, res.stderr[-2000:]
-    assert res.stdout.count(" OK") == 3 and "FAIL" not in res.stdout and "tma 1" in res.stdout, res.stdout
