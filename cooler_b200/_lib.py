@@ -103,6 +103,8 @@ SIGNATURES = {
     "cb200_ice_combine": (C.c_int, [C.POINTER(Ice), _P]),
     "cb200_ice_update": (C.c_int, [C.POINTER(Ice), _I32, _I32, _P]),
     "cb200_ice_update_peer": (C.c_int, [C.POINTER(Ice), _I32, _P, _I32, _I64, _P]),
+    "cb200_ice_reduce_peer": (C.c_int, [C.POINTER(Ice), _P, _I32, _I32, _I64, _P, _P]),
+    "cb200_ice_update_gather": (C.c_int, [C.POINTER(Ice), _I32, _P, _I32, _I64, _P]),
     "cb200_bin_pairs": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P]),
     "cb200_fetch_count": (C.c_int, [C.POINTER(Copy), _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "cb200_fetch_dense": (C.c_int, [C.POINTER(Copy), _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
@@ -110,9 +112,11 @@ SIGNATURES = {
     "cb200_fetch_balance_dense": (C.c_int, [_P, _I64, _I64, _P, _P, _I32, _P, _P]),
     "cb200_fetch_balance_coo": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I32, _P, _P]),
     "cb200_coarsen_remap": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
+    "cb200_coarsen_maps": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "cb200_coarsen_merge_round": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
     "cb200_runs_count": (C.c_int, [_P, _P, _I64, _P, _P]),
     "cb200_runs_write": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P]),
+    "cb200_runs_aggregate": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
     "cb200_unpack_pixels": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
 }
 

@@ -188,8 +188,12 @@ class MatrixSelector:
         return coo_matrix((data, (row, col)), shape=(h, w))
 
 
+# The 4DN data portal and hic2cool store these weight vectors in divisive form (api.py:28)
+_4DN_DIVISIVE_WEIGHTS = {"KR", "VC", "VC_SQRT"}
+
+
 def matrix(clr, *, field=None, balance=True, sparse=False, as_pixels=False, join=False,
-           ignore_index=True, divisive_weights=False, chunksize=10_000_000, fill_lower=True,
+           ignore_index=True, divisive_weights=None, chunksize=10_000_000, fill_lower=True,
            weights=None, table=None, device="cuda"):
     """``clr.matrix(...)`` on the GPU: returns a selector supporting ``.fetch(region[, region2])``
     and ``[i0:i1, j0:j1]``.
@@ -201,6 +205,8 @@ def matrix(clr, *, field=None, balance=True, sparse=False, as_pixels=False, join
     """
     if field not in (None, "count"):
         raise NotImplementedError("cooler_b200.matrix fetches the 'count' column only")
+    if isinstance(balance, str) and balance in _4DN_DIVISIVE_WEIGHTS and divisive_weights is None:
+        divisive_weights = True                                        # api.py:367-368
     if join and as_pixels:
         raise NotImplementedError("as_pixels with join=True is not supported by the CUDA path")
     name = balance if isinstance(balance, str) else "weight"

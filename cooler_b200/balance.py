@@ -69,10 +69,13 @@ class _TableInfo:
 
 
 class _PeerVectors:
-    """Double-buffered per-bin vector in NVLink peer-mapped (symmetric) memory."""
+    """Double-buffered per-bin vectors in NVLink peer-mapped (symmetric) memory: halves 0 / 1 hold
+    the local partial sums s of alternating passes, halves 2 / 3 the slice-wise reduced vector of
+    the two-stage all-reduce (long vectors, see TWO_STAGE_BYTES)."""
 
     def __init__(self, local, handle, ptrs, stride, world):
         self.local, self.handle, self.ptrs, self.stride, self.world = local, handle, ptrs, stride, world
+        self.rank = handle.rank
         self.tick = 0     # which half is written next; never reset, so a half is only reused after
                           # a later barrier proved every peer is done reading it
 
@@ -98,7 +101,7 @@ class _PeerVectors:
             if dist.get_backend(group) != "nccl":
                 return None
             stride = -(-max(n, 1) // 64) * 64
-            local = symm_mem.empty(2 * stride, dtype=_F64, device=dev)
+            local = symm_mem.empty(4 * stride, dtype=_F64, device=dev)
             local.zero_()
             handle = symm_mem.rendezvous(local, group)
             ptrs = torch.tensor(list(handle.buffer_ptrs), dtype=torch.int64, device=dev)
@@ -323,6 +326,7 @@ DEFAULT_STRIP_BINS = 16_384    # 128 KB of float64 bias per strip: stays in the 
 MIN_PIXELS_PER_ROW_STRIP = 16  # below this the per-(row, strip) bookkeeping costs more than it saves
 BLOCKS_MIN_BINS = 1 << 20      # sparse tables with at least this many bins use the 2-D blocked layout (csrc/far.cuh)
 FAR_COL_SHIFT = 13             # 8192-column tiles of w (64 KB each, two in shared memory next to the 4096 row sums)
+TWO_STAGE_BYTES = 32 << 20     # peer bytes per rank and pass from which the all-reduce runs in two stages
 FAR_UNITS_PER_SM = 4           # work units of the blocked kernel per SM (2..16 measured equal)
 
 
@@ -450,10 +454,14 @@ class IceState:
         # multi-GPU: local s vectors live in peer-mapped symmetric memory (double-buffered) and
         # K4a sums them over NVLink; falls back to an NCCL all-reduce if that is unavailable
         self.peer = None
+        self.two_stage = False
         if prob.group is not None and prob.peer_reduce:
             self.peer = _PeerVectors.create(n, prob.group, dev)
             if self.peer is not None:
                 t["s"] = self.peer.local[: max(n, 1)]
+                # every rank reading every rank's whole vector moves (world - 1) x 8 B per bin over NVLink;
+                # beyond TWO_STAGE_BYTES the reduce-scatter + all-gather form (one more barrier) is cheaper
+                self.two_stage = (self.peer.world - 1) * 8 * n > TWO_STAGE_BYTES
         t["blk_sum"], t["blk_cnt"], t["blk_dev"] = f64(nb), f64(nb), f64(nb)
         t["seg_mean"], t["seg_nnz"] = f64(S), f64(S)
         t["seg_scale"], t["seg_var"] = f64(S, 1.0), f64(S, float("nan"))
@@ -524,8 +532,19 @@ class IceState:
             if timed:
                 c1.record()
                 self.comm_events.append((c0, c1))
-            _lib.call("cb200_ice_update_peer", C.byref(self.st), int(it), _ptr(self.peer.ptrs),
-                      self.peer.world, half * self.peer.stride, stream)
+            if self.two_stage:
+                # reduce-scatter (own slice, summed in rank order) -> barrier -> all-gather inside K4a
+                red_off = (2 + half) * self.peer.stride
+                _lib.call("cb200_ice_reduce_peer", C.byref(self.st), _ptr(self.peer.ptrs), self.peer.world,
+                          self.peer.rank, half * self.peer.stride,
+                          C.c_void_p(self.peer.local.data_ptr() + 8 * red_off), stream)
+                self.peer.handle.barrier(channel=2 + half)
+                _lib.call("cb200_ice_update_gather", C.byref(self.st), int(it), _ptr(self.peer.ptrs),
+                          self.peer.world, red_off, stream)
+                self.launches += 1
+            else:
+                _lib.call("cb200_ice_update_peer", C.byref(self.st), int(it), _ptr(self.peer.ptrs),
+                          self.peer.world, half * self.peer.stride, stream)
             self.launches += 4 + (1 if self.n_far_units else 0)
         else:
             _lib.call("cb200_ice_combine", st, stream)

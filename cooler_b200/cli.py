@@ -210,6 +210,7 @@ def balance(cool_uri, nproc, chunksize, mad_max, min_nnz, min_count, blacklist, 
 
     code = _on_rank0(group, rank, pre)
     if code is not None:
+        _finish_dist(group)
         sys.exit(code)
     clr = store.open_cooler(cool_uri)
 

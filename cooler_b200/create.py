@@ -94,6 +94,21 @@ def _binsize(ids, start, end):
     return int(sizes[0]) if len(sizes) == 1 else None
 
 
+def refuse_truncating_source(dst_path, sources, mode):
+    """``mode="w"`` truncates the destination.  When the destination IS one of the source files
+    (``zoomify x.mcool::resolutions/1000`` without ``-o``, or ``-o`` equal to the input) that would
+    destroy the user's data before it has been read -- the sources are memory-mapped.  h5py refuses
+    to truncate a file it has open (the reference therefore fails with an OSError); so do we."""
+    if mode != "w":
+        return
+    dst = os.path.realpath(dst_path)
+    for src in sources:
+        name = getattr(src, "filename", None)
+        if isinstance(name, str) and os.path.exists(name) and os.path.realpath(name) == dst:
+            raise OSError(f"Unable to create file '{dst_path}': it is the input file '{name}' "
+                          "(unable to truncate a file which is already open); choose another output path")
+
+
 def _open_target(file_path, group_path, mode):
     """The file and the (emptied) destination group, as create() prepares them (_create.py:611-623)."""
     if mode in ("r+", "a") and not (os.path.exists(file_path) and os.path.getsize(file_path) > 0):
@@ -230,6 +245,7 @@ def copy_cooler(src, dst_uri, columns=("count",), mode="w"):
     """
     file_path, group_path = parse_cooler_uri(dst_uri)
     opts = {"compression": "gzip", "compression_opts": 6, "shuffle": True}
+    refuse_truncating_source(file_path, [src], mode)
     f, h5 = _open_target(os.path.realpath(file_path), group_path, mode)
     try:
         with src.open("r") as g:

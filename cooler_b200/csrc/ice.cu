@@ -180,6 +180,19 @@ __global__ void ice_combine_kernel(const cb200_ice st) {
   st.s[i] = v;
 }
 
+// Reduce-scatter half of the two-stage all-reduce: this rank sums, in rank order, the slice of
+// the per-bin vector it owns over every rank's local s (peer loads) into its own `red` buffer.
+__global__ void ice_reduce_slice_kernel(const int32_t* __restrict__ all_done,
+                                        const double* const* __restrict__ peer_s, int world, int64_t peer_off,
+                                        double* __restrict__ red, int lo, int hi) {
+  if (*all_done) return;
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  double v = 0.0;
+  for (int r = 0; r < world; ++r) v += __ldcv(peer_s[r] + peer_off + i);
+  red[i] = v;
+}
+
 constexpr int UPD_THREADS = 256;
 constexpr int UPD_BINS = 1024;   // bins per block of the per-bin kernels (host block table uses the same)
 
@@ -217,7 +230,10 @@ __device__ __forceinline__ bool last_block_ticket(int32_t* ticket) {
 // kMode 0: s is given (after an NCCL all-reduce); 1: s = row totals of the local
 // sub-copies (single GPU); 2: s = sum over ranks, in rank order, of every rank's local s
 // read through peer (NVLink) pointers -- the all-reduce fused into K4a, identical bits
-// on every rank.
+// on every rank; 3: s was reduced slice-wise by ice_reduce_slice_kernel (rank q owns the bins
+// [q, q+1) * ceil(n_bins / world)) and is gathered here from the owners' buffers -- the
+// all-gather half of a two-stage all-reduce, (world - 1) / world * 8 B per bin over NVLink
+// instead of (world - 1) * 8 B.
 template <int kMode>
 __global__ void __launch_bounds__(UPD_THREADS)
 ice_marg_kernel(cb200_ice st, const double* const* __restrict__ peer_s, int world, int64_t peer_off) {
@@ -233,6 +249,9 @@ ice_marg_kernel(cb200_ice st, const double* const* __restrict__ peer_s, int worl
       if (kMode == 2) {
         si = 0.0;
         for (int r = 0; r < world; ++r) si += __ldcv(peer_s[r] + peer_off + i);
+      } else if (kMode == 3) {
+        const int slice = (st.n_bins + world - 1) / world;
+        si = __ldcv(peer_s[i / slice] + peer_off + i);
       } else if (kMode == 1) {
         si = 0.0;
         for (int k = 0; k < st.n_subs; ++k) {
@@ -453,6 +472,30 @@ int cb200_ice_update_peer(const cb200_ice* st, int32_t iter, const double* const
   if (st->n_blocks <= 0) return 0;
   ice_marg_kernel<2><<<st->n_blocks, UPD_THREADS, 0, s>>>(*st, peer_s, world, peer_offset);
   CB_LAUNCH_CHECK("ice_marg_peer");
+  ice_update_kernel<<<st->n_blocks, UPD_THREADS, 0, s>>>(*st, iter);
+  CB_LAUNCH_CHECK("ice_update");
+  return 0;
+}
+
+int cb200_ice_reduce_peer(const cb200_ice* st, const double* const* peer_s, int32_t world, int32_t rank,
+                          int64_t peer_offset, double* red_local, void* stream) {
+  if (st->n_bins <= 0 || world <= 0 || rank < 0 || rank >= world) return 0;
+  const int slice = (st->n_bins + world - 1) / world;
+  const int lo = rank * slice < st->n_bins ? rank * slice : st->n_bins;
+  const int hi = lo + slice < st->n_bins ? lo + slice : st->n_bins;
+  if (hi <= lo) return 0;
+  ice_reduce_slice_kernel<<<(unsigned)ceil_div64(hi - lo, 256), 256, 0, (cudaStream_t)stream>>>(
+      st->all_done, peer_s, world, peer_offset, red_local, lo, hi);
+  CB_LAUNCH_CHECK("ice_reduce_slice");
+  return 0;
+}
+
+int cb200_ice_update_gather(const cb200_ice* st, int32_t iter, const double* const* peer_red,
+                            int32_t world, int64_t peer_offset, void* stream) {
+  cudaStream_t s = (cudaStream_t)stream;
+  if (st->n_blocks <= 0) return 0;
+  ice_marg_kernel<3><<<st->n_blocks, UPD_THREADS, 0, s>>>(*st, peer_red, world, peer_offset);
+  CB_LAUNCH_CHECK("ice_marg_gather");
   ice_update_kernel<<<st->n_blocks, UPD_THREADS, 0, s>>>(*st, iter);
   CB_LAUNCH_CHECK("ice_update");
   return 0;

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .store import MemCooler
+from .store import MemCooler, parse_cooler_uri
 from .table import (PixelTable, TableCopy, _ptr, _stream, _use_device, exclusive_scan_i32,
                     indptr_from_sorted, key_bits_for, n_tiles, sort_pairs, swap_key_other)
 
@@ -159,31 +159,29 @@ def align_rows_to_factor(chrom_offset, factor, row):
 # --------------------------------------------------------------------------
 # device path
 # --------------------------------------------------------------------------
-def coarsen_table(table: PixelTable, factor: int):
-    """Coarsen a device-resident table by ``factor``.  Returns (new PixelTable, bin1' ids).
-
-    The new table's raw copy is sorted by (bin1', bin2') and duplicate-free, with
-    counts summed (int64 accumulation; OverflowError if a sum leaves int32).
-
-    No global sort: the fine rows of a coarse row are already sorted by the (monotone) coarse
-    column, so the coarse row is their multi-way merge -- ceil(log2(rows per coarse row)) rounds of
-    pairwise merge-path merges (``cb200_coarsen_merge_round``), then one reduce-by-key over
-    adjacent equal (bin1', bin2')."""
+def _merge_coarse_rows(table: PixelTable, factor: int):
+    """The merge part of K5: returns (keys = coarse row of every pixel, vals = {coarse column,
+    payload} sorted by (coarse row, coarse column) with equal pairs adjacent in pixel order,
+    n_new, new chrom_offset).  The payload is whatever the table's raw copy carries as "count"."""
     factor = int(factor)
     assert factor > 1
     dev = _use_device(table.device)
     csr = table.raw
-    bin_map, new_off = coarsen_bin_map(table.chrom_offset, factor)
+    new_off = coarsen_chrom_offset(table.chrom_offset, factor)
     n_new = int(new_off[-1])
     n = csr.nnz
     if csr.row_base != 0 or csr.n_rows != table.n_bins:
         raise ValueError("coarsen_table needs the whole-row-range raw copy of the table")
-    # first fine row of every coarse row (the map is monotone and onto)
-    group_first = np.searchsorted(bin_map, np.arange(n_new + 1), side="left").astype(np.int32)
-    max_group = int(np.diff(group_first).max()) if n_new else 1
+    # old bin -> new bin and the first old bin of every new bin, on the device (closed forms)
+    n_chroms = len(new_off) - 1
+    offs = torch.from_numpy(np.stack([np.asarray(table.chrom_offset, dtype=np.int64), new_off])).to(dev)
+    bin_map_d = torch.empty(max(table.n_bins, 1), dtype=_I32, device=dev)
+    group_first_d = torch.empty(n_new + 1, dtype=_I32, device=dev)
+    _lib.call("cb200_coarsen_maps", _ptr(offs[0]), _ptr(offs[1]), n_chroms, factor, table.n_bins, n_new,
+              _ptr(bin_map_d), _ptr(group_first_d), _stream())
+    nb = np.diff(table.chrom_offset)
+    max_group = int(min(factor, nb.max())) if len(nb) and nb.max() > 0 else 1
     rounds = max(1, int(max_group - 1).bit_length())
-    bin_map_d = torch.from_numpy(bin_map).to(dev)
-    group_first_d = torch.from_numpy(group_first).to(dev)
     claim = torch.zeros(1, dtype=_I64, device=dev)
     keys = torch.empty(max(n, 1), dtype=_I32, device=dev)
     bufs = [torch.empty((n + 2, 2), dtype=_I32, device=dev) for _ in range(min(rounds, 2))]
@@ -195,13 +193,77 @@ def coarsen_table(table: PixelTable, factor: int):
                   n_new, r, -(-lists // 2), _ptr(bin_map_d) if r == 0 else C.c_void_p(0),
                   _ptr(keys) if r == rounds - 1 else C.c_void_p(0), _ptr(claim), _stream())
         src = dst
-    k2, v2, n_out, overflow = _reduce_runs(keys, src, n, 0, dev)
-    del keys, bufs, src
+    return keys, src, n_new, new_off
+
+
+def coarsen_table(table: PixelTable, factor: int):
+    """Coarsen a device-resident table by ``factor``.  Returns (new PixelTable, bin1' ids).
+
+    The new table's raw copy is sorted by (bin1', bin2') and duplicate-free, with
+    counts summed (int64 accumulation; OverflowError if a sum leaves int32).
+
+    No global sort: the fine rows of a coarse row are already sorted by the (monotone) coarse
+    column, so the coarse row is their multi-way merge -- ceil(log2(rows per coarse row)) rounds of
+    pairwise merge-path merges (``cb200_coarsen_merge_round``), then one reduce-by-key over
+    adjacent equal (bin1', bin2')."""
+    dev = table.device
+    n = table.raw.nnz
+    keys, vals, n_new, new_off = _merge_coarse_rows(table, factor)
+    k2, v2, n_out, overflow = _reduce_runs(keys, vals, n, 0, dev)
+    del keys, vals
     if int(overflow.item()):
         raise OverflowError("coarsened count does not fit int32")
     indptr = indptr_from_sorted(k2, n_out, n_new)
     new_raw = TableCopy(v2, indptr, n_out, n_new)
     return PixelTable(new_raw, new_off), k2[:n_out]
+
+
+AGG_OPS = {"sum": 0, "min": 1, "max": 2, "first": 3, "last": 4, "mean": 5}
+_SRC_DTYPES = {torch.int32: 0, torch.int64: 1, torch.float32: 2, torch.float64: 3}
+
+
+def coarsen_columns(bin1_offset, bin2_id, chrom_offset, factor, columns, agg, device="cuda"):
+    """Coarsening with arbitrary value columns and aggregators -- the general form of
+    ``CoolerCoarsener._aggregate`` (_reduce.py:582-620: ``groupby([bin1_id, bin2_id], sort=True)
+    .aggregate(agg)``).  ``columns``: {name: host array, any numeric dtype}; ``agg``: {name: "sum" |
+    "min" | "max" | "first" | "last" | "mean"}.  The pixels are merged once carrying their own
+    position as payload; every column is then gathered through that order and reduced per
+    (bin1', bin2') run in pixel order, integers in int64, floats in float64 (mean always float64).
+    Returns (bin1' int64, bin2' int64, {name: numpy array}, new chrom_offset)."""
+    dev = _use_device(device)
+    n = len(bin2_id)
+    if n >= 2**31 - 1:
+        raise NotImplementedError("the general aggregation path indexes pixels with int32")
+    idx = torch.arange(n, dtype=_I32)
+    table = PixelTable.from_arrays(bin1_offset, bin2_id, idx, chrom_offset, device=dev)
+    keys, vals, n_new, new_off = _merge_coarse_rows(table, factor)
+    nt = n_tiles(n)
+    tile_count = torch.zeros(max(nt, 1), dtype=_I32, device=dev)
+    _lib.call("cb200_runs_count", _ptr(keys), _ptr(vals), n, _ptr(tile_count), _stream())
+    tile_off = exclusive_scan_i32(tile_count[:nt])
+    n_out = int(tile_off[-1].item())
+    b1 = torch.empty(max(n_out, 1), dtype=_I32, device=dev)
+    b2 = torch.empty(max(n_out, 1), dtype=_I32, device=dev)
+    out = {}
+    first = True
+    for name, col in columns.items():
+        op = agg.get(name, "sum")
+        if callable(op) or op not in AGG_OPS:
+            raise NotImplementedError(f"aggregator {op!r} is not supported by the CUDA coarsener "
+                                      f"(supported: {sorted(AGG_OPS)})")
+        t = torch.from_numpy(np.ascontiguousarray(col))
+        if t.dtype not in _SRC_DTYPES:
+            t = t.to(torch.float64 if t.dtype.is_floating_point else torch.int64)
+        src = t.to(dev)
+        is_float = src.dtype.is_floating_point or op == "mean"
+        res = torch.empty(max(n_out, 1), dtype=torch.float64 if is_float else _I64, device=dev)
+        _lib.call("cb200_runs_aggregate", _ptr(keys), _ptr(vals), n, _ptr(tile_off), _ptr(src),
+                  _SRC_DTYPES[src.dtype], AGG_OPS[op], _ptr(b1) if first else C.c_void_p(0),
+                  _ptr(b2) if first else C.c_void_p(0), _ptr(res) if not is_float else C.c_void_p(0),
+                  _ptr(res) if is_float else C.c_void_p(0), _stream())
+        out[name] = res[:n_out].cpu().numpy()
+        first = False
+    return (b1[:n_out].to(_I64).cpu().numpy(), b2[:n_out].to(_I64).cpu().numpy(), out, new_off)
 
 
 def _reduce_runs(keys, vals, n, swap, dev):
@@ -279,9 +341,10 @@ def _check_columns(clr, columns, agg):
         if col not in input_dtypes:
             raise ValueError(
                 f"Pixel value column '{col}' not found in input '{clr.filename}'.")
-    if columns != ["count"] or (agg and any(v != "sum" for v in agg.values())):
-        raise NotImplementedError(
-            "the CUDA coarsener aggregates the integer 'count' column with 'sum' only")
+    for col, op in (agg or {}).items():
+        if callable(op) or op not in AGG_OPS:
+            raise NotImplementedError(f"aggregator {op!r} for column '{col}' is not supported by the CUDA "
+                                      f"coarsener (supported: {sorted(AGG_OPS)})")
     return columns
 
 
@@ -301,6 +364,14 @@ class CoolerCoarsener:
         self.factor = factor
         self.chunksize = int(chunksize)
         self.columns = _check_columns(source, columns, agg)
+        self.agg = {col: "sum" for col in self.columns}           # _reduce.py:529-531
+        if agg is not None:
+            self.agg.update(agg)
+        dt = source.pixels().dtypes
+        # the fast path carries an int32 count through the merge; anything else (other columns, other
+        # aggregators, floating-point or wide counts) goes through the general index-payload path
+        self._fast = (self.columns == ["count"] and self.agg["count"] == "sum"
+                      and np.dtype(dt["count"]).kind in "iu" and np.dtype(dt["count"]).itemsize <= 4)
         self.old_binsize = source.binsize
         self.new_binsize = None if self.old_binsize is None else self.old_binsize * factor
         old_bins = source.bins()[:]
@@ -309,7 +380,8 @@ class CoolerCoarsener:
                                old_bins["end"].values, chromsizes.values, factor)
         self.new_bins_arrays = (c, s, e)
         self._chromnames = list(chromsizes.index)
-        self._table = table if table is not None else PixelTable.from_cooler(source, device=device)
+        self._device = device
+        self._table = table if (table is not None or not self._fast) else PixelTable.from_cooler(source, device=device)
         self.result_table = None
 
     @property
@@ -320,6 +392,9 @@ class CoolerCoarsener:
         return pd.DataFrame({"chrom": chrom, "start": s, "end": e})
 
     def __iter__(self):
+        if not self._fast:
+            yield from self._iter_general()
+            return
         new_table, b1ids = coarsen_table(self._table, self.factor)
         self.result_table = new_table
         b1, b2, cnt = table_to_host(new_table, b1ids)
@@ -330,6 +405,38 @@ class CoolerCoarsener:
         for lo, hi in zip(edges[:-1], edges[1:]):
             if hi > lo:
                 yield {"bin1_id": b1[lo:hi], "bin2_id": b2[lo:hi], "count": cnt[lo:hi]}
+
+    def _iter_general(self):
+        """Any numeric value columns / aggregators (``coarsen_columns``).  Column dtypes follow pandas'
+        groupby: sum / min / max / first / last keep the input dtype (an integer sum that leaves it
+        widens to int64), mean is float64; ``create`` then casts to the requested ``dtypes``."""
+        clr = self.clr
+        chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
+        bin1_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
+        in_dt = clr.pixels().dtypes
+        with clr.open("r") as grp:
+            bin2 = np.asarray(grp["pixels"]["bin2_id"][:])
+            cols = {c: np.asarray(grp["pixels"][c][:]) for c in self.columns}
+        b1, b2, vals, new_off = coarsen_columns(bin1_offset, bin2, chrom_offset, self.factor, cols, self.agg,
+                                                device=self._device)
+        for c in self.columns:
+            want = np.dtype(in_dt[c])
+            v = vals[c]
+            if self.agg[c] == "mean":
+                if want == np.float32:
+                    vals[c] = v.astype(np.float32)             # pandas: the mean of a float32 column is float32
+                continue
+            if want.kind in "iu" and len(v) and (v.min() < np.iinfo(want).min or v.max() > np.iinfo(want).max):
+                continue                                       # overflowing integer sum: stays int64
+            vals[c] = v.astype(want, copy=False)
+        self.result_table = None                               # nothing to chain: the next level re-reads its source
+        ind = np.searchsorted(b1, np.arange(int(new_off[-1]) + 1), side="left")
+        edges = _prune_edges(ind, self.chunksize)
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            if hi > lo:
+                chunk = {"bin1_id": b1[lo:hi], "bin2_id": b2[lo:hi]}
+                chunk.update({c: vals[c][lo:hi] for c in self.columns})
+                yield chunk
 
 
 def _as_cooler(obj):
@@ -374,7 +481,7 @@ def _coarsen(clr, output_uri, factor, chunksize, nproc, columns, dtypes, agg, de
     if output_uri is None:
         chunks = list(iterator)
         cat = {k: (np.concatenate([c[k] for c in chunks]) if chunks else np.zeros(0, dtype=np.int64))
-               for k in ("bin1_id", "bin2_id", "count")}
+               for k in ("bin1_id", "bin2_id", "count")}        # like create(): only 'count' is kept
         c, s, e = iterator.new_bins_arrays
         out = MemCooler.from_arrays(iterator._chromnames, clr.chromsizes.values, c, s, e,
                                     cat["bin1_id"], cat["bin2_id"],
@@ -384,6 +491,9 @@ def _coarsen(clr, output_uri, factor, chunksize, nproc, columns, dtypes, agg, de
         return out, iterator.result_table
     kwargs = dict(kwargs)
     kwargs.setdefault("append", True)
+    if kwargs.get("mode") == "w":                  # `coarsen x.cool -o x.cool`: never truncate the input
+        from .create import refuse_truncating_source
+        refuse_truncating_source(parse_cooler_uri(output_uri)[0], [clr], "w")
     _create(output_uri, iterator.new_bins, iterator, dtypes=dtypes, symmetric_upper=symmetric_upper,
             **kwargs)
     return None, iterator.result_table
@@ -431,6 +541,7 @@ def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=
     if outfile is not None:
         from . import create as _cr
         from . import h5write
+        _cr.refuse_truncating_source(outfile, bases.values(), "w")
         cols = tuple(columns) if columns is not None else ("count",)
         first = True
         for res, clr in bases.items():
@@ -470,6 +581,7 @@ def legacy_zoomify(input_uri, outfile, nproc, chunksize, lock=None, device="cuda
     from . import create as _cr
     from . import h5write
     clr = _as_cooler(input_uri)
+    _cr.refuse_truncating_source(outfile, [clr], "w")
     n_zooms = get_quadtree_depth(clr.chromsizes, clr.binsize, HIGLASS_TILE_DIM)
     factor = 2
     zoom_levels = OrderedDict()
@@ -565,7 +677,7 @@ def merge_coolers(output_uri, input_uris, mergebuf, columns=None, dtypes=None, a
     if output_uri is None:
         chunks = list(iterator)
         cat = {k: (np.concatenate([c[k] for c in chunks]) if chunks else np.zeros(0, dtype=np.int64))
-               for k in ("bin1_id", "bin2_id", "count")}
+               for k in ("bin1_id", "bin2_id", "count")}        # like create(): only 'count' is kept
         c0 = clrs[0]
         bins = c0.bins()[:]
         out = MemCooler.from_arrays(list(c0.chromsizes.index), c0.chromsizes.values,

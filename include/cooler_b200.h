@@ -270,12 +270,30 @@ int cb200_ice_update(const cb200_ice* st, int32_t iter, int32_t fused_combine, v
 int cb200_ice_update_peer(const cb200_ice* st, int32_t iter, const double* const* peer_s,
                           int32_t world, int64_t peer_offset, void* stream);
 
+/* Two-stage form of the same fused all-reduce for long per-bin vectors (1 kb matrices: 25 MB per
+ * rank): cb200_ice_reduce_peer sums -- in rank order -- the slice [rank, rank+1) * ceil(n_bins /
+ * world) of every rank's local s (peer_s[r] + peer_offset) into red_local[bin]; after a second
+ * cross-rank barrier cb200_ice_update_gather reads every bin from its owner's buffer
+ * (peer_red[owner] + peer_offset) and runs K4.  NVLink traffic per rank and pass drops from
+ * (world - 1) to 2 (world - 1) / world vectors; every rank still sees identical bits. */
+int cb200_ice_reduce_peer(const cb200_ice* st, const double* const* peer_s, int32_t world, int32_t rank,
+                          int64_t peer_offset, double* red_local, void* stream);
+int cb200_ice_update_gather(const cb200_ice* st, int32_t iter, const double* const* peer_red,
+                            int32_t world, int64_t peer_offset, void* stream);
+
 /* ---- coarsen (replaces CoolerCoarsener._aggregate's join + pandas
  *      groupby(sort=True).sum(), src/cooler/_reduce.py:582-620) ------------ */
 /* Fused bin remap of one CSR copy: for every pixel (r, c, v)
  *   key_out = bin_map[c], val_out = {bin_map[r], v}   (sort input). */
 int cb200_coarsen_remap(const cb200_copy* csr, int32_t n_rows, const int32_t* bin_map,
                         int32_t* key_out, cb200_px* val_out, void* stream);
+/* Bin maps of one coarsening step on the device: bin_map[n_bins] (old bin -> new bin = new_off[c] +
+ * (bin - off[c]) / factor, the closed form of src/cooler/_reduce.py:597-614 for chromosome c) and
+ * group_first[n_new + 1] (first old bin of every new bin).  chrom_offset / new_chrom_offset: DEVICE
+ * int64 [n_chroms + 1]; chromosomes without bins are allowed. */
+int cb200_coarsen_maps(const int64_t* chrom_offset, const int64_t* new_chrom_offset, int32_t n_chroms,
+                       int32_t factor, int32_t n_bins, int32_t n_new, int32_t* bin_map,
+                       int32_t* group_first, void* stream);
 /* One round of the merge form of K5.  `in` = pixels {column, count} of a bin1-major copy (round 0:
  * fine column ids, remapped through bin_map on the fly; later rounds: coarse column ids); the
  * fine rows group_first[g] .. group_first[g+1] pool into coarse row g.  In round r a list is the
@@ -301,6 +319,15 @@ int cb200_runs_write(const int32_t* keys, const cb200_px* vals, int64_t n,
                      const int64_t* tile_off, int32_t swap,
                      int32_t* key_out, cb200_px* val_out, int64_t* sum64_out,
                      int32_t* overflow, void* stream);
+/* Generic form for any numeric value column and aggregator (the `agg` argument of
+ * coarsen_cooler / CoolerCoarsener, src/cooler/_reduce.py:616-620): vals = {other, index into src},
+ * stream sorted so that equal (key, other) are adjacent in pixel order.  src_dtype: 0 int32, 1 int64
+ * (accumulated in int64 -> int_out), 2 float32, 3 float64 (accumulated in float64 -> float_out);
+ * op: 0 sum, 1 min, 2 max, 3 first, 4 last, 5 mean (always -> float_out).  key_out / other_out
+ * (NULL to skip) receive the run's (key, other).  tile_off as for cb200_runs_write. */
+int cb200_runs_aggregate(const int32_t* keys, const cb200_px* vals, int64_t n, const int64_t* tile_off,
+                         const void* src, int32_t src_dtype, int32_t op, int32_t* key_out,
+                         int32_t* other_out, int64_t* int_out, double* float_out, void* stream);
 /* (bin1', val={bin2', v}) sorted by (bin1', bin2') -> bin1_id/bin2_id int64 + count,
  * the ContactBinner chunk layout (src/cooler/create/_ingest.py:507-528). */
 int cb200_unpack_pixels(const int32_t* bin1, const cb200_px* val, int64_t n,

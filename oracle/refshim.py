@@ -145,7 +145,7 @@ class MemGroup(dict):
 
 
 def register(name, chromnames, chromsizes, bins_chrom, bins_start, bins_end,
-             bin1, bin2, count, binsize, symmetric_upper=True):
+             bin1, bin2, count, binsize, symmetric_upper=True, extra_columns=None):
     """Register an in-memory cooler under file name ``name``.
 
     ``binsize`` None means variable-size bins.
@@ -163,7 +163,7 @@ def register(name, chromnames, chromsizes, bins_chrom, bins_start, bins_end,
                  "start": np.asarray(bins_start, np.int32),
                  "end": np.asarray(bins_end, np.int32)},
         "pixels": {"bin1_id": bin1, "bin2_id": np.asarray(bin2, np.int64),
-                   "count": np.asarray(count)},
+                   "count": np.asarray(count), **{k: np.asarray(v) for k, v in (extra_columns or {}).items()}},
         "indexes": {"chrom_offset": chrom_offset, "bin1_offset": bin1_offset},
     }
     attrs = {
@@ -227,14 +227,15 @@ def ref_balance(name, **kwargs):
     return bias, stats, passes, warned
 
 
-def ref_coarsen(name, factor, chunksize=10_000_000):
+def ref_coarsen(name, factor, chunksize=10_000_000, columns=None, agg=None):
     """Concatenated chunk stream of the reference's CoolerCoarsener (_reduce.py:501-642)."""
     cooler = import_reference()
+    columns = ["count"] if columns is None else list(columns)
     it = cooler._reduce.CoolerCoarsener(name, int(factor), chunksize,
-                                       columns=["count"], agg=None, batchsize=1)
+                                       columns=columns, agg=agg, batchsize=1)
     chunks = list(it)
     out = {k: np.concatenate([c[k] for c in chunks]) if chunks else np.array([])
-           for k in ("bin1_id", "bin2_id", "count")}
+           for k in ["bin1_id", "bin2_id", *columns]}
     nb = it.new_bins
     new_bins = {"chrom": np.asarray(nb["chrom"].cat.codes if hasattr(nb["chrom"], "cat") else nb["chrom"]),
                 "start": nb["start"].values, "end": nb["end"].values}

@@ -308,6 +308,32 @@ def test_zoomify_cli_legacy_layout(tmp_path):
     assert sums == [100000] * 4
 
 
+def test_zoomify_and_coarsen_never_truncate_their_input(tmp_path):
+    """`zoomify x.mcool::resolutions/2` without -o derives the output name x.mcool == the input;
+    opening it with mode 'w' would destroy the (memory-mapped) source.  The reference is protected
+    because h5py refuses to truncate an open file; here the call fails before anything is opened."""
+    import hashlib
+    import shutil
+
+    from cooler_b200.cli import cli
+    src = str(tmp_path / "toy.mcool")
+    shutil.copy(os.path.join(COOL, "toy.symm.upper.2.mcool"), src)
+    digest = hashlib.sha256(open(src, "rb").read()).hexdigest()
+    r = CliRunner()
+    res = r.invoke(cli, ["zoomify", src + "::resolutions/2", "-r", "4,8"])          # no -o
+    assert res.exit_code != 0 and isinstance(res.exception, OSError), (res.output, res.exception)
+    res = r.invoke(cli, ["zoomify", src + "::resolutions/2", "-r", "4,8", "-o", src])
+    assert res.exit_code != 0 and isinstance(res.exception, OSError)
+    res = r.invoke(cli, ["zoomify", src + "::resolutions/2", "--legacy", "-o", src])
+    assert res.exit_code != 0 and isinstance(res.exception, OSError)
+    one = _copy_cool("toy.asymm.2.cool", tmp_path)
+    d1 = hashlib.sha256(open(one, "rb").read()).hexdigest()
+    res = r.invoke(cli, ["coarsen", one, "-k", "2", "-o", one])
+    assert res.exit_code != 0 and isinstance(res.exception, OSError)
+    assert hashlib.sha256(open(src, "rb").read()).hexdigest() == digest
+    assert hashlib.sha256(open(one, "rb").read()).hexdigest() == d1
+
+
 def test_merge_cli_writes_file(tmp_path):
     """`cooler merge out.cool a b c` on real files (cli/merge.py:8-80)."""
     from cooler_b200 import h5lite, store

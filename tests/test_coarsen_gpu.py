@@ -2,6 +2,8 @@
 (toy.*.bg2 chains, tests/test_reduce.py:83-175), with reference outputs frozen in
 tests/golden (GM12878 x2/x5/x10, odd.1 x4 & co., variable bins) and with the oracle
 on larger random tables.  Bar: bit-exact pixels."""
+import os
+
 import numpy as np
 import pytest
 
@@ -195,3 +197,60 @@ def test_merge_matches_oracle_large():
     np.testing.assert_array_equal(g1, want[0]), np.testing.assert_array_equal(g2, want[1])
     np.testing.assert_array_equal(gc, want[2])
     assert int(gc.sum()) == sum(int(p["count"].sum()) for p in pxs)
+
+
+# --- general value columns / aggregators (reference tests/test_reduce.py:100-118) ---------
+@pytest.mark.parametrize("key", ["gm_mean_x2", "gm_min_x5", "gm_max_x3", "gm_first_x2", "gm_last_x7",
+                                 "gm_cols_x2", "gm_fsum_x5", "gmf_sum_x2", "gmf_mean_x10"])
+def test_general_aggregation_matches_reference_golden(key):
+    """CoolerCoarsener with agg = mean / min / max / first / last, extra value columns (float64, wide
+    int64) and a float32 count column, against the UNMODIFIED reference (pandas groupby): ids and
+    integer results bit-exact, float64 results to 1e-12, float32 to 1e-6; dtypes as pandas gives them."""
+    from cooler_b200 import MemCooler
+    from cooler_b200.reduce import CoolerCoarsener
+    from tests import _agg_cases
+    tab, factor, columns, agg = _agg_cases.CASES[key]
+    gm = _golden.gm12878()
+    fcount, big = _agg_cases.derived(gm)
+    count = gm["count"] if tab == "gm" else (gm["count"] * 0.5).astype(np.float32)
+    clr = MemCooler.from_arrays([str(x) for x in gm["chromnames"]], gm["chromsizes"], gm["bins_chrom"],
+                                gm["bins_start"], gm["bins_end"], gm["bin1_id"], gm["bin2_id"], count,
+                                binsize=2_000_000, extra_pixel_columns={"fcount": fcount, "big": big})
+    chunks = list(CoolerCoarsener(clr, factor, 5000, columns=columns, agg=agg))
+    got = {k: np.concatenate([c[k] for c in chunks]) for k in chunks[0]}
+    G = dict(np.load(os.path.join(_golden.GOLD, "coarsen_agg_golden.npz")))
+    assert sorted(got) == sorted(k.split("/", 1)[1] for k in G if k.startswith(key + "/"))
+    for k, v in got.items():
+        want = G[f"{key}/{k}"]
+        assert v.dtype == want.dtype, (k, v.dtype, want.dtype)
+        if want.dtype.kind in "iu":
+            np.testing.assert_array_equal(v, want)
+        else:
+            np.testing.assert_allclose(v, want, rtol=1e-6 if want.dtype == np.float32 else 1e-12)
+    # chunks never split a coarse row and stay sorted / duplicate-free
+    keyv = got["bin1_id"] * (got["bin2_id"].max() + 1) + got["bin2_id"]
+    assert np.all(np.diff(keyv) > 0)
+
+
+def test_coarsen_cooler_with_float_dtype_and_mean(tmp_path):
+    """`--field count:dtype=float,agg=mean` (reference tests/test_cli_ops.py:58-65): the output column is
+    float and holds the means."""
+    from cooler_b200 import MemCooler, store
+    from cooler_b200.cli import cli
+    from click.testing import CliRunner
+    gm = _golden.gm12878()
+    clr = MemCooler.from_arrays([str(x) for x in gm["chromnames"]], gm["chromsizes"], gm["bins_chrom"],
+                                gm["bins_start"], gm["bins_end"], gm["bin1_id"], gm["bin2_id"], gm["count"],
+                                binsize=2_000_000)
+    store.REGISTRY.clear()
+    store.register("gm.cool", clr)
+    out = str(tmp_path / "mean.cool")
+    res = CliRunner().invoke(cli, ["coarsen", "gm.cool", "--factor", "2", "--field", "count:dtype=float,agg=mean",
+                                   "-o", out])
+    assert res.exit_code == 0, (res.output, res.exception)
+    G = dict(np.load(os.path.join(_golden.GOLD, "coarsen_agg_golden.npz")))
+    with store.open_cooler(out).open("r") as grp:
+        cnt = np.asarray(grp["pixels"]["count"][:])
+        assert cnt.dtype.kind == "f"
+        np.testing.assert_allclose(cnt, G["gm_mean_x2/count"], rtol=1e-12)
+        np.testing.assert_array_equal(np.asarray(grp["pixels"]["bin2_id"][:]), G["gm_mean_x2/bin2_id"])

@@ -18,3 +18,50 @@ def test_sharded_balance_matches_single_gpu():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(res.stdout[-3000:], res.stderr[-3000:])
     assert res.returncode == 0
+
+
+def _torchrun(args, port, timeout=900):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port)] + args
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+
+
+@pytest.mark.gpu
+def test_balance_cooler_group_reads_row_shards_of_real_files(tmp_path):
+    """balance_cooler(clr, group=...) on the bundled GM12878 .cool (reference goldens) and on a
+    written 1e7-pixel .cool (oracle), two ranks, every rank reading its own bin1 row range."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    res = _torchrun([os.path.join(ROOT, "tools", "check_dist_cooler.py"), str(tmp_path)], 29519)
+    print(res.stdout[-3000:], res.stderr[-3000:])
+    assert res.returncode == 0 and "FAIL" not in res.stdout and res.stdout.count(" OK") >= 5
+
+
+@pytest.mark.gpu
+def test_balance_cli_under_torchrun(tmp_path):
+    """`torchrun ... -m cooler_b200.cli balance FILE`: rank 0 checks and writes, exit codes as the
+    reference's CLI (cli/balance.py:180-206)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import shutil
+
+    import numpy as np
+
+    from cooler_b200 import store
+    from tests import _golden
+    src = os.path.join(ROOT, "tests", "golden", "cool", "hg19.GM12878-MboI.matrix.2000kb.cool")
+    fn = str(tmp_path / "gm.cool")
+    shutil.copy(src, fn)
+    res = _torchrun(["-m", "cooler_b200.cli", "balance", fn, "--check"], 29521)
+    assert res.returncode == 1 and "No 'weight' column found" in res.stdout, (res.stdout, res.stderr[-2000:])
+    res = _torchrun(["-m", "cooler_b200.cli", "balance", fn], 29523)
+    assert res.returncode == 0, res.stderr[-3000:]
+    BAL, _ = _golden.balance_golden()
+    with store.open_cooler(fn).open("r") as grp:
+        np.testing.assert_allclose(np.asarray(grp["bins"]["weight"][:]), BAL["gm/defaults"], rtol=1e-9, equal_nan=True)
+    res = _torchrun(["-m", "cooler_b200.cli", "balance", fn], 29525)          # exists, no --force
+    assert res.returncode == 1 and "already exists" in res.stderr
+    res = _torchrun(["-m", "cooler_b200.cli", "balance", fn, "--force", "--cis-only"], 29527)
+    assert res.returncode == 0, res.stderr[-3000:]
+    with store.open_cooler(fn).open("r") as grp:
+        np.testing.assert_allclose(np.asarray(grp["bins"]["weight"][:]), BAL["gm/cis_only"], rtol=1e-9, equal_nan=True)

@@ -51,6 +51,22 @@ def test_region_fetch_and_missing_weights():
     np.testing.assert_allclose(direct, MC.GOLD["chr1_bal"], rtol=1e-9, equal_nan=True)
 
 
+def test_4dn_weight_columns_are_divisive_by_default():
+    """balance='KR' | 'VC' | 'VC_SQRT' (4DN / hic2cool columns) divide unless divisive_weights is
+    given, exactly like Cooler.matrix (api.py:28, 367-368): the golden divisive window is reproduced."""
+    import cooler_b200
+    t, w, (i0, i1, j0, j1), kw = MC.inputs("divisive")
+    clr = _clr(t, True, w)
+    with clr.open("r+") as g:
+        g["bins"].create_dataset("KR", data=w)
+    want = MC.GOLD["divisive"]
+    np.testing.assert_array_equal(cooler_b200.matrix(clr, balance="KR")[i0:i1, j0:j1], want)
+    np.testing.assert_array_equal(clr.matrix(balance="KR")[i0:i1, j0:j1], want)
+    mult = cooler_b200.matrix(clr, balance="KR", divisive_weights=False)[i0:i1, j0:j1]
+    np.testing.assert_array_equal(mult, cooler_b200.matrix(clr, balance=True)[i0:i1, j0:j1])
+    assert not np.array_equal(mult, want, equal_nan=True)
+
+
 @pytest.mark.parametrize("case", MC.SPARSE)
 def test_sparse_fetch_matches_reference_golden(case):
     import cooler_b200

@@ -1,0 +1,102 @@
+"""Multi-GPU entry through the reference API, run under torchrun (one rank per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29519 tools/check_dist_cooler.py [workdir]
+
+1. ``balance_cooler(clr, group=WORLD)`` on the reference's own bundled GM12878 2 Mb ``.cool``
+   (every rank reads its bin1 row range of the file) against the golden vectors made by the
+   UNMODIFIED reference (tests/golden/make_golden.py): masks exact, bias within 1e-9, all modes.
+2. A ~1e7-pixel synthetic ``.cool`` written by rank 0 (``create_cooler``), balanced across the ranks
+   with ``store=True``, against the CPU oracle (oracle/ice_numpy.py) run to convergence on rank 0:
+   mask, pass count (from the stored stats: converged), bias, scale, var; the stored column is read back.
+3. ``python -m cooler_b200.cli balance`` semantics under torchrun are covered by
+   tests/test_dist_gpu.py, which launches the CLI itself.
+"""
+import os
+import sys
+import tempfile
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import cooler_b200
+    from cooler_b200 import store, synth
+    from tests import _golden
+    group = dist.group.WORLD
+    ok = True
+    workdir = sys.argv[1] if len(sys.argv) > 1 else tempfile.gettempdir()
+
+    # ---- 1. the bundled GM12878 file vs the reference goldens -------------------------------
+    BAL, META = _golden.balance_golden()
+    path = os.path.join(ROOT, "tests", "golden", "cool", "hg19.GM12878-MboI.matrix.2000kb.cool")
+    for key in ("gm/defaults", "gm/cis_only", "gm/trans_only", "gm/diag0"):
+        kw = dict(META[key]["kwargs"])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            bias, stats = cooler_b200.balance_cooler(store.open_cooler(path), group=group, **kw)
+        want = BAL[key]
+        same = np.array_equal(np.isnan(bias), np.isnan(want))
+        err = float(np.nanmax(np.abs(bias / want - 1))) if np.isfinite(want).any() else 0.0
+        good = same and err < 1e-9
+        ok &= bool(good)
+        if rank == 0:
+            print(f"[check_dist_cooler] world={world} {key}: mask_equal={same} max_rel_err={err:.2e} "
+                  f"{'OK' if good else 'FAIL'}", flush=True)
+
+    # ---- 2. a written ~1e7-pixel .cool, store=True, vs the oracle -----------------------------
+    synth.ROWS_PER_BLOCK_TARGET = 4_000_000
+    plan = synth.SynthPlan(250_000, 10_000_000, seed=3)
+    fn = os.path.join(workdir, "check_dist_1e7.cool")
+    if rank == 0:
+        import pandas as pd
+        full = synth.generate(plan, device=f"cuda:{local}", pin=False)
+        off = full["bin1_offset"].numpy()
+        b1 = np.repeat(np.arange(plan.n_bins, dtype=np.int64), np.diff(off))
+        nb = np.diff(plan.chrom_offset)
+        start = np.concatenate([np.arange(k, dtype=np.int64) * plan.binsize for k in nb])
+        bins = pd.DataFrame({"chrom": np.repeat(np.array(synth.HG38_NAMES), nb), "start": start,
+                             "end": np.minimum(start + plan.binsize, np.repeat(plan.chromsizes, nb))})
+        px = {"bin1_id": b1, "bin2_id": full["bin2_id"].numpy(), "count": full["count"].numpy()}
+        from cooler_b200.create import create_cooler
+        create_cooler(fn, bins, px)
+    dist.barrier()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bias, stats = cooler_b200.balance_cooler(store.open_cooler(fn), group=group, store=True)
+    if rank == 0:
+        from oracle import ice_numpy
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want, wstats, wpasses, _ = ice_numpy.balance_arrays(px, plan.chrom_offset, off, return_passes=True)
+        same = np.array_equal(np.isnan(bias), np.isnan(want))
+        err = float(np.nanmax(np.abs(bias / want - 1)))
+        with store.open_cooler(fn).open("r") as grp:
+            stored = np.asarray(grp["bins"]["weight"][:])
+            attrs = dict(grp["bins"]["weight"].attrs)
+        good = (same and err < 1e-9 and bool(stats["converged"]) == bool(wstats["converged"])
+                and abs(stats["scale"] / wstats["scale"] - 1) < 1e-9 and abs(stats["var"] / wstats["var"] - 1) < 1e-9
+                and np.array_equal(stored, bias, equal_nan=True) and bool(attrs["converged"]))
+        ok &= bool(good)
+        print(f"[check_dist_cooler] world={world} written .cool nnz={len(b1)} oracle passes={wpasses} "
+              f"mask_equal={same} max_rel_err={err:.2e} stored_column_equal={np.array_equal(stored, bias, equal_nan=True)} "
+              f"{'OK' if good else 'FAIL'}", flush=True)
+        os.unlink(fn)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
