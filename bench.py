@@ -415,6 +415,7 @@ def main():
     barrier()
     state.sweep_events = []
     state.comm_events = []
+    state.stage_events = []
     state.launches = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launched = 0
@@ -440,6 +441,14 @@ def main():
     comm_ms = [c0.elapsed_time(c1) for k, (c0, c1) in enumerate(state.comm_events)
                if (k % per_step) < passes_per_step]
     comm_ms_avg = float(np.mean(comm_ms)) if comm_ms else 0.0
+    # multi-GPU: mean duration of the stages after the sweep (this rank; the slowest rank's line is reported)
+    stage_names = (["combine", "barrier", "reduce_scatter", "barrier2", "gather+update"]
+                   if getattr(state, "two_stage", False) else ["combine", "barrier", "allreduce+update"])
+    stage_ms = [0.0] * len(stage_names)
+    used = [m for k, m in enumerate(state.stage_events) if (k % per_step) < passes_per_step]
+    for m in used:
+        for i in range(len(stage_names)):
+            stage_ms[i] += m[i].elapsed_time(m[i + 1]) / len(used)
     gpu_launches = state.launches
     state.sweep_events = None
     value = nnz_total * passes_per_step * args.steps / (t_ms * 1e-3)
@@ -448,8 +457,9 @@ def main():
     bytes_pass_local = prob.bytes_per_pass()
     achieved = bytes_pass_local / (sweep_ms_avg * 1e-3) / 1e9
     # the roofline line is the SLOWEST rank's: the loop runs at its pace
-    per_rank = torch.zeros(world, 3, dtype=torch.float64, device="cuda")
-    per_rank[rank] = torch.tensor([sweep_ms_avg, achieved / peak, comm_ms_avg], dtype=torch.float64)
+    per_rank = torch.zeros(world, 3 + 5, dtype=torch.float64, device="cuda")
+    per_rank[rank, :3] = torch.tensor([sweep_ms_avg, achieved / peak, comm_ms_avg], dtype=torch.float64)
+    per_rank[rank, 3:3 + len(stage_ms)] = torch.tensor(stage_ms, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(per_rank)
     per_rank = per_rank.cpu().numpy()
@@ -557,7 +567,10 @@ def main():
                                 "sweep_slowest_rank": float(per_rank[:, 0].max()),
                                 "sweep_fastest_rank": float(per_rank[:, 0].min()),
                                 "sweep_per_rank": [round(float(x), 4) for x in per_rank[:, 0]],
-                                "allreduce_incl_wait_slowest_rank": float(per_rank[:, 2].max())}}
+                                "allreduce_incl_wait_slowest_rank": float(per_rank[:, 2].max()),
+                                "stages_after_sweep_on_slowest_rank": (
+                                    {nm: round(float(per_rank[int(np.argmax(per_rank[:, 0])), 3 + i]), 4)
+                                     for i, nm in enumerate(stage_names)} if world > 1 else None)}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -85,6 +85,8 @@ SIGNATURES = {
     "cb200_exclusive_scan_i32": (C.c_int, [_P, _P, _I64, _P, _SZ, _P]),
     "cb200_sort_workspace_bytes": (_SZ, [_I64]),
     "cb200_sort_pairs": (C.c_int, [_P, _P, _P, _P, _P, _P, _I64, C.c_int, C.c_int, _P, _SZ, _P]),
+    "cb200_median_workspace_bytes": (_SZ, [_I32]),
+    "cb200_segment_medians": (C.c_int, [_P, _P, _I32, _I64, _I32, _P, _P, _P, _SZ, _P]),
     "cb200_pack_pixels": (C.c_int, [_P, _P, _I64, _P, _P]),
     "cb200_pack_pixels_i32": (C.c_int, [_P, _P, _I64, _P, _P]),
     "cb200_tile_rows": (C.c_int, [_P, _I32, _I64, _P, _P]),

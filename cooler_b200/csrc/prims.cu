@@ -329,3 +329,151 @@ int cb200_sort_pairs(const int32_t* keys_in, const cb200_px* vals_in, int32_t* k
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------ exact medians ----
+// Order statistics of float64 values by radix selection (8 passes of 8 bits from the most
+// significant byte of an order-preserving 64-bit key).  Used for the medians of the bin filters
+// (_balance.py:400-409, util.mad): selection returns elements of the input, so the result is
+// bit-identical to numpy's partition-based np.median whatever the order of evaluation.
+// Query q = 2 s + h asks for the element of rank (cnt_s - 1) / 2 (h = 0) or cnt_s / 2 (h = 1)
+// among the valid elements of segment s -- the two middle elements whose mean is the median.
+namespace cb200 {
+
+__device__ __forceinline__ unsigned long long f64_order_key(double v) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);      // negatives reversed below the positives
+}
+__device__ __forceinline__ double f64_from_order_key(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ bool median_valid(double v, int positive_only) {
+  return positive_only ? (v > 0.0) : (v == v);               // NaNs never take part
+}
+
+__global__ void median_count_kernel(const double* __restrict__ x, const int64_t* __restrict__ seg_offset,
+                                    int n_segs, int positive_only, unsigned long long* __restrict__ cnt) {
+  const int s = blockIdx.y;
+  const int64_t lo = seg_offset[s], hi = seg_offset[s + 1];
+  unsigned long long c = 0;
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x)
+    c += median_valid(x[i], positive_only) ? 1 : 0;
+  c = (unsigned long long)warp_sum((long long)c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt[s], c);
+}
+
+// state[q] = {prefix, rank}; hist[q][256]
+__global__ void median_init_kernel(const unsigned long long* __restrict__ cnt, int n_segs,
+                                   unsigned long long* __restrict__ state) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 2 * n_segs) return;
+  const unsigned long long c = cnt[q >> 1];
+  state[2 * q] = 0ULL;
+  state[2 * q + 1] = c ? ((q & 1) ? c / 2 : (c - 1) / 2) : 0ULL;
+}
+
+__global__ void median_hist_kernel(const double* __restrict__ x, const int64_t* __restrict__ seg_offset,
+                                   int n_segs, int positive_only, int pass,
+                                   const unsigned long long* __restrict__ state,
+                                   unsigned int* __restrict__ hist) {
+  __shared__ unsigned int sh[2][256];
+  const int s = blockIdx.y;
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  const int shift = 56 - 8 * pass;
+  const unsigned long long p0 = state[2 * (2 * s)], p1 = state[2 * (2 * s + 1)];
+  const int64_t lo = seg_offset[s], hi = seg_offset[s + 1];
+  for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    if (!median_valid(v, positive_only)) continue;
+    const unsigned long long k = f64_order_key(v);
+    const unsigned long long high = pass ? (k >> (shift + 8)) : 0ULL;
+    const unsigned d = (unsigned)(k >> shift) & 255u;
+    if (high == p0) atomicAdd(&sh[0][d], 1u);
+    if (high == p1) atomicAdd(&sh[1][d], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+    const unsigned v = (&sh[0][0])[i];
+    if (v) atomicAdd(&hist[(size_t)(2 * s) * 256 + i], v);
+  }
+}
+
+// one warp per query: find the digit whose bucket holds the wanted rank, descend into it
+__global__ void median_step_kernel(int n_queries, unsigned long long* __restrict__ state,
+                                   unsigned int* __restrict__ hist) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (q >= n_queries) return;
+  const int lane = threadIdx.x & 31;
+  unsigned int* h = hist + (size_t)q * 256;
+  unsigned long long c[8], tot = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { c[k] = h[lane * 8 + k]; tot += c[k]; h[lane * 8 + k] = 0; }   // re-armed for the next pass
+  unsigned long long incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  const unsigned long long rank = state[2 * q + 1];
+  const unsigned long long before = incl - tot;
+  if (rank >= before && rank < incl) {             // exactly one lane (none when the segment is empty)
+    unsigned long long r = rank - before;
+    int k = 0;
+    while (r >= c[k]) { r -= c[k]; ++k; }
+    state[2 * q] = (state[2 * q] << 8) | (unsigned long long)(lane * 8 + k);
+    state[2 * q + 1] = r;
+  }
+}
+
+__global__ void median_finish_kernel(const unsigned long long* __restrict__ state,
+                                     const unsigned long long* __restrict__ cnt, int n_segs,
+                                     double* __restrict__ mid, int64_t* __restrict__ count_out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 2 * n_segs) return;
+  const unsigned long long c = cnt[q >> 1];
+  mid[q] = c ? f64_from_order_key(state[2 * q]) : __longlong_as_double(0x7ff8000000000000LL);
+  if (!(q & 1)) count_out[q >> 1] = (int64_t)c;
+}
+
+}  // namespace cb200
+
+extern "C" {
+
+size_t cb200_median_workspace_bytes(int32_t n_segs) {
+  return (size_t)n_segs * (8 + 2 * 16 + 2 * 256 * 4);
+}
+
+int cb200_segment_medians(const double* x, const int64_t* seg_offset, int32_t n_segs, int64_t max_seg_len,
+                          int32_t positive_only, double* mid_out, int64_t* count_out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  using namespace cb200;
+  if (n_segs <= 0) return 0;
+  if (workspace_bytes < cb200_median_workspace_bytes(n_segs)) {
+    set_error_msg("segment_medians: workspace too small");
+    return -1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  CB_CHECK(cudaMemsetAsync(workspace, 0, cb200_median_workspace_bytes(n_segs), s));
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(workspace);
+  unsigned long long* state = cnt + n_segs;
+  unsigned int* hist = reinterpret_cast<unsigned int*>(state + 4 * (size_t)n_segs);
+  int64_t bx = ceil_div64(max_seg_len > 0 ? max_seg_len : 1, 256 * 8);
+  if (bx > 1024) bx = 1024;
+  const dim3 grid((unsigned)bx, (unsigned)n_segs);
+  median_count_kernel<<<grid, 256, 0, s>>>(x, seg_offset, n_segs, positive_only, cnt);
+  CB_LAUNCH_CHECK("median_count");
+  median_init_kernel<<<(unsigned)ceil_div64(2 * n_segs, 128), 128, 0, s>>>(cnt, n_segs, state);
+  CB_LAUNCH_CHECK("median_init");
+  for (int pass = 0; pass < 8; ++pass) {
+    median_hist_kernel<<<grid, 256, 0, s>>>(x, seg_offset, n_segs, positive_only, pass, state, hist);
+    CB_LAUNCH_CHECK("median_hist");
+    median_step_kernel<<<(unsigned)ceil_div64(2 * n_segs, 4), 128, 0, s>>>(2 * n_segs, state, hist);
+    CB_LAUNCH_CHECK("median_step");
+  }
+  median_finish_kernel<<<(unsigned)ceil_div64(2 * n_segs, 128), 128, 0, s>>>(state, cnt, n_segs, mid_out, count_out);
+  CB_LAUNCH_CHECK("median_finish");
+  return 0;
+}
+
+}  // extern "C"

@@ -301,25 +301,70 @@ def plan_far_units(copies_counts, target):
     their partial sums."""
     target = max(int(target), 1)
     units, tiles, rb_units = [], [], []
+    n_units = n_tiles_ = 0
     for c, (rb0, j0, counts) in enumerate(copies_counts):
-        rb_unit = np.zeros(counts.shape[0] + 1, dtype=np.int32)
-        for k in range(counts.shape[0]):
-            rb_unit[k] = len(units)               # global index of the first unit of this row block
-            row = counts[k]
-            js = np.flatnonzero(row)
-            if len(js) == 0:
-                continue
-            cum = np.cumsum(row[js])
-            parts = max(1, int(round(cum[-1] / target)))     # equal parts of about `target` records
-            edges = np.searchsorted(cum, cum[-1] * np.arange(1, parts) / parts, side="left") + 1
+        n_rb = counts.shape[0]
+        rows, cols = np.nonzero(counts)                       # row-major: the tile list of every row block in order
+        per_row = np.bincount(rows, minlength=n_rb)           # non-empty tiles per row block
+        tstart = np.r_[0, np.cumsum(per_row)]
+        totals = counts.sum(axis=1)
+        parts = np.maximum(1, np.rint(totals / target).astype(np.int64))
+        parts[per_row == 0] = 0
+        n_row_units = np.where(parts <= 1, parts, 0)          # rows split below are counted there
+        split_units = {}
+        for k in np.flatnonzero(parts > 1):                   # only the (few) heavy row blocks need a search
+            js = cols[tstart[k]:tstart[k + 1]]
+            cum = np.cumsum(counts[k, js])
+            p = int(parts[k])
+            edges = np.searchsorted(cum, cum[-1] * np.arange(1, p) / p, side="left") + 1
             edges = np.unique(np.r_[0, edges, len(js)])
-            base = len(tiles)
-            tiles.extend((js + j0).tolist())
-            for e0, e1 in zip(edges[:-1], edges[1:]):
-                units.append((c, rb0 + k, base + int(e0), base + int(e1)))
-        rb_unit[counts.shape[0]] = len(units)
-        rb_units.append(rb_unit)
-    return (np.asarray(units, dtype=np.int32).reshape(-1, 4), np.asarray(tiles, dtype=np.int32), rb_units)
+            split_units[int(k)] = edges
+            n_row_units[k] = len(edges) - 1
+        first_unit = n_units + np.r_[0, np.cumsum(n_row_units)]
+        u = np.zeros((int(n_row_units.sum()), 4), dtype=np.int32)
+        single = np.flatnonzero(parts == 1)
+        pos = (first_unit[single] - n_units).astype(np.int64)
+        u[pos, 0], u[pos, 1] = c, rb0 + single
+        u[pos, 2], u[pos, 3] = n_tiles_ + tstart[single], n_tiles_ + tstart[single + 1]
+        for k, edges in split_units.items():
+            p0 = int(first_unit[k] - n_units)
+            m = len(edges) - 1
+            u[p0:p0 + m, 0], u[p0:p0 + m, 1] = c, rb0 + k
+            u[p0:p0 + m, 2] = n_tiles_ + tstart[k] + edges[:-1]
+            u[p0:p0 + m, 3] = n_tiles_ + tstart[k] + edges[1:]
+        units.append(u)
+        tiles.append((cols + j0).astype(np.int32))
+        rb_units.append(first_unit.astype(np.int32))
+        n_units += len(u)
+        n_tiles_ += len(cols)
+    units = np.concatenate(units) if units else np.zeros((0, 4), dtype=np.int32)
+    tiles = np.concatenate(tiles) if tiles else np.zeros(0, dtype=np.int32)
+    return units.reshape(-1, 4), tiles, rb_units
+
+
+def segment_medians(x, seg_offset, positive_only=False):
+    """Exact medians of the segments ``x[seg_offset[s]:seg_offset[s+1]]`` of a float64 DEVICE vector
+    (``cb200_segment_medians``: radix selection, bit-identical to ``np.median`` of the valid
+    elements -- positive ones when ``positive_only``).  Returns a numpy array, NaN for segments
+    without valid elements (as ``np.median`` of an empty array)."""
+    dev = x.device
+    seg_offset = np.asarray(seg_offset, dtype=np.int64)
+    S = len(seg_offset) - 1
+    if S <= 0:
+        return np.zeros(0)
+    off_d = torch.from_numpy(seg_offset).to(dev)
+    mid = torch.empty(2 * S, dtype=torch.float64, device=dev)
+    cnt = torch.empty(S, dtype=_I64, device=dev)
+    ws_bytes = _lib.load().cb200_median_workspace_bytes(S)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.call("cb200_segment_medians", _ptr(x), _ptr(off_d), S, int(np.diff(seg_offset).max()), int(bool(positive_only)),
+              _ptr(mid), _ptr(cnt), _ptr(ws), ws_bytes, _stream())
+    mid = mid.cpu().numpy().reshape(S, 2)
+    cnt = cnt.cpu().numpy()
+    out = np.full(S, np.nan)
+    for s in np.flatnonzero(cnt > 0):
+        out[s] = np.median(mid[s])                 # the same mean-of-the-two-middle-elements numpy takes
+    return out
 
 
 def marginals_i64(copy):

@@ -56,6 +56,19 @@ int cb200_sort_pairs(const int32_t* keys_in, const cb200_px* vals_in,
                      int64_t n, int key_shift, int key_bits,
                      void* workspace, size_t workspace_bytes, void* stream);
 
+/* Exact medians of float64 segments by radix selection (the medians of the bin filters,
+ * src/cooler/_balance.py:400-409 and util.mad, util.py:513-514, on O(n_bins) vectors -- 3.1e6 bins at
+ * 1 kb made numpy's three np.median calls the largest single item of the end-to-end time).  For
+ * every segment s = [seg_offset[s], seg_offset[s+1]) of x: count_out[s] = number of valid elements
+ * (positive_only != 0: x > 0, as in `c_marg[c_marg > 0]`; else: not NaN) and mid_out[2s], mid_out[2s+1]
+ * = the valid elements of rank (count-1)/2 and count/2 (NaN when count == 0); the median is their
+ * mean.  Selection returns input elements, hence bit-identical to np.median.  max_seg_len sizes the
+ * grid. */
+size_t cb200_median_workspace_bytes(int32_t n_segs);
+int cb200_segment_medians(const double* x, const int64_t* seg_offset, int32_t n_segs, int64_t max_seg_len,
+                          int32_t positive_only, double* mid_out, int64_t* count_out, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- pixel table build (replaces parallel.chunkgetter re-reading the file
  *      every pass, src/cooler/parallel.py:276-304, and the per-chunk filter
  *      functions _zero_diags/_zero_trans/_zero_cis, src/cooler/_balance.py:34-54,

@@ -24,6 +24,9 @@ class ConvergenceWarning(UserWarning):
     pass
 
 
+_SHARED = {}   # arrays inherited by fork()ed pool workers, see share()
+
+
 def _spans(nnz, chunksize):
     # _balance.py:351-357
     if chunksize is None:
@@ -67,6 +70,12 @@ def span_marginal_task(args):
 
 def _marginal(px, chrom_ids, n_bins, spans, map_, **kw):
     acc = np.zeros(n_bins)
+    if _SHARED.get("px") is px:
+        # the arrays were share()d with fork()ed pool workers: only the span travels, as in the
+        # reference, whose workers re-open the file (parallel.py:289-304)
+        for part in map_(shared_span_task, [(lo, hi, kw) for lo, hi in spans]):
+            acc = acc + part
+        return acc
     tasks = [(px, chrom_ids, n_bins, lo, hi, kw) for lo, hi in spans]
     for part in map_(span_marginal_task, tasks):            # reduce(add, zeros) parallel.py:253-273
         acc = acc + part
@@ -248,9 +257,6 @@ def balance_arrays(px, chrom_offset, bin1_offset, *, cis_only=False, trans_only=
 # while the per-task bias vector and the per-span n_bins result vector travel
 # by pickle exactly as in the reference.
 # ---------------------------------------------------------------------------
-_SHARED = {}
-
-
 def share(px, chrom_ids, n_bins):
     _SHARED.clear()
     _SHARED.update(px=px, chrom_ids=chrom_ids, n_bins=n_bins)

@@ -154,3 +154,56 @@ def test_row_walk_adversarial_shapes(name):
         _lib.call("cb200_ice_combine", st, T._stream())
         got = state.t["s"][:n].cpu().numpy()
         np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-9)
+
+
+def test_segment_medians_are_bit_identical_to_numpy():
+    """cb200_segment_medians (radix selection): np.median of every segment, ties, negatives,
+    zeros, empty segments, odd / even counts, the positive-only rule of the MAD-max filter."""
+    import torch
+    from cooler_b200.table import segment_medians, _use_device
+    dev = _use_device("cuda")
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.lognormal(0, 2, 100_001), -rng.lognormal(0, 1, 5000), np.zeros(777),
+                        np.repeat(rng.random(50), 400), [1e-310, 1e300, -1e-310]])
+    rng.shuffle(x)
+    off = np.array([0, 0, 1, 2, 5, 1000, 1000, 40_000, len(x) - 1, len(x)])
+    xd = torch.from_numpy(x).to(dev)
+    got = segment_medians(xd, off)
+    got_pos = segment_medians(xd, off, positive_only=True)
+    for s, (lo, hi) in enumerate(zip(off[:-1], off[1:])):
+        seg = x[lo:hi]
+        want = np.median(seg) if len(seg) else np.nan
+        pos = seg[seg > 0]
+        want_pos = np.median(pos) if len(pos) else np.nan
+        assert (np.isnan(want) and np.isnan(got[s])) or got[s] == want, (s, got[s], want)
+        assert (np.isnan(want_pos) and np.isnan(got_pos[s])) or got_pos[s] == want_pos, (s, got_pos[s], want_pos)
+
+
+def test_device_medians_give_the_same_filter_mask_as_numpy():
+    """prefilter_bias with the medians selected on the device == the all-numpy statement-for-statement path."""
+    import cooler_b200.balance as B
+    from cooler_b200.table import _use_device
+    dev = _use_device("cuda")
+    rng = np.random.default_rng(5)
+    sizes = [70_000, 50_001, 0, 3, 40_000]
+    co = np.r_[0, np.cumsum(sizes)].astype(np.int64)
+    n = int(co[-1])
+
+    class P:
+        pass
+    p = P()
+    p.table = P()
+    p.table.n_bins, p.table.device = n, dev
+    p.marg_sum = np.floor(rng.lognormal(7, 0.5, n))
+    p.marg_sum[rng.random(n) < 0.03] = 0
+    p.marg_sum[rng.random(n) < 0.01] *= 0.01
+    p.marg_nnz = np.floor(p.marg_sum / 3)
+    kw = dict(mad_max=5, min_nnz=10, min_count=0, blacklist=None, x0=None)
+    a = B.prefilter_bias(p, co, **kw)
+    old, B.DEVICE_MEDIAN_MIN_BINS = B.DEVICE_MEDIAN_MIN_BINS, 1 << 40
+    try:
+        b = B.prefilter_bias(p, co, **kw)
+    finally:
+        B.DEVICE_MEDIAN_MIN_BINS = old
+    assert n >= old and (a == 0).sum() > 100
+    np.testing.assert_array_equal(a, b)
