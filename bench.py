@@ -309,6 +309,9 @@ def main():
     ap.add_argument("--host-bin2", default="int32", choices=["int64", "int32"],
                     help="dtype of the pinned host bin2_id column of the e2e leg: int32 = narrowed while "
                          "reading the file, as read_cooler_arrays does (default); int64 = the on-disk dtype")
+    ap.add_argument("--calibrate", type=int, default=3,
+                    help="multi-GPU: rounds of cost calibration of the row shards (one sweep per rank, then the "
+                         "row boundaries move so that the sweep times agree); 0 = shards of equal pixel counts")
     ap.add_argument("--layout", default=None, help="force a sweep layout (IceProblem band=...), e.g. rows, allblocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
@@ -366,14 +369,6 @@ def main():
     from cooler_b200.balance import IceProblem, IceState, prefilter_bias
 
     dev = f"cuda:{local_rank}"
-    blocks = plan.shard_rows(rank, world)
-    data = synth.generate(plan, rows=blocks, device=dev)
-    torch.cuda.empty_cache()
-    nnz_local = data["nnz"]
-    nnz_total = torch.tensor([nnz_local], dtype=torch.int64, device="cuda")
-    if world > 1:
-        dist.all_reduce(nnz_total)
-    nnz_total = int(nnz_total.item())
     kw = dict(cis_only=args.mode == "cis", trans_only=args.mode == "trans")
 
     def barrier():
@@ -381,22 +376,67 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def build(rows):
+        """This rank's shard resident in HBM: host arrays, uploaded table, filtered copies, loop state."""
+        data = synth.generate(plan, rows=rows, device=dev)
+        torch.cuda.empty_cache()
+        table = cooler_b200.PixelTable.from_arrays(data["bin1_offset"], data["bin2_id"], data["count"],
+                                                   data["chrom_offset"], device=dev, row_range=data["row_range"])
+        prob = IceProblem(table, ignore_diags=ICE_KW["ignore_diags"], group=group, band=args.layout, **kw)
+        bias0 = prefilter_bias(prob, table.chrom_offset, mad_max=ICE_KW["mad_max"], min_nnz=ICE_KW["min_nnz"],
+                               min_count=ICE_KW["min_count"], blacklist=None, x0=None)
+        n = table.n_bins
+        cweights = None
+        if args.mode == "cis":
+            seg_offset = table.chrom_offset
+        else:
+            seg_offset = np.array([0, n])
+            if args.mode == "trans":
+                co = table.chrom_offset
+                cweights = 1.0 / np.repeat(1 - np.diff(co) / n, np.diff(co))
+        state = IceState(prob, bias0, cweights, seg_offset, ICE_KW["tol"], ICE_KW["max_iters"])
+        return data, table, prob, bias0, seg_offset, state
+
     # --- resident leg: table and filtered copies already in HBM ---------------
-    table = cooler_b200.PixelTable.from_arrays(data["bin1_offset"], data["bin2_id"], data["count"],
-                                               data["chrom_offset"], device=dev, row_range=data["row_range"])
-    prob = IceProblem(table, ignore_diags=ICE_KW["ignore_diags"], group=group, band=args.layout, **kw)
-    bias0 = prefilter_bias(prob, table.chrom_offset, mad_max=ICE_KW["mad_max"], min_nnz=ICE_KW["min_nnz"],
-                           min_count=ICE_KW["min_count"], blacklist=None, x0=None)
+    rows = plan.shard_rows(rank, world)
+    calibration = None
+    shares = np.full(world, 1.0 / world)
+    for rnd in range(args.calibrate if world > 1 else 0):
+        # cost-balanced shards: pixels are not equally expensive (a row near the start of the genome spreads
+        # its pixels over more column strips / tiles than one near the end), so every rank times its sweep and
+        # the pixel shares are scaled by (mean time / own time) ** 0.8 until the sweep times agree within 4 %
+        data, table, prob, bias0, seg_offset, state = build(rows)
+        import ctypes as C
+        from cooler_b200 import _lib
+        from cooler_b200.table import _stream
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        for k in range(2):                       # warm-up launch set, then the timed one
+            barrier()
+            ev[0].record()
+            for _ in range(4):
+                _lib.call("cb200_ice_sweep", C.byref(state.st), _stream())
+            ev[1].record()
+            torch.cuda.synchronize()
+        t_all = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t_all[rank] = ev[0].elapsed_time(ev[1]) / 4
+        dist.all_reduce(t_all)
+        t_all = t_all.cpu().numpy()
+        calibration = (calibration or []) + [{"round": rnd + 1, "pixel_share": [round(float(x), 4) for x in shares],
+                                             "sweep_ms": [round(float(x), 4) for x in t_all]}]
+        del data, table, prob, state
+        torch.cuda.empty_cache()
+        if t_all.max() / t_all.min() < 1.04:
+            break
+        shares = shares * (t_all.mean() / t_all) ** 0.8
+        shares /= shares.sum()
+        rows = synth.shard_rows_by_share(plan, shares)[rank]
+    data, table, prob, bias0, seg_offset, state = build(rows)
     n = table.n_bins
-    cweights = None
-    if args.mode == "cis":
-        seg_offset = table.chrom_offset
-    else:
-        seg_offset = np.array([0, n])
-        if args.mode == "trans":
-            co = table.chrom_offset
-            cweights = 1.0 / np.repeat(1 - np.diff(co) / n, np.diff(co))
-    state = IceState(prob, bias0, cweights, seg_offset, ICE_KW["tol"], ICE_KW["max_iters"])
+    nnz_local = data["nnz"]
+    nnz_total = torch.tensor([nnz_local], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nnz_total)
+    nnz_total = int(nnz_total.item())
     nnz_eff = torch.tensor([prob.nnz_eff], dtype=torch.int64, device="cuda")
     if world > 1:
         dist.all_reduce(nnz_eff)
@@ -553,7 +593,7 @@ def main():
         cpu["sample"] = f"{what}; " + cpu["sample"]
 
     if rank == 0:
-        detail = {"sweep_layout": layout, "nnz_stored": nnz_total, "nnz_effective": nnz_eff,
+        detail = {"shard_calibration": calibration if world > 1 else None, "sweep_layout": layout, "nnz_stored": nnz_total, "nnz_effective": nnz_eff,
                   "passes_per_step": passes_per_step, "converged": converged,
                   "masked_bins": int(np.isnan(bias).sum())}
         line = {"metric": "ICE pixels/s", "value": value, "unit": "pixels/s", "n_gpus": world,

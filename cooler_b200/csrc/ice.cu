@@ -194,7 +194,6 @@ __global__ void ice_reduce_slice_kernel(const int32_t* __restrict__ all_done,
 }
 
 constexpr int UPD_THREADS = 256;
-constexpr int UPD_BINS = 1024;   // bins per block of the per-bin kernels (host block table uses the same)
 
 __device__ __forceinline__ double block_sum(double v, double* sm) {
   v = warp_sum(v);
@@ -244,6 +243,7 @@ ice_marg_kernel(cb200_ice st, const double* const* __restrict__ peer_s, int worl
   if (!st.seg_done[seg]) {
     const int lo = st.blk_lo[b], hi = st.blk_hi[b];
     double sum = 0.0, cnt = 0.0;
+#pragma unroll 4                                   // independent (peer) loads of several bins in flight per thread
     for (int i = lo + threadIdx.x; i < hi; i += UPD_THREADS) {
       double si;
       if (kMode == 2) {

@@ -99,6 +99,20 @@ class SynthPlan:
         return lo, hi
 
 
+def shard_rows_by_share(plan: SynthPlan, shares):
+    """Contiguous row ranges [(lo, hi), ...] holding the given fractions of the expected pixels
+    (``shares`` sums to 1): the cost-balanced variant of ``SynthPlan.shard_rows``, whose shares are
+    all 1 / world."""
+    cw = plan.row_weight_cum
+    n = plan.n_bins
+    cum = np.r_[0.0, np.cumsum(np.asarray(shares, dtype=np.float64))]
+    cum /= cum[-1]
+    cuts = np.searchsorted(cw, cw[-1] * cum[1:-1], side="left")
+    cuts = np.maximum.accumulate(np.minimum(np.r_[0, cuts, n], n))
+    cuts[0], cuts[-1] = 0, n
+    return [(int(a), int(b)) for a, b in zip(cuts[:-1], cuts[1:])]
+
+
 def _gen_block(plan: SynthPlan, blk, bias_t, row_lo_t, row_hi_t, device):
     n = plan.n_bins
     r0, r1 = int(plan.block_edges[blk]), int(plan.block_edges[blk + 1])
