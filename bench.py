@@ -312,6 +312,9 @@ def main():
     ap.add_argument("--calibrate", type=int, default=3,
                     help="multi-GPU: rounds of cost calibration of the row shards (one sweep per rank, then the "
                          "row boundaries move so that the sweep times agree); 0 = shards of equal pixel counts")
+    ap.add_argument("--two-stage", action="store_true",
+                    help="multi-GPU: force the reduce-scatter + all-gather form of the fused all-reduce (default: "
+                         "only for vectors beyond balance.TWO_STAGE_BYTES, i.e. the 1 kb config at 8 GPUs)")
     ap.add_argument("--layout", default=None, help="force a sweep layout (IceProblem band=...), e.g. rows, allblocks")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
@@ -366,7 +369,10 @@ def main():
         group = dist.group.WORLD
 
     import cooler_b200
+    from cooler_b200 import balance as _balance
     from cooler_b200.balance import IceProblem, IceState, prefilter_bias
+    if args.two_stage:
+        _balance.TWO_STAGE_BYTES = 0
 
     dev = f"cuda:{local_rank}"
     kw = dict(cis_only=args.mode == "cis", trans_only=args.mode == "trans")

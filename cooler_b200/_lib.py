@@ -53,6 +53,7 @@ class Ice(C.Structure):
         ("far_copies", C.c_void_p), ("far_units", C.c_void_p), ("far_tiles", C.c_void_p),
         ("far_parts", C.c_void_p), ("far_claim", C.c_void_p),
         ("n_far_units", C.c_int32), ("far_col_shift", C.c_int32), ("far_warps", C.c_int32),
+        ("far_rec_bytes", C.c_int32),
     ]
 
 
@@ -95,6 +96,10 @@ SIGNATURES = {
     "cb200_strip_finish": (C.c_int, [_P, _P, _I64, _I32, _P, _P, _P, _P]),
     "cb200_far_finish": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "cb200_far_slot_chunks": (C.c_int, [_P, _I64, _P, _P]),
+    "cb200_far_pieces": (C.c_int, [_P, _I64, _P, _P, _P]),
+    "cb200_far_expand": (C.c_int, [_P, _P, _I64, _P, _P, _P, _P]),
+    "cb200_far_finish4": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _I32, _I32, _P, _P, _P]),
+    "cb200_far_interleave4": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
     "cb200_far_interleave": (C.c_int, [_P, _P, _P, _P, _I64, _I64, _P, _P]),
     "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),

@@ -124,7 +124,7 @@ class IceProblem:
 
     def __init__(self, table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2,
                  group=None, strip_bins=None, use_smem=True, band=None, peer_reduce=None,
-                 far_col_shift=None):
+                 far_col_shift=None, far_compact=None):
         self.table = table
         self.use_smem = use_smem
         self.far_copies = []
@@ -172,9 +172,11 @@ class IceProblem:
                 ckeys, cval = swap_key_other(ckeys, csc.px, csc.nnz)
             n1, n2 = csr.nnz, csc.nnz
             self.csr = self.csc = csr = csc = None
-            self.far_copies = [far_blocks(tkey[:n1], tval, n1, n_bins, self.far_col_shift)]
+            # both orientations hold the same counts, so they agree on compact (4-byte) records
+            self.far_copies = [far_blocks(tkey[:n1], tval, n1, n_bins, self.far_col_shift, compact=far_compact)]
             tkey = tval = None
-            self.far_copies.append(far_blocks(ckeys[:n2], cval, n2, n_bins, self.far_col_shift))
+            compact = self.far_copies[0].rec_bytes == 4 if self.far_copies[0] is not None else far_compact
+            self.far_copies.append(far_blocks(ckeys[:n2], cval, n2, n_bins, self.far_col_shift, compact=compact))
             self.subs = []
         elif sh is None:
             self.subs = [csr.tight(), csc.tight()]
@@ -201,7 +203,9 @@ class IceProblem:
                 if far.nnz and blocks:            # far field in (row block, column tile) order: csrc/far.cuh
                     nfar = far.nnz
                     del far
-                    self.far_copies.append(far_blocks(fkey, fval, nfar, n_bins, self.far_col_shift))
+                    fc = far_blocks(fkey, fval, nfar, n_bins, self.far_col_shift, compact=far_compact)
+                    far_compact = fc.rec_bytes == 4   # the other orientation holds the same counts
+                    self.far_copies.append(fc)
                 elif far.nnz:                     # far field as one row-ordered copy gathered through L2
                     subs.append(far.tight())
                 del fkey, fval
@@ -490,6 +494,8 @@ class IceState:
             for k in ("far_copies", "far_units", "far_tiles", "far_parts", "far_claim"):
                 setattr(st, k, t[k].data_ptr())
             st.far_col_shift, st.far_warps = far[0].col_shift, far[0].warps
+            st.far_rec_bytes = far[0].rec_bytes
+            assert all(f.rec_bytes == far[0].rec_bytes for f in far)
         self.st = st
         self.prob = prob
         self.flag_host = torch.zeros(1, dtype=_I32).pin_memory() if torch.cuda.is_available() else None
@@ -652,7 +658,7 @@ def prefilter_bias(prob: IceProblem, chrom_offset, *, mad_max, min_nnz, min_coun
 def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2, mad_max=5,
                   min_nnz=10, min_count=0, blacklist=None, rescale_marginals=True, x0=None,
                   tol=1e-5, max_iters=200, group=None, problem=None, chromnames=None,
-                  return_info=False, strip_bins=None, band=None, far_col_shift=None):
+                  return_info=False, strip_bins=None, band=None, far_col_shift=None, far_compact=None):
     """Balance a device-resident table.  Same semantics as ``balance_cooler``.
 
     ``problem`` lets callers reuse the filtered copies (bench: inputs resident
@@ -665,7 +671,7 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
     n_chroms = len(chrom_offset) - 1
     prob = problem or IceProblem(table, cis_only=cis_only, trans_only=trans_only,
                                  ignore_diags=ignore_diags, group=group, strip_bins=strip_bins, band=band,
-                                 far_col_shift=far_col_shift)
+                                 far_col_shift=far_col_shift, far_compact=far_compact)
     bias = prefilter_bias(prob, chrom_offset, mad_max=mad_max, min_nnz=min_nnz, min_count=min_count,
                           blacklist=blacklist, x0=x0)
 
@@ -737,7 +743,9 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
                 "hit_limit": hit_limit, "gpu_launches": state.launches,
                 "n_subcopies": len(prob.subs), "strip_shift": prob.strip_shift, "band": prob.band,
                 "far_units": state.n_far_units,
-                "far_pixels": sum(f.nnz for f in getattr(prob, "far_copies", []) if f is not None)}
+                "far_pixels": sum(getattr(f, "n_pixels", f.nnz) for f in getattr(prob, "far_copies", []) if f is not None),
+                "far_records": sum(f.nnz for f in getattr(prob, "far_copies", []) if f is not None),
+                "far_rec_bytes": [f.rec_bytes for f in getattr(prob, "far_copies", []) if f is not None]}
         return bias, stats, info
     return bias, stats
 

@@ -21,7 +21,22 @@
 // merge, separated by __syncwarp): no atomics, fixed summation order,
 // bit-reproducible.  Padding records (row id R = a dummy accumulator) fill the last chunk
 // of a slot.
+//
+// Two record formats (cb200_ice.far_rec_bytes): 8 bytes {swz row << 16 | column, count} and the
+// compact 4 bytes {swz row : 12 | column : 13 | count : 7} (counts above 127 are split into several
+// records of the same cell when the table is built).  The kernel is bound by the shared-memory
+// data pipe, not by HBM (ncu, 8-byte records, 1 kb rank-0 shard: 262 M shared wavefronts per
+// launch = 6.0 per random 64-bit gather instruction, ideal 2, + 1.5 per predicated accumulator
+// load / store; l1tex data pipe 78 % busy, 13 points of that the record stream itself), so halving
+// the stream takes load off the limiting pipe: 1.40 -> 1.33 ms on that shard, 1.33 -> 1.23 and
+// 1.42 -> 1.25 ms on the rank-3 and rank-7 shards (0.73 / 0.78 / 0.74 of the measured HBM rate in
+// terms of the algorithmic 16 B per pixel).  A variant without the per-tile CTA barrier (mbarrier
+// ring of three / two tiles, warps drifting up to a tile apart, thread 0 or a 17th warp as the
+// producer) was measured SLOWER on the same shard (1.59-1.96 ms): waiting warps spin on
+// mbarrier.try_wait through the same shared-memory pipe that bounds the kernel, whereas a warp
+// parked at __syncthreads costs nothing -- so the per-tile barrier stays.
 #pragma once
+#include <type_traits>
 #include "walk.cuh"
 #include "../../include/cooler_b200.h"
 
@@ -161,6 +176,84 @@ __device__ __forceinline__ void far_slot(const int4* __restrict__ px4, const int
   __syncwarp();
 }
 
+// ---- compact records {swz row : 12 | column : 13 | count : 7} (cb200_far_finish4): a chunk of 64
+// records is 256 bytes, one 64-bit load per lane.  Padding records repeat the row of the slot's last
+// record with count 0, so they extend a run instead of closing one.
+__device__ __forceinline__ void far_add4(unsigned& key, double& val, const unsigned x, const double g,
+                                         const unsigned acc_s) {
+  const unsigned k = x >> 20;
+  const unsigned c = x & 127u;
+  // exact small int -> double: {0x43300000, c} is 2^52 + c.  A record with count 0 adds exactly
+  // nothing, whatever the gathered value is.
+  const double v = c ? g * (__hiloint2double(0x43300000, (int)c) - 4503599627370496.0) : 0.0;
+  const bool changed = (k != key);
+  if (changed) {
+    const unsigned a = acc_s + (key << 3);
+    sts_f64(a, lds_f64(a) + val);
+  }
+  val = changed ? v : val + v;
+  key = k;
+}
+
+template <int U>
+__device__ __forceinline__ void far_first_group4(const int2* __restrict__ px2, const int64_t c0,
+                                                 const int64_t c1, int2 (&qn)[U], const int lane) {
+  const int2* __restrict__ src = px2 + c0 * 32 + lane;
+  const int nch = (int)(c1 - c0);
+#pragma unroll
+  for (int u = 0; u < U; ++u) qn[u] = (u < nch) ? ld_stream_int2(src + u * 32) : make_int2(0, 0);
+}
+
+template <int U>
+__device__ __forceinline__ void far_slot4(const int2* __restrict__ px2, const int64_t c0, const int64_t c1,
+                                          int2 (&qn)[U], const unsigned ws_s, const unsigned acc_s,
+                                          const int lane) {
+  constexpr unsigned F = 0xffffffffu;
+  const int nch = (int)(c1 - c0);
+  if (nch <= 0) return;                            // warp-uniform
+  const int2* __restrict__ src = px2 + c0 * 32 + lane;
+  unsigned key = FAR_NOKEY;
+  double val = 0.0;
+  for (int c = 0; c < nch; c += U) {
+    int2 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = qn[u];
+    const int cn = c + U;
+    if (cn < nch) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) qn[u] = (cn + u < nch) ? ld_stream_int2(src + (cn + u) * 32) : make_int2(0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (c + u >= nch) break;                     // warp-uniform
+      // byte offset of w[column] in the tile: ((x >> 7) & 0x1FFF) << 3
+      const double g0 = lds_f64(ws_s + (((unsigned)q[u].x >> 4) & 0xFFF8u));
+      const double g1 = lds_f64(ws_s + (((unsigned)q[u].y >> 4) & 0xFFF8u));
+      far_add4(key, val, (unsigned)q[u].x, g0, acc_s);
+      far_add4(key, val, (unsigned)q[u].y, g1, acc_s);
+    }
+  }
+  // merge the open last runs of the lanes (see far_slot); every lane holds a real row here
+  __syncwarp();
+  const unsigned pk = __shfl_up_sync(F, key, 1);
+  const unsigned nk = __shfl_down_sync(F, key, 1);
+  const bool head = (lane == 0) || (pk != key);
+  const unsigned heads = __ballot_sync(F, head);
+  const int h = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+  const int span = lane - h;
+  const int ms = __reduce_max_sync(F, span);
+  double x = val;
+  for (int d = 1; d <= ms; d <<= 1) {
+    const double y = __shfl_up_sync(F, x, d);
+    if (lane - d >= h) x += y;
+  }
+  if (lane == 31 || nk != key) {
+    const unsigned a = acc_s + (key << 3);
+    sts_f64(a, lds_f64(a) + x);
+  }
+  __syncwarp();
+}
+
 constexpr int FAR_BUFS = 2;                       // shared-memory buffers of C doubles: the tile in use + the next one
 
 // One persistent CTA per SM.  The slice of w of the NEXT column tile is staged with ONE bulk copy
@@ -168,7 +261,7 @@ constexpr int FAR_BUFS = 2;                       // shared-memory buffers of C 
 // Measured on the 1 kb rank-0 shard (3.87e8 px): per-thread 8-byte cp.async 1.56 ms, one bulk copy
 // per tile 1.40 ms, two tiles in flight (three buffers) 1.63 ms -- the second copy competes with
 // the record stream for the SM's L2 port -- so the distance stays at one tile.
-template <int WARPS, int U>
+template <int WARPS, int U, bool kCompact>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 ice_sweep_far_kernel(const cb200_ice st) {
   extern __shared__ double far_sm[];               // acc[FAR_ACC] | w tile [FAR_BUFS][C]
@@ -219,13 +312,15 @@ ice_sweep_far_kernel(const cb200_ice st) {
     for (int i = lane; i < RW; i += 32) acc[wid * RW + i] = 0.0;
     // slot (j, wid) of this row block: chunks tp[j * WARPS] .. tp[j * WARPS + 1]
     const int64_t* __restrict__ tp = fc.ptr + ((int64_t)(un.rb - fc.rb0) * fc.n_j - fc.j0) * WARPS + wid;
-    const int4* __restrict__ px4 = reinterpret_cast<const int4*>(fc.px);
+    typedef typename std::conditional<kCompact, int2, int4>::type Q;    // one lane's share of a 64-record chunk
+    const Q* __restrict__ pxq = reinterpret_cast<const Q*>(fc.px);
     const int j_first = st.far_tiles[un.t0];
     int jn = (un.t0 + 1 < un.t1) ? st.far_tiles[un.t0 + 1] : -1;
     stage(j_first, 0);
     int64_t a = tp[(int64_t)j_first * WARPS], b = tp[(int64_t)j_first * WARPS + 1];
-    int4 qn[U];
-    far_first_group<U>(px4, a, b, qn, lane);
+    Q qn[U];
+    if constexpr (kCompact) far_first_group4<U>(pxq, a, b, qn, lane);
+    else far_first_group<U>(pxq, a, b, qn, lane);
     staged(0);
     __syncthreads();                               // tile 0 staged; accumulators zeroed
     int buf = 0;
@@ -237,9 +332,11 @@ ice_sweep_far_kernel(const cb200_ice st) {
         a2 = tp[(int64_t)jn * WARPS];
         b2 = tp[(int64_t)jn * WARPS + 1];
       }
-      far_slot<U>(px4, a, b, qn, wb_s + (unsigned)buf * (unsigned)C * 8u, acc_s, lane);
+      if constexpr (kCompact) far_slot4<U>(pxq, a, b, qn, wb_s + (unsigned)buf * (unsigned)C * 8u, acc_s, lane);
+      else far_slot<U>(pxq, a, b, qn, wb_s + (unsigned)buf * (unsigned)C * 8u, acc_s, lane);
       if (jn >= 0) {
-        far_first_group<U>(px4, a2, b2, qn, lane);
+        if constexpr (kCompact) far_first_group4<U>(pxq, a2, b2, qn, lane);
+        else far_first_group<U>(pxq, a2, b2, qn, lane);
         staged(buf ^ 1);                           // (a barrier is only waited on when a copy was issued to it)
       }
       __syncthreads();                             // next tile staged, this one released

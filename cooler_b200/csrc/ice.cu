@@ -368,8 +368,9 @@ int cb200_far_row_shift(void) { return CB200_FAR_ROW_SHIFT; }
 // K3 over the far-field blocks (far.cuh): one persistent CTA per SM claims units.
 static int ice_sweep_far(const cb200_ice* st, void* stream) {
   if (st->n_far_units <= 0) return 0;
-  if (st->far_col_shift < 1 || st->far_col_shift > 13 || st->far_warps != 16) {
-    set_error_msg("ice_sweep: far_col_shift must be in 1..13 and far_warps 16");
+  if (st->far_col_shift < 1 || st->far_col_shift > 13 || st->far_warps != 16 ||
+      (st->far_rec_bytes != 8 && !(st->far_rec_bytes == 4 && CB200_FAR_ROW_SHIFT <= 12))) {
+    set_error_msg("ice_sweep: far_col_shift must be in 1..13, far_warps 16, far_rec_bytes 8 (or 4 with <= 4096-row blocks)");
     return -1;
   }
   const size_t smem = ((size_t)FAR_ACC + FAR_BUFS * ((size_t)1 << st->far_col_shift)) * sizeof(double);
@@ -380,7 +381,8 @@ static int ice_sweep_far(const cb200_ice* st, void* stream) {
   }
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CB_CHECK(cudaFuncSetAttribute(ice_sweep_far_kernel<16, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
   }
   int dev = 0, sms = 148;
@@ -388,7 +390,11 @@ static int ice_sweep_far(const cb200_ice* st, void* stream) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = st->n_far_units < sms ? st->n_far_units : sms;
   // 16 warps x 8 128-bit loads in flight per lane (measured 1.70 vs 2.15 ms with 4 on the 1 kb rank-0 shard)
-  ice_sweep_far_kernel<16, 8><<<grid, 512, smem, (cudaStream_t)stream>>>(*st);
+  // compact records, 8 x 64-bit loads in flight per lane: 1.33 ms on the 1 kb rank-0 shard (4: 1.57, 16: 1.35)
+  if (st->far_rec_bytes == 4)
+    ice_sweep_far_kernel<16, 8, true><<<grid, 512, smem, (cudaStream_t)stream>>>(*st);
+  else
+    ice_sweep_far_kernel<16, 8, false><<<grid, 512, smem, (cudaStream_t)stream>>>(*st);
   CB_LAUNCH_CHECK("ice_sweep_far");
   return 0;
 }

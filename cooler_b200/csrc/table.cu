@@ -138,6 +138,102 @@ __global__ void far_interleave_kernel(const int2* __restrict__ rec, const int32_
   }
 }
 
+// ---- compact (4-byte) far-field records: {swz(row & (R - 1)) : 12 | other & (C - 1) : 13 | count : 7}
+// (R <= 4096, C <= 8192).  98 % of the counts of a 1 kb matrix are <= 3; a count above 127 becomes
+// ceil(count / 127) consecutive records of the same cell (same row, same column: they extend the
+// lane's run and add up to the same product), a count of 0 is a record that adds nothing.
+// pieces[i] = records that element i needs; flags[0] |= 1 if any count > 127, flags[1] |= 1 if any
+// count < 0 (such a stream keeps the 8-byte records).
+__global__ void far_pieces_kernel(const int2* __restrict__ vals, int64_t n, int32_t* __restrict__ pieces,
+                                  int32_t* __restrict__ flags) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int big = 0, neg = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int c = vals[i].y;
+    neg |= (c < 0);
+    const int p = (c <= 127) ? 1 : (int)(((int64_t)c + 126) / 127);
+    big |= (p > 1);
+    pieces[i] = p;
+  }
+  big = __syncthreads_or(big);
+  neg = __syncthreads_or(neg);
+  if (threadIdx.x == 0) {
+    if (big) atomicOr(flags, 1);
+    if (neg) atomicOr(flags + 1, 1);
+  }
+}
+
+// element i -> records [off[i], off[i+1]) of the expanded stream (order preserved)
+__global__ void far_expand_kernel(const int32_t* __restrict__ rows, const int2* __restrict__ vals, int64_t n,
+                                  const int64_t* __restrict__ off, int32_t* __restrict__ rows_out,
+                                  int2* __restrict__ vals_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int r = rows[i];
+    const int2 v = vals[i];
+    int left = v.y;
+    for (int64_t o = off[i]; o < off[i + 1]; ++o) {
+      const int c = left > 127 ? 127 : left;
+      left -= c;
+      rows_out[o] = r;
+      vals_out[o] = make_int2(v.x, c);
+    }
+  }
+}
+
+__global__ void far_finish4_kernel(const int32_t* __restrict__ rows, const int2* __restrict__ vals,
+                                   int64_t n, int col_shift, int rb0, int j0, int n_j, int warps,
+                                   uint32_t* __restrict__ rec_out, int32_t* __restrict__ slot_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int cmask = (1 << col_shift) - 1;
+  constexpr int RS = CB200_FAR_ROW_SHIFT;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int r = rows[i];
+    const int2 v = vals[i];
+    const int lrow = r & ((1 << RS) - 1);
+    rec_out[i] = ((uint32_t)far_swizzle(lrow, warps) << 20) | ((uint32_t)(v.x & cmask) << 7) | (uint32_t)(v.y & 127);
+    slot_out[i] = (((r >> RS) - rb0) * n_j + ((v.x >> col_shift) - j0)) * warps + ((lrow * warps) >> RS);
+  }
+}
+
+// Same lane-interleaved layout as far_interleave_kernel with 4-byte records (a chunk is 256 bytes,
+// one 64-bit load per lane).
+__global__ void far_interleave4_kernel(const uint32_t* __restrict__ rec, const int32_t* __restrict__ slot,
+                                       const int64_t* __restrict__ ptr_rec, const int64_t* __restrict__ cptr,
+                                       int64_t n, uint32_t* __restrict__ px_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int s = slot[i];
+    const int j = (int)(i - ptr_rec[s]);
+    const int64_t c0 = cptr[s];
+    const int L = 2 * (int)(cptr[s + 1] - c0);
+    const int lane = j / L, idx = j - lane * L;
+    px_out[(c0 + (idx >> 1)) * CHUNK + 2 * lane + (idx & 1)] = rec[i];
+  }
+}
+
+// Padding of the last chunk(s) of every slot: count 0 on the row of the slot's LAST record, so a
+// padding record neither closes a run nor opens a new one (there is no spare row id in 12 bits).
+__global__ void far_pad4_kernel(const uint32_t* __restrict__ rec, const int64_t* __restrict__ ptr_rec,
+                                const int64_t* __restrict__ cptr, int64_t n_slots, uint32_t* __restrict__ px_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t s = warp; s < n_slots; s += n_warps) {
+    const int64_t r0 = ptr_rec[s], r1 = ptr_rec[s + 1];
+    const int64_t c0 = cptr[s];
+    const int nch = (int)(cptr[s + 1] - c0);
+    const int n_s = (int)(r1 - r0);
+    if (nch == 0 || n_s == nch * CHUNK) continue;
+    const uint32_t pad = rec[r1 - 1] & 0xFFF00000u;
+    const int L = 2 * nch;
+    for (int j = n_s + lane; j < nch * CHUNK; j += 32) {
+      const int ln = j / L, idx = j - ln * L;
+      px_out[(c0 + (idx >> 1)) * CHUNK + 2 * ln + (idx & 1)] = pad;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- filter ----
 struct KeepRule {
   const int32_t* row_lo;
@@ -378,6 +474,59 @@ int cb200_far_interleave(const cb200_px* rec, const int32_t* slot, const int64_t
   far_interleave_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const int2*>(rec), slot, ptr_rec, chunk_ptr, n, reinterpret_cast<int2*>(px_out));
   CB_LAUNCH_CHECK("far_interleave");
+  return 0;
+}
+
+int cb200_far_pieces(const cb200_px* vals, int64_t n, int32_t* pieces_out, int32_t* flags, void* stream) {
+  CB_CHECK(cudaMemsetAsync(flags, 0, 2 * sizeof(int32_t), (cudaStream_t)stream));
+  if (n <= 0) return 0;
+  int64_t blocks = ceil_div64(n, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  far_pieces_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const int2*>(vals), n,
+                                                                       pieces_out, flags);
+  CB_LAUNCH_CHECK("far_pieces");
+  return 0;
+}
+
+int cb200_far_expand(const int32_t* rows, const cb200_px* vals, int64_t n, const int64_t* offsets,
+                     int32_t* rows_out, cb200_px* vals_out, void* stream) {
+  if (n <= 0) return 0;
+  int64_t blocks = ceil_div64(n, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  far_expand_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      rows, reinterpret_cast<const int2*>(vals), n, offsets, rows_out, reinterpret_cast<int2*>(vals_out));
+  CB_LAUNCH_CHECK("far_expand");
+  return 0;
+}
+
+int cb200_far_finish4(const int32_t* rows, const cb200_px* vals, int64_t n, int32_t col_shift,
+                      int32_t rb0, int32_t j0, int32_t n_j, int32_t warps, uint32_t* rec_out,
+                      int32_t* slot_out, void* stream) {
+  if (col_shift < 1 || col_shift > 13 || CB200_FAR_ROW_SHIFT > 12 || warps != 16 || n_j <= 0) {
+    set_error_msg("far_finish4: compact records need col_shift <= 13 and 4096-row blocks at most");
+    return -1;
+  }
+  int64_t blocks = ceil_div64(n > 0 ? n : 1, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  far_finish4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      rows, reinterpret_cast<const int2*>(vals), n, col_shift, rb0, j0, n_j, warps, rec_out, slot_out);
+  CB_LAUNCH_CHECK("far_finish4");
+  return 0;
+}
+
+int cb200_far_interleave4(const uint32_t* rec, const int32_t* slot, const int64_t* ptr_rec,
+                          const int64_t* chunk_ptr, int64_t n, int64_t n_slots, int64_t total_chunks,
+                          uint32_t* px_out, void* stream) {
+  (void)total_chunks;
+  if (n <= 0) return 0;
+  int64_t blocks = ceil_div64(n, 256 * 4);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  far_interleave4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rec, slot, ptr_rec, chunk_ptr, n, px_out);
+  CB_LAUNCH_CHECK("far_interleave4");
+  blocks = ceil_div64(n_slots, 8);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  far_pad4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rec, ptr_rec, chunk_ptr, n_slots, px_out);
+  CB_LAUNCH_CHECK("far_pad4");
   return 0;
 }
 

@@ -243,12 +243,20 @@ class FarCopy:
         return self.px.numel() * 4 + self.ptr.numel() * 8
 
 
-def far_blocks(key_other, val_rowcount, n, n_bins, col_shift, warps=16):
+FAR_COMPACT_MAX_GROWTH = 1.25   # compact records are used while splitting counts > 127 adds < 25 % records
+
+
+def far_blocks(key_other, val_rowcount, n, n_bins, col_shift, warps=16, compact=None):
     """Row-ordered stream (key = gathered bin, val = {row, count}) -> FarCopy.
 
     Two stable radix sorts bring the records into (row >> RS, other >> col_shift, row,
     other) order: first on the column-tile bits of the gathered bin, then -- after swapping
-    key and other -- on the row-block bits of the row."""
+    key and other -- on the row-block bits of the row.
+
+    ``compact``: True = 4-byte records {row:12 | column:13 | count:7} (counts above 127 become
+    several records of the same cell), False = 8-byte records, None = compact when the geometry
+    allows it (<= 4096-row blocks, <= 8192-column tiles), no count is negative and splitting adds
+    less than 25 % records.  The choice made is ``FarCopy.rec_bytes``."""
     dev = key_other.device
     n = int(n)
     if n == 0:
@@ -261,16 +269,41 @@ def far_blocks(key_other, val_rowcount, n, n_bins, col_shift, warps=16):
     del ks, vs
     if n_rb_all > 1:
         kr, vr = sort_pairs(kr, vr, key_bits_for(n_rb_all), key_shift=FAR_ROW_SHIFT)
+    n_px = n
+    can_compact = FAR_ROW_SHIFT <= 12 and col_shift <= 13
+    if compact and not can_compact:
+        raise ValueError("compact far-field records need <= 4096-row blocks and <= 8192-column tiles")
+    if compact is None:
+        compact = can_compact
+    if compact:
+        pieces = torch.empty(n, dtype=_I32, device=dev)
+        flags = torch.empty(2, dtype=_I32, device=dev)
+        _lib.call("cb200_far_pieces", _ptr(vr), n, _ptr(pieces), _ptr(flags), _stream())
+        big, neg = (int(x) for x in flags.cpu().numpy())
+        if neg:
+            compact = False                       # negative counts do not fit the 7-bit field
+        elif big:
+            off = exclusive_scan_i32(pieces)
+            n2 = int(off[-1].item())
+            if n2 > FAR_COMPACT_MAX_GROWTH * n:
+                compact = False
+            else:
+                kr2 = torch.empty(n2, dtype=_I32, device=dev)
+                vr2 = _new_px(n2, dev)
+                _lib.call("cb200_far_expand", _ptr(kr), _ptr(vr), n, _ptr(off), _ptr(kr2), _ptr(vr2), _stream())
+                kr, vr, n = kr2, vr2, n2
+            del off
+        del pieces, flags
     ends = kr[torch.tensor([0, n - 1], device=dev)].cpu().numpy()
     rb0, rb1 = int(ends[0]) >> FAR_ROW_SHIFT, int(ends[1]) >> FAR_ROW_SHIFT
     n_rb, j0, n_j = rb1 - rb0 + 1, 0, n_j_all
     n_slots = n_rb * n_j * warps
     if n_slots >= 2**31 - 1:
         raise ValueError("far-field slot table does not fit int32")
-    rec = _new_px(n, dev)
+    rec = torch.empty(n, dtype=_I32, device=dev) if compact else _new_px(n, dev)
     slot = torch.empty(n, dtype=_I32, device=dev)
-    _lib.call("cb200_far_finish", _ptr(kr), _ptr(vr), n, int(col_shift), rb0, j0, n_j, int(warps),
-              _ptr(rec), _ptr(slot), _stream())
+    _lib.call("cb200_far_finish4" if compact else "cb200_far_finish", _ptr(kr), _ptr(vr), n, int(col_shift),
+              rb0, j0, n_j, int(warps), _ptr(rec), _ptr(slot), _stream())
     del kr, vr
     ptr_rec = indptr_from_sorted(slot, n, n_slots)            # first record of every slot
     # lane-interleaved chunks: every slot is padded to whole 64-record chunks
@@ -279,14 +312,21 @@ def far_blocks(key_other, val_rowcount, n, n_bins, col_shift, warps=16):
     cptr = exclusive_scan_i32(nch)                            # first chunk of every slot
     del nch
     total_chunks = int(cptr[-1].item())
-    px = torch.empty((total_chunks * 64 + 2, 2), dtype=_I32, device=dev)
-    _lib.call("cb200_far_interleave", _ptr(rec), _ptr(slot), _ptr(ptr_rec), _ptr(cptr), n, total_chunks,
-              _ptr(px), _stream())
+    if compact:
+        px = torch.empty(total_chunks * 64 + 4, dtype=_I32, device=dev)
+        _lib.call("cb200_far_interleave4", _ptr(rec), _ptr(slot), _ptr(ptr_rec), _ptr(cptr), n, n_slots,
+                  total_chunks, _ptr(px), _stream())
+    else:
+        px = torch.empty((total_chunks * 64 + 2, 2), dtype=_I32, device=dev)
+        _lib.call("cb200_far_interleave", _ptr(rec), _ptr(slot), _ptr(ptr_rec), _ptr(cptr), n, total_chunks,
+                  _ptr(px), _stream())
     del rec, slot
     tile_start = ptr_rec[::warps].cpu().numpy()               # [n_rb * n_j + 1]
     counts = np.diff(tile_start).reshape(n_rb, n_j)
     fc = FarCopy(px, cptr, n, rb0, n_rb, j0, n_j, col_shift, warps, counts)
     fc.n_chunks = total_chunks
+    fc.rec_bytes = 4 if compact else 8
+    fc.n_pixels = n_px                                        # before counts > 127 were split
     return fc
 
 

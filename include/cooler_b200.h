@@ -119,6 +119,24 @@ int cb200_far_interleave(const cb200_px* rec, const int32_t* slot, const int64_t
                          const int64_t* chunk_ptr, int64_t n, int64_t total_chunks, cb200_px* px_out,
                          void* stream);
 
+/* Compact (4-byte) far-field records {swz(row & (R - 1)) : 12 | other & (C - 1) : 13 | count : 7}
+ * (R <= 4096, col_shift <= 13): half the bytes per record of the blocked sweep.
+ * cb200_far_pieces: pieces_out[i] = ceil(count_i / 127) (>= 1) = records element i needs;
+ * flags[0] = 1 if any count > 127, flags[1] = 1 if any count < 0 (then the 8-byte records are kept).
+ * cb200_far_expand: element i -> records [offsets[i], offsets[i+1]) (offsets = exclusive scan of the
+ * pieces) with counts <= 127 that add up to count_i; order is preserved.
+ * cb200_far_finish4 / cb200_far_interleave4: as cb200_far_finish / cb200_far_interleave for 4-byte
+ * records; chunks are 64 records = 256 bytes, padding = count 0 on the row of the slot's last record. */
+int cb200_far_pieces(const cb200_px* vals, int64_t n, int32_t* pieces_out, int32_t* flags, void* stream);
+int cb200_far_expand(const int32_t* rows, const cb200_px* vals, int64_t n, const int64_t* offsets,
+                     int32_t* rows_out, cb200_px* vals_out, void* stream);
+int cb200_far_finish4(const int32_t* rows, const cb200_px* vals, int64_t n, int32_t col_shift,
+                      int32_t rb0, int32_t j0, int32_t n_j, int32_t warps, uint32_t* rec_out,
+                      int32_t* slot_out, void* stream);
+int cb200_far_interleave4(const uint32_t* rec, const int32_t* slot, const int64_t* ptr_rec,
+                          const int64_t* chunk_ptr, int64_t n, int64_t n_slots, int64_t total_chunks,
+                          uint32_t* px_out, void* stream);
+
 /* Static pixel filter.  A pixel (row r, other c) is KEPT iff
  *   !(ndiag > 0 && |r - c| < ndiag)                       (_zero_diags)
  *   && (keep == CB200_KEEP_ALL
@@ -201,7 +219,7 @@ enum { CB200_FAR_ROW_SHIFT = CB200_FAR_ROW_SHIFT_VALUE };
 /* The value this library was built with (hosts size far_parts and sort keys from it). */
 int cb200_far_row_shift(void);
 typedef struct {
-  const cb200_px* px;        /* [n_chunks * 64] (+2 pad) lane-interleaved records, see above */
+  const void*     px;        /* [n_chunks * 64] (+2 pad) lane-interleaved records, see above: cb200_px, or uint32_t when cb200_ice.far_rec_bytes == 4 */
   const int64_t*  ptr;       /* [n_rb * n_j * far_warps + 1] first CHUNK of every slot (row block, column tile, warp row slice) */
   int64_t  nnz;              /* records without padding */
   int32_t  rb0, n_rb;        /* row blocks [rb0, rb0 + n_rb) */
@@ -256,6 +274,7 @@ typedef struct {
   int32_t  n_far_units;
   int32_t  far_col_shift;             /* log2 C, 1..13; (rows + 2 C) * 8 B must fit the 227 KB of shared memory */
   int32_t  far_warps;                 /* 16: warps per CTA = row slices per block */
+  int32_t  far_rec_bytes;             /* 8: cb200_px records; 4: compact records (cb200_far_finish4), every far copy alike */
 } cb200_ice;
 
 /* Tuning of K3 (optional): ice_unroll in {0,1,2,4,8} = 128-bit stream loads kept in

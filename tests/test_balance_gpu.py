@@ -286,10 +286,13 @@ def test_far_blocks_large_synthetic_matches_unstripped(strip_bins, col_shift):
     np.testing.assert_array_equal(b, c)
 
 
+@pytest.mark.parametrize("compact", [False, True])
 @pytest.mark.parametrize("key,col_shift", [("gm/defaults", 4), ("gm/cis_only", 7), ("gm/trans_only", 5),
                                            ("rnd3/gw", 2), ("gm/diag0", 12), ("gm/mad0_nnz0", 6), ("rnd1/cis", 13)])
-def test_all_blocks_layout_matches_reference_golden(key, col_shift):
-    """Every pixel (dense diagonal runs included) through the 2-D blocked kernel."""
+def test_all_blocks_layout_matches_reference_golden(key, col_shift, compact):
+    """Every pixel (dense diagonal runs included) through the 2-D blocked kernel, with 8-byte and with
+    compact 4-byte records (the GM12878 2 Mb counts reach thousands: every such pixel is split into
+    pieces of <= 127, far beyond the 25 % growth at which the automatic choice keeps 8-byte records)."""
     import cooler_b200
     from cooler_b200 import PixelTable
     src, case = key.split("/")
@@ -299,9 +302,16 @@ def test_all_blocks_layout_matches_reference_golden(key, col_shift):
     tab = PixelTable.from_arrays(bin1_offset, t["bin2_id"], t["count"], chrom_offset)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        bias, stats, info = cooler_b200.balance_table(tab, return_info=True, band="allblocks",
-                                                      far_col_shift=col_shift, **kw)
+        import cooler_b200.table as tbl
+        growth, tbl.FAR_COMPACT_MAX_GROWTH = tbl.FAR_COMPACT_MAX_GROWTH, 1e9
+        try:
+            bias, stats, info = cooler_b200.balance_table(tab, return_info=True, band="allblocks",
+                                                          far_col_shift=col_shift, far_compact=compact, **kw)
+        finally:
+            tbl.FAR_COMPACT_MAX_GROWTH = growth
     assert info["band"] == "allblocks" and info["n_subcopies"] == 0 and info["far_units"] > 0
+    assert info["far_rec_bytes"] == [4 if compact else 8] * 2
+    assert info["far_records"] >= info["far_pixels"] and (compact or info["far_records"] == info["far_pixels"])
     want = BAL[key]
     np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
     assert sum(info["passes"]) == sum(META[key]["passes"])
@@ -316,9 +326,11 @@ def test_all_blocks_large_synthetic_matches_unstripped():
     bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
     tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset)
     a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0)
-    for col_shift in (13, 10):       # the default 8192-column tiles (three 64 KB buffers) and narrow ones
-        b, sb, ib = cooler_b200.balance_table(tab, return_info=True, band="allblocks", far_col_shift=col_shift)
+    for col_shift, compact in ((13, None), (13, False), (10, True)):   # the default 8192-column tiles and narrow ones
+        b, sb, ib = cooler_b200.balance_table(tab, return_info=True, band="allblocks", far_col_shift=col_shift,
+                                              far_compact=compact)
         assert ib["far_pixels"] == 2 * ia["nnz_eff"] and ia["passes"] == ib["passes"]
+        assert ib["far_rec_bytes"] == [8 if compact is False else 4] * 2
         np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
         np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
 
@@ -458,3 +470,43 @@ def test_auto_layout_uses_blocks_for_huge_sparse_tables():
     c, sc = cooler_b200.balance_arrays(bin1_offset, b2, cnt, chrom_offset)
     np.testing.assert_array_equal(b, c)
     assert abs(sc["scale"] / sb["scale"] - 1) < 1e-12
+
+
+def test_far_record_format_choice():
+    """Compact 4-byte far-field records are the automatic choice when the counts allow it: counts
+    above 127 are split (and must add up to the same sweep), a negative count or too many heavy
+    counts keep the 8-byte records."""
+    import cooler_b200
+    from cooler_b200 import PixelTable
+    b1, b2, cnt, chrom_offset = _synthetic(41, [9000, 6000, 3001], 0.01)
+    n = int(chrom_offset[-1])
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    cnt = cnt.copy()
+    heavy = np.flatnonzero(np.abs(b1 - b2) >= 2)[:: 97]
+    cnt[heavy] = 127 + (np.arange(len(heavy)) % 900) * 7            # 127 .. 6420: one to 51 pieces
+    ref = None
+    for name, c, want_bytes in (("split", cnt, 4), ("forced8", cnt, 8), ("negative", None, 8), ("heavy", None, 8)):
+        cc = c
+        kw = {}
+        if name == "forced8":
+            kw["far_compact"] = False
+        if name == "negative":
+            cc = cnt.copy()
+            cc[heavy[0]] = -3
+        if name == "heavy":
+            cc = cnt * 200
+        tab = PixelTable.from_arrays(bin1_offset, b2, cc, chrom_offset)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            a, sa, ia = cooler_b200.balance_table(tab, return_info=True, strip_bins=0, max_iters=30)
+            b, sb, ib = cooler_b200.balance_table(tab, return_info=True, band="allblocks", far_col_shift=9,
+                                                  max_iters=30, **kw)
+        assert ib["far_rec_bytes"] == [want_bytes] * 2, (name, ib["far_rec_bytes"])
+        assert ib["far_pixels"] == 2 * ia["nnz_eff"]
+        assert (ib["far_records"] > ib["far_pixels"]) == (name == "split")
+        assert ia["passes"] == ib["passes"]
+        np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+        np.testing.assert_allclose(a, b, rtol=1e-11, equal_nan=True)
+        if name in ("split", "forced8"):
+            ref = a if ref is None else ref
+            np.testing.assert_array_equal(a, ref)

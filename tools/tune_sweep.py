@@ -43,13 +43,15 @@ for var in variants:
         t0 = time.time()
         band = {2: True, 3: "blocks", 4: "allblocks"}.get(use_smem, False) if strip_bins else None
         prob = IceProblem(tab, strip_bins=strip_bins, use_smem=bool(use_smem), band=band,
-                          far_col_shift=far_cs)
+                          far_col_shift=far_cs,
+                          far_compact={"0": False, "1": True}.get(os.environ.get("TUNE_COMPACT", ""), None))
         bias0 = prefilter_bias(prob, tab.chrom_offset, mad_max=5, min_nnz=10, min_count=0, blacklist=None, x0=None)
         state = IceState(prob, bias0, None, np.array([0, tab.n_bins]), 1e-5, 200)
         torch.cuda.synchronize()
         print(f"  build {time.time() - t0:.2f} s  far_px={sum(f.nnz for f in prob.far_copies)} "
               f"far_units={state.n_far_units} near_px={sum(c.nnz for c in prob.subs)} "
-              f"padded={sum(f.px.shape[0] for f in prob.far_copies)}", flush=True)
+              f"padded={sum(f.n_chunks * 64 for f in prob.far_copies)} rec_bytes={[f.rec_bytes for f in prob.far_copies]} "
+              f"records={sum(f.nnz for f in prob.far_copies)}", flush=True)
         last_strip = (strip_bins, use_smem, far_cs, far_w)
     assert lib.cb200_set_tuning(unroll % 10, -1 if unroll < 10 else (unroll // 10) - 1) == 0   # 1x: selective off, 2x: on
     state.reset(bias0)
