@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .table import (PixelTable, TableCopy, _new_px, _ptr, _stream, _use_device,  # noqa: F401
+from .table import (PixelTable, TableCopy, _new_px, _ptr, _stream, _use_device, to_host,  # noqa: F401
                     far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays,
                     segment_medians, shard_rows_by_pixels,
                     strip_partition, swap_key_other, transpose_from)
@@ -112,6 +112,35 @@ class _PeerVectors:
             return None
 
 
+def merge_row_pieces(pieces, strip):
+    """Concatenate row-ordered sub-copies that cover ascending, disjoint row ranges (the pieces of
+    one column strip coming from successive row chunks) into ONE sub-copy: pixel arrays back to back
+    (device-to-device copies), row pointers shifted by the pixels before them, rows between two
+    pieces empty."""
+    if len(pieces) == 1:
+        pieces[0].strip = strip
+        return pieces[0]
+    dev = pieces[0].px.device
+    total = sum(p.nnz for p in pieces)
+    base = pieces[0].row_base
+    n_rows = pieces[-1].row_base + pieces[-1].n_rows - base
+    px = _new_px(total, dev)
+    indptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+    o, a_prev_end = 0, 0
+    for p in pieces:
+        a = p.row_base - base
+        assert a >= a_prev_end - 1 and p.indptr.numel() == p.n_rows + 1
+        if a > a_prev_end:
+            indptr[a_prev_end:a].fill_(o)               # empty rows between two pieces
+        px[o:o + p.nnz].copy_(p.px[: p.nnz])
+        torch.add(p.indptr, o, out=indptr[a:a + p.n_rows + 1])
+        o += p.nnz
+        a_prev_end = a + p.n_rows + 1
+    sub = TableCopy(px, indptr, total, n_rows, row_base=base)
+    sub.strip = strip
+    return sub
+
+
 class IceProblem:
     """Filtered CSR/CSC copies of one table for one (mode, ignore_diags) choice.
 
@@ -145,7 +174,7 @@ class IceProblem:
         marg = torch.stack([nnz_r + nnz_c, sum_r + sum_c])
         del nnz_r, sum_r, nnz_c, sum_c
         _allreduce(marg, group)
-        marg = marg.cpu().numpy()
+        marg = to_host(marg)
         self.marg_nnz = marg[0].astype(np.float64)
         self.marg_sum = marg[1].astype(np.float64)
         cval = None
@@ -220,12 +249,20 @@ class IceProblem:
                   row_range=None):
         """Build the problem straight from host arrays, **pipelined with the host->device copy**.
 
+        Whole-copy layout (bias vector served by L1/L2): row chunks of equal pixel counts.  Column-strip
+        layout (10 kb class): one chunk per strip-aligned range of 16 384 ROWS; the bin2-major copy of
+        such a chunk gathers only the chunk's own rows, i.e. it IS one strip of the bin2-major side, and
+        its bin1-major pixels are cut into strip pieces that are concatenated per strip once the last
+        chunk is in (`merge_row_pieces`).  The resulting sub-copies -- and therefore every bit of the
+        sweep -- are identical to those of the two-step build (PixelTable + IceProblem), but only the
+        last chunk's build and the concatenation (a few ms) are left when the last byte has crossed PCIe.
+
         The table is cut into row chunks; chunk c+1 crosses PCIe (copy stream) while chunk c is
         packed, filtered, radix-sorted into its own bin2-major copy and marginalised on the main
         stream.  Every chunk contributes a bin1-major and a bin2-major sub-copy (the column sums
         of the chunks add up exactly like column strips or multi-GPU shards), so nothing has to
-        wait for the whole table.  Returns None when the layout needs column strips or far-field
-        blocks (large n_bins): the caller then uses the two-step path (PixelTable + IceProblem).
+        wait for the whole table.  Returns None when the layout needs far-field blocks (1 kb class):
+        the caller then uses the two-step path (PixelTable + IceProblem).
         """
         dev = _use_device(device)
         off_t = bin1_offset if isinstance(bin1_offset, torch.Tensor) else torch.from_numpy(
@@ -244,15 +281,22 @@ class IceProblem:
         if n_bins >= 2**31 - 1:
             raise ValueError("n_bins must fit int32")
         lay = choose_layout(n_bins, nnz, None)
-        if lay[0] is not None or lay[1] or nnz == 0:
+        if lay[1] or nnz == 0:
             return None
+        strip_shift = lay[0]
         chrom_offset = np.asarray(chrom_offset, dtype=np.int64)
         info = _TableInfo(n_bins, chrom_offset, dev, row_range or (0, n_bins))
-        # row-aligned chunks of about nnz / n_chunks pixels
-        targets = (np.arange(1, n_chunks) * (nnz / n_chunks)).astype(np.int64)
-        rows = np.unique(np.r_[0, np.searchsorted(off_np, targets, side="left"), n_bins])
-        rows = rows[np.r_[True, np.diff(off_np[rows]) > 0]] if len(rows) > 2 else rows
-        rows[-1] = n_bins
+        if strip_shift is None:
+            # row-aligned chunks of about nnz / n_chunks pixels
+            targets = (np.arange(1, n_chunks) * (nnz / n_chunks)).astype(np.int64)
+            rows = np.unique(np.r_[0, np.searchsorted(off_np, targets, side="left"), n_bins])
+            rows = rows[np.r_[True, np.diff(off_np[rows]) > 0]] if len(rows) > 2 else rows
+            rows[-1] = n_bins
+        else:
+            # column strips: one chunk per strip of ROWS, so that the bin2-major copy of a chunk is
+            # exactly one strip of the bin2-major side (its gathered bins = the chunk's rows)
+            S = 1 << strip_shift
+            rows = np.unique(np.r_[np.arange(0, n_bins, S), n_bins]).astype(np.int64)
         main = torch.cuda.current_stream()
         copy_stream = _copy_stream(dev)
         indptr_d = off_t.to(dev, non_blocking=True)
@@ -275,12 +319,15 @@ class IceProblem:
         self.table, self.group, self.use_smem = info, group, True
         self.mode = "cis" if cis_only else ("trans" if trans_only else "gw")
         self.peer_reduce = True if peer_reduce is None else bool(peer_reduce)
-        self.strip_shift, self.band, self.csr, self.csc = None, False, None, None
+        self.strip_shift, self.band, self.csr, self.csc = strip_shift, False, None, None
         self.far_copies, self.far_col_shift, self.far_warps = [], 13, 16
         ndiag = int(ignore_diags) if ignore_diags else 0
         keep = _lib.KEEP_CIS if cis_only else _lib.KEEP_ALL
         marg = torch.zeros((2, n_bins), dtype=torch.int64, device=dev)
         subs, nnz_eff = [], 0
+        n_strips = ((max(n_bins, 1) - 1) >> strip_shift) + 1 if strip_shift is not None else 0
+        row_pieces = [[] for _ in range(n_strips)]     # bin1-major side: pieces of strip s, one per row chunk
+        col_strips = []                                # bin2-major side: chunk k IS strip k
         pack = "cb200_pack_pixels_i32" if b2_t.dtype == _I32 else "cb200_pack_pixels"
         for ev, r0, r1 in zip(events, rows[:-1], rows[1:]):
             r0, r1 = int(r0), int(r1)
@@ -294,22 +341,38 @@ class IceProblem:
             csr, tkey, tval = filter_copy(raw, info.row_lo, info.row_hi, ndiag, keep, want_transpose=True)
             del raw, px
             csc = transpose_from(tkey, tval, n_bins)
-            del tkey, tval
+            if strip_shift is None or trans_only:
+                del tkey, tval
             a_nnz, a_sum = marginals_i64(csr)
             marg[0, r0:r1] += a_nnz
             marg[1, r0:r1] += a_sum
             b_nnz, b_sum = marginals_i64(csc)
             marg[0] += b_nnz
             marg[1] += b_sum
-            if trans_only:
+            if trans_only and strip_shift is None:
                 csr, _, _ = filter_copy(csr, info.row_lo, info.row_hi, 0, _lib.KEEP_TRANS)
                 csc, _, _ = filter_copy(csc, info.row_lo, info.row_hi, 0, _lib.KEEP_TRANS)
+            elif trans_only:
+                csr, tkey, tval = filter_copy(csr, info.row_lo, info.row_hi, 0, _lib.KEEP_TRANS, want_transpose=True)
+                csc = transpose_from(tkey, tval, n_bins) if csr.nnz else csc
             nnz_eff += csr.nnz
-            if csr.nnz:
+            if not csr.nnz:
+                continue
+            if strip_shift is None:
                 subs += [csr.tight(), csc.tight()]
+                continue
+            # bin1-major side: this chunk's rows, cut into column strips (pieces of the final strips)
+            for piece in strip_partition(tkey[: csr.nnz], tval, csr.nnz, n_bins, strip_shift):
+                row_pieces[piece.strip].append(piece)
+            del tkey, tval, csr
+            csc = csc.tight()
+            csc.strip = r0 >> strip_shift
+            col_strips.append(csc)
         del bin2_d, count_d
+        if strip_shift is not None:
+            subs = [merge_row_pieces(p, s_) for s_, p in enumerate(row_pieces) if p] + col_strips
         _allreduce(marg, group)
-        marg = marg.cpu().numpy()
+        marg = to_host(marg)
         self.marg_nnz = marg[0].astype(np.float64)
         self.marg_sum = marg[1].astype(np.float64)
         self.subs = subs
@@ -600,7 +663,7 @@ class IceState:
         t = self.t
         out = {k: t[k][: self.S].cpu().numpy() for k in
                ("seg_scale", "seg_var", "seg_iters", "seg_done", "seg_empty")}
-        out["bias"] = t["bias"][: self.n].cpu().numpy()
+        out["bias"] = to_host(t["bias"][: self.n])
         out["var_hist"] = t["var_hist"][: self.max_iters * self.S].cpu().numpy().reshape(self.max_iters, self.S)
         return out
 

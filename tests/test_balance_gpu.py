@@ -482,7 +482,7 @@ def test_far_record_format_choice():
     n = int(chrom_offset[-1])
     bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
     cnt = cnt.copy()
-    heavy = np.flatnonzero(np.abs(b1 - b2) >= 2)[:: 97]
+    heavy = np.flatnonzero(np.abs(b1 - b2) >= 2)[:: 301]       # +8 % records after splitting
     cnt[heavy] = 127 + (np.arange(len(heavy)) % 900) * 7            # 127 .. 6420: one to 51 pieces
     ref = None
     for name, c, want_bytes in (("split", cnt, 4), ("forced8", cnt, 8), ("negative", None, 8), ("heavy", None, 8)):
@@ -510,3 +510,35 @@ def test_far_record_format_choice():
         if name in ("split", "forced8"):
             ref = a if ref is None else ref
             np.testing.assert_array_equal(a, ref)
+
+
+@pytest.mark.parametrize("mode", ["gw", "cis", "trans"])
+@pytest.mark.parametrize("shard", [None, (5000, 17000)])
+def test_streamed_strip_build_is_bit_identical_to_table_path(mode, shard, monkeypatch):
+    """Column-strip layout through balance_arrays: one H2D chunk per strip-aligned row range, the
+    bin2-major copy of a chunk is one strip, the bin1-major pieces are concatenated per strip.  The
+    sub-copies equal those of the two-step build, so the bias is identical to the last bit."""
+    import cooler_b200
+    from cooler_b200 import PixelTable, balance
+    import torch
+    monkeypatch.setattr(balance, "L1_RESIDENT_BINS", 1000)
+    monkeypatch.setattr(balance, "DEFAULT_STRIP_BINS", 2048)
+    monkeypatch.setattr(balance, "MIN_PIXELS_PER_ROW_STRIP", 0)
+    b1, b2, cnt, chrom_offset = _synthetic(52, [9000, 7000, 3, 5000], 0.02)
+    n = int(chrom_offset[-1])
+    if shard is not None:
+        keep = (b1 >= shard[0]) & (b1 < shard[1])
+        b1, b2, cnt = b1[keep], b2[keep], cnt[keep]
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    kw = dict(cis_only=(mode == "cis"), trans_only=(mode == "trans"), row_range=shard)
+    tab = PixelTable.from_arrays(bin1_offset, b2, cnt, chrom_offset, row_range=shard)
+    kw2 = {k: v for k, v in kw.items() if k != "row_range"}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a, sa, ia = cooler_b200.balance_table(tab, return_info=True, max_iters=60, **kw2)
+        pinned = [torch.from_numpy(x).pin_memory() for x in (bin1_offset, b2.astype(np.int32), cnt)]
+        b, sb, ib = cooler_b200.balance_arrays(pinned[0], pinned[1], pinned[2], chrom_offset, return_info=True,
+                                               max_iters=60, **kw)
+    assert ia["strip_shift"] == 11 and ib["strip_shift"] == 11
+    assert ib["n_subcopies"] == ia["n_subcopies"] and ia["passes"] == ib["passes"] and ib["nnz_eff"] == ia["nnz_eff"]
+    np.testing.assert_array_equal(a, b)
