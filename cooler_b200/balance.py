@@ -388,6 +388,12 @@ class IceProblem:
         """Algorithmic bytes of one marginal pass: 16 B/effective pixel + 40 B/bin."""
         return 16 * self.nnz_eff + 40 * self.table.n_bins
 
+    def stream_bytes(self):
+        """Bytes of pixel records one pass actually streams from HBM: 8 B per record of the row-ordered
+        sub-copies, 8 or 4 B (compact) per record of the 2-D blocked copies, padding included."""
+        far = [f for f in self.far_copies if f is not None]
+        return 8 * sum(c.nnz for c in self.subs) + sum(f.n_chunks * 64 * f.rec_bytes for f in far)
+
 
 L1_RESIDENT_BINS = 49_152      # bias vectors up to 384 KB are served well enough by L1 + L2
 DEFAULT_STRIP_BINS = 16_384    # 128 KB of float64 bias per strip: stays in the SM's L1

@@ -186,11 +186,21 @@ __global__ void ice_reduce_slice_kernel(const int32_t* __restrict__ all_done,
                                         const double* const* __restrict__ peer_s, int world, int64_t peer_off,
                                         double* __restrict__ red, int lo, int hi) {
   if (*all_done) return;
-  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= hi) return;
-  double v = 0.0;
-  for (int r = 0; r < world; ++r) v += __ldcv(peer_s[r] + peer_off + i);
-  red[i] = v;
+  // two bins per thread: 2 x world independent peer loads in flight
+  const int i0 = lo + blockIdx.x * (2 * blockDim.x) + threadIdx.x, i1 = i0 + blockDim.x;
+  double v0 = 0.0, v1 = 0.0;
+  if (i1 < hi) {
+    for (int r = 0; r < world; ++r) {
+      const double* __restrict__ p = peer_s[r] + peer_off;
+      v0 += __ldcv(p + i0);
+      v1 += __ldcv(p + i1);
+    }
+    red[i0] = v0;
+    red[i1] = v1;
+  } else if (i0 < hi) {
+    for (int r = 0; r < world; ++r) v0 += __ldcv(peer_s[r] + peer_off + i0);
+    red[i0] = v0;
+  }
 }
 
 constexpr int UPD_THREADS = 256;
@@ -243,30 +253,49 @@ ice_marg_kernel(cb200_ice st, const double* const* __restrict__ peer_s, int worl
   if (!st.seg_done[seg]) {
     const int lo = st.blk_lo[b], hi = st.blk_hi[b];
     double sum = 0.0, cnt = 0.0;
-#pragma unroll 4                                   // independent (peer) loads of several bins in flight per thread
-    for (int i = lo + threadIdx.x; i < hi; i += UPD_THREADS) {
-      double si;
-      if (kMode == 2) {
-        si = 0.0;
-        for (int r = 0; r < world; ++r) si += __ldcv(peer_s[r] + peer_off + i);
-      } else if (kMode == 3) {
-        const int slice = (st.n_bins + world - 1) / world;
-        si = __ldcv(peer_s[i / slice] + peer_off + i);
-      } else if (kMode == 1) {
-        si = 0.0;
-        for (int k = 0; k < st.n_subs; ++k) {
-          const unsigned r = (unsigned)(i - st.subs[k].row_base);
-          if (r < (unsigned)st.subs[k].row_count)
-            si += row_total<double>((int)r, st.subs[k].indptr, st.subs[k].nnz, st.subs[k].direct,
-                                    st.subs[k].pieces);
+    // kMode 3: a block's bins nearly always have ONE owner -> its pointer is fetched once per block
+    const int slice = (kMode == 3) ? (st.n_bins + world - 1) / world : 1;
+    const bool one_owner = (kMode == 3) && (lo / slice == (hi - 1) / slice);
+    const double* __restrict__ owner = one_owner ? peer_s[lo / slice] + peer_off : nullptr;
+    // The loads of a batch of bins are issued before anything is stored: the compiler cannot hoist a
+    // load over the store to st.marg of the previous bin (the pointers may alias), and a peer load
+    // over NVLink takes microseconds -- one bin at a time made this kernel latency-bound.
+    constexpr int B = 8;
+    for (int i0 = lo + threadIdx.x; i0 < hi; i0 += UPD_THREADS * B) {
+      double sv[B], wv[B];
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const int i = i0 + u * UPD_THREADS;
+        sv[u] = 0.0;
+        wv[u] = 0.0;
+        if (i < hi) {
+          if (kMode == 2) {
+            for (int r = 0; r < world; ++r) sv[u] += __ldcv(peer_s[r] + peer_off + i);
+          } else if (kMode == 3) {
+            sv[u] = one_owner ? __ldcv(owner + i) : __ldcv(peer_s[i / slice] + peer_off + i);
+          } else if (kMode == 1) {
+            for (int k = 0; k < st.n_subs; ++k) {
+              const unsigned r = (unsigned)(i - st.subs[k].row_base);
+              if (r < (unsigned)st.subs[k].row_count)
+                sv[u] += row_total<double>((int)r, st.subs[k].indptr, st.subs[k].nnz, st.subs[k].direct,
+                                           st.subs[k].pieces);
+            }
+            if (st.n_far_units > 0) sv[u] += far_row_total(st, i);
+          } else {
+            sv[u] = st.s[i];
+          }
+          wv[u] = st.w[i];
         }
-        if (st.n_far_units > 0) si += far_row_total(st, i);
-      } else {
-        si = st.s[i];
       }
-      const double m = st.w[i] * si;
-      st.marg[i] = m;
-      if (m != 0.0) { sum += m; cnt += 1.0; }
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const int i = i0 + u * UPD_THREADS;
+        if (i < hi) {
+          const double m = wv[u] * sv[u];
+          st.marg[i] = m;
+          if (m != 0.0) { sum += m; cnt += 1.0; }
+        }
+      }
     }
     const double bs = block_sum(sum, sm);
     const double bc = block_sum(cnt, sm);
@@ -303,15 +332,35 @@ ice_update_kernel(cb200_ice st, int iter) {
     const double mean = st.seg_mean[seg];
     const int lo = st.blk_lo[b], hi = st.blk_hi[b];
     double dev = 0.0;
-    for (int i = lo + threadIdx.x; i < hi; i += UPD_THREADS) {
-      const double m = st.marg[i];
-      if (m != 0.0) { const double d = m - mean; dev += d * d; }
-      double q = m / mean;
-      if (q == 0.0) q = 1.0;
-      const double nb = st.bias[i] / q;
-      st.bias[i] = nb;
-      if (st.cweights) st.w[i] = nb * st.cweights[i];
-      else if (st.w != st.bias) st.w[i] = nb;
+    constexpr int B = 8;                           // loads of a batch of bins before its stores (see ice_marg_kernel)
+    for (int i0 = lo + threadIdx.x; i0 < hi; i0 += UPD_THREADS * B) {
+      double mv[B], bv[B], cw[B];
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const int i = i0 + u * UPD_THREADS;
+        mv[u] = 0.0;
+        bv[u] = 0.0;
+        cw[u] = 1.0;
+        if (i < hi) {
+          mv[u] = st.marg[i];
+          bv[u] = st.bias[i];
+          if (st.cweights) cw[u] = st.cweights[i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < B; ++u) {
+        const int i = i0 + u * UPD_THREADS;
+        if (i < hi) {
+          const double m = mv[u];
+          if (m != 0.0) { const double d = m - mean; dev += d * d; }
+          double q = m / mean;
+          if (q == 0.0) q = 1.0;
+          const double nb = bv[u] / q;
+          st.bias[i] = nb;
+          if (st.cweights) st.w[i] = nb * cw[u];
+          else if (st.w != st.bias) st.w[i] = nb;
+        }
+      }
     }
     const double bd = block_sum(dev, sm);
     if (threadIdx.x == 0) st.blk_dev[b] = bd;
@@ -490,7 +539,7 @@ int cb200_ice_reduce_peer(const cb200_ice* st, const double* const* peer_s, int3
   const int lo = rank * slice < st->n_bins ? rank * slice : st->n_bins;
   const int hi = lo + slice < st->n_bins ? lo + slice : st->n_bins;
   if (hi <= lo) return 0;
-  ice_reduce_slice_kernel<<<(unsigned)ceil_div64(hi - lo, 256), 256, 0, (cudaStream_t)stream>>>(
+  ice_reduce_slice_kernel<<<(unsigned)ceil_div64(hi - lo, 512), 256, 0, (cudaStream_t)stream>>>(
       st->all_done, peer_s, world, peer_offset, red_local, lo, hi);
   CB_LAUNCH_CHECK("ice_reduce_slice");
   return 0;

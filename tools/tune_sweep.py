@@ -92,6 +92,18 @@ for var in variants:
     e1.record()
     torch.cuda.synchronize()
     ms_c = e0.elapsed_time(e1) / n
+    upd = []
+    for fused in (0, 1):                           # the two per-bin kernels (K4): s given / s from the sweep outputs
+        e0.record()
+        for k in range(n):
+            _lib.call("cb200_ice_update", st, k, fused, _stream())
+        e1.record()
+        torch.cuda.synchronize()
+        upd.append(e0.elapsed_time(e1) / n)
+    state.reset(bias0)
+    _lib.call("cb200_ice_sweep", st, _stream())
+    _lib.call("cb200_ice_combine", st, _stream())
+    print(f"    per-bin kernels (marg + update, {state.st.n_blocks} blocks): s given {upd[0]*1e3:.1f} us, fused combine {upd[1]*1e3:.1f} us", flush=True)
     s = state.t["s"].cpu().numpy().copy()
     if ref is None:
         ref = s
