@@ -186,21 +186,13 @@ __global__ void ice_reduce_slice_kernel(const int32_t* __restrict__ all_done,
                                         const double* const* __restrict__ peer_s, int world, int64_t peer_off,
                                         double* __restrict__ red, int lo, int hi) {
   if (*all_done) return;
-  // two bins per thread: 2 x world independent peer loads in flight
-  const int i0 = lo + blockIdx.x * (2 * blockDim.x) + threadIdx.x, i1 = i0 + blockDim.x;
-  double v0 = 0.0, v1 = 0.0;
-  if (i1 < hi) {
-    for (int r = 0; r < world; ++r) {
-      const double* __restrict__ p = peer_s[r] + peer_off;
-      v0 += __ldcv(p + i0);
-      v1 += __ldcv(p + i1);
-    }
-    red[i0] = v0;
-    red[i1] = v1;
-  } else if (i0 < hi) {
-    for (int r = 0; r < world; ++r) v0 += __ldcv(peer_s[r] + peer_off + i0);
-    red[i0] = v0;
-  }
+  // one bin per thread, `world` independent peer loads in flight (two bins per thread in half as many
+  // threads measured slower at 8 GPUs: 0.075 vs 0.045 ms for the 3.1e6-bin vector)
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  double v = 0.0;
+  for (int r = 0; r < world; ++r) v += __ldcv(peer_s[r] + peer_off + i);
+  red[i] = v;
 }
 
 constexpr int UPD_THREADS = 256;
@@ -539,7 +531,7 @@ int cb200_ice_reduce_peer(const cb200_ice* st, const double* const* peer_s, int3
   const int lo = rank * slice < st->n_bins ? rank * slice : st->n_bins;
   const int hi = lo + slice < st->n_bins ? lo + slice : st->n_bins;
   if (hi <= lo) return 0;
-  ice_reduce_slice_kernel<<<(unsigned)ceil_div64(hi - lo, 512), 256, 0, (cudaStream_t)stream>>>(
+  ice_reduce_slice_kernel<<<(unsigned)ceil_div64(hi - lo, 256), 256, 0, (cudaStream_t)stream>>>(
       st->all_done, peer_s, world, peer_offset, red_local, lo, hi);
   CB_LAUNCH_CHECK("ice_reduce_slice");
   return 0;
