@@ -29,8 +29,8 @@ __all__ = ["balance_cooler", "balance_table", "balance_arrays", "ConvergenceWarn
 logger = logging.getLogger("cooler")   # same logger name as the reference (_logging.py)
 
 _F64, _I32 = torch.float64, torch.int32
-UPD_BINS = 1024                         # smallest number of bins per block of the per-bin kernels (csrc/ice.cu)
-UPD_BLOCKS_TARGET = 592                 # about 4 blocks per SM: every block takes a ticket on ONE counter per launch
+UPD_BINS = 256                          # smallest number of bins per block of the per-bin kernels (csrc/ice.cu: 256 threads)
+UPD_BLOCKS_TARGET = 1184                # about 8 blocks per SM: every block takes a ticket on ONE counter per launch
 
 
 class ConvergenceWarning(UserWarning):

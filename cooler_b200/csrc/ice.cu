@@ -265,18 +265,43 @@ ice_marg_kernel(cb200_ice st, const double* const* __restrict__ peer_s, int worl
             for (int r = 0; r < world; ++r) sv[u] += __ldcv(peer_s[r] + peer_off + i);
           } else if (kMode == 3) {
             sv[u] = one_owner ? __ldcv(owner + i) : __ldcv(peer_s[i / slice] + peer_off + i);
-          } else if (kMode == 1) {
-            for (int k = 0; k < st.n_subs; ++k) {
-              const unsigned r = (unsigned)(i - st.subs[k].row_base);
-              if (r < (unsigned)st.subs[k].row_count)
-                sv[u] += row_total<double>((int)r, st.subs[k].indptr, st.subs[k].nnz, st.subs[k].direct,
-                                           st.subs[k].pieces);
-            }
-            if (st.n_far_units > 0) sv[u] += far_row_total(st, i);
-          } else {
+          } else if (kMode == 0) {
             sv[u] = st.s[i];
           }
           wv[u] = st.w[i];
+        }
+      }
+      if (kMode == 1) {
+        // row totals over the sub-copies, in sub-copy order per bin.  A row total is two dependent
+        // loads (row pointers, then the sum); per sub-copy the row pointers of the whole batch are
+        // fetched first, then the sums -- bin after bin, sub-copy after sub-copy (38 strips at 10 kb)
+        // was a chain of ~150 dependent load latencies per thread (0.13 ms per pass).
+        for (int k = 0; k < st.n_subs; ++k) {
+          const cb200_sub sb = st.subs[k];
+          int64_t ra[B], rb[B];
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            const int i = i0 + u * UPD_THREADS;
+            const unsigned r = (unsigned)(i - sb.row_base);
+            ra[u] = rb[u] = 0;
+            if (i < hi && r < (unsigned)sb.row_count) {
+              ra[u] = sb.indptr[r];
+              rb[u] = sb.indptr[r + 1];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            const int i = i0 + u * UPD_THREADS;
+            if (ra[u] < rb[u])
+              sv[u] += row_total_ab<double>(i - sb.row_base, ra[u], rb[u], sb.nnz, sb.direct, sb.pieces);
+          }
+        }
+        if (st.n_far_units > 0) {
+#pragma unroll
+          for (int u = 0; u < B; ++u) {
+            const int i = i0 + u * UPD_THREADS;
+            if (i < hi) sv[u] += far_row_total(st, i);
+          }
         }
       }
 #pragma unroll

@@ -170,12 +170,11 @@ __device__ __forceinline__ void walk_reduce_tile(const int2* __restrict__ px,
   walk_reduce_span<Op, U>(px, indptr, tile_row, n_rows, nnz, t, t + 1, op, direct, pieces);
 }
 
-// Total of row r from the outputs of walk_reduce_tile.
+// Total of row r = pixels [a, b) from the outputs of walk_reduce_tile.
 template <typename T>
-__device__ __forceinline__ T row_total(int r, const int64_t* __restrict__ indptr, int64_t nnz,
-                                       const T* __restrict__ direct,
-                                       const T* __restrict__ pieces) {
-  const int64_t a = indptr[r], b = indptr[r + 1];
+__device__ __forceinline__ T row_total_ab(int r, int64_t a, int64_t b, int64_t nnz,
+                                          const T* __restrict__ direct,
+                                          const T* __restrict__ pieces) {
   if (a >= b) return acc_zero((T*)nullptr);
   const int64_t ta = a / WARP_TILE, tb = (b - 1) / WARP_TILE;
   if (ta == tb) {
@@ -186,6 +185,13 @@ __device__ __forceinline__ T row_total(int r, const int64_t* __restrict__ indptr
   T v = (a == ta * WARP_TILE) ? pieces[2 * ta] : pieces[2 * ta + 1];
   for (int64_t t = ta + 1; t <= tb; ++t) v = acc_add(v, pieces[2 * t]);
   return v;
+}
+
+template <typename T>
+__device__ __forceinline__ T row_total(int r, const int64_t* __restrict__ indptr, int64_t nnz,
+                                       const T* __restrict__ direct,
+                                       const T* __restrict__ pieces) {
+  return row_total_ab<T>(r, indptr[r], indptr[r + 1], nnz, direct, pieces);
 }
 
 // F: __device__ void operator()(int64_t pos, bool ok0, bool ok1, int r0, int r1, int4 q)
