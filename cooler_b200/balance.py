@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .table import (PixelTable, TableCopy, _new_px, _ptr, _stream, _use_device, to_host,  # noqa: F401
+from .table import (PixelTable, TableCopy, _as_tensor, _new_px, _ptr, _stream, _use_device, counts_as_int32, to_host,  # noqa: F401
                     far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays,
                     segment_medians, shard_rows_by_pixels,
                     strip_partition, swap_key_other, transpose_from)
@@ -270,11 +270,7 @@ class IceProblem:
         off_np = off_t.numpy()
         n_bins = len(off_np) - 1
         b2_t = bin2_id if isinstance(bin2_id, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bin2_id))
-        c_t = count if isinstance(count, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(count))
-        if c_t.dtype.is_floating_point:
-            raise NotImplementedError("cooler_b200 balances integer count columns only")
-        if c_t.dtype != _I32:
-            c_t = c_t.to(_I32)
+        c_t = counts_as_int32(_as_tensor(count))
         if b2_t.dtype not in (_I32, torch.int64):
             b2_t = b2_t.to(torch.int64)
         nnz = int(b2_t.numel())

@@ -432,7 +432,7 @@ __global__ void bin_pairs_kernel(const int32_t* __restrict__ chrom1, const int64
     if (c1 >= 0 && c2 >= 0) {
       int64_t a1 = pos1[i] - one_based, a2 = pos2[i] - one_based;
       if (a1 < 0 || a2 < 0) f_neg = 1;
-      else if (a1 > chromsizes[c1] || a2 > chromsizes[c2]) f_exc = 1;
+      else if (a1 > chromsizes[c1] || a2 > chromsizes[c2]) f_exc |= 1;
       else {
         bool keep = true;
         if (tril_action != CB200_TRIL_NONE && (c1 > c2 || (c1 == c2 && a1 > a2))) {
@@ -446,6 +446,10 @@ __global__ void bin_pairs_kernel(const int32_t* __restrict__ chrom1, const int64
           other = chrom_binoffset[c1] + (int)(a1 / binsize);   // bin1
           key = chrom_binoffset[c2] + (int)(a2 / binsize);     // bin2: first sort key
           cnt = 1;
+          // a position equal to the length of the LAST chromosome passes the reference's anchor check
+          // (`> chromsize`) but lands on bin n_bins: its bounds check then fails
+          // (create/_ingest.py:401-410).  Never let it collide with the dropped-record sentinel.
+          if (other >= n_bins || key >= n_bins) { f_exc = 2; other = key = n_bins; cnt = 0; }
         }
       }
     }
@@ -454,7 +458,7 @@ __global__ void bin_pairs_kernel(const int32_t* __restrict__ chrom1, const int64
     val_out[i] = make_int2(other, cnt);
   }
   if (f_neg) atomicOr(&flags[0], 1);
-  if (f_exc) atomicOr(&flags[1], 1);
+  if (f_exc) atomicOr(&flags[1], f_exc);
   if (f_tril) atomicOr(&flags[2], 1);
   dropped = warp_sum(dropped);
   if ((threadIdx.x & 31) == 0 && dropped) atomicAdd(&flags[3], dropped);

@@ -78,8 +78,11 @@ def bin_pairs(chrom1_ids, pos1, chrom2_ids, pos2, chromsizes, binsize, *, is_one
     if validate and f[0]:
         raise BadInputError("Found an anchor position with negative value. Make sure your coordinates are "
                             "1-based or use the --zero-based option when loading.")
-    if validate and f[1]:
+    if validate and f[1] & 1:
         raise BadInputError("Found an anchor position exceeding chromosome length")
+    if f[1] & 2:                                          # create/_ingest.py:407-410 (boundscheck)
+        raise BadInputError("Found a bin ID that exceeds the declared number of bins. "
+                            "Check whether your bin table is correct.")
     if f[2]:
         raise BadInputError("Found lower triangle pairs")
     bits = key_bits_for(n_bins + 1)
@@ -88,9 +91,10 @@ def bin_pairs(chrom1_ids, pos1, chrom2_ids, pos2, chromsizes, binsize, *, is_one
     kr, vr = swap_key_other(ks, vs, n)                    # key = bin1, val = {bin2, 1}
     del ks, vs
     kr, vr = sort_pairs(kr, vr, bits)                     # by bin1 (stable): (bin1, bin2) order
-    k2, v2, n_out, overflow = _reduce_runs(kr, vr, n, 0, dev)
-    if int(f[3]) > 0:                                     # dropped / failed records form the last run
-        n_out -= 1
+    n_valid = n - int(f[3])                               # dropped records sort behind every bin: cut them off
+    if n_valid <= 0:                                      # (one thread per run would walk them serially)
+        return empty
+    k2, v2, n_out, overflow = _reduce_runs(kr, vr, n_valid, 0, dev)
     if n_out <= 0:
         return empty
     b1 = torch.empty(n_out, dtype=torch.int64, device=dev)

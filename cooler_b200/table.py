@@ -51,6 +51,38 @@ def to_host(t):
     return h.numpy()
 
 
+def _as_tensor(a):
+    """Host array -> tensor; numpy dtypes torch lacks (uint32 / uint64) are widened to int64 first."""
+    if isinstance(a, torch.Tensor):
+        return a
+    a = np.ascontiguousarray(a)
+    if a.dtype in (np.uint32, np.uint64):
+        if a.size and int(a.max()) > 2**63 - 1:
+            raise OverflowError("count column holds values outside int64")
+        a = a.astype(np.int64)
+    elif a.dtype == np.uint16:
+        a = a.astype(np.int32)
+    return torch.from_numpy(a)
+
+
+def counts_as_int32(count_t):
+    """The count column as an int32 tensor.  Columns of a wider or unsigned integer type are range
+    checked first: a value outside int32 would wrap silently and corrupt the marginals (the
+    reference computes in whatever dtype the column has, _balance.py:25-26)."""
+    if count_t.dtype == _I32:
+        return count_t
+    if count_t.dtype.is_floating_point:
+        raise NotImplementedError(
+            "cooler_b200 balances integer count columns only (float value columns are not "
+            "supported by the CUDA path yet)")
+    if count_t.numel():
+        lo, hi = int(count_t.min()), int(count_t.max())
+        if lo < -2**31 or hi > 2**31 - 1:
+            raise OverflowError(f"count column ({count_t.dtype}) holds values outside int32 "
+                                f"[{lo}, {hi}]: not supported by the CUDA path")
+    return count_t.to(_I32)
+
+
 def warp_tile():
     return _lib.load().cb200_warp_tile()
 
@@ -477,11 +509,7 @@ class PixelTable:
                 t = t.to(dtype)
             return t.to(device, non_blocking=True)
 
-        count_t = count if isinstance(count, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(count))
-        if count_t.dtype.is_floating_point:
-            raise NotImplementedError(
-                "cooler_b200 balances integer count columns only (float value columns are not "
-                "supported by the CUDA path yet)")
+        count_t = counts_as_int32(_as_tensor(count))
         indptr = dev(bin1_offset, _I64)
         bin2_t = bin2_id if isinstance(bin2_id, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bin2_id))
         narrow = bin2_t.dtype == _I32                 # reader already narrowed the ids: 8 B/pixel over PCIe

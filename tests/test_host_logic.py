@@ -212,3 +212,21 @@ def test_read_cooler_arrays_row_slices_tile_the_pixel_table():
     assert total == len(b2)
     np.testing.assert_array_equal(np.concatenate(parts2), np.asarray(b2))
     np.testing.assert_array_equal(np.concatenate(partsc), np.asarray(cnt))
+
+
+def test_count_columns_are_range_checked_before_narrowing():
+    """int64 / uint32 count columns are narrowed to int32 only when every value fits (a silent wrap
+    would corrupt the marginals); floating-point columns are refused."""
+    import pytest
+    import torch
+    from cooler_b200.table import _as_tensor, counts_as_int32
+    ok = counts_as_int32(_as_tensor(np.array([0, 5, 2**31 - 1], dtype=np.int64)))
+    assert ok.dtype == torch.int32 and ok.tolist() == [0, 5, 2**31 - 1]
+    assert counts_as_int32(_as_tensor(np.array([7, 9], dtype=np.uint32))).tolist() == [7, 9]
+    assert counts_as_int32(_as_tensor(np.array([7, 9], dtype=np.uint16))).tolist() == [7, 9]
+    for bad in (np.array([1, 2**31], dtype=np.int64), np.array([3, 2**32 - 1], dtype=np.uint32),
+                np.array([-2**31 - 1], dtype=np.int64)):
+        with pytest.raises(OverflowError):
+            counts_as_int32(_as_tensor(bad))
+    with pytest.raises(NotImplementedError):
+        counts_as_int32(_as_tensor(np.array([1.5])))

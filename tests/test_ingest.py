@@ -70,6 +70,18 @@ def test_gpu_bin_pairs_errors_and_edges():
         ingest.bin_pairs([0], [5], [0], [5], sizes, 10, tril_action="bogus")
     out = ingest.bin_pairs([], [], [], [], sizes, 10)
     assert all(len(v) == 0 for v in out.values())
+    # a 0-based position equal to the length of the LAST chromosome (a multiple of the bin size) passes
+    # the anchor check (`> chromsize`, as in the reference) but is bin n_bins: bounds error, never a
+    # silent drop (it used to collide with the dropped-record sentinel)
+    with pytest.raises(ingest.BadInputError, match="exceeds the declared number of bins"):
+        ingest.bin_pairs([0, 0], [5, 7], [0, 1], [9, 50], sizes, 10, is_one_based=False)
+    # many dropped records (unplaced contigs) next to a few valid ones: cut off, not walked as one run
+    nd = 300_000
+    out = ingest.bin_pairs(np.r_[np.full(nd, -1), 0, 0], np.r_[np.ones(nd, int), 5, 7],
+                           np.r_[np.zeros(nd, int), 0, 1], np.r_[np.ones(nd, int), 95, 3], sizes, 10)
+    np.testing.assert_array_equal(out["bin1_id"], [0, 0])
+    np.testing.assert_array_equal(out["bin2_id"], [9, 10])
+    np.testing.assert_array_equal(out["count"], [1, 1])
     out = ingest.bin_pairs([-1, 0], [5, 7], [0, -1], [5, 9], sizes, 10)        # everything dropped
     assert all(len(v) == 0 for v in out.values())
     out = ingest.bin_pairs([0, 0, 1], [5, 7, 3], [0, 0, 0], [95, 99, 15], sizes, 10, is_one_based=False)
