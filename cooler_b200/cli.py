@@ -133,11 +133,15 @@ def _on_rank0(group, rank, fn):
     return val
 
 
+_KEEP_DIST = 0     # > 0 while an outer command (zoomify --balance) still needs the process group
+
+
 def _finish_dist(group):
     if group is not None:
         import torch.distributed as dist
         dist.barrier(group)
-        dist.destroy_process_group()
+        if _KEEP_DIST == 0:
+            dist.destroy_process_group()
 
 
 @cli.command()
@@ -270,7 +274,11 @@ def balance(cool_uri, nproc, chunksize, mad_max, min_nnz, min_count, blacklist, 
 @click.option("--append", "-a", is_flag=True, default=False,
               help="Append the output cooler to an existing file instead of overwriting the file.")
 def coarsen(cool_uri, factor, nproc, chunksize, field, out, append):
-    """Coarsen a cooler to a lower resolution (k-by-k pooling per chromosomal block)."""
+    """Coarsen a cooler to a lower resolution (k-by-k pooling per chromosomal block).
+
+    Multi-GPU: ``torchrun --nproc-per-node N -m cooler_b200.cli coarsen FILE -k 2 -o OUT``: every
+    rank coarsens its own bin1 row range, rank 0 writes (the reference's ``--nproc`` pool,
+    cli/coarsen.py)."""
     columns, dtypes, agg = _fields(field)
     clr = store.open_cooler(cool_uri)
     if store.is_memory_uri(cool_uri):
@@ -278,8 +286,10 @@ def coarsen(cool_uri, factor, nproc, chunksize, field, out, append):
                                 dtypes=dtypes, agg=agg)
         store.register(out, result)
     else:
+        group, _ = _dist_group()
         coarsen_cooler(clr, out, factor, chunksize=chunksize, nproc=nproc, columns=columns,
-                       dtypes=dtypes, agg=agg, mode="a" if append else "w")
+                       dtypes=dtypes, agg=agg, mode="a" if append else "w", group=group)
+        _finish_dist(group)
 
 
 @cli.command()
@@ -553,11 +563,22 @@ def zoomify(cool_uri, nproc, chunksize, resolutions, do_balance, balance_args, f
         levels = zoomify_cooler(bases, None, resolutions, chunksize, nproc=nproc, columns=columns,
                                 dtypes=dtypes, agg=agg)
         store.register(outfile, {int(r): c for r, c in levels.items()})
-    else:
+        if do_balance:
+            invoke_balance(balance_args, resolutions, outfile)
+        return
+    # files: under torchrun every rank keeps its row shard of every level, rank 0 writes; the per-level
+    # `cooler balance` calls below then run on the same process group
+    global _KEEP_DIST
+    group, _ = _dist_group()
+    _KEEP_DIST += 1
+    try:
         zoomify_cooler([cool_uri, *list(base_uri)], outfile, resolutions, chunksize, nproc=nproc,
-                       columns=columns, dtypes=dtypes, agg=agg)
-    if do_balance:
-        invoke_balance(balance_args, resolutions, outfile)
+                       columns=columns, dtypes=dtypes, agg=agg, group=group)
+        if do_balance:
+            invoke_balance(balance_args, resolutions, outfile)
+    finally:
+        _KEEP_DIST -= 1
+    _finish_dist(group)
 
 
 if __name__ == "__main__":

@@ -4,10 +4,13 @@
 
 The reference re-bins every pixel chunk by joining it with the bin table and
 running a pandas ``groupby([bin1_id, bin2_id], sort=True).sum()``
-(_reduce.py:582-620).  Here one level is: fused bin-remap kernel -> stable
-radix sort by bin2' -> reduce-by-key -> stable radix sort by bin1'
-(csrc/coarsen.cu), all on the device-resident table; the result is again a
-``PixelTable`` so a zoomify chain (and per-level balancing) never leaves HBM.
+(_reduce.py:582-620).  Here one level is: the fine rows of a coarse row are
+merged pairwise (merge path, the bin remap fused into the first round), then
+one reduce-by-key (csrc/coarsen.cu), all on the device-resident table; the
+result is again a ``PixelTable`` so a zoomify chain (and per-level balancing)
+never leaves HBM.  With ``group=`` (one rank per GPU) every rank coarsens the
+stored pixels of its own row range, cut at coarse-bin boundaries so that no
+exchange is needed; rank 0 gathers the pieces in rank order and writes.
 The bin id map is the closed form of the reference's coordinate arithmetic:
 ``new_id = new_chrom_offset[c] + (old_id - old_chrom_offset[c]) // factor``.
 """
@@ -348,6 +351,47 @@ def _check_columns(clr, columns, agg):
     return columns
 
 
+def shard_rows_for_coarsening(clr, group, align):
+    """Row range [lo, hi) of this rank for sharded coarsening: about nnz / world stored pixels
+    (table.shard_rows_by_pixels), both ends moved down to a boundary of ``align`` pooled bins inside
+    their chromosome (``align_rows_to_factor``), so that every coarse row -- of this level and of the
+    levels chained after it, when ``align`` is their common multiple -- lives on exactly one rank."""
+    import torch.distributed as dist
+    from .table import shard_rows_by_pixels
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    off = np.asarray(clr._load_dset("indexes/bin1_offset"))
+    chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
+    lo, hi = shard_rows_by_pixels(off, rank, world)
+    lo = align_rows_to_factor(chrom_offset, align, lo) if rank > 0 else 0
+    hi = align_rows_to_factor(chrom_offset, align, hi) if rank + 1 < world else len(off) - 1
+    return lo, max(hi, lo)
+
+
+def gather_pixels_to_rank0(arrays, group):
+    """Concatenate equally long 1-D numpy arrays of every rank in rank order on group rank 0 (the
+    others get empty arrays).  Padded ``dist.gather`` on the device for NCCL, on the host for gloo."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    n = len(arrays[0])
+    sizes = [torch.zeros(1, dtype=_I64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([n], dtype=_I64, device=dev), group=group)
+    sizes = [int(x.item()) for x in sizes]
+    dst = dist.get_global_rank(group, 0) if group is not None else 0
+    out = []
+    for a in arrays:
+        a = np.ascontiguousarray(a)
+        pad = torch.zeros(max(max(sizes), 1), dtype=torch.from_numpy(a[:0].copy()).dtype, device=dev)
+        pad[:n] = torch.from_numpy(a).to(dev)
+        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad, bufs, dst=dst, group=group)
+        if rank == 0:
+            out.append(torch.cat([b[:k] for b, k in zip(bufs, sizes)]).cpu().numpy())
+        else:
+            out.append(a[:0])
+    return out
+
+
 class CoolerCoarsener:
     """GPU replacement of ``cooler._reduce.CoolerCoarsener`` (_reduce.py:501-642).
 
@@ -358,8 +402,9 @@ class CoolerCoarsener:
     """
 
     def __init__(self, source, factor, chunksize, columns=None, agg=None, batchsize=1, map=map,
-                 device="cuda", table=None):
+                 device="cuda", table=None, group=None, align=None):
         assert isinstance(factor, int) and factor > 1
+        self.group = group
         self.clr = source
         self.factor = factor
         self.chunksize = int(chunksize)
@@ -381,6 +426,14 @@ class CoolerCoarsener:
         self.new_bins_arrays = (c, s, e)
         self._chromnames = list(chromsizes.index)
         self._device = device
+        if group is not None and not self._fast:
+            raise NotImplementedError("sharded coarsening (group=...) covers the integer-count / sum path only")
+        if table is None and self._fast and group is not None:
+            # this rank's row range of the source, cut at boundaries of `align` pooled bins
+            from .table import read_cooler_arrays
+            rows = shard_rows_for_coarsening(source, group, int(align or factor))
+            off, b2, cnt, co = read_cooler_arrays(source, rows=rows)
+            table = PixelTable.from_arrays(off, b2, cnt, co, device=device, row_range=rows)
         self._table = table if (table is not None or not self._fast) else PixelTable.from_cooler(source, device=device)
         self.result_table = None
 
@@ -400,7 +453,13 @@ class CoolerCoarsener:
         b1, b2, cnt = table_to_host(new_table, b1ids)
         count_dtype = self.clr.pixels().dtypes["count"]
         cnt = cnt.astype(count_dtype, copy=False)
-        ind = new_table.raw.indptr.cpu().numpy()
+        if self.group is not None:
+            # shards hold disjoint, ascending coarse row ranges: the rank-ordered concatenation IS the
+            # coarsened table (bit-identical to the single-GPU result); rank 0 alone yields chunks
+            b1, b2, cnt = gather_pixels_to_rank0([b1, b2, cnt], self.group)
+            ind = np.searchsorted(b1, np.arange(new_table.n_bins + 1), side="left")
+        else:
+            ind = new_table.raw.indptr.cpu().numpy()
         edges = _prune_edges(ind, self.chunksize)
         for lo, hi in zip(edges[:-1], edges[1:]):
             if hi > lo:
@@ -467,18 +526,25 @@ def _create(output_uri, bins, iterator, **kwargs):
     return create(output_uri, bins, iterator, **kwargs)
 
 
-def _coarsen(clr, output_uri, factor, chunksize, nproc, columns, dtypes, agg, device, table, kwargs):
-    """Shared body of coarsen_cooler / zoomify_cooler: returns (MemCooler or None, device table)."""
+def _coarsen(clr, output_uri, factor, chunksize, nproc, columns, dtypes, agg, device, table, kwargs,
+             group=None, align=None):
+    """Shared body of coarsen_cooler / zoomify_cooler: returns (MemCooler or None, device table).
+    With ``group`` every rank coarsens its row shard; group rank 0 receives the pixels and writes (or
+    holds the MemCooler), the other ranks get a MemCooler without pixels (bins / metadata only)."""
     factor = int(factor)
+    rank0 = True
+    if group is not None:
+        import torch.distributed as dist
+        rank0 = dist.get_rank(group) == 0
     columns = _check_columns(clr, columns, agg)
     dtypes = dict(dtypes or {})
     input_dtypes = clr.pixels().dtypes
     for col in columns:
         dtypes.setdefault(col, input_dtypes[col])
     iterator = CoolerCoarsener(clr, factor, chunksize, columns=columns, agg=agg, batchsize=nproc,
-                               device=device, table=table)
+                               device=device, table=table, group=group, align=align)
     symmetric_upper = clr.storage_mode == "symmetric-upper"
-    if output_uri is None:
+    if output_uri is None or not rank0:
         chunks = list(iterator)
         cat = {k: (np.concatenate([c[k] for c in chunks]) if chunks else np.zeros(0, dtype=np.int64))
                for k in ("bin1_id", "bin2_id", "count")}        # like create(): only 'count' is kept (SURVEY 8 a10)
@@ -488,7 +554,7 @@ def _coarsen(clr, output_uri, factor, chunksize, nproc, columns, dtypes, agg, de
                                     cat["count"].astype(dtypes["count"], copy=False),
                                     binsize=iterator.new_binsize, symmetric_upper=symmetric_upper)
         out.device_table = iterator.result_table
-        return out, iterator.result_table
+        return (out if output_uri is None else None), iterator.result_table
     kwargs = dict(kwargs)
     kwargs.setdefault("append", True)
     if kwargs.get("mode") == "w":                  # `coarsen x.cool -o x.cool`: never truncate the input
@@ -500,7 +566,7 @@ def _coarsen(clr, output_uri, factor, chunksize, nproc, columns, dtypes, agg, de
 
 
 def coarsen_cooler(base_uri, output_uri, factor, chunksize, nproc=1, columns=None, dtypes=None,
-                   agg=None, device="cuda", **kwargs):
+                   agg=None, device="cuda", group=None, **kwargs):
     """Coarsen a cooler by an integer factor on the GPU.
 
     Same arguments as ``cooler.coarsen_cooler`` (_reduce.py:645-749); ``nproc`` is
@@ -510,15 +576,26 @@ def coarsen_cooler(base_uri, output_uri, factor, chunksize, nproc=1, columns=Non
     otherwise it is written like the reference does it -- ``create(..., append=True,
     symmetric_upper=<propagated>)`` -- through ``cooler.create`` (h5py) when available, else
     through the built-in writer (``cooler_b200.create`` / ``h5write``).
+
+    ``group``: a ``torch.distributed`` process group (one rank per GPU).  Where the reference maps
+    pixel chunks over a process pool (``nproc``, _reduce.py:726-744), every rank here reads and
+    coarsens the stored pixels of its own bin1 row range, cut at coarse-bin boundaries so that no
+    coarse row is split (no exchange step); group rank 0 gathers the pieces in rank order --
+    bit-identical to the single-GPU result -- and writes / returns them (the other ranks return a
+    MemCooler without pixels, or None).  Call it on all ranks.
     """
     clr = _as_cooler(base_uri)
     table = kwargs.pop("table", None)
-    out, _ = _coarsen(clr, output_uri, factor, chunksize, nproc, columns, dtypes, agg, device, table, kwargs)
+    out, _ = _coarsen(clr, output_uri, factor, chunksize, nproc, columns, dtypes, agg, device, table, kwargs,
+                      group=group)
+    if group is not None and output_uri is not None:
+        import torch.distributed as dist
+        dist.barrier(group)                           # the file is complete when any rank returns
     return out
 
 
 def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=None, dtypes=None,
-                   agg=None, device="cuda", **kwargs):
+                   agg=None, device="cuda", group=None, **kwargs):
     """Multi-resolution coarsening chain (``cooler.zoomify_cooler``, _reduce.py:752-877).
 
     Each target resolution is derived from the largest already-available
@@ -528,7 +605,15 @@ def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=
     (the base included); otherwise writes the MCOOL v2 layout ``resolutions/<r>`` into
     ``outfile`` (base levels copied first, _reduce.py:838-854; root attributes ``format`` /
     ``format-version`` last, 873-877) and returns None.
+
+    ``group`` (one rank per GPU): every rank keeps ITS row shard of every level on its device -- the
+    base shards are cut at boundaries of the least common multiple of all zoom factors, so every
+    level of the chain stays exchange-free -- and group rank 0 gathers and writes each level.
     """
+    rank0 = True
+    if group is not None:
+        import torch.distributed as dist
+        rank0 = dist.get_rank(group) == 0
     if not isinstance(base_uris, (list, tuple)):
         base_uris = [base_uris]
     bases = {}
@@ -538,15 +623,26 @@ def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=
             raise ValueError("Cannot zoomify a cooler with variable-size bins")   # cli/zoomify.py
         bases[int(clr.binsize)] = clr
     resn, pred, mult = get_multiplier_sequence(list(resolutions), list(bases))
+    # zoom factor of every level relative to ITS base, and their common multiple per base
+    to_base, base_of = {}, {}
+    for i, res in enumerate(resn):
+        if pred[i] == -1:
+            to_base[int(res)], base_of[int(res)] = 1, int(res)
+        else:
+            prev = int(resn[pred[i]])
+            to_base[int(res)], base_of[int(res)] = to_base[prev] * int(mult[i]), base_of[prev]
+    align = {b: math.lcm(*[f for r, f in to_base.items() if base_of[r] == b]) for b in bases}
     if outfile is not None:
         from . import create as _cr
-        from . import h5write
-        _cr.refuse_truncating_source(outfile, bases.values(), "w")
+        _cr.refuse_truncating_source(outfile, bases.values(), "w")      # on every rank: all raise or none
+    if outfile is not None and rank0:
         cols = tuple(columns) if columns is not None else ("count",)
         first = True
         for res, clr in bases.items():
             _cr.copy_cooler(clr, f"{outfile}::resolutions/{res}", columns=cols, mode="w" if first else "r+")
             first = False
+    if group is not None and outfile is not None:
+        dist.barrier(group)
     out = {}
     tables = {}
     for i, res in enumerate(resn):
@@ -559,13 +655,22 @@ def zoomify_cooler(base_uris, outfile, resolutions, chunksize, nproc=1, columns=
         kw = dict(kwargs)
         if outfile is not None:
             kw["mode"] = "r+"
+        # a level made from a base reads shards aligned for the whole chain; later levels inherit them
         lvl, tables[res] = _coarsen(out[prev], dest, int(mult[i]), chunksize, nproc, columns, dtypes, agg,
-                                    device, tables.get(prev), kw)
+                                    device, tables.get(prev), kw, group=group,
+                                    align=max(1, align[base_of[res]] // to_base[prev]))
+        if group is not None and outfile is not None:
+            dist.barrier(group)                       # rank 0 has written the level every rank opens next
         out[res] = lvl if outfile is None else _as_cooler(dest)
     if outfile is None:
         return out
-    with h5write.File(outfile, "r+") as fw:
-        fw.attrs.update({"format": "HDF5::MCOOL", "format-version": _cr.FORMAT_VERSION_MCOOL})
+    if rank0:
+        from . import create as _cr
+        from . import h5write
+        with h5write.File(outfile, "r+") as fw:
+            fw.attrs.update({"format": "HDF5::MCOOL", "format-version": _cr.FORMAT_VERSION_MCOOL})
+    if group is not None:
+        dist.barrier(group)
     return None
 
 

@@ -9,7 +9,11 @@
 2. A ~1e7-pixel synthetic ``.cool`` written by rank 0 (``create_cooler``), balanced across the ranks
    with ``store=True``, against the CPU oracle (oracle/ice_numpy.py) run to convergence on rank 0:
    mask, pass count (from the stored stats: converged), bias, scale, var; the stored column is read back.
-3. ``python -m cooler_b200.cli balance`` semantics under torchrun are covered by
+3. ``coarsen_cooler(..., group=WORLD)`` on the bundled GM12878 file (every rank coarsens its own
+   row range, rank 0 gathers) against the reference's coarsening goldens x2 / x5 / x10, and
+   ``zoomify_cooler(..., group=WORLD)`` of the written file to an ``.mcool`` whose levels must be
+   bit-identical to a single-rank run of the same chain.
+4. ``python -m cooler_b200.cli balance`` semantics under torchrun are covered by
    tests/test_dist_gpu.py, which launches the CLI itself.
 """
 import os
@@ -90,6 +94,37 @@ def main():
         print(f"[check_dist_cooler] world={world} written .cool nnz={len(b1)} oracle passes={wpasses} "
               f"mask_equal={same} max_rel_err={err:.2e} stored_column_equal={np.array_equal(stored, bias, equal_nan=True)} "
               f"{'OK' if good else 'FAIL'}", flush=True)
+
+    # ---- 3. sharded coarsening / zoomify through the reference API ----------------------------
+    from cooler_b200.reduce import coarsen_cooler, zoomify_cooler
+    CO = _golden.coarsen_golden()
+    for factor in (2, 5, 10):
+        out = coarsen_cooler(store.open_cooler(path), None, factor, chunksize=50_000, group=group)
+        if rank == 0:
+            with out.open("r") as grp:
+                got = [np.asarray(grp["pixels"][c][:]) for c in ("bin1_id", "bin2_id", "count")]
+            good = all(np.array_equal(g, CO[f"gm/x{factor}/{c}"]) for g, c in zip(got, ("bin1_id", "bin2_id", "count")))
+            ok &= bool(good)
+            print(f"[check_dist_cooler] world={world} sharded coarsen_cooler x{factor} vs reference golden: "
+                  f"nnz_out={len(got[0])} {'OK (bit-exact)' if good else 'FAIL'}", flush=True)
+    resolutions = [500_000, 1_000_000, 2_500_000, 5_000_000]
+    mc = os.path.join(workdir, "check_dist_zoom.mcool")
+    zoomify_cooler(fn, mc, resolutions, chunksize=2_000_000, group=group)
+    if rank == 0:
+        single = zoomify_cooler(fn, None, resolutions, chunksize=2_000_000)
+        good = True
+        for res in resolutions:
+            with store.open_cooler(f"{mc}::resolutions/{res}").open("r") as grp:
+                got = [np.asarray(grp["pixels"][c][:]) for c in ("bin1_id", "bin2_id", "count")]
+            with single[res].open("r") as grp:
+                want = [np.asarray(grp["pixels"][c][:]) for c in ("bin1_id", "bin2_id", "count")]
+            good &= all(np.array_equal(a, b) for a, b in zip(got, want)) and len(got[0]) > 0
+        ok &= bool(good)
+        print(f"[check_dist_cooler] world={world} sharded zoomify_cooler {resolutions} vs single rank: "
+              f"{'OK (bit-exact)' if good else 'FAIL'}", flush=True)
+        os.unlink(mc)
+    dist.barrier()
+    if rank == 0:
         os.unlink(fn)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
