@@ -318,7 +318,7 @@ def test_zoomify_file_plumbing_with_oracle_coarsener(tmp_path, monkeypatch):
 
     class OracleCoarsener(reduce.CoolerCoarsener):
         def __init__(self, source, factor, chunksize, columns=None, agg=None, batchsize=1, map=map,
-                     device="cuda", table=None):
+                     device="cuda", table=None, **kw):
             super().__init__(source, factor, chunksize, columns=columns, agg=agg, table=object())
 
         def __iter__(self):
@@ -375,7 +375,7 @@ def test_legacy_zoomify_plumbing_with_oracle_coarsener(tmp_path, monkeypatch):
 
     class OracleCoarsener(reduce.CoolerCoarsener):
         def __init__(self, source, factor, chunksize, columns=None, agg=None, batchsize=1, map=map,
-                     device="cuda", table=None):
+                     device="cuda", table=None, **kw):
             super().__init__(source, factor, chunksize, columns=columns, agg=agg, table=object())
 
         def __iter__(self):
