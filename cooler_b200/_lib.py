@@ -27,7 +27,7 @@ class Sub(C.Structure):
                 ("nnz", C.c_int64), ("direct", C.c_void_p), ("pieces", C.c_void_p),
                 ("first_warp", C.c_int64), ("first_tile", C.c_int64),
                 ("gather_base", C.c_int32), ("gather_len", C.c_int32),
-                ("row_base", C.c_int32), ("row_count", C.c_int32)]
+                ("row_base", C.c_int32), ("row_count", C.c_int32), ("val", C.c_void_p)]
 
 
 class Ice(C.Structure):
@@ -53,7 +53,7 @@ class Ice(C.Structure):
         ("far_copies", C.c_void_p), ("far_units", C.c_void_p), ("far_tiles", C.c_void_p),
         ("far_parts", C.c_void_p), ("far_claim", C.c_void_p),
         ("n_far_units", C.c_int32), ("far_col_shift", C.c_int32), ("far_warps", C.c_int32),
-        ("far_rec_bytes", C.c_int32),
+        ("far_rec_bytes", C.c_int32), ("float_counts", C.c_int32),
     ]
 
 
@@ -104,6 +104,8 @@ SIGNATURES = {
     "cb200_filter_count": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P]),
     "cb200_filter_write": (C.c_int, [_P, _P, _P, _I32, _I64, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
+    "cb200_attach_values": (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
+    "cb200_values_nonzero": (C.c_int, [_P, _I64, _P, _P]),
     "cb200_set_tuning": (C.c_int, [_I32, _I32]),
     "cb200_far_row_shift": (C.c_int, []),
     "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .table import (PixelTable, TableCopy, _as_tensor, _new_px, _ptr, _stream, _use_device, counts_as_int32, to_host,  # noqa: F401
-                    far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays,
+                    attach_values, is_float_column, values_nonzero, far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays,
                     segment_medians, shard_rows_by_pixels,
                     strip_partition, swap_key_other, transpose_from)
 
@@ -163,16 +163,23 @@ class IceProblem:
         self.group = group
         self.mode = "cis" if cis_only else ("trans" if trans_only else "gw")
         n_bins = table.n_bins
+        fval = getattr(table, "fval", None)          # floating-point count column: records carry positions
+        self.float_counts = fval is not None
+        if self.float_counts and band not in (None, False):
+            raise NotImplementedError("the band / 2-D blocked layouts hold integer counts only")
         ndiag = int(ignore_diags) if ignore_diags else 0
         keep = _lib.KEEP_CIS if cis_only else _lib.KEEP_ALL
         csr, tkey, tval = filter_copy(table.raw, table.row_lo, table.row_hi, ndiag, keep,
                                       want_transpose=True)
         csc, ckeys = transpose_from(tkey, tval, n_bins, return_keys=True)
-        # prefilter marginals (exact integers)
-        nnz_r, sum_r = marginals_i64(csr)
-        nnz_c, sum_c = marginals_i64(csc)
-        marg = torch.stack([nnz_r + nnz_c, sum_r + sum_c])
-        del nnz_r, sum_r, nnz_c, sum_c
+        if fval is None:
+            # prefilter marginals (exact integers)
+            nnz_r, sum_r = marginals_i64(csr)
+            nnz_c, sum_c = marginals_i64(csc)
+            marg = torch.stack([nnz_r + nnz_c, sum_r + sum_c])
+            del nnz_r, sum_r, nnz_c, sum_c
+        else:
+            marg = float_marginals([csr, csc], fval, n_bins)
         _allreduce(marg, group)
         marg = to_host(marg)
         self.marg_nnz = marg[0].astype(np.float64)
@@ -187,6 +194,8 @@ class IceProblem:
         self._nnz_eff = csr.nnz
         # layout of the sweep: whole copies, column strips, or diagonal band strips + far rest
         self.strip_shift, self.band = choose_layout(n_bins, csr.nnz, strip_bins, band)
+        if self.float_counts:
+            self.band = False                         # whole copies or column strips
         sh = self.strip_shift
         if band is None and self.band == "allblocks":
             # automatic choice: the block build keeps ~5 transient 12-byte copies of the pixel stream
@@ -208,6 +217,8 @@ class IceProblem:
             self.far_copies.append(far_blocks(ckeys[:n2], cval, n2, n_bins, self.far_col_shift, compact=compact))
             self.subs = []
         elif sh is None:
+            if fval is not None:
+                attach_values(csr, fval), attach_values(csc, fval)
             self.subs = [csr.tight(), csc.tight()]
             self.csr, self.csc = csr, csc
         elif not self.band:
@@ -216,6 +227,9 @@ class IceProblem:
             if cval is None:                      # csc came from the sort: (key = row, val = {other, count})
                 ckeys, cval = swap_key_other(ckeys, csc.px, csc.nnz)
             subs += strip_partition(ckeys[: csc.nnz], cval, csc.nnz, n_bins, sh)
+            if fval is not None:
+                for sub in subs:
+                    attach_values(sub, fval)
             self.subs = subs
             self.csr = self.csc = None            # the strips replace the whole copies
         else:
@@ -264,6 +278,8 @@ class IceProblem:
         wait for the whole table.  Returns None when the layout needs far-field blocks (1 kb class):
         the caller then uses the two-step path (PixelTable + IceProblem).
         """
+        if is_float_column(count):
+            return None                               # floating-point counts: two-step build
         dev = _use_device(device)
         off_t = bin1_offset if isinstance(bin1_offset, torch.Tensor) else torch.from_numpy(
             np.ascontiguousarray(bin1_offset, dtype=np.int64))
@@ -313,6 +329,7 @@ class IceProblem:
 
         self = cls.__new__(cls)
         self.table, self.group, self.use_smem = info, group, True
+        self.float_counts = False
         self.mode = "cis" if cis_only else ("trans" if trans_only else "gw")
         self.peer_reduce = True if peer_reduce is None else bool(peer_reduce)
         self.strip_shift, self.band, self.csr, self.csc = strip_shift, False, None, None
@@ -381,14 +398,16 @@ class IceProblem:
         return self._nnz_eff
 
     def bytes_per_pass(self):
-        """Algorithmic bytes of one marginal pass: 16 B/effective pixel + 40 B/bin."""
-        return 16 * self.nnz_eff + 40 * self.table.n_bins
+        """Algorithmic bytes of one marginal pass: 16 B/effective pixel + 40 B/bin (32 B/pixel with a
+        floating-point count column: 8 B record + 8 B value in both copies)."""
+        return (32 if self.float_counts else 16) * self.nnz_eff + 40 * self.table.n_bins
 
     def stream_bytes(self):
         """Bytes of pixel records one pass actually streams from HBM: 8 B per record of the row-ordered
         sub-copies, 8 or 4 B (compact) per record of the 2-D blocked copies, padding included."""
         far = [f for f in self.far_copies if f is not None]
-        return 8 * sum(c.nnz for c in self.subs) + sum(f.n_chunks * 64 * f.rec_bytes for f in far)
+        return (16 if self.float_counts else 8) * sum(c.nnz for c in self.subs) + \
+            sum(f.n_chunks * 64 * f.rec_bytes for f in far)
 
 
 L1_RESIDENT_BINS = 49_152      # bias vectors up to 384 KB are served well enough by L1 + L2
@@ -438,6 +457,67 @@ def choose_layout(n_bins, nnz_eff, strip_bins=None, band=None):
     return shift, (band if band in ("blocks", "allblocks") else bool(band))
 
 
+def sub_descriptors(subs, n_bins, strip_shift, smem, dev, float_counts=False, val=None):
+    """Device array of cb200_sub for the sub-copies ``subs`` plus their output buffers.  Returns
+    (subs_dev, direct, pieces, claim, span, total_warps, total_tiles).  ``val`` overrides the value array
+    of every sub-copy (prefilter marginals of floating-point columns: the raw column, records holding
+    positions in the stored table)."""
+    total_tiles = sum(n_tiles(c.nnz) for c in subs)
+    span = int(min(8, max(1, -(-total_tiles // (148 * 32 * 8)))))
+    if smem:
+        span = min(span, 4)                       # persistent strip kernel: finer claims, see csrc/ice.cu
+    arr = (_lib.Sub * max(len(subs), 1))()
+    direct = torch.zeros(sum(c.n_rows for c in subs) + 1, dtype=_F64, device=dev)
+    pieces = torch.zeros(2 * total_tiles + 2, dtype=_F64, device=dev)
+    warp0, tile0, row0 = 0, 0, 0
+    for k, c in enumerate(subs):
+        arr[k].px, arr[k].indptr, arr[k].tile_row = c.px.data_ptr(), c.indptr.data_ptr(), c.tile_row.data_ptr()
+        arr[k].nnz = c.nnz
+        arr[k].row_base, arr[k].row_count = c.row_base, c.n_rows
+        arr[k].direct = direct.data_ptr() + 8 * row0
+        row0 += c.n_rows
+        arr[k].pieces = pieces.data_ptr() + 8 * 2 * tile0
+        arr[k].first_warp = warp0
+        arr[k].first_tile = tile0
+        if float_counts:
+            arr[k].val = (val if val is not None else c.val).data_ptr()
+        strip = getattr(c, "strip", None)
+        if strip is None or strip_shift is None:
+            arr[k].gather_base, arr[k].gather_len = 0, n_bins
+        else:
+            base = strip << strip_shift
+            arr[k].gather_base, arr[k].gather_len = base, min(1 << strip_shift, n_bins - base)
+        warp0 += -(-n_tiles(c.nnz) // span)
+        tile0 += n_tiles(c.nnz)
+    subs_dev = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
+    claim = torch.zeros(len(subs) + 1, dtype=torch.int64, device=dev)
+    return subs_dev, direct, pieces, claim, span, warp0, total_tiles
+
+
+def float_marginals(copies, fval, n_bins):
+    """Prefilter marginals of a floating-point count column (_balance.py:375-393): float64 [2, n_bins] =
+    (number of nonzero values, sum of values) over the rows of every copy in ``copies`` -- the records
+    hold positions into ``fval``.  One sweep (K3, whole-copy form, w = 1) + combine per quantity."""
+    dev = fval.device
+    out = torch.zeros((2, max(n_bins, 1)), dtype=_F64, device=dev)
+    subs = [c.tight() for c in copies if c.nnz]
+    if not subs or n_bins == 0:
+        return out[:, :n_bins]
+    ones = torch.ones(n_bins, dtype=_F64, device=dev)
+    done = torch.zeros(1, dtype=_I32, device=dev)
+    for k, val in enumerate((values_nonzero(fval), fval)):
+        subs_dev, direct, pieces, claim, span, warps, tiles = sub_descriptors(
+            subs, n_bins, None, False, dev, float_counts=True, val=val)
+        st = _lib.Ice()
+        st.subs, st.n_subs, st.span, st.total_warps, st.total_tiles = subs_dev.data_ptr(), len(subs), span, warps, tiles
+        st.smem_bins, st.claim, st.n_bins = 0, claim.data_ptr(), n_bins
+        st.w, st.s, st.all_done, st.float_counts = ones.data_ptr(), out[k].data_ptr(), done.data_ptr(), 1
+        _lib.call("cb200_ice_sweep", C.byref(st), _stream())
+        _lib.call("cb200_ice_combine", C.byref(st), _stream())
+        torch.cuda.current_stream().synchronize()       # the descriptors are released at the end of the turn
+    return out[:, :n_bins]
+
+
 class IceState:
     """Device buffers + cb200_ice descriptor for the iteration loop."""
 
@@ -477,33 +557,9 @@ class IceState:
             t["w"] = t["bias"]
         # sub-copy descriptors (whole copies or column strips) for K3 / combine
         subs = prob.subs
-        total_tiles = sum(n_tiles(c.nnz) for c in subs)
-        span = int(min(8, max(1, -(-total_tiles // (148 * 32 * 8)))))
-        if prob.strip_shift is not None and prob.use_smem:
-            span = min(span, 4)                       # persistent strip kernel: finer claims, see csrc/ice.cu
-        arr = (_lib.Sub * max(len(subs), 1))()
-        t["direct"] = f64(sum(c.n_rows for c in subs) + 1)
-        t["pieces"] = f64(2 * total_tiles + 2)
-        warp0, tile0, row0 = 0, 0, 0
-        for k, c in enumerate(subs):
-            arr[k].px, arr[k].indptr, arr[k].tile_row = c.px.data_ptr(), c.indptr.data_ptr(), c.tile_row.data_ptr()
-            arr[k].nnz = c.nnz
-            arr[k].row_base, arr[k].row_count = c.row_base, c.n_rows
-            arr[k].direct = t["direct"].data_ptr() + 8 * row0
-            row0 += c.n_rows
-            arr[k].pieces = t["pieces"].data_ptr() + 8 * 2 * tile0
-            arr[k].first_warp = warp0
-            arr[k].first_tile = tile0
-            strip = getattr(c, "strip", None)
-            if strip is None or prob.strip_shift is None:
-                arr[k].gather_base, arr[k].gather_len = 0, n
-            else:
-                base = strip << prob.strip_shift
-                arr[k].gather_base, arr[k].gather_len = base, min(1 << prob.strip_shift, n - base)
-            warp0 += -(-n_tiles(c.nnz) // span)
-            tile0 += n_tiles(c.nnz)
-        t["subs"] = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
-        t["claim"] = torch.zeros(len(subs) + 1, dtype=torch.int64, device=dev)
+        smem = prob.strip_shift is not None and prob.use_smem
+        t["subs"], t["direct"], t["pieces"], t["claim"], span, warp0, total_tiles = sub_descriptors(
+            subs, n, prob.strip_shift, smem, dev, float_counts=getattr(prob, "float_counts", False))
         t["s"], t["marg"] = f64(n), f64(n)
         # far-field blocks: units of about equal size, a few per SM (csrc/far.cuh)
         far = [f for f in getattr(prob, "far_copies", []) if f is not None]
@@ -561,6 +617,7 @@ class IceState:
             st.far_col_shift, st.far_warps = far[0].col_shift, far[0].warps
             st.far_rec_bytes = far[0].rec_bytes
             assert all(f.rec_bytes == far[0].rec_bytes for f in far)
+        st.float_counts = 1 if getattr(prob, "float_counts", False) else 0
         self.st = st
         self.prob = prob
         self.flag_host = torch.zeros(1, dtype=_I32).pin_memory() if torch.cuda.is_available() else None
@@ -820,7 +877,8 @@ def balance_arrays(bin1_offset, bin2_id, count, chrom_offset, *, cis_only=False,
                    chromnames=None, strip_bins=None, band=None, **kwargs):
     """Balance a pixel table given as HOST arrays (numpy or torch, ideally pinned):
     ``bin1_offset`` int64[n_bins+1] (the cooler's indexes/bin1_offset), ``bin2_id`` int64 or int32,
-    ``count`` int32.  The build is pipelined with the host->device copy (IceProblem.from_host);
+    ``count`` any integer type within int32 range, or float32 / float64 (kept as float64: the reference
+    computes in whatever dtype the column has, _balance.py:25-26).  The build is pipelined with the host->device copy (IceProblem.from_host);
     tables that need column strips go through PixelTable + IceProblem.  Other keyword
     arguments and the return value are those of ``balance_table``."""
     prob = None
@@ -832,7 +890,7 @@ def balance_arrays(bin1_offset, bin2_id, count, chrom_offset, *, cis_only=False,
         table = prob.table
     else:
         table = PixelTable.from_arrays(bin1_offset, bin2_id, count, chrom_offset, device=device,
-                                       row_range=row_range)
+                                       row_range=row_range, float_values=True)
     return balance_table(table, cis_only=cis_only, trans_only=trans_only, ignore_diags=ignore_diags,
                          group=group, problem=prob, return_info=return_info, chromnames=chromnames,
                          strip_bins=strip_bins, band=band, **kwargs)

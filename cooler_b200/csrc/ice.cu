@@ -50,11 +50,32 @@ struct IceOpT {
 };
 typedef IceOpT<false> IceOp;
 
+// Floating-point count columns (cb200_ice.float_counts): the count field of a record indexes the
+// sub-copy's value array (cb200_sub.val) -- its own stream position after cb200_attach_values, so the
+// loads are coalesced and bypass L1 like the record stream.
+template <bool kSelective>
+struct IceOpValT {
+  typedef double T;
+  const double* __restrict__ w;
+  const double* __restrict__ val;
+  int row_base;
+  int center;
+  __device__ __forceinline__ void at_row(int row) { if (kSelective) center = row + row_base; }
+  __device__ __forceinline__ double value(int other, int idx) const {
+    double wv;
+    if (kSelective && (unsigned)(other - center + kNearBins) > (unsigned)(2 * kNearBins))
+      wv = ld_gather_far(w + other);
+    else
+      wv = __ldg(w + other);
+    return wv * ld_gather_far(val + idx);
+  }
+};
+
 // Tuning knob (cb200_set_tuning): 128-bit stream loads kept in flight per lane.
 static int g_selective = -1;   // -1 = automatic
 static int g_ice_unroll = 0;   // 0 = automatic: 4 chunks in flight per lane (strip kernel: 768-thread CTAs)
 
-template <int U, bool kSelective, int MINB>
+template <int U, bool kSelective, int MINB, bool kFloat = false>
 __global__ void __launch_bounds__(BLOCK_THREADS, MINB)
 ice_sweep_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span, int64_t total_warps,
                  const double* __restrict__ w, const int32_t* __restrict__ all_done) {
@@ -70,9 +91,15 @@ ice_sweep_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span, int64
   const int64_t n_tiles = (sub.nnz + WARP_TILE - 1) / WARP_TILE;
   const int64_t t0 = (wg - sub.first_warp) * span;
   if (t0 >= n_tiles) return;
-  IceOpT<kSelective> op{w, sub.row_base, 0};
-  walk_reduce_span<IceOpT<kSelective>, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
-                                          sub.row_count, sub.nnz, t0, min(t0 + span, n_tiles), op, sub.direct, sub.pieces);
+  if constexpr (kFloat) {
+    IceOpValT<kSelective> op{w, sub.val, sub.row_base, 0};
+    walk_reduce_span<IceOpValT<kSelective>, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
+                                               sub.row_count, sub.nnz, t0, min(t0 + span, n_tiles), op, sub.direct, sub.pieces);
+  } else {
+    IceOpT<kSelective> op{w, sub.row_base, 0};
+    walk_reduce_span<IceOpT<kSelective>, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
+                                            sub.row_count, sub.nnz, t0, min(t0 + span, n_tiles), op, sub.direct, sub.pieces);
+  }
 }
 
 // Shared-memory form of K3 for column strips: a persistent CTA per SM owns a
@@ -89,6 +116,16 @@ struct IceOpSmem {
     return ws[other - base] * i32_to_f64(count);
   }
 };
+struct IceOpSmemVal {                               // floating-point count columns, see IceOpValT
+  typedef double T;
+  const double* ws;
+  int base;
+  const double* __restrict__ val;
+  __device__ __forceinline__ void at_row(int) {}
+  __device__ __forceinline__ double value(int other, int idx) const {
+    return ws[other - base] * ld_gather_far(val + idx);
+  }
+};
 
 
 // Work distribution: one persistent CTA per SM.  Every sub-copy has a claim counter.
@@ -98,7 +135,7 @@ struct IceOpSmem {
 // the sub-copy is exhausted (no CTA barrier per claim).  Claims only decide WHO
 // computes a tile, never the arithmetic, so results stay bit-reproducible.  The last
 // CTA to finish re-arms the counters.
-template <int U, int STRIP_THREADS>
+template <int U, int STRIP_THREADS, bool kFloat = false>
 __global__ void __launch_bounds__(STRIP_THREADS, 1)
 ice_sweep_strips_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span,
                         int64_t total_tiles, int smem_bins, const double* __restrict__ w,
@@ -142,7 +179,17 @@ ice_sweep_strips_kernel(const cb200_sub* __restrict__ subs, int n_subs, int span
       take = __shfl_sync(0xffffffffu, take, 0);
       if (t0 >= n_tiles) break;
       const int64_t t1 = min(t0 + take, n_tiles);
-      if (in_smem) {
+      if constexpr (kFloat) {
+        if (in_smem) {
+          IceOpSmemVal op{w_s, sub.gather_base, sub.val};
+          walk_reduce_span<IceOpSmemVal, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
+                                            sub.row_count, sub.nnz, t0, t1, op, sub.direct, sub.pieces);
+        } else {
+          IceOpValT<false> op{w, sub.val, 0, 0};
+          walk_reduce_span<IceOpValT<false>, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
+                                                sub.row_count, sub.nnz, t0, t1, op, sub.direct, sub.pieces);
+        }
+      } else if (in_smem) {
         IceOpSmem op{w_s, sub.gather_base};
         walk_reduce_span<IceOpSmem, U>(reinterpret_cast<const int2*>(sub.px), sub.indptr, sub.tile_row,
                                        sub.row_count, sub.nnz, t0, t1, op, sub.direct, sub.pieces);
@@ -434,6 +481,10 @@ int cb200_far_row_shift(void) { return CB200_FAR_ROW_SHIFT; }
 // K3 over the far-field blocks (far.cuh): one persistent CTA per SM claims units.
 static int ice_sweep_far(const cb200_ice* st, void* stream) {
   if (st->n_far_units <= 0) return 0;
+  if (st->float_counts) {
+    set_error_msg("ice_sweep: far-field blocks hold integer counts only");
+    return -1;
+  }
   if (st->far_col_shift < 1 || st->far_col_shift > 13 || st->far_warps != 16 ||
       (st->far_rec_bytes != 8 && !(st->far_rec_bytes == 4 && CB200_FAR_ROW_SHIFT <= 12))) {
     set_error_msg("ice_sweep: far_col_shift must be in 1..13, far_warps 16, far_rec_bytes 8 (or 4 with <= 4096-row blocks)");
@@ -487,6 +538,7 @@ static int ice_sweep_near(const cb200_ice* st, void* stream) {
       CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<4, 768, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_bytes = smem;
     }
     int dev = 0, sms = 148;
@@ -497,6 +549,11 @@ static int ice_sweep_near(const cb200_ice* st, void* stream) {
       st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,                 \
       reinterpret_cast<unsigned long long*>(st->claim), st->all_done)
     // default: 24 warps x 4 chunks in flight (80 registers, no spills) beats 32 warps x 2
+    if (st->float_counts) {
+      ice_sweep_strips_kernel<4, 768, true><<<sms, 768, smem, (cudaStream_t)stream>>>(
+          st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,
+          reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
+    } else
     switch (g_ice_unroll) {
       case 1: CB_STRIPS(1, 1024); break;
       case 2: CB_STRIPS(2, 1024); break;
@@ -519,6 +576,14 @@ static int ice_sweep_near(const cb200_ice* st, void* stream) {
       ice_sweep_kernel<U, false, MINB><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(\
           st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);                    \
   } while (0)
+  if (st->float_counts) {
+    if (selective)
+      ice_sweep_kernel<4, true, 2, true><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(
+          st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);
+    else
+      ice_sweep_kernel<4, false, 2, true><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(
+          st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);
+  } else
   switch (g_ice_unroll) {
     case 1: CB_SWEEP(1, 4); break;
     case 2: CB_SWEEP(2, 4); break;

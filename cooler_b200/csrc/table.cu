@@ -357,11 +357,32 @@ __global__ void marginals_finish_kernel(const int64_t* __restrict__ indptr, int6
 
 }  // namespace cb200
 
+namespace cb200 {
+
+// Floating-point count columns: the build carries the position of every pixel in the stored table in
+// the count field; this attaches the values in stream order and relabels the field with the position
+// inside the sub-copy (see cb200_attach_values in the header).
+__global__ void attach_values_kernel(int2* __restrict__ px, int64_t n, const double* __restrict__ values,
+                                     int64_t n_values, double* __restrict__ val_out) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int2 v = px[k];
+  val_out[k] = ((unsigned long long)(long long)v.y < (unsigned long long)n_values) ? values[v.y] : 0.0;
+  px[k] = make_int2(v.x, (int)k);
+}
+
+__global__ void values_nonzero_kernel(const double* __restrict__ values, int64_t n, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = values[i] != 0.0 ? 1.0 : 0.0;
+}
+
+}  // namespace cb200
+
 using namespace cb200;
 
 extern "C" {
 
-int cb200_abi_version(void) { return 2; }
+int cb200_abi_version(void) { return 3; }
 const char* cb200_last_error(void) { return g_err; }
 int cb200_set_device(int device) {
   CB_CHECK(cudaSetDevice(device));
@@ -581,6 +602,26 @@ int cb200_marginals_i64(const cb200_copy* copy, int32_t n_rows, int64_t* nnz_out
         copy->indptr, nnz, n_rows, direct, pc, nnz_out, sum_out);
     CB_LAUNCH_CHECK("marginals_finish");
   }
+  return 0;
+}
+
+int cb200_attach_values(cb200_px* px, int64_t n, const double* values, int64_t n_values, double* val_out,
+                        void* stream) {
+  if (n <= 0) return 0;
+  if (n >= ((int64_t)1 << 31)) {
+    set_error_msg("attach_values: a sub-copy with floating-point values must hold fewer than 2^31 pixels");
+    return -1;
+  }
+  attach_values_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<int2*>(px), n, values, n_values, val_out);
+  CB_LAUNCH_CHECK("attach_values");
+  return 0;
+}
+
+int cb200_values_nonzero(const double* values, int64_t n, double* out, void* stream) {
+  if (n <= 0) return 0;
+  values_nonzero_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(values, n, out);
+  CB_LAUNCH_CHECK("values_nonzero");
   return 0;
 }
 

@@ -73,14 +73,38 @@ def counts_as_int32(count_t):
         return count_t
     if count_t.dtype.is_floating_point:
         raise NotImplementedError(
-            "cooler_b200 balances integer count columns only (float value columns are not "
-            "supported by the CUDA path yet)")
+            "this cooler_b200 path takes integer count columns only (balancing handles floating-point "
+            "columns: balance_cooler / balance_arrays)")
     if count_t.numel():
         lo, hi = int(count_t.min()), int(count_t.max())
         if lo < -2**31 or hi > 2**31 - 1:
             raise OverflowError(f"count column ({count_t.dtype}) holds values outside int32 "
                                 f"[{lo}, {hi}]: not supported by the CUDA path")
     return count_t.to(_I32)
+
+
+def is_float_column(count):
+    """True for a floating-point count column (numpy array or tensor)."""
+    if isinstance(count, torch.Tensor):
+        return count.dtype.is_floating_point
+    return np.issubdtype(np.asarray(count).dtype, np.floating)
+
+
+def attach_values(copy, values):
+    """Floating-point count columns: ``copy`` was built with the pixel's position in the stored table in
+    the count field; sets ``copy.val`` = the float64 values in the copy's own order and relabels the
+    field with the position inside the copy (cb200_attach_values)."""
+    val = torch.empty(max(copy.nnz, 1), dtype=torch.float64, device=copy.px.device)
+    _lib.call("cb200_attach_values", _ptr(copy.px), copy.nnz, _ptr(values), int(values.numel()), _ptr(val), _stream())
+    copy.val = val
+    return copy
+
+
+def values_nonzero(values):
+    """float64 1.0 / 0.0 per value: ``data[data != 0] = 1`` (_binarize, _balance.py:29-31)."""
+    out = torch.empty_like(values)
+    _lib.call("cb200_values_nonzero", _ptr(values), int(values.numel()), _ptr(out), _stream())
+    return out
 
 
 def warp_tile():
@@ -132,7 +156,7 @@ class TableCopy:
             return self
         sub = TableCopy(self.px, self.indptr[first_r:last_r + 2], self.nnz, last_r - first_r + 1,
                         row_base=self.row_base + first_r)
-        for a in ("strip",):
+        for a in ("strip", "val"):
             if hasattr(self, a):
                 setattr(sub, a, getattr(self, a))
         return sub
@@ -471,8 +495,9 @@ class PixelTable:
     of rows [row_range[0], row_range[1]) of an n_bins x n_bins matrix.
     """
 
-    def __init__(self, raw, chrom_offset, row_range=None):
+    def __init__(self, raw, chrom_offset, row_range=None, fval=None):
         self.raw = raw
+        self.fval = fval          # float64 values of a floating-point count column (raw's count field = position), else None
         self.n_bins = raw.n_rows
         self.chrom_offset = np.asarray(chrom_offset, dtype=np.int64)
         self.row_range = row_range or (0, self.n_bins)
@@ -491,11 +516,16 @@ class PixelTable:
         return self.raw.nnz
 
     @classmethod
-    def from_arrays(cls, bin1_offset, bin2_id, count, chrom_offset, device="cuda", row_range=None):
+    def from_arrays(cls, bin1_offset, bin2_id, count, chrom_offset, device="cuda", row_range=None,
+                    float_values=False):
         """Upload (host arrays or tensors; pinned memory is copied asynchronously).
 
         ``bin1_offset`` is the cooler's ``indexes/bin1_offset`` (the CSR indptr;
         docs/schema_v3.rst) -- bin1_id itself is never shipped to the device.
+
+        ``float_values`` (balancing only): a floating-point count column is kept as float64
+        (``table.fval``) and the records' count field holds the pixel's position, so the filters,
+        the transposition and the strip partition carry the values along as indices.
         """
         device = _use_device(device)
         n_bins = len(bin1_offset) - 1
@@ -509,17 +539,23 @@ class PixelTable:
                 t = t.to(dtype)
             return t.to(device, non_blocking=True)
 
-        count_t = counts_as_int32(_as_tensor(count))
+        fval = None
+        if float_values and is_float_column(count):
+            if nnz >= 2**31 - 1:
+                raise ValueError("a table with floating-point counts must hold fewer than 2^31 pixels per GPU")
+            fval = dev(_as_tensor(count), torch.float64)
+            count_d = torch.arange(nnz, dtype=_I32, device=device)
+        else:
+            count_d = dev(counts_as_int32(_as_tensor(count)), _I32)
         indptr = dev(bin1_offset, _I64)
         bin2_t = bin2_id if isinstance(bin2_id, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(bin2_id))
         narrow = bin2_t.dtype == _I32                 # reader already narrowed the ids: 8 B/pixel over PCIe
         bin2_d = dev(bin2_t, _I32 if narrow else _I64)
-        count_d = dev(count_t, _I32)
         px = _new_px(nnz, device)
         _lib.call("cb200_pack_pixels_i32" if narrow else "cb200_pack_pixels", _ptr(bin2_d), _ptr(count_d),
                   nnz, _ptr(px), _stream())
         raw = TableCopy(px, indptr, nnz, n_bins)
-        return cls(raw, chrom_offset, row_range=row_range)
+        return cls(raw, chrom_offset, row_range=row_range, fval=fval)
 
     @classmethod
     def from_cooler(cls, clr, device="cuda"):

@@ -181,6 +181,16 @@ typedef struct {
 int cb200_marginals_i64(const cb200_copy* copy, int32_t n_rows,
                         int64_t* nnz_out, int64_t* sum_out, int64_t* scratch, void* stream);
 
+/* Floating-point count columns (_init copies the column in its own dtype, src/cooler/_balance.py:25-26;
+ * every later product is float64).  The table is built with px[k].count = position of the pixel in the
+ * stored table, so filters, transposition and strip partition carry the values along as indices.
+ *   cb200_attach_values: val_out[k] = values[px[k].count] (0 when the index is outside [0, n_values)),
+ *     then px[k].count = k: the sweep reads val_out in stream order.
+ *   cb200_values_nonzero: out[i] = values[i] != 0 ? 1.0 : 0.0   (_binarize, _balance.py:29-31). */
+int cb200_attach_values(cb200_px* px, int64_t n, const double* values, int64_t n_values,
+                        double* val_out, void* stream);
+int cb200_values_nonzero(const double* values, int64_t n, double* out, void* stream);
+
 /* ---- ICE iteration (replaces the PASS C map-reduce + the O(n_bins) numpy
  *      update of _balance_genomewide/_cisonly/_transonly,
  *      src/cooler/_balance.py:72-260) ------------------------------------- */
@@ -197,6 +207,10 @@ typedef struct {
   int32_t  gather_len;
   int32_t  row_base;
   int32_t  row_count;
+  const double* val;         /* NULL: integer counts in px[k].count.  Floating-point count columns (cb200_ice.float_counts
+                                != 0): the pixel's value is val[px[k].count] -- px[k].count is an INDEX: k itself after
+                                cb200_attach_values (sweeps read val in stream order), or the pixel's position in the
+                                stored table while val is the raw column (prefilter marginals) */
 } cb200_sub;
 
 /* Far-field blocks (large, very sparse matrices: the gathered bias vector is far larger
@@ -275,6 +289,8 @@ typedef struct {
   int32_t  far_col_shift;             /* log2 C, 1..13; (rows + 2 C) * 8 B must fit the 227 KB of shared memory */
   int32_t  far_warps;                 /* 16: warps per CTA = row slices per block */
   int32_t  far_rec_bytes;             /* 8: cb200_px records; 4: compact records (cb200_far_finish4), every far copy alike */
+  int32_t  float_counts;              /* != 0: every sub-copy carries cb200_sub.val (float64 values, _balance.py:25-26 copies
+                                         whatever dtype the count column has); far-field blocks are not available then */
 } cb200_ice;
 
 /* Tuning of K3 (optional): ice_unroll in {0,1,2,4,8} = 128-bit stream loads kept in

@@ -27,6 +27,21 @@ def balance_golden():
     return _npz("balance_golden.npz"), meta
 
 
+def balance_float_golden():
+    with open(os.path.join(GOLD, "balance_float_golden.json")) as f:
+        meta = json.load(f)
+    return _npz("balance_float_golden.npz"), meta
+
+
+def float_counts(count, kind):
+    """Seeded floating-point value column derived from an integer count column: count x lognormal noise,
+    ~2 % exact zeros (stored zeros must not count as nonzero, _balance.py:29-31); ``kind`` f64 | f32."""
+    rng = np.random.default_rng(20240607)
+    v = count.astype(np.float64) * rng.lognormal(0.0, 0.3, len(count))
+    v[rng.random(len(count)) < 0.02] = 0.0
+    return v.astype(np.float32) if kind == "f32" else v
+
+
 def coarsen_golden():
     return _npz("coarsen_golden.npz")
 

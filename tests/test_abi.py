@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, s), s
         assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.cb200_abi_version() == 2
+    assert lib.cb200_abi_version() == 3
     assert lib.cb200_warp_tile() == 2048
     assert lib.cb200_scan_workspace_bytes(10_000_000) > 0
     assert lib.cb200_sort_workspace_bytes(10_000_000) > 0
@@ -45,17 +45,19 @@ def test_struct_layout_matches_header(tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(
         '#include <stdio.h>\n#include <stddef.h>\n#include "cooler_b200.h"\n'
-        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(cb200_copy), sizeof(cb200_ice),'
+        'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(cb200_copy), sizeof(cb200_ice),'
         ' offsetof(cb200_ice, n_bins), offsetof(cb200_ice, bias), offsetof(cb200_ice, tol),'
         ' offsetof(cb200_ice, max_iters), offsetof(cb200_ice, far_copies), offsetof(cb200_ice, far_warps),'
-        ' sizeof(cb200_far_copy), offsetof(cb200_far_copy, rb_unit), sizeof(cb200_far_unit), sizeof(cb200_sub));'
+        ' sizeof(cb200_far_copy), offsetof(cb200_far_copy, rb_unit), sizeof(cb200_far_unit), sizeof(cb200_sub),'
+        ' offsetof(cb200_sub, val), offsetof(cb200_ice, float_counts));'
         ' return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     want = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     got = [C.sizeof(_lib.Copy), C.sizeof(_lib.Ice), _lib.Ice.n_bins.offset, _lib.Ice.bias.offset,
            _lib.Ice.tol.offset, _lib.Ice.max_iters.offset, _lib.Ice.far_copies.offset, _lib.Ice.far_warps.offset,
-           C.sizeof(_lib.FarCopy), _lib.FarCopy.rb_unit.offset, C.sizeof(_lib.FarUnit), C.sizeof(_lib.Sub)]
+           C.sizeof(_lib.FarCopy), _lib.FarCopy.rb_unit.offset, C.sizeof(_lib.FarUnit), C.sizeof(_lib.Sub),
+           _lib.Sub.val.offset, _lib.Ice.float_counts.offset]
     assert got == want
 
 

@@ -76,6 +76,54 @@ def test_balance_matches_reference_golden(key):
         assert bias is kw["x0"]          # the reference mutates and returns x0 (_balance.py:368-370)
 
 
+FBAL, FMETA = _golden.balance_float_golden()
+
+
+@pytest.mark.parametrize("strip_bins", [None, 256])
+@pytest.mark.parametrize("key", sorted(FMETA))
+def test_balance_float_counts_match_reference_golden(key, strip_bins):
+    """Floating-point count columns (float64 / float32, stored zeros included) against the unmodified
+    reference: masks and pass counts identical, bias / scale / var within 1e-9.  ``strip_bins`` 256 forces
+    the column-strip kernel (value arrays attached per strip)."""
+    import cooler_b200
+    src, kind, _ = key.split("/")
+    t = dict(_golden.table_of(src))
+    t["count"] = _golden.float_counts(t["count"], kind)
+    kw = dict(FMETA[key]["kwargs"])
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        if strip_bins is None:                       # through the drop-in entry point
+            bias, stats = cooler_b200.balance_cooler(_mem_cooler(t), **kw)
+            passes = None
+        else:
+            chrom_offset, bin1_offset = _golden.offsets(t)
+            bias, stats, info = cooler_b200.balance_arrays(bin1_offset, t["bin2_id"], t["count"], chrom_offset,
+                                                           strip_bins=strip_bins, return_info=True, **kw)
+            assert info["strip_shift"] == 8 and info["n_subcopies"] > 2
+            passes = [p for p in info["passes"] if p]
+    warned = any(issubclass(x.category, cooler_b200.ConvergenceWarning) for x in w)
+    want = FBAL[key]
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    if passes is not None:
+        assert passes == [p for p in FMETA[key]["passes"] if p]
+    assert warned == FMETA[key]["warned"]
+    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
+    _check_stats(stats, FMETA[key]["stats"], kw.get("cis_only", False))
+
+
+def test_balance_float_counts_equal_integer_counts_when_integral():
+    """The same integers stored as float64 give the integer path's result (different kernels, same sums)."""
+    import cooler_b200
+    t = _golden.gm12878()
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    a, sa = cooler_b200.balance_arrays(bin1_offset, t["bin2_id"], t["count"], chrom_offset)
+    b, sb = cooler_b200.balance_arrays(bin1_offset, t["bin2_id"], t["count"].astype(np.float64), chrom_offset)
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_allclose(a, b, rtol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(a, BAL["gm/defaults"], rtol=RTOL, equal_nan=True)
+    assert sa["converged"] == sb["converged"]
+
+
 def _synthetic(seed, n_per_chrom, density):
     rng = np.random.default_rng(seed)
     n = int(sum(n_per_chrom))
@@ -118,6 +166,31 @@ def test_balance_matches_oracle_synthetic(mode, seed, n_per_chrom, density):
     np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
     np.testing.assert_allclose(np.atleast_1d(stats["var"]), np.atleast_1d(wstats["var"]), rtol=1e-9, equal_nan=True)
     np.testing.assert_allclose(np.atleast_1d(stats["scale"]), np.atleast_1d(wstats["scale"]), rtol=1e-9, equal_nan=True)
+
+
+@pytest.mark.parametrize("mode", ["gw", "cis", "trans"])
+def test_balance_float_counts_match_oracle_default_strips(mode):
+    """60 000 bins, float64 values: the automatic layout is column strips of 16 384 bins (the bias vector no
+    longer fits L1); compared with the oracle, which is bit-identical to the reference on float columns."""
+    import cooler_b200
+    from oracle import ice_numpy
+    b1, b2, cnt, chrom_offset = _synthetic(21, [30000, 20000, 10000], 0.008)
+    rng = np.random.default_rng(3)
+    val = cnt * rng.lognormal(0.0, 0.25, len(cnt))
+    val[rng.random(len(val)) < 0.01] = 0.0
+    n = int(chrom_offset[-1])
+    bin1_offset = np.searchsorted(b1, np.arange(n + 1)).astype(np.int64)
+    kw = dict(cis_only=(mode == "cis"), trans_only=(mode == "trans"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want, wstats, wpasses, _ = ice_numpy.balance_arrays(
+            dict(bin1_id=b1, bin2_id=b2, count=val), chrom_offset, bin1_offset, return_passes=True, **kw)
+        bias, stats, info = cooler_b200.balance_arrays(bin1_offset, b2, val, chrom_offset, return_info=True, **kw)
+    assert not info["band"] and (info["strip_shift"] == 14 or mode == "trans")   # few trans pixels: whole copies
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    assert info["passes"] == wpasses
+    np.testing.assert_allclose(bias, want, rtol=RTOL, atol=0, equal_nan=True)
+    np.testing.assert_allclose(np.atleast_1d(stats["var"]), np.atleast_1d(wstats["var"]), rtol=1e-9, equal_nan=True)
 
 
 def test_balance_is_deterministic():

@@ -43,6 +43,26 @@ def test_ice_oracle_bit_identical_to_reference(key):
     _stats_equal(stats, META[key]["stats"])
 
 
+FBAL, FMETA = _golden.balance_float_golden()
+
+
+@pytest.mark.parametrize("key", sorted(FMETA))
+def test_ice_oracle_float_counts_bit_identical_to_reference(key):
+    """Floating-point count columns (float64 and float32; _balance.py:25-26 copies the column's dtype)."""
+    src, kind, _ = key.split("/")
+    t = dict(_golden.table_of(src))
+    t["count"] = _golden.float_counts(t["count"], kind)
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    px = {k: t[k] for k in ("bin1_id", "bin2_id", "count")}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bias, stats, passes, warned = ice_numpy.balance_arrays(
+            px, chrom_offset, bin1_offset, return_passes=True, **FMETA[key]["kwargs"])
+    assert passes == FMETA[key]["passes"] and warned == FMETA[key]["warned"]
+    np.testing.assert_array_equal(bias, FBAL[key])
+    _stats_equal(stats, FMETA[key]["stats"])
+
+
 @pytest.mark.parametrize("chunksize", [None, 5000, 977])
 def test_ice_oracle_chunking_within_1e12(chunksize):
     t = _golden.gm12878()
