@@ -123,6 +123,8 @@ SIGNATURES = {
     "cb200_coarsen_remap": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
     "cb200_coarsen_maps": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "cb200_coarsen_merge_round": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "cb200_coarsen_merge_reduce": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
+    "cb200_coarsen_compact": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P]),
     "cb200_runs_count": (C.c_int, [_P, _P, _I64, _P, _P]),
     "cb200_runs_write": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P]),
     "cb200_runs_aggregate": (C.c_int, [_P, _P, _I64, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),

@@ -98,28 +98,44 @@ runs_write_kernel(const int32_t* __restrict__ keys, const int2* __restrict__ val
 // than the fine indptr and the first fine row of every coarse row is needed.
 //
 // One warp per (coarse row, pair), claimed dynamically.  The warp walks through the merged output
-// in chunks of 256 elements: it stages the next 256 elements of either list in shared memory
-// (coalesced loads; in round 0 the column ids are remapped on the fly), every lane finds the
-// start of its 8 outputs with a merge-path binary search in shared memory, merges them
-// sequentially (ties: the earlier list first, i.e. stable) and writes 64 contiguous bytes.
-constexpr int MG_VT = 8;                           // outputs per lane and chunk
-constexpr int MG_CHUNK = 32 * MG_VT;               // outputs per warp and chunk
+// in chunks of 32 * VT elements: it stages the next chunk of either list in shared memory (coalesced
+// loads; in round 0 the column ids are remapped on the fly), every lane finds the start of its VT
+// outputs with a merge-path binary search and merges them sequentially (ties: the earlier list
+// first, i.e. stable).  Keys and payloads are staged in separate 4-byte arrays and VT is odd: a
+// lane's accesses are VT (or about VT / 2) words apart from its neighbour's, which keeps shared-memory
+// bank conflicts low -- with 8-byte elements and VT = 8 the kernel was bound by the shared-memory
+// pipe (8- to 16-way conflicts on every merge step and on the staging of the outputs).
+//
+// kReduce (the LAST round, one pair per coarse row): adjacent equal coarse columns are summed on the
+// fly (int64) -- the reduce-by-key of `groupby(...).sum()` fused into the merge.  A lane closes a run
+// when it meets the next column; a run that continues from earlier lanes gets their open sum through
+// a warp-level segmented scan, a run that continues into the next chunk is carried in registers.
+// The reduced row g is written at the row's INPUT offset (it is never longer than the input) and its
+// length to row_count[g]; cb200_coarsen_compact then moves the rows to their final places.
 constexpr int MG_WARPS = 8;
+constexpr int MG_KEY_MAX = 0x7fffffff;
 
+template <int VT, bool kReduce>
 __global__ void __launch_bounds__(MG_WARPS * 32)
-coarsen_merge_round_kernel(const int2* __restrict__ in, int2* __restrict__ out,
-                           const int64_t* __restrict__ indptr, const int32_t* __restrict__ group_first,
-                           int n_groups, int round, int pairs_per_group,
-                           const int32_t* __restrict__ bin_map,      // round 0: column remap; else nullptr
-                           int32_t* __restrict__ key_out,            // last round: coarse row of every element; else nullptr
-                           unsigned long long* __restrict__ claim) {
-  __shared__ int2 sm[MG_WARPS][2][MG_CHUNK];
+coarsen_merge_kernel(const int2* __restrict__ in, int2* __restrict__ out,
+                     const int64_t* __restrict__ indptr, const int32_t* __restrict__ group_first,
+                     int n_groups, int round, int pairs_per_group,
+                     const int32_t* __restrict__ bin_map,      // round 0: column remap; else nullptr
+                     int32_t* __restrict__ key_out,            // coarse row of every output element, or nullptr
+                     int32_t* __restrict__ row_count,          // kReduce: outputs of every coarse row
+                     int32_t* __restrict__ overflow,           // kReduce: set when a sum leaves int32
+                     unsigned long long* __restrict__ claim) {
+  constexpr int NOUT = 32 * VT;                    // outputs per warp and chunk
+  __shared__ int32_t sm[MG_WARPS][4][NOUT];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int2* sA = sm[wid][0];
-  int2* sB = sm[wid][1];
+  int32_t* kA = sm[wid][0];
+  int32_t* vA = sm[wid][1];
+  int32_t* kB = sm[wid][2];
+  int32_t* vB = sm[wid][3];
   constexpr unsigned FULL = 0xffffffffu;
   const int64_t n_items = (int64_t)n_groups * pairs_per_group;
   const int span = 1 << round;                     // fine rows per list
+  int ovf = 0;
   while (true) {
     unsigned long long w = 0;
     if (lane == 0) w = atomicAdd(claim, 1ULL);
@@ -128,7 +144,10 @@ coarsen_merge_round_kernel(const int2* __restrict__ in, int2* __restrict__ out,
     const int g = (int)(w / pairs_per_group), q = (int)(w % pairs_per_group);
     const int g0 = group_first[g], g1 = group_first[g + 1];
     const int a0 = g0 + 2 * q * span;
-    if (a0 >= g1) continue;                        // this coarse row has fewer lists
+    if (a0 >= g1) {                                // this coarse row has fewer lists
+      if (kReduce && lane == 0) row_count[g] = 0;
+      continue;
+    }
     const int a1 = min(a0 + span, g1), a2 = min(a1 + span, g1);
     const int64_t pa = indptr[a0], pb = indptr[a1], pe = indptr[a2];
     const int na = (int)(pb - pa), nb = (int)(pe - pb);
@@ -136,70 +155,190 @@ coarsen_merge_round_kernel(const int2* __restrict__ in, int2* __restrict__ out,
     const int2* __restrict__ B = in + pb;
     int2* __restrict__ Y = out + pa;
     int i0 = 0, j0 = 0;
+    int obase = 0;                                 // elements of this item written so far
+    int ckey = 0;                                  // the run left open by the previous chunk
+    long long csum = 0;
+    bool cvalid = false;
     while (i0 + j0 < na + nb) {
-      const int la = min(MG_CHUNK, na - i0), lb = min(MG_CHUNK, nb - j0);
-      const int nout = min(MG_CHUNK, la + lb);
-      // 2 x 8 independent loads per lane in flight (a loop with a run-time bound would serialise the
-      // load -> remap-gather chains: measured 3.6 ms per 2e8 elements, latency-bound)
-      int2 va[MG_VT], vb[MG_VT];
+      const int la = min(NOUT, na - i0), lb = min(NOUT, nb - j0);
+      const int nout = min(NOUT, la + lb);
+      // 2 x VT independent loads per lane in flight (a loop with a run-time bound would serialise the
+      // load -> remap-gather chains)
+      int2 va[VT], vb[VT];
 #pragma unroll
-      for (int t = 0; t < MG_VT; ++t) {
+      for (int t = 0; t < VT; ++t) {
         const int k = lane + 32 * t;
         va[t] = (k < la) ? ld_stream_int2(A + i0 + k) : make_int2(0, 0);
         vb[t] = (k < lb) ? ld_stream_int2(B + j0 + k) : make_int2(0, 0);
       }
       if (bin_map) {
 #pragma unroll
-        for (int t = 0; t < MG_VT; ++t) {
+        for (int t = 0; t < VT; ++t) {
           va[t].x = __ldg(bin_map + va[t].x);      // (padding lanes read bin_map[0])
           vb[t].x = __ldg(bin_map + vb[t].x);
         }
       }
 #pragma unroll
-      for (int t = 0; t < MG_VT; ++t) {
+      for (int t = 0; t < VT; ++t) {
         const int k = lane + 32 * t;
-        if (k < la) sA[k] = va[t];
-        if (k < lb) sB[k] = vb[t];
+        if (k < la) { kA[k] = va[t].x; vA[k] = va[t].y; }
+        if (k < lb) { kB[k] = vb[t].x; vB[k] = vb[t].y; }
       }
       __syncwarp();
       // merge path: the split (ia, ib), ia + ib = d, with A[ia-1] <= B[ib] and B[ib-1] < A[ia]
-      const int d = min(lane * MG_VT, nout);
+      const int d = min(lane * VT, nout);
       int lo = max(0, d - lb), hi = min(d, la);
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (sA[mid].x <= sB[d - 1 - mid].x) lo = mid + 1; else hi = mid;
+        if (kA[mid] <= kB[d - 1 - mid]) lo = mid + 1; else hi = mid;
       }
       int ia = lo, ib = d - lo;
-      int2 e[MG_VT];
+      int ka = ia < la ? kA[ia] : MG_KEY_MAX, kb = ib < lb ? kB[ib] : MG_KEY_MAX;
+      int key[VT], val[VT];
 #pragma unroll
-      for (int v = 0; v < MG_VT; ++v) {
-        e[v] = make_int2(0, 0);
+      for (int v = 0; v < VT; ++v) {
+        key[v] = 0;
+        val[v] = 0;
         if (d + v < nout) {
-          const bool take_a = (ib >= lb) || (ia < la && sA[ia].x <= sB[ib].x);
-          e[v] = take_a ? sA[ia] : sB[ib];
+          const bool take_a = ka <= kb;            // an exhausted list shows MG_KEY_MAX; ties: A first
+          key[v] = take_a ? ka : kb;
+          val[v] = take_a ? vA[ia] : vB[ib];
           ia += take_a ? 1 : 0;
           ib += take_a ? 0 : 1;
-        }
-      }
-      __syncwarp();                                // every lane is done reading the staged lists
-      // the merged chunk goes through shared memory so that the warp writes 256 contiguous bytes per
-      // store (a lane writing its own 8 outputs touches 32 sectors per instruction)
-#pragma unroll
-      for (int v = 0; v < MG_VT; ++v)
-        if (d + v < nout) sA[d + v] = e[v];
-      __syncwarp();
-      const int64_t o = (int64_t)(i0 + j0);
-#pragma unroll
-      for (int t = 0; t < MG_VT; ++t) {
-        const int k = lane + 32 * t;
-        if (k < nout) {
-          Y[o + k] = sA[k];
-          if (key_out) key_out[pa + o + k] = g;
+          const int nxt = take_a ? ia : ib;        // only the consumed list shows a new head
+          const int nk = (nxt < (take_a ? la : lb)) ? (take_a ? kA : kB)[nxt] : MG_KEY_MAX;
+          ka = take_a ? nk : ka;
+          kb = take_a ? kb : nk;
         }
       }
       i0 += __shfl_sync(FULL, ia, 31);             // lane 31 ends at the split of diagonal nout
       j0 += __shfl_sync(FULL, ib, 31);
+      __syncwarp();                                // every lane is done reading the staged lists
+      // ---- close runs.  hm: bit v = element v starts a run (kReduce: its column differs from the
+      // previous element's; else every element).  A run is emitted by the lane that meets the NEXT head.
+      const int cnt = min(VT, nout - d);
+      int pk = __shfl_up_sync(FULL, key[VT - 1], 1);    // lane l has elements only if lane l-1 is full
+      const bool pvalid = lane > 0 || cvalid;
+      if (lane == 0) pk = ckey;
+      unsigned hm = 0;
+      long long open = 0;                          // sum behind the lane's last head (or of the whole lane)
+      int lastk = pk;
+      {
+        int prev = pk;
+        bool pv = pvalid;
+#pragma unroll
+        for (int v = 0; v < VT; ++v) {
+          if (v < cnt) {
+            const bool head = kReduce ? (!pv || key[v] != prev) : true;
+            if (head) { hm |= 1u << v; open = 0; }
+            open += val[v];
+            prev = key[v];
+            pv = true;
+          }
+        }
+        lastk = prev;
+      }
+      const bool has_head = hm != 0;
+      const int n_emit = __popc(hm) - (((hm & 1u) && !pvalid) ? 1 : 0);
+      if (lane == 0 && !has_head) open += csum;    // the whole lane continues the previous chunk's run
+      long long S = open;                          // inclusive segmented scan: open sum at the end of lane l
+      bool F = has_head;
+      int incl = n_emit;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const long long ts = __shfl_up_sync(FULL, S, o);
+        const int tf = __shfl_up_sync(FULL, (int)F, o);
+        const int tn = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) {
+          if (!F) S += ts;
+          F = F || (tf != 0);
+          incl += tn;
+        }
+      }
+      long long cin = __shfl_up_sync(FULL, S, 1);
+      if (lane == 0) cin = csum;
+      const int total = __shfl_sync(FULL, incl, 31);
+      {
+        int pos = incl - n_emit;
+        long long run = cin;
+        int prev = pk;
+        bool have = pvalid;
+#pragma unroll
+        for (int v = 0; v < VT; ++v) {
+          if (v < cnt) {
+            if ((hm >> v) & 1u) {
+              if (have) {
+                const int lo32 = (int)run;
+                if ((long long)lo32 != run) ovf = 1;
+                kA[pos] = prev;
+                vA[pos] = lo32;
+                ++pos;
+              }
+              run = 0;
+            }
+            run += val[v];
+            prev = key[v];
+            have = true;
+          }
+        }
+      }
+      csum = __shfl_sync(FULL, S, 31);
+      ckey = __shfl_sync(FULL, lastk, (nout - 1) / VT);
+      cvalid = true;
       __syncwarp();
+      // the closed runs leave through shared memory: the warp writes contiguous 256-byte rows
+#pragma unroll
+      for (int t = 0; t < VT; ++t) {
+        const int k = lane + 32 * t;
+        if (k < total) {
+          Y[obase + k] = make_int2(kA[k], vA[k]);
+          if (key_out) key_out[pa + obase + k] = g;
+        }
+      }
+      obase += total;
+      __syncwarp();
+    }
+    if (cvalid) {                                  // the last run of the item
+      if (lane == 0) {
+        const int lo32 = (int)csum;
+        if ((long long)lo32 != csum) ovf = 1;
+        Y[obase] = make_int2(ckey, lo32);
+        if (key_out) key_out[pa + obase] = g;
+      }
+      ++obase;
+    }
+    if (kReduce && lane == 0) row_count[g] = obase;
+  }
+  if (kReduce && ovf) *overflow = 1;
+}
+
+// Moves the reduced coarse rows (written at their input offsets by the kReduce round) to their final,
+// contiguous places: row g = new_indptr[g+1] - new_indptr[g] elements from in + indptr[group_first[g]].
+__global__ void __launch_bounds__(256)
+coarsen_compact_kernel(const int2* __restrict__ in, const int64_t* __restrict__ indptr,
+                       const int32_t* __restrict__ group_first, const int64_t* __restrict__ new_indptr,
+                       int n_groups, int2* __restrict__ out, int32_t* __restrict__ key_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g < n_groups; g += n_warps) {
+    const int2* __restrict__ src = in + indptr[group_first[g]];
+    const int64_t o0 = new_indptr[g];
+    const int n = (int)(new_indptr[g + 1] - o0);
+    for (int k0 = 0; k0 < n; k0 += 128) {
+      int2 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + lane + 32 * u;
+        v[u] = (k < n) ? ld_stream_int2(src + k) : make_int2(0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + lane + 32 * u;
+        if (k < n) {
+          out[o0 + k] = v[u];
+          if (key_out) key_out[o0 + k] = (int)g;
+        }
+      }
     }
   }
 }
@@ -295,7 +434,36 @@ __global__ void unpack_pixels_kernel(const int32_t* __restrict__ bin1, const int
 
 using namespace cb200;
 
+// outputs per lane and chunk of the merge kernel: 7 (measured on the 10 kb table, factor 2 / 5: VT 5: 1.68 / 1.05 ms,
+// 7: 1.59 / 0.96, 9: 1.65 / 1.00, 11: 1.85 / 1.18 for the fused round; profiles/r02d_profile_coarsen_fused_10kb.log)
+constexpr int MG_VT = 7;
+
+template <bool kReduce>
+static int launch_merge(const cb200_px* in, cb200_px* out, const int64_t* indptr, const int32_t* group_first,
+                        int32_t n_groups, int32_t round, int32_t pairs_per_group, const int32_t* bin_map,
+                        int32_t* key_out, int32_t* row_count, int32_t* overflow, int64_t* claim, void* stream) {
+  if (n_groups <= 0 || pairs_per_group <= 0) return 0;
+  if (round < 0 || round > 30) {
+    set_error_msg("coarsen_merge: bad round");
+    return -1;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  CB_CHECK(cudaMemsetAsync(claim, 0, sizeof(int64_t), s));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t items = (int64_t)n_groups * pairs_per_group;
+  int64_t blocks = ceil_div64(items, MG_WARPS);
+  if (blocks > (int64_t)sms * 6) blocks = (int64_t)sms * 6;      // up to 48 warps per SM claim the pairs dynamically
+  coarsen_merge_kernel<MG_VT, kReduce><<<(unsigned)blocks, MG_WARPS * 32, 0, s>>>(
+      reinterpret_cast<const int2*>(in), reinterpret_cast<int2*>(out), indptr, group_first, n_groups, round,
+      pairs_per_group, bin_map, key_out, row_count, overflow, reinterpret_cast<unsigned long long*>(claim));
+  CB_LAUNCH_CHECK("coarsen_merge");
+  return 0;
+}
+
 extern "C" {
+
 
 int cb200_coarsen_remap(const cb200_copy* csr, int32_t n_rows, const int32_t* bin_map,
                         int32_t* key_out, cb200_px* val_out, void* stream) {
@@ -328,23 +496,28 @@ int cb200_coarsen_merge_round(const cb200_px* in, cb200_px* out, const int64_t* 
                               const int32_t* group_first, int32_t n_groups, int32_t round,
                               int32_t pairs_per_group, const int32_t* bin_map, int32_t* key_out,
                               int64_t* claim, void* stream) {
-  if (n_groups <= 0 || pairs_per_group <= 0) return 0;
-  if (round < 0 || round > 30) {
-    set_error_msg("coarsen_merge_round: bad round");
-    return -1;
-  }
-  cudaStream_t s = (cudaStream_t)stream;
-  CB_CHECK(cudaMemsetAsync(claim, 0, sizeof(int64_t), s));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int64_t items = (int64_t)n_groups * pairs_per_group;
-  int64_t blocks = ceil_div64(items, MG_WARPS);
-  if (blocks > (int64_t)sms * 6) blocks = (int64_t)sms * 6;      // 48 warps per SM claim the pairs dynamically
-  coarsen_merge_round_kernel<<<(unsigned)blocks, MG_WARPS * 32, 0, s>>>(
-      reinterpret_cast<const int2*>(in), reinterpret_cast<int2*>(out), indptr, group_first, n_groups, round,
-      pairs_per_group, bin_map, key_out, reinterpret_cast<unsigned long long*>(claim));
-  CB_LAUNCH_CHECK("coarsen_merge_round");
+  return launch_merge<false>(in, out, indptr, group_first, n_groups, round, pairs_per_group, bin_map, key_out,
+                             nullptr, nullptr, claim, stream);
+}
+
+int cb200_coarsen_merge_reduce(const cb200_px* in, cb200_px* out, const int64_t* indptr,
+                               const int32_t* group_first, int32_t n_groups, int32_t round,
+                               const int32_t* bin_map, int32_t* row_count, int32_t* overflow,
+                               int64_t* claim, void* stream) {
+  return launch_merge<true>(in, out, indptr, group_first, n_groups, round, 1, bin_map, nullptr, row_count,
+                            overflow, claim, stream);
+}
+
+int cb200_coarsen_compact(const cb200_px* in, const int64_t* indptr, const int32_t* group_first,
+                          const int64_t* new_indptr, int32_t n_groups, cb200_px* out, int32_t* key_out,
+                          void* stream) {
+  if (n_groups <= 0) return 0;
+  int64_t blocks = ceil_div64(n_groups, 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  coarsen_compact_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const int2*>(in), indptr, group_first, new_indptr, n_groups,
+      reinterpret_cast<int2*>(out), key_out);
+  CB_LAUNCH_CHECK("coarsen_compact");
   return 0;
 }
 

@@ -162,17 +162,15 @@ def align_rows_to_factor(chrom_offset, factor, row):
 # --------------------------------------------------------------------------
 # device path
 # --------------------------------------------------------------------------
-def _merge_coarse_rows(table: PixelTable, factor: int):
-    """The merge part of K5: returns (keys = coarse row of every pixel, vals = {coarse column,
-    payload} sorted by (coarse row, coarse column) with equal pairs adjacent in pixel order,
-    n_new, new chrom_offset).  The payload is whatever the table's raw copy carries as "count"."""
+def _coarse_maps(table: PixelTable, factor: int):
+    """Device bin maps of one coarsening step: (bin_map, group_first, n_new, new chrom_offset, number of
+    merge rounds, largest number of fine rows per coarse row)."""
     factor = int(factor)
     assert factor > 1
     dev = _use_device(table.device)
     csr = table.raw
     new_off = coarsen_chrom_offset(table.chrom_offset, factor)
     n_new = int(new_off[-1])
-    n = csr.nnz
     if csr.row_base != 0 or csr.n_rows != table.n_bins:
         raise ValueError("coarsen_table needs the whole-row-range raw copy of the table")
     # old bin -> new bin and the first old bin of every new bin, on the device (closed forms)
@@ -185,18 +183,38 @@ def _merge_coarse_rows(table: PixelTable, factor: int):
     nb = np.diff(table.chrom_offset)
     max_group = int(min(factor, nb.max())) if len(nb) and nb.max() > 0 else 1
     rounds = max(1, int(max_group - 1).bit_length())
+    return bin_map_d, group_first_d, n_new, new_off, rounds, max_group
+
+
+def _merge_rounds(csr, maps, n_rounds, keys=None):
+    """Rounds 0 .. n_rounds-1 of the pairwise merges (no reduction); returns the buffer holding the result
+    (the input copy's own pixels when n_rounds == 0).  ``keys``: filled with the coarse row of every
+    element by the last round run here."""
+    bin_map_d, group_first_d, n_new, _, _, max_group = maps
+    dev = csr.px.device
+    n = csr.nnz
     claim = torch.zeros(1, dtype=_I64, device=dev)
-    keys = torch.empty(max(n, 1), dtype=_I32, device=dev)
-    bufs = [torch.empty((n + 2, 2), dtype=_I32, device=dev) for _ in range(min(rounds, 2))]
+    bufs = [torch.empty((n + 2, 2), dtype=_I32, device=dev) for _ in range(min(n_rounds, 2))]
     src = csr.px
-    for r in range(rounds):
+    for r in range(n_rounds):
         dst = bufs[r % 2]
         lists = -(-max_group // (1 << r))
         _lib.call("cb200_coarsen_merge_round", _ptr(src), _ptr(dst), _ptr(csr.indptr), _ptr(group_first_d),
                   n_new, r, -(-lists // 2), _ptr(bin_map_d) if r == 0 else C.c_void_p(0),
-                  _ptr(keys) if r == rounds - 1 else C.c_void_p(0), _ptr(claim), _stream())
+                  _ptr(keys) if (keys is not None and r == n_rounds - 1) else C.c_void_p(0), _ptr(claim), _stream())
         src = dst
-    return keys, src, n_new, new_off
+    return src
+
+
+def _merge_coarse_rows(table: PixelTable, factor: int):
+    """The merge part of K5 without the reduction (general aggregators): returns (keys = coarse row of every
+    pixel, vals = {coarse column, payload} sorted by (coarse row, coarse column) with equal pairs adjacent in
+    pixel order, n_new, new chrom_offset).  The payload is whatever the table's raw copy carries as "count"."""
+    maps = _coarse_maps(table, factor)
+    csr = table.raw
+    keys = torch.empty(max(csr.nnz, 1), dtype=_I32, device=csr.px.device)
+    vals = _merge_rounds(csr, maps, maps[4], keys=keys)
+    return keys, vals, maps[2], maps[3]
 
 
 def coarsen_table(table: PixelTable, factor: int):
@@ -207,16 +225,31 @@ def coarsen_table(table: PixelTable, factor: int):
 
     No global sort: the fine rows of a coarse row are already sorted by the (monotone) coarse
     column, so the coarse row is their multi-way merge -- ceil(log2(rows per coarse row)) rounds of
-    pairwise merge-path merges (``cb200_coarsen_merge_round``), then one reduce-by-key over
-    adjacent equal (bin1', bin2')."""
+    pairwise merge-path merges; the LAST round sums adjacent equal (bin1', bin2') on the fly
+    (``cb200_coarsen_merge_reduce``) and writes every reduced row at its input offset, a scan of the
+    row lengths is the new row pointer, and ``cb200_coarsen_compact`` moves the rows into place."""
     dev = table.device
-    n = table.raw.nnz
-    keys, vals, n_new, new_off = _merge_coarse_rows(table, factor)
-    k2, v2, n_out, overflow = _reduce_runs(keys, vals, n, 0, dev)
-    del keys, vals
+    csr = table.raw
+    n = csr.nnz
+    maps = _coarse_maps(table, factor)
+    bin_map_d, group_first_d, n_new, new_off, rounds, _ = maps
+    src = _merge_rounds(csr, maps, rounds - 1)
+    tmp = torch.empty((n + 2, 2), dtype=_I32, device=dev)
+    row_count = torch.zeros(max(n_new, 1), dtype=_I32, device=dev)
+    overflow = torch.zeros(1, dtype=_I32, device=dev)
+    claim = torch.zeros(1, dtype=_I64, device=dev)
+    _lib.call("cb200_coarsen_merge_reduce", _ptr(src), _ptr(tmp), _ptr(csr.indptr), _ptr(group_first_d), n_new,
+              rounds - 1, _ptr(bin_map_d) if rounds == 1 else C.c_void_p(0), _ptr(row_count), _ptr(overflow),
+              _ptr(claim), _stream())
+    del src
+    indptr = exclusive_scan_i32(row_count[:n_new])            # the new row pointer
+    n_out = int(indptr[-1].item())
+    k2 = torch.empty(max(n_out, 1), dtype=_I32, device=dev)
+    v2 = torch.empty((n_out + 2, 2), dtype=_I32, device=dev)
+    _lib.call("cb200_coarsen_compact", _ptr(tmp), _ptr(csr.indptr), _ptr(group_first_d), _ptr(indptr), n_new,
+              _ptr(v2), _ptr(k2), _stream())
     if int(overflow.item()):
         raise OverflowError("coarsened count does not fit int32")
-    indptr = indptr_from_sorted(k2, n_out, n_new)
     new_raw = TableCopy(v2, indptr, n_out, n_new)
     return PixelTable(new_raw, new_off), k2[:n_out]
 

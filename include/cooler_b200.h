@@ -354,6 +354,18 @@ int cb200_coarsen_merge_round(const cb200_px* in, cb200_px* out, const int64_t* 
                               const int32_t* group_first, int32_t n_groups, int32_t round,
                               int32_t pairs_per_group, const int32_t* bin_map, int32_t* key_out,
                               int64_t* claim, void* stream);
+/* The LAST merge round with the reduce-by-key of groupby(...).sum() (src/cooler/_reduce.py:616-620) fused
+ * in: the two remaining lists of every coarse row are merged and adjacent equal coarse columns summed
+ * (int64; *overflow = 1 if a sum leaves int32).  The reduced row g lands at out + indptr[group_first[g]]
+ * (its input offset) and its length in row_count[g]; an exclusive scan of row_count is the new row
+ * pointer and cb200_coarsen_compact moves the rows there (key_out, if not NULL: coarse row per element). */
+int cb200_coarsen_merge_reduce(const cb200_px* in, cb200_px* out, const int64_t* indptr,
+                               const int32_t* group_first, int32_t n_groups, int32_t round,
+                               const int32_t* bin_map, int32_t* row_count, int32_t* overflow,
+                               int64_t* claim, void* stream);
+int cb200_coarsen_compact(const cb200_px* in, const int64_t* indptr, const int32_t* group_first,
+                          const int64_t* new_indptr, int32_t n_groups, cb200_px* out, int32_t* key_out,
+                          void* stream);
 /* Reduce-by-key over a stream sorted so that equal (key, val.other) pairs are
  * adjacent.  Pass 1 counts run heads per tile of cb200_warp_tile() elements. */
 int cb200_runs_count(const int32_t* keys, const cb200_px* vals, int64_t n,

@@ -1,25 +1,33 @@
-"""Stage timings of the merge form of K5 (cooler_b200.reduce.coarsen_table) on a resident
-synthetic table:  python tools/profile_coarsen.py <binsize> <nnz> <factor>"""
+"""Stage timings of K5 (cooler_b200.reduce.coarsen_table: merge rounds, fused merge + reduce, scan,
+compaction) on a resident synthetic table, for several chunk widths of the merge kernel, each checked
+bit for bit against the unfused path (merge rounds -> runs_count -> runs_write):
+
+    python tools/profile_coarsen.py <binsize> <nnz> <factor> [factor ...]
+"""
 import ctypes as C
+import json
 import os
 import sys
 import time
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import cooler_b200  # noqa: E402
 from cooler_b200 import _lib, synth  # noqa: E402
+from cooler_b200 import reduce as R  # noqa: E402
 from cooler_b200 import table as T  # noqa: E402
-from cooler_b200.reduce import coarsen_bin_map, coarsen_table  # noqa: E402
 
-binsize, target, factor = int(sys.argv[1]), int(float(sys.argv[2])), int(sys.argv[3])
+binsize, target = int(sys.argv[1]), int(float(sys.argv[2]))
+factors = [int(x) for x in sys.argv[3:]]
+VTS = [int(x) for x in os.environ.get("VTS", "7").split(",")]
 plan = synth.SynthPlan(binsize, target, seed=0)
 data = synth.generate(plan)
 tab = cooler_b200.PixelTable.from_arrays(data["bin1_offset"], data["bin2_id"], data["count"], data["chrom_offset"])
 dev = tab.device
+lib = _lib.load()
+PEAK = 6536.7
 
 
 class Tm:
@@ -34,51 +42,61 @@ class Tm:
         self._l, self._n = now, name
 
 
-for rep in range(3):
-    tm = Tm()
-    tm("setup")
-    csr = tab.raw
-    bin_map, new_off = coarsen_bin_map(tab.chrom_offset, factor)
-    n_new = int(new_off[-1])
-    n = csr.nnz
-    gf = np.searchsorted(bin_map, np.arange(n_new + 1), side="left").astype(np.int32)
-    mg = int(np.diff(gf).max())
-    rounds = max(1, int(mg - 1).bit_length())
-    bm = torch.from_numpy(bin_map).to(dev)
-    gfd = torch.from_numpy(gf).to(dev)
-    claim = torch.zeros(1, dtype=torch.int64, device=dev)
-    keys = torch.empty(n, dtype=torch.int32, device=dev)
-    bufs = [torch.empty((n + 2, 2), dtype=torch.int32, device=dev) for _ in range(min(rounds, 2))]
-    src = csr.px
-    for r in range(rounds):
-        tm(f"merge_round_{r}")
-        dst = bufs[r % 2]
-        lists = -(-mg // (1 << r))
-        _lib.call("cb200_coarsen_merge_round", T._ptr(src), T._ptr(dst), T._ptr(csr.indptr), T._ptr(gfd), n_new, r,
-                  -(-lists // 2), T._ptr(bm) if r == 0 else C.c_void_p(0),
-                  T._ptr(keys) if r == rounds - 1 else C.c_void_p(0), T._ptr(claim), T._stream())
-        src = dst
-    tm("runs_count+scan")
-    nt = T.n_tiles(n)
-    tc = torch.zeros(nt, dtype=torch.int32, device=dev)
-    _lib.call("cb200_runs_count", T._ptr(keys), T._ptr(src), n, T._ptr(tc), T._stream())
-    toff = T.exclusive_scan_i32(tc)
-    n_out = int(toff[-1].item())
-    tm("runs_write")
-    k2 = torch.empty(n_out, dtype=torch.int32, device=dev)
-    v2 = torch.empty((n_out + 2, 2), dtype=torch.int32, device=dev)
-    ov = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.call("cb200_runs_write", T._ptr(keys), T._ptr(src), n, T._ptr(toff), 0, T._ptr(k2), T._ptr(v2),
-              C.c_void_p(0), T._ptr(ov), T._stream())
-    tm("indptr")
-    ind = T.indptr_from_sorted(k2, n_out, n_new)
-    tm("end")
-    if rep:
-        print(n, n_out, "rounds", rounds, {k: round(v * 1e3, 2) for k, v in tm.t.items()}, flush=True)
-    del keys, bufs, src, k2, v2
-coarsen_table(tab, factor)
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-new, ids = coarsen_table(tab, factor)
-torch.cuda.synchronize()
-print("coarsen_table wall ms", (time.perf_counter() - t0) * 1e3)
+def unfused(table, factor):
+    keys, vals, n_new, new_off = R._merge_coarse_rows(table, factor)
+    k2, v2, n_out, _ = R._reduce_runs(keys, vals, table.raw.nnz, 0, dev)
+    return k2[:n_out].clone(), v2[:n_out].clone()
+
+
+out = []
+for factor in factors:
+    want_k, want_v = unfused(tab, factor)
+    for vt in VTS:
+        if hasattr(lib, "cb200_dev_set_merge_vt"):
+            lib.cb200_dev_set_merge_vt(vt)
+        for rep in range(3):
+            tm = Tm()
+            tm("maps")
+            csr = tab.raw
+            n = csr.nnz
+            maps = R._coarse_maps(tab, factor)
+            bin_map_d, group_first_d, n_new, new_off, rounds, _ = maps
+            tm("merge_rounds")
+            src = R._merge_rounds(csr, maps, rounds - 1)
+            tm("alloc")
+            tmp = torch.empty((n + 2, 2), dtype=torch.int32, device=dev)
+            row_count = torch.zeros(n_new, dtype=torch.int32, device=dev)
+            ov = torch.zeros(1, dtype=torch.int32, device=dev)
+            claim = torch.zeros(1, dtype=torch.int64, device=dev)
+            tm("merge_reduce")
+            _lib.call("cb200_coarsen_merge_reduce", T._ptr(src), T._ptr(tmp), T._ptr(csr.indptr), T._ptr(group_first_d),
+                      n_new, rounds - 1, T._ptr(bin_map_d) if rounds == 1 else C.c_void_p(0), T._ptr(row_count),
+                      T._ptr(ov), T._ptr(claim), T._stream())
+            tm("scan")
+            indptr = T.exclusive_scan_i32(row_count)
+            n_out = int(indptr[-1].item())
+            tm("compact")
+            k2 = torch.empty(n_out, dtype=torch.int32, device=dev)
+            v2 = torch.empty((n_out + 2, 2), dtype=torch.int32, device=dev)
+            _lib.call("cb200_coarsen_compact", T._ptr(tmp), T._ptr(csr.indptr), T._ptr(group_first_d), T._ptr(indptr),
+                      n_new, T._ptr(v2), T._ptr(k2), T._stream())
+            tm("end")
+        ok = bool(n_out == want_k.numel() and torch.equal(k2, want_k) and torch.equal(v2[:n_out], want_v))
+        R.coarsen_table(tab, factor)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        new, ids = R.coarsen_table(tab, factor)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        algo = 12 * (n + n_out)
+        rec = {"factor": factor, "vt": vt, "nnz_in": n, "nnz_out": n_out, "rounds": rounds, "equal_to_unfused": ok,
+               "stages_ms": {k: round(v * 1e3, 3) for k, v in tm.t.items()}, "coarsen_table_ms": ms,
+               "algorithmic_GBps": algo / ms / 1e6, "frac_of_measured_hbm": algo / ms / 1e6 / PEAK}
+        print(json.dumps(rec), flush=True)
+        out.append(rec)
+        del tmp, k2, v2, src
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+with open(os.path.join(ROOT, "gpurun_out", "profile_coarsen.json"), "w") as f:
+    json.dump(out, f, indent=1)
