@@ -64,6 +64,12 @@ class FarCopy(C.Structure):
                 ("rb_unit", C.c_void_p)]
 
 
+class Remap(C.Structure):
+    """cb200_remap"""
+    _fields_ = [("bin_map", C.c_void_p), ("blocks", C.c_void_p), ("block_shift", C.c_int32),
+                ("magic", C.c_uint32), ("magic_shift", C.c_int32)]
+
+
 class FarUnit(C.Structure):
     """cb200_far_unit"""
     _fields_ = [("copy", C.c_int32), ("rb", C.c_int32), ("t0", C.c_int32), ("t1", C.c_int32)]
@@ -122,8 +128,9 @@ SIGNATURES = {
     "cb200_fetch_balance_coo": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I32, _P, _P]),
     "cb200_coarsen_remap": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
     "cb200_coarsen_maps": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
-    "cb200_coarsen_merge_round": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
-    "cb200_coarsen_merge_reduce": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P]),
+    "cb200_coarsen_block_table": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P]),
+    "cb200_coarsen_merge_round": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, C.POINTER(Remap), _P, _P, _P]),
+    "cb200_coarsen_merge_reduce": (C.c_int, [_P, _P, _P, _P, _I32, _I32, C.POINTER(Remap), _P, _P, _P, _P]),
     "cb200_coarsen_compact": (C.c_int, [_P, _P, _P, _P, _I32, _P, _P, _P]),
     "cb200_runs_count": (C.c_int, [_P, _P, _I64, _P, _P]),
     "cb200_runs_write": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _P, _P, _P]),

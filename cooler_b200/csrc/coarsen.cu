@@ -115,12 +115,33 @@ runs_write_kernel(const int32_t* __restrict__ keys, const int2* __restrict__ val
 constexpr int MG_WARPS = 8;
 constexpr int MG_KEY_MAX = 0x7fffffff;
 
+// Column remap of round 0.  A gather from the full bin_map costs one L1 tag lookup per lane (the columns
+// of a row are spread over the whole genome: ~20 distinct lines per warp load, which made the gathers
+// 90 % of the kernel's L1 requests).  The map is piecewise arithmetic, new = (col + pad[chromosome]) / factor
+// with pad = new_off * factor - off, so a table with one entry per BLOCK of 2^shift bins -- {first chromosome
+// boundary inside the block or INT_MAX, pad before it, pad behind it} -- answers it from a few cached
+// lines; blocks holding several boundaries (tiny scaffolds) are marked and fall back to the gather.
+struct RemapFn {
+  const int32_t* __restrict__ bin_map;
+  const int4* __restrict__ blocks;                 // nullptr: always gather
+  int shift;
+  unsigned magic;
+  int mshift;
+  __device__ __forceinline__ int operator()(int x) const {
+    if (blocks == nullptr) return __ldg(bin_map + x);
+    const int4 e = __ldg(blocks + (x >> shift));
+    if (e.x < 0) return __ldg(bin_map + x);
+    const unsigned y = (unsigned)x + (unsigned)(x >= e.x ? e.z : e.y);
+    return (int)(__umulhi(y, magic) >> mshift);    // y / factor, exact for y < 2^31
+  }
+};
+
 template <int VT, bool kReduce>
-__global__ void __launch_bounds__(MG_WARPS * 32)
+__global__ void __launch_bounds__(MG_WARPS * 32, 4)
 coarsen_merge_kernel(const int2* __restrict__ in, int2* __restrict__ out,
                      const int64_t* __restrict__ indptr, const int32_t* __restrict__ group_first,
                      int n_groups, int round, int pairs_per_group,
-                     const int32_t* __restrict__ bin_map,      // round 0: column remap; else nullptr
+                     const bool do_remap, const RemapFn remap,  // round 0: column remap
                      int32_t* __restrict__ key_out,            // coarse row of every output element, or nullptr
                      int32_t* __restrict__ row_count,          // kReduce: outputs of every coarse row
                      int32_t* __restrict__ overflow,           // kReduce: set when a sum leaves int32
@@ -171,11 +192,11 @@ coarsen_merge_kernel(const int2* __restrict__ in, int2* __restrict__ out,
         va[t] = (k < la) ? ld_stream_int2(A + i0 + k) : make_int2(0, 0);
         vb[t] = (k < lb) ? ld_stream_int2(B + j0 + k) : make_int2(0, 0);
       }
-      if (bin_map) {
+      if (do_remap) {
 #pragma unroll
         for (int t = 0; t < VT; ++t) {
-          va[t].x = __ldg(bin_map + va[t].x);      // (padding lanes read bin_map[0])
-          vb[t].x = __ldg(bin_map + vb[t].x);
+          va[t].x = remap(va[t].x);                // (padding lanes remap column 0)
+          vb[t].x = remap(vb[t].x);
         }
       }
 #pragma unroll
@@ -372,6 +393,34 @@ __global__ void coarsen_maps_kernel(const int64_t* __restrict__ off, const int64
   }
 }
 
+// Block table of RemapFn: entry b describes the bins [b << shift, (b + 1) << shift).
+__global__ void coarsen_block_table_kernel(const int64_t* __restrict__ off, const int64_t* __restrict__ new_off,
+                                           int n_chroms, int factor, int n_bins, int shift, int n_blocks,
+                                           int4* __restrict__ blocks) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  const int64_t i0 = (int64_t)b << shift;
+  const int64_t end = min(i0 + ((int64_t)1 << shift), (int64_t)n_bins);
+  auto chrom_of = [&](int64_t i) {                 // largest c with off[c] <= i: the non-empty chromosome holding bin i
+    int lo = 0, hi = n_chroms;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+  };
+  const int c0 = chrom_of(i0);
+  const int pad0 = (int)(new_off[c0] * factor - off[c0]);
+  const int64_t bnd = off[c0 + 1];
+  int4 e = make_int4(0x7fffffff, pad0, pad0, 0);
+  if (bnd < end) {
+    const int c1 = chrom_of(bnd);
+    if (off[c1 + 1] < end) e = make_int4(-1, 0, 0, 0);          // a second boundary: gather instead
+    else e = make_int4((int)bnd, pad0, (int)(new_off[c1] * factor - off[c1]), 0);
+  }
+  blocks[b] = e;
+}
+
 // Generic aggregation of one value column over the runs of equal (key, other) of a sorted stream
 // whose vals are {other, index into the source column}: what `groupby([bin1_id, bin2_id],
 // sort=True).aggregate({col: agg})` of CoolerCoarsener._aggregate (_reduce.py:616-620) computes for
@@ -440,7 +489,7 @@ constexpr int MG_VT = 7;
 
 template <bool kReduce>
 static int launch_merge(const cb200_px* in, cb200_px* out, const int64_t* indptr, const int32_t* group_first,
-                        int32_t n_groups, int32_t round, int32_t pairs_per_group, const int32_t* bin_map,
+                        int32_t n_groups, int32_t round, int32_t pairs_per_group, const cb200_remap* rm,
                         int32_t* key_out, int32_t* row_count, int32_t* overflow, int64_t* claim, void* stream) {
   if (n_groups <= 0 || pairs_per_group <= 0) return 0;
   if (round < 0 || round > 30) {
@@ -455,9 +504,19 @@ static int launch_merge(const cb200_px* in, cb200_px* out, const int64_t* indptr
   const int64_t items = (int64_t)n_groups * pairs_per_group;
   int64_t blocks = ceil_div64(items, MG_WARPS);
   if (blocks > (int64_t)sms * 6) blocks = (int64_t)sms * 6;      // up to 48 warps per SM claim the pairs dynamically
+  RemapFn fn{nullptr, nullptr, 0, 0u, 0};
+  if (rm) {
+    if (rm->bin_map == nullptr || (rm->blocks != nullptr && (rm->block_shift < 0 || rm->block_shift > 30 ||
+                                                             rm->magic_shift < 0 || rm->magic_shift > 31))) {
+      set_error_msg("coarsen_merge: bad remap descriptor");
+      return -1;
+    }
+    fn = RemapFn{rm->bin_map, reinterpret_cast<const int4*>(rm->blocks), rm->block_shift, rm->magic, rm->magic_shift};
+  }
   coarsen_merge_kernel<MG_VT, kReduce><<<(unsigned)blocks, MG_WARPS * 32, 0, s>>>(
       reinterpret_cast<const int2*>(in), reinterpret_cast<int2*>(out), indptr, group_first, n_groups, round,
-      pairs_per_group, bin_map, key_out, row_count, overflow, reinterpret_cast<unsigned long long*>(claim));
+      pairs_per_group, rm != nullptr, fn, key_out, row_count, overflow,
+      reinterpret_cast<unsigned long long*>(claim));
   CB_LAUNCH_CHECK("coarsen_merge");
   return 0;
 }
@@ -492,19 +551,35 @@ int cb200_coarsen_maps(const int64_t* chrom_offset, const int64_t* new_chrom_off
   return 0;
 }
 
+int cb200_coarsen_block_table(const int64_t* chrom_offset, const int64_t* new_chrom_offset, int32_t n_chroms,
+                              int32_t factor, int32_t n_bins, int32_t block_shift, int32_t* blocks_out,
+                              void* stream) {
+  if (n_chroms <= 0 || factor <= 0 || block_shift < 0 || block_shift > 30) {
+    set_error_msg("coarsen_block_table: bad arguments");
+    return -1;
+  }
+  if (n_bins <= 0) return 0;
+  const int n_blocks = (int)(((int64_t)n_bins - 1) >> block_shift) + 1;
+  coarsen_block_table_kernel<<<(unsigned)ceil_div64(n_blocks, 128), 128, 0, (cudaStream_t)stream>>>(
+      chrom_offset, new_chrom_offset, n_chroms, factor, n_bins, block_shift, n_blocks,
+      reinterpret_cast<int4*>(blocks_out));
+  CB_LAUNCH_CHECK("coarsen_block_table");
+  return 0;
+}
+
 int cb200_coarsen_merge_round(const cb200_px* in, cb200_px* out, const int64_t* indptr,
                               const int32_t* group_first, int32_t n_groups, int32_t round,
-                              int32_t pairs_per_group, const int32_t* bin_map, int32_t* key_out,
+                              int32_t pairs_per_group, const cb200_remap* remap, int32_t* key_out,
                               int64_t* claim, void* stream) {
-  return launch_merge<false>(in, out, indptr, group_first, n_groups, round, pairs_per_group, bin_map, key_out,
+  return launch_merge<false>(in, out, indptr, group_first, n_groups, round, pairs_per_group, remap, key_out,
                              nullptr, nullptr, claim, stream);
 }
 
 int cb200_coarsen_merge_reduce(const cb200_px* in, cb200_px* out, const int64_t* indptr,
                                const int32_t* group_first, int32_t n_groups, int32_t round,
-                               const int32_t* bin_map, int32_t* row_count, int32_t* overflow,
+                               const cb200_remap* remap, int32_t* row_count, int32_t* overflow,
                                int64_t* claim, void* stream) {
-  return launch_merge<true>(in, out, indptr, group_first, n_groups, round, 1, bin_map, nullptr, row_count,
+  return launch_merge<true>(in, out, indptr, group_first, n_groups, round, 1, remap, nullptr, row_count,
                             overflow, claim, stream);
 }
 

@@ -183,14 +183,27 @@ def _coarse_maps(table: PixelTable, factor: int):
     nb = np.diff(table.chrom_offset)
     max_group = int(min(factor, nb.max())) if len(nb) and nb.max() > 0 else 1
     rounds = max(1, int(max_group - 1).bit_length())
-    return bin_map_d, group_first_d, n_new, new_off, rounds, max_group
+    # column remap of round 0 (cb200_remap): block table + division by multiplication when it applies
+    remap = _lib.Remap()
+    remap.bin_map = bin_map_d.data_ptr()
+    if table.n_bins > 0 and n_new * factor < 2**31:
+        shift = max(4, int((table.n_bins - 1) >> 11).bit_length())        # <= 2048 blocks: the table stays in L1
+        n_blocks = ((table.n_bins - 1) >> shift) + 1
+        blocks_d = torch.empty((n_blocks, 4), dtype=_I32, device=dev)
+        _lib.call("cb200_coarsen_block_table", _ptr(offs[0]), _ptr(offs[1]), n_chroms, factor, table.n_bins, shift,
+                  _ptr(blocks_d), _stream())
+        lg = int(factor - 1).bit_length()
+        remap.blocks, remap.block_shift = blocks_d.data_ptr(), shift
+        remap.magic, remap.magic_shift = -(-(1 << (31 + lg)) // factor), lg - 1
+        remap._keep = (bin_map_d, blocks_d)
+    return bin_map_d, group_first_d, n_new, new_off, rounds, max_group, remap
 
 
 def _merge_rounds(csr, maps, n_rounds, keys=None):
     """Rounds 0 .. n_rounds-1 of the pairwise merges (no reduction); returns the buffer holding the result
     (the input copy's own pixels when n_rounds == 0).  ``keys``: filled with the coarse row of every
     element by the last round run here."""
-    bin_map_d, group_first_d, n_new, _, _, max_group = maps
+    bin_map_d, group_first_d, n_new, _, _, max_group, remap = maps
     dev = csr.px.device
     n = csr.nnz
     claim = torch.zeros(1, dtype=_I64, device=dev)
@@ -200,7 +213,7 @@ def _merge_rounds(csr, maps, n_rounds, keys=None):
         dst = bufs[r % 2]
         lists = -(-max_group // (1 << r))
         _lib.call("cb200_coarsen_merge_round", _ptr(src), _ptr(dst), _ptr(csr.indptr), _ptr(group_first_d),
-                  n_new, r, -(-lists // 2), _ptr(bin_map_d) if r == 0 else C.c_void_p(0),
+                  n_new, r, -(-lists // 2), C.byref(remap) if r == 0 else None,
                   _ptr(keys) if (keys is not None and r == n_rounds - 1) else C.c_void_p(0), _ptr(claim), _stream())
         src = dst
     return src
@@ -232,14 +245,14 @@ def coarsen_table(table: PixelTable, factor: int):
     csr = table.raw
     n = csr.nnz
     maps = _coarse_maps(table, factor)
-    bin_map_d, group_first_d, n_new, new_off, rounds, _ = maps
+    bin_map_d, group_first_d, n_new, new_off, rounds, _, remap = maps
     src = _merge_rounds(csr, maps, rounds - 1)
     tmp = torch.empty((n + 2, 2), dtype=_I32, device=dev)
     row_count = torch.zeros(max(n_new, 1), dtype=_I32, device=dev)
     overflow = torch.zeros(1, dtype=_I32, device=dev)
     claim = torch.zeros(1, dtype=_I64, device=dev)
     _lib.call("cb200_coarsen_merge_reduce", _ptr(src), _ptr(tmp), _ptr(csr.indptr), _ptr(group_first_d), n_new,
-              rounds - 1, _ptr(bin_map_d) if rounds == 1 else C.c_void_p(0), _ptr(row_count), _ptr(overflow),
+              rounds - 1, C.byref(remap) if rounds == 1 else None, _ptr(row_count), _ptr(overflow),
               _ptr(claim), _stream())
     del src
     indptr = exclusive_scan_i32(row_count[:n_new])            # the new row pointer

@@ -342,8 +342,24 @@ int cb200_coarsen_remap(const cb200_copy* csr, int32_t n_rows, const int32_t* bi
 int cb200_coarsen_maps(const int64_t* chrom_offset, const int64_t* new_chrom_offset, int32_t n_chroms,
                        int32_t factor, int32_t n_bins, int32_t n_new, int32_t* bin_map,
                        int32_t* group_first, void* stream);
+/* Column remap of merge round 0.  bin_map (cb200_coarsen_maps) is always valid; with `blocks`
+ * (cb200_coarsen_block_table: 4 int32 per block of 2^block_shift bins, 16-byte aligned) the kernels compute
+ * new = (col + pad) / factor from the block's entry instead of gathering bin_map[col] -- a row's columns are
+ * spread over the whole genome, so the gathers cost one L1 tag lookup per lane.  magic / magic_shift:
+ * x / factor == umulhi(x, magic) >> magic_shift for 0 <= x < 2^31 (l = ceil(log2 factor),
+ * magic = ceil(2^(31+l) / factor), magic_shift = l - 1); requires n_new * factor < 2^31. */
+typedef struct {
+  const int32_t* bin_map;
+  const int32_t* blocks;     /* NULL: gather from bin_map */
+  int32_t  block_shift;
+  uint32_t magic;
+  int32_t  magic_shift;
+} cb200_remap;
+int cb200_coarsen_block_table(const int64_t* chrom_offset, const int64_t* new_chrom_offset, int32_t n_chroms,
+                              int32_t factor, int32_t n_bins, int32_t block_shift, int32_t* blocks_out,
+                              void* stream);
 /* One round of the merge form of K5.  `in` = pixels {column, count} of a bin1-major copy (round 0:
- * fine column ids, remapped through bin_map on the fly; later rounds: coarse column ids); the
+ * fine column ids, remapped on the fly (remap != NULL); later rounds: coarse column ids, remap == NULL); the
  * fine rows group_first[g] .. group_first[g+1] pool into coarse row g.  In round r a list is the
  * run of 2^r consecutive fine rows of one coarse row; lists 2q and 2q+1 (q < pairs_per_group) are
  * merged by coarse column (stable) into the same element range of `out`.  After
@@ -352,7 +368,7 @@ int cb200_coarsen_maps(const int64_t* chrom_offset, const int64_t* new_chrom_off
  * round, else NULL): coarse row of every element.  claim: one int64 of scratch. */
 int cb200_coarsen_merge_round(const cb200_px* in, cb200_px* out, const int64_t* indptr,
                               const int32_t* group_first, int32_t n_groups, int32_t round,
-                              int32_t pairs_per_group, const int32_t* bin_map, int32_t* key_out,
+                              int32_t pairs_per_group, const cb200_remap* remap, int32_t* key_out,
                               int64_t* claim, void* stream);
 /* The LAST merge round with the reduce-by-key of groupby(...).sum() (src/cooler/_reduce.py:616-620) fused
  * in: the two remaining lists of every coarse row are merged and adjacent equal coarse columns summed
@@ -361,7 +377,7 @@ int cb200_coarsen_merge_round(const cb200_px* in, cb200_px* out, const int64_t* 
  * pointer and cb200_coarsen_compact moves the rows there (key_out, if not NULL: coarse row per element). */
 int cb200_coarsen_merge_reduce(const cb200_px* in, cb200_px* out, const int64_t* indptr,
                                const int32_t* group_first, int32_t n_groups, int32_t round,
-                               const int32_t* bin_map, int32_t* row_count, int32_t* overflow,
+                               const cb200_remap* remap, int32_t* row_count, int32_t* overflow,
                                int64_t* claim, void* stream);
 int cb200_coarsen_compact(const cb200_px* in, const int64_t* indptr, const int32_t* group_first,
                           const int64_t* new_indptr, int32_t n_groups, cb200_px* out, int32_t* key_out,

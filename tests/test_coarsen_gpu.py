@@ -134,6 +134,37 @@ def test_coarsen_matches_oracle_large(factor):
     np.testing.assert_array_equal(new.raw.indptr.cpu().numpy(), np.searchsorted(g1, np.arange(new.n_bins + 1)))
 
 
+@pytest.mark.parametrize("factor", [2, 3, 5, 16, 64])
+def test_coarsen_many_small_chromosomes(factor):
+    """400 chromosomes of 1 .. 300 bins (plus empty ones): blocks of the column-remap table hold no, one or
+    several chromosome boundaries (the latter fall back to the bin_map gather); rounds 1 .. 6."""
+    from cooler_b200 import PixelTable
+    from cooler_b200.reduce import coarsen_table, table_to_host
+    from oracle import coarsen_numpy
+    rng = np.random.default_rng(factor)
+    nb = rng.integers(1, 300, 400)
+    nb[::7] = 1
+    nb[5::50] = 0                                     # chromosomes without bins
+    chrom_offset = np.r_[0, np.cumsum(nb)].astype(np.int64)
+    n = int(chrom_offset[-1])
+    m = 1_500_000
+    i = rng.integers(0, n, m)
+    j = np.where(rng.random(m) < 0.5, np.minimum(i + rng.integers(0, 40, m), n - 1), rng.integers(0, n, m))
+    i, j = np.minimum(i, j), np.maximum(i, j)
+    key = np.unique(i.astype(np.int64) * n + j)
+    b1, b2 = key // n, key % n
+    cnt = rng.integers(1, 100, len(b1)).astype(np.int32)
+    sizes = np.maximum(nb, 0) * 1000
+    bc, bs, be = _golden.uniform_bins(sizes, 1000)
+    want = coarsen_numpy.coarsen_pixels(dict(bin1_id=b1, bin2_id=b2, count=cnt), bc, bs, be, sizes, factor)
+    tab = PixelTable.from_arrays(np.searchsorted(b1, np.arange(n + 1)), b2, cnt, chrom_offset)
+    new, ids = coarsen_table(tab, factor)
+    g1, g2, gc = table_to_host(new, ids)
+    np.testing.assert_array_equal(g1, want[0]), np.testing.assert_array_equal(g2, want[1])
+    np.testing.assert_array_equal(gc, want[2])
+    assert int(gc.sum()) == int(cnt.sum())
+
+
 def _gm_part(k):
     t = _golden.gm12878()
     return _mem(t["chromnames"], t["chromsizes"], t["bins_chrom"], t["bins_start"], t["bins_end"],

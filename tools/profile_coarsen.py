@@ -60,7 +60,7 @@ for factor in factors:
             csr = tab.raw
             n = csr.nnz
             maps = R._coarse_maps(tab, factor)
-            bin_map_d, group_first_d, n_new, new_off, rounds, _ = maps
+            bin_map_d, group_first_d, n_new, new_off, rounds, _, remap = maps
             tm("merge_rounds")
             src = R._merge_rounds(csr, maps, rounds - 1)
             tm("alloc")
@@ -70,7 +70,7 @@ for factor in factors:
             claim = torch.zeros(1, dtype=torch.int64, device=dev)
             tm("merge_reduce")
             _lib.call("cb200_coarsen_merge_reduce", T._ptr(src), T._ptr(tmp), T._ptr(csr.indptr), T._ptr(group_first_d),
-                      n_new, rounds - 1, T._ptr(bin_map_d) if rounds == 1 else C.c_void_p(0), T._ptr(row_count),
+                      n_new, rounds - 1, C.byref(remap) if rounds == 1 else None, T._ptr(row_count),
                       T._ptr(ov), T._ptr(claim), T._stream())
             tm("scan")
             indptr = T.exclusive_scan_i32(row_count)
