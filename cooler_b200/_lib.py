@@ -70,6 +70,12 @@ class Remap(C.Structure):
                 ("magic", C.c_uint32), ("magic_shift", C.c_int32)]
 
 
+class Chunk(C.Structure):
+    """cb200_chunk"""
+    _fields_ = [("src", C.c_void_p), ("src_bytes", C.c_int64), ("dst_row", C.c_int64),
+                ("row0", C.c_int32), ("row1", C.c_int32), ("filter_mask", C.c_uint32)]
+
+
 class FarUnit(C.Structure):
     """cb200_far_unit"""
     _fields_ = [("copy", C.c_int32), ("rb", C.c_int32), ("t0", C.c_int32), ("t1", C.c_int32)]
@@ -120,6 +126,7 @@ SIGNATURES = {
     "cb200_ice_update_peer": (C.c_int, [C.POINTER(Ice), _I32, _P, _I32, _I64, _P]),
     "cb200_ice_reduce_peer": (C.c_int, [C.POINTER(Ice), _P, _I32, _I32, _I64, _P, _P]),
     "cb200_ice_update_gather": (C.c_int, [C.POINTER(Ice), _I32, _P, _I32, _I64, _P]),
+    "cb200_decode_chunks": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _I32]),
     "cb200_bin_pairs": (C.c_int, [_P, _P, _P, _P, _I64, _P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P]),
     "cb200_fetch_count": (C.c_int, [C.POINTER(Copy), _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
     "cb200_fetch_dense": (C.c_int, [C.POINTER(Copy), _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),

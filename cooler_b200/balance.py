@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .table import (PixelTable, TableCopy, _as_tensor, _new_px, _ptr, _stream, _use_device, counts_as_int32, to_host,  # noqa: F401
-                    attach_values, is_float_column, values_nonzero, far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays,
+                    attach_values, is_float_column, values_nonzero, far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays, read_cooler_device,
                     segment_medians, shard_rows_by_pixels,
                     strip_partition, swap_key_other, transpose_from)
 
@@ -882,7 +882,8 @@ def balance_arrays(bin1_offset, bin2_id, count, chrom_offset, *, cis_only=False,
     tables that need column strips go through PixelTable + IceProblem.  Other keyword
     arguments and the return value are those of ``balance_table``."""
     prob = None
-    if strip_bins is None and band is None:
+    on_device = isinstance(bin2_id, torch.Tensor) and bin2_id.is_cuda       # read_cooler_device streamed it already
+    if strip_bins is None and band is None and not on_device:
         prob = IceProblem.from_host(bin1_offset, bin2_id, count, chrom_offset, cis_only=cis_only,
                                     trans_only=trans_only, ignore_diags=ignore_diags, group=group,
                                     device=device, row_range=row_range)
@@ -924,7 +925,7 @@ def balance_cooler(clr, *, cis_only=False, trans_only=False, ignore_diags=2, mad
         rank, world = dist.get_rank(group), dist.get_world_size(group)
         full_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
         rows = shard_rows_by_pixels(full_offset, rank, world)
-    bin1_offset, bin2, count, chrom_offset = read_cooler_arrays(clr, rows=rows)
+    bin1_offset, bin2, count, chrom_offset = read_cooler_device(clr, rows=rows, device=device)
     try:
         chromnames = list(clr.chroms()["name"][:])
     except Exception:  # pragma: no cover - duck-typed stores without a chroms selector

@@ -10,13 +10,13 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC_DIR = os.path.join(_HERE, "csrc")
-SOURCES = ["prims.cu", "table.cu", "ice.cu", "coarsen.cu", "fetch.cu"]
+SOURCES = ["prims.cu", "table.cu", "ice.cu", "coarsen.cu", "fetch.cu", "h5decode.cpp"]
 HEADERS = ["common.cuh", "walk.cuh", "far.cuh", os.path.join("..", "..", "include", "cooler_b200.h")]
 OUT = os.path.join(_HERE, "libcooler_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "-lz", "-lpthread",
 ]
 
 

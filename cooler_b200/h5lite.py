@@ -308,6 +308,169 @@ def _attrs_of(obj: _Obj):
     return out
 
 
+def _narrowable(storage, want):
+    """A little-endian integer column may be read as a narrower integer of the same signedness class
+    (values are checked to fit: the dropped byte planes must be all zero)."""
+    storage, want = np.dtype(storage), np.dtype(want)
+    if storage == want:
+        return True
+    return (storage.kind in "iu" and want.kind in "iu" and storage.byteorder in "<=|"
+            and want.itemsize < storage.itemsize)
+
+
+class _ChunkTask:
+    """Decode one stored chunk into its slice of a destination array.  Runs on a worker thread: inflate
+    releases the GIL, and so do the numpy passes that assemble the byte planes of a shuffled chunk."""
+
+    __slots__ = ("ds", "ch", "dt", "c", "i0", "i1", "dest")
+
+    def __init__(self, ds, ch, dt, c, i0, i1, dest):
+        self.ds, self.ch, self.dt, self.c, self.i0, self.i1, self.dest = ds, ch, dt, c, i0, i1, dest
+
+    def __call__(self):
+        ds, dt, dest = self.ds, self.dt, self.dest
+        _offs, addr, csize, mask = self.ch
+        rd = ds._rd
+        if addr < 0 or addr + csize > len(rd.mv):
+            raise H5FormatError(f"read past end of file ({addr}+{csize})")
+        data = rd.mv[addr:addr + csize]
+        es = dt.itemsize
+        planes = None
+        for i in range(len(ds._filters) - 1, -1, -1):
+            if mask & (1 << i):
+                continue
+            fid, cd = ds._filters[i]
+            if fid == 1:
+                # the inflated size is known (HDF5 stores whole chunks): one allocation instead of the
+                # doubling re-allocations of the default 16 KB buffer, which also scale badly over threads
+                data = zlib.decompress(data, bufsize=self.c * es + 4)
+            elif fid == 2:
+                if i != 0:
+                    data = ds._unfilter_shuffle(data, cd, es)
+                else:
+                    planes = cd[0] if cd else es            # outermost on write = last to undo: keep the planes
+            elif fid == 3:
+                data = data[:len(data) - 4]
+            else:
+                raise H5FormatError(f"unsupported HDF5 filter id {fid}")
+        i0, i1 = self.i0, self.i1
+        if planes is not None and planes == es and es > 1 and dt.kind in "iuf" and dt.byteorder in "<=|":
+            n = len(data) // es
+            p = np.frombuffer(data, dtype=np.uint8, count=n * es).reshape(es, n)
+            ws = dest.dtype.itemsize
+            if ws < es and p[ws:, i0:i1].any():
+                raise OverflowError(f"values of {ds.name} do not fit {dest.dtype}")
+            u = np.dtype(f"<u{ws}")
+            dv = dest.view(u)
+            np.copyto(dv, p[0, i0:i1], casting="unsafe")
+            for k in range(1, ws):
+                t = p[k, i0:i1].astype(u)
+                t <<= 8 * k
+                dv |= t
+            return
+        if planes is not None:
+            data = ds._unfilter_shuffle(data, (planes,), es)
+        arr = np.frombuffer(data, dtype=dt, count=min(self.c, len(data) // es))[i0:i1]
+        if dest.dtype != arr.dtype and dest.dtype.itemsize < arr.dtype.itemsize and len(arr):
+            lo_, hi_ = arr.min(), arr.max()
+            info = np.iinfo(dest.dtype)
+            if lo_ < info.min or hi_ > info.max:
+                raise OverflowError(f"values of {ds.name} do not fit {dest.dtype}")
+        dest[:] = arr
+
+
+_POOL = None
+
+
+def decode_pool():
+    """The process-wide pool of decode threads (one per core, at most 32)."""
+    global _POOL
+    if _POOL is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+        _POOL = ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1), thread_name_prefix="h5lite")
+    return _POOL
+
+
+_CHUNK_DT = np.dtype([("src", "<u8"), ("src_bytes", "<i8"), ("dst_row", "<i8"), ("row0", "<i4"), ("row1", "<i4"),
+                      ("filter_mask", "<u4")], align=True)          # cb200_chunk (include/cooler_b200.h)
+
+
+def _native_decode(ds, lo, hi, dest):
+    """Rows [lo, hi) of ``ds`` into ``dest`` through ``cb200_decode_chunks`` (inflate + un-shuffle (+ narrowing)
+    of all overlapping chunks by native host threads inside one call: no interpreter lock is held while the
+    file is decoded).  Returns False when the dataset's filter pipeline or types are outside what the native
+    decoder covers -- the caller then uses the Python chunk tasks."""
+    try:
+        from . import _lib
+        lib = _lib.load()
+    except Exception:
+        return False
+    dt = ds._np_storage_dtype()
+    es, ws = dt.itemsize, dest.dtype.itemsize
+    ids = [fid for fid, _ in ds._filters]
+    order = {2: 0, 1: 1, 3: 2}                               # only [shuffle][deflate][fletcher32], in that order
+    if any(f not in order for f in ids) or [order[f] for f in ids] != sorted({order[f] for f in ids}):
+        return False
+    for fid, cd in ds._filters:
+        if fid == 2 and cd and cd[0] != es:
+            return False
+    if dt.kind not in "iuf" or (es > 1 and dt.byteorder not in "<=|") or not dest.flags.c_contiguous:
+        return False
+    if ws != es and not (_narrowable(dt, dest.dtype) and dest.dtype.kind in "iu"):
+        return False
+    if ws == es and dest.dtype.kind != dt.kind:
+        return False
+    flags = (1 if 2 in ids else 0) | (2 if 1 in ids else 0) | (4 if 3 in ids else 0)
+    # HDF5 numbers mask bits by pipeline position; the native side re-derives positions from `flags`
+    a, addr, csize, mask, c = ds._chunk_arrays()
+    n_rows = ds.shape[0]
+    sel = np.flatnonzero((addr >= 0) & (a < hi) & (a + c > lo))
+    s0 = np.maximum(a[sel], lo)
+    s1 = np.minimum(np.minimum(a[sel] + c, hi), n_rows)
+    ok = s1 > s0
+    sel, s0, s1 = sel[ok], s0[ok], s1[ok]
+    if int((s1 - s0).sum()) < hi - lo:
+        dest[:] = 0                                          # chunks that were never written read as 0
+    if len(sel) == 0:
+        return True
+    rd = ds._rd
+    if int((addr[sel] + csize[sel]).max()) > len(rd.mv):
+        raise H5FormatError("read past end of file")
+    arr = np.zeros(len(sel), dtype=_CHUNK_DT)
+    arr["src"] = (rd.buf.ctypes.data + addr[sel]).astype(np.uint64)
+    arr["src_bytes"], arr["dst_row"] = csize[sel], s0 - lo
+    arr["row0"], arr["row1"], arr["filter_mask"] = s0 - a[sel], s1 - a[sel], mask[sel]
+    rc = lib.cb200_decode_chunks(arr.ctypes.data, len(sel), int(c), es, ws, flags, dest.ctypes.data, 0)
+    if rc == -3:
+        raise OverflowError(f"values of {ds.name} do not fit {dest.dtype}")
+    if rc != 0:
+        raise H5FormatError(f"{ds.name}: " + lib.cb200_last_error().decode("utf-8", "replace"))
+    return True
+
+
+def read_rows_into(jobs):
+    """``jobs``: [(dataset, lo, hi, dest)] -- rows [lo, hi) of 1-D chunked datasets into numpy arrays
+    (``dest`` may be pinned staging memory), straight into the destinations: no zero-filled staging array,
+    no whole-column dtype cast.  Columns written the way h5py / cooler write them (shuffle + gzip) are
+    decoded by native host threads (``cb200_decode_chunks``); anything else by a pool of Python threads
+    (zlib and the plane assembly release the GIL)."""
+    tasks = []
+    for ds, lo, hi, dest in jobs:
+        if hi <= lo or _native_decode(ds, lo, hi, dest):
+            continue
+        t, covered = ds.chunk_tasks(lo, hi, dest)
+        if covered < hi - lo:
+            dest[:] = 0                                   # chunks that were never written read as the fill value 0
+        tasks += t
+    if len(tasks) > 4:
+        for f in [decode_pool().submit(t) for t in tasks]:
+            f.result()
+    else:
+        for t in tasks:
+            t()
+
+
 class Dataset:
     def __init__(self, rd: _Reader, obj: _Obj, name):
         self._rd, self._obj, self.name = rd, obj, name
@@ -317,6 +480,8 @@ class Dataset:
         self._filters = self._parse_filters()
         self._attrs = None
         self._as = None
+        self._cidx = None
+        self._cidx_np = None
 
     # -- h5py-like surface ---------------------------------------------------------------
     @property
@@ -397,6 +562,15 @@ class Dataset:
             out.append((fid, cd))
         return out
 
+    @staticmethod
+    def _unfilter_shuffle(data, cd, elsize):
+        es = cd[0] if cd else elsize
+        n = len(data) // es
+        if es > 1 and n > 0:
+            a = np.frombuffer(data, dtype=np.uint8, count=n * es).reshape(es, n).T
+            data = np.ascontiguousarray(a).tobytes() + bytes(data[n * es:])
+        return data
+
     def _unfilter(self, data, mask, elsize):
         for i in range(len(self._filters) - 1, -1, -1):
             if mask & (1 << i):
@@ -422,7 +596,12 @@ class Dataset:
         return self._type.np_dtype
 
     def _chunk_index(self):
-        """[(offset tuple, address, stored size, filter mask)] of a chunked dataset."""
+        """[(offset tuple, address, stored size, filter mask)] of a chunked dataset (parsed once)."""
+        if getattr(self, "_cidx", None) is None:
+            self._cidx = self._parse_chunk_index()
+        return self._cidx
+
+    def _parse_chunk_index(self):
         rd, b = self._rd, self._layout
         ver = b[0]
         if ver == 3:
@@ -485,29 +664,50 @@ class Dataset:
     def _read_chunked_1d(self, lo, hi):
         """Rows [lo, hi) of a 1-D chunked dataset (only the chunks that overlap are decoded)."""
         dt = self._np_storage_dtype()
+        want = dt
+        if self._as is not None and np.dtype(self._as) != dt and _narrowable(dt, self._as):
+            want = np.dtype(self._as)                    # assembled from the low byte planes, no wide staging copy
+        out = np.empty(hi - lo, dtype=want)
+        read_rows_into([(self, lo, hi, out)])
+        return self._finish(out)
+
+    def _chunk_arrays(self):
+        """The chunk index as numpy columns: (first row, address or -1, stored bytes, filter mask, rows per chunk)."""
+        if getattr(self, "_cidx_np", None) is None:
+            cdims, chunks = self._chunk_index()
+            self._cidx_np = (np.array([ch[0][0] for ch in chunks], dtype=np.int64),
+                             np.array([-1 if ch[1] is None else ch[1] for ch in chunks], dtype=np.int64),
+                             np.array([ch[2] for ch in chunks], dtype=np.int64),
+                             np.array([ch[3] for ch in chunks], dtype=np.uint32), int(cdims[0]))
+        return self._cidx_np
+
+    def is_chunked_1d(self):
+        return len(self.shape) == 1 and self._layout[1] == 2
+
+    def chunk_rows(self):
+        return int(self._chunk_index()[0][0])
+
+    def chunk_tasks(self, lo, hi, dest):
+        """Decode tasks (callables) that fill ``dest[0:hi-lo]`` with rows [lo, hi) of this 1-D chunked
+        dataset, one per overlapping chunk, plus the number of rows they cover (rows of chunks that were
+        never written are not covered: the caller zero-fills).  ``dest`` is a numpy array of the
+        dataset's dtype, or of a narrower integer type of the same kind (see ``_narrowable``: only the
+        low byte planes of a shuffled chunk are then assembled)."""
+        dt = self._np_storage_dtype()
         cdims, chunks = self._chunk_index()
         c = cdims[0]
-        out = np.zeros(hi - lo, dtype=dt)
-        todo = [ch for ch in chunks if ch[1] is not None and ch[0][0] < hi and ch[0][0] + c > lo]
         n_rows = self.shape[0]
-
-        def decode(ch):
-            offs, addr, csize, mask = ch
-            a = offs[0]
-            raw = self._unfilter(self._rd.bytes(addr, csize), mask, dt.itemsize)
-            arr = np.frombuffer(raw, dtype=dt, count=min(c, len(raw) // dt.itemsize))
+        tasks, covered = [], 0
+        for ch in chunks:
+            a = ch[0][0]
+            if ch[1] is None or a >= hi or a + c <= lo:
+                continue
             s0, s1 = max(a, lo), min(a + c, hi, n_rows)
-            out[s0 - lo:s1 - lo] = arr[s0 - a:s1 - a]
-
-        if len(todo) > 16 and self._filters:             # zlib releases the GIL: inflate chunks in parallel
-            import os
-            from concurrent.futures import ThreadPoolExecutor
-            with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
-                list(ex.map(decode, todo))
-        else:
-            for ch in todo:
-                decode(ch)
-        return self._finish(out)
+            if s1 <= s0:
+                continue
+            covered += s1 - s0
+            tasks.append(_ChunkTask(self, ch, dt, c, s0 - a, s1 - a, dest[s0 - lo:s1 - lo]))
+        return tasks, covered
 
     def _finish(self, arr):
         if arr.dtype.kind in "iuf" and arr.dtype.byteorder == ">":

@@ -559,8 +559,8 @@ class PixelTable:
 
     @classmethod
     def from_cooler(cls, clr, device="cuda"):
-        """Read the pixel table of a ``cooler.Cooler``-like object once (see read_cooler_arrays)."""
-        bin1_offset, bin2, count, chrom_offset = read_cooler_arrays(clr)
+        """Read the pixel table of a ``cooler.Cooler``-like object once (see read_cooler_device)."""
+        bin1_offset, bin2, count, chrom_offset = read_cooler_device(clr, device=device)
         return cls.from_arrays(bin1_offset, bin2, count, chrom_offset, device=device)
 
 
@@ -576,6 +576,80 @@ def shard_rows_by_pixels(bin1_offset, rank, world):
     cuts[0], cuts[-1] = 0, n_bins
     cuts = np.maximum.accumulate(cuts)
     return int(cuts[rank]), int(cuts[rank + 1])
+
+
+_PINNED_RING: dict = {}
+
+
+def _pinned_ring(slots, rows, dtypes):
+    """``slots`` pinned staging buffers per column, allocated once per process (page-locking memory costs
+    about as much as decoding into it)."""
+    key = (slots, rows, tuple(str(d) for d in dtypes))
+    if key not in _PINNED_RING:
+        _PINNED_RING.clear()
+        _PINNED_RING[key] = [[torch.empty(rows, dtype=d, pin_memory=True) for d in dtypes] for _ in range(slots)]
+    return _PINNED_RING[key]
+
+
+_NP2TORCH = {"int32": torch.int32, "int64": torch.int64, "float32": torch.float32, "float64": torch.float64,
+             "int16": torch.int16, "uint8": torch.uint8, "int8": torch.int8}
+
+
+def read_cooler_device(clr, rows=None, device="cuda", piece_rows=1 << 23, slots=3, min_pixels=1 << 20):
+    """The pixel columns of a Cooler-like object straight into DEVICE memory: returns (bin1_offset host
+    int64 -- local to ``rows`` as in ``read_cooler_arrays`` --, bin2_id device int32 / int64, count device,
+    chrom_offset host).
+
+    For files read by ``h5lite`` the stored chunks are inflated by a pool of host threads directly into a
+    small ring of pinned staging buffers (bin2_id assembled as int32 from the low byte planes) and every
+    finished piece of ``piece_rows`` pixels crosses PCIe on a copy stream while later pieces are still
+    being inflated: the table is read ONCE, through pinned memory, and the host never holds a whole
+    column.  For other stores (h5py, MemCooler) and tables below ``min_pixels`` the columns come back as HOST arrays
+    (``read_cooler_arrays``) and the caller's build uploads them."""
+    from . import h5lite
+    device = _use_device(device)
+    chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
+    bin1_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
+    n_bins = len(bin1_offset) - 1
+    p0, p1 = 0, int(bin1_offset[-1])
+    if rows is not None:
+        p0, p1 = int(bin1_offset[rows[0]]), int(bin1_offset[rows[1]])
+        bin1_offset = np.clip(bin1_offset, p0, p1) - p0
+    with clr.open("r") as grp:
+        d2, dc = grp["pixels"]["bin2_id"], grp["pixels"]["count"]
+        fast = all(isinstance(d, h5lite.Dataset) and d.is_chunked_1d() for d in (d2, dc)) and \
+            str(dc.dtype) in _NP2TORCH and np.dtype(dc.dtype).byteorder in "<=|"
+        if not fast or p1 - p0 < min_pixels:
+            _, bin2, count, _ = read_cooler_arrays(clr, rows=rows)     # host arrays: the caller uploads (pipelined build)
+            return bin1_offset, bin2, count, chrom_offset
+        narrow = n_bins < 2**31 - 1 and h5lite._narrowable(d2.dtype, np.int32)
+        t2 = torch.int32 if narrow else _NP2TORCH[str(np.dtype(d2.dtype))]
+        tc = _NP2TORCH[str(np.dtype(dc.dtype))]
+        csz = max(d2.chunk_rows(), dc.chunk_rows())
+        piece = max(csz, piece_rows // csz * csz)          # pieces start on chunk boundaries of the file
+        start = p0 // csz * csz
+        pieces = [(max(a, p0), min(a + piece, p1)) for a in range(start, p1, piece)]
+        ring = _pinned_ring(slots, piece, (t2, tc))
+        events = [None] * slots
+        bin2_d = torch.empty(p1 - p0, dtype=t2, device=device)
+        count_d = torch.empty(p1 - p0, dtype=tc, device=device)
+        copy_stream = torch.cuda.Stream(device=device)
+        for k, (a, b) in enumerate(pieces):
+            slot = k % slots
+            if events[slot] is not None:
+                events[slot].synchronize()                 # the slot's previous upload has left the buffer
+            # blocking, all host cores, no interpreter lock held; the upload of the previous piece runs meanwhile
+            h5lite.read_rows_into([(d2, a, b, ring[slot][0].numpy()[: b - a]), (dc, a, b, ring[slot][1].numpy()[: b - a])])
+            with torch.cuda.stream(copy_stream):
+                bin2_d[a - p0:b - p0].copy_(ring[slot][0][: b - a], non_blocking=True)
+                count_d[a - p0:b - p0].copy_(ring[slot][1][: b - a], non_blocking=True)
+                events[slot] = torch.cuda.Event()
+                events[slot].record(copy_stream)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        for ev in events:                                  # the ring is reused by the next call
+            if ev is not None:
+                ev.synchronize()
+    return bin1_offset, bin2_d, count_d, chrom_offset
 
 
 def read_cooler_arrays(clr, rows=None):

@@ -409,6 +409,23 @@ int cb200_runs_aggregate(const int32_t* keys, const cb200_px* vals, int64_t n, c
 int cb200_unpack_pixels(const int32_t* bin1, const cb200_px* val, int64_t n,
                         int64_t* bin1_out, int64_t* bin2_out, int32_t* count_out, void* stream);
 
+/* ---- reading .cool columns (replaces the H5Dread chunk pipeline of libhdf5 that the reference reaches
+ *      through h5py in every worker, src/cooler/parallel.py:289-304 / core/_selectors.py) ------------- */
+/* One stored chunk of a 1-D chunked dataset: `src_bytes` bytes at `src` (the mapped file); rows
+ * [row0, row1) of the chunk go to destination rows dst_row ...; filter_mask = the chunk's HDF5 filter
+ * mask (bit i set: filter i of the pipeline was not applied). */
+typedef struct {
+  const void* src; int64_t src_bytes; int64_t dst_row; int32_t row0; int32_t row1; uint32_t filter_mask;
+} cb200_chunk;
+/* Decodes a batch of chunks with n_threads host threads (0 = all cores) into dst (host memory, pinned or
+ * not).  filters: bit 0 shuffle, bit 1 deflate, bit 2 fletcher32 -- present in that pipeline order, as
+ * h5py writes them.  elem_bytes = stored element size; dst_elem_bytes <= elem_bytes: little-endian
+ * integers are narrowed (rc -3 if a dropped byte is not zero).  rc -2: corrupt chunk.  Host-only: needs
+ * no GPU. */
+int cb200_decode_chunks(const cb200_chunk* chunks, int64_t n_chunks, int32_t chunk_rows,
+                        int32_t elem_bytes, int32_t dst_elem_bytes, int32_t filters, void* dst,
+                        int32_t n_threads);
+
 /* ---- ingest binning (replaces create/_ingest.py:68-214 _sanitize_records for integer chromosome
  *      ids and fixed-size bins; the groupby(bin1, bin2).size() of aggregate_records, :452-504, is
  *      cb200_sort_pairs x2 + cb200_runs_count / cb200_runs_write as for coarsening) ------------- */

@@ -88,3 +88,71 @@ def test_not_hdf5(tmp_path):
     assert not h5lite.is_hdf5(str(p))
     with pytest.raises(h5lite.H5FormatError):
         h5lite.File(str(p))
+
+
+def _written_cool(tmp_path, n_px=700_000, seed=0, float_counts=False):
+    """A multi-chunk .cool written by the built-in writer: (path, bin1, bin2, count)."""
+    import pandas as pd
+
+    from cooler_b200 import create
+    rng = np.random.default_rng(seed)
+    nb = np.array([900, 600, 1, 300])
+    n = int(nb.sum())
+    i = rng.integers(0, n, n_px)
+    j = rng.integers(0, n, n_px)
+    i, j = np.minimum(i, j), np.maximum(i, j)
+    key = np.unique(i.astype(np.int64) * n + j)
+    b1, b2 = key // n, key % n
+    cnt = rng.integers(1, 1000, len(b1)).astype(np.int32)
+    if float_counts:
+        cnt = cnt * rng.random(len(b1))
+    names = ["c1", "c2", "c3", "c4"]
+    bins = pd.DataFrame({"chrom": pd.Categorical.from_codes(np.repeat(np.arange(4), nb), categories=names, ordered=True),
+                         "start": np.concatenate([np.arange(k, dtype=np.int64) * 1000 for k in nb])})
+    bins["end"] = bins["start"] + 1000
+    path = str(tmp_path / "w.cool")
+    create.create_cooler(path, bins, [{"bin1_id": b1, "bin2_id": b2, "count": cnt}], dupcheck=False,
+                         dtypes={"count": cnt.dtype})
+    return path, b1, b2, cnt
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_threaded_decode_into_destinations(tmp_path, monkeypatch, native):
+    """read_rows_into: the chunks of a column decoded by native host threads (cb200_decode_chunks) or, for
+    pipelines it does not cover, by the pool of Python threads -- straight into caller buffers; bin ids
+    narrowed to int32 from the low byte planes; unaligned row ranges."""
+    from cooler_b200 import h5lite
+    if not native:
+        monkeypatch.setattr(h5lite, "_native_decode", lambda *a: False)
+    path, b1, b2, cnt = _written_cool(tmp_path)
+    f = h5lite.File(path)
+    d2, dc = f["pixels/bin2_id"], f["pixels/count"]
+    assert d2.is_chunked_1d() and d2.dtype == np.int64 and len(d2._chunk_index()[1]) > 4
+    n = len(b2)
+    for lo, hi in [(0, n), (12345, n - 777), (d2.chunk_rows() - 1, d2.chunk_rows() + 1), (5, 5)]:
+        o2 = np.full(hi - lo, -7, np.int32)
+        oc = np.full(hi - lo, -7, np.int32)
+        o8 = np.full(hi - lo, -7, np.int64)
+        h5lite.read_rows_into([(d2, lo, hi, o2), (dc, lo, hi, oc), (d2, lo, hi, o8)])
+        np.testing.assert_array_equal(o2, b2[lo:hi].astype(np.int32))
+        np.testing.assert_array_equal(o8, b2[lo:hi])
+        np.testing.assert_array_equal(oc, cnt[lo:hi])
+    np.testing.assert_array_equal(d2.astype(np.int32)[100:n - 100], b2[100:n - 100].astype(np.int32))
+    assert d2.astype(np.int32)[:].dtype == np.int32
+    # a value that does not fit the narrower type is an error, never a silent wrap
+    small = np.zeros(n, np.int8)
+    with pytest.raises(OverflowError):
+        h5lite.read_rows_into([(d2, 0, n, small)])
+
+
+@pytest.mark.parametrize("native", [True, False])
+def test_threaded_decode_float_column(tmp_path, monkeypatch, native):
+    from cooler_b200 import h5lite
+    if not native:
+        monkeypatch.setattr(h5lite, "_native_decode", lambda *a: False)
+    path, b1, b2, val = _written_cool(tmp_path, n_px=200_000, float_counts=True)
+    dc = h5lite.File(path)["pixels/count"]
+    assert dc.dtype == np.float64
+    out = np.empty(len(val))
+    h5lite.read_rows_into([(dc, 0, len(val), out)])
+    np.testing.assert_array_equal(out, val)

@@ -61,6 +61,14 @@ t0 = time.perf_counter()
 arrs = cooler_b200.table.read_cooler_arrays(clr)
 res["read_decode_s"] = time.perf_counter() - t0
 del arrs
+for rep in range(2):                                    # first call allocates the pinned ring
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    arrs = cooler_b200.table.read_cooler_device(store.open_cooler(path))
+    torch.cuda.synchronize()
+    res["read_to_device_s"] = time.perf_counter() - t0
+assert arrs[1].is_cuda and bool((arrs[1].cpu() == data["bin2_id"].to(arrs[1].dtype)).all())
+del arrs
 for rep in range(2):                                    # first call pays CUDA context + allocator warm-up
     clr = store.open_cooler(path)
     torch.cuda.synchronize()
