@@ -40,7 +40,11 @@ def test_balance_cooler_file_streams_and_matches_arrays(tmp_path):
         warnings.simplefilter("ignore")
         want, wstats = cooler_b200.balance_arrays(bin1_offset, b2, cnt, chrom_offset, ignore_diags=1)
         bias, stats = cooler_b200.balance_cooler(store.open_cooler(path), ignore_diags=1, store=True)
-    np.testing.assert_array_equal(bias, want)              # same device build either way: identical bits
+    # the streamed host build cuts the table into row chunks, the file path builds whole copies: the sums
+    # are associated differently (1e-15), the masks and the converged state are the same
+    np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
+    np.testing.assert_allclose(bias, want, rtol=1e-12, atol=0, equal_nan=True)
+    assert stats["converged"] == wstats["converged"]
     with store.open_cooler(path).open("r") as g:
         np.testing.assert_array_equal(g["bins/weight"][:], bias)
 
