@@ -89,6 +89,26 @@ def main():
                     print(f"[check_dist] world={world} binsize={binsize} two-stage all-reduce vs ORACLE: "
                           f"max_rel_err={err:.2e} {'OK' if good else 'FAIL'}", flush=True)
                 dist.barrier()
+                # floating-point count column on the shards (values = count x a position-keyed factor, so every
+                # rank derives its own slice without communication); float prefilter marginals all-reduced
+                def fvals(cnt, b2id):
+                    return cnt.numpy().astype(np.float64) * (0.5 + (b2id.numpy() % 7) / 7.0)
+                tabf = cooler_b200.PixelTable.from_arrays(shard["bin1_offset"], shard["bin2_id"],
+                                                          fvals(shard["count"], shard["bin2_id"]), shard["chrom_offset"],
+                                                          device=f"cuda:{local}", row_range=shard["row_range"],
+                                                          float_values=True)
+                b4, s4, i4 = cooler_b200.balance_table(tabf, group=dist.group.WORLD, return_info=True, **kw)
+                if rank == 0:
+                    pxf = dict(px, count=fvals(full["count"], full["bin2_id"]))
+                    with warnings.catch_warnings():
+                        warnings.simplefilter("ignore")
+                        want, wstats, wpasses, _ = ice_numpy.balance_arrays(pxf, plan.chrom_offset, off,
+                                                                            return_passes=True, **kw)
+                    good, same_mask, err = judge(b4, s4, i4)
+                    ok &= bool(good)
+                    print(f"[check_dist] world={world} binsize={binsize} float64 counts on shards vs ORACLE: "
+                          f"mask_equal={same_mask} max_rel_err={err:.2e} {'OK' if good else 'FAIL'}", flush=True)
+                dist.barrier()
     # coarsening shards with no exchange: rows cut at coarse-bin boundaries, every rank coarsens its
     # shard, rank-ordered concatenation == single-GPU result (bit-exact)
     from cooler_b200.reduce import align_rows_to_factor, coarsen_table, table_to_host
