@@ -71,9 +71,12 @@ struct IceOpValT {
   }
 };
 
-// Tuning knob (cb200_set_tuning): 128-bit stream loads kept in flight per lane.
-static int g_selective = -1;   // -1 = automatic
-static int g_ice_unroll = 0;   // 0 = automatic: 4 chunks in flight per lane (strip kernel: 768-thread CTAs)
+// 128-bit stream loads kept in flight per lane: 4 (whole copies: 3 blocks of 8 warps per SM; strips: one
+// 768-thread CTA per SM, 80 registers, no spills).  The variants with 1, 2 and 8 loads and 512- / 1024-thread
+// strip CTAs lost the round-1 / round-2 measurements (profiles/r01_tune_*.log) and were removed.
+constexpr int ICE_U = 4;
+constexpr int STRIP_THREADS_DEFAULT = 768;
+static int g_selective = -1;   // cb200_set_tuning: -1 = automatic
 
 template <int U, bool kSelective, int MINB, bool kFloat = false>
 __global__ void __launch_bounds__(BLOCK_THREADS, MINB)
@@ -470,8 +473,10 @@ using namespace cb200;
 extern "C" {
 
 int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1) {
-  if (ice_unroll != 0 && ice_unroll != 1 && ice_unroll != 2 && ice_unroll != 4 && ice_unroll != 5 && ice_unroll != 8) return -1;
-  g_ice_unroll = ice_unroll;
+  if (ice_unroll != 0 && ice_unroll != ICE_U) {
+    set_error_msg("set_tuning: the sweep kernels keep 4 stream loads in flight (ice_unroll 0 or 4)");
+    return -1;
+  }
   g_selective = selective_l1 < 0 ? -1 : (selective_l1 ? 1 : 0);
   return 0;
 }
@@ -534,64 +539,39 @@ static int ice_sweep_near(const cb200_ice* st, void* stream) {
         set_error_msg("ice_sweep: strip slice does not fit shared memory");
         return -1;
       }
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<2, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<4, 768, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<ICE_U, STRIP_THREADS_DEFAULT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CB_CHECK(cudaFuncSetAttribute(ice_sweep_strips_kernel<ICE_U, STRIP_THREADS_DEFAULT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_bytes = smem;
     }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-#define CB_STRIPS(U, T)                                                                      \
-  ice_sweep_strips_kernel<U, T><<<sms, T, smem, (cudaStream_t)stream>>>(                     \
-      st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,                 \
-      reinterpret_cast<unsigned long long*>(st->claim), st->all_done)
-    // default: 24 warps x 4 chunks in flight (80 registers, no spills) beats 32 warps x 2
-    if (st->float_counts) {
-      ice_sweep_strips_kernel<4, 768, true><<<sms, 768, smem, (cudaStream_t)stream>>>(
+    if (st->float_counts)
+      ice_sweep_strips_kernel<ICE_U, STRIP_THREADS_DEFAULT, true><<<sms, STRIP_THREADS_DEFAULT, smem, (cudaStream_t)stream>>>(
           st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,
           reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
-    } else
-    switch (g_ice_unroll) {
-      case 1: CB_STRIPS(1, 1024); break;
-      case 2: CB_STRIPS(2, 1024); break;
-      case 8: CB_STRIPS(4, 512); break;
-      default: CB_STRIPS(4, 768); break;
-    }
-#undef CB_STRIPS
+    else
+      ice_sweep_strips_kernel<ICE_U, STRIP_THREADS_DEFAULT><<<sms, STRIP_THREADS_DEFAULT, smem, (cudaStream_t)stream>>>(
+          st->subs, st->n_subs, st->span, st->total_tiles, st->smem_bins, st->w,
+          reinterpret_cast<unsigned long long*>(st->claim), st->all_done);
     CB_LAUNCH_CHECK("ice_sweep_strips");
     return 0;
   }
   const int64_t blocks = ceil_div64(st->total_warps, WARPS_PER_BLOCK);
   // selective L1 allocation only pays when w is much larger than L1 (tools/tune_sweep.py)
   const int selective = g_selective < 0 ? (st->n_bins > 4 * kNearBins ? 1 : 0) : g_selective;
-#define CB_SWEEP(U, MINB)                                                                           \
-  do {                                                                                              \
-    if (selective)                                                                                  \
-      ice_sweep_kernel<U, true, MINB><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(\
-          st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);                    \
-    else                                                                                            \
-      ice_sweep_kernel<U, false, MINB><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(\
-          st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);                    \
-  } while (0)
+  const cudaStream_t cs = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)blocks;
   if (st->float_counts) {
     if (selective)
-      ice_sweep_kernel<4, true, 2, true><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(
-          st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);
+      ice_sweep_kernel<ICE_U, true, 2, true><<<grid, BLOCK_THREADS, 0, cs>>>(st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);
     else
-      ice_sweep_kernel<4, false, 2, true><<<(unsigned)blocks, BLOCK_THREADS, 0, (cudaStream_t)stream>>>(
-          st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);
-  } else
-  switch (g_ice_unroll) {
-    case 1: CB_SWEEP(1, 4); break;
-    case 2: CB_SWEEP(2, 4); break;
-    case 8: CB_SWEEP(8, 2); break;
-    case 5: CB_SWEEP(4, 4); break;     // 64 registers (4 blocks per SM) at the price of a few spills
-    default: CB_SWEEP(4, 3); break;
+      ice_sweep_kernel<ICE_U, false, 2, true><<<grid, BLOCK_THREADS, 0, cs>>>(st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);
+  } else if (selective) {
+    ice_sweep_kernel<ICE_U, true, 3><<<grid, BLOCK_THREADS, 0, cs>>>(st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);
+  } else {
+    ice_sweep_kernel<ICE_U, false, 3><<<grid, BLOCK_THREADS, 0, cs>>>(st->subs, st->n_subs, st->span, st->total_warps, st->w, st->all_done);
   }
-#undef CB_SWEEP
   CB_LAUNCH_CHECK("ice_sweep");
   return 0;
 }

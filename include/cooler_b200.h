@@ -293,10 +293,10 @@ typedef struct {
                                          whatever dtype the count column has); far-field blocks are not available then */
 } cb200_ice;
 
-/* Tuning of K3 (optional): ice_unroll in {0,1,2,4,8} = 128-bit stream loads kept in
- * flight per lane; 0 (default) = 4 (the strip kernel then runs 768-thread CTAs).
- * selective_l1: -1 automatic, 0/1 = whether gathers far from the diagonal bypass L1
- * allocation in the L1/L2-gather kernel. */
+/* Tuning of K3 (optional).  ice_unroll: 0 or 4 -- the sweep kernels keep 4 128-bit stream loads in flight
+ * per lane (the 1 / 2 / 8 variants lost the measurements and were removed; any other value is an error).
+ * selective_l1: -1 automatic, 0/1 = whether gathers far from the diagonal bypass L1 allocation in the
+ * L1/L2-gather kernel. */
 int cb200_set_tuning(int32_t ice_unroll, int32_t selective_l1);
 /* K3: the marginal sweeps of every sub-copy (bin1-major rows, bin2-major columns), one
  * launch, followed by one launch over the far-field blocks if there are any.  No-op once

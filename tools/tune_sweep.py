@@ -53,7 +53,7 @@ for var in variants:
               f"padded={sum(f.n_chunks * 64 for f in prob.far_copies)} rec_bytes={[f.rec_bytes for f in prob.far_copies]} "
               f"records={sum(f.nnz for f in prob.far_copies)}", flush=True)
         last_strip = (strip_bins, use_smem, far_cs, far_w)
-    assert lib.cb200_set_tuning(unroll % 10, -1 if unroll < 10 else (unroll // 10) - 1) == 0   # 1x: selective off, 2x: on
+    assert lib.cb200_set_tuning(0, -1 if unroll < 10 else (unroll // 10) - 1) == 0   # 1x: selective off, 2x: on
     state.reset(bias0)
     st = C.byref(state.st)
     for _ in range(3):
