@@ -32,7 +32,10 @@ logger = logging.getLogger("cooler")
 
 @click.group()
 def cli():
-    """B200-native subset of the cooler CLI: balance, coarsen, zoomify, merge, cload pairs, dump."""
+    """B200-native subset of the cooler CLI: balance, coarsen, zoomify, merge, cload pairs, dump.
+
+    Files are written through the real `cooler` + h5py when they are installed; otherwise through the
+    built-in HDF5 writer, which is EXPERIMENTAL (its output has not been opened by libhdf5)."""
     if not logger.handlers:
         h = logging.StreamHandler(sys.stderr)
         h.setFormatter(logging.Formatter("%(levelname)s:%(name)s:%(message)s"))

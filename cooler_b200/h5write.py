@@ -682,12 +682,29 @@ def _copy_dataset_raw(dst_group, name, src):
     return Dataset(f, grp._state, leaf)
 
 
+_NOTICE_GIVEN = False
+
+
+def _experimental_notice():
+    """One log line per process: this writer's files have never been opened by libhdf5 / h5py (neither is
+    in the build image); they are checked by tests/_h5check.py and read back by h5lite only."""
+    global _NOTICE_GIVEN
+    if not _NOTICE_GIVEN:
+        _NOTICE_GIVEN = True
+        import logging
+        logging.getLogger("cooler").warning(
+            "h5py is not installed: writing with cooler_b200's built-in HDF5 writer (EXPERIMENTAL -- verify "
+            "the output with h5py / `cooler info` before relying on it)")
+
+
 class File(Group):
-    """Writable HDF5 file: ``File(path, 'w' | 'r+' | 'a')``; use as a context manager."""
+    """Writable HDF5 file: ``File(path, 'w' | 'r+' | 'a')``; use as a context manager.  EXPERIMENTAL:
+    used only when ``cooler`` + h5py are not importable (see ``_experimental_notice``)."""
 
     def __init__(self, path, mode="r+"):
         if mode not in ("w", "r+", "a"):
             raise ValueError("mode must be 'w', 'r+' or 'a'")
+        _experimental_notice()
         exists = os.path.exists(path) and os.path.getsize(path) > 0
         if mode == "a":
             mode = "r+" if exists else "w"

@@ -472,8 +472,7 @@ class CoolerCoarsener:
         self.new_bins_arrays = (c, s, e)
         self._chromnames = list(chromsizes.index)
         self._device = device
-        if group is not None and not self._fast:
-            raise NotImplementedError("sharded coarsening (group=...) covers the integer-count / sum path only")
+        self._align = int(align or factor)
         if table is None and self._fast and group is not None:
             # this rank's row range of the source, cut at boundaries of `align` pooled bins
             from .table import read_cooler_arrays
@@ -519,11 +518,23 @@ class CoolerCoarsener:
         chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
         bin1_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
         in_dt = clr.pixels().dtypes
+        sl = slice(None)
+        if self.group is not None:
+            # this rank's rows, cut at coarse-bin boundaries: every (bin1', bin2') run lives on one rank
+            rows = shard_rows_for_coarsening(clr, self.group, self._align)
+            p0, p1 = int(bin1_offset[rows[0]]), int(bin1_offset[rows[1]])
+            sl = slice(p0, p1)
+            bin1_offset = np.clip(bin1_offset, p0, p1) - p0
         with clr.open("r") as grp:
-            bin2 = np.asarray(grp["pixels"]["bin2_id"][:])
-            cols = {c: np.asarray(grp["pixels"][c][:]) for c in self.columns}
+            bin2 = np.asarray(grp["pixels"]["bin2_id"][sl])
+            cols = {c: np.asarray(grp["pixels"][c][sl]) for c in self.columns}
         b1, b2, vals, new_off = coarsen_columns(bin1_offset, bin2, chrom_offset, self.factor, cols, self.agg,
                                                 device=self._device)
+        if self.group is not None:
+            # rank-ordered concatenation on rank 0 (accumulator dtypes: the casts below see the whole column)
+            got = gather_pixels_to_rank0([b1, b2] + [vals[c] for c in self.columns], self.group)
+            b1, b2 = got[0], got[1]
+            vals = dict(zip(self.columns, got[2:]))
         for c in self.columns:
             want = np.dtype(in_dt[c])
             v = vals[c]

@@ -107,6 +107,34 @@ def main():
             ok &= bool(good)
             print(f"[check_dist_cooler] world={world} sharded coarsen_cooler x{factor} vs reference golden: "
                   f"nnz_out={len(got[0])} {'OK (bit-exact)' if good else 'FAIL'}", flush=True)
+    # general aggregators / extra value columns on row shards (CoolerCoarsener(group=...)), against the goldens
+    # of the unmodified reference (tests/golden/make_agg_golden.py)
+    from cooler_b200 import MemCooler
+    from cooler_b200.reduce import CoolerCoarsener
+    from tests import _agg_cases
+    gm = _golden.gm12878()
+    fcount, big = _agg_cases.derived(gm)
+    G = dict(np.load(os.path.join(_golden.GOLD, "coarsen_agg_golden.npz")))
+    for key in ("gm_mean_x2", "gm_last_x7", "gm_cols_x2", "gmf_mean_x10"):
+        tab, factor, columns, agg = _agg_cases.CASES[key]
+        count = gm["count"] if tab == "gm" else (gm["count"] * 0.5).astype(np.float32)
+        clr = MemCooler.from_arrays([str(x) for x in gm["chromnames"]], gm["chromsizes"], gm["bins_chrom"],
+                                    gm["bins_start"], gm["bins_end"], gm["bin1_id"], gm["bin2_id"], count,
+                                    binsize=2_000_000, extra_pixel_columns={"fcount": fcount, "big": big})
+        chunks = list(CoolerCoarsener(clr, factor, 5000, columns=columns, agg=agg, group=group))
+        if rank == 0:
+            got = {k: np.concatenate([c[k] for c in chunks]) for k in chunks[0]}
+            good = sorted(got) == sorted(k.split("/", 1)[1] for k in G if k.startswith(key + "/"))
+            for k, v in got.items():
+                want = G[f"{key}/{k}"]
+                good = good and v.dtype == want.dtype and (
+                    np.array_equal(v, want) if want.dtype.kind in "iu" else
+                    np.allclose(v, want, rtol=1e-6 if want.dtype == np.float32 else 1e-12, atol=0))
+            ok &= bool(good)
+            print(f"[check_dist_cooler] world={world} sharded general aggregation {key} vs reference golden: "
+                  f"{'OK' if good else 'FAIL'}", flush=True)
+        else:
+            assert not chunks or all(len(c["bin1_id"]) == 0 for c in chunks)
     resolutions = [500_000, 1_000_000, 2_500_000, 5_000_000]
     mc = os.path.join(workdir, "check_dist_zoom.mcool")
     zoomify_cooler(fn, mc, resolutions, chunksize=2_000_000, group=group)
