@@ -65,4 +65,7 @@ def test_balance_cooler_float_count_file_matches_oracle(tmp_path):
         bias, stats = cooler_b200.balance_cooler(store.open_cooler(path), cis_only=True)
     np.testing.assert_array_equal(np.isnan(bias), np.isnan(want))
     np.testing.assert_allclose(bias, want, rtol=1e-9, atol=0, equal_nan=True)
-    np.testing.assert_allclose(stats["var"], wstats["var"], rtol=1e-9, equal_nan=True)
+    # the variance of marginals that agree to 1e-16 is a difference of nearly equal numbers: at var ~ 1e-7 of
+    # scale^2 its own relative error is ~1e-9 (the bar is on the bias; BASELINE north_star)
+    np.testing.assert_allclose(stats["var"], wstats["var"], rtol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(stats["scale"], wstats["scale"], rtol=1e-9, equal_nan=True)
