@@ -605,7 +605,8 @@ def read_cooler_device(clr, rows=None, device="cuda", piece_rows=1 << 23, slots=
     finished piece of ``piece_rows`` pixels crosses PCIe on a copy stream while later pieces are still
     being inflated: the table is read ONCE, through pinned memory, and the host never holds a whole
     column.  For other stores (h5py, MemCooler) and tables below ``min_pixels`` the columns come back as HOST arrays
-    (``read_cooler_arrays``) and the caller's build uploads them."""
+    (``read_cooler_arrays``) and the caller's build uploads them.  The staging ring is shared by all calls of
+    the process: one call at a time."""
     from . import h5lite
     device = _use_device(device)
     chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
@@ -617,8 +618,8 @@ def read_cooler_device(clr, rows=None, device="cuda", piece_rows=1 << 23, slots=
         bin1_offset = np.clip(bin1_offset, p0, p1) - p0
     with clr.open("r") as grp:
         d2, dc = grp["pixels"]["bin2_id"], grp["pixels"]["count"]
-        fast = all(isinstance(d, h5lite.Dataset) and d.is_chunked_1d() for d in (d2, dc)) and \
-            str(dc.dtype) in _NP2TORCH and np.dtype(dc.dtype).byteorder in "<=|"
+        fast = all(isinstance(d, h5lite.Dataset) and d.is_chunked_1d() and str(np.dtype(d.dtype)) in _NP2TORCH
+                   and np.dtype(d.dtype).byteorder in "<=|" for d in (d2, dc))      # native little-endian columns
         if not fast or p1 - p0 < min_pixels:
             _, bin2, count, _ = read_cooler_arrays(clr, rows=rows)     # host arrays: the caller uploads (pipelined build)
             return bin1_offset, bin2, count, chrom_offset

@@ -156,3 +156,21 @@ def test_threaded_decode_float_column(tmp_path, monkeypatch, native):
     out = np.empty(len(val))
     h5lite.read_rows_into([(dc, 0, len(val), out)])
     np.testing.assert_array_equal(out, val)
+
+
+def test_native_decoder_reports_corrupt_chunks(tmp_path):
+    """cb200_decode_chunks: a damaged deflate stream is an error (H5FormatError), never silent garbage."""
+    from cooler_b200 import h5lite
+    path, b1, b2, cnt = _written_cool(tmp_path, n_px=200_000)
+    f = h5lite.File(path)
+    dc = f["pixels/count"]
+    _offs, addr, csize, _mask = dc._chunk_index()[1][0]
+    del f, dc
+    with open(path, "r+b") as fh:
+        fh.seek(addr + csize // 2)
+        fh.write(bytes(range(37, 37 + 64)))
+    dc = h5lite.File(path)["pixels/count"]
+    out = np.empty(len(cnt), np.int32)
+    with pytest.raises((h5lite.H5FormatError, Exception)) as ei:
+        h5lite.read_rows_into([(dc, 0, len(cnt), out)])
+    assert "corrupt" in str(ei.value) or "decompress" in str(ei.value) or "Error" in type(ei.value).__name__
