@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # `python -m cooler_b200.build --far-row-shift 13`); default: the in-tree library.
 LIB_PATH = os.environ.get("CB200_LIB") or os.path.join(_HERE, "libcooler_b200.so")
 
-KEEP_ALL, KEEP_CIS, KEEP_TRANS, KEEP_BAND_NEAR, KEEP_BAND_FAR = 0, 1, 2, 3, 4
+KEEP_ALL, KEEP_CIS, KEEP_TRANS, KEEP_BAND_NEAR, KEEP_BAND_FAR, KEEP_EARLIER_CHROM = 0, 1, 2, 3, 4, 5
 
 
 class Copy(C.Structure):
@@ -118,6 +118,7 @@ SIGNATURES = {
     "cb200_marginals_i64": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
     "cb200_attach_values": (C.c_int, [_P, _I64, _P, _I64, _P, _P]),
     "cb200_values_nonzero": (C.c_int, [_P, _I64, _P, _P]),
+    "cb200_cis_touch": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _P, _P, _P]),
     "cb200_set_tuning": (C.c_int, [_I32, _I32]),
     "cb200_far_row_shift": (C.c_int, []),
     "cb200_ice_sweep": (C.c_int, [C.POINTER(Ice), _P]),

@@ -20,7 +20,7 @@ import torch
 
 from . import _lib
 from .table import (PixelTable, TableCopy, _as_tensor, _new_px, _ptr, _stream, _use_device, counts_as_int32, to_host,  # noqa: F401
-                    attach_values, is_float_column, values_nonzero, far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays, read_cooler_device,
+                    attach_values, earlier_chrom_pixels, is_float_column, values_nonzero, far_blocks, far_rows, filter_copy, marginals_i64, n_tiles, plan_far_units, read_cooler_arrays, read_cooler_device,
                     segment_medians, shard_rows_by_pixels,
                     strip_partition, swap_key_other, transpose_from)
 
@@ -171,6 +171,11 @@ class IceProblem:
         keep = _lib.KEEP_CIS if cis_only else _lib.KEEP_ALL
         csr, tkey, tval = filter_copy(table.raw, table.row_lo, table.row_hi, ndiag, keep,
                                       want_transpose=True)
+        self.earlier = []                            # cis_only, square storage: see cis_touch_flags
+        if cis_only:
+            e = earlier_chrom_pixels(table.raw, table.row_lo, table.row_hi)
+            if e is not None:
+                self.earlier.append(e)
         csc, ckeys = transpose_from(tkey, tval, n_bins, return_keys=True)
         if fval is None:
             # prefilter marginals (exact integers)
@@ -334,6 +339,7 @@ class IceProblem:
         self.peer_reduce = True if peer_reduce is None else bool(peer_reduce)
         self.strip_shift, self.band, self.csr, self.csc = strip_shift, False, None, None
         self.far_copies, self.far_col_shift, self.far_warps = [], 13, 16
+        self.earlier = []
         ndiag = int(ignore_diags) if ignore_diags else 0
         keep = _lib.KEEP_CIS if cis_only else _lib.KEEP_ALL
         marg = torch.zeros((2, n_bins), dtype=torch.int64, device=dev)
@@ -352,6 +358,10 @@ class IceProblem:
             _lib.call(pack, _ptr(bin2_d[p0:p1]), _ptr(count_d[p0:p1]), p1 - p0, _ptr(px), _stream())
             raw = TableCopy(px, indptr_d[r0:r1 + 1] - p0, p1 - p0, r1 - r0, row_base=r0)
             csr, tkey, tval = filter_copy(raw, info.row_lo, info.row_hi, ndiag, keep, want_transpose=True)
+            if cis_only:
+                e = earlier_chrom_pixels(raw, info.row_lo, info.row_hi)
+                if e is not None:
+                    self.earlier.append(e)
             del raw, px
             csc = transpose_from(tkey, tval, n_bins)
             if strip_shift is None or trans_only:
@@ -777,6 +787,63 @@ def prefilter_bias(prob: IceProblem, chrom_offset, *, mad_max, min_nnz, min_coun
     return bias
 
 
+MAX_CHROMS_CIS_TOUCH = 8192
+
+
+def cis_touch_flags(prob, bias, chrom_offset, group=None):
+    """cis_only: which chromosomes are linked by stored pixels (r, c) with c in a chromosome BEFORE r's.
+
+    Returns None (no such pixel: every symmetric-upper table) or two bool matrices [n_chroms, n_chroms]
+    ``(any, masked)``: ``any[a, b]`` = a row of chromosome a holds a pixel in a column of the earlier
+    chromosome b; ``masked[a, b]`` = one of those columns is a masked bin (``bias == 0`` after the bin
+    filters).  See ``poisoned_chromosomes`` and cb200_cis_touch (include/cooler_b200.h)."""
+    table = prob.table
+    dev = table.device
+    n_chroms = len(chrom_offset) - 1
+    earlier = getattr(prob, "earlier", [])
+    have = torch.tensor([1 if earlier else 0], dtype=torch.int32, device=dev)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(have, op=dist.ReduceOp.MAX, group=group)
+    if not int(have.item()):
+        return None
+    if n_chroms > MAX_CHROMS_CIS_TOUCH:
+        raise NotImplementedError(
+            f"cis_only on a square-storage table with more than {MAX_CHROMS_CIS_TOUCH} chromosomes")
+    nb = np.diff(np.asarray(chrom_offset, dtype=np.int64))
+    bin_chrom = torch.from_numpy(np.repeat(np.arange(n_chroms, dtype=np.int32), nb)).to(dev)
+    bias_d = torch.from_numpy(np.ascontiguousarray(bias, dtype=np.float64)).to(dev)
+    flags = torch.zeros((2, n_chroms * n_chroms), dtype=torch.uint8, device=dev)
+    for px, rows, n in earlier:
+        _lib.call("cb200_cis_touch", _ptr(px), _ptr(rows), int(n), _ptr(bin_chrom), n_chroms, _ptr(bias_d),
+                  _ptr(flags[0]), _ptr(flags[1]), _stream())
+    if group is not None:
+        import torch.distributed as dist
+        wide = flags.to(torch.int32)
+        dist.all_reduce(wide, op=dist.ReduceOp.MAX, group=group)
+        flags = wide
+    f = flags.cpu().numpy().astype(bool).reshape(2, n_chroms, n_chroms)
+    return f[0], f[1]
+
+
+def poisoned_chromosomes(touch, seg_empty):
+    """The chromosomes on which the reference's sequential ``_balance_cisonly`` (_balance.py:127-196)
+    ends in NaN on a square-storage table.  It scans the ROWS of a chromosome (:150-151); a stored pixel
+    (r, c) with c in an earlier chromosome is zeroed by ``_zero_trans`` but still weighted
+    ``bias[r] * bias[c] * 0`` (:57-60), which is NaN when ``bias[c]`` already is -- c a masked bin of a
+    finished chromosome (:186), or that chromosome all-NaN (empty, :166-170, or itself poisoned).  Then
+    r's marginal, the mean of the nonzero marginals and every bias of r's chromosome are NaN, the
+    variance never drops below ``tol`` and all ``max_iters`` passes are made (:173-182)."""
+    any_, masked = touch
+    n_chroms = len(seg_empty)
+    all_nan = np.asarray(seg_empty, dtype=bool).copy()
+    poisoned = np.zeros(n_chroms, dtype=bool)
+    for c in range(1, n_chroms):
+        if (masked[c, :c] | (any_[c, :c] & all_nan[:c])).any():
+            poisoned[c] = all_nan[c] = True
+    return poisoned
+
+
 def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore_diags=2, mad_max=5,
                   min_nnz=10, min_count=0, blacklist=None, rescale_marginals=True, x0=None,
                   tol=1e-5, max_iters=200, group=None, problem=None, chromnames=None,
@@ -807,10 +874,12 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
                 [[(1 - (hi - lo) / n_bins)] * (hi - lo)
                  for lo, hi in zip(chrom_offset[:-1], chrom_offset[1:])]) if n_bins else np.zeros(0)
 
+    touch = cis_touch_flags(prob, bias, chrom_offset, group) if cis_only else None
     state = IceState(prob, bias, cweights, seg_offset, tol, max_iters)
     passes = state.run()
     res = state.results()
     bias[:] = res["bias"]
+    poisoned = poisoned_chromosomes(touch, res["seg_empty"]) if touch is not None else None
 
     hit_limit = False
     if cis_only:
@@ -819,6 +888,18 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
         for cid, lo, hi in zip(range(n_chroms), chrom_offset[:-1], chrom_offset[1:]):
             if chromnames is not None:
                 logger.info(chromnames[cid])
+            if poisoned is not None and poisoned[cid]:            # square storage: poisoned_chromosomes()
+                for _ in range(max_iters):
+                    logger.info(f"variance is {np.nan}")
+                res["seg_iters"][cid] = max_iters
+                scale = var = np.nan
+                bias[lo:hi] = np.nan
+                hit_limit = True
+                name = chromnames[cid] if chromnames is not None else cid
+                warnings.warn(f"Iteration limit reached without convergence on {name}.",
+                              ConvergenceWarning, stacklevel=2)
+                scales[cid], variances[cid] = scale, var
+                continue
             for v in res["var_hist"][: res["seg_iters"][cid], cid]:
                 logger.info(f"variance is {v}")
             if res["seg_empty"][cid]:                             # _balance.py:166-170

@@ -250,6 +250,7 @@ struct KeepRule {
       if (d < ndiag) return false;
     }
     if (keep == CB200_KEEP_ALL) return true;
+    if (keep == CB200_KEEP_EARLIER_CHROM) return c < row_lo[r];
     if (keep == CB200_KEEP_BAND_NEAR || keep == CB200_KEEP_BAND_FAR) {
       int ds = (c >> band_shift) - (r >> band_shift);
       if (ds < 0) ds = -ds;
@@ -374,6 +375,23 @@ __global__ void attach_values_kernel(int2* __restrict__ px, int64_t n, const dou
 __global__ void values_nonzero_kernel(const double* __restrict__ values, int64_t n, double* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = values[i] != 0.0 ? 1.0 : 0.0;
+}
+
+// cis_only on tables that store pixels (r, c) with c in a chromosome BEFORE r's (square storage): which
+// (chromosome of r, chromosome of c) pairs occur at all, and which occur with a masked column bin (see
+// cb200_cis_touch in the header).  Every thread stores the same value 1: no atomics needed.
+__global__ void cis_touch_kernel(const int2* __restrict__ px, const int32_t* __restrict__ rows, int64_t n,
+                                 const int32_t* __restrict__ bin_chrom, int n_chroms,
+                                 const double* __restrict__ bias, uint8_t* __restrict__ touch_any,
+                                 uint8_t* __restrict__ touch_masked) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const int c = px[k].x;
+    const int64_t cell = (int64_t)bin_chrom[rows[k]] * n_chroms + bin_chrom[c];
+    touch_any[cell] = 1;
+    const double b = bias[c];
+    if (b == 0.0 || b != b) touch_masked[cell] = 1;
+  }
 }
 
 }  // namespace cb200
@@ -622,6 +640,22 @@ int cb200_values_nonzero(const double* values, int64_t n, double* out, void* str
   if (n <= 0) return 0;
   values_nonzero_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, (cudaStream_t)stream>>>(values, n, out);
   CB_LAUNCH_CHECK("values_nonzero");
+  return 0;
+}
+
+int cb200_cis_touch(const cb200_px* px, const int32_t* rows, int64_t n, const int32_t* bin_chrom,
+                    int32_t n_chroms, const double* bias, uint8_t* touch_any, uint8_t* touch_masked,
+                    void* stream) {
+  if (n <= 0) return 0;
+  if (!px || !rows || !bin_chrom || !bias || !touch_any || !touch_masked || n_chroms <= 0) {
+    set_error_msg("cis_touch: bad arguments");
+    return -1;
+  }
+  int64_t blocks = ceil_div64(n, 256 * 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  cis_touch_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const int2*>(px), rows, n, bin_chrom, n_chroms, bias, touch_any, touch_masked);
+  CB_LAUNCH_CHECK("cis_touch");
   return 0;
 }
 

@@ -237,6 +237,30 @@ def filter_copy(copy, row_lo, row_hi, ndiag, keep, *, want_rows=False, want_tran
     return new, (tkey[:kept] if tkey is not None else None), tval
 
 
+def earlier_chrom_pixels(copy, row_lo, row_hi):
+    """The stored pixels (r, c) of ``copy`` whose column lies in a chromosome BEFORE r's own
+    (``c < row_lo[r]``) as ``(px {c, count}, rows int32, n)``, or None when there is none -- the case
+    of every symmetric-upper table, which then costs one counting pass.  Input of ``cb200_cis_touch``
+    (cis_only on square-storage tables, see include/cooler_b200.h)."""
+    dev = copy.device
+    nt = n_tiles(copy.nnz)
+    if nt == 0:
+        return None
+    tile_count = torch.zeros(nt, dtype=_I32, device=dev)
+    args = (_ptr(copy.px), _ptr(copy.indptr), _ptr(copy.tile_row), copy.n_rows, copy.nnz, _ptr(row_lo),
+            _ptr(row_hi), 0, _lib.KEEP_EARLIER_CHROM, 0, copy.row_base)
+    _lib.call("cb200_filter_count", *args, _ptr(tile_count), _stream())
+    tile_off = exclusive_scan_i32(tile_count)
+    kept = int(tile_off[-1].item())
+    if kept == 0:
+        return None
+    px_out = _new_px(kept, dev)
+    rows = torch.empty(kept, dtype=_I32, device=dev)
+    _lib.call("cb200_filter_write", *args, _ptr(tile_off), _ptr(px_out), _ptr(rows), _ptr(None), _ptr(None),
+              _stream())
+    return px_out, rows, kept
+
+
 def transpose_from(tkey, tval, n_rows, return_keys=False):
     """(key = other bin, val = {row, count}) in row-major order -> the other-major copy."""
     n = tkey.numel()

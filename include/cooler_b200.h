@@ -148,7 +148,10 @@ int cb200_far_interleave4(const uint32_t* rec, const int32_t* slot, const int64_
 enum { CB200_KEEP_ALL = 0, CB200_KEEP_CIS = 1, CB200_KEEP_TRANS = 2,
        /* layout-only rules (no reference counterpart): split a copy into the band
         * |(c >> band_shift) - (r >> band_shift)| <= 1 around the diagonal and the rest */
-       CB200_KEEP_BAND_NEAR = 3, CB200_KEEP_BAND_FAR = 4 };
+       CB200_KEEP_BAND_NEAR = 3, CB200_KEEP_BAND_FAR = 4,
+       /* c < row_lo[r]: the pixels of a row that lie in a chromosome BEFORE the row's own (they exist
+        * only in square storage); input of cb200_cis_touch */
+       CB200_KEEP_EARLIER_CHROM = 5 };
 int cb200_filter_count(const cb200_px* px, const int64_t* indptr, const int32_t* tile_row,
                        int32_t n_rows, int64_t nnz,
                        const int32_t* row_lo, const int32_t* row_hi, int32_t ndiag, int32_t keep,
@@ -190,6 +193,24 @@ int cb200_marginals_i64(const cb200_copy* copy, int32_t n_rows,
 int cb200_attach_values(cb200_px* px, int64_t n, const double* values, int64_t n_values,
                         double* val_out, void* stream);
 int cb200_values_nonzero(const double* values, int64_t n, double* out, void* stream);
+
+/* cis_only on square-storage tables.  _balance_cisonly (src/cooler/_balance.py:127-196) balances the
+ * chromosomes one after the other, scanning the ROWS of a chromosome (spans from bin1_offset, :150-151)
+ * with `_zero_trans` piped.  A stored pixel (r, c) whose column lies in an EARLIER chromosome is zeroed,
+ * but its weight is still bias[r] * bias[c] * 0 (_timesouterproduct, :57-60), and bias[c] is NaN once
+ * c's chromosome is finished and c is a masked bin (:186 `bias[lo:hi][bias == 0] = nan`), or when that
+ * whole chromosome came out NaN: the row marginal of r turns NaN and r's chromosome never converges
+ * (NaN bias, scale and variance, max_iters passes, ConvergenceWarning).  Symmetric-upper tables hold no
+ * such pixel.  To return what the reference returns, the host needs to know which chromosome pairs are
+ * linked by such pixels:  for the n pixels selected by CB200_KEEP_EARLIER_CHROM (px[k].other = c,
+ * rows[k] = r, absolute bin ids) set
+ *   touch_any   [chrom(r) * n_chroms + chrom(c)] = 1
+ *   touch_masked[chrom(r) * n_chroms + chrom(c)] = 1   if bias[c] == 0 or bias[c] is NaN
+ * (bias = the vector after the bin filters, 0 = masked; bin_chrom[b] = chromosome index of bin b).
+ * The flag matrices are caller-zeroed uint8[n_chroms * n_chroms]. */
+int cb200_cis_touch(const cb200_px* px, const int32_t* rows, int64_t n, const int32_t* bin_chrom,
+                    int32_t n_chroms, const double* bias, uint8_t* touch_any, uint8_t* touch_masked,
+                    void* stream);
 
 /* ---- ICE iteration (replaces the PASS C map-reduce + the O(n_bins) numpy
  *      update of _balance_genomewide/_cisonly/_transonly,

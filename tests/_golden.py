@@ -17,14 +17,18 @@ def gm12878():
 
 
 def random_table(name):
-    z = _npz("random_tables.npz")
+    z = _npz("square_tables.npz" if name.startswith("sq") else "random_tables.npz")
     return {k.split("/", 1)[1]: v for k, v in z.items() if k.startswith(name + "/")}
 
 
 def balance_golden():
-    with open(os.path.join(GOLD, "balance_golden.json")) as f:
-        meta = json.load(f)
-    return _npz("balance_golden.npz"), meta
+    """Symmetric-upper cases (make_golden.py) + square-storage cases 'sq*/...' (make_square_golden.py)."""
+    bal, meta = {}, {}
+    for stem in ("balance_golden", "balance_square_golden"):
+        with open(os.path.join(GOLD, stem + ".json")) as f:
+            meta.update(json.load(f))
+        bal.update(_npz(stem + ".npz"))
+    return bal, meta
 
 
 def balance_float_golden():

@@ -19,7 +19,8 @@ def _mem_cooler(t):
     from cooler_b200 import MemCooler
     return MemCooler.from_arrays(t["chromnames"], t["chromsizes"], t["bins_chrom"], t["bins_start"],
                                  t["bins_end"], t["bin1_id"], t["bin2_id"], t["count"],
-                                 binsize=int(t["binsize"]))
+                                 binsize=int(t["binsize"]),
+                                 symmetric_upper=not bool((t["bin2_id"] < t["bin1_id"]).any()))
 
 
 class _Count(logging.Handler):
@@ -235,7 +236,8 @@ def test_flat_marginals_property():
 
 @pytest.mark.parametrize("key,strip_bins", [("gm/defaults", 64), ("gm/cis_only", 128), ("gm/trans_only", 256),
                                             ("rnd3/gw", 32), ("rnd3/cis", 64), ("rnd3/trans", 16),
-                                            ("gm/diag0", 512), ("gm/mad0_nnz0", 1024)])
+                                            ("gm/diag0", 512), ("gm/mad0_nnz0", 1024),
+                                            ("sq22/gw", 64), ("sq22/cis", 32), ("sq21/trans", 16)])
 def test_column_strips_match_reference_golden(key, strip_bins):
     """Cache-blocked layout (column strips of the gathered bias) gives the same answers."""
     import cooler_b200
@@ -361,7 +363,8 @@ def test_far_blocks_large_synthetic_matches_unstripped(strip_bins, col_shift):
 
 @pytest.mark.parametrize("compact", [False, True])
 @pytest.mark.parametrize("key,col_shift", [("gm/defaults", 4), ("gm/cis_only", 7), ("gm/trans_only", 5),
-                                           ("rnd3/gw", 2), ("gm/diag0", 12), ("gm/mad0_nnz0", 6), ("rnd1/cis", 13)])
+                                           ("rnd3/gw", 2), ("gm/diag0", 12), ("gm/mad0_nnz0", 6), ("rnd1/cis", 13),
+                                           ("sq22/gw", 5), ("sq22/cis", 4)])
 def test_all_blocks_layout_matches_reference_golden(key, col_shift, compact):
     """Every pixel (dense diagonal runs included) through the 2-D blocked kernel, with 8-byte and with
     compact 4-byte records (the GM12878 2 Mb counts reach thousands: every such pixel is split into
@@ -471,7 +474,7 @@ def test_degenerate_tables_match_oracle(case, mode):
 
 
 @pytest.mark.parametrize("key", ["gm/defaults", "gm/cis_only", "gm/trans_only", "gm/diag0", "rnd3/gw",
-                                 "rnd3/cis", "rnd3/trans", "rnd1/cis"])
+                                 "rnd3/cis", "rnd3/trans", "rnd1/cis", "sq22/gw", "sq22/cis", "sq21/trans"])
 def test_streamed_build_matches_reference_golden(key):
     """balance_arrays: row-chunked build pipelined with the H2D copy (chunk CSR/CSC sub-copies)."""
     import cooler_b200

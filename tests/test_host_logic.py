@@ -230,3 +230,41 @@ def test_count_columns_are_range_checked_before_narrowing():
             counts_as_int32(_as_tensor(bad))
     with pytest.raises(NotImplementedError):
         counts_as_int32(_as_tensor(np.array([1.5])))
+
+
+@pytest.mark.parametrize("key", ["sq21/cis", "sq21/cis_diag1", "sq22/cis", "sq22/cis_diag1"])
+def test_poisoned_chromosomes_of_square_tables_match_reference(key):
+    """cis_only on square-storage tables: the chromosomes the reference leaves NaN after max_iters
+    passes (NaN bias of an earlier chromosome times a zeroed trans pixel, _balance.py:57-60,150-151,186)
+    are exactly those ``poisoned_chromosomes`` derives from the chromosome-link matrices; the matrices are
+    restated here in numpy (the product computes them with cb200_cis_touch)."""
+    from cooler_b200.balance import poisoned_chromosomes
+    from oracle import ice_numpy
+    bal, meta = _golden.balance_golden()
+    src, _ = key.split("/")
+    t = _golden.table_of(src)
+    chrom_offset, _ = _golden.offsets(t)
+    n_bins, n_chroms = int(chrom_offset[-1]), len(chrom_offset) - 1
+    kw = meta[key]["kwargs"]
+    px = {k: t[k] for k in ("bin1_id", "bin2_id", "count")}
+    chrom_ids = np.repeat(np.arange(n_chroms, dtype=np.int32), np.diff(chrom_offset))
+    spans = [(0, len(px["count"]))]
+    base = dict(zero_trans=True, n_diags=kw.get("ignore_diags", 2), zero_cis=False)
+    marg_nnz = ice_numpy._marginal(px, chrom_ids, n_bins, spans, map, binarize=True, vec=None, **base)
+    marg = ice_numpy._marginal(px, chrom_ids, n_bins, spans, map, binarize=False, vec=None, **base)
+    bias0 = ice_numpy.initial_bias(n_bins, marg_nnz, marg, chrom_offset)
+    first = ice_numpy._marginal(px, chrom_ids, n_bins, spans, map, binarize=False, vec=bias0, **base)
+    seg_empty = np.array([not np.any(first[lo:hi]) for lo, hi in zip(chrom_offset[:-1], chrom_offset[1:])])
+    c1, c2 = chrom_ids[t["bin1_id"]], chrom_ids[t["bin2_id"]]
+    early = c2 < c1
+    any_ = np.zeros((n_chroms, n_chroms), bool)
+    masked = np.zeros_like(any_)
+    any_[c1[early], c2[early]] = True
+    m = early & (bias0[t["bin2_id"]] == 0)
+    masked[c1[m], c2[m]] = True
+    got = poisoned_chromosomes((any_, masked), seg_empty)
+    scale = np.array([np.nan if x is None else x for x in meta[key]["stats"]["scale"]], dtype=float)
+    want = np.isnan(scale) & (np.array(meta[key]["passes"]) == 200)
+    assert want.any() and not want.all()
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(seg_empty & ~got, np.array(meta[key]["passes"]) == 0)
