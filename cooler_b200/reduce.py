@@ -286,33 +286,8 @@ def coarsen_columns(bin1_offset, bin2_id, chrom_offset, factor, columns, agg, de
     idx = torch.arange(n, dtype=_I32)
     table = PixelTable.from_arrays(bin1_offset, bin2_id, idx, chrom_offset, device=dev)
     keys, vals, n_new, new_off = _merge_coarse_rows(table, factor)
-    nt = n_tiles(n)
-    tile_count = torch.zeros(max(nt, 1), dtype=_I32, device=dev)
-    _lib.call("cb200_runs_count", _ptr(keys), _ptr(vals), n, _ptr(tile_count), _stream())
-    tile_off = exclusive_scan_i32(tile_count[:nt])
-    n_out = int(tile_off[-1].item())
-    b1 = torch.empty(max(n_out, 1), dtype=_I32, device=dev)
-    b2 = torch.empty(max(n_out, 1), dtype=_I32, device=dev)
-    out = {}
-    first = True
-    for name, col in columns.items():
-        op = agg.get(name, "sum")
-        if callable(op) or op not in AGG_OPS:
-            raise NotImplementedError(f"aggregator {op!r} is not supported by the CUDA coarsener "
-                                      f"(supported: {sorted(AGG_OPS)})")
-        t = torch.from_numpy(np.ascontiguousarray(col))
-        if t.dtype not in _SRC_DTYPES:
-            t = t.to(torch.float64 if t.dtype.is_floating_point else torch.int64)
-        src = t.to(dev)
-        is_float = src.dtype.is_floating_point or op == "mean"
-        res = torch.empty(max(n_out, 1), dtype=torch.float64 if is_float else _I64, device=dev)
-        _lib.call("cb200_runs_aggregate", _ptr(keys), _ptr(vals), n, _ptr(tile_off), _ptr(src),
-                  _SRC_DTYPES[src.dtype], AGG_OPS[op], _ptr(b1) if first else C.c_void_p(0),
-                  _ptr(b2) if first else C.c_void_p(0), _ptr(res) if not is_float else C.c_void_p(0),
-                  _ptr(res) if is_float else C.c_void_p(0), _stream())
-        out[name] = res[:n_out].cpu().numpy()
-        first = False
-    return (b1[:n_out].to(_I64).cpu().numpy(), b2[:n_out].to(_I64).cpu().numpy(), out, new_off)
+    b1, b2, out = _aggregate_runs(keys, vals, n, columns, agg, dev)
+    return (b1, b2, out, new_off)
 
 
 def _reduce_runs(keys, vals, n, swap, dev):
@@ -330,10 +305,10 @@ def _reduce_runs(keys, vals, n, swap, dev):
     return k2, v2, n_out, overflow
 
 
-def merge_tables(tables):
-    """Sum several device-resident tables over identical bins (the k-way merge of
-    ``CoolerMerger``, _reduce.py:132-208): concatenate, stable radix sort by bin2 then by
-    bin1, reduce-by-key.  Returns (PixelTable, bin1 ids)."""
+def _concat_sorted(tables):
+    """Concatenate device-resident tables over identical bins in the given order and bring the pixels
+    into (bin1, bin2) order by two stable radix sorts (by bin2, then by bin1): pixels of one (bin1, bin2)
+    stay in table order.  Returns (keys = bin1, vals = {bin2, count}, n)."""
     n_bins = tables[0].n_bins
     dev = _use_device(tables[0].device)
     ident = torch.arange(n_bins, dtype=_I32, device=dev)
@@ -358,13 +333,102 @@ def merge_tables(tables):
     k2, v2 = swap_key_other(ks, vs, n)                         # key = bin1, val = {bin2, count}
     del ks, vs
     k3, v3 = sort_pairs(k2, v2, bits)                          # stable by bin1 -> (bin1, bin2) order
-    del k2, v2
+    return k3, v3, n
+
+
+def merge_tables(tables):
+    """Sum several device-resident tables over identical bins (the k-way merge of
+    ``CoolerMerger``, _reduce.py:132-208): concatenate, stable radix sort by bin2 then by
+    bin1, reduce-by-key.  Returns (PixelTable, bin1 ids)."""
+    n_bins = tables[0].n_bins
+    dev = _use_device(tables[0].device)
+    k3, v3, n = _concat_sorted(tables)
     k4, v4, n_out, overflow = _reduce_runs(k3, v3, n, 0, dev)
     del k3, v3
     if int(overflow.item()):
         raise OverflowError("merged count does not fit int32")
     indptr = indptr_from_sorted(k4, n_out, n_bins)
     return PixelTable(TableCopy(v4, indptr, n_out, n_bins), tables[0].chrom_offset), k4[:n_out]
+
+
+def _aggregate_runs(keys, vals, n, columns, agg, dev):
+    """Reduce every (key, vals.other) run of a sorted stream whose payload ``vals.count`` is the pixel's
+    position in the value columns: one ``cb200_runs_aggregate`` per column, in stream order inside a run.
+    Returns (bin1 int64, bin2 int64, {name: numpy array; integers in int64, floats / means in float64})."""
+    nt = n_tiles(n)
+    tile_count = torch.zeros(max(nt, 1), dtype=_I32, device=dev)
+    _lib.call("cb200_runs_count", _ptr(keys), _ptr(vals), n, _ptr(tile_count), _stream())
+    tile_off = exclusive_scan_i32(tile_count[:nt])
+    n_out = int(tile_off[-1].item())
+    b1 = torch.empty(max(n_out, 1), dtype=_I32, device=dev)
+    b2 = torch.empty(max(n_out, 1), dtype=_I32, device=dev)
+    out = {}
+    first = True
+    for name, col in columns.items():
+        op = agg.get(name, "sum")
+        if callable(op) or op not in AGG_OPS:
+            raise NotImplementedError(f"aggregator {op!r} is not supported by the CUDA path "
+                                      f"(supported: {sorted(AGG_OPS)})")
+        t = torch.from_numpy(np.ascontiguousarray(col))
+        if t.dtype not in _SRC_DTYPES:
+            t = t.to(torch.float64 if t.dtype.is_floating_point else torch.int64)
+        src = t.to(dev)
+        is_float = src.dtype.is_floating_point or op == "mean"
+        res = torch.empty(max(n_out, 1), dtype=torch.float64 if is_float else _I64, device=dev)
+        _lib.call("cb200_runs_aggregate", _ptr(keys), _ptr(vals), n, _ptr(tile_off), _ptr(src),
+                  _SRC_DTYPES[src.dtype], AGG_OPS[op], _ptr(b1) if first else C.c_void_p(0),
+                  _ptr(b2) if first else C.c_void_p(0), _ptr(res) if not is_float else C.c_void_p(0),
+                  _ptr(res) if is_float else C.c_void_p(0), _stream())
+        out[name] = res[:n_out].cpu().numpy()
+        first = False
+    return b1[:n_out].to(_I64).cpu().numpy(), b2[:n_out].to(_I64).cpu().numpy(), out
+
+
+def _settle_dtypes(vals, in_dtypes, agg):
+    """Column dtypes as pandas' groupby gives them: sum / min / max / first / last keep the input dtype
+    (an integer sum that leaves it stays int64), the mean is float64 (float32 for a float32 column)."""
+    for c, v in vals.items():
+        want = np.dtype(in_dtypes[c])
+        if agg.get(c, "sum") == "mean":
+            if want == np.float32:
+                vals[c] = v.astype(np.float32)
+            continue
+        if want.kind in "iu" and len(v) and (v.min() < np.iinfo(want).min or v.max() > np.iinfo(want).max):
+            continue
+        vals[c] = v.astype(want, copy=False)
+    return vals
+
+
+def merge_columns(inputs, chrom_offset, columns, agg, device="cuda"):
+    """Merge pixel tables over identical bins with arbitrary value columns and aggregators -- the
+    general form of ``CoolerMerger.__iter__`` (_reduce.py:188-203: ``pd.concat`` of the inputs in cooler
+    order, ``groupby([bin1_id, bin2_id], sort=True).aggregate(agg)``).  ``inputs``: one
+    ``(bin1_offset, bin2_id, {name: host array})`` per cooler.  The tables are merged once carrying the
+    pixel's position in the concatenated columns as payload (stable sorts keep the cooler order inside a
+    group); every column is then reduced per (bin1, bin2) run.  Numeric dtypes promote like
+    ``pd.concat``.  Returns (bin1 int64, bin2 int64, {name: numpy array})."""
+    dev = _use_device(device)
+    sizes = [len(b2) for _, b2, _ in inputs]
+    n = int(sum(sizes))
+    if n >= 2**31 - 1:
+        raise NotImplementedError("the general aggregation path indexes pixels with int32")
+    tables, base = [], 0
+    for (off, b2, _), m in zip(inputs, sizes):
+        idx = torch.arange(base, base + m, dtype=_I32)
+        tables.append(PixelTable.from_arrays(off, b2, idx, chrom_offset, device=dev))
+        base += m
+    cat, in_dt = {}, {}
+    for name in columns:
+        arrs = [np.asarray(cols[name]) for _, _, cols in inputs]
+        in_dt[name] = np.result_type(*[a.dtype for a in arrs])
+        cat[name] = np.concatenate([a.astype(in_dt[name], copy=False) for a in arrs]) if arrs else np.zeros(0)
+    if n == 0:
+        empty = np.zeros(0, dtype=np.int64)
+        return empty, empty, {c: cat[c][:0] for c in columns}
+    keys, vals, n = _concat_sorted(tables)
+    del tables
+    b1, b2, out = _aggregate_runs(keys, vals, n, cat, agg, dev)
+    return b1, b2, _settle_dtypes(out, in_dt, agg)
 
 
 def table_to_host(table: PixelTable, bin1_ids=None):
@@ -774,9 +838,18 @@ class CoolerMerger:
         self.coolers = list(coolers)
         self.mergebuf = int(mergebuf)
         self.columns = ["count"] if columns is None else list(columns)
-        if self.columns != ["count"] or (agg and any(v != "sum" for v in agg.values())):
-            raise NotImplementedError(
-                "the CUDA merger aggregates the integer 'count' column with 'sum' only")
+        self.agg = {col: "sum" for col in self.columns}            # _reduce.py:146-149
+        if agg is not None:
+            self.agg.update(agg)
+        for col, op in self.agg.items():
+            if callable(op) or op not in AGG_OPS:
+                raise NotImplementedError(f"aggregator {op!r} for column '{col}' is not supported by the CUDA "
+                                          f"merger (supported: {sorted(AGG_OPS)})")
+        # the fast path sums int32 counts inside the sort / reduce-by-key kernels; anything else (other
+        # columns, other aggregators, floating-point or wide counts) carries pixel positions instead
+        dts = [c.pixels().dtypes for c in self.coolers]
+        self._fast = (list(self.agg) == ["count"] and self.agg["count"] == "sum" and all(
+            "count" in d and np.dtype(d["count"]).kind in "iu" and np.dtype(d["count"]).itemsize <= 4 for d in dts))
         binsize = self.coolers[0].binsize                          # compatibility checks: 150-166
         if binsize is not None:
             if len({c.binsize for c in self.coolers}) > 1:
@@ -799,6 +872,9 @@ class CoolerMerger:
         self.result_table = None
 
     def __iter__(self):
+        if not self._fast:
+            yield from self._iter_general()
+            return
         tables = [PixelTable.from_cooler(c, device=self.device) for c in self.coolers]
         merged, ids = merge_tables(tables)
         self.result_table = merged
@@ -808,6 +884,31 @@ class CoolerMerger:
         for lo, hi in zip(edges[:-1], edges[1:]):
             if hi > lo:
                 yield {"bin1_id": b1[lo:hi], "bin2_id": b2[lo:hi], "count": cnt[lo:hi]}
+
+    def _iter_general(self):
+        """Any numeric value columns / aggregators (``merge_columns``); the chunks carry the columns of
+        ``agg`` in its order, as ``groupby(...).aggregate(agg)`` returns them (_reduce.py:196-203)."""
+        names = list(self.agg)
+        inputs = []
+        for c in self.coolers:
+            dt = c.pixels().dtypes
+            for col in names:
+                if col not in dt:
+                    raise ValueError(f"Pixel value column '{col}' not found in input '{c.filename}'.")
+            with c.open("r") as grp:
+                cols = {col: np.asarray(grp["pixels"][col][:]) for col in names}
+                inputs.append((np.asarray(c._load_dset("indexes/bin1_offset")),
+                               np.asarray(grp["pixels"]["bin2_id"][:]), cols))
+        chrom_offset = np.asarray(self.coolers[0]._load_dset("indexes/chrom_offset"))
+        b1, b2, vals = merge_columns(inputs, chrom_offset, names, self.agg, device=self.device)
+        self.result_table = None
+        ind = np.searchsorted(b1, np.arange(int(chrom_offset[-1]) + 1), side="left")
+        edges = _prune_edges(ind, self.mergebuf)
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            if hi > lo:
+                chunk = {"bin1_id": b1[lo:hi], "bin2_id": b2[lo:hi]}
+                chunk.update({col: vals[col][lo:hi] for col in names})
+                yield chunk
 
 
 def merge_coolers(output_uri, input_uris, mergebuf, columns=None, dtypes=None, agg=None,
@@ -838,15 +939,19 @@ def merge_coolers(output_uri, input_uris, mergebuf, columns=None, dtypes=None, a
     iterator = CoolerMerger(clrs, mergebuf=mergebuf, columns=columns, agg=agg, device=device)
     if output_uri is None:
         chunks = list(iterator)
-        cat = {k: (np.concatenate([c[k] for c in chunks]) if chunks else np.zeros(0, dtype=np.int64))
-               for k in ("bin1_id", "bin2_id", "count")}        # like create(): only 'count' is kept
+        keys = ["bin1_id", "bin2_id", *columns]
+        cat = {k: (np.concatenate([c[k] for c in chunks]) if chunks else np.zeros(0, dtype=np.int64)) for k in keys}
         c0 = clrs[0]
         bins = c0.bins()[:]
+        extra = {col: cat[col].astype(dtypes[col], copy=False) for col in columns if col != "count"}
+        # the in-memory store always has a count column: zeros when 'count' was not among the merged columns
+        count = cat["count"].astype(dtypes["count"], copy=False) if "count" in cat \
+            else np.zeros(len(cat["bin1_id"]), dtype=np.int32)
         out = MemCooler.from_arrays(list(c0.chromsizes.index), c0.chromsizes.values,
                                     np.asarray(c0._load_dset("bins/chrom")), bins["start"].values,
-                                    bins["end"].values, cat["bin1_id"], cat["bin2_id"],
-                                    cat["count"].astype(dtypes["count"], copy=False),
-                                    binsize=c0.binsize, symmetric_upper=symmetric_upper)
+                                    bins["end"].values, cat["bin1_id"], cat["bin2_id"], count,
+                                    binsize=c0.binsize, symmetric_upper=symmetric_upper,
+                                    extra_pixel_columns=extra or None)
         out.device_table = iterator.result_table
         return out
     _create(output_uri, _bins_frame(clrs[0]), iterator, columns=columns, dtypes=dtypes,

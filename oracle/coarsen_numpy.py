@@ -120,3 +120,44 @@ def merge_pixels(tables, count_dtype=None):
     starts = np.flatnonzero(head)
     acc = np.add.reduceat(cnt.astype(np.int64 if cnt.dtype.kind in "iu" else np.float64), starts)
     return b1[starts], b2[starts], acc.astype(count_dtype)
+
+
+def merge_columns(tables, columns, agg=None):
+    """Restatement of ``CoolerMerger.__iter__`` with general value columns / aggregators
+    (_reduce.py:144-149 defaults every column to 'sum'; :188-203 ``pd.concat`` of the inputs in
+    cooler order, then ``groupby([bin1_id, bin2_id], sort=True).aggregate(agg)``): a stable sort
+    keeps the concatenation order inside a group (what 'first' / 'last' and the floating-point
+    summation order see); numeric dtypes promote as ``pd.concat`` promotes them; integer sums /
+    min / max / first / last keep the promoted dtype, 'mean' is float64.
+    ``tables``: dicts with bin1_id, bin2_id and the value columns.  Returns a dict of arrays.
+    PINNED by tests/golden/merge_agg_golden.npz (unmodified reference, make_merge_golden.py)."""
+    ops = {c: "sum" for c in columns}
+    ops.update(agg or {})
+    b1 = np.concatenate([np.asarray(t["bin1_id"], dtype=np.int64) for t in tables])
+    b2 = np.concatenate([np.asarray(t["bin2_id"], dtype=np.int64) for t in tables])
+    order = np.lexsort((b2, b1))                             # stable
+    b1, b2 = b1[order], b2[order]
+    head = np.r_[True, (b1[1:] != b1[:-1]) | (b2[1:] != b2[:-1])] if len(b1) else np.zeros(0, bool)
+    starts = np.flatnonzero(head)
+    ends = np.r_[starts[1:], len(b1)]
+    out = {"bin1_id": b1[starts], "bin2_id": b2[starts]}
+    for c, op in ops.items():
+        v = np.concatenate([np.asarray(t[c]) for t in tables])[order]
+        wide = v.astype(np.int64 if v.dtype.kind in "iu" else np.float64)
+        if not len(starts):
+            out[c] = v[:0] if op != "mean" else wide[:0].astype(np.float64)
+        elif op == "sum":
+            out[c] = np.add.reduceat(wide, starts).astype(v.dtype)
+        elif op == "mean":
+            out[c] = np.add.reduceat(wide.astype(np.float64), starts) / (ends - starts)
+        elif op == "min":
+            out[c] = np.minimum.reduceat(v, starts)
+        elif op == "max":
+            out[c] = np.maximum.reduceat(v, starts)
+        elif op == "first":
+            out[c] = v[starts]
+        elif op == "last":
+            out[c] = v[ends - 1]
+        else:
+            raise ValueError(op)
+    return out

@@ -242,10 +242,10 @@ def ref_coarsen(name, factor, chunksize=10_000_000, columns=None, agg=None):
     return out, new_bins
 
 
-def ref_merge(names, mergebuf=20_000_000):
+def ref_merge(names, mergebuf=20_000_000, columns=None, agg=None):
     """Concatenated chunk stream of the reference's CoolerMerger (_reduce.py:132-208)."""
     cooler = import_reference()
     clrs = [cooler.Cooler(n) for n in names]
-    it = cooler._reduce.CoolerMerger(clrs, mergebuf=mergebuf)
+    it = cooler._reduce.CoolerMerger(clrs, mergebuf=mergebuf, columns=columns, agg=agg)
     chunks = list(it)
-    return {k: np.concatenate([c[k] for c in chunks]) for k in ("bin1_id", "bin2_id", "count")}
+    return {k: np.concatenate([c[k] for c in chunks]) for k in chunks[0]}

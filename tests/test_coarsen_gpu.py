@@ -230,6 +230,61 @@ def test_merge_matches_oracle_large():
     assert int(gc.sum()) == sum(int(p["count"].sum()) for p in pxs)
 
 
+def _merge_part_coolers():
+    from cooler_b200 import MemCooler
+    from tests import _merge_cases
+    gm = _golden.gm12878()
+    out = []
+    for sel, cols in _merge_cases.parts(gm):
+        extra = {c: v for c, v in cols.items() if c != "count"}
+        out.append(MemCooler.from_arrays([str(x) for x in gm["chromnames"]], gm["chromsizes"], gm["bins_chrom"],
+                                         gm["bins_start"], gm["bins_end"], gm["bin1_id"][sel], gm["bin2_id"][sel],
+                                         cols["count"], binsize=2_000_000, extra_pixel_columns=extra))
+    return out
+
+
+@pytest.mark.parametrize("mergebuf", [20_000_000, 5000])
+@pytest.mark.parametrize("key", ["mean", "min", "max_last", "first", "cols_sum", "fmean", "mixed_sum"])
+def test_general_merge_matches_reference_golden(key, mergebuf):
+    """CoolerMerger with value columns / aggregators (mean, min, max, first, last; float64, wide int64 and
+    mixed int32 / float32 columns) against the UNMODIFIED reference (pandas concat + groupby,
+    _reduce.py:188-203; tests/golden/make_merge_golden.py): ids, integer results and dtypes exact,
+    floating-point results to 1e-12."""
+    from cooler_b200.reduce import CoolerMerger
+    from tests import _merge_cases
+    columns, agg = _merge_cases.CASES[key]
+    chunks = list(CoolerMerger(_merge_part_coolers(), mergebuf, columns=columns, agg=agg))
+    got = {k: np.concatenate([c[k] for c in chunks]) for k in chunks[0]}
+    G = _golden._npz("merge_agg_golden.npz")
+    assert list(got) == [k.split("/", 1)[1] for k in G if k.startswith(key + "/")]
+    for k, v in got.items():
+        want = G[f"{key}/{k}"]
+        assert v.dtype == want.dtype, (k, v.dtype, want.dtype)
+        if want.dtype.kind in "iu":
+            np.testing.assert_array_equal(v, want)
+        else:
+            np.testing.assert_allclose(v, want, rtol=1e-12)
+    if mergebuf == 5000:
+        assert len(chunks) > 3
+
+
+def test_merge_coolers_keeps_extra_columns_and_float_counts():
+    """merge_coolers(None, ...) with columns=[count, fcount]: both land in the result with the promoted
+    dtypes (merge_coolers: np.result_type over the inputs, _reduce.py:286-291)."""
+    from cooler_b200.reduce import merge_coolers
+    G = _golden._npz("merge_agg_golden.npz")
+    out = merge_coolers(None, _merge_part_coolers(), mergebuf=10_000, columns=["count", "fcount", "big"])
+    with out.open() as g:
+        np.testing.assert_array_equal(g["pixels/bin2_id"][:], G["cols_sum/bin2_id"])
+        np.testing.assert_array_equal(g["pixels/count"][:], G["cols_sum/count"])
+        np.testing.assert_array_equal(g["pixels/big"][:], G["cols_sum/big"])
+        np.testing.assert_allclose(g["pixels/fcount"][:], G["cols_sum/fcount"], rtol=1e-12)
+    out = merge_coolers(None, _merge_part_coolers(), mergebuf=10_000, columns=["mixed"])
+    with out.open() as g:
+        assert g["pixels/mixed"][:].dtype == np.float64
+        np.testing.assert_allclose(g["pixels/mixed"][:], G["mixed_sum/mixed"], rtol=1e-12)
+
+
 # --- general value columns / aggregators (SURVEY 8 a9; reference tests/test_reduce.py:100-118) ---------
 @pytest.mark.parametrize("key", ["gm_mean_x2", "gm_min_x5", "gm_max_x3", "gm_first_x2", "gm_last_x7",
                                  "gm_cols_x2", "gm_fsum_x5", "gmf_sum_x2", "gmf_mean_x10"])

@@ -476,3 +476,52 @@ def test_copy_cooler_from_memory_store(tmp_path):
     assert h5lite.File(out)["bins/chrom"].enum == {"x": 0, "y": 1}
     for k in ("pixels/bin1_id", "pixels/bin2_id", "pixels/count", "bins/start", "bins/end", "indexes/bin1_offset"):
         np.testing.assert_array_equal(np.asarray(clr._load_dset(k)), np.asarray(dst._load_dset(k)))
+
+
+def test_merge_files_with_value_columns_and_aggregators(tmp_path, monkeypatch):
+    """`cooler merge --field count --field score:dtype=float32,agg=mean` on real files: both columns are
+    read, merged (oracle stand-in for the device merge; GPU run: tests/test_coarsen_gpu.py) and written with
+    the requested dtypes."""
+    import pandas as pd
+    from click.testing import CliRunner
+
+    from cooler_b200 import create, reduce, store
+    from cooler_b200.cli import cli
+    from oracle import coarsen_numpy
+
+    def oracle_merge_columns(inputs, chrom_offset, columns, agg, device="cuda"):
+        tables = []
+        for off, b2, cols in inputs:
+            b1 = np.repeat(np.arange(len(off) - 1, dtype=np.int64), np.diff(off))
+            tables.append(dict(bin1_id=b1, bin2_id=b2, **cols))
+        out = coarsen_numpy.merge_columns(tables, list(columns), agg)
+        return out.pop("bin1_id"), out.pop("bin2_id"), out
+
+    monkeypatch.setattr(reduce, "merge_columns", oracle_merge_columns)
+    bins = pd.DataFrame({"chrom": ["a"] * 4 + ["b"] * 3, "start": [0, 10, 20, 30, 0, 10, 20],
+                         "end": [10, 20, 30, 35, 10, 20, 22]})
+    rng = np.random.default_rng(5)
+    paths, tables = [], []
+    for k in range(2):
+        i, j = np.triu_indices(7)
+        keep = rng.random(len(i)) < 0.6
+        px = {"bin1_id": i[keep].astype(np.int64), "bin2_id": j[keep].astype(np.int64),
+              "count": rng.integers(1, 50, keep.sum()).astype(np.int32), "score": rng.random(keep.sum())}
+        p = str(tmp_path / f"in{k}.cool")
+        create.create_cooler(p, bins, px, columns=["count", "score"], dtypes={"score": np.float64})
+        check(p)
+        paths.append(p)
+        tables.append(px)
+    out = str(tmp_path / "merged.cool")
+    res = CliRunner().invoke(cli, ["merge", out, *paths, "--field", "count", "--field", "score:dtype=float32,agg=mean"])
+    assert res.exit_code == 0, (res.output, res.exception)
+    check(out)
+    want = coarsen_numpy.merge_columns(tables, ["count", "score"], {"score": "mean"})
+    got = store.open_cooler(out)
+    np.testing.assert_array_equal(np.asarray(got._load_dset("pixels/bin1_id")), want["bin1_id"])
+    np.testing.assert_array_equal(np.asarray(got._load_dset("pixels/bin2_id")), want["bin2_id"])
+    np.testing.assert_array_equal(np.asarray(got._load_dset("pixels/count")), want["count"])
+    score = np.asarray(got._load_dset("pixels/score"))
+    assert score.dtype == np.float32
+    np.testing.assert_allclose(score, want["score"].astype(np.float32), rtol=1e-6)
+    assert got.info["sum"] == int(want["count"].sum()) and got.info["nnz"] == len(want["count"])

@@ -268,3 +268,52 @@ def test_poisoned_chromosomes_of_square_tables_match_reference(key):
     assert want.any() and not want.all()
     np.testing.assert_array_equal(got, want)
     np.testing.assert_array_equal(seg_empty & ~got, np.array(meta[key]["passes"]) == 0)
+
+
+def test_general_merge_host_logic_with_oracle_stand_in(monkeypatch):
+    """CoolerMerger / merge_coolers with value columns and aggregators: column checks, chunking by
+    ``mergebuf`` without splitting a row, column order of ``agg``, dtype promotion -- the numpy oracle
+    stands in for the device merge (GPU run: tests/test_coarsen_gpu.py)."""
+    from cooler_b200 import MemCooler, reduce
+    from oracle import coarsen_numpy
+    from tests import _merge_cases
+
+    def oracle_merge_columns(inputs, chrom_offset, columns, agg, device="cuda"):
+        tables = []
+        for off, b2, cols in inputs:
+            b1 = np.repeat(np.arange(len(off) - 1, dtype=np.int64), np.diff(off))
+            tables.append(dict(bin1_id=b1, bin2_id=b2, **cols))
+        out = coarsen_numpy.merge_columns(tables, list(columns), agg)
+        return out.pop("bin1_id"), out.pop("bin2_id"), out
+
+    monkeypatch.setattr(reduce, "merge_columns", oracle_merge_columns)
+    gm = _golden.gm12878()
+    clrs = []
+    for sel, cols in _merge_cases.parts(gm):
+        extra = {c: v for c, v in cols.items() if c != "count"}
+        clrs.append(MemCooler.from_arrays([str(x) for x in gm["chromnames"]], gm["chromsizes"], gm["bins_chrom"],
+                                          gm["bins_start"], gm["bins_end"], gm["bin1_id"][sel], gm["bin2_id"][sel],
+                                          cols["count"], binsize=2_000_000, extra_pixel_columns=extra))
+    G = _golden._npz("merge_agg_golden.npz")
+    for key, (columns, agg) in _merge_cases.CASES.items():
+        m = reduce.CoolerMerger(clrs, 5000, columns=columns, agg=agg)
+        assert not m._fast
+        chunks = list(m)
+        assert len(chunks) > 3
+        for a, b in zip(chunks[:-1], chunks[1:]):
+            assert a["bin1_id"][-1] < b["bin1_id"][0]                  # a row is never split
+        got = {k: np.concatenate([c[k] for c in chunks]) for k in chunks[0]}
+        assert list(got) == [k.split("/", 1)[1] for k in G if k.startswith(key + "/")]
+        for k, v in got.items():
+            want = G[f"{key}/{k}"]
+            assert v.dtype == want.dtype
+            np.testing.assert_allclose(v, want, rtol=1e-12)
+    assert reduce.CoolerMerger(clrs, 5000)._fast                       # plain integer count + sum
+    with pytest.raises(ValueError, match="not found"):
+        list(reduce.CoolerMerger(clrs, 5000, columns=["count", "nope"]))
+    with pytest.raises(NotImplementedError):
+        reduce.CoolerMerger(clrs, 5000, agg={"count": "median"})
+    out = reduce.merge_coolers(None, clrs, mergebuf=10_000, columns=["count", "fcount"], dtypes={"fcount": np.float32})
+    with out.open() as g:
+        assert g["pixels/fcount"][:].dtype == np.float32 and g["pixels/count"][:].dtype == np.int32
+        np.testing.assert_array_equal(g["pixels/count"][:], G["cols_sum/count"])

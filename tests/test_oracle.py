@@ -152,3 +152,25 @@ def test_merge_oracle_matches_reference_golden():
     b1, b2, c = coarsen_numpy.merge_pixels(parts)
     np.testing.assert_array_equal(np.stack([b1, b2, c], 1), CO["merge/out"])
     assert c.dtype == np.int32
+
+
+@pytest.mark.parametrize("key", ["mean", "min", "max_last", "first", "cols_sum", "fmean", "mixed_sum"])
+def test_general_merge_oracle_matches_reference_golden(key):
+    """oracle.coarsen_numpy.merge_columns against the unmodified reference's CoolerMerger with value
+    columns / aggregators (tests/golden/make_merge_golden.py): ids, integers and dtypes exact, floats to
+    1e-12 (pandas sums groups with Kahan compensation)."""
+    from tests import _merge_cases
+    gm = _golden.gm12878()
+    columns, agg = _merge_cases.CASES[key]
+    tables = [dict(bin1_id=gm["bin1_id"][sel], bin2_id=gm["bin2_id"][sel], **cols)
+              for sel, cols in _merge_cases.parts(gm)]
+    got = coarsen_numpy.merge_columns(tables, columns, agg)
+    G = _golden._npz("merge_agg_golden.npz")
+    assert sorted(got) == sorted(k.split("/", 1)[1] for k in G if k.startswith(key + "/"))
+    for k, v in got.items():
+        want = G[f"{key}/{k}"]
+        assert v.dtype == want.dtype, (k, v.dtype, want.dtype)
+        if want.dtype.kind in "iu":
+            np.testing.assert_array_equal(v, want)
+        else:
+            np.testing.assert_allclose(v, want, rtol=1e-12)
