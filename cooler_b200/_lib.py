@@ -134,6 +134,10 @@ SIGNATURES = {
     "cb200_fetch_coo": (C.c_int, [C.POINTER(Copy), _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "cb200_fetch_balance_dense": (C.c_int, [_P, _I64, _I64, _P, _P, _I32, _P, _P]),
     "cb200_fetch_balance_coo": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I32, _P, _P]),
+    "cb200_fetch_dense_f64": (C.c_int, [C.POINTER(Copy), _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P]),
+    "cb200_fetch_coo_f64": (C.c_int, [C.POINTER(Copy), _P, _I32, _I32, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "cb200_fetch_balance_dense_f64": (C.c_int, [_P, _I64, _I64, _P, _P, _I32, _P, _P]),
+    "cb200_fetch_balance_coo_f64": (C.c_int, [_P, _P, _P, _I64, _P, _P, _I32, _P, _P]),
     "cb200_coarsen_remap": (C.c_int, [C.POINTER(Copy), _I32, _P, _P, _P, _P]),
     "cb200_coarsen_maps": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P, _P]),
     "cb200_coarsen_block_table": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _P]),

@@ -99,9 +99,21 @@ class MatrixSelector:
     """2-D range selector over a device-resident pixel table (``RangeSelector2D`` semantics)."""
 
     def __init__(self, clr, table, weights, *, sparse=False, as_pixels=False, divisive_weights=False,
-                 fill_lower=True, weight_name="weight"):
+                 fill_lower=True, weight_name="weight", field="count", values=None):
         self.clr, self.table = clr, table
         self.sparse, self.as_pixels = sparse, as_pixels
+        # another value column than the table's int32 counts: float64 on the device, one value per stored
+        # pixel in file order; results are cast back to the column's dtype (exact: every cell holds one pixel)
+        self.field = field
+        self.values, self.value_dtype = None, None
+        if values is not None:
+            v = np.asarray(values)
+            if len(v) != table.raw.nnz:
+                raise ValueError("values must have one entry per stored pixel")
+            if v.dtype.kind in "iu" and len(v) and max(abs(int(v.max())), abs(int(v.min()))) > 2**53:
+                raise NotImplementedError("integer value columns beyond 2**53 are not supported by the CUDA path")
+            self.value_dtype = v.dtype
+            self.values = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).to(table.device)
         self.divisive = bool(divisive_weights)
         self.weight_name = weight_name
         n = table.n_bins
@@ -150,13 +162,20 @@ class MatrixSelector:
         n = self.table.n_bins
         h, w = i1 - i0, j1 - j0
         fill = 1 if self.fill_lower else 0
+        fv = self.values is not None
+        vdt = torch.float64 if fv else torch.int32
+        sfx = "_f64" if fv else ""
+        vargs = (_ptr(self.values),) if fv else ()
+
+        def native(a):                                   # back to the column's own dtype
+            return a.astype(self.value_dtype, copy=False) if fv else a
         if not (self.sparse or self.as_pixels):
-            dense = torch.empty(max(h * w, 1), dtype=torch.int32, device=dev)
-            _lib.call("cb200_fetch_dense", C.byref(cs), n, i0, i1, j0, j1, fill, _ptr(dense), _stream())
+            dense = torch.empty(max(h * w, 1), dtype=vdt, device=dev)
+            _lib.call("cb200_fetch_dense" + sfx, C.byref(cs), *vargs, n, i0, i1, j0, j1, fill, _ptr(dense), _stream())
             if self.weights is None:
-                return dense[: h * w].reshape(h, w).cpu().numpy()
+                return native(dense[: h * w].reshape(h, w).cpu().numpy())
             out = torch.empty(max(h * w, 1), dtype=torch.float64, device=dev)
-            _lib.call("cb200_fetch_balance_dense", _ptr(dense), h, w, _ptr(self.weights[i0:i1]),
+            _lib.call("cb200_fetch_balance_dense" + sfx, _ptr(dense), h, w, _ptr(self.weights[i0:i1]),
                       _ptr(self.weights[j0:j1]), int(self.divisive), _ptr(out), _stream())
             return out[: h * w].reshape(h, w).cpu().numpy()
         q = h + (w if fill else 0)
@@ -166,20 +185,21 @@ class MatrixSelector:
         total = int(off[-1].item())
         row = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
         col = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-        val = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-        _lib.call("cb200_fetch_coo", C.byref(cs), n, i0, i1, j0, j1, fill, _ptr(off), _ptr(row), _ptr(col),
-                  _ptr(val), _stream())
+        val = torch.empty(max(total, 1), dtype=vdt, device=dev)
+        _lib.call("cb200_fetch_coo" + sfx, C.byref(cs), *vargs, n, i0, i1, j0, j1, fill, _ptr(off), _ptr(row),
+                  _ptr(col), _ptr(val), _stream())
         bal = None
         if self.weights is not None:
             bal = torch.empty(max(total, 1), dtype=torch.float64, device=dev)
-            _lib.call("cb200_fetch_balance_coo", _ptr(row), _ptr(col), _ptr(val), total, _ptr(self.weights[i0:i1]),
-                      _ptr(self.weights[j0:j1]), int(self.divisive), _ptr(bal), _stream())
+            _lib.call("cb200_fetch_balance_coo" + sfx, _ptr(row), _ptr(col), _ptr(val), total,
+                      _ptr(self.weights[i0:i1]), _ptr(self.weights[j0:j1]), int(self.divisive), _ptr(bal), _stream())
             bal = bal[:total].cpu().numpy()
         row, col, val = (t[:total].cpu().numpy() for t in (row, col, val))
+        val = native(val)
         if self.as_pixels:
             import pandas as pd
             df = pd.DataFrame({"bin1_id": row.astype(np.int64) + i0, "bin2_id": col.astype(np.int64) + j0,
-                               "count": val})
+                               self.field: val})
             if bal is not None:
                 df["balanced"] = bal
             return df
@@ -200,11 +220,12 @@ def matrix(clr, *, field=None, balance=True, sparse=False, as_pixels=False, join
 
     ``balance``: True -> the ``weight`` column of the bin table, a string -> that column, False ->
     raw counts; ``weights`` passes the weight vector directly (e.g. the bias just returned by
-    ``balance_cooler``).  ``table`` reuses an uploaded ``PixelTable``.  ``field`` other than
-    ``count``, ``join=True`` and ``ignore_index=False`` are not supported by the CUDA path.
+    ``balance_cooler``).  ``table`` reuses an uploaded ``PixelTable``.  ``field``: any numeric column of the
+    pixel table (default ``count``); columns other than an int32-class ``count`` are fetched through the
+    float64 kernels and returned in their own dtype.  ``as_pixels`` with ``join=True`` and
+    ``ignore_index=False`` are not supported by the CUDA path.
     """
-    if field not in (None, "count"):
-        raise NotImplementedError("cooler_b200.matrix fetches the 'count' column only")
+    field = "count" if field is None else field
     if isinstance(balance, str) and balance in _4DN_DIVISIVE_WEIGHTS and divisive_weights is None:
         divisive_weights = True                                        # api.py:367-368
     if join and as_pixels:
@@ -218,7 +239,20 @@ def matrix(clr, *, field=None, balance=True, sparse=False, as_pixels=False, join
             weights = np.asarray(grp["bins"][name][:], dtype=np.float64)
     if not balance:
         weights = None
+    dtypes = clr.pixels().dtypes
+    if field not in dtypes:
+        raise KeyError(field)
+    dt = np.dtype(dtypes[field])
+    # int32-class counts live in the table's records; any other column (another field, floating-point or
+    # wide counts) is fetched as float64 values next to a table that only carries the structure
+    values = None
+    if not (field == "count" and dt.kind in "iu" and dt.itemsize <= 4):
+        with clr.open("r") as grp:
+            values = np.asarray(grp["pixels"][field][:])
+        if values.dtype.kind not in "iuf":
+            raise TypeError(f"pixel column '{field}' is not numeric")
     if table is None:
-        table = PixelTable.from_cooler(clr, device=device)
+        table = PixelTable.from_cooler(clr, device=device, structure_only=values is not None)
     return MatrixSelector(clr, table, weights, sparse=sparse, as_pixels=as_pixels,
-                          divisive_weights=divisive_weights, fill_lower=fill_lower, weight_name=name)
+                          divisive_weights=divisive_weights, fill_lower=fill_lower, weight_name=name,
+                          field=field, values=values)

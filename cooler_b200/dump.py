@@ -143,9 +143,16 @@ def dump(clr, out=None, *, table="pixels", columns=None, header=False, na_rep=""
             bin1_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
             tasks = plan_tasks(bbox, bin1_offset, chunksize,
                                bool(fill_lower) and clr.storage_mode == "symmetric-upper")
-            tab = pixel_table if pixel_table is not None else PixelTable.from_cooler(clr, device=device)
+            # an int32-class count column lives in the table's records; a floating-point or wide one is
+            # fetched as float64 values through the same queries (api.MatrixSelector(values=...))
+            values = None
+            dt = np.dtype(clr.pixels().dtypes["count"])
+            if not (dt.kind in "iu" and dt.itemsize <= 4):
+                values = np.asarray(clr._load_dset("pixels/count"))
+            tab = pixel_table if pixel_table is not None else PixelTable.from_cooler(
+                clr, device=device, structure_only=values is not None)
             weights = bins["weight"].to_numpy(np.float64) if balanced else None
-            sel = MatrixSelector(clr, tab, weights, as_pixels=True)
+            sel = MatrixSelector(clr, tab, weights, as_pixels=True, values=values)
 
             def gen():
                 for task in tasks:

@@ -278,7 +278,8 @@ class MemCooler:
         the next call."""
         from .api import matrix
         sel = matrix(self, table=getattr(self, "_b200_table", None), **kwargs)
-        self._b200_table = sel.table
+        if sel.values is None:            # a table built for another field carries no counts: do not keep it
+            self._b200_table = sel.table
         return sel
 
 

@@ -582,8 +582,17 @@ class PixelTable:
         return cls(raw, chrom_offset, row_range=row_range, fval=fval)
 
     @classmethod
-    def from_cooler(cls, clr, device="cuda"):
-        """Read the pixel table of a ``cooler.Cooler``-like object once (see read_cooler_device)."""
+    def from_cooler(cls, clr, device="cuda", structure_only=False):
+        """Read the pixel table of a ``cooler.Cooler``-like object once (see read_cooler_device).
+        ``structure_only``: rows and columns only, every count 0 -- for consumers that bring their own
+        value column (``api.matrix(field=...)``)."""
+        if structure_only:
+            bin1_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
+            chrom_offset = np.asarray(clr._load_dset("indexes/chrom_offset"))
+            with clr.open("r") as grp:
+                bin2 = np.asarray(grp["pixels"]["bin2_id"][:])
+            return cls.from_arrays(bin1_offset, bin2, torch.zeros(len(bin2), dtype=_I32), chrom_offset,
+                                   device=device)
         bin1_offset, bin2, count, chrom_offset = read_cooler_device(clr, device=device)
         return cls.from_arrays(bin1_offset, bin2, count, chrom_offset, device=device)
 

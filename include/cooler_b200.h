@@ -487,6 +487,21 @@ int cb200_fetch_balance_dense(const int32_t* dense, int64_t h, int64_t w, const 
 int cb200_fetch_balance_coo(const int32_t* row, const int32_t* col, const int32_t* val, int64_t n,
                             const double* w1, const double* w2, int32_t divisive, double* out,
                             void* stream);
+/* The same queries filled from ANOTHER value column of the pixel table (`field=` of Cooler.matrix,
+ * src/cooler/api.py:326-329, 724-726: a floating-point count column, or any extra numeric column):
+ * values[p] (float64) is the value of stored pixel p -- the bin1-major copy is in file order, so record
+ * p of `csr` is pixel p.  Windows and COO values are float64. */
+int cb200_fetch_dense_f64(const cb200_copy* csr, const double* values, int32_t n_rows, int32_t i0,
+                          int32_t i1, int32_t j0, int32_t j1, int32_t fill_lower, double* dense_out,
+                          void* stream);
+int cb200_fetch_coo_f64(const cb200_copy* csr, const double* values, int32_t n_rows, int32_t i0,
+                        int32_t i1, int32_t j0, int32_t j1, int32_t fill_lower, const int64_t* row_off,
+                        int32_t* row_out, int32_t* col_out, double* val_out, void* stream);
+int cb200_fetch_balance_dense_f64(const double* dense, int64_t h, int64_t w, const double* w1,
+                                  const double* w2, int32_t divisive, double* out, void* stream);
+int cb200_fetch_balance_coo_f64(const int32_t* row, const int32_t* col, const double* val, int64_t n,
+                                const double* w1, const double* w2, int32_t divisive, double* out,
+                                void* stream);
 
 #ifdef __cplusplus
 }

@@ -36,6 +36,10 @@ CASES = [   # (cooler, args)
     ("toy", ["-f", "-H"]),
     ("toy", ["-r", "chr1", "-r2", "chr2", "--join"]),
     ("toy", ["-r", "chr2:8-30", "-r2", "chr1:4-20"]),
+    # a float32 count column (count * 0.5): values printed with the float format, balanced products in float64
+    ("gmf", ["-r", "chr21", "-b", "-H"]),
+    ("gmf", ["-r", "chr2:0-60,000,000", "-r2", "chr2:30,000,000-120,000,000", "-f", "-k", "300"]),
+    ("gmf", ["-r", "chr20", "--join", "--float-format", ".10g"]),
 ]
 
 
@@ -48,6 +52,10 @@ def main():
     g = refshim.register("gm_dump.cool", [str(x) for x in t["chromnames"]], t["chromsizes"], t["bins_chrom"],
                          t["bins_start"], t["bins_end"], t["bin1_id"], t["bin2_id"], t["count"], 2_000_000)
     g["bins"]["weight"] = BAL["gm/defaults"].copy()
+    g = refshim.register("gmf_dump.cool", [str(x) for x in t["chromnames"]], t["chromsizes"], t["bins_chrom"],
+                         t["bins_start"], t["bins_end"], t["bin1_id"], t["bin2_id"],
+                         (t["count"] * 0.5).astype("float32"), 2_000_000)
+    g["bins"]["weight"] = BAL["gm/defaults"].copy()
     CO = _golden.coarsen_golden()
     a = CO["toy.asymm/2"]
     c, s, e = _golden.uniform_bins([32, 32], 2)
@@ -55,7 +63,7 @@ def main():
                      symmetric_upper=False)
     out = []
     for which, args in CASES:
-        name = "gm_dump.cool" if which == "gm" else "toy_dump.cool"
+        name = {"gm": "gm_dump.cool", "gmf": "gmf_dump.cool", "toy": "toy_dump.cool"}[which]
         res = CliRunner().invoke(cli, ["dump", name, *args])
         assert res.exit_code == 0, (args, res.exception)
         text = res.output

@@ -27,7 +27,11 @@ def _coolers():
     c, s, e = _golden.uniform_bins([32, 32], 2)
     toy = MemCooler.from_arrays(["chr1", "chr2"], [32, 32], c, s, e, a[:, 0], a[:, 1], a[:, 2].astype(np.int32),
                                 binsize=2, symmetric_upper=False)
-    return {"gm": gm, "toy": toy}
+    gmf = MemCooler.from_arrays([str(x) for x in t["chromnames"]], t["chromsizes"], t["bins_chrom"], t["bins_start"],
+                                t["bins_end"], t["bin1_id"], t["bin2_id"], (t["count"] * 0.5).astype(np.float32),
+                                binsize=2_000_000)
+    gmf.root["bins"].create_dataset("weight", BAL["gm/defaults"].copy())
+    return {"gm": gm, "toy": toy, "gmf": gmf}
 
 
 def _kwargs(args):

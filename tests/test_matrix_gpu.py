@@ -137,3 +137,59 @@ def test_cooler_objects_have_a_matrix_method():
     assert np.array_equal(a, a.T) and a.sum() > 0
     with pytest.raises(ValueError, match="No column 'bins/weight'"):
         clr.matrix(balance=True)
+
+
+# --- `field=`: value columns other than an int32 count (api.py:326-329; cb200_fetch_*_f64) ----------
+from tests import _matrix_field_cases as MF  # noqa: E402
+
+
+def _field_clr(t, weights):
+    from cooler_b200 import MemCooler
+    clr = MemCooler.from_arrays([str(x) for x in t["chromnames"]], t["chromsizes"], t["bins_chrom"],
+                                t["bins_start"], t["bins_end"], t["bin1_id"], t["bin2_id"], t["count"],
+                                binsize=2_000_000, extra_pixel_columns=t["extra"] or None)
+    if weights is not None:
+        with clr.open("r+") as g:
+            g["bins"].create_dataset("weight", data=weights)
+    return clr
+
+
+@pytest.mark.parametrize("key", sorted(MF.CASES))
+def test_field_fetch_matches_reference_golden(key):
+    """matrix(field=...) on float64 / wide int64 extra columns and on a float32 count column: dense, sparse
+    and as_pixels, raw and balanced -- values and dtypes bit-identical to the unmodified reference."""
+    import cooler_b200
+    t, field, w, (i0, i1, j0, j1), kind, extra = MF.inputs(key)
+    G = MF.gold()
+    sel = cooler_b200.matrix(_field_clr(t, w), field=field, balance=w is not None, sparse=kind == "sparse",
+                             as_pixels=kind == "pixels", **extra)
+    got = sel[i0:i1, j0:j1]
+    if kind == "dense":
+        assert got.dtype == G[key].dtype and got.shape == G[key].shape
+        np.testing.assert_array_equal(got, G[key])
+    elif kind == "sparse":
+        o = np.lexsort((got.col, got.row))
+        np.testing.assert_array_equal(got.row[o], G[key + "/row"])
+        np.testing.assert_array_equal(got.col[o], G[key + "/col"])
+        assert got.data.dtype == G[key + "/data"].dtype
+        np.testing.assert_array_equal(got.data[o], G[key + "/data"])
+    else:
+        cols = ["bin1_id", "bin2_id", field] + (["balanced"] if w is not None else [])
+        assert list(got.columns) == cols
+        for c in cols:
+            assert got[c].to_numpy().dtype == G[f"{key}/{c}"].dtype
+            np.testing.assert_array_equal(got[c].to_numpy(), G[f"{key}/{c}"])
+
+
+def test_field_fetch_errors_and_table_reuse():
+    import cooler_b200
+    t, field, w, win, kind, extra = MF.inputs("f_dense_raw")
+    clr = _field_clr(t, None)
+    with pytest.raises(KeyError):
+        cooler_b200.matrix(clr, field="nope", balance=False)
+    a = clr.matrix(balance=False)[100:140, 90:130]                   # int32 counts: table kept on the store
+    tab = clr._b200_table
+    f = clr.matrix(field="fcount", balance=False)[100:140, 90:130]   # the kept table serves the structure
+    assert clr._b200_table is tab and f.dtype == np.float64 and a.dtype == np.int32
+    np.testing.assert_array_equal(f != 0, a != 0)
+    np.testing.assert_array_equal(f, MF.gold()["f_dense_raw"])

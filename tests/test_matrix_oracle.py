@@ -42,3 +42,34 @@ def test_region_parsing_matches_reference_extents():
     for bad in ("chrNope", "chr1:10-5", "chr1:0-999,999,999,999", ":5-10"):
         with pytest.raises(ValueError):
             region_to_extent(clr, bad)
+
+
+# --- `field=`: value columns other than an int32 count (api.py:326-329) -----------------------------
+from tests import _matrix_field_cases as MF  # noqa: E402
+
+
+@pytest.mark.parametrize("key", sorted(MF.CASES))
+def test_oracle_field_fetch_matches_reference(key):
+    """The restatement is dtype-generic: float64 / wide int64 extra columns and a float32 count column
+    come back in their own dtype (raw) or float64 (balanced), bit-identical to the unmodified reference."""
+    from oracle import matrix_numpy
+    t, field, w, (i0, i1, j0, j1), kind, extra = MF.inputs(key)
+    G = MF.gold()
+    args = (t["bin1_id"], t["bin2_id"], t["values"], i0, i1, j0, j1)
+    if kind == "dense":
+        got = matrix_numpy.fetch_dense(*args, weights=w, divisive_weights=extra.get("divisive_weights", False))
+        assert got.dtype == G[key].dtype
+        np.testing.assert_array_equal(got, G[key])
+    elif kind == "sparse":
+        r, c, d = matrix_numpy.fetch_sparse(*args, weights=w)
+        np.testing.assert_array_equal(r, G[key + "/row"]), np.testing.assert_array_equal(c, G[key + "/col"])
+        assert d.dtype == G[key + "/data"].dtype
+        np.testing.assert_array_equal(d, G[key + "/data"])
+    else:
+        r, c, v = matrix_numpy.fetch_pixels(*args, fill_lower=False)
+        o = np.lexsort((c, r))
+        np.testing.assert_array_equal(r[o] + i0, G[key + "/bin1_id"])
+        np.testing.assert_array_equal(c[o] + j0, G[key + "/bin2_id"])
+        np.testing.assert_array_equal(v[o], G[f"{key}/{field}"])
+        if w is not None:
+            np.testing.assert_array_equal(w[i0:i1][r[o]] * w[j0:j1][c[o]] * v[o], G[key + "/balanced"])
