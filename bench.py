@@ -291,6 +291,38 @@ def oracle_parity(data, prob, state_factory, bias0_gpu, group, world, rank, full
     return out
 
 
+def _cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_host_to_gpu_node(torch, index):
+    """Run this rank's host threads on the NUMA node its GPU hangs off, so that the pinned host buffers
+    (first touched by cudaHostAlloc in this process) are local to the GPU's PCIe root -- what `numactl
+    --cpunodebind` does for a one-process-per-GPU job.  Returns a dict for the JSON line, or None when the
+    topology is unknown (single-node hosts report numa_node -1).  Undone by ``os.sched_setaffinity(0, all)``
+    before the CPU-baseline leg, which uses every core."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _cpulist(f.read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"gpu_pci": bus, "numa_node": node, "cpus": len(cpus)}
+    except Exception:  # pragma: no cover - depends on the host
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -316,6 +348,8 @@ def main():
                     help="multi-GPU: force the reduce-scatter + all-gather form of the fused all-reduce (default: "
                          "only for vectors beyond balance.TWO_STAGE_BYTES, i.e. the 1 kb config at 8 GPUs)")
     ap.add_argument("--layout", default=None, help="force a sweep layout (IceProblem band=...), e.g. rows, allblocks")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="do not move this rank's host threads to the NUMA node of its GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)          # timing rule: at least 3 warm-up steps
 
@@ -362,6 +396,8 @@ def main():
     # ------------------------------------------------------------------ our arm
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    host_numa = None if args.no_numa_bind else bind_host_to_gpu_node(torch, local_rank)
     group = None
     if world > 1:
         import torch.distributed as dist
@@ -562,7 +598,10 @@ def main():
         def state_factory(k):
             return IceState(prob, bias0.copy(), None, seg_offset, ICE_KW["tol"], k)
 
+        os.sched_setaffinity(0, all_cpus)          # the oracle uses every core
         parity = oracle_parity(data, prob, state_factory, bias0, group, world, rank, full, dev)
+        if host_numa is not None:
+            bind_host_to_gpu_node(torch, local_rank)
         ok = torch.tensor([1 if parity["ok"] else 0], device="cuda")
         if world > 1:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
@@ -597,10 +636,12 @@ def main():
            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "seconds_per_call": float(t_e.item()), "passes": e2e_passes,
            "host_bin2_dtype": args.host_bin2,
+           "host_numa": host_numa,     # this rank's threads and pinned buffers on the GPU's NUMA node (None: unknown / off)
            "n_subcopies": info["n_subcopies"],
            "api": "cooler_b200.balance_arrays(pinned host arrays) -> numpy bias (per rank: its row shard)"}
 
     cpu = None
+    os.sched_setaffinity(0, all_cpus)              # the CPU leg uses every core
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rows, what = bounded_rows(plan, nnz_total, args.cpu_passes + 3 + 2)
         sample = data if rows == (0, plan.n_bins) else synth.generate(plan, rows=rows, device=dev, pin=False)
