@@ -174,3 +174,66 @@ def test_general_merge_oracle_matches_reference_golden(key):
             np.testing.assert_array_equal(v, want)
         else:
             np.testing.assert_allclose(v, want, rtol=1e-12)
+
+
+# --- the known answers SURVEY.md 8c records from its own probe of the unmodified reference ------------
+_SURVEY_BALANCE = [   # kwargs, passes (sum), masked bins, scale, var, nansum(bias)
+    ({}, 14, 118, 56.94014353567062, 3.7801217049722795e-06, 208.7776861403485),
+    ({"trans_only": True}, 11, 118, 36.1473609947245, 5.314829440303912e-06, 286.2395194205529),
+    ({"cis_only": True}, 295, 219, None, None, 297.58865027208265),
+    ({"ignore_diags": 1, "tol": 1e-2}, 10, 120, None, 0.006900641970473413, 186.2982920213636),
+    ({"mad_max": 0}, None, 105, 56.727150542796146, 3.543021571573216e-06, 214.07478676441906),
+    ({"min_nnz": 0}, None, 107, 56.692392600713006, 6.064179624498289e-06, 233.53153166476125),
+    ({"mad_max": 0, "min_nnz": 0}, 200, 0, 57.23676633284351, 0.005221833681348441, 2084.2446240263525),
+    ({"min_count": 100}, 29, 1556, None, 8.003508570781497e-06, None),
+]
+
+
+@pytest.mark.parametrize("k", range(len(_SURVEY_BALANCE)))
+def test_oracle_reproduces_survey_known_answers(k):
+    """SURVEY.md 8c, table of known answers (the survey's own run of the unmodified reference on the
+    GM12878 2 Mb fixture): pass counts, masked bins, scale, variance and the sum of the weights."""
+    kw, passes, masked, scale, var, total = _SURVEY_BALANCE[k]
+    t = _golden.gm12878()
+    chrom_offset, bin1_offset = _golden.offsets(t)
+    assert list(chrom_offset[:6]) == [0, 125, 247, 347, 443, 534] and chrom_offset[-1] == 1561
+    px = {c: t[c] for c in ("bin1_id", "bin2_id", "count")}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        bias, stats, n, warned = ice_numpy.balance_arrays(px, chrom_offset, bin1_offset, return_passes=True, **kw)
+    if passes is not None:
+        assert sum(n) == passes
+    assert int(np.isnan(bias).sum()) == masked
+    if kw.get("cis_only"):
+        assert n[:5] == [15, 12, 11, 20, 21] and n[-2:] == [0, 0]          # chrY and chrM are empty
+        np.testing.assert_allclose(stats["scale"][:2], [28.964751069515653, 30.062431951299605], rtol=1e-13)
+        np.testing.assert_allclose(stats["var"][:3], [8.782106318499245e-06, 9.988300598962036e-06,
+                                                      4.030316950816017e-06], rtol=1e-9)
+    else:
+        if scale is not None:
+            assert abs(stats["scale"] / scale - 1) < 1e-13
+        if var is not None:
+            assert abs(stats["var"] / var - 1) < 1e-9
+    if total is not None:
+        assert abs(np.nansum(bias) / total - 1) < 1e-12
+    assert warned == (kw == {"mad_max": 0, "min_nnz": 0})
+
+
+@pytest.mark.parametrize("factor,n_new,nnz,diag,cmax,sha", [(2, 784, 30050, 742, 149, "9401b2d7389ad098"),
+                                                            (5, 323, 19174, 312, 344, "a96dfa4bfa403a50"),
+                                                            (10, 167, 10188, 165, 682, "dfaf335a324267bc")])
+def test_coarsen_oracle_reproduces_survey_known_answers(factor, n_new, nnz, diag, cmax, sha):
+    """SURVEY.md 8c, coarsening table: new bin count, output pixels, total, diagonal pixels, maximum and
+    the sha1 of the (bin1, bin2, count) columns."""
+    import hashlib
+    t = _golden.gm12878()
+    b1, b2, c, (nc, ns, ne) = coarsen_numpy.coarsen_pixels(
+        {k: t[k] for k in ("bin1_id", "bin2_id", "count")}, t["bins_chrom"], t["bins_start"], t["bins_end"],
+        t["chromsizes"], factor)
+    assert len(nc) == n_new and len(b1) == nnz and int(c.sum()) == 100000
+    assert int((b1 == b2).sum()) == diag and int(c.max()) == cmax
+    h = hashlib.sha1(b1.astype("<i8").tobytes() + b2.astype("<i8").tobytes() + c.astype("<i4").tobytes())
+    assert h.hexdigest()[:16] == sha
+    if factor == 2:
+        assert (int(ns[124 // 2]), int(ne[124 // 2])) == (248_000_000, 249_250_621)      # chr1's last x2 bin
+        assert (int(ns[-1]), int(ne[-1])) == (0, 16_571)                                 # chrM stays one bin
