@@ -32,7 +32,7 @@ logger = logging.getLogger("cooler")
 
 @click.group()
 def cli():
-    """B200-native subset of the cooler CLI: balance, coarsen, zoomify, merge, cload pairs, dump.
+    """B200-native subset of the cooler CLI: balance, coarsen, zoomify, merge, cload pairs, load, dump.
 
     Files are written through the real `cooler` + h5py when they are installed; otherwise through the
     built-in HDF5 writer, which is EXPERIMENTAL (its output has not been opened by libhdf5)."""
@@ -442,6 +442,152 @@ def pairs(bins, pairs_path, cool_path, metadata, assembly, chrom1, pos1, chrom2,
     create_cooler(cool_path, bins, px, columns=["count"], metadata=metadata, assembly=assembly,
                   boundscheck=False, triucheck=False, dupcheck=False, ensure_sorted=False,
                   symmetric_upper=symmetric_upper, h5opts=h5opts, mode="a" if append else "w")
+
+
+def _parse_load_field(arg):
+    """'<name>[=<field number>][:dtype=<dtype>]' (cli/_util.py:53-97 with includes_agg=False)."""
+    parts = arg.split(":")
+    if len(parts) > 2:
+        raise click.BadParameter(arg)
+    head = parts[0].split("=")
+    if len(head) > 2:
+        raise click.BadParameter(arg)
+    name, colnum = head[0], None
+    if len(head) == 2:
+        try:
+            colnum = int(head[1]) - 1
+        except ValueError as e:
+            raise click.BadParameter(f"Not a number: '{head[1]}'", param_hint=arg) from e
+        if colnum < 0:
+            raise click.BadParameter("Field numbers start at 1.", param_hint=arg)
+    dtype = None
+    if len(parts) == 2:
+        for item in parts[1].split(","):
+            try:
+                prop, value = item.split("=")
+            except ValueError as e:
+                raise click.BadParameter(arg) from e
+            if prop != "dtype":
+                raise click.BadParameter(f"Invalid property: '{prop}'.", param_hint=arg)
+            dtype = np.dtype(value)
+    return name, colnum, dtype
+
+
+@cli.command()
+@click.argument("bins_path", metavar="BINS_PATH")
+@click.argument("pixels_path", metavar="PIXELS_PATH")
+@click.argument("cool_path", metavar="COOL_PATH")
+@click.option("--format", "-f", "format_", type=click.Choice(["coo", "bg2"]), required=True,
+              help="'coo': tab-delimited sparse triplets (bin1, bin2, count); 'bg2': 2D bedGraph-like file "
+                   "(chrom1, start1, end1, chrom2, start2, end2, count).")
+@click.option("--metadata", help="Path to JSON file containing user metadata.")
+@click.option("--assembly", help="Name of genome assembly (e.g. hg19, mm10)")
+@click.option("--field", type=str, multiple=True,
+              help="Supplemental value fields or other field numbers: '<name>=<field number>[:dtype=<dtype>]' "
+                   "(field numbers are 1-based); repeat for each field.")
+@click.option("--count-as-float", is_flag=True, default=False, help="Store the 'count' column as floating point.")
+@click.option("--one-based", is_flag=True, default=False,
+              help="The bin IDs of a COO file (the start coordinates of a BG2 file) are one-based.")
+@click.option("--comment-char", type=str, default="#", show_default=True, help="Comment character that skips lines.")
+@click.option("--no-symmetric-upper", "-N", is_flag=True, default=False,
+              help="Create a complete square matrix without implicit symmetry.")
+@click.option("--input-copy-status", type=click.Choice(["unique", "duplex"]), default="unique", show_default=True,
+              help="'unique': lower-triangle records are mirrored; 'duplex': they are dropped (symmetric-upper only).")
+@click.option("--chunksize", "-c", type=int, default=int(20e6), show_default=True,
+              help="Lines of the input parsed (and duplicate-checked) at a time.")
+@click.option("--mergebuf", type=int, help="Rows of the merged table written at a time. Default: CHUNKSIZE.")
+@click.option("--temp-dir", type=str, help="Accepted for compatibility; ignored (no temporary coolers).")
+@click.option("--max-merge", type=int, default=200, help="Accepted for compatibility; ignored.")
+@click.option("--no-delete-temp", is_flag=True, default=False, help="Accepted for compatibility; ignored.")
+@click.option("--storage-options", help="HDF5 filter options 'k1=v1,k2=v2,...'.")
+@click.option("--append", "-a", is_flag=True, default=False,
+              help="Append the output cooler to an existing file instead of overwriting the file.")
+def load(bins_path, pixels_path, cool_path, format_, metadata, assembly, field, count_as_float, one_based,
+         comment_char, no_symmetric_upper, input_copy_status, chunksize, mergebuf, temp_dir, max_merge,
+         no_delete_temp, storage_options, append):
+    """Create a cooler from a pre-binned matrix in COO or BG2 text form, records in any order
+    (cli/load.py:15-400).  PIXELS_PATH '-' reads stdin; the file may be compressed.
+
+    The reference sorts every chunk into a temporary cooler and merges the files; here the chunks are checked,
+    parked on the GPU and merged by one device-wide sort / reduce-by-key (create.create_from_unordered)."""
+    import json
+
+    import pandas as pd
+
+    from . import ingest
+    from .create import _bins_arrays, create_from_unordered
+    chromsizes, bins = parse_bins(bins_path)
+    if mergebuf is None:
+        mergebuf = chunksize
+    symmetric_upper = not no_symmetric_upper
+    tril_action = None
+    if symmetric_upper:                                           # cli/load.py:199-204
+        tril_action = "reflect" if input_copy_status == "unique" else "drop"
+    if metadata is not None:
+        with open(metadata) as f:
+            metadata = json.load(f)
+    out_names = ["bin1_id", "bin2_id"]
+    out_dtypes = {"bin1_id": np.int64, "bin2_id": np.int64, "count": np.int32}
+    if format_ == "bg2":
+        in_names = ["chrom1", "start1", "end1", "chrom2", "start2", "end2"]
+        in_dtypes = {"chrom1": str, "start1": int, "end1": int, "chrom2": str, "start2": int, "end2": int,
+                     "count": out_dtypes["count"]}
+        in_numbers = {"chrom1": 0, "start1": 1, "end1": 2, "chrom2": 3, "start2": 4, "end2": 5, "count": 6}
+    else:
+        in_names = ["bin1_id", "bin2_id"]
+        in_dtypes = {"bin1_id": int, "bin2_id": int, "count": out_dtypes["count"]}
+        in_numbers = {"bin1_id": 0, "bin2_id": 1, "count": 2}
+    if len(field):                                                # cli/load.py:270-305
+        for arg in field:
+            name, colnum, dtype = _parse_load_field(arg)
+            if colnum is None:
+                if name in ("bin1_id", "bin2_id") and dtype is not None:
+                    out_dtypes[name] = dtype
+                    continue
+                if name == "count" and dtype is not None:
+                    in_names.append("count")
+                    out_names.append("count")
+                    in_dtypes[name] = out_dtypes[name] = dtype
+                    continue
+                raise click.BadParameter("A field number is required.", param_hint=arg)
+            if name not in in_names:
+                in_names.append(name)
+            if name not in out_names:
+                out_names.append(name)
+            in_numbers[name] = colnum
+            if dtype is not None:
+                in_dtypes[name] = out_dtypes[name] = dtype
+    else:
+        in_names.append("count")
+        out_names.append("count")
+    if "count" in in_names and count_as_float:
+        in_dtypes["count"] = out_dtypes["count"] = np.float64
+    h5opts = None
+    if storage_options is not None:
+        h5opts = {}
+        for kv in storage_options.split(","):
+            k, v = kv.split("=", 1)
+            h5opts[k.strip()] = int(v) if v.strip().lstrip("-").isdigit() else v.strip()
+    order = sorted(in_names, key=in_numbers.get)                  # read_csv hands usecols back in file order
+    reader = pd.read_csv(sys.stdin if pixels_path == "-" else pixels_path, sep="\t", comment=comment_char or None,
+                         header=None, usecols=[in_numbers[n] for n in order], names=order,
+                         dtype={n: in_dtypes[n] for n in order if n in in_dtypes}, iterator=True,
+                         chunksize=chunksize, compression="infer")
+    names, ids, start, end, _ = _bins_arrays(bins)
+    lengths = np.asarray(end)[np.r_[ids[1:] != ids[:-1], True]] if len(ids) else np.zeros(0, np.int64)
+
+    def pipeline():
+        for chunk in reader:
+            cols = {k: chunk[k].to_numpy() for k in chunk.columns}
+            if format_ == "bg2":
+                yield ingest.sanitize_bg2(cols, names, lengths, ids, start, end, is_one_based=one_based,
+                                          tril_action=tril_action)
+            else:
+                yield ingest.sanitize_pixels(cols, is_one_based=one_based, tril_action=tril_action)
+
+    create_from_unordered(cool_path, bins, pipeline(), columns=out_names, dtypes=out_dtypes, metadata=metadata,
+                          assembly=assembly, mergebuf=mergebuf, triucheck=symmetric_upper,
+                          symmetric_upper=symmetric_upper, h5opts=h5opts, mode="a" if append else "w")
 
 
 @cli.command()

@@ -21,7 +21,7 @@ import numpy as np
 from . import h5lite, h5write
 from .store import parse_cooler_uri
 
-__all__ = ["create_cooler", "copy_cooler", "BadInputError", "MAGIC", "MAGIC_MCOOL"]
+__all__ = ["create_cooler", "create_from_unordered", "copy_cooler", "BadInputError", "MAGIC", "MAGIC_MCOOL"]
 
 MAGIC = "HDF5::Cooler"                    # create/_constants.py:3-5
 MAGIC_MCOOL = "HDF5::MCOOL"
@@ -233,6 +233,59 @@ def create_cooler(cool_uri, bins, pixels, columns=None, dtypes=None, metadata=No
     finally:
         f.close()
     return nnz, total
+
+
+def create_from_unordered(cool_uri, bins, chunks, columns=None, dtypes=None, mode=None, mergebuf=20_000_000,
+                          delete_temp=True, temp_dir=None, max_merge=200, device="cuda", **kwargs):
+    """Create a cooler from pixel chunks given in ANY order (``cooler.create.create_from_unordered``,
+    create/_create.py:716-812; the back end of ``cooler load``).
+
+    The reference writes every chunk, sorted, to a temporary cooler (``create(...)`` with its chunk checks)
+    and k-way merges the temporary files with ``CoolerMerger`` (every value column summed).  Here every
+    chunk gets the same checks -- bounds and the upper-triangle rule on the host, duplicates inside a chunk by
+    a sort + run count on the device --, is parked on the GPU, and one device-wide stable sort + reduce-by-key
+    merges all of them (``ingest.UnorderedPixels``).  As in the reference, value columns are cast to their
+    output ``dtypes`` chunk by chunk (the temporary coolers store them that way) before they are summed.
+    ``mergebuf`` sets the chunking of the output; ``delete_temp``, ``temp_dir`` and ``max_merge`` are
+    accepted and ignored (nothing is spilled to disk)."""
+    import pandas as pd
+
+    from .ingest import UnorderedPixels
+    value_cols = [c for c in (["count"] if columns is None else list(columns)) if c not in ("bin1_id", "bin2_id")]
+    dt = dict(_PIXEL_DTYPES)
+    dt.update(dict(dtypes or {}))
+    for c in value_cols:
+        dt.setdefault(c, float)
+    boundscheck = kwargs.pop("boundscheck", True)
+    triucheck = kwargs.pop("triucheck", True) and kwargs.get("symmetric_upper", True)
+    dupcheck = kwargs.pop("dupcheck", True)
+    kwargs.pop("ensure_sorted", None)
+    n_bins = len(bins)
+    acc = UnorderedPixels(n_bins, device=device)
+    parts = {c: [] for c in value_cols}
+    for chunk in chunks:
+        if isinstance(chunk, pd.DataFrame):
+            chunk = {k: v.values for k, v in chunk.items()}
+        for col in ("bin1_id", "bin2_id", *value_cols):
+            if col not in chunk:
+                kind = "Standard" if col in _PIXEL_DTYPES else "User"
+                raise ValueError(f"{kind} column not found in input: '{col}'")
+        _validate_chunk(chunk, n_bins, boundscheck, triucheck, False, False)
+        acc.add(np.asarray(chunk["bin1_id"]), np.asarray(chunk["bin2_id"]), dupcheck=dupcheck)
+        for c in value_cols:
+            parts[c].append(np.asarray(chunk[c]).astype(dt[c], copy=False))
+    cat = {c: (np.concatenate(parts[c]) if parts[c] else np.zeros(0, dtype=dt[c])) for c in value_cols}
+    b1, b2, vals = acc.merge(cat)
+
+    def merged():
+        step = max(int(mergebuf), 1)
+        for lo in range(0, len(b1), step):
+            out = {"bin1_id": b1[lo:lo + step], "bin2_id": b2[lo:lo + step]}
+            out.update({c: vals[c][lo:lo + step] for c in value_cols})
+            yield out
+
+    return create_cooler(cool_uri, bins, merged(), columns=value_cols, dtypes=dt, mode=mode, boundscheck=False,
+                         triucheck=False, dupcheck=False, ensure_sorted=False, **kwargs)
 
 
 def copy_cooler(src, dst_uri, columns=("count",), mode="w"):

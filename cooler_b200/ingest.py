@@ -15,10 +15,11 @@ import numpy as np
 import torch
 
 from . import _lib
-from .reduce import _reduce_runs
-from .table import _ptr, _stream, _use_device, key_bits_for, sort_pairs, swap_key_other
+from .reduce import _aggregate_runs, _reduce_runs, _settle_dtypes
+from .table import _new_px, _ptr, _stream, _use_device, exclusive_scan_i32, key_bits_for, n_tiles, sort_pairs, \
+    swap_key_other
 
-__all__ = ["bin_pairs", "BadInputError"]
+__all__ = ["bin_pairs", "BadInputError", "sanitize_pixels", "sanitize_bg2", "UnorderedPixels"]
 
 _TRIL = {None: 0, "reflect": 1, "drop": 2, "raise": 3}
 
@@ -102,3 +103,158 @@ def bin_pairs(chrom1_ids, pos1, chrom2_ids, pos2, chromsizes, binsize, *, is_one
     cnt = torch.empty(n_out, dtype=torch.int32, device=dev)
     _lib.call("cb200_unpack_pixels", _ptr(k2), _ptr(v2), n_out, _ptr(b1), _ptr(b2), _ptr(cnt), _stream())
     return {"bin1_id": b1.cpu().numpy(), "bin2_id": b2.cpu().numpy(), "count": cnt.cpu().numpy()}
+
+
+# ------------------------------------------------------------------------------------------------
+# Already-binned or bedGraph-2D text records in any order: the sanitizers of ``cooler load``
+# (host, vectorised numpy -- the text parser dominates them) and the device side of
+# ``create_from_unordered`` (create/_create.py:716-812): where the reference sorts every chunk into a
+# temporary cooler file and k-way merges the files (CoolerMerger, every value column summed), the
+# chunks are parked on the device and ONE pair of stable radix sorts + one reduce-by-key per value
+# column does the merge (the kernels of the coarsening / merging path).
+# ------------------------------------------------------------------------------------------------
+def sanitize_pixels(chunk, *, is_one_based=False, tril_action="reflect"):
+    """``_sanitize_pixels`` (create/_ingest.py:307-349) for a dict / frame of arrays with ``bin1_id``,
+    ``bin2_id`` and value columns: one-based ids become zero-based; pixels below the diagonal are
+    mirrored ('reflect'), discarded ('drop'), refused ('raise') or kept (None).  Order is kept (the
+    device sorts).  Returns a dict of numpy arrays."""
+    if tril_action not in _TRIL:
+        raise ValueError(f"Unknown tril_action value: '{tril_action}'")
+    out = {k: np.asarray(v) for k, v in dict(chunk).items()}
+    b1, b2 = out["bin1_id"].astype(np.int64), out["bin2_id"].astype(np.int64)
+    if is_one_based:
+        b1, b2 = b1 - 1, b2 - 1
+    if tril_action is not None:
+        low = b1 > b2
+        if low.any():
+            if tril_action == "raise":
+                raise BadInputError("Found bin1_id greater than bin2_id")
+            if tril_action == "reflect":
+                b1, b2 = np.where(low, b2, b1), np.where(low, b1, b2)
+            else:
+                keep = ~low
+                b1, b2 = b1[keep], b2[keep]
+                out = {k: v[keep] for k, v in out.items()}
+    out["bin1_id"], out["bin2_id"] = b1, b2
+    return out
+
+
+def sanitize_bg2(chunk, chromnames, chromsizes, bins_chrom, bins_start, bins_end, *, is_one_based=False,
+                 tril_action="reflect", validate=True):
+    """``_sanitize_records`` with the ``bg2`` preset (create/_ingest.py:45-55, 68-214): columns
+    ``chrom1, start1, chrom2, start2`` (+ value columns) -> ``bin1_id, bin2_id`` (+ value columns).
+    Records on chromosomes that are not in the bin table are dropped, anchors are checked against the
+    chromosome lengths, records below the diagonal (by chromosome order, then anchor) are mirrored /
+    dropped / refused, and every anchor gets the bin that contains it -- ``offset[chrom] + start //
+    binsize`` for fixed-size bins, else the last bin of the chromosome starting at or before it."""
+    if tril_action not in _TRIL:
+        raise ValueError(f"Unknown tril_action value: '{tril_action}'")
+    import pandas as pd
+    out = {k: np.asarray(v) for k, v in dict(chunk).items()}
+    idx = pd.Index([str(c) for c in chromnames])
+    c1 = idx.get_indexer(pd.Index(out["chrom1"]).astype(str)).astype(np.int64)
+    c2 = idx.get_indexer(pd.Index(out["chrom2"]).astype(str)).astype(np.int64)
+    a1, a2 = out["start1"], out["start2"]
+    if validate and not (np.issubdtype(a1.dtype, np.integer) and np.issubdtype(a2.dtype, np.integer)):
+        raise BadInputError("Found a non-integer anchor column")
+    known = (c1 >= 0) & (c2 >= 0)
+    if not known.all():
+        c1, c2, a1, a2 = c1[known], c2[known], a1[known], a2[known]
+        out = {k: v[known] for k, v in out.items()}
+    a1, a2 = a1.astype(np.int64), a2.astype(np.int64)
+    if is_one_based:
+        a1, a2 = a1 - 1, a2 - 1
+    sizes = np.asarray(chromsizes, dtype=np.int64)
+    if validate and len(a1):
+        if ((a1 < 0) | (a2 < 0)).any():
+            raise BadInputError("Found an anchor position with negative value. Make sure your coordinates are "
+                                "1-based or use the --zero-based option when loading.")
+        if ((a1 > sizes[c1]) | (a2 > sizes[c2])).any():
+            raise BadInputError("Found an anchor position exceeding chromosome length")
+    if tril_action is not None and len(a1):
+        low = (c1 > c2) | ((c1 == c2) & (a1 > a2))
+        if low.any():
+            if tril_action == "raise":
+                raise BadInputError("Found lower triangle pairs")
+            if tril_action == "reflect":
+                c1, c2 = np.where(low, c2, c1), np.where(low, c1, c2)
+                a1, a2 = np.where(low, a2, a1), np.where(low, a1, a2)
+            else:
+                keep = ~low
+                c1, c2, a1, a2 = c1[keep], c2[keep], a1[keep], a2[keep]
+                out = {k: v[keep] for k, v in out.items()}
+    bins_chrom = np.asarray(bins_chrom, dtype=np.int64)
+    bins_start = np.asarray(bins_start, dtype=np.int64)
+    nb = np.bincount(bins_chrom, minlength=len(sizes))
+    binoff = np.r_[0, np.cumsum(nb)]                                   # GenomeSegmentation.chrom_binoffset
+    from .create import _binsize
+    binsize = _binsize(bins_chrom, bins_start, np.asarray(bins_end, dtype=np.int64))
+    if binsize is not None:
+        b1, b2 = binoff[c1] + a1 // binsize, binoff[c2] + a2 // binsize
+    else:
+        abspos = np.r_[0, np.cumsum(sizes)]                            # chrom_abspos / start_abspos
+        start_abs = abspos[bins_chrom] + bins_start
+        b1 = np.minimum(np.searchsorted(start_abs, abspos[c1] + a1, side="right") - 1, binoff[c1 + 1] - 1)
+        b2 = np.minimum(np.searchsorted(start_abs, abspos[c2] + a2, side="right") - 1, binoff[c2 + 1] - 1)
+    res = {"bin1_id": b1.astype(np.int64), "bin2_id": b2.astype(np.int64)}
+    res.update({k: v for k, v in out.items() if k not in ("chrom1", "start1", "end1", "chrom2", "start2", "end2")})
+    return res
+
+
+class UnorderedPixels:
+    """Device side of ``create_from_unordered``: ``add`` parks a sanitized chunk of (bin1, bin2) ids on
+    the device -- its duplicate check (``create(..., dupcheck=True)`` of every temporary cooler,
+    create/_ingest.py:421-427) is a sort of the chunk + a run count --; ``merge`` sorts all parked
+    pixels by (bin1, bin2), stable, and sums every value column per pixel in input order."""
+
+    def __init__(self, n_bins, device="cuda"):
+        self.dev = _use_device(device)
+        self.n_bins = int(n_bins)
+        if self.n_bins >= 2**31 - 2:
+            raise ValueError("n_bins must fit int32")
+        self.bits = key_bits_for(max(self.n_bins, 1))
+        self.keys, self.vals, self.n = [], [], 0
+
+    def _sorted(self, key, val, n):
+        ks, vs = sort_pairs(key, val, self.bits)                       # by bin2
+        kr, vr = swap_key_other(ks, vs, n)                             # key = bin1, val = {bin2, position}
+        del ks, vs
+        return sort_pairs(kr, vr, self.bits)                           # by bin1 (stable): (bin1, bin2) order
+
+    def add(self, bin1, bin2, dupcheck=True):
+        m = len(bin1)
+        if m == 0:
+            return
+        if self.n + m >= 2**31 - 1:
+            raise NotImplementedError("the unordered ingest path indexes pixels with int32")
+        b1 = torch.from_numpy(np.ascontiguousarray(bin1, dtype=np.int32)).to(self.dev)
+        key = torch.from_numpy(np.ascontiguousarray(bin2, dtype=np.int32)).to(self.dev)
+        pos = torch.arange(self.n, self.n + m, dtype=torch.int32, device=self.dev)
+        val = _new_px(m, self.dev)
+        _lib.call("cb200_pack_pixels_i32", _ptr(b1), _ptr(pos), m, _ptr(val), _stream())   # {bin1, position}
+        if dupcheck:
+            kr, vr = self._sorted(key, val, m)
+            tile_count = torch.zeros(max(n_tiles(m), 1), dtype=torch.int32, device=self.dev)
+            _lib.call("cb200_runs_count", _ptr(kr), _ptr(vr), m, _ptr(tile_count), _stream())
+            if int(exclusive_scan_i32(tile_count[: n_tiles(m)])[-1].item()) != m:
+                raise BadInputError("Found duplicate pixels")
+        self.keys.append(key)
+        self.vals.append(val[:m])
+        self.n += m
+
+    def merge(self, columns, dtypes=None):
+        """``columns``: {name: host array over ALL added pixels in the order they were added}.  Returns
+        (bin1 int64, bin2 int64, {name: summed column}) sorted by (bin1, bin2), one entry per pixel --
+        CoolerMerger's ``groupby([bin1_id, bin2_id], sort=True).sum()`` over the chunks."""
+        n = self.n
+        if n == 0:
+            e = np.zeros(0, dtype=np.int64)
+            return e, e, {c: np.asarray(v)[:0] for c, v in columns.items()}
+        key = torch.cat(self.keys)
+        val = torch.cat(self.vals + [torch.zeros((2, 2), dtype=torch.int32, device=self.dev)])
+        self.keys, self.vals = [], []
+        kr, vr = self._sorted(key, val, n)
+        del key, val
+        cols = {c: np.asarray(v) for c, v in columns.items()}
+        b1, b2, out = _aggregate_runs(kr, vr, n, cols, {}, self.dev)
+        return b1, b2, _settle_dtypes(out, {c: v.dtype for c, v in cols.items()}, {})
