@@ -372,7 +372,8 @@ def cload():
               help="Create a complete square matrix without implicit symmetry.")
 @click.option("--input-copy-status", type=click.Choice(["unique", "duplex"]), default="unique", show_default=True,
               help="Copy status of input data when using symmetric-upper storage.")
-@click.option("--field", type=str, multiple=True, help="Extra value columns (not supported by the GPU path).")
+@click.option("--field", type=str, multiple=True,
+              help="Value columns next to the pair counts: '<name>=<field number>[:dtype=<dtype>][,agg=<agg>]'.")
 @click.option("--chunksize", "-c", type=int, default=15_000_000, help="Lines of the input parsed at a time.")
 @click.option("--mergebuf", type=int, help="Accepted for compatibility; ignored (one device-wide sort).")
 @click.option("--max-merge", type=int, default=200, help="Accepted for compatibility; ignored.")
@@ -394,12 +395,14 @@ def pairs(bins, pairs_path, cool_path, metadata, assembly, chrom1, pos1, chrom2,
 
     from . import ingest
     from .create import create_cooler
-    if len(field):
-        raise click.UsageError("--field value columns are not supported by the B200 ingest path")
     chromsizes, bins = parse_bins(bins)
     from .create import _binsize, _bins_arrays
     names, ids, start, end, _ = _bins_arrays(bins)
     binsize = _binsize(ids, start, end)
+    if len(field):
+        return _cload_pairs_with_fields(bins, pairs_path, cool_path, metadata, assembly, chrom1, pos1, chrom2, pos2,
+                                        zero_based, comment_char, no_symmetric_upper, input_copy_status, field,
+                                        chunksize, mergebuf, storage_options, append)
     uniform = binsize is not None and np.array_equal(
         np.asarray(start), np.concatenate([np.arange(k) * binsize for k in np.bincount(ids)]))
     if not uniform:
@@ -444,8 +447,89 @@ def pairs(bins, pairs_path, cool_path, metadata, assembly, chrom1, pos1, chrom2,
                   symmetric_upper=symmetric_upper, h5opts=h5opts, mode="a" if append else "w")
 
 
-def _parse_load_field(arg):
-    """'<name>[=<field number>][:dtype=<dtype>]' (cli/_util.py:53-97 with includes_agg=False)."""
+def _cload_pairs_with_fields(bins, pairs_path, cool_path, metadata, assembly, chrom1, pos1, chrom2, pos2, zero_based,
+                             comment_char, no_symmetric_upper, input_copy_status, field, chunksize, mergebuf,
+                             storage_options, append):
+    """``cooler cload pairs --field <name>=<number>[:dtype=..,agg=..]`` (cli/cload.py:540-666): value columns
+    next to the pair counts.  As in the reference every chunk of records is sanitized and aggregated per pixel
+    with the requested functions (``aggregate_records``; the count is the group size unless a field is named
+    ``count``), and the chunk tables are then merged by SUMMING every column (``create_from_unordered`` ->
+    ``CoolerMerger``).  Both aggregations run on the device (``ingest.UnorderedPixels``); the records are
+    sanitized on the host (``ingest.sanitize_records``, the ``pairs`` preset)."""
+    import json
+
+    import pandas as pd
+
+    from . import ingest
+    from .create import _bins_arrays, create_from_unordered
+    symmetric_upper = not no_symmetric_upper
+    tril_action = None
+    if symmetric_upper:
+        tril_action = "reflect" if input_copy_status == "unique" else "drop"
+    if metadata is not None:
+        with open(metadata) as f:
+            metadata = json.load(f)
+    in_numbers = {}
+    for name, num in (("chrom1", chrom1), ("pos1", pos1), ("chrom2", chrom2), ("pos2", pos2)):
+        if num == 0:
+            raise click.BadParameter("Field numbers start at 1", param_hint=name)
+        in_numbers[name] = num - 1
+    in_dtypes = {"chrom1": str, "pos1": np.int64, "chrom2": str, "pos2": np.int64}
+    out_names, out_dtypes, aggregations = [], {}, {}
+    for arg in field:                                             # cli/cload.py:546-585
+        name, colnum, dtype, agg = _parse_input_field(arg, includes_agg=True)
+        if colnum is None:
+            if agg is None and dtype is not None and name in ("bin1_id", "bin2_id", "count"):
+                out_dtypes[name] = dtype
+                continue
+            raise click.BadParameter("A field number is required.", param_hint=arg)
+        if name not in out_names:
+            out_names.append(name)
+        in_numbers[name] = colnum
+        if dtype is not None:
+            in_dtypes[name] = out_dtypes[name] = dtype
+        aggregations[name] = agg if agg is not None else "sum"
+    if "count" not in out_names:
+        out_names.append("count")
+    h5opts = None
+    if storage_options is not None:
+        h5opts = {}
+        for kv in storage_options.split(","):
+            k, v = kv.split("=", 1)
+            h5opts[k.strip()] = int(v) if v.strip().lstrip("-").isdigit() else v.strip()
+    order = sorted(in_numbers, key=in_numbers.get)                # read_csv hands usecols back in file order
+    reader = pd.read_csv(sys.stdin if pairs_path == "-" else pairs_path, sep="\t", comment=comment_char or None,
+                         header=None, usecols=[in_numbers[n] for n in order], names=order,
+                         dtype={n: in_dtypes[n] for n in order if n in in_dtypes}, iterator=True,
+                         chunksize=chunksize, compression="infer")
+    names, ids, start, end, _ = _bins_arrays(bins)
+    lengths = np.asarray(end)[np.r_[ids[1:] != ids[:-1], True]] if len(ids) else np.zeros(0, np.int64)
+    n_bins = len(ids)
+
+    def pipeline():
+        for chunk in reader:
+            rec = ingest.sanitize_records({k: chunk[k].to_numpy() for k in chunk.columns}, names, lengths, ids,
+                                          start, end, anchor_field="pos", is_one_based=not zero_based,
+                                          tril_action=tril_action)
+            vals = {f: rec[f] for f in aggregations}
+            agg = dict(aggregations)
+            if "count" not in agg:                                # aggregate_records(count=True): the group size
+                vals["count"] = np.ones(len(rec["bin1_id"]), dtype=np.int64)
+                agg["count"] = "sum"
+            acc = ingest.UnorderedPixels(n_bins)
+            acc.add(rec["bin1_id"], rec["bin2_id"], dupcheck=False)
+            b1, b2, out = acc.merge(vals, agg)
+            yield {"bin1_id": b1, "bin2_id": b2, **out}
+
+    create_from_unordered(cool_path, bins, pipeline(), columns=out_names, dtypes=out_dtypes, metadata=metadata,
+                          assembly=assembly, mergebuf=mergebuf or chunksize, boundscheck=False, triucheck=False,
+                          dupcheck=False, symmetric_upper=symmetric_upper, h5opts=h5opts,
+                          mode="a" if append else "w")
+
+
+def _parse_input_field(arg, includes_agg=False):
+    """'<name>[=<field number>][:dtype=<dtype>][,agg=<agg>]' (cli/_util.py:53-97): (name, 0-based column |
+    None, dtype | None, agg | None)."""
     parts = arg.split(":")
     if len(parts) > 2:
         raise click.BadParameter(arg)
@@ -460,17 +544,20 @@ def _parse_load_field(arg):
             raise click.BadParameter(f"Not a number: '{head[1]}'", param_hint=arg) from e
         if colnum < 0:
             raise click.BadParameter("Field numbers start at 1.", param_hint=arg)
-    dtype = None
+    dtype = agg = None
     if len(parts) == 2:
         for item in parts[1].split(","):
             try:
                 prop, value = item.split("=")
             except ValueError as e:
                 raise click.BadParameter(arg) from e
-            if prop != "dtype":
+            if prop == "dtype":
+                dtype = np.dtype(value)
+            elif prop == "agg" and includes_agg:
+                agg = value
+            else:
                 raise click.BadParameter(f"Invalid property: '{prop}'.", param_hint=arg)
-            dtype = np.dtype(value)
-    return name, colnum, dtype
+    return name, colnum, dtype, agg
 
 
 @cli.command()
@@ -539,7 +626,7 @@ def load(bins_path, pixels_path, cool_path, format_, metadata, assembly, field, 
         in_numbers = {"bin1_id": 0, "bin2_id": 1, "count": 2}
     if len(field):                                                # cli/load.py:270-305
         for arg in field:
-            name, colnum, dtype = _parse_load_field(arg)
+            name, colnum, dtype, _ = _parse_input_field(arg)
             if colnum is None:
                 if name in ("bin1_id", "bin2_id") and dtype is not None:
                     out_dtypes[name] = dtype

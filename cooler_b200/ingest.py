@@ -19,7 +19,7 @@ from .reduce import _aggregate_runs, _reduce_runs, _settle_dtypes
 from .table import _new_px, _ptr, _stream, _use_device, exclusive_scan_i32, key_bits_for, n_tiles, sort_pairs, \
     swap_key_other
 
-__all__ = ["bin_pairs", "BadInputError", "sanitize_pixels", "sanitize_bg2", "UnorderedPixels"]
+__all__ = ["bin_pairs", "BadInputError", "sanitize_pixels", "sanitize_records", "sanitize_bg2", "UnorderedPixels"]
 
 _TRIL = {None: 0, "reflect": 1, "drop": 2, "raise": 3}
 
@@ -139,22 +139,25 @@ def sanitize_pixels(chunk, *, is_one_based=False, tril_action="reflect"):
     return out
 
 
-def sanitize_bg2(chunk, chromnames, chromsizes, bins_chrom, bins_start, bins_end, *, is_one_based=False,
-                 tril_action="reflect", validate=True):
-    """``_sanitize_records`` with the ``bg2`` preset (create/_ingest.py:45-55, 68-214): columns
-    ``chrom1, start1, chrom2, start2`` (+ value columns) -> ``bin1_id, bin2_id`` (+ value columns).
+def sanitize_records(chunk, chromnames, chromsizes, bins_chrom, bins_start, bins_end, *, anchor_field="start",
+                     is_one_based=False, tril_action="reflect", validate=True):
+    """``_sanitize_records`` (create/_ingest.py:68-214) with string chromosome columns (``decode_chroms``):
+    columns ``chrom1, <anchor>1, chrom2, <anchor>2`` (+ value columns) -> ``bin1_id, bin2_id`` (+ value
+    columns); ``anchor_field`` is ``start`` for the ``bg2`` preset (:45-55) and ``pos`` for ``pairs`` (:56-66).
     Records on chromosomes that are not in the bin table are dropped, anchors are checked against the
     chromosome lengths, records below the diagonal (by chromosome order, then anchor) are mirrored /
-    dropped / refused, and every anchor gets the bin that contains it -- ``offset[chrom] + start //
-    binsize`` for fixed-size bins, else the last bin of the chromosome starting at or before it."""
+    dropped / refused, and every anchor gets the bin that contains it -- ``offset[chrom] + anchor //
+    binsize`` for fixed-size bins, else the last bin of the chromosome starting at or before it.  Order is
+    kept (the device sorts)."""
     if tril_action not in _TRIL:
         raise ValueError(f"Unknown tril_action value: '{tril_action}'")
     import pandas as pd
+    f1, f2 = anchor_field + "1", anchor_field + "2"
     out = {k: np.asarray(v) for k, v in dict(chunk).items()}
     idx = pd.Index([str(c) for c in chromnames])
     c1 = idx.get_indexer(pd.Index(out["chrom1"]).astype(str)).astype(np.int64)
     c2 = idx.get_indexer(pd.Index(out["chrom2"]).astype(str)).astype(np.int64)
-    a1, a2 = out["start1"], out["start2"]
+    a1, a2 = out[f1], out[f2]
     if validate and not (np.issubdtype(a1.dtype, np.integer) and np.issubdtype(a2.dtype, np.integer)):
         raise BadInputError("Found a non-integer anchor column")
     known = (c1 >= 0) & (c2 >= 0)
@@ -197,8 +200,15 @@ def sanitize_bg2(chunk, chromnames, chromsizes, bins_chrom, bins_start, bins_end
         b1 = np.minimum(np.searchsorted(start_abs, abspos[c1] + a1, side="right") - 1, binoff[c1 + 1] - 1)
         b2 = np.minimum(np.searchsorted(start_abs, abspos[c2] + a2, side="right") - 1, binoff[c2 + 1] - 1)
     res = {"bin1_id": b1.astype(np.int64), "bin2_id": b2.astype(np.int64)}
-    res.update({k: v for k, v in out.items() if k not in ("chrom1", "start1", "end1", "chrom2", "start2", "end2")})
+    sided = {"chrom1", "chrom2", "start1", "start2", "end1", "end2", "pos1", "pos2"}
+    res.update({k: v for k, v in out.items() if k not in sided})
     return res
+
+
+def sanitize_bg2(chunk, chromnames, chromsizes, bins_chrom, bins_start, bins_end, **kwargs):
+    """``sanitize_records`` with the ``bg2`` preset: anchors are the ``start`` columns."""
+    return sanitize_records(chunk, chromnames, chromsizes, bins_chrom, bins_start, bins_end,
+                            anchor_field="start", **kwargs)
 
 
 class UnorderedPixels:
@@ -242,10 +252,13 @@ class UnorderedPixels:
         self.vals.append(val[:m])
         self.n += m
 
-    def merge(self, columns, dtypes=None):
-        """``columns``: {name: host array over ALL added pixels in the order they were added}.  Returns
-        (bin1 int64, bin2 int64, {name: summed column}) sorted by (bin1, bin2), one entry per pixel --
-        CoolerMerger's ``groupby([bin1_id, bin2_id], sort=True).sum()`` over the chunks."""
+    def merge(self, columns, agg=None):
+        """``columns``: {name: host array over ALL added pixels in the order they were added}; ``agg``:
+        {name: "sum" | "min" | "max" | "first" | "last" | "mean"}, default sum.  Returns (bin1 int64, bin2
+        int64, {name: aggregated column}) sorted by (bin1, bin2), one entry per pixel -- CoolerMerger's
+        ``groupby([bin1_id, bin2_id], sort=True).sum()`` over the chunks, or the ``aggregate_records`` of one
+        chunk of records (create/_ingest.py:452-504)."""
+        agg = dict(agg or {})
         n = self.n
         if n == 0:
             e = np.zeros(0, dtype=np.int64)
@@ -256,5 +269,5 @@ class UnorderedPixels:
         kr, vr = self._sorted(key, val, n)
         del key, val
         cols = {c: np.asarray(v) for c, v in columns.items()}
-        b1, b2, out = _aggregate_runs(kr, vr, n, cols, {}, self.dev)
-        return b1, b2, _settle_dtypes(out, {c: v.dtype for c, v in cols.items()}, {})
+        b1, b2, out = _aggregate_runs(kr, vr, n, cols, agg, self.dev)
+        return b1, b2, _settle_dtypes(out, {c: v.dtype for c, v in cols.items()}, agg)

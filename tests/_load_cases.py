@@ -52,3 +52,16 @@ def write_synthetic(path, n_chunks=6, chunk=300, seed=3):
             for q in rng.permutation(len(recs)):
                 a, b, cnt, score = recs[q]
                 f.write(f"{a}\t{b}\t{cnt}\t{score}\n")
+
+
+# `cooler cload pairs --field ...` on the reference's toy.pairs (columns: readID chr1 pos1 chr2 pos2 strand1
+# strand2 score), called like its tests/test_cli_ingest.py:_run_cload_pairs.  key -> (binsize, extra arguments)
+PAIRS_BASE = ["-c1", "2", "-p1", "3", "-c2", "4", "-p2", "5", "--assembly", "toy", "--chunksize", "10"]
+PAIRS_CASES = {
+    "pairs_score": (2, ["--field", "score=8"]),
+    "pairs_count_int": (2, ["--field", "count=8"]),
+    "pairs_count_float": (2, ["--field", "count=8:dtype=float"]),
+    "pairs_count_min": (2, ["--field", "count=8:agg=min,dtype=float"]),
+    "pairs_score_mean_f32": (4, ["--field", "score=8:agg=mean,dtype=float32", "--field", "count:dtype=int64"]),
+    "pairs_max_zero_based": (8, ["--field", "score=8:agg=max", "--zero-based"]),
+}

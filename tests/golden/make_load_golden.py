@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from oracle import refshim  # noqa: E402
 
-from tests._load_cases import CASES, TEXT  # noqa: E402
+from tests._load_cases import CASES, PAIRS_BASE, PAIRS_CASES, TEXT  # noqa: E402
 
 
 def reference_load(fmt, bins_spec, pixels, args):
@@ -98,9 +98,77 @@ def reference_load(fmt, bins_spec, pixels, args):
     return chunks, merged, {c: np.dtype(out_dtypes.get(c, float)) for c in value_cols}
 
 
+def reference_cload_pairs(binsize, args):
+    """cli/cload.py:512-666 followed literally up to ``create_cooler(..., ordered=False)``: the chunks
+    ``aggregate_records(agg, count=True, sort=False)(sanitize_records(schema="pairs", ...)(chunk))`` are cast
+    to the output dtypes (the temporary coolers of create_from_unordered) and merged by summing."""
+    refshim.import_reference()
+    from cooler.cli._util import parse_bins, parse_field_param
+    from cooler.create._ingest import aggregate_records, sanitize_records
+    _, bins = parse_bins(os.path.join(TEXT, f"toy.chrom.sizes:{binsize}"))
+    opt = {"chunksize": 10, "zero_based": False, "field": []}
+    nums = {}
+    it = iter(args)
+    for a in it:
+        if a in ("-c1", "-p1", "-c2", "-p2"):
+            nums[{"-c1": "chrom1", "-p1": "pos1", "-c2": "chrom2", "-p2": "pos2"}[a]] = int(next(it)) - 1
+        elif a == "--chunksize":
+            opt["chunksize"] = int(next(it))
+        elif a == "--field":
+            opt["field"].append(next(it))
+        elif a == "--assembly":
+            next(it)
+        else:
+            opt[a.lstrip("-").replace("-", "_")] = True
+    in_names = ["chrom1", "pos1", "chrom2", "pos2"]
+    in_dtypes = {"chrom1": str, "pos1": np.int64, "chrom2": str, "pos2": np.int64}
+    in_numbers = dict(nums)
+    out_names, out_dtypes, aggregations = [], {}, {}
+    for arg in opt["field"]:
+        name, colnum, dtype, agg = parse_field_param(arg)
+        if colnum is None:
+            assert agg is None and dtype is not None and name in {"bin1_id", "bin2_id", "count"}
+            out_dtypes[name] = dtype
+            continue
+        if name not in in_names:
+            in_names.append(name)
+        if name not in out_names:
+            out_names.append(name)
+        in_numbers[name] = colnum
+        if dtype is not None:
+            in_dtypes[name] = out_dtypes[name] = dtype
+        aggregations[name] = agg if agg is not None else "sum"
+    if "count" not in out_names:
+        out_names.append("count")
+    order = sorted(in_names, key=in_numbers.get)          # field numbers ascending: names line up with usecols
+    reader = pd.read_csv(os.path.join(TEXT, "toy.pairs"), sep="\t", usecols=[in_numbers[n] for n in order],
+                         names=order, dtype=in_dtypes, iterator=True, chunksize=opt["chunksize"])
+    sanitize = sanitize_records(bins, schema="pairs", decode_chroms=True, is_one_based=not opt["zero_based"],
+                                tril_action="reflect", sort=True, validate=True)
+    aggregate = aggregate_records(agg=dict(aggregations), count=True, sort=False)
+    default = {"count": np.int32}
+    chunks = []
+    for raw in reader:
+        chunk = aggregate(sanitize(raw))
+        cols = {"bin1_id": chunk["bin1_id"].to_numpy(np.int64), "bin2_id": chunk["bin2_id"].to_numpy(np.int64)}
+        for c in out_names:
+            cols[c] = chunk[c].to_numpy().astype(out_dtypes.get(c, default.get(c, float)))
+        chunks.append(pd.DataFrame(cols))
+    merged = (pd.concat(chunks, axis=0, ignore_index=True).groupby(["bin1_id", "bin2_id"], sort=True)
+              .aggregate({c: "sum" for c in out_names}).reset_index())
+    return chunks, merged, {c: np.dtype(out_dtypes.get(c, default.get(c, float))) for c in out_names}
+
+
 def main():
     assert refshim.available()
     out = {}
+    for key, (binsize, extra) in PAIRS_CASES.items():
+        chunks, merged, dtypes = reference_cload_pairs(binsize, PAIRS_BASE + extra)
+        for c in merged.columns:
+            v = merged[c].to_numpy()
+            out[f"{key}/merged/{c}"] = v.astype(dtypes[c]) if c in dtypes else v
+        print(key, sum(len(c) for c in chunks), len(merged), {c: str(out[f"{key}/merged/{c}"].dtype) for c in merged.columns},
+              merged.iloc[0].to_dict())
     for key, (fmt, bins_spec, pixels, args) in CASES.items():
         chunks, merged, dtypes = reference_load(fmt, bins_spec, pixels, args)
         cat = pd.concat(chunks, axis=0, ignore_index=True)

@@ -73,10 +73,10 @@ class _NumpyAccumulator:
             raise BadInputError("Found duplicate pixels")
         self.b1.append(np.asarray(bin1)), self.b2.append(np.asarray(bin2))
 
-    def merge(self, columns, dtypes=None):
+    def merge(self, columns, agg=None):
         from oracle import coarsen_numpy
         t = dict(bin1_id=np.concatenate(self.b1), bin2_id=np.concatenate(self.b2), **columns)
-        out = coarsen_numpy.merge_columns([t], list(columns))
+        out = coarsen_numpy.merge_columns([t], list(columns), agg)
         return out.pop("bin1_id"), out.pop("bin2_id"), out
 
 
@@ -118,6 +118,56 @@ def test_load_cli_plumbing_with_numpy_accumulator(key, tmp_path, monkeypatch):
     res = CliRunner().invoke(cli, _args(key, out))
     assert res.exit_code == 0, (res.output, res.exception)
     _check_output(key, out)
+
+
+def _pairs_args(key, out):
+    binsize, extra = LC.PAIRS_CASES[key]
+    return ["cload", "pairs", os.path.join(LC.TEXT, f"toy.chrom.sizes:{binsize}"), os.path.join(LC.TEXT, "toy.pairs"),
+            out, *LC.PAIRS_BASE, *extra]
+
+
+def _check_pairs_output(key, out):
+    from cooler_b200 import store
+    from tests.test_h5write import check
+    check(out)
+    clr = store.open_cooler(out)
+    cols = [k.split("/")[2] for k in G if k.startswith(key + "/merged/")]
+    assert sorted(clr.pixels().dtypes.keys()) == sorted(cols)
+    for c in cols:
+        got, want = np.asarray(clr._load_dset("pixels/" + c)), G[f"{key}/merged/{c}"]
+        assert got.dtype == want.dtype, (c, got.dtype, want.dtype)
+        if want.dtype.kind == "f":
+            np.testing.assert_allclose(got, want, rtol=1e-6 if want.dtype == np.float32 else 1e-12, err_msg=c)
+        else:
+            np.testing.assert_array_equal(got, want, err_msg=c)
+
+
+@pytest.mark.parametrize("key", sorted(LC.PAIRS_CASES))
+def test_cload_pairs_fields_plumbing_with_numpy_accumulator(key, tmp_path, monkeypatch):
+    """`cooler cload pairs --field ...` (reference tests/test_cli_ingest.py:95-135): value columns aggregated
+    per chunk with the requested function, chunk tables summed -- against the reference's own
+    sanitize_records + aggregate_records run chunk by chunk (make_load_golden.py)."""
+    from click.testing import CliRunner
+
+    from cooler_b200 import ingest
+    from cooler_b200.cli import cli
+    monkeypatch.setattr(ingest, "UnorderedPixels", _NumpyAccumulator)
+    out = str(tmp_path / "out.cool")
+    res = CliRunner().invoke(cli, _pairs_args(key, out))
+    assert res.exit_code == 0, (res.output, res.exception)
+    _check_pairs_output(key, out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", sorted(LC.PAIRS_CASES))
+def test_cload_pairs_fields_gpu(key, tmp_path):
+    from click.testing import CliRunner
+
+    from cooler_b200.cli import cli
+    out = str(tmp_path / "out.cool")
+    res = CliRunner().invoke(cli, _pairs_args(key, out))
+    assert res.exit_code == 0, (res.output, res.exception)
+    _check_pairs_output(key, out)
 
 
 def _bad_inputs(tmp_path):
