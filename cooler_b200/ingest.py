@@ -237,6 +237,11 @@ class UnorderedPixels:
             return
         if self.n + m >= 2**31 - 1:
             raise NotImplementedError("the unordered ingest path indexes pixels with int32")
+        b1h, b2h = np.asarray(bin1), np.asarray(bin2)
+        if min(int(b1h.min()), int(b2h.min())) < 0 or max(int(b1h.max()), int(b2h.max())) >= self.n_bins:
+            # the radix sorts look at the bits of a valid bin id only: an id outside [0, n_bins) must not get here
+            raise BadInputError("Found a bin ID that exceeds the declared number of bins. "
+                                "Check whether your bin table is correct.")
         b1 = torch.from_numpy(np.ascontiguousarray(bin1, dtype=np.int32)).to(self.dev)
         key = torch.from_numpy(np.ascontiguousarray(bin2, dtype=np.int32)).to(self.dev)
         pos = torch.arange(self.n, self.n + m, dtype=torch.int32, device=self.dev)

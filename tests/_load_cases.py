@@ -63,5 +63,5 @@ PAIRS_CASES = {
     "pairs_count_float": (2, ["--field", "count=8:dtype=float"]),
     "pairs_count_min": (2, ["--field", "count=8:agg=min,dtype=float"]),
     "pairs_score_mean_f32": (4, ["--field", "score=8:agg=mean,dtype=float32", "--field", "count:dtype=int64"]),
-    "pairs_max_zero_based": (8, ["--field", "score=8:agg=max", "--zero-based"]),
+    "pairs_max_binsize8": (8, ["--field", "score=8:agg=max"]),
 }

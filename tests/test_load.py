@@ -65,10 +65,12 @@ class _NumpyAccumulator:
     """Stands in for ingest.UnorderedPixels on the CPU (same contract)."""
 
     def __init__(self, n_bins, device="cuda"):
-        self.b1, self.b2 = [], []
+        self.b1, self.b2, self.n_bins = [], [], n_bins
 
     def add(self, bin1, bin2, dupcheck=True):
         from cooler_b200.ingest import BadInputError
+        if len(bin1) and (min(np.min(bin1), np.min(bin2)) < 0 or max(np.max(bin1), np.max(bin2)) >= self.n_bins):
+            raise BadInputError("Found a bin ID that exceeds the declared number of bins.")
         if dupcheck and len(np.unique(np.asarray(bin1) * (1 << 32) + np.asarray(bin2))) != len(bin1):
             raise BadInputError("Found duplicate pixels")
         self.b1.append(np.asarray(bin1)), self.b2.append(np.asarray(bin2))
@@ -195,6 +197,10 @@ def _run_errors(tmp_path):
     assert res.exit_code == 0, res.exception                     # the two records sit in different chunks: summed
     res = CliRunner().invoke(cli, ["load", "-f", "coo", bins, oob, out])
     assert res.exit_code != 0 and isinstance(res.exception, CreateError) and "exceeds" in str(res.exception)
+    # toy.pairs is one-based: read as zero-based its last position equals the chromosome length, which passes the
+    # anchor check (`> chromsize`, create/_ingest.py:142) but lands on bin n_bins -- refused like in bin_pairs
+    res = CliRunner().invoke(cli, _pairs_args("pairs_max_binsize8", out) + ["--zero-based"])
+    assert res.exit_code != 0 and isinstance(res.exception, BadInputError) and "exceeds" in str(res.exception)
     res = CliRunner().invoke(cli, ["load", "-f", "coo", bins, low, out, "-N"])
     assert res.exit_code == 0, res.exception                     # square storage keeps the lower pixel
     return out
