@@ -369,7 +369,8 @@ def _aggregate_runs(keys, vals, n, columns, agg, dev):
         if callable(op) or op not in AGG_OPS:
             raise NotImplementedError(f"aggregator {op!r} is not supported by the CUDA path "
                                       f"(supported: {sorted(AGG_OPS)})")
-        t = torch.from_numpy(np.ascontiguousarray(col))
+        a = np.ascontiguousarray(col)
+        t = torch.from_numpy(a if a.flags.writeable else a.copy())      # read-only views (npz, memmap) are copied
         if t.dtype not in _SRC_DTYPES:
             t = t.to(torch.float64 if t.dtype.is_floating_point else torch.int64)
         src = t.to(dev)
