@@ -1,6 +1,7 @@
-"""world_size-2 gloo test of the multi-GPU host logic (no CUDA): row-range shards of
-the synthetic table, per-shard partial marginals all-reduced across ranks == the
-single-process marginal; every rank then derives identical bias updates."""
+"""gloo tests (world size 2 and 3, no CUDA) of the multi-GPU host logic: row-range shards of the synthetic
+table and of a real .cool file -- per-shard partial marginals all-reduced across ranks == the single-process
+marginal --, and exchange-free sharded coarsening (shards cut at coarse-bin boundaries, pieces gathered in
+rank order == the reference's coarsened table).  The numpy oracle stands in for the device kernels."""
 import os
 import socket
 import sys
@@ -78,3 +79,106 @@ def test_sharded_marginal_allreduce_equals_global(tmp_path):
                                     n_diags=2, zero_cis=False, vec=w)
     assert int(np.load(out + ".nnz.npy")[0]) == len(b1)
     np.testing.assert_allclose(got, want, rtol=1e-12)
+
+
+def _coarsen_worker(rank, world, port, out, factor):
+    sys.path.insert(0, ROOT)
+    torch.set_num_threads(1)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cooler_b200 import MemCooler
+    from cooler_b200.reduce import gather_pixels_to_rank0, shard_rows_for_coarsening
+    from oracle import coarsen_numpy
+    from tests import _golden
+    t = _golden.gm12878()
+    clr = MemCooler.from_arrays([str(x) for x in t["chromnames"]], t["chromsizes"], t["bins_chrom"], t["bins_start"],
+                                t["bins_end"], t["bin1_id"], t["bin2_id"], t["count"], binsize=2_000_000)
+    lo, hi = shard_rows_for_coarsening(clr, dist.group.WORLD, factor)
+    sel = (t["bin1_id"] >= lo) & (t["bin1_id"] < hi)          # this rank's rows, cut at coarse-bin boundaries
+    px = {k: t[k][sel] for k in ("bin1_id", "bin2_id", "count")}
+    b1, b2, c, _ = coarsen_numpy.coarsen_pixels(px, t["bins_chrom"], t["bins_start"], t["bins_end"], t["chromsizes"],
+                                                factor)
+    g1, g2, gc = gather_pixels_to_rank0([b1, b2, c], dist.group.WORLD)
+    if rank == 0:
+        np.save(out, np.stack([g1, g2, gc.astype(np.int64)], axis=1))
+        np.save(out + ".rows.npy", np.array([lo, hi]))
+    else:
+        assert len(g1) == 0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,factor", [(2, 5), (3, 2)])
+def test_sharded_coarsening_needs_no_exchange(tmp_path, world, factor):
+    """coarsen_cooler(group=...): every rank coarsens the rows `shard_rows_for_coarsening` gives it (the numpy
+    oracle stands in for the device coarsener) and `gather_pixels_to_rank0` concatenates the pieces in rank
+    order -- the result equals the unmodified reference's coarsened table: no coarse row is split, nothing
+    is exchanged."""
+    out = str(tmp_path / "coarse.npy")
+    mp.start_processes(_coarsen_worker, args=(world, _free_port(), out, factor), nprocs=world, join=True,
+                       start_method="spawn")
+    got = np.load(out)
+    sys.path.insert(0, ROOT)
+    from tests import _golden
+    CO = _golden.coarsen_golden()
+    want = np.stack([CO[f"gm/x{factor}/{k}"].astype(np.int64) for k in ("bin1_id", "bin2_id", "count")], axis=1)
+    np.testing.assert_array_equal(got, want)
+    lo, hi = np.load(out + ".rows.npy")
+    assert lo == 0 and 0 < hi < 1561
+
+
+def _file_shard_worker(rank, world, port, out, path):
+    sys.path.insert(0, ROOT)
+    torch.set_num_threads(1)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cooler_b200 import store
+    from cooler_b200.balance import _allreduce
+    from cooler_b200.table import read_cooler_arrays, shard_rows_by_pixels
+    from oracle import ice_numpy
+    clr = store.open_cooler(path)
+    full_offset = np.asarray(clr._load_dset("indexes/bin1_offset"))
+    rows = shard_rows_by_pixels(full_offset, rank, world)            # what balance_cooler(group=...) reads
+    off, bin2, count, chrom_offset = read_cooler_arrays(clr, rows=rows)
+    n = len(off) - 1
+    assert int(off[rows[0]]) == 0 and int(off[-1]) == len(bin2) == int(full_offset[rows[1]] - full_offset[rows[0]])
+    b1 = np.repeat(np.arange(n, dtype=np.int64), np.diff(off))
+    assert len(b1) == 0 or (b1.min() >= rows[0] and b1.max() < rows[1])
+    px = dict(bin1_id=b1, bin2_id=np.asarray(bin2, dtype=np.int64), count=np.asarray(count))
+    chrom_ids = np.repeat(np.arange(len(chrom_offset) - 1, dtype=np.int32), np.diff(chrom_offset))
+    w = np.random.default_rng(1).lognormal(0, 0.2, n)
+    part = ice_numpy._span_marginal(px, chrom_ids, n, 0, len(b1), binarize=False, zero_trans=False, n_diags=2,
+                                    zero_cis=False, vec=w)
+    t = torch.from_numpy(part.copy())
+    _allreduce(t, dist.group.WORLD)
+    sizes = torch.tensor([len(b1)])
+    dist.all_reduce(sizes)
+    if rank == 0:
+        np.save(out, t.numpy())
+        np.save(out + ".nnz.npy", sizes.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_file_row_shards_cover_the_table_once(tmp_path):
+    """balance_cooler(clr, group=...) on a real .cool file: rank g reads pixels[bin1_offset[r_g] :
+    bin1_offset[r_g+1]] through the built-in HDF5 reader; the shards' partial marginals summed over
+    the ranks equal the marginal of the whole file (the oracle stands in for the device sweep)."""
+    path = os.path.join(ROOT, "tests", "golden", "cool", "hg19.GM12878-MboI.matrix.2000kb.cool")
+    out = str(tmp_path / "marg.npy")
+    world = 3
+    mp.start_processes(_file_shard_worker, args=(world, _free_port(), out, path), nprocs=world, join=True,
+                       start_method="spawn")
+    sys.path.insert(0, ROOT)
+    from oracle import ice_numpy
+    from tests import _golden
+    t = _golden.gm12878()
+    chrom_offset, _ = _golden.offsets(t)
+    n = len(t["bins_chrom"])
+    chrom_ids = np.repeat(np.arange(len(chrom_offset) - 1, dtype=np.int32), np.diff(chrom_offset))
+    w = np.random.default_rng(1).lognormal(0, 0.2, n)
+    px = {k: t[k] for k in ("bin1_id", "bin2_id", "count")}
+    want = ice_numpy._span_marginal(px, chrom_ids, n, 0, len(t["count"]), binarize=False, zero_trans=False,
+                                    n_diags=2, zero_cis=False, vec=w)
+    assert int(np.load(out + ".nnz.npy")[0]) == len(t["count"])
+    np.testing.assert_allclose(np.load(out), want, rtol=1e-12)
