@@ -260,3 +260,22 @@ def test_unordered_pixels_matches_oracle_large():
     np.testing.assert_allclose(vals["score"], want["score"], rtol=1e-12)
     with pytest.raises(BadInputError, match="duplicate"):
         UnorderedPixels(n_bins).add(np.array([3, 9, 3]), np.array([7, 9, 7]))
+
+
+def test_sanitizers_agree_with_the_live_reference_on_random_chunks():
+    """900 seeded random cases (fixed and variable bins, every tril_action, unknown chromosomes, anchors at and
+    beyond the chromosome ends) through ingest.sanitize_records / sanitize_pixels and through the unmodified
+    reference's functions: same tables or same errors.  Runs in a subprocess (the reference needs stub modules);
+    skipped where no copy of the reference exists."""
+    import subprocess
+    import sys
+
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference sources not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "_fuzz_sanitize_vs_reference.py"), "300", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=root,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
+    assert res.stdout.strip().startswith("ok:")
