@@ -237,3 +237,24 @@ def test_coarsen_oracle_reproduces_survey_known_answers(factor, n_new, nnz, diag
     if factor == 2:
         assert (int(ns[124 // 2]), int(ne[124 // 2])) == (248_000_000, 249_250_621)      # chr1's last x2 bin
         assert (int(ns[-1]), int(ne[-1])) == (0, 16_571)                                 # chrM stays one bin
+
+
+def test_oracle_is_bit_identical_to_the_live_reference_on_random_tables():
+    """300 balance runs + ~70 coarsenings on seeded random tables (symmetric-upper and square storage, integer
+    and floating-point counts, all three modes, random filter settings, warm starts, blacklists) through the
+    oracle and through the LIVE unmodified reference (oracle/refshim.py): bias bit-identical incl. the NaN
+    pattern, pass counts, warnings, scale / var / converged equal; coarsened tables and bin tables equal.
+    Runs in a subprocess (the reference needs stub modules); skipped where no copy of the reference exists."""
+    import os
+    import subprocess
+    import sys
+
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference sources not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "_fuzz_oracle_vs_reference.py"), "150", "0"],
+                         capture_output=True, text=True, timeout=900, cwd=root,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
+    assert res.stdout.strip().splitlines()[-1].startswith("ok: 300 balance runs")
