@@ -36,20 +36,35 @@ def parse_humanized(s):
     return int(value * mult[unit])
 
 
+_REGION_TOKEN = re.compile(r"\s*(?:(-)|([0-9,]+(?:\.[0-9]*)?(?:[a-z]+)?)|(.+))", re.IGNORECASE)
+
+
 def parse_region_string(s):
+    """'chr5:10,100,000-30,000,000' -> (chrom, start | None, end | None), with the reference's token rules
+    (util.parse_region_string, util.py:78-140): after the colon come a coordinate, a hyphen and optionally a
+    second coordinate; whatever follows them is ignored."""
     parts = s.split(":")
     chrom = parts[0].strip()
     if not len(chrom):
         raise ValueError("Chromosome name cannot be empty")
     if len(parts) < 2:
         return chrom, None, None
-    m = re.fullmatch(r"\s*([0-9,]+(?:\.[0-9]*)?(?:[a-zA-Z]+)?)\s*-\s*([0-9,]+(?:\.[0-9]*)?(?:[a-zA-Z]+)?)?\s*",
-                     parts[1])
-    if m is None:
-        raise ValueError(f'Unexpected token "{parts[1]}"')
-    start = parse_humanized(m.group(1))
-    end = parse_humanized(m.group(2)) if m.group(2) else None
-    if end is not None and end < start:
+    tokens = [("hyphen" if m.group(1) is not None else "coord" if m.group(2) is not None else "other",
+               m.group(m.lastindex)) for m in _REGION_TOKEN.finditer(parts[1])]
+
+    def take(k, kind):
+        if k >= len(tokens):
+            raise ValueError(f"Expected {kind.upper()} token missing")
+        if tokens[k][0] != kind:
+            raise ValueError(f'Unexpected token "{tokens[k][1]}"')
+        return tokens[k][1]
+
+    start = parse_humanized(take(0, "coord"))
+    take(1, "hyphen")
+    if len(tokens) < 3:
+        return chrom, start, None
+    end = parse_humanized(take(2, "coord"))
+    if end < start:
         raise ValueError("End coordinate less than start")
     return chrom, start, end
 

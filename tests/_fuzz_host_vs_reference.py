@@ -1,0 +1,113 @@
+"""Run in a SUBPROCESS by tests/test_host_logic.py: pure host functions of cooler_b200 against their
+counterparts in the LIVE unmodified reference on seeded random inputs -- zoom planners
+(get_multiplier_sequence, preferred_sequence, _greedy_prune_partition), region parsing (util.parse_region,
+region_to_extent), and the general-aggregation oracles (CoolerMerger / CoolerCoarsener with random
+aggregators) that pin oracle.coarsen_numpy.merge_columns."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import coarsen_numpy, refshim  # noqa: E402
+
+from cooler_b200 import api, reduce  # noqa: E402
+
+
+def main(n_cases, seed):
+    cooler = refshim.import_reference()
+    import cooler._reduce as R
+    import cooler.util as U
+    rng = np.random.default_rng(seed)
+    counts = {"multiplier": 0, "preferred": 0, "prune": 0, "region": 0, "merge": 0}
+    nice = [1000, 2000, 5000, 10000, 25000, 50000, 100000, 250000, 500000, 1000000, 2500000, 5000000, 10000000]
+    for case in range(n_cases):
+        # ---- zoom planners -------------------------------------------------------------------------
+        base = int(rng.choice([1, 2, 10, 100, 1000, 5000]))
+        res = sorted({base * int(m) for m in rng.choice([1, 2, 3, 4, 5, 6, 8, 10, 20, 25, 50, 100], int(rng.integers(1, 7)))}
+                     | ({int(x) for x in rng.choice(nice, 2)} if rng.random() < 0.3 else set()))
+        bases = [base] + ([base * 3] if rng.random() < 0.3 else [])
+        try:
+            want = R.get_multiplier_sequence(list(res), list(bases))
+            werr = None
+        except ValueError as e:
+            want, werr = None, str(e)[:30]
+        try:
+            got = reduce.get_multiplier_sequence(list(res), list(bases))
+            gerr = None
+        except ValueError as e:
+            got, gerr = None, str(e)[:30]
+        assert (werr is None) == (gerr is None), (res, bases, werr, gerr)
+        if werr is None:
+            for a, b in zip(got, want):
+                assert list(a) == list(b), (res, bases, got, want)
+        counts["multiplier"] += 1
+        lo, hi = int(rng.integers(1, 5000)), int(rng.integers(1, 20_000_000))
+        for style in ("nice", "binary"):
+            assert list(reduce.preferred_sequence(lo, hi, style)) == list(R.preferred_sequence(lo, hi, style)), (lo, hi, style)
+            counts["preferred"] += 1
+        edges = np.unique(np.r_[0, np.sort(rng.integers(1, 5000, int(rng.integers(1, 60))))])
+        maxlen = int(rng.integers(1, 800))
+        assert list(reduce._prune_edges(edges, maxlen)) == list(R._greedy_prune_partition(edges, maxlen)), (edges, maxlen)
+        counts["prune"] += 1
+        # ---- region parsing ------------------------------------------------------------------------
+        sizes = {"chr1": 1000, "chrX": 123_456_789, "c.2": 5}
+        name = str(rng.choice(list(sizes) + ["nope", ""]))
+        a, b = int(rng.integers(-5, 2000)), int(rng.integers(-5, 200_000_000))
+        forms = [name, f"{name}:{a}-{b}", f"{name}:{a:,}-{b:,}", f"{name}:{a}-", f"{name}:{abs(a)}kb-{abs(b) // 1000}Mb",
+                 f" {name} : {a} - {b} ", f"{name}:{a}", f"{name}:{a}-{b}-{a}", (name, a, b), (name, None, None), (name, a, None)]
+        import pandas as pd
+        cs = pd.Series(sizes)
+        for reg in forms:
+            try:
+                want, werr = U.parse_region(reg, cs), None
+            except Exception as e:                        # noqa: BLE001 - the reference raises several types
+                want, werr = None, type(e).__name__
+            try:
+                got, gerr = api.parse_region(reg, cs), None
+            except Exception as e:                        # noqa: BLE001
+                got, gerr = None, type(e).__name__
+            assert (werr is None) == (gerr is None), (reg, want, got, werr, gerr)
+            if werr is None:
+                assert tuple(got) == tuple(want), (reg, got, want)
+            counts["region"] += 1
+        # ---- general merge oracle vs CoolerMerger with random aggregators --------------------------------
+        if case % 4 == 0:
+            n_chroms = int(rng.integers(1, 4))
+            nb = [int(rng.integers(2, 25)) for _ in range(n_chroms)]
+            bc = np.repeat(np.arange(n_chroms, dtype=np.int32), nb)
+            bs = np.concatenate([np.arange(k) * 10 for k in nb]).astype(np.int64)
+            be = bs + 10
+            n = len(bc)
+            tables, names = [], []
+            for k in range(int(rng.integers(2, 5))):
+                i, j = np.triu_indices(n)
+                sel = rng.random(len(i)) < rng.uniform(0.2, 0.8)
+                m = int(sel.sum())
+                cols = {"count": rng.integers(1, 50, m).astype(np.int32), "score": rng.random(m),
+                        "w": rng.integers(-5, 5, m).astype(np.int64)}
+                nm = f"fuzzmerge{case}_{k}.cool"
+                refshim.register(nm, [f"c{q}" for q in range(n_chroms)], np.array(nb) * 10, bc, bs, be,
+                                 i[sel], j[sel], cols["count"], 10, extra_columns={"score": cols["score"], "w": cols["w"]})
+                tables.append(dict(bin1_id=i[sel].astype(np.int64), bin2_id=j[sel].astype(np.int64), **cols))
+                names.append(nm)
+            ops = ["sum", "min", "max", "first", "last", "mean"]
+            columns = ["count", "score", "w"]
+            agg = {c: str(rng.choice(ops)) for c in columns if rng.random() < 0.7}
+            ref = refshim.ref_merge(names, mergebuf=int(rng.integers(20, 2000)), columns=columns, agg=dict(agg))
+            got = coarsen_numpy.merge_columns(tables, columns, agg)
+            assert sorted(got) == sorted(ref), (got.keys(), ref.keys())
+            for c, v in got.items():
+                w = ref[c]
+                if w.dtype.kind in "iu":
+                    assert v.dtype == w.dtype and np.array_equal(v, w), (case, c, agg)
+                else:
+                    assert v.dtype == w.dtype, (case, c, agg, v.dtype, w.dtype)
+                    np.testing.assert_allclose(v, w, rtol=1e-12, err_msg=f"{case} {c} {agg}")
+            counts["merge"] += 1
+    print("ok:", counts)
+
+
+if __name__ == "__main__":
+    main(int(sys.argv[1]) if len(sys.argv) > 1 else 100, int(sys.argv[2]) if len(sys.argv) > 2 else 0)

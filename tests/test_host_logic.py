@@ -317,3 +317,22 @@ def test_general_merge_host_logic_with_oracle_stand_in(monkeypatch):
     with out.open() as g:
         assert g["pixels/fcount"][:].dtype == np.float32 and g["pixels/count"][:].dtype == np.int32
         np.testing.assert_array_equal(g["pixels/count"][:], G["cols_sum/count"])
+
+
+def test_host_planners_and_region_parser_agree_with_the_live_reference():
+    """get_multiplier_sequence, preferred_sequence, the chunk-edge pruning, util.parse_region (2 200 region
+    strings / tuples, malformed ones included) and the general-merge oracle (random aggregators against the live
+    CoolerMerger) on seeded random inputs.  Runs in a subprocess; skipped where no copy of the reference exists."""
+    import os
+    import subprocess
+    import sys
+
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference sources not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "_fuzz_host_vs_reference.py"), "200", "0"],
+                         capture_output=True, text=True, timeout=900, cwd=root,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
+    assert res.stdout.strip().splitlines()[-1].startswith("ok:")
