@@ -10,7 +10,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import coarsen_numpy, refshim  # noqa: E402
+from oracle import coarsen_numpy, matrix_numpy, refshim  # noqa: E402
 
 from cooler_b200 import api, reduce  # noqa: E402
 
@@ -20,7 +20,12 @@ def main(n_cases, seed):
     import cooler._reduce as R
     import cooler.util as U
     rng = np.random.default_rng(seed)
-    counts = {"multiplier": 0, "preferred": 0, "prune": 0, "region": 0, "merge": 0}
+    counts = {"multiplier": 0, "preferred": 0, "prune": 0, "region": 0, "merge": 0, "matrix": 0, "validate": 0}
+    from cooler.create._ingest import BadInputError as RefBad
+    from cooler.create._ingest import validate_pixels as ref_validate
+
+    from cooler_b200.create import BadInputError as OurBad
+    from cooler_b200.create import _validate_chunk
     nice = [1000, 2000, 5000, 10000, 25000, 50000, 100000, 250000, 500000, 1000000, 2500000, 5000000, 10000000]
     for case in range(n_cases):
         # ---- zoom planners -------------------------------------------------------------------------
@@ -106,6 +111,63 @@ def main(n_cases, seed):
                     assert v.dtype == w.dtype, (case, c, agg, v.dtype, w.dtype)
                     np.testing.assert_allclose(v, w, rtol=1e-12, err_msg=f"{case} {c} {agg}")
             counts["merge"] += 1
+        # ---- chunk validation (create/_ingest.py:401-446): same verdicts -----------------------------------
+        nb_ = int(rng.integers(2, 30))
+        m = int(rng.integers(0, 40))
+        chunk = {"bin1_id": rng.integers(-1 if rng.random() < 0.1 else 0, nb_ + (1 if rng.random() < 0.1 else 0), m),
+                 "bin2_id": rng.integers(0, nb_, m), "count": rng.integers(1, 5, m)}
+        if rng.random() < 0.5:
+            o = np.lexsort((chunk["bin2_id"], chunk["bin1_id"]))
+            chunk = {k: v[o] for k, v in chunk.items()}
+        flags = [bool(rng.integers(0, 2)) for _ in range(4)]
+        import pandas as pd
+        try:
+            w = ref_validate(nb_, *flags)(pd.DataFrame(chunk))
+            werr = None
+        except RefBad as e:
+            w, werr = None, str(e)[:22]
+        try:
+            g = _validate_chunk({k: v.copy() for k, v in chunk.items()}, nb_, *flags)
+            gerr = None
+        except OurBad as e:
+            g, gerr = None, str(e)[:22]
+        assert werr == gerr, (chunk, flags, werr, gerr)
+        if werr is None:
+            for k in chunk:
+                assert np.array_equal(np.asarray(g[k]), w[k].to_numpy()), (k, flags)
+        counts["validate"] += 1
+        # ---- matrix oracle vs the live Cooler.matrix on random windows ----------------------------------------
+        if case % 5 == 0:
+            n = int(rng.integers(5, 60))
+            square = rng.random() < 0.4
+            i, j = (np.indices((n, n)).reshape(2, -1) if square else np.triu_indices(n))
+            sel = rng.random(len(i)) < 0.4
+            b1, b2 = i[sel].astype(np.int64), j[sel].astype(np.int64)
+            cnt = rng.integers(0, 30, len(b1)).astype(np.int32)
+            wts = rng.lognormal(0, 0.3, n)
+            wts[rng.random(n) < 0.15] = np.nan
+            grp = refshim.register(f"fuzzmat{case}.cool", ["a"], [n * 10], np.zeros(n, np.int32), np.arange(n) * 10,
+                                   np.arange(1, n + 1) * 10, b1, b2, cnt, 10, symmetric_upper=not square)
+            grp["bins"]["weight"] = wts.copy()
+            clr = cooler.Cooler(f"fuzzmat{case}.cool")
+            for _ in range(6):
+                i0, i1 = sorted(int(x) for x in rng.integers(0, n + 1, 2))
+                j0, j1 = sorted(int(x) for x in rng.integers(0, n + 1, 2))
+                bal, div = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+                with np.errstate(all="ignore"):
+                    want = clr.matrix(balance=bal, divisive_weights=div)[i0:i1, j0:j1]
+                    got = matrix_numpy.fetch_dense(b1, b2, cnt, i0, i1, j0, j1, symmetric_upper=not square,
+                                                   weights=wts if bal else None, divisive_weights=div)
+                assert got.shape == want.shape and got.dtype == want.dtype, (case, got.dtype, want.dtype)
+                assert np.array_equal(got, want, equal_nan=True), (case, i0, i1, j0, j1, bal, div, square)
+                with np.errstate(all="ignore"):
+                    sp = clr.matrix(balance=bal, sparse=True)[i0:i1, j0:j1]
+                    r, c, d = matrix_numpy.fetch_sparse(b1, b2, cnt, i0, i1, j0, j1, symmetric_upper=not square,
+                                                        weights=wts if bal else None)
+                o = np.lexsort((sp.col, sp.row))
+                assert np.array_equal(sp.row[o], r) and np.array_equal(sp.col[o], c)
+                assert np.array_equal(sp.data[o], d, equal_nan=True), (case, "sparse")
+                counts["matrix"] += 1
     print("ok:", counts)
 
 
