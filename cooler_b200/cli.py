@@ -91,11 +91,14 @@ def _blacklist_bins(clr, path):
     else:
         chrom = chrom.astype(str)
     start, end = bins["start"].values, bins["end"].values
+    from .api import parse_region
+    chromsizes = clr.chromsizes
     out = []
     for _, reg in bad.iterrows():
-        sel = np.flatnonzero((chrom == reg.chrom) & (end > reg.start) & (start < reg.end))
+        c, s, e = parse_region((reg.chrom, reg.start, reg.end), chromsizes)    # util.bedslice: unknown names and
+        sel = np.flatnonzero((chrom == c) & (end > s) & (start < e))            # out-of-bounds regions are errors
         out.append(sel)
-    return np.concatenate(out) if out else np.zeros(0, dtype=np.int64)
+    return np.concatenate(out)                                     # no region at all: ValueError, as in the reference
 
 
 def _dist_group():

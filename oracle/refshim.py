@@ -143,6 +143,12 @@ class MemGroup(dict):
     def close(self):
         pass
 
+    def __enter__(self):                  # `with h5py.File(path, mode) as h5:` (cli/balance.py:181, 195)
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
 
 def register(name, chromnames, chromsizes, bins_chrom, bins_start, bins_end,
              bin1, bin2, count, binsize, symmetric_upper=True, extra_columns=None):
