@@ -11,7 +11,7 @@ import pandas as pd
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from oracle import refshim  # noqa: E402
+from oracle import ingest_numpy, refshim  # noqa: E402
 
 from cooler_b200 import ingest  # noqa: E402
 from cooler_b200.create import _bins_arrays  # noqa: E402
@@ -40,6 +40,7 @@ def main(n_cases, seed):
     refshim.import_reference()
     from cooler.create._ingest import BadInputError as RefError
     from cooler.create._ingest import sanitize_pixels as ref_pixels
+    from cooler.create._ingest import aggregate_records as ref_aggregate
     from cooler.create._ingest import sanitize_records as ref_records
     rng = np.random.default_rng(seed)
     n_err = n_ok = 0
@@ -90,6 +91,33 @@ def main(n_cases, seed):
             for k in ("bin1_id", "bin2_id", "v"):
                 np.testing.assert_array_equal(np.asarray(got[k])[o], w[k].to_numpy(), err_msg=f"{case} {schema} {k}")
             n_ok += 1
+        # the pairs-binning oracle (integer chromosome ids, fixed bins) against sanitize + aggregate_records
+        if not variable and m:
+            ids1 = rng.integers(-1, len(names), m)
+            ids2 = rng.integers(-1, len(names), m)
+            p1 = pos(np.array(names + ["zz"], dtype=object)[ids1])
+            p2 = pos(np.array(names + ["zz"], dtype=object)[ids2])
+            rec = pd.DataFrame({"chrom1": ids1, "pos1": p1, "chrom2": ids2, "pos2": p2})
+            try:
+                w = ref_aggregate(sort=True, count=True)(ref_records(
+                    bins, schema="pairs", decode_chroms=False, is_one_based=one_based, tril_action=tril,
+                    sort=False, validate=True)(rec.copy()))
+                werr = None
+            except RefError:
+                w, werr = None, "bad"
+            try:
+                g = ingest_numpy.bin_pairs(ids1, p1, ids2, p2, lengths, BINSIZE, is_one_based=one_based,
+                                           tril_action=tril)
+                gerr = None
+            except ingest_numpy.BadInputError:
+                g, gerr = None, "bad"
+            assert werr == gerr, (case, "pairs oracle", werr, gerr)
+            if werr is None:
+                for k in ("bin1_id", "bin2_id", "count"):
+                    np.testing.assert_array_equal(g[k], w[k].to_numpy(), err_msg=f"{case} pairs oracle {k}")
+                n_ok += 1
+            else:
+                n_err += 1
         # already-binned pixels
         n_bins = len(bins)
         px = pd.DataFrame({"bin1_id": rng.integers(one_based, n_bins + one_based, m),

@@ -263,9 +263,10 @@ def test_unordered_pixels_matches_oracle_large():
 
 
 def test_sanitizers_agree_with_the_live_reference_on_random_chunks():
-    """900 seeded random cases (fixed and variable bins, every tril_action, unknown chromosomes, anchors at and
+    """~1 050 seeded random cases (fixed and variable bins, every tril_action, unknown chromosomes, anchors at and
     beyond the chromosome ends) through ingest.sanitize_records / sanitize_pixels and through the unmodified
-    reference's functions: same tables or same errors.  Runs in a subprocess (the reference needs stub modules);
+    reference's functions -- and the pairs-binning oracle (oracle/ingest_numpy.py) against the reference's
+    sanitize_records + aggregate_records: same tables or same errors.  Runs in a subprocess (the reference needs stub modules);
     skipped where no copy of the reference exists."""
     import subprocess
     import sys
