@@ -20,7 +20,8 @@ def main(n_cases, seed):
     import cooler._reduce as R
     import cooler.util as U
     rng = np.random.default_rng(seed)
-    counts = {"multiplier": 0, "preferred": 0, "prune": 0, "region": 0, "merge": 0, "matrix": 0, "validate": 0}
+    counts = {"multiplier": 0, "preferred": 0, "prune": 0, "region": 0, "merge": 0, "matrix": 0, "validate": 0,
+              "binmap": 0}
     from cooler.create._ingest import BadInputError as RefBad
     from cooler.create._ingest import validate_pixels as ref_validate
 
@@ -111,6 +112,44 @@ def main(n_cases, seed):
                     assert v.dtype == w.dtype, (case, c, agg, v.dtype, w.dtype)
                     np.testing.assert_allclose(v, w, rtol=1e-12, err_msg=f"{case} {c} {agg}")
             counts["merge"] += 1
+        # ---- coarsened bin table and the closed-form bin map vs the live CoolerCoarsener ------------------------
+        if case % 2 == 0:
+            variable = bool(rng.integers(0, 2))
+            nch = int(rng.integers(1, 5))
+            rows = []
+            for c in range(nch):
+                length = int(rng.integers(3, 500))
+                edges_ = (np.unique(np.r_[0, rng.integers(1, length, int(rng.integers(0, 15))), length]) if variable
+                          else np.unique(np.r_[np.arange(0, length, 9), length]))
+                rows += [(c, int(a), int(b)) for a, b in zip(edges_[:-1], edges_[1:])]
+            bt = np.array(rows, dtype=np.int64)
+            bcx, bsx, bex = bt[:, 0].astype(np.int32), bt[:, 1], bt[:, 2]
+            sizes_ = np.array([bex[bcx == c].max() for c in range(nch)], dtype=np.int64)
+            nb_tot = len(bcx)
+            diag = np.arange(nb_tot, dtype=np.int64)
+            nm = f"fuzzbins{case}.cool"
+            refshim.register(nm, [f"c{q}" for q in range(nch)], sizes_, bcx, bsx, bex, diag, diag,
+                             np.ones(nb_tot, np.int32), None if variable else 9)
+            factor = int(rng.integers(2, 12))
+            ref_px, ref_bins = refshim.ref_coarsen(nm, factor, chunksize=int(rng.integers(3, 200)))
+            gc_, gs_, ge_ = reduce.coarsen_bins(bcx, bsx, bex, sizes_, factor)
+            assert np.array_equal(gc_, ref_bins["chrom"]) and np.array_equal(gs_, ref_bins["start"]) \
+                and np.array_equal(ge_, ref_bins["end"]), (case, factor, variable)
+            off_ = np.searchsorted(bcx, np.arange(nch + 1))
+            bmap, new_off = reduce.coarsen_bin_map(off_, factor)
+            pooled = np.bincount(bmap, minlength=int(new_off[-1]))
+            assert int(new_off[-1]) == len(gc_)
+            # A variable-bin table whose COARSENED bins happen to look uniform (all but the last bin of every
+            # chromosome equally wide) sends the reference down its fixed-bin formula `offset + start // binsize`
+            # (_reduce.py:611-614), which mis-assigns pixels of such a table (ids can even exceed the new bin
+            # table).  cooler_b200 pools `factor` consecutive bins, which is what the new bin table describes;
+            # the comparison is made wherever the reference's formula applies.
+            quirk = variable and coarsen_numpy._binsize_of(gc_, gs_, ge_) is not None
+            if not quirk:
+                assert np.array_equal(np.flatnonzero(pooled), ref_px["bin1_id"]), (case, factor, variable)
+                assert np.array_equal(pooled[pooled > 0], ref_px["count"])
+                assert np.array_equal(ref_px["bin1_id"], ref_px["bin2_id"])
+                counts["binmap"] += 1
         # ---- chunk validation (create/_ingest.py:401-446): same verdicts -----------------------------------
         nb_ = int(rng.integers(2, 30))
         m = int(rng.integers(0, 40))

@@ -321,7 +321,9 @@ def test_general_merge_host_logic_with_oracle_stand_in(monkeypatch):
 
 def test_host_planners_and_region_parser_agree_with_the_live_reference():
     """get_multiplier_sequence, preferred_sequence, the chunk-edge pruning, util.parse_region (2 200 region
-    strings / tuples, malformed ones included), create's chunk validation, the general-merge oracle (random
+    strings / tuples, malformed ones included), the coarsened bin table and the closed-form old -> new bin map
+    (fixed and variable bins, random factors, against the live CoolerCoarsener), create's chunk validation, the
+    general-merge oracle (random
     aggregators against the live CoolerMerger) and the matrix-fetch oracle (240 random dense / sparse windows,
     symmetric-upper and square storage, NaN weights, against the live Cooler.matrix) on seeded random inputs.  Runs in a subprocess; skipped where no copy of the reference exists."""
     import os
