@@ -21,7 +21,7 @@ def main(n_cases, seed):
     import cooler.util as U
     rng = np.random.default_rng(seed)
     counts = {"multiplier": 0, "preferred": 0, "prune": 0, "region": 0, "merge": 0, "matrix": 0, "validate": 0,
-              "binmap": 0}
+              "binmap": 0, "extent": 0}
     from cooler.create._ingest import BadInputError as RefBad
     from cooler.create._ingest import validate_pixels as ref_validate
 
@@ -130,6 +130,17 @@ def main(n_cases, seed):
             nm = f"fuzzbins{case}.cool"
             refshim.register(nm, [f"c{q}" for q in range(nch)], sizes_, bcx, bsx, bex, diag, diag,
                              np.ones(nb_tot, np.int32), None if variable else 9)
+            # region -> bin extent (core/_rangequery.py:11-31) on the same bin table
+            from cooler_b200 import MemCooler
+            mine = MemCooler.from_arrays([f"c{q}" for q in range(nch)], sizes_, bcx, bsx, bex, diag, diag,
+                                         np.ones(nb_tot, np.int32), binsize=None if variable else 9)
+            theirs = cooler.Cooler(nm)
+            for _q in range(6):
+                c = int(rng.integers(0, nch))
+                a_, b_ = sorted(int(x) for x in rng.integers(0, sizes_[c] + 1, 2))
+                reg = (f"c{c}", a_, b_) if rng.random() < 0.5 else (f"c{c}:{a_}-{b_}" if rng.random() < 0.8 else f"c{c}")
+                assert tuple(api.region_to_extent(mine, reg)) == tuple(int(x) for x in theirs.extent(reg)), (case, reg, variable)
+                counts["extent"] += 1
             factor = int(rng.integers(2, 12))
             ref_px, ref_bins = refshim.ref_coarsen(nm, factor, chunksize=int(rng.integers(3, 200)))
             gc_, gs_, ge_ = reduce.coarsen_bins(bcx, bsx, bex, sizes_, factor)
