@@ -128,7 +128,7 @@ def merge_columns(tables, columns, agg=None):
     cooler order, then ``groupby([bin1_id, bin2_id], sort=True).aggregate(agg)``): a stable sort
     keeps the concatenation order inside a group (what 'first' / 'last' and the floating-point
     summation order see); numeric dtypes promote as ``pd.concat`` promotes them; integer sums /
-    min / max / first / last keep the promoted dtype, 'mean' is float64.
+    min / max / first / last keep the promoted dtype, 'mean' is float64 (float32 for a float32 column).
     ``tables``: dicts with bin1_id, bin2_id and the value columns.  Returns a dict of arrays.
     PINNED by tests/golden/merge_agg_golden.npz (unmodified reference, make_merge_golden.py)."""
     ops = {c: "sum" for c in columns}
@@ -148,8 +148,10 @@ def merge_columns(tables, columns, agg=None):
             out[c] = v[:0] if op != "mean" else wide[:0].astype(np.float64)
         elif op == "sum":
             out[c] = np.add.reduceat(wide, starts).astype(v.dtype)
-        elif op == "mean":
+        elif op == "mean":                                   # float64, or float32 for a float32 column (pandas)
             out[c] = np.add.reduceat(wide.astype(np.float64), starts) / (ends - starts)
+            if v.dtype == np.float32:
+                out[c] = out[c].astype(np.float32)
         elif op == "min":
             out[c] = np.minimum.reduceat(v, starts)
         elif op == "max":

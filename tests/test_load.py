@@ -301,3 +301,24 @@ def test_load_cli_agrees_with_the_live_reference_cli_on_random_text_files():
                          env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
     assert res.stdout.strip().splitlines()[-1].startswith("ok: 150 load command lines agree")
+
+
+def test_cload_pairs_fields_agree_with_the_live_reference_cli_on_random_pairs_files():
+    """150 `cooler cload pairs --field ...` command lines on seeded random pairs files (every aggregator, dtypes,
+    a field called count, --zero-based, -N, --input-copy-status, unknown chromosomes, positions outside their
+    chromosome) through cooler_b200/cli.py (numpy accumulator standing in for the device one) and through the live
+    unmodified reference CLI, the writers replaced by recorders: same exit status, same per-chunk pixel tables,
+    columns, dtypes (900 more command lines were compared once by hand).  Field numbers ascend in the order given --
+    see the note on pandas' usecols in DESIGN.md 7.  Subprocess; skipped without the reference."""
+    import subprocess
+    import sys
+
+    from oracle import refshim
+    if not refshim.available():
+        pytest.skip("reference sources not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "_fuzz_cload_fields_vs_reference.py"), "150", "0"],
+                         capture_output=True, text=True, timeout=900, cwd=root,
+                         env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
+    assert res.stdout.strip().splitlines()[-1].startswith("ok: 150 cload pairs --field command lines agree")
