@@ -14,6 +14,7 @@ file, ``coarsen -o out.cool`` and ``zoomify -o out.mcool [--balance]`` write rea
 from __future__ import annotations
 
 import logging
+import os
 import shlex
 import sys
 import warnings
@@ -398,10 +399,13 @@ def pairs(bins, pairs_path, cool_path, metadata, assembly, chrom1, pos1, chrom2,
 
     from . import ingest
     from .create import create_cooler
+    bins_spec = bins
     chromsizes, bins = parse_bins(bins)
     from .create import _binsize, _bins_arrays
     names, ids, start, end, _ = _bins_arrays(bins)
     binsize = _binsize(ids, start, end)
+    if binsize is None and ":" in os.path.splitdrive(bins_spec)[1]:
+        binsize = int(bins_spec.rsplit(":", maxsplit=1)[1])      # every chromosome shorter than one bin
     if len(field):
         return _cload_pairs_with_fields(bins, pairs_path, cool_path, metadata, assembly, chrom1, pos1, chrom2, pos2,
                                         zero_based, comment_char, no_symmetric_upper, input_copy_status, field,

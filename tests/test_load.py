@@ -321,4 +321,4 @@ def test_cload_pairs_fields_agree_with_the_live_reference_cli_on_random_pairs_fi
                          capture_output=True, text=True, timeout=900, cwd=root,
                          env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
-    assert res.stdout.strip().splitlines()[-1].startswith("ok: 150 cload pairs --field command lines agree")
+    assert res.stdout.strip().splitlines()[-1].startswith("ok: 300 cload pairs command lines")
