@@ -21,7 +21,7 @@ def main(n_cases, seed):
     import cooler.util as U
     rng = np.random.default_rng(seed)
     counts = {"multiplier": 0, "preferred": 0, "prune": 0, "region": 0, "merge": 0, "matrix": 0, "validate": 0,
-              "binmap": 0, "extent": 0}
+              "binmap": 0, "extent": 0, "compat": 0}
     from cooler.create._ingest import BadInputError as RefBad
     from cooler.create._ingest import validate_pixels as ref_validate
 
@@ -161,6 +161,51 @@ def main(n_cases, seed):
                 assert np.array_equal(pooled[pooled > 0], ref_px["count"])
                 assert np.array_equal(ref_px["bin1_id"], ref_px["bin2_id"])
                 counts["binmap"] += 1
+        # ---- CoolerMerger's compatibility checks (_reduce.py:150-166): same verdicts -------------------------
+        if case % 3 == 0:
+            from cooler_b200 import MemCooler as _MC
+
+            def make(tag, nchr, bsz, lens, variable):
+                rows_ = []
+                for c in range(nchr):
+                    e_ = (np.unique(np.r_[0, rng.integers(1, lens[c], 3), lens[c]]) if variable
+                          else np.unique(np.r_[np.arange(0, lens[c], bsz), lens[c]]))
+                    rows_ += [(c, int(a), int(b)) for a, b in zip(e_[:-1], e_[1:])]
+                t_ = np.array(rows_, dtype=np.int64)
+                nm_ = f"fuzzcompat{case}_{tag}.cool"
+                nmz = [f"c{q}" for q in range(nchr)]
+                z = np.zeros(1, np.int64)
+                refshim.register(nm_, nmz, np.array(lens[:nchr]), t_[:, 0].astype(np.int32), t_[:, 1], t_[:, 2], z, z,
+                                 np.ones(1, np.int32), None if variable else bsz)
+                mine_ = _MC.from_arrays(nmz, np.array(lens[:nchr]), t_[:, 0].astype(np.int32), t_[:, 1], t_[:, 2], z, z,
+                                        np.ones(1, np.int32), binsize=None if variable else bsz)
+                return cooler.Cooler(nm_), mine_
+            lens_a = [int(rng.integers(20, 90)) for _ in range(3)]
+            spec_a = (int(rng.integers(1, 4)), int(rng.choice([5, 10])), lens_a, rng.random() < 0.25)
+            spec_b = list(spec_a)
+            r = rng.random()
+            if r < 0.2:
+                spec_b[0] = int(rng.integers(1, 4))
+            elif r < 0.4:
+                spec_b[1] = int(rng.choice([5, 10]))
+            elif r < 0.6:
+                spec_b[2] = [x + int(rng.integers(0, 2)) for x in lens_a]
+            elif r < 0.7:
+                spec_b[3] = not spec_a[3]
+            ra, ma = make("a", *spec_a)
+            rb, mb = make("b", *spec_b)
+            try:
+                R.CoolerMerger([ra, rb], mergebuf=100)
+                werr = None
+            except ValueError as e:
+                werr = "ValueError"
+            try:
+                reduce.CoolerMerger([ma, mb], mergebuf=100)
+                gerr = None
+            except ValueError as e:
+                gerr = "ValueError"
+            assert werr == gerr, (case, spec_a, spec_b, werr, gerr)
+            counts["compat"] += 1
         # ---- chunk validation (create/_ingest.py:401-446): same verdicts -----------------------------------
         nb_ = int(rng.integers(2, 30))
         m = int(rng.integers(0, 40))
