@@ -9,7 +9,11 @@ Parity status: PINNED.  The reference's own balance tests are property tests
 (tests/test_oracle.py) against golden vectors produced by running the
 UNMODIFIED reference in the build container through ``oracle/refshim.py``
 (generator: tests/golden/make_golden.py): bias bit-identical, masks, iteration
-counts, scale and var identical, in all three modes.
+counts, scale and var identical, in all three modes (symmetric-upper and square
+storage, integer and floating-point counts), on SURVEY.md 8c's own known answers,
+and -- wherever a copy of the reference exists -- against the LIVE reference on
+seeded random tables and option sets (tests/_fuzz_oracle_vs_reference.py, run in
+a subprocess by the CPU suite: bit-identical).
 
 The chunked map-reduce of the reference (parallel.py:53-320) is restated as a
 loop over pixel spans with per-span ``np.bincount`` partials folded in span
