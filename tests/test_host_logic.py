@@ -381,3 +381,41 @@ def test_zoomify_and_coarsen_cli_arguments_agree_with_the_live_reference_cli():
                          env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
     assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-3000:]
     assert res.stdout.strip().splitlines()[-1].startswith("ok: 600 zoomify / coarsen command lines")
+
+
+def test_prefilter_bias_equals_the_oracle_on_random_marginals():
+    """balance.prefilter_bias (the host half of the bin filters, _balance.py:366-413) against
+    oracle.ice_numpy.initial_bias -- itself bit-identical to the live reference -- on 400 random marginal vectors
+    with random chromosome layouts, filter settings, blacklists and warm starts: the bias vectors are identical bit
+    for bit (NaN-free by construction), and the warm-start array is mutated in place as the reference does."""
+    from types import SimpleNamespace
+
+    from cooler_b200.balance import prefilter_bias
+    from oracle import ice_numpy
+    rng = np.random.default_rng(12)
+    for case in range(400):
+        nb = [int(rng.integers(1, 60)) for _ in range(int(rng.integers(1, 6)))]
+        chrom_offset = np.r_[0, np.cumsum(nb)].astype(np.int64)
+        n = int(chrom_offset[-1])
+        marg_sum = np.floor(rng.lognormal(4, 1.5, n) * (rng.random(n) > 0.1))
+        marg_nnz = np.minimum(marg_sum, np.floor(rng.uniform(0, 30, n)))
+        if rng.random() < 0.1:
+            lo, hi = chrom_offset[0], chrom_offset[1]
+            marg_sum[lo:hi] = 0                               # an empty chromosome: median of nothing
+            marg_nnz[lo:hi] = 0
+        kw = dict(mad_max=int(rng.integers(0, 7)), min_nnz=int(rng.integers(0, 12)),
+                  min_count=int(rng.integers(0, 2)) * int(rng.integers(0, 200)),
+                  blacklist=(sorted({int(x) for x in rng.integers(0, n, 3)}) if rng.random() < 0.3 else None))
+        x0 = None
+        if rng.random() < 0.3:
+            x0 = rng.lognormal(0, 0.3, n)
+            x0[rng.random(n) < 0.1] = np.nan
+        prob = SimpleNamespace(table=SimpleNamespace(n_bins=n, device=None), marg_nnz=marg_nnz.copy(), marg_sum=marg_sum.copy())
+        mine_x0 = None if x0 is None else x0.copy()
+        got = prefilter_bias(prob, chrom_offset, x0=mine_x0, **kw)
+        want = ice_numpy.initial_bias(n, marg_nnz.copy(), marg_sum.copy(), chrom_offset,
+                                      x0=None if x0 is None else x0.copy(), **kw)
+        np.testing.assert_array_equal(got, want, err_msg=str((case, kw)))
+        if x0 is not None:
+            assert got is mine_x0                             # _balance.py:368-370: x0 is the bias vector
+        np.testing.assert_array_equal(prob.marg_sum, marg_sum)   # the stored marginal itself is left alone
