@@ -873,6 +873,11 @@ def balance_table(table: PixelTable, *, cis_only=False, trans_only=False, ignore
             cweights = 1.0 / np.concatenate(
                 [[(1 - (hi - lo) / n_bins)] * (hi - lo)
                  for lo, hi in zip(chrom_offset[:-1], chrom_offset[1:])]) if n_bins else np.zeros(0)
+            raw = getattr(table, "raw", None)
+            if raw is not None and raw.nnz == 0 and not np.all(np.isfinite(cweights)):
+                # one chromosome only (weights 1 / 0) and not a single stored pixel: the reference's marginal is
+                # exactly zero (_balance.py:98-102: "empty"), whereas w_i * (sum over no pixels) would be inf * 0
+                cweights = np.ones(n_bins)
 
     touch = cis_touch_flags(prob, bias, chrom_offset, group) if cis_only else None
     state = IceState(prob, bias, cweights, seg_offset, tol, max_iters)
