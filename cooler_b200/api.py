@@ -162,6 +162,8 @@ class MatrixSelector:
                 k = int(k)
                 if k < 0:
                     k += n
+                if not 0 <= k < n:                       # core/_selectors.py:46-51
+                    raise IndexError("index is out of bounds")
                 return k, k + 1
             lo, hi, step = k.indices(n)
             if step != 1:
