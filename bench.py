@@ -337,7 +337,8 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--parity", default="auto", choices=["auto", "full", "3"],
                     help="oracle passes compared: all to convergence, or the first 3 (auto: full on one GPU)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3,
+                    help="timed end-to-end calls after one warm-up call (at most --steps); their mean is reported")
     ap.add_argument("--host-bin2", default="int32", choices=["int64", "int32"],
                     help="dtype of the pinned host bin2_id column of the e2e leg: int32 = narrowed while "
                          "reading the file, as read_cooler_arrays does (default); int64 = the on-disk dtype")
